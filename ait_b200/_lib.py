@@ -1,0 +1,155 @@
+"""ctypes binding of libaitb200.so (include/aitb200.h).  No fallback: a missing library or a
+non-sm_100 device raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaitb200.so")
+
+AITB_F32, AITB_BF16 = 0, 1
+
+EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU = (
+    1, 2, 4, 8, 16, 32, 64, 128)
+
+
+class View4(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dims", C.c_uint64 * 4), ("strides", C.c_uint64 * 3),
+                ("box", C.c_uint32 * 4)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("M", C.c_int), ("N", C.c_int), ("k_per_tap", C.c_int), ("taps", C.c_int),
+        ("a", View4), ("a_m_dim", C.c_int), ("a_m_step", C.c_int), ("a_group_c", C.c_int),
+        ("tap_dx", C.c_int8 * 9), ("tap_dy", C.c_int8 * 9),
+        ("w", C.c_void_p), ("block_n", C.c_int),
+        ("flags", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
+        ("rows_in", C.c_int), ("rows_out", C.c_int),
+        ("bias", C.c_void_p), ("res", C.c_void_p), ("ldr", C.c_int),
+        ("res_div", C.c_int), ("res_rep", C.c_int),
+        ("pos", C.c_void_p), ("pos_rows", C.c_int),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
+    ]
+
+
+class Linear(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class LNorm(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p)]
+
+
+class MHA(C.Structure):
+    _fields_ = [("w_qkv", C.c_void_p), ("w_sk", C.c_void_p), ("b_sk", C.c_void_p), ("w_fc", C.c_void_p),
+                ("ln", LNorm)]
+
+
+class FFN(C.Structure):
+    _fields_ = [("w1", Linear), ("w2", Linear), ("ln", LNorm)]
+
+
+class Bottleneck(C.Structure):
+    _fields_ = [("conv1", Linear), ("conv2", Linear), ("conv3", Linear), ("down", Linear)]
+
+
+class SKBlock(C.Structure):
+    _fields_ = [("conv1x1", Linear), ("conv3x3", Linear)]
+
+
+class HeadWeights(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("round_tf32", C.c_int),
+        ("enc_emb", Linear), ("dec_emb", Linear), ("dec_trans", Linear),
+        ("enc_pos", C.c_void_p), ("dec_pos", C.c_void_p),
+        ("enc_ln", LNorm), ("dec_ln", LNorm),
+        ("enc_slf", MHA), ("dec_slf", MHA), ("dec_enc", MHA),
+        ("enc_ffn", FFN), ("dec_ffn", FFN),
+        ("sk_props", SKBlock), ("sk_query", SKBlock),
+        ("top", Bottleneck * 3),
+        ("w_bbox", C.c_void_p), ("b_bbox", C.c_void_p),
+        ("w_cls1", C.c_void_p), ("b_cls1", C.c_void_p),
+        ("w_cls2", C.c_void_p), ("b_cls2", C.c_void_p),
+    ]
+
+
+class HeadTaps(C.Structure):
+    _fields_ = [("pooled", C.c_void_p), ("enc_out", C.c_void_p), ("ait_out", C.c_void_p),
+                ("sk_out", C.c_void_p), ("feat", C.c_void_p), ("qfeat", C.c_void_p)]
+
+
+# every symbol include/aitb200.h declares: (restype, argtypes)
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SIGNATURES = {
+    "aitb_last_error": (C.c_char_p, []),
+    "aitb_version": (_i, []),
+    "aitb_check_device": (_i, []),
+    "aitb_launch_count": (C.c_longlong, [_i]),
+    "aitb_nms_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aitb_nms_batched": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "aitb_topk_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aitb_topk_desc": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "aitb_roi_align_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp]),
+    "aitb_roi_align_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp]),
+    "aitb_transpose_cs": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "aitb_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
+    "aitb_attn_core": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "aitb_pool_heads": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_head_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aitb_head_forward": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp,
+                               C.POINTER(HeadTaps), _vp, _sz, _vp]),
+    "aitb_ait_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aitb_ait_forward": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+_device_checked = False
+
+
+def load(check_device=True):
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib, _device_checked
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libaitb200.so is not built (%s). Run `python -m ait_b200.build`; there is no "
+                "CPU/PyTorch fallback for this path." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if check_device and not _device_checked:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("ait_b200 needs a CUDA device (sm_100a); none is visible")
+        if _lib.aitb_check_device() != 0:
+            raise RuntimeError(_lib.aitb_last_error().decode())
+        _device_checked = True
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("libaitb200: " + _lib.aitb_last_error().decode())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def dtype_enum(torch_dtype):
+    import torch
+    if torch_dtype == torch.float32:
+        return AITB_F32
+    if torch_dtype == torch.bfloat16:
+        return AITB_BF16
+    raise RuntimeError("ait_b200 supports float32 (tf32 tensor cores) and bfloat16 only, got %s "
+                       "(the reference's fp64 dispatch is not provided)" % torch_dtype)

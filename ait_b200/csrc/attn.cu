@@ -1,0 +1,307 @@
+// Attention core of the AIT MultiHeadAttention with selective heads, one CTA per
+// proposal-query pair (T = 64 tokens, 8 heads x 64 channels).
+//
+// Reference: ScaledDotProductAttention.forward (lib/model/system/Modules.py:16-29),
+// SHBlock.forward (lib/model/system/SubLayers.py:22-39) and the head-sum in
+// MultiHeadAttention.forward (SubLayers.py:89-97).  Masks are generated from indices
+// (Models.py:258-263 builds them as uint8 tensors on the host every forward).
+//
+//   O_h  = softmax(mask(Q_h K_h^T / 8)) V_h                      h = 0..7
+//   s    = mean_T( sum_h O_h )                                   [64]
+//   gate = softmax over h of view(W_sk s + b_sk, [8, 64])        [8, 64]
+//   out  = sum_h O_h * gate_h                                    [64, 64]
+//
+// The gate needs a reduction over ALL heads and rows before any head can be weighted, which
+// normally forces the 8 O_h tiles (128 KB fp32) to be kept.  We avoid that with two identities:
+//   sum_t O_h[t,:] = colsum(P_h) V_h            (so s needs only the 64 column sums of each P_h)
+//   sum_h O_h * gate_h = sum_h P_h (V_h * gate_h)   (the gate scales V's columns; heads
+//                                                    accumulate into ONE 64x64 register tile)
+// Pass A computes P_h, its column sums and s; pass B recomputes P_h (cheap: 64x64x64) and
+// accumulates the gated PV product.  Shared memory drops to ~72 KB -> 3 CTAs per SM.
+// The 64x64x64 products run on mma.sync m16n8k8 TF32 (fp32 accumulate); this block is ~1% of the
+// head's FLOPs, the tcgen05 kernels carry the projections around it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+static constexpr int kT = 64;    // tokens
+static constexpr int kD = 64;    // head dim
+static constexpr int kH = 8;     // heads
+static constexpr int kQS = 68;   // smem row stride (floats) of Q, K, P tiles (conflict-free frags)
+static constexpr int kVS = 72;   // smem row stride of V
+static constexpr int kAttnThreads = 128;
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// 64x64 tile global -> smem (tf32-rounded), optional per-column scale (the head gate)
+template <typename T>
+__device__ __forceinline__ void load_tile(const T* __restrict__ g, int ld, float* __restrict__ s, int stride,
+                                          const float* __restrict__ colscale) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = threadIdx.x + kAttnThreads * i;
+    const int r = f >> 4, c4 = (f & 15) * 4;
+    float4 v = load4(g + (size_t)r * ld + c4);
+    if (colscale) {
+      v.x *= colscale[c4 + 0]; v.y *= colscale[c4 + 1]; v.z *= colscale[c4 + 2]; v.w *= colscale[c4 + 3];
+    }
+    float* d = s + r * stride + c4;
+    d[0] = to_tf32(v.x); d[1] = to_tf32(v.y); d[2] = to_tf32(v.z); d[3] = to_tf32(v.w);
+  }
+}
+
+// S = Q K^T / 8 for this warp's 16 rows, mask, softmax in registers.  p[nt][0..3] follows the mma
+// C layout: rows (g, g+8), cols nt*8 + 2t, +1.
+__device__ __forceinline__ void scores_softmax(const float* __restrict__ Qs, const float* __restrict__ Ks, int row0,
+                                               int mask_mode, int n_keys, float (&p)[8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < kD; k0 += 8) {
+    uint32_t a[4];
+    a[0] = __float_as_uint(Qs[(row0 + g) * kQS + k0 + t]);
+    a[1] = __float_as_uint(Qs[(row0 + g + 8) * kQS + k0 + t]);
+    a[2] = __float_as_uint(Qs[(row0 + g) * kQS + k0 + t + 4]);
+    a[3] = __float_as_uint(Qs[(row0 + g + 8) * kQS + k0 + t + 4]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t b[2];
+      b[0] = __float_as_uint(Ks[(nt * 8 + g) * kQS + k0 + t]);
+      b[1] = __float_as_uint(Ks[(nt * 8 + g) * kQS + k0 + t + 4]);
+      mma_tf32(p[nt], a, b);
+    }
+  }
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + 2 * t + (e & 1);
+      const int row = (e < 2) ? r_lo : r_hi;
+      const bool masked = mask_mode == 0 ? (col >= n_keys) : (col > row);
+      const float v = masked ? -1e9f : p[nt][e] * 0.125f;  // masked_fill(mask == 0, -1e9)
+      p[nt][e] = v;
+      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
+    }
+  }
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] = expf(p[nt][0] - m_lo); p[nt][1] = expf(p[nt][1] - m_lo);
+    p[nt][2] = expf(p[nt][2] - m_hi); p[nt][3] = expf(p[nt][3] - m_hi);
+    s_lo += p[nt][0] + p[nt][1];
+    s_hi += p[nt][2] + p[nt][3];
+  }
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+  const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] *= i_lo; p[nt][1] *= i_lo; p[nt][2] *= i_hi; p[nt][3] *= i_hi;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
+                 int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
+                 T* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                    // [64][68]
+  float* Ks = Qs + kT * kQS;         // [64][68]
+  float* Vs = Ks + kT * kQS;         // [64][72]
+  float* Ps = Vs + kT * kVS;         // [4 warps][16][68]
+  float* colsum = Ps + 4 * 16 * kQS; // [4][64]
+  float* svec = colsum + 4 * kD;     // [2][64] partial s, then s
+  float* gate = svec + 2 * kD;       // [8][64]
+
+  const int grp = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16;
+  const T* qg = q + (size_t)(grp / q_rep) * kT * ldq;
+  const T* kg = k + (size_t)grp * kT * ldkv;
+  const T* vg = v + (size_t)grp * kT * ldkv;
+
+  // ---------------- pass A: s = mean_T(sum_h O_h) via column sums of P_h
+  float s_part = 0.f;  // thread (half = tid >> 6, c = tid & 63)
+  for (int h = 0; h < kH; ++h) {
+    __syncthreads();
+    load_tile(qg + h * kD, ldq, Qs, kQS, nullptr);
+    load_tile(kg + h * kD, ldkv, Ks, kQS, nullptr);
+    load_tile(vg + h * kD, ldkv, Vs, kVS, nullptr);
+    __syncthreads();
+    float p[8][4];
+    scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float c0 = p[nt][0] + p[nt][2], c1 = p[nt][1] + p[nt][3];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      }
+      if (g == 0) {
+        colsum[warp * kD + nt * 8 + 2 * t] = c0;
+        colsum[warp * kD + nt * 8 + 2 * t + 1] = c1;
+      }
+    }
+    __syncthreads();
+    {
+      const int half = threadIdx.x >> 6, c = threadIdx.x & 63;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int j = half * 32; j < half * 32 + 32; ++j) {
+        const float cs = colsum[j] + colsum[kD + j] + colsum[2 * kD + j] + colsum[3 * kD + j];
+        acc += cs * Vs[j * kVS + c];
+      }
+      s_part += acc;
+    }
+  }
+  svec[(threadIdx.x >> 6) * kD + (threadIdx.x & 63)] = s_part;
+  __syncthreads();
+  if (threadIdx.x < kD) svec[threadIdx.x] = (svec[threadIdx.x] + svec[kD + threadIdx.x]) * (1.f / kT);
+  __syncthreads();
+  // ---------------- gate = softmax_h(W_sk s + b_sk): thread -> 4 of the 512 outputs
+  for (int o = threadIdx.x; o < kH * kD; o += kAttnThreads) {
+    const float* wr = w_sk + (size_t)o * kD;
+    float acc = __ldg(b_sk + o);
+#pragma unroll 8
+    for (int c = 0; c < kD; c += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
+      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
+    }
+    gate[o] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kD) {
+    const int c = threadIdx.x;
+    float m = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) m = fmaxf(m, gate[h * kD + c]);
+    float e[kH], sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) { e[h] = expf(gate[h * kD + c] - m); sum += e[h]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) gate[h * kD + c] = e[h] * inv;
+  }
+
+  // ---------------- pass B: out = sum_h P_h (V_h * gate_h)
+  float o_acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
+  float* Pw = Ps + warp * 16 * kQS;
+  for (int h = 0; h < kH; ++h) {
+    __syncthreads();
+    load_tile(qg + h * kD, ldq, Qs, kQS, nullptr);
+    load_tile(kg + h * kD, ldkv, Ks, kQS, nullptr);
+    load_tile(vg + h * kD, ldkv, Vs, kVS, gate + h * kD);
+    __syncthreads();
+    float p[8][4];
+    scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      Pw[g * kQS + nt * 8 + 2 * t] = to_tf32(p[nt][0]);
+      Pw[g * kQS + nt * 8 + 2 * t + 1] = to_tf32(p[nt][1]);
+      Pw[(g + 8) * kQS + nt * 8 + 2 * t] = to_tf32(p[nt][2]);
+      Pw[(g + 8) * kQS + nt * 8 + 2 * t + 1] = to_tf32(p[nt][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k0 = 0; k0 < kT; k0 += 8) {
+      uint32_t a[4];
+      a[0] = __float_as_uint(Pw[g * kQS + k0 + t]);
+      a[1] = __float_as_uint(Pw[(g + 8) * kQS + k0 + t]);
+      a[2] = __float_as_uint(Pw[g * kQS + k0 + t + 4]);
+      a[3] = __float_as_uint(Pw[(g + 8) * kQS + k0 + t + 4]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t b[2];
+        b[0] = __float_as_uint(Vs[(k0 + t) * kVS + nt * 8 + g]);
+        b[1] = __float_as_uint(Vs[(k0 + t + 4) * kVS + nt * 8 + g]);
+        mma_tf32(o_acc[nt], a, b);
+      }
+    }
+    __syncwarp();
+  }
+  T* og = out + (size_t)grp * kT * kD;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    Act<T>::st(og + (size_t)(row0 + g) * kD + c, o_acc[nt][0]);
+    Act<T>::st(og + (size_t)(row0 + g) * kD + c + 1, o_acc[nt][1]);
+    Act<T>::st(og + (size_t)(row0 + g + 8) * kD + c, o_acc[nt][2]);
+    Act<T>::st(og + (size_t)(row0 + g + 8) * kD + c + 1, o_acc[nt][3]);
+  }
+}
+
+static constexpr size_t kAttnSmem =
+    (size_t)(2 * kT * kQS + kT * kVS + 4 * 16 * kQS + 4 * kD + 2 * kD + kH * kD) * sizeof(float);
+
+int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
+                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream) {
+  AITB_REQUIRE(G > 0, "aitb_attn_core: G must be positive");
+  AITB_REQUIRE(q && k && v && w_sk && b_sk && out, "aitb_attn_core: null pointer");
+  AITB_REQUIRE(q_rep >= 1, "aitb_attn_core: q_rep must be >= 1");
+  AITB_REQUIRE(mask_mode == 0 || mask_mode == 1, "aitb_attn_core: mask_mode must be 0 (key padding) or 1 (causal)");
+  AITB_REQUIRE(n_keys >= 1 && n_keys <= kT, "aitb_attn_core: n_keys=%d out of range", n_keys);
+  AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "aitb_attn_core: leading dimensions must be multiples of 4");
+  static bool attr[2] = {false, false};
+  if (dtype == AITB_F32) {
+    auto kern = attn_core_kernel<float>;
+    if (!attr[0]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem);
+      AITB_REQUIRE(e == cudaSuccess, "aitb_attn_core: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      attr[0] = true;
+    }
+    kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const float*)q, ldq, q_rep, (const float*)k, (const float*)v, ldkv,
+                                                 w_sk, b_sk, mask_mode, n_keys, (float*)out);
+  } else if (dtype == AITB_BF16) {
+    auto kern = attn_core_kernel<__nv_bfloat16>;
+    if (!attr[1]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem);
+      AITB_REQUIRE(e == cudaSuccess, "aitb_attn_core: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      attr[1] = true;
+    }
+    kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k,
+                                                 (const __nv_bfloat16*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
+                                                 (__nv_bfloat16*)out);
+  } else {
+    set_error("aitb_attn_core: bad dtype %d", dtype);
+    return 1;
+  }
+  return check_launch("attn_core_kernel");
+}
+
+}  // namespace aitb

@@ -1,0 +1,630 @@
+// C ABI of libaitb200 (see include/aitb200.h) and the native head engine: the per-step launch
+// sequence ROIAlign -> AIT -> SKNet -> RCNN_top -> heads for a batch of (image, query) units.
+// Host code only orchestrates: every FLOP/byte of the path runs in the kernels of this library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+// ---- implemented in the other translation units
+int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream);
+size_t nms_workspace_bytes(int B, int n_total, int n);
+int nms_run(const float* boxes, const int64_t* order, int B, int n_total, int n, float thr, int max_out, int mode,
+            int64_t* keep_out, int32_t* n_keep, float* rois_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t topk_workspace_bytes(int B, int n_total, int n);
+int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, void* ws, size_t ws_bytes,
+             cudaStream_t stream);
+int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream);
+int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream);
+int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
+                      int pw, int sampling_ratio, float* gfeat, cudaStream_t stream);
+int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
+                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream);
+int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat, const float* w_bbox,
+                   const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
+                   float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// error string + launch counter (thread-local)
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small fused helper: encoder rows t >= n_valid of every pair are zero-padded AFTER enc_emb
+// (system/Models.py:268-270), so their encoder input is LayerNorm(pos_table[t]) -- independent of
+// the proposal.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __restrict__ pos,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int round_tf) {
+  const int n_pad = 64 - n_valid;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pairs * n_pad) return;
+  const int pair = row / n_pad, t = n_valid + row % n_pad;
+  const float* pr = pos + (size_t)t * 512;
+  float v[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = pr[lane + 32 * i];
+    sum += v[i];
+  }
+  const float mean = warp_sum(sum) * (1.f / 512.f);
+  float ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ssq += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum(ssq) * (1.f / 512.f) + eps);
+  T* xr = x + ((size_t)pair * 64 + t) * 512;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (sizeof(T) == 4 && round_tf) {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(o));
+      o = __uint_as_float(r);
+    }
+    Act<T>::st(xr + c, o);
+  }
+}
+
+static int ln_pad_rows(void* x, int dtype, int n_pairs, int n_valid, const float* pos, const aitb_lnorm& ln,
+                       int round_tf, cudaStream_t st) {
+  const int rows = n_pairs * (64 - n_valid);
+  if (rows <= 0) return 0;
+  const int grid = (rows + 7) / 8;
+  if (dtype == AITB_F32)
+    ln_pad_rows_kernel<float><<<grid, 256, 0, st>>>((float*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta, 1e-6f, round_tf);
+  else
+    ln_pad_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta,
+                                                            1e-6f, round_tf);
+  return check_launch("ln_pad_rows_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM descriptor builders
+// ---------------------------------------------------------------------------------------------
+static inline int esize(int dtype) { return dtype == AITB_F32 ? 4 : 2; }
+
+static aitb_gemm_desc gemm_base(int dtype, int M, int N, int K, const void* W, int block_n, void* out, int ldo,
+                                int round_tf) {
+  aitb_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.dtype = dtype;
+  d.M = M;
+  d.N = N;
+  d.k_per_tap = K;
+  d.taps = 1;
+  d.w = W;
+  d.block_n = block_n;
+  d.out = out;
+  d.ldo = ldo;
+  d.rows_in = d.rows_out = M;
+  d.res_div = d.res_rep = 1;
+  d.pos_rows = 1;
+  d.eps = 1e-6f;
+  d.round_tf32 = round_tf;
+  return d;
+}
+
+// A = row-major [M, K] with leading dimension lda (elements)
+static void view_plain(aitb_gemm_desc& d, const void* A, int lda) {
+  const int eb = esize(d.dtype);
+  d.a.ptr = A;
+  d.a.dims[0] = (uint64_t)d.k_per_tap * d.taps;
+  if (d.a_group_c) d.a.dims[0] = (uint64_t)lda;  // grouped: the view spans all input channels
+  d.a.dims[1] = (uint64_t)d.M;
+  d.a.dims[2] = d.a.dims[3] = 1;
+  d.a.strides[0] = (uint64_t)lda * eb;
+  d.a.strides[1] = d.a.strides[2] = (uint64_t)lda * eb * d.M;
+  d.a.box[0] = 128 / eb;
+  d.a.box[1] = 128;
+  d.a.box[2] = d.a.box[3] = 1;
+  d.a_m_dim = 1;
+  d.a_m_step = 128;
+}
+
+// A = channels-last map [G, S, S, C] seen as an s x s grid sampled with `stride`; one m-tile = 128 / (s*s) maps
+static void view_map(aitb_gemm_desc& d, const void* A, int C, int S, int s, int stride, int G) {
+  const int eb = esize(d.dtype);
+  d.a.ptr = A;
+  d.a.dims[0] = (uint64_t)C;
+  d.a.dims[1] = d.a.dims[2] = (uint64_t)s;
+  d.a.dims[3] = (uint64_t)G;
+  d.a.strides[0] = (uint64_t)stride * C * eb;
+  d.a.strides[1] = (uint64_t)stride * S * C * eb;
+  d.a.strides[2] = (uint64_t)S * S * C * eb;
+  d.a.box[0] = 128 / eb;
+  d.a.box[1] = d.a.box[2] = (uint32_t)s;
+  d.a.box[3] = (uint32_t)(128 / (s * s));
+  d.a_m_dim = 3;
+  d.a_m_step = 128 / (s * s);
+}
+
+static void taps3x3(aitb_gemm_desc& d) {
+  d.taps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      d.tap_dx[ky * 3 + kx] = (int8_t)(kx - 1);
+      d.tap_dy[ky * 3 + kx] = (int8_t)(ky - 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace bump allocator
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 1023) & ~(size_t)1023;
+    return p;
+  }
+};
+
+struct HeadBufs {
+  void *featT, *pooled, *qtok, *X1, *QKV, *AO, *X2, *Hh, *ENC;
+  void *T0, *QKVd, *AOd, *T1, *Qc;
+  void *KVc, *D1, *DEC, *AIT, *SK;
+  void *c1, *c2, *ds, *y0, *y1;
+  void *SKq, *qc1, *qc2, *qds, *qy0, *qy1;
+  float *feat, *qfeat;
+  void* in_tok;  // ait_forward only: token-major copy of x_props
+};
+
+static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool with_roi, bool with_top) {
+  const size_t eb = esize(dtype);
+  const size_t bp = (size_t)B * P, R = bp * 64, RQ = (size_t)B * 64;
+  memset(&hb, 0, sizeof(hb));
+  if (with_roi) hb.featT = b.take((size_t)B * HW * 1024 * eb);
+  hb.pooled = b.take(bp * 49 * 1024 * eb);
+  hb.qtok = b.take(RQ * 1024 * eb);
+  hb.X1 = b.take(R * 512 * eb);
+  hb.QKV = b.take(R * 1536 * eb);
+  hb.AO = b.take(R * 64 * eb);
+  hb.X2 = b.take(R * 512 * eb);
+  hb.Hh = b.take(R * 2048 * eb);
+  hb.ENC = b.take(R * 512 * eb);
+  hb.T0 = b.take(RQ * 512 * eb);
+  hb.QKVd = b.take(RQ * 1536 * eb);
+  hb.AOd = b.take(RQ * 64 * eb);
+  hb.T1 = b.take(RQ * 512 * eb);
+  hb.Qc = b.take(RQ * 512 * eb);
+  hb.KVc = b.take(R * 1024 * eb);
+  hb.D1 = b.take(R * 512 * eb);
+  hb.DEC = b.take(R * 512 * eb);
+  hb.AIT = b.take(R * 1024 * eb);
+  if (with_top) {
+    const size_t R16 = bp * 16, RQ16 = (size_t)B * 16;
+    hb.SK = b.take(R * 1024 * eb);
+    hb.c1 = b.take(R16 * 512 * eb);
+    hb.c2 = b.take(R16 * 512 * eb);
+    hb.ds = b.take(R16 * 2048 * eb);
+    hb.y0 = b.take(R16 * 2048 * eb);
+    hb.y1 = b.take(R16 * 2048 * eb);
+    hb.SKq = b.take(RQ * 1024 * eb);
+    hb.qc1 = b.take(RQ16 * 512 * eb);
+    hb.qc2 = b.take(RQ16 * 512 * eb);
+    hb.qds = b.take(RQ16 * 2048 * eb);
+    hb.qy0 = b.take(RQ16 * 2048 * eb);
+    hb.qy1 = b.take(RQ16 * 2048 * eb);
+    hb.feat = (float*)b.take(bp * 2048 * 4);
+    hb.qfeat = (float*)b.take((size_t)B * 2048 * 4);
+  }
+}
+
+#define RUN(expr)        \
+  do {                   \
+    if ((expr)) return 1; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// AIT: Transformer.forward (system/Models.py:231-280) on token-major inputs
+//   pooled [bp*49, 1024], qtok [B*64, 1024]  ->  hb.AIT [bp*64, 1024]
+// ---------------------------------------------------------------------------------------------
+static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* x_q_in, int q_groups, int q_rep,
+                     const void* qbuf, int ldq, const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode,
+                     int n_keys, void* ao, const void* res, int res_rep, void* out, cudaStream_t st) {
+  (void)x_q_in; (void)q_groups;
+  const int dt = w->dtype;
+  RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st));
+  // fc (64 -> 512, no bias) + residual + LayerNorm   (SubLayers.py:97-100)
+  aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 512, out, 512, w->round_tf32);
+  view_plain(d, ao, 64);
+  d.flags = AITB_EPI_RES | AITB_EPI_LN;
+  d.res = res;
+  d.ldr = 512;
+  d.res_div = 64;
+  d.res_rep = res_rep;
+  d.gamma = m.ln.gamma;
+  d.beta = m.ln.beta;
+  return gemm_run(&d, st);
+}
+
+static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* x, int M, void* hidden, void* out,
+                     cudaStream_t st) {
+  const int dt = w->dtype;
+  aitb_gemm_desc d1 = gemm_base(dt, M, 2048, 512, f.w1.w, 256, hidden, 2048, w->round_tf32);
+  view_plain(d1, x, 512);
+  d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
+  d1.bias = f.w1.bias;
+  RUN(gemm_run(&d1, st));
+  aitb_gemm_desc d2 = gemm_base(dt, M, 512, 2048, f.w2.w, 512, out, 512, w->round_tf32);
+  view_plain(d2, hidden, 2048);
+  d2.flags = AITB_EPI_BIAS | AITB_EPI_RES | AITB_EPI_LN;
+  d2.bias = f.w2.bias;
+  d2.res = x;
+  d2.ldr = 512;
+  d2.gamma = f.ln.gamma;
+  d2.beta = f.ln.beta;
+  return gemm_run(&d2, st);
+}
+
+static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st) {
+  const int dt = w->dtype, eb = esize(dt), rt = w->round_tf32;
+  const int bp = B * P, R = bp * 64, RQ = B * 64;
+  // ---- encoder input: enc_emb (1x1 conv 1024->512 + bias) on the 49 real rows, + pos, LayerNorm
+  {
+    aitb_gemm_desc d = gemm_base(dt, bp * 49, 512, 1024, w->enc_emb.w, 512, hb.X1, 512, rt);
+    view_plain(d, hb.pooled, 1024);
+    d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
+    d.bias = w->enc_emb.bias;
+    d.pos = w->enc_pos;
+    d.pos_rows = 64;
+    d.rows_in = 49;
+    d.rows_out = 64;
+    d.gamma = w->enc_ln.gamma;
+    d.beta = w->enc_ln.beta;
+    RUN(gemm_run(&d, st));
+    RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st));
+  }
+  // ---- encoder self-attention
+  {
+    aitb_gemm_desc d = gemm_base(dt, R, 1536, 512, w->enc_slf.w_qkv, 256, hb.QKV, 1536, rt);
+    view_plain(d, hb.X1, 512);
+    RUN(gemm_run(&d, st));
+    const uint8_t* qkv = (const uint8_t*)hb.QKV;
+    RUN(mha_block(w, w->enc_slf, nullptr, 0, 1, qkv, 1536, qkv + 512 * eb, qkv + 1024 * eb, 1536, bp, 0, 49, hb.AO,
+                  hb.X1, 1, hb.X2, st));
+  }
+  RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st));
+  if (enc_tap) {
+    cudaError_t e = cudaMemcpyAsync(enc_tap, hb.ENC, (size_t)R * 512 * eb, cudaMemcpyDeviceToDevice, st);
+    AITB_REQUIRE(e == cudaSuccess, "enc tap copy failed: %s", cudaGetErrorString(e));
+  }
+  // ---- decoder, proposal-independent part (once per unit): dec_emb + pos + LN, causal self-attention,
+  //      and the cross-attention query projection
+  {
+    aitb_gemm_desc d = gemm_base(dt, RQ, 512, 1024, w->dec_emb.w, 512, hb.T0, 512, rt);
+    view_plain(d, hb.qtok, 1024);
+    d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
+    d.bias = w->dec_emb.bias;
+    d.pos = w->dec_pos;
+    d.pos_rows = 64;
+    d.gamma = w->dec_ln.gamma;
+    d.beta = w->dec_ln.beta;
+    RUN(gemm_run(&d, st));
+    aitb_gemm_desc dq = gemm_base(dt, RQ, 1536, 512, w->dec_slf.w_qkv, 256, hb.QKVd, 1536, rt);
+    view_plain(dq, hb.T0, 512);
+    RUN(gemm_run(&dq, st));
+    const uint8_t* qkv = (const uint8_t*)hb.QKVd;
+    RUN(mha_block(w, w->dec_slf, nullptr, 0, 1, qkv, 1536, qkv + 512 * eb, qkv + 1024 * eb, 1536, B, 1, 64, hb.AOd,
+                  hb.T0, 1, hb.T1, st));
+    aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
+    view_plain(dc, hb.T1, 512);
+    RUN(gemm_run(&dc, st));
+  }
+  // ---- cross attention: K, V from the encoder output of each pair, Q shared by the unit's P pairs
+  {
+    const uint8_t* wkv = (const uint8_t*)w->dec_enc.w_qkv + (size_t)512 * 512 * eb;
+    aitb_gemm_desc d = gemm_base(dt, R, 1024, 512, wkv, 256, hb.KVc, 1024, rt);
+    view_plain(d, hb.ENC, 512);
+    RUN(gemm_run(&d, st));
+    const uint8_t* kv = (const uint8_t*)hb.KVc;
+    RUN(mha_block(w, w->dec_enc, nullptr, 0, P, hb.Qc, 512, kv, kv + 512 * eb, 1024, bp, 0, 49, hb.AO, hb.T1, P,
+                  hb.D1, st));
+  }
+  RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh, hb.DEC, st));
+  // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
+  {
+    aitb_gemm_desc d = gemm_base(dt, R, 1024, 512, w->dec_trans.w, 256, hb.AIT, 1024, rt);
+    view_plain(d, hb.DEC, 512);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->dec_trans.bias;
+    RUN(gemm_run(&d, st));
+  }
+  return 0;
+}
+
+// SKBlock (bug-compatible: relu(conv1x1_g8(x))^2 + relu(conv3x3_g8(x))^2, blocks_coatt_transformer_sk.py:973-984)
+static int sk_block(const aitb_head_weights* w, const aitb_skblock& sk, const void* x, int G, void* out,
+                    cudaStream_t st) {
+  const int dt = w->dtype;
+  aitb_gemm_desc d1 = gemm_base(dt, G * 64, 1024, 128, sk.conv1x1.w, 128, out, 1024, w->round_tf32);
+  d1.a_group_c = 128;
+  view_plain(d1, x, 1024);
+  d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_SQUARE;
+  d1.bias = sk.conv1x1.bias;
+  RUN(gemm_run(&d1, st));
+  aitb_gemm_desc d3 = gemm_base(dt, G * 64, 1024, 128, sk.conv3x3.w, 128, out, 1024, w->round_tf32);
+  d3.a_group_c = 128;
+  view_map(d3, x, 1024, 8, 8, 1, G);
+  taps3x3(d3);
+  d3.flags = AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_SQUARE | AITB_EPI_ACCUM;
+  d3.bias = sk.conv3x3.bias;
+  return gemm_run(&d3, st);
+}
+
+// ResNet-50 layer4 (3 bottlenecks, stride 2 on the first 1x1, frozen BN folded) on [G, 8, 8, 1024] -> [G, 16, 2048]
+static int layer4(const aitb_head_weights* w, const void* x, int G, void* c1, void* c2, void* ds, void* y0, void* y1,
+                  void** result, cudaStream_t st) {
+  const int dt = w->dtype, rt = w->round_tf32;
+  const int M = G * 16;
+  const void* in = x;
+  void* outs[2] = {y0, y1};
+  for (int blk = 0; blk < 3; ++blk) {
+    const aitb_bottleneck& bn = w->top[blk];
+    const int cin = blk == 0 ? 1024 : 2048;
+    void* out = outs[blk & 1];
+    aitb_gemm_desc d1 = gemm_base(dt, M, 512, cin, bn.conv1.w, 256, c1, 512, rt);
+    if (blk == 0) view_map(d1, in, 1024, 8, 4, 2, G); else view_plain(d1, in, 2048);
+    d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
+    d1.bias = bn.conv1.bias;
+    RUN(gemm_run(&d1, st));
+    aitb_gemm_desc d2 = gemm_base(dt, M, 512, 512, bn.conv2.w, 256, c2, 512, rt);
+    view_map(d2, c1, 512, 4, 4, 1, G);
+    taps3x3(d2);
+    d2.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
+    d2.bias = bn.conv2.bias;
+    RUN(gemm_run(&d2, st));
+    const void* res = in;
+    if (blk == 0) {
+      AITB_REQUIRE(bn.down.w != nullptr, "layer4: first bottleneck needs the downsample branch");
+      aitb_gemm_desc dd = gemm_base(dt, M, 2048, 1024, bn.down.w, 256, ds, 2048, rt);
+      view_map(dd, in, 1024, 8, 4, 2, G);
+      dd.flags = AITB_EPI_BIAS;
+      dd.bias = bn.down.bias;
+      RUN(gemm_run(&dd, st));
+      res = ds;
+    }
+    aitb_gemm_desc d3 = gemm_base(dt, M, 2048, 512, bn.conv3.w, 256, out, 2048, rt);
+    view_plain(d3, c2, 512);
+    d3.flags = AITB_EPI_BIAS | AITB_EPI_RES | AITB_EPI_RES_RELU;
+    d3.bias = bn.conv3.bias;
+    d3.res = res;
+    d3.ldr = 2048;
+    RUN(gemm_run(&d3, st));
+    in = out;
+  }
+  *result = const_cast<void*>(in);
+  return 0;
+}
+
+static int check_weights(const aitb_head_weights* w, bool with_top) {
+  AITB_REQUIRE(w != nullptr, "null weights");
+  AITB_REQUIRE(w->dtype == AITB_F32 || w->dtype == AITB_BF16, "bad dtype %d", w->dtype);
+  AITB_REQUIRE(w->enc_emb.w && w->enc_emb.bias && w->dec_emb.w && w->dec_emb.bias && w->dec_trans.w &&
+                   w->dec_trans.bias && w->enc_pos && w->dec_pos && w->enc_ln.gamma && w->dec_ln.gamma,
+               "AIT embedding weights missing");
+  const aitb_mha* ms[3] = {&w->enc_slf, &w->dec_slf, &w->dec_enc};
+  for (int i = 0; i < 3; ++i)
+    AITB_REQUIRE(ms[i]->w_qkv && ms[i]->w_sk && ms[i]->b_sk && ms[i]->w_fc && ms[i]->ln.gamma && ms[i]->ln.beta,
+                 "attention block %d weights missing", i);
+  const aitb_ffn* fs[2] = {&w->enc_ffn, &w->dec_ffn};
+  for (int i = 0; i < 2; ++i)
+    AITB_REQUIRE(fs[i]->w1.w && fs[i]->w1.bias && fs[i]->w2.w && fs[i]->w2.bias && fs[i]->ln.gamma, "ffn %d missing", i);
+  if (with_top) {
+    AITB_REQUIRE(w->sk_props.conv1x1.w && w->sk_props.conv3x3.w && w->sk_query.conv1x1.w && w->sk_query.conv3x3.w,
+                 "SKNet weights missing");
+    for (int i = 0; i < 3; ++i)
+      AITB_REQUIRE(w->top[i].conv1.w && w->top[i].conv2.w && w->top[i].conv3.w, "layer4 block %d weights missing", i);
+    AITB_REQUIRE(w->w_bbox && w->b_bbox && w->w_cls1 && w->b_cls1 && w->w_cls2 && w->b_cls2, "head weights missing");
+  }
+  return 0;
+}
+
+}  // namespace aitb
+
+using namespace aitb;
+
+extern "C" {
+
+const char* aitb_last_error(void) { return g_err; }
+int aitb_version(void) { return 100; }
+
+int aitb_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    set_error("libaitb200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+    return 1;
+  }
+  return 0;
+}
+
+long long aitb_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+size_t aitb_nms_workspace_bytes(int B, int n_total, int n) { return nms_workspace_bytes(B, n_total, n); }
+
+int aitb_nms_batched(const float* boxes, const int64_t* order, int B, int n_total, int n, float thr, int max_out,
+                     int mode, int64_t* keep_out, int32_t* n_keep, float* rois_out, void* workspace,
+                     size_t workspace_bytes, aitb_stream_t stream) {
+  return nms_run(boxes, order, B, n_total, n, thr, max_out, mode, keep_out, n_keep, rois_out, workspace,
+                 workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t aitb_topk_workspace_bytes(int B, int n_total, int n) { return topk_workspace_bytes(B, n_total, n); }
+
+int aitb_topk_desc(const float* scores, int B, int n_total, int n, int64_t* order, void* workspace,
+                   size_t workspace_bytes, aitb_stream_t stream) {
+  return topk_run(scores, B, n_total, n, order, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int aitb_roi_align_forward(const void* feat_nhwc, const float* rois, int B, int C, int H, int W, int K,
+                           float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int dtype,
+                           int out_layout, void* out, aitb_stream_t stream) {
+  return roi_align_fwd_run(feat_nhwc, rois, B, C, H, W, K, spatial_scale, pooled_h, pooled_w, sampling_ratio, dtype,
+                           out_layout, out, (cudaStream_t)stream);
+}
+
+int aitb_roi_align_backward(const float* grad, const float* rois, int B, int C, int H, int W, int K,
+                            float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                            float* grad_feat_nhwc, aitb_stream_t stream) {
+  return roi_align_bwd_run(grad, rois, B, C, H, W, K, spatial_scale, pooled_h, pooled_w, sampling_ratio,
+                           grad_feat_nhwc, (cudaStream_t)stream);
+}
+
+int aitb_transpose_cs(const void* src, int src_dtype, void* dst, int dst_dtype, int G, int C, int S,
+                      int to_channels_last, aitb_stream_t stream) {
+  return transpose_run(src, src_dtype, dst, dst_dtype, G, C, S, to_channels_last, (cudaStream_t)stream);
+}
+
+int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream) { return gemm_run(d, (cudaStream_t)stream); }
+
+int aitb_attn_core(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
+                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, aitb_stream_t stream) {
+  return attn_core_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, (cudaStream_t)stream);
+}
+
+int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat, const float* w_bbox,
+                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* feat_out, float* bbox_out, float* cls_prob_out, aitb_stream_t stream) {
+  return pool_heads_run(top, dtype, G, P, qfeat, w_bbox, b_bbox, w1, b1, w2, b2, feat_out, bbox_out, cls_prob_out,
+                        (cudaStream_t)stream);
+}
+
+size_t aitb_head_workspace_bytes(int B, int P, int dtype) {
+  Bump b{nullptr, 0};
+  HeadBufs hb;
+  carve(b, hb, B, P, 64 * 64, dtype, true, true);  // map budget: up to 64x64 cells (1024x1024 px input)
+  return b.off + 1024;
+}
+
+size_t aitb_ait_workspace_bytes(int B, int P, int dtype) {
+  Bump b{nullptr, 0};
+  HeadBufs hb;
+  carve(b, hb, B, P, 0, dtype, false, false);
+  return b.off + 1024;
+}
+
+int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H, int W, const float* query_nchw,
+                      const float* rois, int B, int P, float* cls_prob, float* bbox_pred, const aitb_head_taps* taps,
+                      void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(check_weights(w, true));
+  AITB_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0, "aitb_head_forward: bad sizes B=%d P=%d H=%d W=%d", B, P, H, W);
+  AITB_REQUIRE(H * W <= 64 * 64, "aitb_head_forward: map %dx%d exceeds the 4096-cell workspace budget", H, W);
+  AITB_REQUIRE(feat_nchw && query_nchw && rois && cls_prob && bbox_pred && workspace, "aitb_head_forward: null pointer");
+  AITB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "aitb_head_forward: workspace must be 1024-byte aligned");
+  AITB_REQUIRE(workspace_bytes >= aitb_head_workspace_bytes(B, P, w->dtype), "aitb_head_forward: workspace too small");
+  const int dt = w->dtype, eb = esize(dt);
+  const int bp = B * P;
+  Bump b{(uint8_t*)workspace, 0};
+  HeadBufs hb;
+  carve(b, hb, B, P, 64 * 64, dt, true, true);
+
+  // a3: ROIAlign from a channels-last copy of the map, token-major output feeding enc_emb
+  RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt, B, 1024, H * W, 1, st));
+  for (int k0 = 0; k0 < bp; k0 += 32768) {
+    const int kn = bp - k0 < 32768 ? bp - k0 : 32768;
+    RUN(roi_align_fwd_run(hb.featT, rois + (size_t)k0 * 5, B, 1024, H, W, kn, 1.f / 16.f, 7, 7, 0, dt, 1,
+                          (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st));
+  }
+  RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st));
+  if (taps && taps->pooled) {
+    cudaError_t e = cudaMemcpyAsync(taps->pooled, hb.pooled, (size_t)bp * 49 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
+    AITB_REQUIRE(e == cudaSuccess, "pooled tap copy failed: %s", cudaGetErrorString(e));
+  }
+  // a5-a9: AIT
+  RUN(ait_core(w, hb, B, P, taps ? taps->enc_out : nullptr, st));
+  if (taps && taps->ait_out) {
+    cudaError_t e = cudaMemcpyAsync(taps->ait_out, hb.AIT, (size_t)bp * 64 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
+    AITB_REQUIRE(e == cudaSuccess, "ait tap copy failed: %s", cudaGetErrorString(e));
+  }
+  // a10: SKNet (separate weights for the proposal and the query branch)
+  RUN(sk_block(w, w->sk_props, hb.AIT, bp, hb.SK, st));
+  RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, st));
+  if (taps && taps->sk_out) {
+    cudaError_t e = cudaMemcpyAsync(taps->sk_out, hb.SK, (size_t)bp * 64 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
+    AITB_REQUIRE(e == cudaSuccess, "sk tap copy failed: %s", cudaGetErrorString(e));
+  }
+  // a11: RCNN_top on both branches
+  void *ytop = nullptr, *yq = nullptr;
+  RUN(layer4(w, hb.SKq, B, hb.qc1, hb.qc2, hb.qds, hb.qy0, hb.qy1, &yq, st));
+  RUN(layer4(w, hb.SK, bp, hb.c1, hb.c2, hb.ds, hb.y0, hb.y1, &ytop, st));
+  // a12: spatial mean + bbox / similarity heads
+  float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
+  RUN(pool_heads_run(yq, dt, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, qfeat, nullptr,
+                     nullptr, st));
+  RUN(pool_heads_run(ytop, dt, bp, P, qfeat, w->w_bbox, w->b_bbox, w->w_cls1, w->b_cls1, w->w_cls2, w->b_cls2,
+                     taps ? taps->feat : nullptr, bbox_pred, cls_prob, st));
+  return 0;
+}
+
+int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const float* x_query, int B, int P,
+                     float* out_nchw, void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(check_weights(w, false));
+  AITB_REQUIRE(B > 0 && P > 0, "aitb_ait_forward: bad sizes B=%d P=%d", B, P);
+  AITB_REQUIRE(x_props && x_query && out_nchw && workspace, "aitb_ait_forward: null pointer");
+  AITB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "aitb_ait_forward: workspace must be 1024-byte aligned");
+  AITB_REQUIRE(workspace_bytes >= aitb_ait_workspace_bytes(B, P, w->dtype), "aitb_ait_forward: workspace too small");
+  const int dt = w->dtype;
+  const int bp = B * P;
+  Bump b{(uint8_t*)workspace, 0};
+  HeadBufs hb;
+  carve(b, hb, B, P, 0, dt, false, false);
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (uint8_t*)hb.pooled + (size_t)g0 * 49 * 1024 * esize(dt),
+                      dt, gn, 1024, 49, 1, st));
+  }
+  RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st));
+  RUN(ait_core(w, hb, B, P, nullptr, st));
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run((const uint8_t*)hb.AIT + (size_t)g0 * 64 * 1024 * esize(dt), dt, out_nchw + (size_t)g0 * 1024 * 64,
+                      AITB_F32, gn, 1024, 64, 0, st));
+  }
+  return 0;
+}
+
+}  // extern "C"

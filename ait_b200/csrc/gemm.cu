@@ -1,0 +1,510 @@
+// tcgen05 GEMM for the AIT head:  out[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+//   * A and W tiles arrive by TMA (128-byte swizzle) into a 4-stage shared-memory ring.
+//     A is addressed through a 4-D strided view, so a 3x3 convolution on an 8x8 / 4x4 map is a
+//     loop over 9 shifted boxes (out-of-bounds rows are zero-filled by TMA = the conv padding)
+//     and a stride-2 1x1 convolution is just a strided view.  No im2col buffer exists.
+//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N<=256 per instruction,
+//     K = 32 bytes per instruction: 8 x tf32 or 16 x bf16); accumulators live in TMEM.
+//   * persistent CTAs (one per SM) walk the tile list; with BLOCK_N <= 256 the accumulator is
+//     double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * 4 epilogue warps read TMEM with tcgen05.ld (one output row per thread) and apply the fused
+//     epilogue: bias, ReLU / ReLU^2, residual, positional table, full-row LayerNorm (N = 512
+//     held entirely in TMEM: mean / variance are per-thread reductions, no shuffles needed).
+//
+// Reference ops this replaces (all plain torch calls into cuBLAS/cuDNN in the reference):
+//   nn.Conv2d 1x1 (system/Models.py:188-209), nn.Linear in MultiHeadAttention / FFN
+//   (system/SubLayers.py:51-58,172-187), grouped Conv2d in SKBlock
+//   (modules/blocks_coatt_transformer_sk.py:929-935), ResNet layer4 convs + frozen BN
+//   (faster_rcnn/resnet_coatt_transformer_sk.py:73-109).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+static constexpr int kBlockM = 128;
+static constexpr int kABytes = kBlockM * 128;  // one A stage: 128 rows x 128 B
+static constexpr int kThreads = 192;           // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+struct GemmKParams {
+  int M, N;
+  int k_chunks;  // 128-byte K chunks per tap
+  int taps;
+  int a_m_dim, a_m_step, a_group_c;
+  int ke;  // elements per 128-byte chunk
+  int8_t tap_dx[9], tap_dy[9];
+  int m_tiles, n_tiles;
+  // epilogue
+  int flags;
+  void* out;
+  int ldo;
+  int rows_in, rows_out;
+  const float* bias;
+  const void* res;
+  int ldr, res_div, res_rep;
+  const float* pos;
+  int pos_rows;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int round_tf32;
+};
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 512) ? 2 : 4;
+  static constexpr int kAccStages = (BLOCK_N == 512) ? 1 : 2;
+  static constexpr int kUmmaN = (BLOCK_N > 256) ? 256 : BLOCK_N;
+  static constexpr int kTmemCols = (BLOCK_N * kAccStages < 32) ? 32 : BLOCK_N * kAccStages;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T, int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kAcc = Cfg::kAccStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;    // [kAcc]
+  uint64_t* acc_empty = acc_full + kAcc;      // [kAcc]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  const int iters_per_tile = p.taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int nt = tile - mt * p.n_tiles;
+        const int a_c_base = nt * p.a_group_c;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
+          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_4d(sa, &tmA, &full_bar[s], a_c_base + kc * p.ke, c1, c2, c3);
+            const int kb = (tap * p.k_chunks + kc) * p.ke;
+            tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
+            if constexpr (BLOCK_N > 256)
+              tma_load_2d(sb + 256 * 128, &tmB, &full_bar[s], kb, nt * BLOCK_N + 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, kBlockM, Cfg::kUmmaN);
+      uint32_t it = 0;
+      uint32_t lt = 0;  // local tile counter
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++lt) {
+        const uint32_t as = lt % kAcc;
+        const uint32_t aph = (lt / kAcc) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int i = 0; i < iters_per_tile; ++i, ++it) {
+          const uint32_t s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte chunk
+#pragma unroll
+            for (int nb = 0; nb < BLOCK_N / Cfg::kUmmaN; ++nb) {
+              umma_ss<Act<T>::kBytes>(d_tmem + nb * Cfg::kUmmaN, adesc + (uint64_t)(k * 2),
+                                      bdesc + (uint64_t)(k * 2 + nb * (Cfg::kUmmaN * 128 / 16)),
+                                      idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
+        tc_commit(&acc_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    T* out = reinterpret_cast<T*>(p.out);
+    const T* res = reinterpret_cast<const T*>(p.res);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++lt) {
+      const int mt = tile / p.n_tiles;
+      const int nt = tile - mt * p.n_tiles;
+      const uint32_t as = lt % kAcc;
+      const uint32_t aph = (lt / kAcc) & 1;
+      const int m = mt * kBlockM + row_in_tile;
+      const bool valid = m < p.M;
+      const int mm = valid ? m : 0;
+      const int out_row = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
+      int res_row = 0;
+      if (p.flags & AITB_EPI_RES)
+        res_row = ((out_row / p.res_div) / p.res_rep) * p.res_div + (out_row % p.res_div);
+      const int pos_row = (p.flags & AITB_EPI_POS) ? (out_row % p.pos_rows) : 0;
+      const int n0 = nt * BLOCK_N;
+      T* orow = out + (size_t)out_row * p.ldo + n0;
+      const T* rrow = res + (size_t)res_row * p.ldr + n0;
+      const float* prow = p.pos + (size_t)pos_row * p.N + n0;
+
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
+
+      if ((p.flags & AITB_EPI_LN) == 0) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j8 + j]);
+              if (p.flags & AITB_EPI_BIAS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + n0 + c0 + j8 + j);
+              }
+              if (p.flags & AITB_EPI_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (p.flags & AITB_EPI_SQUARE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
+              }
+              if (p.flags & AITB_EPI_RES) {
+                float r[8];
+                ld8(rrow + c0 + j8, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += r[j];
+              }
+              if (p.flags & AITB_EPI_POS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += __ldg(prow + c0 + j8 + j);
+              }
+              if (p.flags & AITB_EPI_ACCUM) {
+                float r[8];
+                ld8(orow + c0 + j8, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += r[j];
+              }
+              if (p.flags & AITB_EPI_RES_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (sizeof(T) == 4 && p.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = round_tf32(v[j]);
+              }
+              st8(orow + c0 + j8, v);
+            }
+          }
+        }
+      } else {
+        // ---- full-row LayerNorm: the CTA's accumulator holds all N = BLOCK_N columns of the row
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j8 + j]);
+            if (p.flags & AITB_EPI_BIAS) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + c0 + j8 + j);
+            }
+            if (p.flags & AITB_EPI_RES) {
+              float r[8];
+              ld8(rrow + c0 + j8, r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += r[j];
+            }
+            if (p.flags & AITB_EPI_POS) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += __ldg(prow + c0 + j8 + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sum += v[j];
+              raw[j8 + j] = __float_as_uint(v[j]);
+            }
+          }
+          tmem_st32(t_row + c0, raw);
+        }
+        tmem_st_wait();
+        const float mean = sum * (1.f / BLOCK_N);
+        float ssq = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(raw[j]) - mean;
+            ssq += d * d;
+          }
+        }
+        const float rstd = rsqrtf(ssq * (1.f / BLOCK_N) + p.eps);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int n = c0 + j8 + j;
+                v[j] = (__uint_as_float(raw[j8 + j]) - mean) * rstd * __ldg(p.gamma + n) +
+                       __ldg(p.beta + n);
+                if (sizeof(T) == 4 && p.round_tf32) v[j] = round_tf32(v[j]);
+              }
+              st8(orow + c0 + j8, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  cuuint64_t gdims[4];
+  cuuint64_t gstr[3];
+  cuuint32_t gbox[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(tm, dtype == AITB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(ptr), gdims, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+              what, (int)r, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 1;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename T, int BLOCK_N>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<T, BLOCK_N>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm<%d>) failed: %s", BLOCK_N, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, kp);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
+  AITB_REQUIRE(d != nullptr, "aitb_gemm: null descriptor");
+  AITB_REQUIRE(d->dtype == AITB_F32 || d->dtype == AITB_BF16, "aitb_gemm: bad dtype %d", d->dtype);
+  const int eb = d->dtype == AITB_F32 ? 4 : 2;
+  const int ke = 128 / eb;
+  AITB_REQUIRE(d->M > 0 && d->N > 0, "aitb_gemm: empty problem M=%d N=%d", d->M, d->N);
+  AITB_REQUIRE(d->block_n == 128 || d->block_n == 256 || d->block_n == 512 || d->block_n == 64,
+               "aitb_gemm: block_n %d unsupported", d->block_n);
+  AITB_REQUIRE(d->N % d->block_n == 0, "aitb_gemm: N=%d not a multiple of block_n=%d", d->N, d->block_n);
+  AITB_REQUIRE(d->k_per_tap % ke == 0 && d->k_per_tap > 0, "aitb_gemm: K per tap %d not a multiple of %d",
+               d->k_per_tap, ke);
+  AITB_REQUIRE(d->taps >= 1 && d->taps <= 9, "aitb_gemm: taps=%d", d->taps);
+  AITB_REQUIRE(d->a.box[0] == (uint32_t)ke, "aitb_gemm: A box[0] must span 128 bytes");
+  AITB_REQUIRE(d->a.box[1] * d->a.box[2] * d->a.box[3] == 128, "aitb_gemm: A box must cover 128 rows");
+  AITB_REQUIRE(d->a_m_dim == 1 || d->a_m_dim == 3, "aitb_gemm: a_m_dim must be 1 or 3");
+  AITB_REQUIRE((d->flags & AITB_EPI_LN) == 0 || (d->block_n == 512 && d->N == 512),
+               "aitb_gemm: the LayerNorm epilogue needs block_n == N == 512");
+  AITB_REQUIRE(d->rows_in > 0 && d->rows_out >= d->rows_in, "aitb_gemm: bad row remap %d->%d", d->rows_in,
+               d->rows_out);
+  AITB_REQUIRE(d->ldo % 8 == 0, "aitb_gemm: ldo must be a multiple of 8 elements");
+  AITB_REQUIRE(((uintptr_t)d->out & 31) == 0 && ((uintptr_t)d->a.ptr & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
+               "aitb_gemm: pointers must be 16/32-byte aligned");
+  if (d->flags & AITB_EPI_RES)
+    AITB_REQUIRE(d->res != nullptr && d->res_div > 0 && d->res_rep > 0 && d->ldr % 8 == 0 &&
+                     ((uintptr_t)d->res & 31) == 0,
+                 "aitb_gemm: bad residual spec");
+  if (d->flags & AITB_EPI_POS) AITB_REQUIRE(d->pos != nullptr && d->pos_rows > 0, "aitb_gemm: bad pos spec");
+  if (d->flags & AITB_EPI_BIAS) AITB_REQUIRE(d->bias != nullptr, "aitb_gemm: bias flag without bias");
+  if (d->flags & AITB_EPI_LN) AITB_REQUIRE(d->gamma && d->beta, "aitb_gemm: LN flag without gamma/beta");
+
+  CUtensorMap tmA, tmB;
+  if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, d->a.box, "A")) return 1;
+  const uint64_t wdims[2] = {(uint64_t)d->taps * d->k_per_tap, (uint64_t)d->N};
+  const uint64_t wstr[1] = {(uint64_t)d->taps * d->k_per_tap * eb};
+  const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(d->block_n > 256 ? 256 : d->block_n)};
+  if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = d->M;
+  kp.N = d->N;
+  kp.k_chunks = d->k_per_tap / ke;
+  kp.taps = d->taps;
+  kp.a_m_dim = d->a_m_dim;
+  kp.a_m_step = d->a_m_step;
+  kp.a_group_c = d->a_group_c;
+  kp.ke = ke;
+  for (int i = 0; i < 9; ++i) {
+    kp.tap_dx[i] = d->tap_dx[i];
+    kp.tap_dy[i] = d->tap_dy[i];
+  }
+  kp.m_tiles = (d->M + kBlockM - 1) / kBlockM;
+  kp.n_tiles = d->N / d->block_n;
+  kp.flags = d->flags;
+  kp.out = d->out;
+  kp.ldo = d->ldo;
+  kp.rows_in = d->rows_in;
+  kp.rows_out = d->rows_out;
+  kp.bias = d->bias;
+  kp.res = d->res;
+  kp.ldr = d->ldr;
+  kp.res_div = d->res_div > 0 ? d->res_div : 1;
+  kp.res_rep = d->res_rep > 0 ? d->res_rep : 1;
+  kp.pos = d->pos;
+  kp.pos_rows = d->pos_rows > 0 ? d->pos_rows : 1;
+  kp.gamma = d->gamma;
+  kp.beta = d->beta;
+  kp.eps = d->eps;
+  kp.round_tf32 = d->round_tf32;
+
+#define AITB_DISPATCH(BN)                                                              \
+  (d->dtype == AITB_F32 ? launch_gemm<float, BN>(tmA, tmB, kp, stream)                 \
+                        : launch_gemm<__nv_bfloat16, BN>(tmA, tmB, kp, stream))
+  switch (d->block_n) {
+    case 64: return AITB_DISPATCH(64);
+    case 128: return AITB_DISPATCH(128);
+    case 256: return AITB_DISPATCH(256);
+    case 512: return AITB_DISPATCH(512);
+  }
+#undef AITB_DISPATCH
+  set_error("aitb_gemm: unreachable");
+  return 1;
+}
+
+}  // namespace aitb

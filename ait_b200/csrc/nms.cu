@@ -1,0 +1,284 @@
+// Batched greedy NMS, entirely on the device (no D2H round trip, no host scan).
+//
+// Replaces `_C.nms` (lib/model/csrc/nms.h:10-28 -> nms_cuda, csrc/cuda/nms.cu:70-131) and the
+// per-image python loop around it (lib/model/rpn/proposal_layer.py:134-164).
+//
+//   1. gather   : boxes in descending-score order (the caller supplies the order)
+//   2. bitmask  : 64x64 tiles of the IoU > thr relation, upper triangle only (the reference
+//                 computes all tiles, nms.cu:28 has the early exit commented out), one warp-pair
+//                 per tile, 64 candidate boxes staged in shared memory
+//   3. scan     : one CTA per image walks the 64-box blocks in order.  Warp 0 resolves the 64
+//                 in-block decisions from the diagonal words held in registers; then every
+//                 thread ORs the kept rows into its slice of the suppression vector (coalesced
+//                 64-bit loads).  In "proposal" mode the scan stops as soon as max_out boxes are
+//                 kept (the caller only consumes keep[:post_nms_topN], proposal_layer.py:156).
+//   4. emit     : kept positions, or (mode 1) original indices in ascending order like the
+//                 reference's final sort (nms.cu:127-130), plus the zero-padded roi tensor.
+//
+// IoU arithmetic follows devIoU (nms.cu:13-21) with the legacy +1 convention; every operation
+// is an explicitly rounded IEEE op (__fadd_rn/__fmul_rn/__fdiv_rn) so no FMA contraction can
+// change a comparison: results are bit-exact against the C oracle (oracle/oracle_ops.c).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ float iou_legacy(const float4 a, const float4 b) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+}
+
+__global__ void nms_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ order,
+                                  float4* __restrict__ sorted, int n_total, int n) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t src = order ? order[(size_t)b * n + i] : i;
+  sorted[(size_t)b * n + i] = boxes[(size_t)b * n_total + src];
+}
+
+// grid (col_blk, row_blk, B), 64 threads.  mask[b][row][col_blk] bit j = IoU(row, col_blk*64+j) > thr
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ sorted, u64* __restrict__ mask, int n, int nblk, float thr) {
+  const int col_blk = blockIdx.x, row_blk = blockIdx.y, b = blockIdx.z;
+  if (col_blk < row_blk) return;  // lower triangle is never read by the scan
+  const float4* bx = sorted + (size_t)b * n;
+  __shared__ float4 cols[64];
+  const int col_size = min(n - col_blk * 64, 64);
+  const int row_size = min(n - row_blk * 64, 64);
+  if ((int)threadIdx.x < col_size) cols[threadIdx.x] = bx[col_blk * 64 + threadIdx.x];
+  __syncthreads();
+  if ((int)threadIdx.x < row_size) {
+    const int row = row_blk * 64 + threadIdx.x;
+    const float4 me = bx[row];
+    u64 t = 0;
+    const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < col_size; ++j)
+      if (iou_legacy(me, cols[j]) > thr) t |= 1ULL << j;
+    mask[((size_t)b * n + row) * nblk + col_blk] = t;
+  }
+}
+
+// one CTA per image
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const u64* __restrict__ mask, int n, int nblk, int max_out, int stop_early,
+                int32_t* __restrict__ keep_pos /*[B, n]*/, int32_t* __restrict__ n_keep_all /*[B]*/) {
+  extern __shared__ u64 remv[];  // [nblk]
+  __shared__ u64 diag[64];
+  __shared__ u64 s_kept;
+  __shared__ int s_total;
+  const int b = blockIdx.x;
+  const u64* m = mask + (size_t)b * n * nblk;
+  int32_t* kp = keep_pos + (size_t)b * n;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) remv[k] = 0;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int base = blk * 64;
+    if (threadIdx.x < 64) {
+      const int box = base + threadIdx.x;
+      diag[threadIdx.x] = (box < n) ? m[(size_t)box * nblk + blk] : 0ULL;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u64 d[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) d[j] = diag[j];
+      u64 cur = remv[blk];
+      const int cnt = min(n - base, 64);
+      if (cnt < 64) cur |= ~0ULL << cnt;  // boxes past the end count as suppressed
+      u64 kept = 0;
+      int total = s_total;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        if (!((cur >> j) & 1ULL) && !(stop_early && total >= max_out)) {
+          kept |= 1ULL << j;
+          cur |= d[j];
+          ++total;
+        }
+      }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const u64 kept = s_kept;
+    const int before = s_total;
+    if (threadIdx.x < 64 && ((kept >> threadIdx.x) & 1ULL)) {
+      const int pos = before + __popcll(kept & ((1ULL << threadIdx.x) - 1ULL));
+      kp[pos] = base + threadIdx.x;
+    }
+    const int total = before + __popcll(kept);
+    const bool done = stop_early && total >= max_out;
+    if (!done && kept != 0ULL) {
+      for (int k = blk + 1 + threadIdx.x; k < nblk; k += blockDim.x) {
+        u64 acc = 0;
+        u64 bits = kept;
+        while (bits) {
+          const int j = __ffsll((long long)bits) - 1;
+          bits &= bits - 1;
+          acc |= m[(size_t)(base + j) * nblk + k];
+        }
+        remv[k] |= acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_total = total;
+    if (done) break;  // uniform: derived from shared values read after the barrier
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) n_keep_all[b] = s_total;
+}
+
+// mode 0 outputs: keep_out[b, i] = kept position (or -1), n_keep, rois_out
+__global__ void nms_emit_proposals_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ keep_pos,
+                                          const int32_t* __restrict__ n_keep_all, int n, int max_out,
+                                          int64_t* __restrict__ keep_out, int32_t* __restrict__ n_keep,
+                                          float* __restrict__ rois_out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nk = min(n_keep_all[b], max_out);
+  if (i == 0) n_keep[b] = nk;
+  if (i >= max_out) return;
+  const bool live = i < nk;
+  const int pos = live ? keep_pos[(size_t)b * n + i] : -1;
+  keep_out[(size_t)b * max_out + i] = pos;
+  if (rois_out) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) bx = sorted[(size_t)b * n + pos];
+    float* r = rois_out + ((size_t)b * max_out + i) * 5;
+    r[0] = (float)b;
+    r[1] = bx.x;
+    r[2] = bx.y;
+    r[3] = bx.z;
+    r[4] = bx.w;
+  }
+}
+
+// mode 1: flag the kept boxes in original index space ...
+__global__ void nms_mark_kernel(const int32_t* __restrict__ keep_pos, const int32_t* __restrict__ n_keep_all,
+                                const int64_t* __restrict__ order, int n, int n_total, uint8_t* __restrict__ flags) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keep_all[b]) return;
+  const int pos = keep_pos[(size_t)b * n + i];
+  const int64_t orig = order ? order[(size_t)b * n + pos] : pos;
+  flags[(size_t)b * n_total + orig] = 1;
+}
+
+// ... and compact them in ascending index order (one CTA per image, ordered block scan)
+__global__ void __launch_bounds__(1024)
+nms_compact_kernel(const uint8_t* __restrict__ flags, int n_total, int max_out, int64_t* __restrict__ keep_out,
+                   int32_t* __restrict__ n_keep) {
+  __shared__ int warp_cnt[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const uint8_t* f = flags + (size_t)b * n_total;
+  int64_t* ko = keep_out + (size_t)b * max_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < n_total; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const bool on = i < n_total && f[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (on) {
+      const int pos = off + __popc(bal & ((1u << lane) - 1u));
+      if (pos < max_out) ko[pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_cnt[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  const int total = s_base;
+  if (threadIdx.x == 0) n_keep[b] = min(total, max_out);
+  for (int i = total + threadIdx.x; i < max_out; i += blockDim.x) ko[i] = -1;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct NmsWs {
+  size_t sorted, mask, keep_pos, n_keep_all, flags, total;
+};
+static NmsWs nms_layout(int B, int n_total, int n) {
+  NmsWs w;
+  const size_t nblk = (n + 63) / 64;
+  size_t off = 0;
+  w.sorted = off; off += align256((size_t)B * n * 16);
+  w.mask = off; off += align256((size_t)B * n * nblk * 8);
+  w.keep_pos = off; off += align256((size_t)B * n * 4);
+  w.n_keep_all = off; off += align256((size_t)B * 4);
+  w.flags = off; off += align256((size_t)B * n_total);
+  w.total = off;
+  return w;
+}
+
+size_t nms_workspace_bytes(int B, int n_total, int n) { return nms_layout(B, n_total, n).total; }
+
+int nms_run(const float* boxes, const int64_t* order, int B, int n_total, int n, float thr, int max_out,
+            int mode, int64_t* keep_out, int32_t* n_keep, float* rois_out, void* ws, size_t ws_bytes,
+            cudaStream_t stream) {
+  AITB_REQUIRE(B > 0 && n > 0 && n_total >= n, "aitb_nms: bad sizes B=%d n_total=%d n=%d", B, n_total, n);
+  AITB_REQUIRE(mode == 0 || mode == 1, "aitb_nms: mode must be 0 or 1");
+  AITB_REQUIRE(max_out > 0, "aitb_nms: max_out must be positive");
+  AITB_REQUIRE(mode == 0 || max_out >= n, "aitb_nms: mode 1 needs max_out >= n");
+  AITB_REQUIRE(order != nullptr || n == n_total, "aitb_nms: order == NULL requires n == n_total");
+  AITB_REQUIRE(boxes && keep_out && n_keep && ws, "aitb_nms: null pointer");
+  AITB_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)ws & 255) == 0, "aitb_nms: misaligned boxes/workspace");
+  const NmsWs L = nms_layout(B, n_total, n);
+  AITB_REQUIRE(ws_bytes >= L.total, "aitb_nms: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  const int nblk = (n + 63) / 64;
+  AITB_REQUIRE((size_t)nblk * 8 <= 200 * 1024, "aitb_nms: n=%d too large for the on-chip suppression vector", n);
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  float4* sorted = reinterpret_cast<float4*>(w + L.sorted);
+  u64* mask = reinterpret_cast<u64*>(w + L.mask);
+  int32_t* keep_pos = reinterpret_cast<int32_t*>(w + L.keep_pos);
+  int32_t* n_keep_all = reinterpret_cast<int32_t*>(w + L.n_keep_all);
+  uint8_t* flags = w + L.flags;
+
+  nms_gather_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(reinterpret_cast<const float4*>(boxes), order,
+                                                                  sorted, n_total, n);
+  if (check_launch("nms_gather_kernel")) return 1;
+  nms_mask_kernel<<<dim3(nblk, nblk, B), 64, 0, stream>>>(sorted, mask, n, nblk, thr);
+  if (check_launch("nms_mask_kernel")) return 1;
+  const size_t smem = (size_t)nblk * 8;
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    AITB_REQUIRE(e == cudaSuccess, "aitb_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  }
+  nms_scan_kernel<<<B, 256, smem, stream>>>(mask, n, nblk, max_out, mode == 0 ? 1 : 0, keep_pos, n_keep_all);
+  if (check_launch("nms_scan_kernel")) return 1;
+  if (mode == 0) {
+    nms_emit_proposals_kernel<<<dim3((max_out + 127) / 128, B), 128, 0, stream>>>(sorted, keep_pos, n_keep_all, n,
+                                                                                 max_out, keep_out, n_keep, rois_out);
+    if (check_launch("nms_emit_proposals_kernel")) return 1;
+  } else {
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)B * n_total, stream);
+    AITB_REQUIRE(e == cudaSuccess, "aitb_nms: memset failed: %s", cudaGetErrorString(e));
+    nms_mark_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(keep_pos, n_keep_all, order, n, n_total, flags);
+    if (check_launch("nms_mark_kernel")) return 1;
+    nms_compact_kernel<<<B, 1024, 0, stream>>>(flags, n_total, max_out, keep_out, n_keep);
+    if (check_launch("nms_compact_kernel")) return 1;
+  }
+  return 0;
+}
+
+}  // namespace aitb

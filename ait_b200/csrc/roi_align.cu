@@ -1,0 +1,329 @@
+// ROIAlign (legacy maskrcnn-benchmark flavour: no half-pixel shift, adaptive sampling grid)
+// forward + backward, and the [G,C,S] <-> [G,S,C] layout kernels around it.
+//
+// Replaces `_C.roi_align_forward/backward`
+// (lib/model/csrc/cuda/ROIAlign_cuda.cu:65-122 / 178-254, semantics of bilinear_interpolate
+//  :16-62; CPU twin lib/model/csrc/cpu/ROIAlign_cpu.cpp:17-219).
+//
+// Design (HBM/L2-bound gather, not GEMM-shaped):
+//   * the map is read from a channels-last copy, so each bilinear tap is ONE coalesced,
+//     vectorised 128-bit load per lane (lanes = channels) instead of the reference's four
+//     scattered 4-byte gathers per output element;
+//   * sample positions/weights are channel independent: they are computed once per CTA into
+//     shared-memory tables (x table: pooled_w * grid_w entries, y table: pooled_h * grid_h);
+//   * a CTA owns (roi, channel slab); its feature window is small enough to stay in L1, so every
+//     map byte is fetched from L2 about once per CTA;
+//   * output goes either token-major [K, ph*pw, C] (feeds the enc_emb GEMM K-major, no NCHW
+//     round trip) or NCHW [K, C, ph, pw] through a shared-memory transpose (the drop-in layout).
+//   Sample coordinates use explicitly rounded fp32 ops in the reference's association order so
+//   that floor/clamp decisions match the CPU reference bit for bit; only the accumulation order
+//   of the (up to 4*grid) products differs (FMA), well inside the 1e-5 relative tolerance.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+static constexpr int kMaxGrid = 16;   // max adaptive samples per bin per axis held in smem tables
+static constexpr int kMaxPooled = 8;  // pooled_h/w up to 8
+
+struct Tap {   // one axis of one bilinear sample
+  int lo, hi;  // clamped cell indices
+  float wlo, whi;  // (1-l), l ; both 0 when the sample is outside [-1, size]
+};
+
+// One axis of bilinear_interpolate (ROIAlign_cuda.cu:22-52): validity, clamp, floor, weights.
+__device__ __forceinline__ Tap make_tap(float c, int size) {
+  Tap t;
+  if (c < -1.0f || c > (float)size) {
+    t.lo = t.hi = 0;
+    t.wlo = t.whi = 0.f;
+    return t;
+  }
+  if (c <= 0.f) c = 0.f;
+  int lo = (int)c;
+  int hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    c = (float)lo;
+  } else {
+    hi = lo + 1;
+  }
+  const float l = __fsub_rn(c, (float)lo);
+  t.lo = lo;
+  t.hi = hi;
+  t.whi = l;
+  t.wlo = __fsub_rn(1.f, l);
+  return t;
+}
+
+struct RoiGeom {
+  int batch;
+  float start_w, start_h, bin_w, bin_h;
+  int grid_w, grid_h;
+};
+
+// ROIAlign_cuda.cu:78-100 (same expressions, same order, fp32)
+__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, float scale, int ph, int pw,
+                                               int sampling_ratio) {
+  RoiGeom g;
+  g.batch = (int)roi[0];
+  g.start_w = __fmul_rn(roi[1], scale);
+  g.start_h = __fmul_rn(roi[2], scale);
+  const float end_w = __fmul_rn(roi[3], scale);
+  const float end_h = __fmul_rn(roi[4], scale);
+  const float rw = fmaxf(__fsub_rn(end_w, g.start_w), 1.f);
+  const float rh = fmaxf(__fsub_rn(end_h, g.start_h), 1.f);
+  g.bin_h = __fdiv_rn(rh, (float)ph);
+  g.bin_w = __fdiv_rn(rw, (float)pw);
+  g.grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)ph));
+  g.grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)pw));
+  return g;
+}
+
+// y = roi_start + p*bin + (i + .5f)*bin/grid   (ROIAlign_cuda.cu:109,112)
+__device__ __forceinline__ float sample_coord(float start, int p, float bin, int i, int grid) {
+  const float a = __fadd_rn(start, __fmul_rn((float)p, bin));
+  const float b = __fdiv_rn(__fmul_rn(__fadd_rn((float)i, .5f), bin), (float)grid);
+  return __fadd_rn(a, b);
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  __device__ static __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  __device__ static __forceinline__ float4 ld(const __nv_bfloat16* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  __device__ static __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+    uint2 r;
+    *reinterpret_cast<__nv_bfloat162*>(&r.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&r.y) = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+// grid (C / 128, K); block 256 = 8 warps; lane owns 4 consecutive channels of the 128-channel slab,
+// warps stride over the ph*pw bins.
+template <typename T, bool NCHW_OUT>
+__global__ void __launch_bounds__(256)
+roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
+                     int ph, int pw, int sampling_ratio, T* __restrict__ out) {
+  __shared__ Tap xtab[kMaxPooled * kMaxGrid];
+  __shared__ Tap ytab[kMaxPooled * kMaxGrid];
+  extern __shared__ float stage[];  // NCHW_OUT: [128][ph*pw + 1]
+  const int k = blockIdx.y;
+  const int c0 = blockIdx.x * 128;
+  const RoiGeom g = roi_geometry(rois + (size_t)k * 5, scale, ph, pw, sampling_ratio);
+  const int gw = g.grid_w, gh = g.grid_h;
+  // rois far larger than the map (unclipped inputs) overflow the tables: compute taps inline then
+  const bool xt = gw <= kMaxGrid, yt = gh <= kMaxGrid;
+  if (xt)
+    for (int i = threadIdx.x; i < pw * gw; i += blockDim.x)
+      xtab[i] = make_tap(sample_coord(g.start_w, i / gw, g.bin_w, i % gw, gw), W);
+  if (yt)
+    for (int i = threadIdx.x; i < ph * gh; i += blockDim.x)
+      ytab[i] = make_tap(sample_coord(g.start_h, i / gh, g.bin_h, i % gh, gh), H);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cvalid = min(128, C - c0);          // last slab may be partial (C % 4 == 0)
+  const bool lane_on = lane * 4 < cvalid;
+  const T* fb = feat + (size_t)g.batch * H * W * C + c0 + (lane_on ? lane * 4 : 0);
+  const float count = (float)(g.grid_h * g.grid_w);
+  const int nbins = ph * pw;
+  for (int bin = warp; bin < nbins; bin += 8) {
+    const int py = bin / pw, px = bin - py * pw;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < gh; ++iy) {
+      const Tap ty = yt ? ytab[py * gh + iy] : make_tap(sample_coord(g.start_h, py, g.bin_h, iy, gh), H);
+      const T* r0 = fb + (size_t)ty.lo * W * C;
+      const T* r1 = fb + (size_t)ty.hi * W * C;
+      for (int ix = 0; ix < gw; ++ix) {
+        const Tap tx = xt ? xtab[px * gw + ix] : make_tap(sample_coord(g.start_w, px, g.bin_w, ix, gw), W);
+        const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+        const float4 v1 = Vec4<T>::ld(r0 + (size_t)tx.lo * C);
+        const float4 v2 = Vec4<T>::ld(r0 + (size_t)tx.hi * C);
+        const float4 v3 = Vec4<T>::ld(r1 + (size_t)tx.lo * C);
+        const float4 v4 = Vec4<T>::ld(r1 + (size_t)tx.hi * C);
+        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+        acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+        acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+      }
+    }
+    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);   // output_val /= count (:118)
+    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+    if (!lane_on) continue;
+    if constexpr (NCHW_OUT) {
+      const int s = nbins + 1;
+      stage[(lane * 4 + 0) * s + bin] = acc.x;
+      stage[(lane * 4 + 1) * s + bin] = acc.y;
+      stage[(lane * 4 + 2) * s + bin] = acc.z;
+      stage[(lane * 4 + 3) * s + bin] = acc.w;
+    } else {
+      Vec4<T>::st(out + ((size_t)k * nbins + bin) * C + c0 + lane * 4, acc);
+    }
+  }
+  if constexpr (NCHW_OUT) {
+    __syncthreads();
+    // the slab's 128 channels x nbins outputs are contiguous in NCHW: fully coalesced store
+    T* ob = out + ((size_t)k * C + c0) * nbins;
+    const int s = nbins + 1;
+    for (int i = threadIdx.x; i < cvalid * nbins; i += blockDim.x) {
+      const int c = i / nbins, bin = i - c * nbins;
+      Act<T>::st(ob + i, stage[c * s + bin]);
+    }
+  }
+}
+
+// Backward (ROIAlign_cuda.cu:178-254): scatter g*w/count to the 4 taps.  Same CTA shape as the
+// forward; the NCHW grad slab is staged through shared memory, and the accumulation target is
+// channels-last so each atomic warp instruction hits 32 consecutive floats (red.global.add.v4
+// is not available for fp32 vectors before sm_90+ PTX; plain atomicAdd per component).
+__global__ void __launch_bounds__(256)
+roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ rois, int C, int H, int W, float scale,
+                     int ph, int pw, int sampling_ratio, float* __restrict__ gfeat) {
+  __shared__ Tap xtab[kMaxPooled * kMaxGrid];
+  __shared__ Tap ytab[kMaxPooled * kMaxGrid];
+  extern __shared__ float stage[];  // [32][nbins + 1]
+  const int k = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+  const int nbins = ph * pw;
+  const RoiGeom g = roi_geometry(rois + (size_t)k * 5, scale, ph, pw, sampling_ratio);
+  const int gw = g.grid_w, gh = g.grid_h;
+  const bool xt = gw <= kMaxGrid, yt = gh <= kMaxGrid;
+  if (xt)
+    for (int i = threadIdx.x; i < pw * gw; i += blockDim.x)
+      xtab[i] = make_tap(sample_coord(g.start_w, i / gw, g.bin_w, i % gw, gw), W);
+  if (yt)
+    for (int i = threadIdx.x; i < ph * gh; i += blockDim.x)
+      ytab[i] = make_tap(sample_coord(g.start_h, i / gh, g.bin_h, i % gh, gh), H);
+  const float* gb = grad + ((size_t)k * C + c0) * nbins;
+  const int s = nbins + 1;
+  const int cvalid = min(32, C - c0);
+  for (int i = threadIdx.x; i < cvalid * nbins; i += blockDim.x) {
+    const int c = i / nbins, bin = i - c * nbins;
+    stage[c * s + bin] = gb[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane >= cvalid) return;
+  float* fb = gfeat + (size_t)g.batch * H * W * C + c0 + lane;
+  const float count = (float)(g.grid_h * g.grid_w);
+  for (int bin = warp; bin < nbins; bin += 8) {
+    const int py = bin / pw, px = bin - py * pw;
+    const float gv = stage[lane * s + bin];
+    for (int iy = 0; iy < gh; ++iy) {
+      const Tap ty = yt ? ytab[py * gh + iy] : make_tap(sample_coord(g.start_h, py, g.bin_h, iy, gh), H);
+      for (int ix = 0; ix < gw; ++ix) {
+        const Tap tx = xt ? xtab[px * gw + ix] : make_tap(sample_coord(g.start_w, px, g.bin_w, ix, gw), W);
+        if (ty.wlo == 0.f && ty.whi == 0.f) continue;  // sample outside the map (x_low = -1 branch)
+        if (tx.wlo == 0.f && tx.whi == 0.f) continue;
+        const float g1 = gv * (ty.wlo * tx.wlo) / count, g2 = gv * (ty.wlo * tx.whi) / count;
+        const float g3 = gv * (ty.whi * tx.wlo) / count, g4 = gv * (ty.whi * tx.whi) / count;
+        atomicAdd(fb + ((size_t)ty.lo * W + tx.lo) * C, g1);
+        atomicAdd(fb + ((size_t)ty.lo * W + tx.hi) * C, g2);
+        atomicAdd(fb + ((size_t)ty.hi * W + tx.lo) * C, g3);
+        atomicAdd(fb + ((size_t)ty.hi * W + tx.hi) * C, g4);
+      }
+    }
+  }
+}
+
+// [G, C, S] -> [G, S, C] (to_cl) or back, 32x32 smem tiles, optional dtype conversion.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc) {
+  // src [G, R, Cc] -> dst [G, Cc, R]
+  __shared__ float tile[32][33];
+  const int g = blockIdx.z;
+  const TS* s = src + (size_t)g * R * Cc;
+  TD* d = dst + (size_t)g * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    if (r < R && c < Cc) tile[j][tx] = Act<TS>::ld(s + (size_t)r * Cc + c);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < R && c < Cc) Act<TD>::st(d + (size_t)c * R + r, tile[tx][j]);
+  }
+}
+
+int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream) {
+  AITB_REQUIRE(G > 0 && C > 0 && S > 0, "aitb_transpose_cs: empty tensor");
+  AITB_REQUIRE(G <= 65535, "aitb_transpose_cs: G=%d exceeds grid.z", G);
+  // to_cl: src [G, C, S] -> dst [G, S, C]  => R = C, Cc = S ; else src [G, S, C] -> dst [G, C, S] => R = S, Cc = C
+  const int R = to_cl ? C : S, Cc = to_cl ? S : C;
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, G);
+  if (sdt == AITB_F32 && ddt == AITB_F32)
+    transpose_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, R, Cc);
+  else if (sdt == AITB_F32 && ddt == AITB_BF16)
+    transpose_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, R, Cc);
+  else if (sdt == AITB_BF16 && ddt == AITB_F32)
+    transpose_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, R, Cc);
+  else if (sdt == AITB_BF16 && ddt == AITB_BF16)
+    transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src,
+                                                                              (__nv_bfloat16*)dst, R, Cc);
+  else {
+    set_error("aitb_transpose_cs: bad dtypes %d -> %d", sdt, ddt);
+    return 1;
+  }
+  return check_launch("transpose_kernel");
+}
+
+int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream) {
+  AITB_REQUIRE(K >= 0 && B > 0, "aitb_roi_align_forward: bad sizes");
+  if (K == 0) return 0;
+  AITB_REQUIRE(C % 4 == 0, "aitb_roi_align_forward: C=%d must be a multiple of 4 (128-bit channel vectors)", C);
+  AITB_REQUIRE(ph >= 1 && pw >= 1 && ph <= kMaxPooled && pw <= kMaxPooled, "aitb_roi_align_forward: pooled size %dx%d unsupported", ph, pw);
+  AITB_REQUIRE(K <= 65535, "aitb_roi_align_forward: K=%d exceeds one launch (chunk the rois)", K);
+  AITB_REQUIRE(out_layout == 0 || out_layout == 1, "aitb_roi_align_forward: out_layout must be 0 or 1");
+  dim3 grid((C + 127) / 128, K);
+  const size_t smem = out_layout == 0 ? (size_t)128 * (ph * pw + 1) * 4 : 0;
+  if (dtype == AITB_F32) {
+    if (out_layout == 0)
+      roi_align_fwd_kernel<float, true><<<grid, 256, smem, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
+                                                                      sampling_ratio, (float*)out);
+    else
+      roi_align_fwd_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
+                                                                    sampling_ratio, (float*)out);
+  } else if (dtype == AITB_BF16) {
+    if (out_layout == 0)
+      roi_align_fwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, stream>>>(
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out);
+    else
+      roi_align_fwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out);
+  } else {
+    set_error("aitb_roi_align_forward: bad dtype %d", dtype);
+    return 1;
+  }
+  return check_launch("roi_align_fwd_kernel");
+}
+
+int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
+                      int pw, int sampling_ratio, float* gfeat, cudaStream_t stream) {
+  AITB_REQUIRE(K >= 0 && B > 0, "aitb_roi_align_backward: bad sizes");
+  if (K == 0) return 0;
+  AITB_REQUIRE(C >= 1, "aitb_roi_align_backward: bad C");
+  AITB_REQUIRE(ph >= 1 && pw >= 1 && ph <= kMaxPooled && pw <= kMaxPooled, "aitb_roi_align_backward: pooled size unsupported");
+  AITB_REQUIRE(K <= 65535, "aitb_roi_align_backward: K=%d exceeds one launch", K);
+  dim3 grid((C + 31) / 32, K);
+  const size_t smem = (size_t)32 * (ph * pw + 1) * 4;
+  roi_align_bwd_kernel<<<grid, 256, smem, stream>>>(grad, rois, C, H, W, scale, ph, pw, sampling_ratio, gfeat);
+  return check_launch("roi_align_bwd_kernel");
+}
+
+}  // namespace aitb

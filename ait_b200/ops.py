@@ -1,0 +1,214 @@
+"""Thin Python wrappers over the C ABI (one function per entry point).  Inputs are CUDA tensors;
+outputs are allocated here with torch (caching allocator) and handed to the library as raw
+pointers on torch's current stream.  No math happens on the Python side."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _act_dtype(t):
+    return L.dtype_enum(t.dtype)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ait_b200: expected CUDA tensors (this path has no CPU implementation)")
+
+
+# ---------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------
+def transpose_cs(src, to_channels_last, out_dtype=None):
+    """[G, C, S] -> [G, S, C] (to_channels_last) or [G, S, C] -> [G, C, S]."""
+    lib = L.load()
+    _need_cuda(src)
+    src = src.contiguous()
+    out_dtype = out_dtype or src.dtype
+    G = src.shape[0]
+    if to_channels_last:
+        Cc, S = src.shape[1], src.shape[2]
+        dst = torch.empty((G, S, Cc), device=src.device, dtype=out_dtype)
+    else:
+        S, Cc = src.shape[1], src.shape[2]
+        dst = torch.empty((G, Cc, S), device=src.device, dtype=out_dtype)
+    step = 32768
+    for g0 in range(0, G, step):
+        gn = min(step, G - g0)
+        L.check(lib.aitb_transpose_cs(L.ptr(src[g0:]), _act_dtype(src), L.ptr(dst[g0:]),
+                                      L.dtype_enum(out_dtype), gn, Cc, S, 1 if to_channels_last else 0,
+                                      L.stream_ptr()))
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------
+# ROIAlign
+# ---------------------------------------------------------------------------------------------
+def roi_align_forward(feat_nhwc, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, token_major=False):
+    """feat_nhwc [B, H, W, C] (fp32 | bf16), rois [K, 5] fp32 -> [K, C, ph, pw] or [K, ph*pw, C]."""
+    lib = L.load()
+    _need_cuda(feat_nhwc, rois)
+    feat_nhwc = feat_nhwc.contiguous()
+    rois = rois.contiguous().float()
+    B, H, W, Cc = feat_nhwc.shape
+    K = rois.shape[0]
+    shape = (K, pooled_h * pooled_w, Cc) if token_major else (K, Cc, pooled_h, pooled_w)
+    out = torch.empty(shape, device=feat_nhwc.device, dtype=feat_nhwc.dtype)
+    step = 32768
+    for k0 in range(0, K, step):
+        kn = min(step, K - k0)
+        L.check(lib.aitb_roi_align_forward(L.ptr(feat_nhwc), L.ptr(rois[k0:]), B, Cc, H, W, kn,
+                                           float(spatial_scale), pooled_h, pooled_w, int(sampling_ratio),
+                                           _act_dtype(feat_nhwc), 1 if token_major else 0, L.ptr(out[k0:]),
+                                           L.stream_ptr()))
+    return out
+
+
+def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, B, Cc, H, W, sampling_ratio):
+    """grad [K, C, ph, pw] fp32 -> grad_input [B, C, H, W] fp32 (NCHW, like the reference)."""
+    lib = L.load()
+    _need_cuda(grad, rois)
+    grad = grad.contiguous().float()
+    rois = rois.contiguous().float()
+    K = rois.shape[0]
+    g_nhwc = torch.zeros((B, H, W, Cc), device=grad.device, dtype=torch.float32)
+    step = 32768
+    for k0 in range(0, K, step):
+        kn = min(step, K - k0)
+        L.check(lib.aitb_roi_align_backward(L.ptr(grad[k0:]), L.ptr(rois[k0:]), B, Cc, H, W, kn,
+                                            float(spatial_scale), pooled_h, pooled_w, int(sampling_ratio),
+                                            L.ptr(g_nhwc), L.stream_ptr()))
+    return transpose_cs(g_nhwc.view(B, H * W, Cc), to_channels_last=False).view(B, Cc, H, W)
+
+
+# ---------------------------------------------------------------------------------------------
+# top-n selection + NMS
+# ---------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    key = (tag, device)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:]
+
+
+def topk_desc(scores, n):
+    """scores [B, n_total] fp32 -> order [B, n] int64 (descending score, ties by lower index)."""
+    lib = L.load()
+    _need_cuda(scores)
+    scores = scores.contiguous().float()
+    B, n_total = scores.shape
+    n = min(n, n_total)
+    order = torch.empty((B, n), dtype=torch.int64, device=scores.device)
+    nbytes = lib.aitb_topk_workspace_bytes(B, n_total, n)
+    ws = _workspace(nbytes, scores.device, "topk")
+    L.check(lib.aitb_topk_desc(L.ptr(scores), B, n_total, n, L.ptr(order), L.ptr(ws), nbytes, L.stream_ptr()))
+    return order
+
+
+def nms_batched(boxes, order, thr, max_out, mode, want_rois=False):
+    """boxes [B, n_total, 4] fp32, order [B, n] int64 or None -> (keep [B, max_out] int64, n_keep [B] int32, rois)."""
+    lib = L.load()
+    _need_cuda(boxes, order)
+    boxes = boxes.contiguous().float()
+    B, n_total = boxes.shape[0], boxes.shape[1]
+    n = n_total if order is None else order.shape[1]
+    if order is not None:
+        order = order.contiguous()
+    keep = torch.empty((B, max_out), dtype=torch.int64, device=boxes.device)
+    n_keep = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    rois = torch.empty((B, max_out, 5), dtype=torch.float32, device=boxes.device) if want_rois else None
+    nbytes = lib.aitb_nms_workspace_bytes(B, n_total, n)
+    ws = _workspace(nbytes, boxes.device, "nms")
+    L.check(lib.aitb_nms_batched(L.ptr(boxes), L.ptr(order), B, n_total, n, float(thr), int(max_out), int(mode),
+                                 L.ptr(keep), L.ptr(n_keep), L.ptr(rois), L.ptr(ws), nbytes, L.stream_ptr()))
+    return keep, n_keep, rois
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM building block
+# ---------------------------------------------------------------------------------------------
+def _esize(dt):
+    return 4 if dt == L.AITB_F32 else 2
+
+
+def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
+         bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
+         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6):
+    """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
+    map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels)."""
+    lib = L.load()
+    d = L.GemmDesc()
+    dt = _act_dtype(a)
+    eb = _esize(dt)
+    d.dtype, d.M, d.N, d.k_per_tap, d.taps = dt, M, N, K, taps
+    d.a.ptr = a.data_ptr()
+    d.a_group_c = group_c
+    if view == "plain":
+        lda = lda or K
+        d.a.dims[:] = [lda if group_c else K * taps, M, 1, 1]
+        d.a.strides[:] = [lda * eb, lda * eb * M, lda * eb * M]
+        d.a.box[:] = [128 // eb, 128, 1, 1]
+        d.a_m_dim, d.a_m_step = 1, 128
+    else:
+        Cc, S, s, stride, G = map_args
+        d.a.dims[:] = [Cc, s, s, G]
+        d.a.strides[:] = [stride * Cc * eb, stride * S * Cc * eb, S * S * Cc * eb]
+        d.a.box[:] = [128 // eb, s, s, 128 // (s * s)]
+        d.a_m_dim, d.a_m_step = 3, 128 // (s * s)
+    if taps == 9:
+        for ky in range(3):
+            for kx in range(3):
+                d.tap_dx[ky * 3 + kx] = kx - 1
+                d.tap_dy[ky * 3 + kx] = ky - 1
+    d.w = w.data_ptr()
+    d.block_n = block_n
+    d.flags = flags
+    d.out = out.data_ptr()
+    d.ldo = out.shape[-1]
+    d.rows_in = rows_in or M
+    d.rows_out = rows_out or M
+    d.bias = 0 if bias is None else bias.data_ptr()
+    d.res = 0 if res is None else res.data_ptr()
+    d.ldr, d.res_div, d.res_rep = ldr, res_div, res_rep
+    d.pos = 0 if pos is None else pos.data_ptr()
+    d.pos_rows = pos_rows
+    d.gamma = 0 if gamma is None else gamma.data_ptr()
+    d.beta = 0 if beta is None else beta.data_ptr()
+    d.eps = eps
+    d.round_tf32 = 1 if round_tf32 else 0
+    L.check(lib.aitb_gemm(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def attn_core(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, out):
+    lib = L.load()
+    L.check(lib.aitb_attn_core(L.ptr(q), ldq, q_rep, L.ptr(k), L.ptr(v), ldkv, L.ptr(w_sk), L.ptr(b_sk), G,
+                               mask_mode, n_keys, _act_dtype(q), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def pool_heads(top, P, qfeat=None, w_bbox=None, b_bbox=None, w1=None, b1=None, w2=None, b2=None, want_feat=True):
+    """top [G, 16, 2048] -> (feat [G, 2048] | None, bbox [G, 4] | None, cls_prob [G] | None)."""
+    lib = L.load()
+    G = top.shape[0]
+    dev = top.device
+    feat = torch.empty((G, 2048), dtype=torch.float32, device=dev) if want_feat else None
+    heads = w_bbox is not None
+    bbox = torch.empty((G, 4), dtype=torch.float32, device=dev) if heads else None
+    cls = torch.empty((G,), dtype=torch.float32, device=dev) if heads else None
+    L.check(lib.aitb_pool_heads(L.ptr(top), _act_dtype(top), G, P, L.ptr(qfeat), L.ptr(w_bbox), L.ptr(b_bbox),
+                                L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(feat), L.ptr(bbox), L.ptr(cls),
+                                L.stream_ptr()))
+    return feat, bbox, cls
+
+
+def launch_count(reset=False):
+    return int(L.load(check_device=False).aitb_launch_count(1 if reset else 0))

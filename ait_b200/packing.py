@@ -1,0 +1,297 @@
+"""Weight packing + the host side of the head engine.
+
+`HeadEngine` turns the parameters of the mirror modules (system/Models.py, modules.py, head.py)
+into the flat, GEMM-ready buffers `aitb_head_weights` points at (include/aitb200.h):
+
+  * every projection / convolution becomes a K-major [N, K] matrix in the compute dtype
+    (fp32 pre-rounded to tf32, or bf16); w_qs/w_ks/w_vs are stacked into one [1536, 512] matrix
+  * 3x3 kernels are re-ordered tap-major ([out, ky, kx, in]) to match the shifted-TMA K loop
+  * frozen BatchNorm (eval mode, resnet_coatt_transformer_sk.py:429-435,451-474) is folded into
+    the preceding conv: w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps)
+  * biases, LayerNorm parameters, positional tables and the tiny score/box heads stay fp32
+
+Packing happens once (off the hot path); the per-step call is a single `aitb_head_forward`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def round_to_tf32(t):
+    """fp32 -> nearest tf32 (ties away from zero), like cvt.rna.tf32.f32."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class HeadEngine:
+    def __init__(self, transformer=None, sk=None, top=None, cls_score=None, bbox_pred=None,
+                 dtype=torch.float32, round_acts=False):
+        L.load()
+        self.dtype = dtype
+        self.dt = L.dtype_enum(dtype)
+        self.round_acts = bool(round_acts)
+        self._keep = []          # packed tensors stay alive as long as the engine
+        self.w = L.HeadWeights()
+        self.w.dtype = self.dt
+        self.w.round_tf32 = 1 if self.round_acts else 0
+        self.device = None
+        self.has_ait = transformer is not None
+        self.has_sk = sk is not None
+        self.has_top = top is not None
+        self.has_heads = cls_score is not None and bbox_pred is not None
+        with torch.no_grad():
+            if transformer is not None:
+                self._pack_transformer(transformer)
+            if sk is not None:
+                self._pack_sk(sk)
+            if top is not None:
+                self._pack_top(top)
+            if self.has_heads:
+                self._pack_heads(cls_score, bbox_pred)
+        self._ws = None
+
+    # ------------------------------------------------------------------ packing helpers
+    def _dev(self, t):
+        if not t.is_cuda:
+            raise RuntimeError("ait_b200: module parameters must live on a CUDA device (call .cuda()); "
+                               "there is no CPU execution path")
+        if self.device is None:
+            self.device = t.device
+        elif t.device != self.device:
+            raise RuntimeError("ait_b200: all parameters must be on the same device")
+        return t
+
+    def _mat(self, t):
+        """[N, K] matrix in the compute dtype."""
+        t = self._dev(t).detach().float().contiguous()
+        t = round_to_tf32(t) if self.dtype == torch.float32 else t.to(torch.bfloat16)
+        t = t.contiguous()
+        self._keep.append(t)
+        return t
+
+    def _f32(self, t):
+        t = self._dev(t).detach().float().contiguous()
+        self._keep.append(t)
+        return t
+
+    def _linear(self, dst, w, b=None):
+        m = self._mat(w)
+        bt = self._f32(b) if b is not None else None
+        dst.w = m.data_ptr()
+        dst.bias = bt.data_ptr() if bt is not None else None
+        return m, bt
+
+    def _ln(self, dst, ln):
+        dst.gamma = self._f32(ln.weight).data_ptr()
+        dst.beta = self._f32(ln.bias).data_ptr()
+
+    def _mha(self, dst, m):
+        wqkv = self._mat(torch.cat([m.w_qs.weight, m.w_ks.weight, m.w_vs.weight], dim=0))
+        dst.w_qkv = wqkv.data_ptr()
+        dst.w_sk = self._f32(m.sh.sk.weight).data_ptr()
+        dst.b_sk = self._f32(m.sh.sk.bias).data_ptr()
+        dst.w_fc = self._mat(m.fc.weight).data_ptr()
+        self._ln(dst.ln, m.layer_norm)
+
+    def _ffn(self, dst, f):
+        self._linear(dst.w1, f.w_1.weight, f.w_1.bias)
+        self._linear(dst.w2, f.w_2.weight, f.w_2.bias)
+        self._ln(dst.ln, f.layer_norm)
+
+    def _pack_transformer(self, t):
+        w = self.w
+        self._linear(w.enc_emb, t.enc_emb[0].weight.flatten(1), t.enc_emb[0].bias)
+        self._linear(w.dec_emb, t.dec_emb[0].weight.flatten(1), t.dec_emb[0].bias)
+        self._linear(w.dec_trans, t.dec_trans[0].weight.flatten(1), t.dec_trans[0].bias)
+        enc_pos = t.encoder.position_enc.pos_table
+        dec_pos = t.decoder.position_enc.pos_table
+        if enc_pos.shape[1] < 64 or dec_pos.shape[1] < 64:
+            raise RuntimeError("pos_table must hold at least 64 positions")
+        w.enc_pos = self._f32(enc_pos[0, :64]).data_ptr()
+        w.dec_pos = self._f32(dec_pos[0, :64]).data_ptr()
+        self._ln(w.enc_ln, t.encoder.layer_norm)
+        self._ln(w.dec_ln, t.decoder.layer_norm)
+        el, dl = t.encoder.layer_stack[0], t.decoder.layer_stack[0]
+        self._mha(w.enc_slf, el.slf_attn)
+        self._ffn(w.enc_ffn, el.pos_ffn)
+        self._mha(w.dec_slf, dl.slf_attn)
+        self._mha(w.dec_enc, dl.enc_attn)
+        self._ffn(w.dec_ffn, dl.pos_ffn)
+
+    @staticmethod
+    def _tap_major(wconv):
+        """[out, in, kh, kw] -> [out, kh*kw*in]"""
+        return wconv.permute(0, 2, 3, 1).reshape(wconv.shape[0], -1)
+
+    def _pack_sk(self, sk):
+        self._sk_mats = {}
+        for name, dst, blk in (("props", self.w.sk_props, sk.sk_props), ("query", self.w.sk_query, sk.sk_query)):
+            c1, c3 = blk.convs[0][0], blk.convs[1][0]
+            m1, b1 = self._linear(dst.conv1x1, self._tap_major(c1.weight), c1.bias)
+            m3, b3 = self._linear(dst.conv3x3, self._tap_major(c3.weight), c3.bias)
+            self._sk_mats[name] = (m1, b1, m3, b3)
+
+    @staticmethod
+    def _fold_bn(conv, bn):
+        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        w = conv.weight.float() * scale.view(-1, 1, 1, 1)
+        b = bn.bias.float() - bn.running_mean.float() * scale
+        return w, b
+
+    def _pack_top(self, top):
+        layer4 = top[0]
+        self._top_mats = []
+        for i, blk in enumerate(layer4):
+            dst = self.w.top[i]
+            mats = {}
+            for key, conv, bn in (("conv1", blk.conv1, blk.bn1), ("conv2", blk.conv2, blk.bn2),
+                                  ("conv3", blk.conv3, blk.bn3)):
+                wf, bf = self._fold_bn(conv, bn)
+                mats[key] = self._linear(getattr(dst, key), self._tap_major(wf), bf)
+            if blk.downsample is not None:
+                wf, bf = self._fold_bn(blk.downsample[0], blk.downsample[1])
+                mats["down"] = self._linear(dst.down, self._tap_major(wf), bf)
+            self._top_mats.append(mats)
+
+    def _pack_heads(self, cls_score, bbox_pred):
+        w = self.w
+        self._head_t = dict(
+            w_bbox=self._f32(bbox_pred.weight), b_bbox=self._f32(bbox_pred.bias),
+            w1=self._f32(cls_score[0].weight), b1=self._f32(cls_score[0].bias),
+            w2=self._f32(cls_score[1].weight), b2=self._f32(cls_score[1].bias))
+        w.w_bbox, w.b_bbox = self._head_t["w_bbox"].data_ptr(), self._head_t["b_bbox"].data_ptr()
+        w.w_cls1, w.b_cls1 = self._head_t["w1"].data_ptr(), self._head_t["b1"].data_ptr()
+        w.w_cls2, w.b_cls2 = self._head_t["w2"].data_ptr(), self._head_t["b2"].data_ptr()
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes + 1024:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=self.device)
+        off = (-self._ws.data_ptr()) % 1024
+        return self._ws[off:]
+
+    # ------------------------------------------------------------------ entry points
+    def ait_forward(self, x_props, x_query):
+        if not self.has_ait:
+            raise RuntimeError("engine built without the transformer")
+        lib = L.load()
+        ops._need_cuda(x_props, x_query)
+        x_props = x_props.contiguous().float()
+        x_query = x_query.contiguous().float()
+        bp, bs = x_props.shape[0], x_query.shape[0]
+        P = bp // bs
+        out = torch.empty((bp, 1024, 8, 8), dtype=torch.float32, device=x_props.device)
+        nbytes = lib.aitb_ait_workspace_bytes(bs, P, self.dt)
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(x_props.device):
+            L.check(lib.aitb_ait_forward(C.byref(self.w), L.ptr(x_props), L.ptr(x_query), bs, P, L.ptr(out),
+                                         L.ptr(ws), nbytes, L.stream_ptr()))
+        return out
+
+    def workspace_bytes(self, B, P):
+        return L.load().aitb_head_workspace_bytes(B, P, self.dt)
+
+    def head_forward(self, non_img, non_qry, rois, taps=False, out=None):
+        if not (self.has_ait and self.has_sk and self.has_top and self.has_heads):
+            raise RuntimeError("engine built without the full head")
+        lib = L.load()
+        ops._need_cuda(non_img, non_qry, rois)
+        if non_img.dtype != torch.float32 or non_qry.dtype != torch.float32:
+            raise RuntimeError("ait_b200: feature maps are passed as float32 NCHW (the compute dtype is an "
+                               "engine property)")
+        non_img = non_img.contiguous()
+        non_qry = non_qry.contiguous()
+        B, Cc, H, W = non_img.shape
+        if Cc != 1024 or tuple(non_qry.shape) != (B, 1024, 8, 8):
+            raise RuntimeError("expected non_img [B,1024,H,W] and non_qry [B,1024,8,8]")
+        if rois.dim() != 3 or rois.shape[0] != B or rois.shape[2] != 5:
+            raise RuntimeError("expected rois [B, P, 5]")
+        P = rois.shape[1]
+        rois2 = rois.reshape(B * P, 5).contiguous().float()
+        dev = non_img.device
+        if out is None:
+            cls_prob = torch.empty((B, P, 1), dtype=torch.float32, device=dev)
+            bbox = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+        else:
+            cls_prob, bbox = out
+        tp = None
+        tensors = {}
+        if taps:
+            tp = L.HeadTaps()
+            bp = B * P
+            tensors = dict(
+                pooled=torch.empty((bp, 49, 1024), dtype=self.dtype, device=dev),
+                enc_out=torch.empty((bp, 64, 512), dtype=self.dtype, device=dev),
+                ait_out=torch.empty((bp, 64, 1024), dtype=self.dtype, device=dev),
+                sk_out=torch.empty((bp, 64, 1024), dtype=self.dtype, device=dev),
+                feat=torch.empty((bp, 2048), dtype=torch.float32, device=dev),
+                qfeat=torch.empty((B, 2048), dtype=torch.float32, device=dev))
+            for k, v in tensors.items():
+                setattr(tp, k, v.data_ptr())
+        nbytes = lib.aitb_head_workspace_bytes(B, P, self.dt)
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(dev):
+            L.check(lib.aitb_head_forward(C.byref(self.w), L.ptr(non_img), H, W, L.ptr(non_qry), L.ptr(rois2), B, P,
+                                          L.ptr(cls_prob), L.ptr(bbox), C.byref(tp) if tp is not None else None,
+                                          L.ptr(ws), nbytes, L.stream_ptr()))
+        if taps:
+            return cls_prob, bbox, tensors
+        return cls_prob, bbox
+
+    # ---- module-level forwards of SKNet / RCNN_top, composed from the exported GEMM building block
+    def _sk_branch(self, x_nchw, which):
+        m1, b1, m3, b3 = self._sk_mats[which]
+        G = x_nchw.shape[0]
+        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype)
+        out = torch.empty((G, 64, 1024), dtype=self.dtype, device=x.device)
+        ops.gemm(x, m1, out, M=G * 64, N=1024, K=128, block_n=128, view="plain", lda=1024, group_c=128,
+                 flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE, bias=b1)
+        ops.gemm(x, m3, out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G),
+                 taps=9, group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_ACCUM, bias=b3)
+        return ops.transpose_cs(out, False, out_dtype=torch.float32).view(G, 1024, 8, 8)
+
+    def sk_forward(self, x_props, x_query):
+        if not self.has_sk:
+            raise RuntimeError("engine built without SKNet")
+        return self._sk_branch(x_props, "props"), self._sk_branch(x_query, "query")
+
+    def top_forward(self, x_nchw):
+        """`_head_to_tail`: layer4 + spatial mean, [G,1024,8,8] -> [G,2048]."""
+        if not self.has_top:
+            raise RuntimeError("engine built without RCNN_top")
+        G = x_nchw.shape[0]
+        dev = x_nchw.device
+        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype)
+        M = G * 16
+        c1 = torch.empty((M, 512), dtype=self.dtype, device=dev)
+        c2 = torch.empty((M, 512), dtype=self.dtype, device=dev)
+        ys = [torch.empty((M, 2048), dtype=self.dtype, device=dev) for _ in range(2)]
+        cur = x
+        for i, mats in enumerate(self._top_mats):
+            out = ys[i & 1]
+            w1, b1 = mats["conv1"]
+            if i == 0:
+                ops.gemm(cur, w1, c1, M=M, N=512, K=1024, block_n=256, view="map", map_args=(1024, 8, 4, 2, G),
+                         flags=L.EPI_BIAS | L.EPI_RELU, bias=b1)
+            else:
+                ops.gemm(cur, w1, c1, M=M, N=512, K=2048, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=b1)
+            w2, b2 = mats["conv2"]
+            ops.gemm(c1, w2, c2, M=M, N=512, K=512, block_n=256, view="map", map_args=(512, 4, 4, 1, G), taps=9,
+                     flags=L.EPI_BIAS | L.EPI_RELU, bias=b2)
+            res = cur
+            if i == 0:
+                wd, bd = mats["down"]
+                ds = torch.empty((M, 2048), dtype=self.dtype, device=dev)
+                ops.gemm(cur, wd, ds, M=M, N=2048, K=1024, block_n=256, view="map", map_args=(1024, 8, 4, 2, G),
+                         flags=L.EPI_BIAS, bias=bd)
+                res = ds
+            w3, b3 = mats["conv3"]
+            ops.gemm(c2, w3, out, M=M, N=2048, K=512, block_n=256,
+                     flags=L.EPI_BIAS | L.EPI_RES | L.EPI_RES_RELU, bias=b3, res=res, ldr=2048)
+            cur = out
+        feat, _, _ = ops.pool_heads(cur.view(G, 16, 2048), 1)
+        return feat

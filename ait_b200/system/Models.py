@@ -1,0 +1,174 @@
+"""Adaptive Image Transformer -- parameter-compatible mirror of the reference's
+`model.system.Models.Transformer` (lib/model/system/Models.py:174-280, identical to
+lib/model/transformer/Models.py at the shipped hyper-parameters), executed by libaitb200.
+
+The nn.Module tree below exists to (1) own the parameters/buffers under EXACTLY the reference's
+`state_dict` keys (48 keys; reference checkpoints load with strict=True) and (2) expose the
+reference's constructor and `forward(x_props, x_query)` signature.  No layer has a torch
+forward of its own: `Transformer.forward` packs the weights once and calls `aitb_ait_forward`
+(tcgen05 GEMMs with fused bias / positional / residual / LayerNorm epilogues + the selective-head
+attention kernel).  There is no PyTorch fallback.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import packing
+
+
+def _sinusoid_table(n_position, d_hid):
+    # same float64 construction as PositionalEncoding._get_sinusoid_encoding_table (Models.py:32-45)
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    angle = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    table = np.empty_like(angle)
+    table[:, 0::2] = np.sin(angle[:, 0::2])
+    table[:, 1::2] = np.cos(angle[:, 1::2])
+    return torch.FloatTensor(table).unsqueeze(0)
+
+
+class _Holder(nn.Module):
+    """Parameter container: these sub-modules are never called on their own."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("%s is executed by the fused libaitb200 engine; call Transformer.forward"
+                           % type(self).__name__)
+
+
+class PositionalEncoding(_Holder):
+    def __init__(self, d_hid, n_position=200):
+        super().__init__()
+        self.register_buffer("pos_table", _sinusoid_table(n_position, d_hid))
+
+
+class SHBlock(_Holder):
+    """Selective-head gate (SubLayers.py:9-39): only `sk` carries parameters."""
+
+    def __init__(self, n_head, d_v):
+        super().__init__()
+        self.sk = nn.Linear(d_v, d_v * n_head)
+
+
+class MultiHeadAttention(_Holder):
+    def __init__(self, n_head, d_model, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.n_head, self.d_k, self.d_v = n_head, d_k, d_v
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)
+        self.sh = SHBlock(n_head=n_head, d_v=d_v)
+        self.fc = nn.Linear(d_v, d_model, bias=False)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+        self.p_dropout = dropout
+
+
+class PositionwiseFeedForward(_Holder):
+    def __init__(self, d_in, d_hid, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Linear(d_in, d_hid)
+        self.w_2 = nn.Linear(d_hid, d_in)
+        self.layer_norm = nn.LayerNorm(d_in, eps=1e-6)
+        self.p_dropout = dropout
+
+
+class EncoderLayer(_Holder):
+    def __init__(self, d_model, d_inner, n_head, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.slf_attn = MultiHeadAttention(n_head, d_model, d_k, d_v, dropout=dropout)
+        self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
+
+
+class DecoderLayer(_Holder):
+    def __init__(self, d_model, d_inner, n_head, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.slf_attn = MultiHeadAttention(n_head, d_model, d_k, d_v, dropout=dropout)
+        self.enc_attn = MultiHeadAttention(n_head, d_model, d_k, d_v, dropout=dropout)
+        self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
+
+
+class Encoder(_Holder):
+    def __init__(self, d_word_vec, n_layers, n_head, d_k, d_v, d_model, d_inner, pad_idx, dropout=0.1,
+                 n_position=200):
+        super().__init__()
+        self.position_enc = PositionalEncoding(d_word_vec, n_position=n_position)
+        self.layer_stack = nn.ModuleList(
+            [EncoderLayer(d_model, d_inner, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class Decoder(_Holder):
+    def __init__(self, d_word_vec, n_layers, n_head, d_k, d_v, d_model, d_inner, pad_idx, n_position=200,
+                 dropout=0.1):
+        super().__init__()
+        self.position_enc = PositionalEncoding(d_word_vec, n_position=n_position)
+        self.layer_stack = nn.ModuleList(
+            [DecoderLayer(d_model, d_inner, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class Transformer(nn.Module):
+    """Same constructor as the reference (Models.py:177-181).  Supported envelope of the fused engine:
+    d_model = d_word_vec = 512, d_inner = 2048, n_layers = 1, n_head = 8, d_k = d_v = 64,
+    n_position >= 64 -- what `_fasterRCNN` and adaptive_image_transformer.py instantiate.  Anything
+    else raises (no silent fallback)."""
+
+    def __init__(self, src_pad_idx=1, trg_pad_idx=1, d_word_vec=512, d_model=512, d_inner=2048, n_layers=6,
+                 n_head=8, d_k=64, d_v=64, dropout=0.1, n_position=200, trg_emb_prj_weight_sharing=True,
+                 emb_src_trg_weight_sharing=True, compute_dtype=torch.float32):
+        super().__init__()
+        if d_model != d_word_vec:
+            raise AssertionError("To facilitate the residual connections, the dimensions of all module "
+                                 "outputs shall be the same.")
+        if (d_model, d_inner, n_layers, n_head, d_k, d_v) != (512, 2048, 1, 8, 64, 64) or n_position < 64:
+            raise NotImplementedError(
+                "ait_b200.Transformer supports the shipped AIT configuration only "
+                "(d_model=512, d_inner=2048, n_layers=1, n_head=8, d_k=d_v=64, n_position>=64); got "
+                "d_model=%d d_inner=%d n_layers=%d n_head=%d d_k=%d d_v=%d n_position=%d"
+                % (d_model, d_inner, n_layers, n_head, d_k, d_v, n_position))
+        self.src_pad_idx, self.trg_pad_idx = src_pad_idx, trg_pad_idx
+        self.channels = d_word_vec
+        self.compute_dtype = compute_dtype
+        self.enc_emb = nn.Sequential(nn.Conv2d(d_word_vec * 2, d_word_vec, kernel_size=1, bias=True))
+        self.dec_emb = nn.Sequential(nn.Conv2d(d_word_vec * 2, d_word_vec, kernel_size=1, bias=True))
+        self.encoder = Encoder(n_position=n_position, d_word_vec=d_word_vec, d_model=d_model, d_inner=d_inner,
+                               n_layers=n_layers, n_head=n_head, d_k=d_k, d_v=d_v, pad_idx=src_pad_idx,
+                               dropout=dropout)
+        self.decoder = Decoder(n_position=n_position, d_word_vec=d_word_vec, d_model=d_model, d_inner=d_inner,
+                               n_layers=n_layers, n_head=n_head, d_k=d_k, d_v=d_v, pad_idx=trg_pad_idx,
+                               dropout=dropout)
+        self.dec_trans = nn.Sequential(nn.Conv2d(d_word_vec, d_word_vec * 2, kernel_size=1, bias=True))
+        for p in self.parameters():  # Models.py:214-216
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._engine = None
+
+    def invalidate(self):
+        """Call after changing parameters in place (load_state_dict does it automatically)."""
+        self._engine = None
+
+    def _load_from_state_dict(self, *a, **k):
+        super()._load_from_state_dict(*a, **k)
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, x_props, x_query):
+        """x_props [bs*num_props, 1024, 7, 7], x_query [bs, 1024, 8, 8] -> [bs*num_props, 1024, 8, 8]
+        (Models.py:231-280).  Inference semantics (dropout = identity), like the reference in .eval()."""
+        if self.training and any(m.p_dropout > 0 for m in self.modules() if hasattr(m, "p_dropout")):
+            raise RuntimeError("ait_b200.Transformer: training-mode dropout is not implemented in the fused "
+                               "engine; call .eval() (or construct with dropout=0.0 for forward parity)")
+        if x_props.dim() != 4 or x_query.dim() != 4:
+            raise RuntimeError("expected x_props [bp,1024,7,7] and x_query [bs,1024,8,8]")
+        bp, c_p, h_p, w_p = x_props.shape
+        bs, c_q, h_q, w_q = x_query.shape
+        if (c_p, h_p, w_p) != (2 * self.channels, 7, 7) or (c_q, h_q, w_q) != (2 * self.channels, 8, 8):
+            raise RuntimeError("ait_b200.Transformer: supported shapes are x_props [bp,1024,7,7] and x_query "
+                               "[bs,1024,8,8]; got %s and %s" % (tuple(x_props.shape), tuple(x_query.shape)))
+        if bs == 0 or bp == 0 or bp % bs != 0:
+            raise RuntimeError("bp=%d must be a positive multiple of bs=%d (num_props = bp // bs)" % (bp, bs))
+        if self._engine is None:
+            self._engine = packing.HeadEngine(transformer=self, dtype=self.compute_dtype)
+        return self._engine.ait_forward(x_props, x_query)

@@ -1,0 +1,269 @@
+/*
+ * libaitb200 -- C ABI of the B200-native (sm_100a) AIT detection-head hot path.
+ *
+ * Drop-in boundary for CAIVIAC/AIT's native extension `model._C` (pybind11 module defined in
+ * lib/model/csrc/vision.cpp:7-13) and for the per-(image, query) head that the detector runs on
+ * top of it (lib/model/faster_rcnn/faster_rcnn_coatt_transformer_sk.py:273-337).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named `h_*`
+ *   - the library never allocates or frees device memory and never synchronises the device:
+ *     the caller passes outputs, a workspace and the stream
+ *   - every entry point returns 0 on success; on failure it returns non-zero and
+ *     aitb_last_error() (thread-local) describes why.  There is no CPU fallback.
+ *   - re-entrant; no global mutable state except the thread-local error string and the
+ *     lazily resolved driver entry point used to encode TMA descriptors
+ */
+#ifndef AITB200_H_
+#define AITB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef void* aitb_stream_t; /* cudaStream_t */
+
+enum { AITB_F32 = 0, AITB_BF16 = 1 }; /* activation storage; F32 computes on tf32 tensor cores */
+
+const char* aitb_last_error(void);
+int aitb_version(void);
+/* returns 0 when the current device is sm_100 (compute capability 10.x) */
+int aitb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1/a2  NMS  -- replaces `_C.nms` (csrc/nms.h:10-28 -> nms_cuda, csrc/cuda/nms.cu:70-131) and
+ * the per-image sort/top-N/NMS/pad loop of _ProposalLayer.forward (rpn/proposal_layer.py:129-166).
+ *
+ *   boxes   [B, n_total, 4] f32 (x1,y1,x2,y2), legacy +1 area convention (nms.cu:13-21)
+ *   order   [B, n] int64: per image, indices into n_total of the n candidates in descending
+ *           score order (NULL = boxes are already sorted and n == n_total)
+ *   thr     suppress when IoU >  thr  (CUDA semantics, nms.cu:60)
+ *   mode 0  "proposal": keep_out[b, 0..k) = positions (in score order) of the first
+ *           min(kept, max_out) survivors; the greedy scan stops early once max_out are kept
+ *   mode 1  "reference nms()": keep_out[b, 0..k) = ORIGINAL indices of all survivors in
+ *           ascending index order (nms.cu:127-130); max_out must be >= n
+ *   keep_out [B, max_out] int64 (entries beyond n_keep[b] are set to -1), n_keep [B] int32
+ *   rois_out (optional, mode 0) [B, max_out, 5] f32: rows (b, x1,y1,x2,y2) of the survivors,
+ *           zero-padded, column 0 always = b (proposal_layer.py:160-164)
+ * ---------------------------------------------------------------------------------------- */
+size_t aitb_nms_workspace_bytes(int B, int n_total, int n);
+int aitb_nms_batched(const float* boxes, const int64_t* order, int B, int n_total, int n,
+                     float thr, int max_out, int mode, int64_t* keep_out, int32_t* n_keep,
+                     float* rois_out, void* workspace, size_t workspace_bytes,
+                     aitb_stream_t stream);
+
+/* f1 (next row): K*A-wide descending selection of the top-n scores per image (stable: ties by
+ * lower index first), replacing torch.sort + [:pre_nms_topN] (proposal_layer.py:129,144-145).
+ *   scores [B, n_total] f32 -> order [B, n] int64 */
+size_t aitb_topk_workspace_bytes(int B, int n_total, int n);
+int aitb_topk_desc(const float* scores, int B, int n_total, int n, int64_t* order,
+                   void* workspace, size_t workspace_bytes, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  ROIAlign forward -- replaces `_C.roi_align_forward`
+ * (csrc/ROIAlign.h:11-26 -> ROIAlign_forward_cuda, csrc/cuda/ROIAlign_cuda.cu:257-299).
+ *   feat_nhwc [B, H, W, C]  channels-last copy of the map (see aitb_nchw_to_nhwc), dtype `dtype`
+ *   rois      [K, 5] f32 (batch_idx, x1, y1, x2, y2)
+ *   out_layout 0: NCHW [K, C, ph, pw] (the reference layout), 1: token-major [K, ph*pw, C]
+ *   out dtype = `dtype`.  sampling_ratio <= 0 selects the adaptive grid ceil(roi/pooled).
+ * ---------------------------------------------------------------------------------------- */
+int aitb_roi_align_forward(const void* feat_nhwc, const float* rois, int B, int C, int H, int W,
+                           int K, float spatial_scale, int pooled_h, int pooled_w,
+                           int sampling_ratio, int dtype, int out_layout, void* out,
+                           aitb_stream_t stream);
+
+/* a4  ROIAlign backward -- replaces `_C.roi_align_backward` (ROIAlign_cuda.cu:302-346).
+ *   grad [K, C, ph, pw] f32 NCHW -> grad_feat_nhwc [B, H, W, C] f32 (must be zeroed by caller),
+ *   accumulated with coalesced atomics; convert with aitb_nhwc_to_nchw afterwards. */
+int aitb_roi_align_backward(const float* grad, const float* rois, int B, int C, int H, int W,
+                            int K, float spatial_scale, int pooled_h, int pooled_w,
+                            int sampling_ratio, float* grad_feat_nhwc, aitb_stream_t stream);
+
+/* layout helpers: [G, C, S] <-> [G, S, C] with optional dtype conversion (src/dst dtype enums) */
+int aitb_transpose_cs(const void* src, int src_dtype, void* dst, int dst_dtype, int G, int C,
+                      int S, int to_channels_last, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 GEMM building block (used by the head engine below; exported for unit tests)
+ *   out[M, N] = epilogue( A[M, K] * W[N, K]^T ),  A through a (<=4-D) strided view so that
+ *   3x3 / strided convolutions are expressed as shifted TMA boxes with zero fill.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;
+  uint64_t dims[4];    /* elements, dims[0] innermost (K / channels) */
+  uint64_t strides[3]; /* bytes, for dims[1..3] */
+  uint32_t box[4];     /* TMA box; box[0]*elem = 128 B, box[1]*box[2]*box[3] = 128 rows */
+} aitb_view4;
+
+enum {
+  AITB_EPI_BIAS = 1,
+  AITB_EPI_RELU = 2,
+  AITB_EPI_SQUARE = 4,  /* v = v*v (after relu)                                   */
+  AITB_EPI_RES = 8,     /* v += residual[res_row(out_row), n]                     */
+  AITB_EPI_POS = 16,    /* v += pos[out_row % pos_rows, n]          (fp32 table)  */
+  AITB_EPI_LN = 32,     /* LayerNorm over the full row (requires block_n == N == 512) */
+  AITB_EPI_ACCUM = 64,  /* v += out (read-modify-write)                            */
+  AITB_EPI_RES_RELU = 128 /* relu applied AFTER the residual add (bottleneck tail) */
+};
+
+typedef struct {
+  int dtype; /* AITB_F32 (tf32 MMA) | AITB_BF16 */
+  int M, N, k_per_tap, taps;
+  aitb_view4 a;
+  int a_m_dim;   /* which A coordinate advances with the m-tile: 1 (plain rows) or 3 (conv) */
+  int a_m_step;  /* coordinate step per 128-row m-tile                                      */
+  int a_group_c; /* grouped conv: input-channel offset per n-tile (0 otherwise)             */
+  int8_t tap_dx[9], tap_dy[9];
+  const void* w; /* [N, taps*k_per_tap] K-major, dtype `dtype` */
+  int block_n;   /* 128 | 256 | 512 */
+  /* epilogue */
+  int flags;
+  void* out;
+  int ldo;
+  int rows_in, rows_out; /* out_row = (m / rows_in) * rows_out + m % rows_in */
+  const float* bias;
+  const void* res;
+  int ldr;
+  int res_div, res_rep; /* res_row = ((out_row / res_div) / res_rep) * res_div + out_row % res_div */
+  const float* pos;
+  int pos_rows;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int round_tf32; /* round stored fp32 activations to tf32 (RN) */
+} aitb_gemm_desc;
+
+int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a8 core: scaled-dot-product attention over T = 64 tokens, 8 heads of 64, with the
+ * selective-head gate (system/SubLayers.py:9-39,89-97; system/Modules.py:16-29):
+ *   per group g (a proposal-query pair):  O_h = softmax(mask(Q_h K_h^T / 8)) V_h,
+ *   s = mean_T(sum_h O_h),  gate = softmax_h(view(W_sk s + b_sk, [8, 64])),
+ *   out[g] = sum_h O_h * gate_h           -> [G, 64, 64]
+ *   q rows of group g start at (g / q_rep) * 64 (q_rep > 1 shares one Q block across q_rep groups)
+ *   mask_mode 0: keys j >= n_keys masked;  1: causal (j > i masked)
+ * ---------------------------------------------------------------------------------------- */
+int aitb_attn_core(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv,
+                   const float* w_sk, const float* b_sk, int G, int mask_mode, int n_keys,
+                   int dtype, void* out, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a12: spatial mean over the 4x4 layer-4 map + bbox / similarity-score heads
+ * (resnet_coatt_transformer_sk.py:476-485, 419-427; faster_rcnn_coatt_transformer_sk.py:318-337)
+ *   top [G, 16, 2048] (dtype) -> feat [G, 2048] f32 (optional), bbox [G, 4] f32,
+ *   cls_prob [G] f32 = softmax(W2 (W1 [feat, qfeat[g / P]] + b1) + b2)[1]
+ *   qfeat [G / P, 2048] f32 = pooled query feature (same kernel, run first with w_* = NULL)
+ * ---------------------------------------------------------------------------------------- */
+int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat,
+                    const float* w_bbox, const float* b_bbox, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* feat_out, float* bbox_out,
+                    float* cls_prob_out, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The whole head for a batch of B (image, query) units x P proposals:
+ * ROIAlign -> AIT (a5-a9) -> SKNet (a10) -> RCNN_top (a11) -> heads (a12).
+ * Weights are passed pre-packed (see ait_b200/packing.py): K-major [N, K] matrices in `dtype`,
+ * frozen BN folded into the conv weights / biases, fp32 biases and LayerNorm parameters.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* w;     /* [N, K] K-major (dtype) */
+  const float* bias; /* [N] or NULL */
+} aitb_linear;
+
+typedef struct {
+  const float* gamma;
+  const float* beta;
+} aitb_lnorm;
+
+typedef struct {
+  const void* w_qkv; /* [1536, 512] = rows(w_qs; w_ks; w_vs)   (SubLayers.py:51-53) */
+  const float* w_sk; /* [512, 64] f32, b_sk [512] f32           (SubLayers.py:22)   */
+  const float* b_sk;
+  const void* w_fc; /* [512, 64]                                (SubLayers.py:58)   */
+  aitb_lnorm ln;
+} aitb_mha;
+
+typedef struct {
+  aitb_linear w1; /* [2048, 512] + bias */
+  aitb_linear w2; /* [512, 2048] + bias */
+  aitb_lnorm ln;
+} aitb_ffn;
+
+typedef struct {
+  aitb_linear conv1; /* [512, Cin]        BN folded */
+  aitb_linear conv2; /* [512, 9*512]      tap-major K, BN folded */
+  aitb_linear conv3; /* [2048, 512]       BN folded */
+  aitb_linear down;  /* [2048, 1024] or w == NULL */
+} aitb_bottleneck;
+
+typedef struct {
+  aitb_linear conv1x1; /* [1024, 128]   grouped (8 groups of 128 -> 128) */
+  aitb_linear conv3x3; /* [1024, 9*128] grouped, tap-major K            */
+} aitb_skblock;
+
+typedef struct {
+  int dtype;
+  int round_tf32;
+  /* AIT (system/Models.py:177-220) */
+  aitb_linear enc_emb, dec_emb, dec_trans;
+  const float* enc_pos; /* [64, 512] f32 (encoder.position_enc.pos_table) */
+  const float* dec_pos;
+  aitb_lnorm enc_ln, dec_ln;
+  aitb_mha enc_slf, dec_slf, dec_enc;
+  aitb_ffn enc_ffn, dec_ffn;
+  /* SKNet (blocks_coatt_transformer_sk.py:915-998), separate weights for proposals / query */
+  aitb_skblock sk_props, sk_query;
+  /* RCNN_top = ResNet-50 layer4 (resnet_coatt_transformer_sk.py:416) */
+  aitb_bottleneck top[3];
+  /* heads (resnet_coatt_transformer_sk.py:419-427), fp32 */
+  const float* w_bbox; /* [4, 2048] */
+  const float* b_bbox;
+  const float* w_cls1; /* [8, 4096] */
+  const float* b_cls1;
+  const float* w_cls2; /* [2, 8] */
+  const float* b_cls2;
+} aitb_head_weights;
+
+typedef struct {
+  /* optional taps of intermediates for parity tests (NULL = skip); all in `dtype` unless noted */
+  void* pooled;   /* [B*P, 49, 1024] token-major ROIAlign output */
+  void* enc_out;  /* [B*P, 64, 512]  */
+  void* ait_out;  /* [B*P, 64, 1024] token-major (== [bp,1024,8,8] NCHW transposed) */
+  void* sk_out;   /* [B*P, 64, 1024] */
+  float* feat;    /* [B*P, 2048] f32  pooled layer-4 feature of each pair */
+  float* qfeat;   /* [B, 2048]   f32 */
+} aitb_head_taps;
+
+size_t aitb_head_workspace_bytes(int B, int P, int dtype);
+
+/* feat_nchw [B,1024,H,W] f32, query_nchw [B,1024,8,8] f32, rois [B*P,5] f32 (batch idx = unit)
+ * -> cls_prob [B*P] f32, bbox_pred [B*P,4] f32 */
+int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H, int W,
+                      const float* query_nchw, const float* rois, int B, int P, float* cls_prob,
+                      float* bbox_pred, const aitb_head_taps* taps, void* workspace,
+                      size_t workspace_bytes, aitb_stream_t stream);
+
+/* The AIT module alone (a5): x_props [bp,1024,7,7] f32 NCHW, x_query [B,1024,8,8] f32 NCHW
+ * -> out [bp,1024,8,8] f32 NCHW   (system/Models.py:231-280) */
+size_t aitb_ait_workspace_bytes(int B, int P, int dtype);
+int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const float* x_query,
+                     int B, int P, float* out_nchw, void* workspace, size_t workspace_bytes,
+                     aitb_stream_t stream);
+
+/* number of kernels launched by this thread through the library since the last reset */
+long long aitb_launch_count(int reset);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* AITB200_H_ */

@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (torch functional, fp32 or fp64) of the reference's
+floating-point head path.  Never imported by ait_b200/.  Each function cites the reference lines it
+follows; `tests/test_oracle_pins.py` pins all of them against the reference's own modules (imported
+from /root/reference where present) and against the committed golden vectors.
+
+The arithmetic is the reference's: the same ATen CPU kernels (F.conv2d, F.linear, matmul, softmax,
+F.layer_norm) in the same order, with the literal per-proposal recomputation of the decoder
+self-attention that the reference performs (system/Models.py:250-253).
+
+Weights are passed as a flat dict with the reference's state_dict keys, prefixed like
+`_fasterRCNN`'s sub-modules: transformer.*, sk.*, RCNN_top.0.*, RCNN_cls_score.*, RCNN_bbox_pred.*.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import c_ops
+
+
+def _sub(sd, prefix):
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _cast(sd, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# AIT  (lib/model/system/Models.py, Layers.py, SubLayers.py, Modules.py)
+# ------------------------------------------------------------------------------------------------
+def _attention(q, k, v, mask):
+    """ScaledDotProductAttention.forward (system/Modules.py:16-29), temperature = sqrt(64) = 8."""
+    attn = torch.matmul(q / 8.0, k.transpose(2, 3))
+    attn = attn.masked_fill(mask == 0, -1e9)
+    attn = F.softmax(attn, dim=-1)
+    return torch.matmul(attn, v)
+
+
+def _sh_block(x, w):
+    """SHBlock.forward (system/SubLayers.py:22-39): x [b, 8, T, 64]."""
+    b, n_head, T, Cc = x.shape
+    u = x.sum(dim=1)
+    s = u.transpose(1, 2).mean(dim=2)                      # AdaptiveAvgPool1d(1) over T
+    g = F.linear(s, w["sh.sk.weight"], w["sh.sk.bias"]).view(b, n_head, Cc)
+    g = F.softmax(g, dim=1).unsqueeze(2)
+    return x * g
+
+
+def _mha(w, q_in, k_in, v_in, mask):
+    """MultiHeadAttention.forward (system/SubLayers.py:68-102), n_head = 8, d_k = d_v = 64, eval mode."""
+    b, lq, lk = q_in.size(0), q_in.size(1), k_in.size(1)
+    residual = q_in
+    q = F.linear(q_in, w["w_qs.weight"]).view(b, lq, 8, 64).transpose(1, 2)
+    k = F.linear(k_in, w["w_ks.weight"]).view(b, lk, 8, 64).transpose(1, 2)
+    v = F.linear(v_in, w["w_vs.weight"]).view(b, lk, 8, 64).transpose(1, 2)
+    o = _attention(q, k, v, mask.unsqueeze(1))
+    o = _sh_block(o, w).sum(dim=1, keepdim=True)            # selective heads, summed (:89-92)
+    o = o.transpose(1, 2).contiguous().view(b, lq, -1)
+    o = F.linear(o, w["fc.weight"]) + residual
+    return F.layer_norm(o, (512,), w["layer_norm.weight"], w["layer_norm.bias"], eps=1e-6)
+
+
+def _ffn(w, x):
+    """PositionwiseFeedForward.forward (system/SubLayers.py:177-187)."""
+    y = F.linear(F.relu(F.linear(x, w["w_1.weight"], w["w_1.bias"])), w["w_2.weight"], w["w_2.bias"]) + x
+    return F.layer_norm(y, (512,), w["layer_norm.weight"], w["layer_norm.bias"], eps=1e-6)
+
+
+def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False):
+    """Transformer.forward (system/Models.py:231-280).  sd: the 48 transformer keys (no prefix)."""
+    w = _cast(sd, dtype)
+    x_props, x_query = x_props.to(dtype), x_query.to(dtype)
+    bp, bs = x_props.size(0), x_query.size(0)
+    num_props = bp // bs
+    xp = F.conv2d(x_props, w["enc_emb.0.weight"], w["enc_emb.0.bias"])           # :246
+    xq = F.conv2d(x_query, w["dec_emb.0.weight"], w["dec_emb.0.bias"])           # :247
+    rq = xq.unsqueeze(1).repeat(1, num_props, 1, 1, 1)                            # :250
+    src = xp.view(bp, 512, -1).permute(0, 2, 1)                                   # [bp, 49, 512]
+    trg = rq.view(bp, 512, -1).permute(0, 2, 1)                                   # [bp, 64, 512]
+    n_s, n_t = src.size(1), trg.size(1)
+    src_mask = torch.cat([torch.ones(bp, 1, n_s, dtype=torch.uint8),
+                          torch.zeros(bp, 1, n_t - n_s, dtype=torch.uint8)], dim=2)            # :258-260
+    trg_mask = (1 - torch.triu(torch.ones(1, n_t, n_t), diagonal=1)).to(torch.uint8).expand(bp, n_t, n_t)  # :262-263
+    src = torch.cat([src, torch.zeros(bp, n_t - n_s, 512, dtype=dtype)], dim=1)   # :268-270
+    # Encoder.forward (:83-111)
+    e = src + w["encoder.position_enc.pos_table"][:, :n_t]
+    e = F.layer_norm(e, (512,), w["encoder.layer_norm.weight"], w["encoder.layer_norm.bias"], eps=1e-6)
+    el = _sub(w, "encoder.layer_stack.0.")
+    e = _mha(_sub(el, "slf_attn."), e, e, e, src_mask)
+    e = _ffn(_sub(el, "pos_ffn."), e)
+    # Decoder.forward (:143-172)
+    d = trg + w["decoder.position_enc.pos_table"][:, :n_t]
+    d = F.layer_norm(d, (512,), w["decoder.layer_norm.weight"], w["decoder.layer_norm.bias"], eps=1e-6)
+    dl = _sub(w, "decoder.layer_stack.0.")
+    d = _mha(_sub(dl, "slf_attn."), d, d, d, trg_mask)
+    d = _mha(_sub(dl, "enc_attn."), d, e, e, src_mask)
+    d = _ffn(_sub(dl, "pos_ffn."), d)
+    out = d.permute(0, 2, 1).contiguous().view(bp, 512, 8, 8)                      # :276-277
+    out = F.conv2d(out, w["dec_trans.0.weight"], w["dec_trans.0.bias"])           # :278
+    return (out, e) if return_enc else out
+
+
+# ------------------------------------------------------------------------------------------------
+# SKNet (lib/model/modules/blocks_coatt_transformer_sk.py:960-998) -- bug-compatible
+# ------------------------------------------------------------------------------------------------
+def sk_block(w, x):
+    f1 = F.relu(F.conv2d(x, w["convs.0.0.weight"], w["convs.0.0.bias"], padding=0, groups=8))
+    f3 = F.relu(F.conv2d(x, w["convs.1.0.weight"], w["convs.1.0.bias"], padding=1, groups=8))
+    return f1 * f1 + f3 * f3          # v = f * f.expand_as(f); v.sum(dim=1)   (:980-983)
+
+
+def sknet_forward(sd, x_props, x_query, dtype=torch.float32):
+    w = _cast(sd, dtype)
+    return sk_block(_sub(w, "sk_props."), x_props.to(dtype)), sk_block(_sub(w, "sk_query."), x_query.to(dtype))
+
+
+# ------------------------------------------------------------------------------------------------
+# RCNN_top = layer4, `_head_to_tail` (lib/model/faster_rcnn/resnet_coatt_transformer_sk.py:73-109,476-485)
+# ------------------------------------------------------------------------------------------------
+def _bn(w, p, x):
+    return F.batch_norm(x, w[p + "running_mean"], w[p + "running_var"], w[p + "weight"], w[p + "bias"],
+                        training=False, eps=1e-5)
+
+
+def _bottleneck(w, x, stride, has_down):
+    out = F.relu(_bn(w, "bn1.", F.conv2d(x, w["conv1.weight"], stride=stride)))
+    out = F.relu(_bn(w, "bn2.", F.conv2d(out, w["conv2.weight"], padding=1)))
+    out = _bn(w, "bn3.", F.conv2d(out, w["conv3.weight"]))
+    res = _bn(w, "downsample.1.", F.conv2d(x, w["downsample.0.weight"], stride=stride)) if has_down else x
+    return F.relu(out + res)
+
+
+def head_to_tail(sd, x, dtype=torch.float32):
+    """sd: RCNN_top keys ('0.<block>.<...>').  x [G,1024,8,8] -> [G,2048]."""
+    w = _cast(sd, dtype)
+    x = x.to(dtype)
+    for i in range(3):
+        x = _bottleneck(_sub(w, "0.%d." % i), x, 2 if i == 0 else 1, i == 0)
+    return x.mean(3).mean(2)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole head (lib/model/faster_rcnn/faster_rcnn_coatt_transformer_sk.py:273-337)
+# ------------------------------------------------------------------------------------------------
+def roi_align(feat, rois):
+    """ROIAlign((7,7), 1/16, 0) via the C oracle (fp32, as the reference's CPU kernel)."""
+    out = c_ops.roi_align_forward(feat.float().numpy(), rois.float().numpy(), 1.0 / 16.0, 7, 7, 0)
+    return torch.from_numpy(out)
+
+
+def head_forward(sd, non_img, non_qry, rois, dtype=torch.float32):
+    """non_img [B,1024,H,W], non_qry [B,1024,8,8], rois [B,P,5] -> dict of outputs + intermediates."""
+    B, P = rois.shape[0], rois.shape[1]
+    pooled = roi_align(non_img, rois.reshape(-1, 5))                                   # :279
+    ait, enc = ait_forward(_sub(sd, "transformer."), pooled, non_qry, dtype, True)     # :289
+    sp, sq = sknet_forward(_sub(sd, "sk."), ait, non_qry, dtype)                       # :294
+    top = _sub(sd, "RCNN_top.")
+    pf = head_to_tail(top, sp, dtype)                                                  # :299
+    qf = head_to_tail(top, sq, dtype)                                                  # :300
+    w = _cast(sd, dtype)
+    bbox = F.linear(pf, w["RCNN_bbox_pred.weight"], w["RCNN_bbox_pred.bias"])          # :318
+    stack = torch.cat([pf.view(B, P, -1), qf.unsqueeze(1).repeat(1, P, 1)], dim=2).view(-1, 4096)   # :320-325
+    score = F.linear(F.linear(stack, w["RCNN_cls_score.0.weight"], w["RCNN_cls_score.0.bias"]),
+                     w["RCNN_cls_score.1.weight"], w["RCNN_cls_score.1.bias"])        # :335
+    prob = F.softmax(score, 1)[:, 1]                                                   # :337
+    return dict(pooled=pooled, enc_out=enc, ait_out=ait, sk_out=sp, feat=pf, qfeat=qf, score=score,
+                cls_prob=prob.view(B, P, 1), bbox_pred=bbox.view(B, P, 4))
+
+
+# ------------------------------------------------------------------------------------------------
+# proposal tail (lib/model/rpn/proposal_layer.py:129-166), `>` NMS semantics of the CUDA path
+# ------------------------------------------------------------------------------------------------
+def propose_rois(proposals, scores, pre_nms_topN=6000, post_nms_topN=300, thr=0.7):
+    import numpy as np
+    B, n_total = scores.shape
+    out = torch.zeros(B, post_nms_topN, 5)
+    counts = []
+    for i in range(B):
+        s = scores[i].double().numpy()
+        order = np.argsort(-s, kind="stable")
+        if 0 < pre_nms_topN < scores.numel():
+            order = order[:pre_nms_topN]
+        boxes = proposals[i].float().numpy()[order]
+        keep = c_ops.nms_sorted(boxes, thr, ge=False, max_keep=post_nms_topN)
+        out[i, :, 0] = i
+        out[i, : len(keep), 1:] = torch.from_numpy(boxes[keep])
+        counts.append(len(keep))
+    return out, counts

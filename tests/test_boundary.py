@@ -1,0 +1,125 @@
+"""CPU: the C-ABI library loads and exports every symbol include/aitb200.h declares; the mirror
+modules keep the reference's state_dict keys; host-side helpers agree with the reference."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "aitb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aitb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ait_b200 import _lib
+    from ait_b200.build import build
+    build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert set(names) == set(_lib.SIGNATURES), "ctypes prototypes out of sync with the header"
+    loaded = _lib.load(check_device=False)
+    assert loaded.aitb_version() == 100
+    assert loaded.aitb_head_workspace_bytes(8, 300, 0) > loaded.aitb_ait_workspace_bytes(8, 300, 0) > 0
+    assert loaded.aitb_nms_workspace_bytes(8, 21546, 6000) > 8 * 6000 * 94 * 8
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "ait_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "oracle_ops" not in txt or f.endswith(".cu"), f
+
+
+def test_cuda_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ait_b200 import _lib
+    from ait_b200.roi_layers import ROIAlign, nms
+    with pytest.raises(RuntimeError):
+        _lib.load(check_device=True)
+    with pytest.raises(RuntimeError):
+        nms(torch.zeros(3, 4), torch.zeros(3), 0.5)
+    with pytest.raises(RuntimeError):
+        ROIAlign((7, 7), 1 / 16.0, 0)(torch.zeros(1, 8, 4, 4), torch.zeros(1, 5))
+    # reference contract: empty dets -> empty CPU long tensor (csrc/nms.h:17-18)
+    out = nms(torch.zeros(0, 4), torch.zeros(0), 0.5)
+    assert out.dtype == torch.int64 and out.numel() == 0 and out.device.type == "cpu"
+
+
+def test_state_dict_keys_match_reference():
+    from ait_b200.head import DetectionHead
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    head = DetectionHead()
+    for name, mod in (("transformer", head.transformer), ("sk", head.sk), ("RCNN_top", head.RCNN_top)):
+        mine = {k: list(v.shape) for k, v in mod.state_dict().items()}
+        assert mine == keys[name], name
+    assert len(keys["transformer"]) == 48 and sum(int(np.prod(s)) for k, s in keys["transformer"].items()
+                                                   if "pos_table" not in k) == 8338944
+    assert [k for k in head.state_dict() if k.startswith("RCNN_cls_score")] == [
+        "RCNN_cls_score.0.weight", "RCNN_cls_score.0.bias", "RCNN_cls_score.1.weight", "RCNN_cls_score.1.bias"]
+
+
+def test_transformer_envelope_is_enforced():
+    from ait_b200.system.Models import Transformer
+    with pytest.raises(NotImplementedError):
+        Transformer(n_layers=6)                      # reference default; the engine supports n_layers=1
+    with pytest.raises(AssertionError):
+        Transformer(d_model=256, d_word_vec=512, n_layers=1)
+    t = Transformer(d_k=64, d_v=64, d_model=512, d_word_vec=512, d_inner=2048, n_position=64, n_layers=1, n_head=8)
+    with pytest.raises(RuntimeError):
+        t.eval()(torch.zeros(4, 1024, 6, 6), torch.zeros(2, 1024, 8, 8))
+
+
+def test_anchors_and_box_decoding_match_reference():
+    from ait_b200 import proposal, synth
+    g = load_golden("nms_rpn_unit0.pt")
+    np.testing.assert_array_equal(proposal.generate_anchors(scales=(8, 16, 32)), np.array(g["anchors"]["voc"]))
+    np.testing.assert_array_equal(proposal.generate_anchors(scales=(4, 8, 16, 32)), np.array(g["anchors"]["coco"]))
+    a = proposal.shifted_anchors(38, 63)
+    assert a.shape == (38 * 63 * 9, 4)
+    assert torch.equal(a[9], torch.from_numpy(proposal.generate_anchors()).float()[0] + torch.tensor([16., 0, 16, 0]))
+    boxes, scores = synth.rpn_outputs(0)
+    assert boxes.shape == (21546, 4) and scores.unique().numel() == 21546
+    assert boxes[:, 0::2].min() >= 0 and boxes[:, 0::2].max() <= 999 and boxes[:, 1::2].max() <= 599
+
+
+def test_weight_packing_host_logic():
+    from ait_b200.packing import HeadEngine, round_to_tf32
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -3.14159265, 1e-30, 65504.0])
+    r = round_to_tf32(x)
+    assert torch.all((r.view(torch.int32) & 0x1FFF) == 0)
+    assert torch.all((r - x).abs() <= x.abs() * 2 ** -11)
+    assert r[1].item() == 1.0 + 2 ** -10            # ties away from zero, like cvt.rna.tf32.f32
+    conv = torch.nn.Conv2d(4, 6, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(6).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2); bn.weight.data.normal_(); bn.bias.data.normal_()
+    w, b = HeadEngine._fold_bn(conv, bn)
+    xin = torch.randn(2, 4, 5, 5)
+    torch.testing.assert_close(torch.nn.functional.conv2d(xin, w, b, padding=1), bn(conv(xin)), rtol=1e-5, atol=1e-5)
+    tm = HeadEngine._tap_major(w)
+    assert tm.shape == (6, 36) and torch.equal(tm[2, 4 * 5:4 * 6], w[2, :, 1, 2])   # tap (ky=1,kx=2)
+
+
+def test_unit_sharding_is_a_partition():
+    from ait_b200.sharding import shard_units
+    for n_units in (1, 7, 8, 160):
+        for world in (1, 2, 4, 8):
+            parts = [shard_units(n_units, r, world) for r in range(world)]
+            flat = [u for p in parts for u in p]
+            assert flat == list(range(n_units))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1

@@ -1,0 +1,141 @@
+"""CPU: pin the oracle (oracle/) against the golden vectors generated from the reference
+(tests/golden/make_golden.py) and, where /root/reference is present, against the reference live."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_head, head_inputs, load_golden
+from oracle import c_ops, head_oracle, ref_import
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def test_nms_oracle_matches_reference_golden_rpn_site():
+    from ait_b200 import synth
+    g = load_golden("nms_rpn_unit0.pt")
+    boxes, scores = synth.rpn_outputs(0)
+    order = np.argsort(-scores.double().numpy(), kind="stable")[:6000]
+    b6 = boxes.numpy()[order]
+    keep = c_ops.nms_sorted(b6, 0.7, ge=False)
+    assert len(keep) == g["n_keep"]
+    assert sha(keep.astype(np.int64)) == g["keep_sha"]
+    assert np.array_equal(keep[:300], g["keep_first300"].numpy())
+    # `>=` variant (the CPU reference's own rule) gives the same list here: no exact ties at 0.7
+    assert np.array_equal(c_ops.nms_sorted(b6, 0.7, ge=True), keep)
+    # full nms(dets, scores, thr) contract: ascending ORIGINAL indices
+    keep_all = c_ops.nms(boxes.numpy(), scores.numpy(), 0.7)
+    assert len(keep_all) == g["n_keep_all"] and sha(keep_all) == g["keep_all_sha"]
+    rois, counts = head_oracle.propose_rois(boxes[None], scores[None], 6000, 300, 0.7)
+    assert counts == [300] and torch.equal(rois[0], g["rois"])
+
+
+def test_nms_tie_divergence_cuda_gt_vs_cpu_ge():
+    """IoU == thr exactly: CUDA keeps (>), CPU suppresses (>=)  (nms.cu:60 vs nms_cpu.cpp:60)."""
+    boxes = np.array([[0, 0, 9, 9], [0, 0, 9, 4], [20, 20, 29, 29]], dtype=np.float32)  # IoU(0,1) = 50/100
+    assert list(c_ops.nms_sorted(boxes, 0.5, ge=False)) == [0, 1, 2]
+    assert list(c_ops.nms_sorted(boxes, 0.5, ge=True)) == [0, 2]
+
+
+def test_nms_edge_cases():
+    assert len(c_ops.nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), 0.7)) == 0
+    one = np.array([[1, 2, 3, 4]], np.float32)
+    assert list(c_ops.nms(one, np.array([0.3], np.float32), 0.7)) == [0]
+    same = np.tile(np.array([[5, 5, 50, 50]], np.float32), (70, 1))        # spans two 64-blocks
+    assert list(c_ops.nms(same, np.linspace(1, 0, 70).astype(np.float32), 0.7)) == [0]
+    # equal scores: stable (lower index first)
+    b = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [100, 100, 110, 110]], np.float32)
+    assert list(c_ops.nms(b, np.array([0.5, 0.5, 0.5], np.float32), 0.7)) == [0, 2]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_nms_oracle_vs_reference_live():
+    C = ref_import.load_ref_C()
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 63, 64, 65, 500, 2000):
+        xy = torch.rand(n, 2, generator=g) * 400
+        wh = torch.rand(n, 2, generator=g) * 150 + 1
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.rand(n, generator=g)
+        for thr in (0.3, 0.7):
+            ref = C.nms(boxes, scores, thr).numpy()
+            assert np.array_equal(c_ops.nms(boxes.numpy(), scores.numpy(), thr, ge=True), ref)
+
+
+# ------------------------------------------------------------------------------------------ ROIAlign
+def test_roi_align_oracle_matches_reference_golden():
+    g = load_golden("roi_align_small.pt")
+    feat = torch.randn(2, 8, 38, 63, generator=torch.Generator().manual_seed(g["seed"]))
+    out = c_ops.roi_align_forward(feat.numpy(), g["rois"].numpy(), 1 / 16.0, 7, 7, 0)
+    np.testing.assert_allclose(out, g["out"].numpy(), rtol=1e-5, atol=1e-6)
+    out2 = c_ops.roi_align_forward(feat.numpy(), g["rois"].numpy(), 1 / 16.0, 7, 7, 2)
+    np.testing.assert_allclose(out2, g["out_sr2"].numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_roi_align_oracle_vs_torchvision():
+    """the legacy kernel == torchvision roi_align(sampling_ratio=0, aligned=False)."""
+    tv = pytest.importorskip("torchvision")
+    from ait_b200 import synth
+    feat = synth.c4_map(3, channels=16)[None]
+    rois = synth.random_rois(3, 32)
+    ref = tv.ops.roi_align(feat, rois, (7, 7), 1 / 16.0, 0, False)
+    out = c_ops.roi_align_forward(feat.numpy(), rois.numpy(), 1 / 16.0, 7, 7, 0)
+    np.testing.assert_allclose(out, ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_roi_align_backward_oracle_is_adjoint_of_forward():
+    """<forward(x), g> == <x, backward(g)> (linearity / adjointness), checked in float64."""
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(1, 4, 38, 63, generator=g)
+    rois = torch.tensor([[0, 17.0, 33.0, 411.0, 288.0], [0, 600.0, 10.0, 990.0, 590.0], [0, 5.0, 5.0, 9.0, 9.0]])
+    grad = torch.randn(3, 4, 7, 7, generator=g)
+    out = c_ops.roi_align_forward(feat.numpy(), rois.numpy(), 1 / 16.0, 7, 7, 0)
+    gin = c_ops.roi_align_backward(grad.numpy(), rois.numpy(), 1 / 16.0, 7, 7, 1, 4, 38, 63, 0)
+    lhs = float((out.astype(np.float64) * grad.numpy().astype(np.float64)).sum())
+    rhs = float((feat.numpy().astype(np.float64) * gin).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+# ------------------------------------------------------------------------------------------ AIT + head
+def test_ait_oracle_matches_reference_golden():
+    head, _ = golden_head()
+    g = load_golden("ait_rand.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    xp = torch.rand(6, 1024, 7, 7, generator=gen)
+    xq = torch.rand(2, 1024, 8, 8, generator=gen)
+    with torch.no_grad():
+        out = head_oracle.ait_forward(head.transformer.state_dict(), xp, xq)
+    torch.testing.assert_close(out[:, ::8], g["out_s"], rtol=1e-4, atol=1e-5)
+
+
+def test_head_oracle_matches_reference_golden():
+    head, g = golden_head()
+    non_img, non_qry, rois = head_inputs(g["B"], g["P"])
+    assert torch.equal(rois, g["rois"])
+    with torch.no_grad():
+        o = head_oracle.head_forward(head.state_dict(), non_img, non_qry, rois)
+    torch.testing.assert_close(o["pooled"][:, ::16], g["pooled_s"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(o["ait_out"][:, ::16], g["ait_s"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o["sk_out"][:, ::16], g["sk_s"], rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(o["feat"], g["feat"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o["qfeat"], g["qfeat"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o["bbox_pred"], g["bbox_pred"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(o["cls_prob"], g["cls_prob"], rtol=0, atol=1e-4)
+    assert float(g["cls_prob"].max() - g["cls_prob"].min()) > 0.5     # the gate is not vacuous
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_state_dict_loads_into_reference_strict():
+    import sys
+    sys.path.insert(0, ref_import.REF_ROOT)
+    head, _ = golden_head()
+    ref_import.ref_transformer().load_state_dict(head.transformer.state_dict(), strict=True)
+    ref_import.ref_sknet().load_state_dict(head.sk.state_dict(), strict=True)
+    ref_import.ref_layer4().load_state_dict(head.RCNN_top.state_dict(), strict=True)
