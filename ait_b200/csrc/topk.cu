@@ -19,7 +19,8 @@
 namespace aitb {
 
 __device__ __forceinline__ uint32_t order_key(float f) {
-  const uint32_t u = __float_as_uint(f);
+  uint32_t u = __float_as_uint(f);
+  if (u == 0x80000000u) u = 0u;  // -0.0 == +0.0 for the comparison, like torch.sort
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // larger float -> larger key
 }
 

@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the AIT detection-head hot path (BASELINE.json metric: proposal-query pairs / second
+through RPN-proposal NMS -> ROIAlign -> AIT -> SKNet -> RCNN_top -> score/bbox heads).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype tf32|bf16]
+
+Workload (config.workload): BASELINE.json configs[1] -- PASCAL-VOC test shape, 8 (image, query) units x
+300 proposals per GPU, 600x1000 input -> C4 map [1024,38,63], 128x128 query -> [1024,8,8], 21 546 RPN
+anchors/unit, pre-NMS top 6000, NMS 0.7, post-NMS 300; fp32 storage with tf32 tensor-core math (the
+"fp32" configuration of the north star; --dtype bf16 runs the bf16 configuration).  Weak scaling: every
+rank owns its own 8 units; there is no collective on the data path, only the timing
+all-reduce and a final host-side gather.
+
+One "step" = one pass of the hot path over the rank's 8 units (2400 pairs).
+  value : device-resident inputs, CUDA-event timed on the launch stream, max over ranks
+  e2e   : the same step through the public API with HOST (pinned) inputs: H2D of maps / query / RPN
+          boxes+scores and D2H of rois / cls_prob / bbox_pred inside the timed region
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNITS_PER_GPU = 8
+PROPOSALS = 300
+PRE_NMS, NMS_THR = 6000, 0.7
+FLOP_PER_PAIR = 1.494e9          # de-duplicated algorithmic FLOPs per pair (SURVEY 8d / BASELINE.md section 3)
+FLOP_PER_UNIT_SHARED = 0.214e9 + 0.646e9
+METRIC = "proposal-query pairs/sec (ROIAlign+AIT head+NMS)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of this rank's GPU while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # the median over samples taken while the GPU is busy: drop idle-clock samples below 60% of the top
+        busy = [x for x in sm if sm and x >= 0.6 * sm[-1]] or sm
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU implementation of the path (oracle port + the reference's own C++ CPU
+# kernels from oracle/_ref when that build is present).  Checker code used as the thing TIMED only here.
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(n_units, n_props):
+    import numpy as np
+    import torch
+    from ait_b200 import synth
+    from oracle import c_ops, head_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    refC = None
+    try:
+        from oracle import build_ref, ref_import
+        if os.path.exists(build_ref.so_path()):
+            refC = ref_import.load_ref_C()
+    except Exception:
+        refC = None
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+    sd = {k: v.clone() for k, v in head.state_dict().items()}
+    maps = torch.stack([synth.c4_map(u) for u in range(n_units)])
+    qrys = torch.stack([synth.query_feat(u) for u in range(n_units)])
+    rpn = [synth.rpn_outputs(u) for u in range(n_units)]
+
+    roi_fn = None
+    if refC is not None:                                                         # reference's own CPU kernel
+        roi_fn = lambda feat, rois: refC.roi_align_forward(feat, rois, 1.0 / 16.0, 7, 7, 0)  # noqa: E731
+
+    def step():
+        with torch.no_grad():
+            rois = torch.zeros(n_units, n_props, 5)
+            for i, (boxes, scores) in enumerate(rpn):                            # proposal_layer.py:129-166
+                order = torch.sort(scores, 0, True)[1][:PRE_NMS]
+                b = boxes[order]
+                if refC is not None:
+                    keep = refC.nms(b, scores[order], NMS_THR)[:n_props]         # reference's own CPU kernel
+                else:
+                    keep = torch.from_numpy(c_ops.nms_sorted(b.numpy(), NMS_THR, False, n_props).astype(np.int64))
+                rois[i, :, 0] = i
+                rois[i, : keep.numel(), 1:] = b[keep]
+            out = head_oracle.head_forward(sd, maps, qrys, rois, roi_align_fn=roi_fn)
+        return out["cls_prob"]
+
+    kind = "port"   # torch-CPU restatement of the reference modules (+ the reference's C++ CPU nms/roi_align when built)
+    return step, kind, ("reference C++ nms/roi_align + " if refC is not None else "") + "torch-CPU port of the head"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_units, n_props = 1, PROPOSALS
+    step, kind, what = cpu_step_factory(n_units, n_props)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_units * n_props / dt
+    sample = "%d unit x %d proposals per step (top-%d NMS + head), %s" % (n_units, n_props, PRE_NMS, what)
+    print(json.dumps({
+        "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "PASCAL-VOC test shape: 8 units x 300 proposals per GPU (configs[1]); CPU arm runs a "
+                               "bounded 1-unit sample per step"},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ait_b200 import ops, synth
+    from ait_b200.proposal import propose_rois
+    from ait_b200.sharding import gather_results
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dtype = torch.float32 if args.dtype == "tf32" else torch.bfloat16
+
+    B, P = UNITS_PER_GPU, PROPOSALS
+    units = list(range(rank * B, rank * B + B))                     # weak scaling: 8 fresh units per rank
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True, compute_dtype=dtype).to(dev)
+    h_maps = torch.stack([synth.c4_map(u) for u in units]).pin_memory()
+    h_qrys = torch.stack([synth.query_feat(u) for u in units]).pin_memory()
+    rpn = [synth.rpn_outputs(u) for u in units]
+    h_boxes = torch.stack([r[0] for r in rpn]).pin_memory()
+    h_scores = torch.stack([r[1] for r in rpn]).pin_memory()
+    d_maps, d_qrys, d_boxes, d_scores = (t.to(dev) for t in (h_maps, h_qrys, h_boxes, h_scores))
+    h_out = {k: torch.empty(s, dtype=torch.float32).pin_memory()
+             for k, s in (("rois", (B, P, 5)), ("cls", (B, P, 1)), ("bbox", (B, P, 4)))}
+    eng = head.engine()
+
+    def step_device():
+        rois, _ = propose_rois(d_boxes, d_scores, PRE_NMS, P, NMS_THR)
+        cls, bbox = eng.head_forward(d_maps, d_qrys, rois)
+        return rois, cls, bbox
+
+    def step_e2e():
+        maps = h_maps.to(dev, non_blocking=True)
+        qrys = h_qrys.to(dev, non_blocking=True)
+        boxes = h_boxes.to(dev, non_blocking=True)
+        scores = h_scores.to(dev, non_blocking=True)
+        rois, _ = propose_rois(boxes, scores, PRE_NMS, P, NMS_THR)
+        cls, bbox = eng.head_forward(maps, qrys, rois)
+        h_out["rois"].copy_(rois, non_blocking=True)
+        h_out["cls"].copy_(cls, non_blocking=True)
+        h_out["bbox"].copy_(bbox, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                   # the result is on the host
+        return h_out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        for _ in range(steps):
+            fn()
+        en.record()
+        barrier()
+        ms = st.elapsed_time(en)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.launch_count(reset=True)
+    ms_dev = timed(step_device, args.steps)
+    launches = ops.launch_count(reset=True)
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- stage breakdown and the roofline of the dominant kernel (same process, CUDA events)
+    def ev_time(fn, reps=5):
+        torch.cuda.synchronize()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        st.record()
+        for _ in range(reps):
+            fn()
+        en.record()
+        torch.cuda.synchronize()
+        return st.elapsed_time(en) / reps
+
+    rois_fixed, _ = propose_rois(d_boxes, d_scores, PRE_NMS, P, NMS_THR)
+    ms_nms = ev_time(lambda: propose_rois(d_boxes, d_scores, PRE_NMS, P, NMS_THR))
+    ms_head = ev_time(lambda: eng.head_forward(d_maps, d_qrys, rois_fixed))
+    nhwc = ops.transpose_cs(d_maps.reshape(B, 1024, -1), True, out_dtype=dtype).view(B, 38, 63, 1024)
+    ms_roi = ev_time(lambda: ops.roi_align_forward(nhwc, rois_fixed.view(-1, 5), 1 / 16.0, 7, 7, 0, token_major=True))
+    # dominant kernel: gemm_tcgen05_kernel as launched for the FFN w_1 projection (largest single launch)
+    M, N, K = B * P * 64, 2048, 512
+    a = torch.randn(M, K, device=dev).to(dtype)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(dtype)
+    o = torch.empty(M, N, device=dev, dtype=dtype)
+    bias = torch.zeros(N, device=dev)
+    from ait_b200 import _lib as L
+    ms_gemm = ev_time(lambda: ops.gemm(a, w, o, M=M, N=N, K=K, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=bias), 10)
+    del a, w, o
+    hbm, tf_burst, tf_sus, src = peaks()
+    gemm_tflops = 2.0 * M * N * K / (ms_gemm * 1e-3) / 1e12
+    peak_tf = tf_burst if args.dtype == "bf16" else tf_burst / 2.0
+    pairs = B * P
+    step_flops = pairs * FLOP_PER_PAIR + B * FLOP_PER_UNIT_SHARED
+    roi_bytes = B * (1024 * 38 * 63 * (4 if dtype == torch.float32 else 2)) + pairs * 49 * 1024 * (4 if dtype == torch.float32 else 2)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step, kind, what = cpu_step_factory(2, P)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 2 * P / dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": kind,
+                        "sample": "2 units x %d proposals, one pass after one warm-up (top-%d NMS + head); %s"
+                                  % (P, PRE_NMS, what)}
+
+    results = gather_results([(u, float(h_out["cls"][i].mean())) for i, u in enumerate(units)], world)
+    if rank == 0:
+        h2d = sum(t.numel() * t.element_size() for t in (h_maps, h_qrys, h_boxes, h_scores))
+        d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+        line = {
+            "metric": METRIC, "value": world * pairs / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "PASCAL-VOC test shape (BASELINE configs[1]): %d units x %d proposals per GPU, "
+                                   "C4 map 1024x38x63, query 1024x8x8, 21546 anchors -> top-%d -> NMS %.1f -> %d rois"
+                                   % (B, P, PRE_NMS, NMS_THR, P),
+                       "units_per_gpu": B, "proposals": P, "pairs_per_step_per_gpu": pairs,
+                       "l2": "per-step working set (~6 GB of activations streamed) >> 126 MB L2; no explicit flush",
+                       "sharding": "units split by rank, no data-path collective"},
+            "e2e": {"value": world * pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (FFN w_1: M=%d N=%d K=%d, bias+ReLU epilogue)" % (M, N, K),
+                         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+                         "traffic": None,
+                         "peak_source": "%s bf16 cuBLAS burst %.1f TFLOP/s%s" % (src, tf_burst, "" if args.dtype == "bf16" else " / 2 (tf32 runs at half the bf16 rate; no tf32 figure in MEASURED_PEAKS.json)"),
+                         "frac_of_bf16_peak": gemm_tflops / tf_burst,
+                         "head_step_tflops": step_flops / (ms_head * 1e-3) / 1e12,
+                         "head_frac_of_peak": step_flops / (ms_head * 1e-3) / 1e12 / peak_tf},
+            "roofline_roi_align": {"bound": "hbm", "achieved": roi_bytes / (ms_roi * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": roi_bytes / (ms_roi * 1e-3) / 1e9 / hbm},
+            "breakdown_ms": {"proposal_topk_nms": ms_nms, "head": ms_head, "roi_align_only": ms_roi, "ffn_w1_gemm": ms_gemm},
+            "check": {"units": len(results), "mean_cls_prob_unit0": results[0][1]},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -148,10 +148,11 @@ def roi_align(feat, rois):
     return torch.from_numpy(out)
 
 
-def head_forward(sd, non_img, non_qry, rois, dtype=torch.float32):
-    """non_img [B,1024,H,W], non_qry [B,1024,8,8], rois [B,P,5] -> dict of outputs + intermediates."""
+def head_forward(sd, non_img, non_qry, rois, dtype=torch.float32, roi_align_fn=None):
+    """non_img [B,1024,H,W], non_qry [B,1024,8,8], rois [B,P,5] -> dict of outputs + intermediates.
+    roi_align_fn: optional replacement for the C oracle (bench.py passes the reference's own CPU kernel)."""
     B, P = rois.shape[0], rois.shape[1]
-    pooled = roi_align(non_img, rois.reshape(-1, 5))                                   # :279
+    pooled = (roi_align_fn or roi_align)(non_img, rois.reshape(-1, 5))                 # :279
     ait, enc = ait_forward(_sub(sd, "transformer."), pooled, non_qry, dtype, True)     # :289
     sp, sq = sknet_forward(_sub(sd, "sk."), ait, non_qry, dtype)                       # :294
     top = _sub(sd, "RCNN_top.")
