@@ -136,7 +136,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
                  int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
-                 T* __restrict__ out) {
+                 T* __restrict__ out, int round_tf) {
   extern __shared__ float sm[];
   float* Qs = sm;                    // [64][68]
   float* Ks = Qs + kT * kQS;         // [64][68]
@@ -259,6 +259,10 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const int c = nt * 8 + 2 * t;
+    if (sizeof(T) == 4 && round_tf) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o_acc[nt][e] = to_tf32(o_acc[nt][e]);
+    }
     Act<T>::st(og + (size_t)(row0 + g) * kD + c, o_acc[nt][0]);
     Act<T>::st(og + (size_t)(row0 + g) * kD + c + 1, o_acc[nt][1]);
     Act<T>::st(og + (size_t)(row0 + g + 8) * kD + c, o_acc[nt][2]);
@@ -270,7 +274,8 @@ static constexpr size_t kAttnSmem =
     (size_t)(2 * kT * kQS + kT * kVS + 4 * 16 * kQS + 4 * kD + 2 * kD + kH * kD) * sizeof(float);
 
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
-                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream) {
+                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
+                  int round_tf) {
   AITB_REQUIRE(G > 0, "aitb_attn_core: G must be positive");
   AITB_REQUIRE(q && k && v && w_sk && b_sk && out, "aitb_attn_core: null pointer");
   AITB_REQUIRE(q_rep >= 1, "aitb_attn_core: q_rep must be >= 1");
@@ -286,7 +291,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
       attr[0] = true;
     }
     kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const float*)q, ldq, q_rep, (const float*)k, (const float*)v, ldkv,
-                                                 w_sk, b_sk, mask_mode, n_keys, (float*)out);
+                                                 w_sk, b_sk, mask_mode, n_keys, (float*)out, round_tf);
   } else if (dtype == AITB_BF16) {
     auto kern = attn_core_kernel<__nv_bfloat16>;
     if (!attr[1]) {
@@ -296,7 +301,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     }
     kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k,
                                                  (const __nv_bfloat16*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
-                                                 (__nv_bfloat16*)out);
+                                                 (__nv_bfloat16*)out, 0);
   } else {
     set_error("aitb_attn_core: bad dtype %d", dtype);
     return 1;

@@ -19,13 +19,15 @@ int nms_run(const float* boxes, const int64_t* order, int B, int n_total, int n,
 size_t topk_workspace_bytes(int B, int n_total, int n);
 int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, void* ws, size_t ws_bytes,
              cudaStream_t stream);
-int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream);
+int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream,
+                  int round_tf = 0);
 int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
-                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream);
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf = 0);
 int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
                       int pw, int sampling_ratio, float* gfeat, cudaStream_t stream);
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
-                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream);
+                  const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
+                  int round_tf = 0);
 int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat, const float* w_bbox,
                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
@@ -254,7 +256,8 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
                      int n_keys, void* ao, const void* res, int res_rep, void* out, cudaStream_t st) {
   (void)x_q_in; (void)q_groups;
   const int dt = w->dtype;
-  RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st));
+  RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
+                    w->round_tf32));
   // fc (64 -> 512, no bias) + residual + LayerNorm   (SubLayers.py:97-100)
   aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 512, out, 512, w->round_tf32);
   view_plain(d, ao, 64);
@@ -562,13 +565,13 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
   carve(b, hb, B, P, 64 * 64, dt, true, true);
 
   // a3: ROIAlign from a channels-last copy of the map, token-major output feeding enc_emb
-  RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt, B, 1024, H * W, 1, st));
+  RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt, B, 1024, H * W, 1, st));  // exact copy: ROIAlign parity
   for (int k0 = 0; k0 < bp; k0 += 32768) {
     const int kn = bp - k0 < 32768 ? bp - k0 : 32768;
     RUN(roi_align_fwd_run(hb.featT, rois + (size_t)k0 * 5, B, 1024, H, W, kn, 1.f / 16.f, 7, 7, 0, dt, 1,
-                          (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st));
+                          (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st, taps && taps->pooled ? 0 : w->round_tf32));
   }
-  RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st));
+  RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   if (taps && taps->pooled) {
     cudaError_t e = cudaMemcpyAsync(taps->pooled, hb.pooled, (size_t)bp * 49 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "pooled tap copy failed: %s", cudaGetErrorString(e));
@@ -615,9 +618,9 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
     RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (uint8_t*)hb.pooled + (size_t)g0 * 49 * 1024 * esize(dt),
-                      dt, gn, 1024, 49, 1, st));
+                      dt, gn, 1024, 49, 1, st, w->round_tf32));
   }
-  RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st));
+  RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   RUN(ait_core(w, hb, B, P, nullptr, st));
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;

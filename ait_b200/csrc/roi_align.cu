@@ -90,6 +90,12 @@ __device__ __forceinline__ float sample_coord(float start, int p, float bin, int
   return __fadd_rn(a, b);
 }
 
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
   __device__ static __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -115,7 +121,7 @@ template <> struct Vec4<__nv_bfloat16> {
 template <typename T, bool NCHW_OUT>
 __global__ void __launch_bounds__(256)
 roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
-                     int ph, int pw, int sampling_ratio, T* __restrict__ out) {
+                     int ph, int pw, int sampling_ratio, T* __restrict__ out, int round_tf) {
   __shared__ Tap xtab[kMaxPooled * kMaxGrid];
   __shared__ Tap ytab[kMaxPooled * kMaxGrid];
   extern __shared__ float stage[];  // NCHW_OUT: [128][ph*pw + 1]
@@ -162,6 +168,9 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
     acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);   // output_val /= count (:118)
     acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
     if (!lane_on) continue;
+    if (sizeof(T) == 4 && round_tf) {  // engine-internal: the consumer is a tf32 MMA (RN beats HW truncation)
+      acc.x = rn_tf32(acc.x); acc.y = rn_tf32(acc.y); acc.z = rn_tf32(acc.z); acc.w = rn_tf32(acc.w);
+    }
     if constexpr (NCHW_OUT) {
       const int s = nbins + 1;
       stage[(lane * 4 + 0) * s + bin] = acc.x;
@@ -241,7 +250,7 @@ roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ r
 // [G, C, S] -> [G, S, C] (to_cl) or back, 32x32 smem tiles, optional dtype conversion.
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc) {
+transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc, int round_tf) {
   // src [G, R, Cc] -> dst [G, Cc, R]
   __shared__ float tile[32][33];
   const int g = blockIdx.z;
@@ -256,25 +265,30 @@ transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int c = c0 + j, r = r0 + tx;
-    if (r < R && c < Cc) Act<TD>::st(d + (size_t)c * R + r, tile[tx][j]);
+    if (r < R && c < Cc) {
+      float v = tile[tx][j];
+      if (sizeof(TD) == 4 && round_tf) v = rn_tf32(v);
+      Act<TD>::st(d + (size_t)c * R + r, v);
+    }
   }
 }
 
-int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream) {
+int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream,
+                  int round_tf) {
   AITB_REQUIRE(G > 0 && C > 0 && S > 0, "aitb_transpose_cs: empty tensor");
   AITB_REQUIRE(G <= 65535, "aitb_transpose_cs: G=%d exceeds grid.z", G);
   // to_cl: src [G, C, S] -> dst [G, S, C]  => R = C, Cc = S ; else src [G, S, C] -> dst [G, C, S] => R = S, Cc = C
   const int R = to_cl ? C : S, Cc = to_cl ? S : C;
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, G);
   if (sdt == AITB_F32 && ddt == AITB_F32)
-    transpose_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, R, Cc);
+    transpose_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, R, Cc, round_tf);
   else if (sdt == AITB_F32 && ddt == AITB_BF16)
-    transpose_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, R, Cc);
+    transpose_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, R, Cc, 0);
   else if (sdt == AITB_BF16 && ddt == AITB_F32)
-    transpose_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, R, Cc);
+    transpose_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, R, Cc, 0);
   else if (sdt == AITB_BF16 && ddt == AITB_BF16)
     transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src,
-                                                                              (__nv_bfloat16*)dst, R, Cc);
+                                                                              (__nv_bfloat16*)dst, R, Cc, 0);
   else {
     set_error("aitb_transpose_cs: bad dtypes %d -> %d", sdt, ddt);
     return 1;
@@ -283,7 +297,7 @@ int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, in
 }
 
 int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
-                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream) {
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf) {
   AITB_REQUIRE(K >= 0 && B > 0, "aitb_roi_align_forward: bad sizes");
   if (K == 0) return 0;
   AITB_REQUIRE(C % 4 == 0, "aitb_roi_align_forward: C=%d must be a multiple of 4 (128-bit channel vectors)", C);
@@ -295,17 +309,17 @@ int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, 
   if (dtype == AITB_F32) {
     if (out_layout == 0)
       roi_align_fwd_kernel<float, true><<<grid, 256, smem, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
-                                                                      sampling_ratio, (float*)out);
+                                                                      sampling_ratio, (float*)out, round_tf);
     else
       roi_align_fwd_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
-                                                                    sampling_ratio, (float*)out);
+                                                                    sampling_ratio, (float*)out, round_tf);
   } else if (dtype == AITB_BF16) {
     if (out_layout == 0)
       roi_align_fwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, stream>>>(
-          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out);
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0);
     else
       roi_align_fwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(
-          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out);
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0);
   } else {
     set_error("aitb_roi_align_forward: bad dtype %d", dtype);
     return 1;

@@ -92,7 +92,8 @@ _ws_cache = {}
 def _workspace(nbytes, device, tag):
     key = (tag, device)
     buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
+    # the usable part starts at the next 1024-byte boundary: keep that slack in the reuse test
+    if buf is None or buf.numel() < int(nbytes) + 1024:
         buf = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     off = (-buf.data_ptr()) % 1024

@@ -28,7 +28,7 @@ def round_to_tf32(t):
 
 class HeadEngine:
     def __init__(self, transformer=None, sk=None, top=None, cls_score=None, bbox_pred=None,
-                 dtype=torch.float32, round_acts=False):
+                 dtype=torch.float32, round_acts=True):
         L.load()
         self.dtype = dtype
         self.dt = L.dtype_enum(dtype)

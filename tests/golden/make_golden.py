@@ -74,14 +74,18 @@ def main():
         bbox = bbox_pred(pf)
         stack = torch.cat((pf.view(B, P, -1), qf.unsqueeze(1).repeat(1, P, 1)), dim=2).view(-1, 4096)
         # Spread-calibrated RCNN_cls_score (the stock init gives cls_prob = 0.0057 +- 1e-6,
-        # which would make the 1e-3 absolute gate vacuous).  Fit on these 8 samples so that every hidden
-        # unit has zero mean / unit spread, logits differ by O(1); the weights are saved as overrides.
-        gcal = torch.Generator().manual_seed(99)
-        A = torch.randn(8, 4096, generator=gcal)
-        hdn = stack @ A.t()
-        A = A / hdn.std(dim=0, keepdim=True).t()
+        # which would make the 1e-3 absolute gate vacuous).  The first layer reads the three principal
+        # directions of these 8 feature vectors (what a trained similarity head does: weights aligned with
+        # the discriminative directions), each normalised to unit spread; logits then differ by O(1) while
+        # staying well conditioned (a random direction would amplify feature noise by |x| / |delta x|).
+        Xc = stack - stack.mean(dim=0, keepdim=True)
+        _, S, Vt = torch.linalg.svd(Xc, full_matrices=False)
+        A = torch.zeros(8, 4096)
+        for j in range(3):
+            A[j] = Vt[j] / (S[j] / 8 ** 0.5)
         b1 = -(stack @ A.t()).mean(dim=0)
-        W2 = torch.stack([-torch.ones(8), torch.ones(8)]) * torch.randn(1, 8, generator=gcal).sign() * 0.45
+        wv = torch.tensor([0.9, -0.7, 0.5, 0, 0, 0, 0, 0])
+        W2 = torch.stack([-wv, wv])
         cls_score[0].weight.copy_(A)
         cls_score[0].bias.copy_(b1)
         cls_score[1].weight.copy_(W2)
