@@ -242,6 +242,33 @@ static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool w
   }
 }
 
+// Side stream for the proposal-independent query branch (a few tiny launches that would otherwise sit
+// on the critical path).  Created lazily, one per host thread and device; fork/join with events, so the
+// caller still observes plain stream semantics on the stream it passed (also under graph capture).
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, q1 = nullptr, q2 = nullptr;
+};
+static thread_local SideStream g_side[16];
+
+static int side_stream(SideStream** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  AITB_REQUIRE(e == cudaSuccess && dev >= 0 && dev < 16, "side_stream: bad device");
+  SideStream& s = g_side[dev];
+  if (s.stream == nullptr) {
+    e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    AITB_REQUIRE(e == cudaSuccess, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.q1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.q2, cudaEventDisableTiming);
+    s.device = dev;
+  }
+  *out = &s;
+  return 0;
+}
+
 #define RUN(expr)        \
   do {                   \
     if ((expr)) return 1; \
@@ -251,10 +278,9 @@ static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool w
 // AIT: Transformer.forward (system/Models.py:231-280) on token-major inputs
 //   pooled [bp*49, 1024], qtok [B*64, 1024]  ->  hb.AIT [bp*64, 1024]
 // ---------------------------------------------------------------------------------------------
-static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* x_q_in, int q_groups, int q_rep,
-                     const void* qbuf, int ldq, const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode,
-                     int n_keys, void* ao, const void* res, int res_rep, void* out, cudaStream_t st) {
-  (void)x_q_in; (void)q_groups;
+static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* qbuf, int ldq, int q_rep,
+                     const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode, int n_keys, void* ao,
+                     const void* res, int res_rep, void* out, cudaStream_t st) {
   const int dt = w->dtype;
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32));
@@ -290,9 +316,38 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
   return gemm_run(&d2, st);
 }
 
-static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st) {
+// Decoder part that does not depend on the proposals (system/Models.py:250-253 repeats the
+// query per proposal): dec_emb + pos + LN, causal self-attention block, cross-attention query projection.
+// Computed once per unit on the side stream while the encoder runs.
+static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaStream_t st) {
   const int dt = w->dtype, eb = esize(dt), rt = w->round_tf32;
-  const int bp = B * P, R = bp * 64, RQ = B * 64;
+  const int RQ = B * 64;
+  aitb_gemm_desc d = gemm_base(dt, RQ, 512, 1024, w->dec_emb.w, 512, hb.T0, 512, rt);
+  view_plain(d, hb.qtok, 1024);
+  d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
+  d.bias = w->dec_emb.bias;
+  d.pos = w->dec_pos;
+  d.pos_rows = 64;
+  d.gamma = w->dec_ln.gamma;
+  d.beta = w->dec_ln.beta;
+  RUN(gemm_run(&d, st));
+  aitb_gemm_desc dq = gemm_base(dt, RQ, 1536, 512, w->dec_slf.w_qkv, 256, hb.QKVd, 1536, rt);
+  view_plain(dq, hb.T0, 512);
+  RUN(gemm_run(&dq, st));
+  const uint8_t* qkv = (const uint8_t*)hb.QKVd;
+  RUN(mha_block(w, w->dec_slf, qkv, 1536, 1, qkv + 512 * eb, qkv + 1024 * eb, 1536, B, 1, 64, hb.AOd, hb.T0, 1,
+                hb.T1, st));
+  aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
+  view_plain(dc, hb.T1, 512);
+  return gemm_run(&dc, st);
+}
+
+// `query_ready` (optional): event recorded on the side stream after ait_query_side; waited on before the
+// cross attention.  NULL = the query side already ran on `st`.
+static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st,
+                    cudaEvent_t query_ready) {
+  const int dt = w->dtype, eb = esize(dt), rt = w->round_tf32;
+  const int bp = B * P, R = bp * 64;
   // ---- encoder input: enc_emb (1x1 conv 1024->512 + bias) on the 49 real rows, + pos, LayerNorm
   {
     aitb_gemm_desc d = gemm_base(dt, bp * 49, 512, 1024, w->enc_emb.w, 512, hb.X1, 512, rt);
@@ -314,35 +369,17 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     view_plain(d, hb.X1, 512);
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
-    RUN(mha_block(w, w->enc_slf, nullptr, 0, 1, qkv, 1536, qkv + 512 * eb, qkv + 1024 * eb, 1536, bp, 0, 49, hb.AO,
-                  hb.X1, 1, hb.X2, st));
+    RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * eb, qkv + 1024 * eb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
+                  hb.X2, st));
   }
   RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st));
   if (enc_tap) {
     cudaError_t e = cudaMemcpyAsync(enc_tap, hb.ENC, (size_t)R * 512 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "enc tap copy failed: %s", cudaGetErrorString(e));
   }
-  // ---- decoder, proposal-independent part (once per unit): dec_emb + pos + LN, causal self-attention,
-  //      and the cross-attention query projection
-  {
-    aitb_gemm_desc d = gemm_base(dt, RQ, 512, 1024, w->dec_emb.w, 512, hb.T0, 512, rt);
-    view_plain(d, hb.qtok, 1024);
-    d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
-    d.bias = w->dec_emb.bias;
-    d.pos = w->dec_pos;
-    d.pos_rows = 64;
-    d.gamma = w->dec_ln.gamma;
-    d.beta = w->dec_ln.beta;
-    RUN(gemm_run(&d, st));
-    aitb_gemm_desc dq = gemm_base(dt, RQ, 1536, 512, w->dec_slf.w_qkv, 256, hb.QKVd, 1536, rt);
-    view_plain(dq, hb.T0, 512);
-    RUN(gemm_run(&dq, st));
-    const uint8_t* qkv = (const uint8_t*)hb.QKVd;
-    RUN(mha_block(w, w->dec_slf, nullptr, 0, 1, qkv, 1536, qkv + 512 * eb, qkv + 1024 * eb, 1536, B, 1, 64, hb.AOd,
-                  hb.T0, 1, hb.T1, st));
-    aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
-    view_plain(dc, hb.T1, 512);
-    RUN(gemm_run(&dc, st));
+  if (query_ready) {
+    cudaError_t e = cudaStreamWaitEvent(st, query_ready, 0);
+    AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
   }
   // ---- cross attention: K, V from the encoder output of each pair, Q shared by the unit's P pairs
   {
@@ -351,8 +388,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     view_plain(d, hb.ENC, 512);
     RUN(gemm_run(&d, st));
     const uint8_t* kv = (const uint8_t*)hb.KVc;
-    RUN(mha_block(w, w->dec_enc, nullptr, 0, P, hb.Qc, 512, kv, kv + 512 * eb, 1024, bp, 0, 49, hb.AO, hb.T1, P,
-                  hb.D1, st));
+    RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * eb, 1024, bp, 0, 49, hb.AO, hb.T1, P, hb.D1, st));
   }
   RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh, hb.DEC, st));
   // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
@@ -576,27 +612,44 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
     cudaError_t e = cudaMemcpyAsync(taps->pooled, hb.pooled, (size_t)bp * 49 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "pooled tap copy failed: %s", cudaGetErrorString(e));
   }
+  // query branch on the side stream: decoder self-attention block, SKNet(query), RCNN_top(query), pooling
+  SideStream* ss = nullptr;
+  RUN(side_stream(&ss));
+  float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
+  {
+    cudaError_t e = cudaEventRecord(ss->fork, st);
+    AITB_REQUIRE(e == cudaSuccess, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+    AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+    RUN(ait_query_side(w, hb, B, ss->stream));
+    cudaEventRecord(ss->q1, ss->stream);
+    RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, ss->stream));
+    void* yq = nullptr;
+    RUN(layer4(w, hb.SKq, B, hb.qc1, hb.qc2, hb.qds, hb.qy0, hb.qy1, &yq, ss->stream));
+    RUN(pool_heads_run(yq, dt, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, qfeat, nullptr,
+                       nullptr, ss->stream));
+    cudaEventRecord(ss->q2, ss->stream);
+  }
   // a5-a9: AIT
-  RUN(ait_core(w, hb, B, P, taps ? taps->enc_out : nullptr, st));
+  RUN(ait_core(w, hb, B, P, taps ? taps->enc_out : nullptr, st, ss->q1));
   if (taps && taps->ait_out) {
     cudaError_t e = cudaMemcpyAsync(taps->ait_out, hb.AIT, (size_t)bp * 64 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "ait tap copy failed: %s", cudaGetErrorString(e));
   }
-  // a10: SKNet (separate weights for the proposal and the query branch)
+  // a10: SKNet, proposal branch
   RUN(sk_block(w, w->sk_props, hb.AIT, bp, hb.SK, st));
-  RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, st));
   if (taps && taps->sk_out) {
     cudaError_t e = cudaMemcpyAsync(taps->sk_out, hb.SK, (size_t)bp * 64 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "sk tap copy failed: %s", cudaGetErrorString(e));
   }
-  // a11: RCNN_top on both branches
-  void *ytop = nullptr, *yq = nullptr;
-  RUN(layer4(w, hb.SKq, B, hb.qc1, hb.qc2, hb.qds, hb.qy0, hb.qy1, &yq, st));
+  // a11: RCNN_top, proposal branch
+  void* ytop = nullptr;
   RUN(layer4(w, hb.SK, bp, hb.c1, hb.c2, hb.ds, hb.y0, hb.y1, &ytop, st));
-  // a12: spatial mean + bbox / similarity heads
-  float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
-  RUN(pool_heads_run(yq, dt, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, qfeat, nullptr,
-                     nullptr, st));
+  // a12: spatial mean + bbox / similarity heads (join the query branch first)
+  {
+    cudaError_t e = cudaStreamWaitEvent(st, ss->q2, 0);
+    AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+  }
   RUN(pool_heads_run(ytop, dt, bp, P, qfeat, w->w_bbox, w->b_bbox, w->w_cls1, w->b_cls1, w->w_cls2, w->b_cls2,
                      taps ? taps->feat : nullptr, bbox_pred, cls_prob, st));
   return 0;
@@ -621,7 +674,8 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
                       dt, gn, 1024, 49, 1, st, w->round_tf32));
   }
   RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
-  RUN(ait_core(w, hb, B, P, nullptr, st));
+  RUN(ait_query_side(w, hb, B, st));
+  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr));
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
     RUN(transpose_run((const uint8_t*)hb.AIT + (size_t)g0 * 64 * 1024 * esize(dt), dt, out_nchw + (size_t)g0 * 1024 * 64,

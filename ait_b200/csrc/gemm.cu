@@ -69,7 +69,8 @@ struct GemmCfg {
   static constexpr int kAccStages = (BLOCK_N == 512) ? 1 : 2;
   static constexpr int kUmmaN = (BLOCK_N > 256) ? 256 : BLOCK_N;
   static constexpr int kTmemCols = (BLOCK_N * kAccStages < 32) ? 32 : BLOCK_N * kAccStages;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    4 * 4096 /*epilogue staging, one 32x128 B tile per warp*/;
 };
 
 template <typename T, int BLOCK_N>
@@ -180,9 +181,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
+    // Each thread owns one accumulator row (tcgen05.ld 32x32b).  Global traffic never uses that
+    // row-per-thread shape: 32-column chunks go through a per-warp XOR-swizzled staging tile so that
+    // every global load/store instruction covers whole contiguous row segments (4 rows x 128 B for
+    // fp32, 8 rows x 64 B for bf16) -- fully coalesced, conflict-free in shared memory.
+    constexpr int kRowBytes = 32 * (int)sizeof(T);       // one staged row: 32 columns
+    constexpr int kCh = kRowBytes / 16;                  // 16-byte pieces per row (8 | 4)
+    constexpr int kRpi = 32 / kCh;                       // rows covered by one warp instruction (4 | 8)
+    constexpr int kIt = kCh;                             // instructions per 32-row chunk (8 | 4)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    T* out = reinterpret_cast<T*>(p.out);
+    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + q * 4096;
+    const int piece = lane % kCh;
+    const int srow0 = lane / kCh;
+    auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
     const T* res = reinterpret_cast<const T*>(p.res);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++lt) {
@@ -190,18 +202,81 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int nt = tile - mt * p.n_tiles;
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
-      const int m = mt * kBlockM + row_in_tile;
-      const bool valid = m < p.M;
-      const int mm = valid ? m : 0;
-      const int out_row = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
-      int res_row = 0;
-      if (p.flags & AITB_EPI_RES)
-        res_row = ((out_row / p.res_div) / p.res_rep) * p.res_div + (out_row % p.res_div);
-      const int pos_row = (p.flags & AITB_EPI_POS) ? (out_row % p.pos_rows) : 0;
       const int n0 = nt * BLOCK_N;
-      T* orow = out + (size_t)out_row * p.ldo + n0;
-      const T* rrow = res + (size_t)res_row * p.ldr + n0;
-      const float* prow = p.pos + (size_t)pos_row * p.N + n0;
+      // rows this lane serves in the coalesced phases
+      T* optr[kIt];
+      const T* rptr[kIt];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int m = mt * kBlockM + q * 32 + it * kRpi + srow0;
+        const bool ok = m < p.M;
+        const int mm = ok ? m : 0;
+        const int orow = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
+        optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
+        int rrow = 0;
+        if (p.flags & AITB_EPI_RES) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
+        rptr[it] = res + (size_t)rrow * p.ldr + n0 + piece * (16 / (int)sizeof(T));
+        vmask |= (ok ? 1u : 0u) << it;
+      }
+      // this thread's own row (for the fp32 positional table)
+      const int m_own = mt * kBlockM + row_in_tile;
+      const int mm_own = m_own < p.M ? m_own : 0;
+      const int orow_own = (mm_own / p.rows_in) * p.rows_out + (mm_own % p.rows_in);
+      const float* prow = p.pos + (size_t)((p.flags & AITB_EPI_POS) ? (orow_own % p.pos_rows) : 0) * p.N + n0;
+
+      // coalesced global -> this thread's 32 values of its row (columns c0 .. c0+31)
+      auto stage_load = [&](auto ptrs, int c0, float (&r)[32]) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int sr = it * kRpi + srow0;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if ((vmask >> it) & 1u) val = *reinterpret_cast<const uint4*>(ptrs[it] + c0);
+          *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kCh; ++j) {
+          const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16);
+          if constexpr (sizeof(T) == 4) {
+            r[4 * j + 0] = __uint_as_float(x.x); r[4 * j + 1] = __uint_as_float(x.y);
+            r[4 * j + 2] = __uint_as_float(x.z); r[4 * j + 3] = __uint_as_float(x.w);
+          } else {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              r[8 * j + 2 * e] = f.x;
+              r[8 * j + 2 * e + 1] = f.y;
+            }
+          }
+        }
+        __syncwarp();
+      };
+      // this thread's 32 values -> coalesced global store
+      auto stage_store = [&](int c0, const float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < kCh; ++j) {
+          uint4 x;
+          if constexpr (sizeof(T) == 4) {
+            x = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                           __float_as_uint(v[4 * j + 3]));
+          } else {
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+          }
+          *reinterpret_cast<uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16) = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int sr = it * kRpi + srow0;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
+          if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val;
+        }
+        __syncwarp();
+      };
 
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
@@ -213,51 +288,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
           tmem_ld_wait();
-          if (valid) {
+          float v[32];
 #pragma unroll
-            for (int j8 = 0; j8 < 32; j8 += 8) {
-              float v[8];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.flags & AITB_EPI_BIAS) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j8 + j]);
-              if (p.flags & AITB_EPI_BIAS) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + n0 + c0 + j8 + j);
-              }
-              if (p.flags & AITB_EPI_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (p.flags & AITB_EPI_SQUARE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
-              }
-              if (p.flags & AITB_EPI_RES) {
-                float r[8];
-                ld8(rrow + c0 + j8, r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += r[j];
-              }
-              if (p.flags & AITB_EPI_POS) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += __ldg(prow + c0 + j8 + j);
-              }
-              if (p.flags & AITB_EPI_ACCUM) {
-                float r[8];
-                ld8(orow + c0 + j8, r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += r[j];
-              }
-              if (p.flags & AITB_EPI_RES_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (sizeof(T) == 4 && p.round_tf32) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = round_tf32(v[j]);
-              }
-              st8(orow + c0 + j8, v);
-            }
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
           }
+          if (p.flags & AITB_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.flags & AITB_EPI_SQUARE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+          }
+          if (p.flags & AITB_EPI_RES) {
+            float r[32];
+            stage_load(rptr, c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+          if (p.flags & AITB_EPI_POS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(prow + c0 + j);
+          }
+          if (p.flags & AITB_EPI_ACCUM) {
+            float r[32];
+            stage_load(optr, c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+          if (p.flags & AITB_EPI_RES_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (sizeof(T) == 4 && p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+          stage_store(c0, v);
         }
       } else {
         // ---- full-row LayerNorm: the CTA's accumulator holds all N = BLOCK_N columns of the row
@@ -267,30 +337,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
           tmem_ld_wait();
+          float v[32];
 #pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            float v[8];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.flags & AITB_EPI_BIAS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j8 + j]);
-            if (p.flags & AITB_EPI_BIAS) {
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.flags & AITB_EPI_RES) {
+            float r[32];
+            stage_load(rptr, c0, r);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + c0 + j8 + j);
-            }
-            if (p.flags & AITB_EPI_RES) {
-              float r[8];
-              ld8(rrow + c0 + j8, r);
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+          if (p.flags & AITB_EPI_POS) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += r[j];
-            }
-            if (p.flags & AITB_EPI_POS) {
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(prow + c0 + j);
+          }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += __ldg(prow + c0 + j8 + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              sum += v[j];
-              raw[j8 + j] = __float_as_uint(v[j]);
-            }
+          for (int j = 0; j < 32; ++j) {
+            sum += v[j];
+            raw[j] = __float_as_uint(v[j]);
           }
           tmem_st32(t_row + c0, raw);
         }
@@ -314,20 +381,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
           tmem_ld_wait();
-          if (valid) {
+          float v[32];
 #pragma unroll
-            for (int j8 = 0; j8 < 32; j8 += 8) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int n = c0 + j8 + j;
-                v[j] = (__uint_as_float(raw[j8 + j]) - mean) * rstd * __ldg(p.gamma + n) +
-                       __ldg(p.beta + n);
-                if (sizeof(T) == 4 && p.round_tf32) v[j] = round_tf32(v[j]);
-              }
-              st8(orow + c0 + j8, v);
-            }
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (__uint_as_float(raw[j]) - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
+            if (sizeof(T) == 4 && p.round_tf32) v[j] = round_tf32(v[j]);
           }
+          stage_store(c0, v);
         }
       }
       tc_fence_before();
