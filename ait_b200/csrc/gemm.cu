@@ -55,6 +55,12 @@ struct GemmKParams {
   int round_tf32;
 };
 
+__device__ __forceinline__ uint4 ld_global_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -226,13 +232,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float* prow = p.pos + (size_t)((p.flags & AITB_EPI_POS) ? (orow_own % p.pos_rows) : 0) * p.N + n0;
 
       // coalesced global -> this thread's 32 values of its row (columns c0 .. c0+31)
-      auto stage_load = [&](auto ptrs, int c0, float (&r)[32]) {
+      // issue this lane's share of a coalesced 32-row x 32-column global read (no dependent use yet)
+      auto issue_loads = [&](const T* const* ptrs, int c0, uint4 (&val)[kIt]) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          val[it] = make_uint4(0u, 0u, 0u, 0u);
+          if ((vmask >> it) & 1u) val[it] = ld_global_v4(ptrs[it] + c0);
+        }
+      };
+      // ... and turn it into this thread's 32 values of its own row through the swizzled staging tile
+      auto exchange = [&](const uint4 (&val)[kIt], float (&r)[32]) {
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
           const int sr = it * kRpi + srow0;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
-          if ((vmask >> it) & 1u) val = *reinterpret_cast<const uint4*>(ptrs[it] + c0);
-          *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val;
+          *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val[it];
         }
         __syncwarp();
 #pragma unroll
@@ -253,6 +266,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
       };
+      // vectorised read-only loads of per-column parameters (bias / gamma / beta / pos): 8 x 128-bit
+      auto add_vec = [&](const float* src, float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(src) + j);
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      };
       // this thread's 32 values -> coalesced global store
       auto stage_store = [&](int c0, const float (&v)[32]) {
 #pragma unroll
@@ -269,12 +290,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           *reinterpret_cast<uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16) = x;
         }
         __syncwarp();
+        uint4 val[kIt];
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
           const int sr = it * kRpi + srow0;
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
-          if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val;
+          val[it] = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
         }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it)
+          if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val[it];
         __syncwarp();
       };
 
@@ -283,18 +307,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
 
       if ((p.flags & AITB_EPI_LN) == 0) {
+        // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead
+        const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
+        const bool aux_acc = !aux_res && (p.flags & AITB_EPI_ACCUM) != 0;
+        uint4 pre[kIt];
+        if (aux_res) issue_loads(rptr, 0, pre);
+        if (aux_acc) issue_loads(optr, 0, pre);
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
+          uint4 cur[kIt];
+          if (aux_res || aux_acc) {
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
+            if (c0 + 32 < BLOCK_N) {
+              if (aux_res) issue_loads(rptr, c0 + 32, pre); else issue_loads(optr, c0 + 32, pre);
+            }
+          }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.flags & AITB_EPI_BIAS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
-          }
+          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
           if (p.flags & AITB_EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -303,19 +338,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
           }
-          if (p.flags & AITB_EPI_RES) {
+          if (aux_res) {
             float r[32];
-            stage_load(rptr, c0, r);
+            exchange(cur, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += r[j];
           }
-          if (p.flags & AITB_EPI_POS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(prow + c0 + j);
-          }
+          if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
           if (p.flags & AITB_EPI_ACCUM) {
             float r[32];
-            stage_load(optr, c0, r);
+            if (!aux_acc) issue_loads(optr, c0, cur);   // RES and ACCUM together: second stream not prefetched
+            exchange(cur, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += r[j];
           }
@@ -332,28 +365,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
         // ---- full-row LayerNorm: the CTA's accumulator holds all N = BLOCK_N columns of the row
         float sum = 0.f;
+        const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
+        uint4 pre[kIt];
+        if (aux_res) issue_loads(rptr, 0, pre);
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
+          uint4 cur[kIt];
+          if (aux_res) {
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
+            if (c0 + 32 < BLOCK_N) issue_loads(rptr, c0 + 32, pre);
+          }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.flags & AITB_EPI_BIAS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
-          }
-          if (p.flags & AITB_EPI_RES) {
+          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + c0, v);
+          if (aux_res) {
             float r[32];
-            stage_load(rptr, c0, r);
+            exchange(cur, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += r[j];
           }
-          if (p.flags & AITB_EPI_POS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(prow + c0 + j);
-          }
+          if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             sum += v[j];
@@ -383,9 +419,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = (__uint_as_float(raw[j]) - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
-            if (sizeof(T) == 4 && p.round_tf32) v[j] = round_tf32(v[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0) + j);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0) + j);
+            v[4 * j + 0] = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * g4.x + b4.x;
+            v[4 * j + 1] = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
+            v[4 * j + 2] = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
+            v[4 * j + 3] = (__uint_as_float(raw[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+          }
+          if (sizeof(T) == 4 && p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
           }
           stage_store(c0, v);
         }
