@@ -95,6 +95,51 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// thread-block cluster / distributed shared memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> the same offset in CTA `rank`'s window of the cluster shared address space
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t caddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(caddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {  // remote arrive, releases prior DSMEM stores
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tiled mode, global -> shared, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

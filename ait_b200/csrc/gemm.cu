@@ -76,10 +76,14 @@ struct GemmCfg {
   static constexpr int kUmmaN = (BLOCK_N > 256) ? 256 : BLOCK_N;
   static constexpr int kTmemCols = (BLOCK_N * kAccStages < 32) ? 32 : BLOCK_N * kAccStages;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    4 * 4096 /*epilogue staging, one 32x128 B tile per warp*/;
+                                    2048 /*LN row statistics*/ + 4 * 4096 /*epilogue staging, one 32x128 B tile per warp*/;
 };
 
-template <typename T, int BLOCK_N>
+// CL = true: "cluster LayerNorm" variant.  A 2-CTA cluster shares one 128-row m-tile; CTA rank r owns the
+// output columns [256 r, 256 r + 256) of the N = 512 row (BLOCK_N = 256 machinery: 4-stage ring, double-
+// buffered accumulator).  The LayerNorm row statistics are combined across the two CTAs through
+// distributed shared memory (partial sum + centred M2 per row, Chan's parallel-variance formula).
+template <typename T, int BLOCK_N, bool CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKParams p) {
@@ -94,7 +98,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = bars + kStages;       // [kStages]
   uint64_t* acc_full = bars + 2 * kStages;    // [kAcc]
   uint64_t* acc_empty = acc_full + kAcc;      // [kAcc]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+  uint64_t* stats_full = acc_empty + kAcc;    // [kAcc]  (CL only) peer's row statistics have landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stats_full + kAcc);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,6 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < kAcc; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 128);
+      mbar_init(&stats_full[s], 128);
     }
     fence_mbar_init();
   }
@@ -118,19 +124,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL) cluster_sync_all();  // peer's mbarriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  // tile schedule: plain = tiles round-robin over CTAs (n fastest); CL = m-tiles round-robin over clusters
+  const uint32_t cta_rank = CL ? cluster_ctarank() : 0u;
+  const int t_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_tiles_total = CL ? p.m_tiles : p.m_tiles * p.n_tiles;
   const int iters_per_tile = p.taps * p.k_chunks;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step) {
+        const int mt = CL ? tile : tile / p.n_tiles;
+        const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
         const int a_c_base = nt * p.a_group_c;
         for (int tap = 0; tap < p.taps; ++tap) {
           int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
@@ -157,7 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, kBlockM, Cfg::kUmmaN);
       uint32_t it = 0;
       uint32_t lt = 0;  // local tile counter
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++lt) {
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
         const uint32_t as = lt % kAcc;
         const uint32_t aph = (lt / kAcc) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
@@ -197,15 +208,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kIt = kCh;                             // instructions per 32-row chunk (8 | 4)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + q * 4096;
+    float2* stats = reinterpret_cast<float2*>(smem + kStages * Cfg::kStageBytes + 256);   // [kAcc][128] (CL)
+    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + 2048 + q * 4096;
     const int piece = lane % kCh;
     const int srow0 = lane / kCh;
     auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
     const T* res = reinterpret_cast<const T*>(p.res);
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++lt) {
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
+    for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
+      const int mt = CL ? tile : tile / p.n_tiles;
+      const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const int n0 = nt * BLOCK_N;
@@ -363,7 +375,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stage_store(c0, v);
         }
       } else {
-        // ---- full-row LayerNorm: the CTA's accumulator holds all N = BLOCK_N columns of the row
+        // ---- full-row LayerNorm.  Plain: the CTA's accumulator holds all N = BLOCK_N columns of the row.
+        //      CL: it holds half of the row; partial (sum, M2) are exchanged with the peer CTA via DSMEM.
         float sum = 0.f;
         const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
         uint4 pre[kIt];
@@ -382,7 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + c0, v);
+          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
           if (aux_res) {
             float r[32];
             exchange(cur, r);
@@ -398,7 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_st32(t_row + c0, raw);
         }
         tmem_st_wait();
-        const float mean = sum * (1.f / BLOCK_N);
+        float mean = sum * (1.f / BLOCK_N);
         float ssq = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -411,7 +424,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ssq += d * d;
           }
         }
-        const float rstd = rsqrtf(ssq * (1.f / BLOCK_N) + p.eps);
+        float n_cols = (float)BLOCK_N;
+        if constexpr (CL) {
+          // send (sum, M2) of my half-row to the peer, wait for the peer's, combine (Chan et al.)
+          const uint32_t peer = cta_rank ^ 1u;
+          st_cluster_f32x2(mapa_u32(smem_u32(&stats[as * 128 + row_in_tile]), peer), sum, ssq);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&stats_full[as]), peer));
+          mbar_wait_cluster(&stats_full[as], aph);
+          const float2 ps = stats[as * 128 + row_in_tile];
+          const float mean_p = ps.x * (1.f / BLOCK_N);
+          const float mean_all = (sum + ps.x) * (0.5f / BLOCK_N);
+          const float da = mean - mean_all, db = mean_p - mean_all;
+          ssq = ssq + ps.y + (float)BLOCK_N * (da * da + db * db);
+          mean = mean_all;
+          n_cols = 2.f * BLOCK_N;
+        }
+        const float rstd = rsqrtf(ssq / n_cols + p.eps);
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t raw[32];
@@ -420,8 +448,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0) + j);
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + c0) + j);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + c0) + j);
             v[4 * j + 0] = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * g4.x + b4.x;
             v[4 * j + 1] = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
             v[4 * j + 2] = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
@@ -441,6 +469,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL) cluster_sync_all();  // the peer may still be writing row statistics into my smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -507,12 +536,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <typename T, int BLOCK_N>
+template <typename T, int BLOCK_N, bool CL>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<T, BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<T, BLOCK_N, CL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -521,10 +550,34 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     attr_set = true;
   }
-  const int tiles = kp.m_tiles * kp.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, kp);
-  return check_launch("gemm_tcgen05_kernel");
+  if constexpr (CL) {
+    const int clusters = kp.m_tiles < num_sms() / 2 ? kp.m_tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp);
+    if (e != cudaSuccess) {
+      set_error("gemm_tcgen05_kernel<cluster LN>: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return 1;
+    }
+    return check_launch("gemm_tcgen05_kernel<cluster LN>");
+  } else {
+    const int tiles = kp.m_tiles * kp.n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, kp);
+    return check_launch("gemm_tcgen05_kernel");
+  }
 }
 
 int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
@@ -544,6 +597,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d->a_m_dim == 1 || d->a_m_dim == 3, "aitb_gemm: a_m_dim must be 1 or 3");
   AITB_REQUIRE((d->flags & AITB_EPI_LN) == 0 || (d->block_n == 512 && d->N == 512),
                "aitb_gemm: the LayerNorm epilogue needs block_n == N == 512");
+  AITB_REQUIRE((d->flags & AITB_EPI_LN) != 0 || d->block_n != 512, "aitb_gemm: block_n 512 is the LayerNorm variant");
   AITB_REQUIRE(d->rows_in > 0 && d->rows_out >= d->rows_in, "aitb_gemm: bad row remap %d->%d", d->rows_in,
                d->rows_out);
   AITB_REQUIRE(d->ldo % 8 == 0, "aitb_gemm: ldo must be a multiple of 8 elements");
@@ -562,6 +616,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   const uint64_t wdims[2] = {(uint64_t)d->taps * d->k_per_tap, (uint64_t)d->N};
   const uint64_t wstr[1] = {(uint64_t)d->taps * d->k_per_tap * eb};
   const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(d->block_n > 256 ? 256 : d->block_n)};
+  const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
   if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
 
   GemmKParams kp;
@@ -579,7 +634,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     kp.tap_dy[i] = d->tap_dy[i];
   }
   kp.m_tiles = (d->M + kBlockM - 1) / kBlockM;
-  kp.n_tiles = d->N / d->block_n;
+  kp.n_tiles = cluster_ln ? 2 : d->N / d->block_n;
   kp.flags = d->flags;
   kp.out = d->out;
   kp.ldo = d->ldo;
@@ -597,14 +652,16 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.eps = d->eps;
   kp.round_tf32 = d->round_tf32;
 
-#define AITB_DISPATCH(BN)                                                              \
-  (d->dtype == AITB_F32 ? launch_gemm<float, BN>(tmA, tmB, kp, stream)                 \
-                        : launch_gemm<__nv_bfloat16, BN>(tmA, tmB, kp, stream))
+#define AITB_DISPATCH(BN)                                                                     \
+  (d->dtype == AITB_F32 ? launch_gemm<float, BN, false>(tmA, tmB, kp, stream)                 \
+                        : launch_gemm<__nv_bfloat16, BN, false>(tmA, tmB, kp, stream))
+  if (cluster_ln)
+    return d->dtype == AITB_F32 ? launch_gemm<float, 256, true>(tmA, tmB, kp, stream)
+                                : launch_gemm<__nv_bfloat16, 256, true>(tmA, tmB, kp, stream);
   switch (d->block_n) {
     case 64: return AITB_DISPATCH(64);
     case 128: return AITB_DISPATCH(128);
     case 256: return AITB_DISPATCH(256);
-    case 512: return AITB_DISPATCH(512);
   }
 #undef AITB_DISPATCH
   set_error("aitb_gemm: unreachable");
