@@ -48,6 +48,28 @@ __global__ void nms_gather_kernel(const float4* __restrict__ boxes, const int64_
   sorted[(size_t)b * n + i] = boxes[(size_t)b * n_total + src];
 }
 
+// iou_legacy(a, b) > thr, decided without the IEEE division unless the quotient is within 2^-18 of thr:
+// disjoint boxes have inter == 0 (quotient 0 or NaN, never > thr >= 0); otherwise compare inter with
+// thr * den using a guard band and fall back to the exact division only inside it.
+__device__ __forceinline__ bool iou_gt(const float4 a, float sa, const float4 b, float sb, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  if (thr >= 0.f && inter == 0.f) return false;
+  const float den = __fsub_rn(__fadd_rn(sa, sb), inter);
+  const float t = __fmul_rn(thr, den);
+  if (thr >= 0.f && den > 0.f) {
+    if (inter > __fmul_rn(t, 1.000004f)) return true;
+    if (inter < __fmul_rn(t, 0.999996f)) return false;
+  }
+  return __fdiv_rn(inter, den) > thr;
+}
+__device__ __forceinline__ float area_legacy(const float4 a) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+}
+
 // grid (col_blk, row_blk, B), 64 threads.  mask[b][row][col_blk] bit j = IoU(row, col_blk*64+j) > thr
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4* __restrict__ sorted, u64* __restrict__ mask, int n, int nblk, float thr) {
@@ -55,17 +77,23 @@ nms_mask_kernel(const float4* __restrict__ sorted, u64* __restrict__ mask, int n
   if (col_blk < row_blk) return;  // lower triangle is never read by the scan
   const float4* bx = sorted + (size_t)b * n;
   __shared__ float4 cols[64];
+  __shared__ float col_area[64];
   const int col_size = min(n - col_blk * 64, 64);
   const int row_size = min(n - row_blk * 64, 64);
-  if ((int)threadIdx.x < col_size) cols[threadIdx.x] = bx[col_blk * 64 + threadIdx.x];
+  if ((int)threadIdx.x < col_size) {
+    const float4 c = bx[col_blk * 64 + threadIdx.x];
+    cols[threadIdx.x] = c;
+    col_area[threadIdx.x] = area_legacy(c);
+  }
   __syncthreads();
   if ((int)threadIdx.x < row_size) {
     const int row = row_blk * 64 + threadIdx.x;
     const float4 me = bx[row];
+    const float my_area = area_legacy(me);
     u64 t = 0;
     const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
     for (int j = start; j < col_size; ++j)
-      if (iou_legacy(me, cols[j]) > thr) t |= 1ULL << j;
+      if (iou_gt(me, my_area, cols[j], col_area[j], thr)) t |= 1ULL << j;
     mask[((size_t)b * n + row) * nblk + col_blk] = t;
   }
 }

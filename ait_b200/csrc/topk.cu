@@ -7,9 +7,10 @@
 //   1. 4096-bin histogram of the 12 most significant bits of an order-preserving key, find the
 //      threshold bin that contains the n-th largest score;
 //   2. compact the candidates (bin >= threshold) -- order of compaction is irrelevant;
-//   3. exact rank of every candidate by counting (shared-memory tiles); rank < n scatters the
-//      original index to order[rank].  Ranks are a total order (key desc, index asc), so the
-//      output never depends on atomics ordering.
+//   3. sort the candidates, packed as (key << 32 | ~index) so that one 64-bit comparison is the total
+//      order (score desc, index asc): a bitonic network in shared memory (one CTA per image, up to
+//      16384 candidates), or -- beyond that -- exact rank by counting.  Either way the output never
+//      depends on the (arbitrary) compaction order.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -53,55 +54,82 @@ topk_hist_kernel(const float* __restrict__ scores, int n_total, int n, int32_t* 
   }
 }
 
+// candidates are packed as (order_key << 32) | ~index: one 64-bit descending order = score desc, index asc
 __global__ void __launch_bounds__(256)
 topk_compact_kernel(const float* __restrict__ scores, int n_total, const int32_t* __restrict__ thr_bin,
-                    int32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_key, int32_t* __restrict__ cand_idx) {
+                    int32_t* __restrict__ cand_count, unsigned long long* __restrict__ cand) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_total) return;
   const uint32_t key = order_key(scores[(size_t)b * n_total + i]);
   if ((int)(key >> 20) >= thr_bin[b]) {
     const int pos = atomicAdd(&cand_count[b], 1);
-    cand_key[(size_t)b * n_total + pos] = key;
-    cand_idx[(size_t)b * n_total + pos] = i;
+    cand[(size_t)b * n_total + pos] = ((unsigned long long)key << 32) | (unsigned long long)(~(uint32_t)i);
   }
 }
 
+// nc <= kSortMax: bitonic sort of the candidates in shared memory, one CTA per image.
+static constexpr int kSortMax = 16384;
+
+__global__ void __launch_bounds__(1024)
+topk_bitonic_kernel(const int32_t* __restrict__ cand_count, const unsigned long long* __restrict__ cand, int n_total,
+                    int n, int64_t* __restrict__ order) {
+  extern __shared__ unsigned long long sk[];
+  const int b = blockIdx.x;
+  const int nc = cand_count[b];
+  if (nc > kSortMax) return;  // handled by topk_rank_kernel
+  int S = 1024;
+  while (S < nc) S <<= 1;
+  const unsigned long long* c = cand + (size_t)b * n_total;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sk[i] = i < nc ? c[i] : 0ULL;
+  __syncthreads();
+  for (int k = 2; k <= S; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (S >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+        const int hi = lo | j;
+        const bool desc = (lo & k) == 0;                        // overall descending order
+        const unsigned long long a = sk[lo], d = sk[hi];
+        if ((a < d) == desc) {
+          sk[lo] = d;
+          sk[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < n; r += blockDim.x) order[(size_t)b * n + r] = (int64_t)(~(uint32_t)sk[r]);
+}
+
+// fallback for nc > kSortMax: exact rank by counting over shared-memory tiles
 __global__ void __launch_bounds__(256)
-topk_rank_kernel(const int32_t* __restrict__ cand_count, const uint32_t* __restrict__ cand_key,
-                 const int32_t* __restrict__ cand_idx, int n_total, int n, int64_t* __restrict__ order) {
-  __shared__ uint32_t tk[1024];
-  __shared__ int32_t ti[1024];
+topk_rank_kernel(const int32_t* __restrict__ cand_count, const unsigned long long* __restrict__ cand, int n_total,
+                 int n, int64_t* __restrict__ order) {
+  __shared__ unsigned long long tk[1024];
   const int b = blockIdx.y;
   const int nc = cand_count[b];
-  if ((int)(blockIdx.x * blockDim.x) >= nc) return;  // uniform per CTA
-  const uint32_t* ck = cand_key + (size_t)b * n_total;
-  const int32_t* ci = cand_idx + (size_t)b * n_total;
+  if (nc <= kSortMax || (int)(blockIdx.x * blockDim.x) >= nc) return;  // uniform per CTA
+  const unsigned long long* c = cand + (size_t)b * n_total;
   const int me = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = me < nc;
-  const uint32_t mk = live ? ck[me] : 0u;
-  const int32_t mi = live ? ci[me] : 0;
+  const unsigned long long mk = live ? c[me] : 0ULL;
   int rank = 0;
   for (int t0 = 0; t0 < nc; t0 += 1024) {
     __syncthreads();
-    for (int j = threadIdx.x; j < 1024; j += blockDim.x) {
-      const bool in = t0 + j < nc;
-      tk[j] = in ? ck[t0 + j] : 0u;
-      ti[j] = in ? ci[t0 + j] : 0x7fffffff;
-    }
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tk[j] = t0 + j < nc ? c[t0 + j] : 0ULL;
     __syncthreads();
     const int lim = min(1024, nc - t0);
 #pragma unroll 8
-    for (int j = 0; j < lim; ++j) rank += (tk[j] > mk) || (tk[j] == mk && ti[j] < mi);
+    for (int j = 0; j < lim; ++j) rank += tk[j] > mk;
   }
-  if (live && rank < n) order[(size_t)b * n + rank] = mi;
+  if (live && rank < n) order[(size_t)b * n + rank] = (int64_t)(~(uint32_t)mk);
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t topk_workspace_bytes(int B, int n_total, int n) {
   (void)n;
-  return al256((size_t)B * 4) * 2 + al256((size_t)B * n_total * 4) * 2;
+  return al256((size_t)B * 4) * 2 + al256((size_t)B * n_total * 8);
 }
 
 int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, void* ws, size_t ws_bytes,
@@ -115,17 +143,25 @@ int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, voi
   w += al256((size_t)B * 4);
   int32_t* cand_count = reinterpret_cast<int32_t*>(w);
   w += al256((size_t)B * 4);
-  uint32_t* cand_key = reinterpret_cast<uint32_t*>(w);
-  w += al256((size_t)B * n_total * 4);
-  int32_t* cand_idx = reinterpret_cast<int32_t*>(w);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(w);
   topk_hist_kernel<<<B, 1024, 0, stream>>>(scores, n_total, n, thr_bin, cand_count);
   if (check_launch("topk_hist_kernel")) return 1;
-  topk_compact_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(scores, n_total, thr_bin, cand_count,
-                                                                         cand_key, cand_idx);
+  topk_compact_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(scores, n_total, thr_bin, cand_count, cand);
   if (check_launch("topk_compact_kernel")) return 1;
-  topk_rank_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(cand_count, cand_key, cand_idx, n_total, n,
-                                                                      order);
-  return check_launch("topk_rank_kernel");
+  static bool attr_set = false;
+  const int smem = kSortMax * 8;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(topk_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    AITB_REQUIRE(e == cudaSuccess, "aitb_topk_desc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  topk_bitonic_kernel<<<B, 1024, smem, stream>>>(cand_count, cand, n_total, n, order);
+  if (check_launch("topk_bitonic_kernel")) return 1;
+  if (n_total > kSortMax) {  // only then can an image have more candidates than the smem sort holds
+    topk_rank_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(cand_count, cand, n_total, n, order);
+    if (check_launch("topk_rank_kernel")) return 1;
+  }
+  return 0;
 }
 
 }  // namespace aitb

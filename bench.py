@@ -212,17 +212,41 @@ def run_ours(args):
         cls, bbox = eng.head_forward(d_maps, d_qrys, rois)
         return rois, cls, bbox
 
-    def step_e2e():
-        maps = h_maps.to(dev, non_blocking=True)
-        qrys = h_qrys.to(dev, non_blocking=True)
-        boxes = h_boxes.to(dev, non_blocking=True)
-        scores = h_scores.to(dev, non_blocking=True)
-        rois, _ = propose_rois(boxes, scores, PRE_NMS, P, NMS_THR)
-        cls, bbox = eng.head_forward(maps, qrys, rois)
-        h_out["rois"].copy_(rois, non_blocking=True)
-        h_out["cls"].copy_(cls, non_blocking=True)
-        h_out["bbox"].copy_(bbox, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                   # the result is on the host
+    # e2e: host (pinned) inputs -> H2D -> proposal NMS + head -> D2H of rois / cls_prob / bbox_pred, every step.
+    # The H2D of step i+1 is issued on a copy stream while step i computes (double-buffered device inputs);
+    # every step's copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{"maps": torch.empty_like(d_maps), "qrys": torch.empty_like(d_qrys),
+              "boxes": torch.empty_like(d_boxes), "scores": torch.empty_like(d_scores),
+              "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()} for _ in range(2)]
+
+    def issue_h2d(slot):
+        s = slots[slot]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(s["consumed"])
+            s["maps"].copy_(h_maps, non_blocking=True)
+            s["qrys"].copy_(h_qrys, non_blocking=True)
+            s["boxes"].copy_(h_boxes, non_blocking=True)
+            s["scores"].copy_(h_scores, non_blocking=True)
+            s["copied"].record(copy_stream)
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream()
+        for s in slots:
+            s["consumed"].record(main)
+        issue_h2d(0)
+        for i in range(steps):
+            s = slots[i % 2]
+            main.wait_event(s["copied"])
+            if i + 1 < steps:
+                issue_h2d((i + 1) % 2)
+            rois, _ = propose_rois(s["boxes"], s["scores"], PRE_NMS, P, NMS_THR)
+            cls, bbox = eng.head_forward(s["maps"], s["qrys"], rois)
+            s["consumed"].record(main)
+            h_out["rois"].copy_(rois, non_blocking=True)
+            h_out["cls"].copy_(cls, non_blocking=True)
+            h_out["bbox"].copy_(bbox, non_blocking=True)
+            main.synchronize()                                      # this step's result is on the host
         return h_out
 
     def barrier():
@@ -230,12 +254,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, loop_inside=False):
         barrier()
         st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st.record()
-        for _ in range(steps):
-            fn()
+        if loop_inside:
+            fn(steps)
+        else:
+            for _ in range(steps):
+                fn()
         en.record()
         barrier()
         ms = st.elapsed_time(en)
@@ -253,9 +280,8 @@ def run_ours(args):
     ms_dev = timed(step_device, args.steps)
     launches = ops.launch_count(reset=True)
     clocks = sampler.stop()
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    run_e2e(2)
+    ms_e2e = timed(run_e2e, args.steps, loop_inside=True)
 
     # ---- stage breakdown and the roofline of the dominant kernel (same process, CUDA events)
     def ev_time(fn, reps=5):
