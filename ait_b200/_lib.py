@@ -8,8 +8,8 @@ LIB_PATH = os.path.join(_HERE, "libaitb200.so")
 
 AITB_F32, AITB_BF16 = 0, 1
 
-EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU = (
-    1, 2, 4, 8, 16, 32, 64, 128)
+EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256)
 
 
 class View4(C.Structure):
@@ -29,6 +29,7 @@ class GemmDesc(C.Structure):
         ("res_div", C.c_int), ("res_rep", C.c_int),
         ("pos", C.c_void_p), ("pos_rows", C.c_int),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
+        ("dual", C.c_int), ("bias2", C.c_void_p),
     ]
 
 
@@ -54,7 +55,7 @@ class Bottleneck(C.Structure):
 
 
 class SKBlock(C.Structure):
-    _fields_ = [("conv1x1", Linear), ("conv3x3", Linear)]
+    _fields_ = [("conv1x1", Linear), ("conv3x3", Linear), ("w_fused", C.c_void_p)]
 
 
 class HeadWeights(C.Structure):

@@ -405,20 +405,19 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
 // SKBlock (bug-compatible: relu(conv1x1_g8(x))^2 + relu(conv3x3_g8(x))^2, blocks_coatt_transformer_sk.py:973-984)
 static int sk_block(const aitb_head_weights* w, const aitb_skblock& sk, const void* x, int G, void* out,
                     cudaStream_t st) {
+  // One dual-accumulator grouped GEMM: the nine 3x3 taps accumulate into acc0, the 1x1 conv (a tenth,
+  // centre tap reading the same A tile) into acc1; the epilogue emits relu(acc1+b1)^2 + relu(acc0+b3)^2.
   const int dt = w->dtype;
-  aitb_gemm_desc d1 = gemm_base(dt, G * 64, 1024, 128, sk.conv1x1.w, 128, out, 1024, w->round_tf32);
-  d1.a_group_c = 128;
-  view_plain(d1, x, 1024);
-  d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_SQUARE;
-  d1.bias = sk.conv1x1.bias;
-  RUN(gemm_run(&d1, st));
-  aitb_gemm_desc d3 = gemm_base(dt, G * 64, 1024, 128, sk.conv3x3.w, 128, out, 1024, w->round_tf32);
-  d3.a_group_c = 128;
-  view_map(d3, x, 1024, 8, 8, 1, G);
-  taps3x3(d3);
-  d3.flags = AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_SQUARE | AITB_EPI_ACCUM;
-  d3.bias = sk.conv3x3.bias;
-  return gemm_run(&d3, st);
+  AITB_REQUIRE(sk.w_fused != nullptr, "SKNet fused weights missing");
+  aitb_gemm_desc d = gemm_base(dt, G * 64, 1024, 128, sk.w_fused, 128, out, 1024, w->round_tf32);
+  d.a_group_c = 128;
+  view_map(d, x, 1024, 8, 8, 1, G);
+  taps3x3(d);
+  d.dual = 1;
+  d.flags = AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_SQUARE | AITB_EPI_DUAL;
+  d.bias = sk.conv3x3.bias;
+  d.bias2 = sk.conv1x1.bias;
+  return gemm_run(&d, st);
 }
 
 // ResNet-50 layer4 (3 bottlenecks, stride 2 on the first 1x1, frozen BN folded) on [G, 8, 8, 1024] -> [G, 16, 2048]

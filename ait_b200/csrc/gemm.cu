@@ -53,6 +53,8 @@ struct GemmKParams {
   const float* beta;
   float eps;
   int round_tf32;
+  int dual;  // extra centre tap into a second accumulator (BLOCK_N = 128)
+  const float* bias2;
 };
 
 __device__ __forceinline__ uint4 ld_global_v4(const void* p) {
@@ -74,7 +76,9 @@ struct GemmCfg {
   static constexpr int kStages = (BLOCK_N == 512) ? 2 : 4;
   static constexpr int kAccStages = (BLOCK_N == 512) ? 1 : 2;
   static constexpr int kUmmaN = (BLOCK_N > 256) ? 256 : BLOCK_N;
-  static constexpr int kTmemCols = (BLOCK_N * kAccStages < 32) ? 32 : BLOCK_N * kAccStages;
+  // accumulator stage stride in TMEM columns; BLOCK_N = 128 reserves room for the dual accumulator
+  static constexpr int kAccStride = (BLOCK_N == 128) ? 256 : BLOCK_N;
+  static constexpr int kTmemCols = (kAccStride * kAccStages < 32) ? 32 : kAccStride * kAccStages;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
                                     2048 /*LN row statistics*/ + 4 * 4096 /*epilogue staging, one 32x128 B tile per warp*/;
 };
@@ -133,7 +137,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int t_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int n_tiles_total = CL ? p.m_tiles : p.m_tiles * p.n_tiles;
-  const int iters_per_tile = p.taps * p.k_chunks;
+  const int n_taps = p.taps + (p.dual ? 1 : 0);
+  const int iters_per_tile = n_taps * p.k_chunks;
+  const int dual_first_iter = p.dual ? p.taps * p.k_chunks : -1;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -143,8 +149,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int mt = CL ? tile : tile / p.n_tiles;
         const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
         const int a_c_base = nt * p.a_group_c;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
+        for (int tap = 0; tap < n_taps; ++tap) {
+          int c1 = tap < p.taps ? p.tap_dx[tap] : 0, c2 = tap < p.taps ? p.tap_dy[tap] : 0, c3 = 0;
           if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
             const uint32_t s = it % kStages;
@@ -173,8 +179,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t aph = (lt / kAcc) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const uint32_t d_tmem0 = tmem_base + as * Cfg::kAccStride;
         for (int i = 0; i < iters_per_tile; ++i, ++it) {
+          const bool second = p.dual && i >= dual_first_iter;
+          const uint32_t d_tmem = d_tmem0 + (second ? BLOCK_N : 0);
+          const bool fresh = (i == 0) || (i == dual_first_iter);
           const uint32_t s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -188,7 +197,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int nb = 0; nb < BLOCK_N / Cfg::kUmmaN; ++nb) {
               umma_ss<Act<T>::kBytes>(d_tmem + nb * Cfg::kUmmaN, adesc + (uint64_t)(k * 2),
                                       bdesc + (uint64_t)(k * 2 + nb * (Cfg::kUmmaN * 128 / 16)),
-                                      idesc, (i | k) != 0 ? 1u : 0u);
+                                      idesc, (fresh && k == 0) ? 0u : 1u);
             }
           }
           tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
@@ -316,7 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_row = tmem_base + as * Cfg::kAccStride + ((uint32_t)(q * 32) << 16);
 
       if ((p.flags & AITB_EPI_LN) == 0) {
         // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead
@@ -349,6 +358,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.flags & AITB_EPI_SQUARE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+          }
+          if constexpr (BLOCK_N == 128) {
+            if (p.flags & AITB_EPI_DUAL) {  // second accumulator: same activation, then summed
+              tmem_ld32(t_row + BLOCK_N + c0, raw);
+              tmem_ld_wait();
+              float u[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
+              add_vec(p.bias2 + n0 + c0, u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (p.flags & AITB_EPI_RELU) u[j] = fmaxf(u[j], 0.f);
+                if (p.flags & AITB_EPI_SQUARE) u[j] = u[j] * u[j];
+                v[j] += u[j];
+              }
+            }
           }
           if (aux_res) {
             float r[32];
@@ -611,10 +636,15 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   if (d->flags & AITB_EPI_BIAS) AITB_REQUIRE(d->bias != nullptr, "aitb_gemm: bias flag without bias");
   if (d->flags & AITB_EPI_LN) AITB_REQUIRE(d->gamma && d->beta, "aitb_gemm: LN flag without gamma/beta");
 
+  if (d->dual || (d->flags & AITB_EPI_DUAL))
+    AITB_REQUIRE(d->dual && (d->flags & AITB_EPI_DUAL) && d->block_n == 128 && d->bias2 != nullptr &&
+                     (d->flags & (AITB_EPI_LN | AITB_EPI_RES | AITB_EPI_ACCUM)) == 0,
+                 "aitb_gemm: dual accumulator needs block_n 128, bias2 and the DUAL epilogue");
+  const int w_taps = d->taps + (d->dual ? 1 : 0);
   CUtensorMap tmA, tmB;
   if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, d->a.box, "A")) return 1;
-  const uint64_t wdims[2] = {(uint64_t)d->taps * d->k_per_tap, (uint64_t)d->N};
-  const uint64_t wstr[1] = {(uint64_t)d->taps * d->k_per_tap * eb};
+  const uint64_t wdims[2] = {(uint64_t)w_taps * d->k_per_tap, (uint64_t)d->N};
+  const uint64_t wstr[1] = {(uint64_t)w_taps * d->k_per_tap * eb};
   const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(d->block_n > 256 ? 256 : d->block_n)};
   const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
   if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
@@ -651,6 +681,8 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.beta = d->beta;
   kp.eps = d->eps;
   kp.round_tf32 = d->round_tf32;
+  kp.dual = d->dual ? 1 : 0;
+  kp.bias2 = d->bias2;
 
 #define AITB_DISPATCH(BN)                                                                     \
   (d->dtype == AITB_F32 ? launch_gemm<float, BN, false>(tmA, tmB, kp, stream)                 \

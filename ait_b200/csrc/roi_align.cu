@@ -9,8 +9,9 @@
 //   * the map is read from a channels-last copy, so each bilinear tap is ONE coalesced,
 //     vectorised 128-bit load per lane (lanes = channels) instead of the reference's four
 //     scattered 4-byte gathers per output element;
-//   * sample positions/weights are channel independent: they are computed once per CTA into
-//     shared-memory tables (x table: pooled_w * grid_w entries, y table: pooled_h * grid_h);
+//   * sample positions/weights are channel independent and separable: each CTA folds the adaptive
+//     sampling grid of every bin into per-axis cell-weight tables once, so a bin costs
+//     (grid_h+1)(grid_w+1) vector loads instead of 4*grid_h*grid_w bilinear taps;
 //   * a CTA owns (roi, channel slab); its feature window is small enough to stay in L1, so every
 //     map byte is fetched from L2 about once per CTA;
 //   * output goes either token-major [K, ph*pw, C] (feeds the enc_emb GEMM K-major, no NCHW
@@ -116,28 +117,56 @@ template <> struct Vec4<__nv_bfloat16> {
   }
 };
 
-// grid (C / 128, K); block 256 = 8 warps; lane owns 4 consecutive channels of the 128-channel slab,
+// Per-axis "footprint" of one output bin: the bilinear samples of a bin touch a contiguous run of cells
+// [c0, c0 + n) (sample spacing <= 1 cell), and because bilinear weights are separable the bin value is
+//   (1/count) * sum_cy sum_cx Wy[cy] * Wx[cx] * feat[cy][cx],   Wy[c] = sum over the bin's y-samples of
+// the weight they give to row c (same for x).  That is (gh+1)(gw+1) loads per bin instead of 4*gh*gw taps,
+// the same real-number sum as ROIAlign_cuda.cu:105-118 re-associated (differences ~1e-7 relative).
+struct Foot {
+  int c0, n;
+  float w[kMaxGrid + 1];
+};
+
+// returns false if the footprint does not fit the table (fixed sampling_ratio on a huge roi)
+__device__ __forceinline__ bool build_foot(Foot& f, float start, int p, float bin, int grid, int size) {
+  int c0 = 0, n = 0;
+#pragma unroll 1
+  for (int i = 0; i < kMaxGrid + 1; ++i) f.w[i] = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < grid; ++i) {
+    const Tap t = make_tap(sample_coord(start, p, bin, i, grid), size);
+    if (t.wlo == 0.f && t.whi == 0.f) continue;  // outside [-1, size]: contributes 0 (but counts in `count`)
+    if (n == 0) { c0 = t.lo; n = 1; }
+    // samples are visited in increasing coordinate order, so lo/hi never fall below c0
+    if (t.hi - c0 > kMaxGrid) return false;
+    f.w[t.lo - c0] += t.wlo;
+    f.w[t.hi - c0] += t.whi;
+    n = max(n, t.hi - c0 + 1);
+  }
+  f.c0 = c0;
+  f.n = n;
+  return true;
+}
+
+// grid (ceil(C / 128), K); block 256 = 8 warps; lane owns 4 consecutive channels of the 128-channel slab,
 // warps stride over the ph*pw bins.
 template <typename T, bool NCHW_OUT>
 __global__ void __launch_bounds__(256)
 roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
                      int ph, int pw, int sampling_ratio, T* __restrict__ out, int round_tf) {
-  __shared__ Tap xtab[kMaxPooled * kMaxGrid];
-  __shared__ Tap ytab[kMaxPooled * kMaxGrid];
+  __shared__ Foot xf[kMaxPooled];
+  __shared__ Foot yf[kMaxPooled];
   extern __shared__ float stage[];  // NCHW_OUT: [128][ph*pw + 1]
   const int k = blockIdx.y;
   const int c0 = blockIdx.x * 128;
   const RoiGeom g = roi_geometry(rois + (size_t)k * 5, scale, ph, pw, sampling_ratio);
   const int gw = g.grid_w, gh = g.grid_h;
-  // rois far larger than the map (unclipped inputs) overflow the tables: compute taps inline then
-  const bool xt = gw <= kMaxGrid, yt = gh <= kMaxGrid;
-  if (xt)
-    for (int i = threadIdx.x; i < pw * gw; i += blockDim.x)
-      xtab[i] = make_tap(sample_coord(g.start_w, i / gw, g.bin_w, i % gw, gw), W);
-  if (yt)
-    for (int i = threadIdx.x; i < ph * gh; i += blockDim.x)
-      ytab[i] = make_tap(sample_coord(g.start_h, i / gh, g.bin_h, i % gh, gh), H);
-  __syncthreads();
+  // rois far larger than the map (unclipped inputs) overflow the tables: per-sample taps inline then
+  bool fits = true;
+  if ((int)threadIdx.x < pw) fits = build_foot(xf[threadIdx.x], g.start_w, threadIdx.x, g.bin_w, gw, W);
+  else if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + ph)
+    fits = build_foot(yf[threadIdx.x - 32], g.start_h, threadIdx.x - 32, g.bin_h, gh, H);
+  const bool tables = __syncthreads_and(fits) != 0;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cvalid = min(128, C - c0);          // last slab may be partial (C % 4 == 0)
@@ -148,21 +177,35 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
   for (int bin = warp; bin < nbins; bin += 8) {
     const int py = bin / pw, px = bin - py * pw;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < gh; ++iy) {
-      const Tap ty = yt ? ytab[py * gh + iy] : make_tap(sample_coord(g.start_h, py, g.bin_h, iy, gh), H);
-      const T* r0 = fb + (size_t)ty.lo * W * C;
-      const T* r1 = fb + (size_t)ty.hi * W * C;
-      for (int ix = 0; ix < gw; ++ix) {
-        const Tap tx = xt ? xtab[px * gw + ix] : make_tap(sample_coord(g.start_w, px, g.bin_w, ix, gw), W);
-        const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
-        const float4 v1 = Vec4<T>::ld(r0 + (size_t)tx.lo * C);
-        const float4 v2 = Vec4<T>::ld(r0 + (size_t)tx.hi * C);
-        const float4 v3 = Vec4<T>::ld(r1 + (size_t)tx.lo * C);
-        const float4 v4 = Vec4<T>::ld(r1 + (size_t)tx.hi * C);
-        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-        acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-        acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+    if (tables) {
+      const int ny = yf[py].n, nx = xf[px].n;
+      const T* r = fb + ((size_t)yf[py].c0 * W + xf[px].c0) * C;
+      for (int cy = 0; cy < ny; ++cy, r += (size_t)W * C) {
+        const float wy = yf[py].w[cy];
+        const T* q = r;
+        for (int cx = 0; cx < nx; ++cx, q += C) {
+          const float w = wy * xf[px].w[cx];
+          const float4 v = Vec4<T>::ld(q);
+          acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+      }
+    } else {
+      for (int iy = 0; iy < gh; ++iy) {
+        const Tap ty = make_tap(sample_coord(g.start_h, py, g.bin_h, iy, gh), H);
+        const T* r0 = fb + (size_t)ty.lo * W * C;
+        const T* r1 = fb + (size_t)ty.hi * W * C;
+        for (int ix = 0; ix < gw; ++ix) {
+          const Tap tx = make_tap(sample_coord(g.start_w, px, g.bin_w, ix, gw), W);
+          const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+          const float4 v1 = Vec4<T>::ld(r0 + (size_t)tx.lo * C);
+          const float4 v2 = Vec4<T>::ld(r0 + (size_t)tx.hi * C);
+          const float4 v3 = Vec4<T>::ld(r1 + (size_t)tx.lo * C);
+          const float4 v4 = Vec4<T>::ld(r1 + (size_t)tx.hi * C);
+          acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
       }
     }
     acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);   // output_val /= count (:118)
@@ -183,7 +226,7 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
   }
   if constexpr (NCHW_OUT) {
     __syncthreads();
-    // the slab's 128 channels x nbins outputs are contiguous in NCHW: fully coalesced store
+    // the slab's channels x nbins outputs are contiguous in NCHW: fully coalesced store
     T* ob = out + ((size_t)k * C + c0) * nbins;
     const int s = nbins + 1;
     for (int i = threadIdx.x; i < cvalid * nbins; i += blockDim.x) {

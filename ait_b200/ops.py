@@ -142,7 +142,7 @@ def _esize(dt):
 
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
-         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6):
+         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None):
     """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
     map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels)."""
     lib = L.load()
@@ -185,6 +185,8 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.beta = 0 if beta is None else beta.data_ptr()
     d.eps = eps
     d.round_tf32 = 1 if round_tf32 else 0
+    d.dual = 1 if dual else 0
+    d.bias2 = 0 if bias2 is None else bias2.data_ptr()
     L.check(lib.aitb_gemm(C.byref(d), L.stream_ptr()))
     return out
 

@@ -132,7 +132,9 @@ class HeadEngine:
             c1, c3 = blk.convs[0][0], blk.convs[1][0]
             m1, b1 = self._linear(dst.conv1x1, self._tap_major(c1.weight), c1.bias)
             m3, b3 = self._linear(dst.conv3x3, self._tap_major(c3.weight), c3.bias)
-            self._sk_mats[name] = (m1, b1, m3, b3)
+            mf = self._mat(torch.cat([self._tap_major(c3.weight), self._tap_major(c1.weight)], dim=1))
+            dst.w_fused = mf.data_ptr()
+            self._sk_mats[name] = (m1, b1, m3, b3, mf)
 
     @staticmethod
     def _fold_bn(conv, bn):
@@ -244,14 +246,14 @@ class HeadEngine:
 
     # ---- module-level forwards of SKNet / RCNN_top, composed from the exported GEMM building block
     def _sk_branch(self, x_nchw, which):
-        m1, b1, m3, b3 = self._sk_mats[which]
+        m1, b1, m3, b3, mf = self._sk_mats[which]
         G = x_nchw.shape[0]
         x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype)
         out = torch.empty((G, 64, 1024), dtype=self.dtype, device=x.device)
-        ops.gemm(x, m1, out, M=G * 64, N=1024, K=128, block_n=128, view="plain", lda=1024, group_c=128,
-                 flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE, bias=b1)
-        ops.gemm(x, m3, out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G),
-                 taps=9, group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_ACCUM, bias=b3)
+        # one dual-accumulator GEMM: nine 3x3 taps -> acc0, the 1x1 conv (centre tap) -> acc1
+        ops.gemm(x, mf, out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G),
+                 taps=9, group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_DUAL, bias=b3,
+                 dual=True, bias2=b1)
         return ops.transpose_cs(out, False, out_dtype=torch.float32).view(G, 1024, 8, 8)
 
     def sk_forward(self, x_props, x_query):

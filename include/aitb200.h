@@ -109,7 +109,9 @@ enum {
   AITB_EPI_POS = 16,    /* v += pos[out_row % pos_rows, n]          (fp32 table)  */
   AITB_EPI_LN = 32,     /* LayerNorm over the full row (requires block_n == N == 512) */
   AITB_EPI_ACCUM = 64,  /* v += out (read-modify-write)                            */
-  AITB_EPI_RES_RELU = 128 /* relu applied AFTER the residual add (bottleneck tail) */
+  AITB_EPI_RES_RELU = 128, /* relu applied AFTER the residual add (bottleneck tail) */
+  AITB_EPI_DUAL = 256      /* two accumulators (see `dual`): v = f(acc0 + bias) + f(acc1 + bias2),
+                              f = the RELU / SQUARE flags (SKBlock: relu(conv1x1)^2 + relu(conv3x3)^2) */
 };
 
 typedef struct {
@@ -137,6 +139,10 @@ typedef struct {
   const float* beta;
   float eps;
   int round_tf32; /* round stored fp32 activations to tf32 (RN) */
+  /* dual != 0 (block_n 128 only): after the `taps` taps, one extra centre tap (dx = dy = 0) whose K block
+   * follows them in `w` accumulates into a SECOND accumulator; combined by AITB_EPI_DUAL */
+  int dual;
+  const float* bias2;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
@@ -206,6 +212,7 @@ typedef struct {
 typedef struct {
   aitb_linear conv1x1; /* [1024, 128]   grouped (8 groups of 128 -> 128) */
   aitb_linear conv3x3; /* [1024, 9*128] grouped, tap-major K            */
+  const void* w_fused; /* [1024, 10*128] = conv3x3 taps followed by the conv1x1 block (dual-accumulator GEMM) */
 } aitb_skblock;
 
 typedef struct {

@@ -128,6 +128,13 @@ def test_gemm_strided_1x1_and_grouped_convs(dtype):
     if dtype == torch.bfloat16:
         tol = dict(rtol=3e-2, atol=5e-2)      # squared outputs, stored twice in bf16
     torch.testing.assert_close(out.float().cpu().double(), ref, **tol)
+    # the same SKBlock as ONE dual-accumulator launch (what the engine runs)
+    wf = torch.cat([HeadEngine._tap_major(w3), HeadEngine._tap_major(w1)], dim=1).contiguous().to(DEV, dtype)
+    out2 = torch.zeros((G * 64, 1024), dtype=dtype, device=DEV)
+    ops.gemm(xt, wf, out2, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G), taps=9,
+             group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_DUAL, bias=b3.to(DEV), dual=True,
+             bias2=b1.to(DEV))
+    torch.testing.assert_close(out2.float().cpu().double(), ref, **tol)
 
 
 def _attn_ref(q, k, v, w_sk, b_sk, mask):
