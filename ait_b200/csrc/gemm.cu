@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/aitb200.h"
@@ -83,153 +84,30 @@ struct GemmCfg {
                                     2048 /*LN row statistics*/ + 4 * 4096 /*epilogue staging, one 32x128 B tile per warp*/;
 };
 
-// CL = true: "cluster LayerNorm" variant.  A 2-CTA cluster shares one 128-row m-tile; CTA rank r owns the
-// output columns [256 r, 256 r + 256) of the N = 512 row (BLOCK_N = 256 machinery: 4-stage ring, double-
-// buffered accumulator).  The LayerNorm row statistics are combined across the two CTAs through
-// distributed shared memory (partial sum + centred M2 per row, Chan's parallel-variance formula).
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BLOCK_N accumulator tile, executed by the 4 epilogue warps of a CTA.
+// Each thread owns one accumulator row (tcgen05.ld 32x32b).  Global traffic never uses that
+// row-per-thread shape: 32-column chunks go through a per-warp XOR-swizzled staging tile so that
+// every global load/store instruction covers whole contiguous row segments (4 rows x 128 B for
+// fp32, 8 rows x 64 B for bf16) -- fully coalesced, conflict-free in shared memory.
+//   mt : 128-row tile index (rows mt*128 ...), n0 : first output column, t_row : TMEM address of this
+//   warp's lane quadrant in the accumulator stage, stg : this warp's 4 KB staging tile.
+// ---------------------------------------------------------------------------------------------
 template <typename T, int BLOCK_N, bool CL>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kAcc = Cfg::kAccStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                  // [kStages]
-  uint64_t* empty_bar = bars + kStages;       // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;    // [kAcc]
-  uint64_t* acc_empty = acc_full + kAcc;      // [kAcc]
-  uint64_t* stats_full = acc_empty + kAcc;    // [kAcc]  (CL only) peer's row statistics have landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stats_full + kAcc);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < kAcc; ++s) {
-      mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
-      mbar_init(&stats_full[s], 128);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_holder, Cfg::kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CL) cluster_sync_all();  // peer's mbarriers are initialised before any remote arrive
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-
-  // tile schedule: plain = tiles round-robin over CTAs (n fastest); CL = m-tiles round-robin over clusters
-  const uint32_t cta_rank = CL ? cluster_ctarank() : 0u;
-  const int t_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int t_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int n_tiles_total = CL ? p.m_tiles : p.m_tiles * p.n_tiles;
-  const int n_taps = p.taps + (p.dual ? 1 : 0);
-  const int iters_per_tile = n_taps * p.k_chunks;
-  const int dual_first_iter = p.dual ? p.taps * p.k_chunks : -1;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = t_first; tile < n_tiles_total; tile += t_step) {
-        const int mt = CL ? tile : tile / p.n_tiles;
-        const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
-        const int a_c_base = nt * p.a_group_c;
-        for (int tap = 0; tap < n_taps; ++tap) {
-          int c1 = tap < p.taps ? p.tap_dx[tap] : 0, c2 = tap < p.taps ? p.tap_dy[tap] : 0, c3 = 0;
-          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            const uint32_t s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * Cfg::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-            tma_load_4d(sa, &tmA, &full_bar[s], a_c_base + kc * p.ke, c1, c2, c3);
-            const int kb = (tap * p.k_chunks + kc) * p.ke;
-            tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
-            if constexpr (BLOCK_N > 256)
-              tma_load_2d(sb + 256 * 128, &tmB, &full_bar[s], kb, nt * BLOCK_N + 256);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, kBlockM, Cfg::kUmmaN);
-      uint32_t it = 0;
-      uint32_t lt = 0;  // local tile counter
-      for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
-        const uint32_t as = lt % kAcc;
-        const uint32_t aph = (lt / kAcc) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem0 = tmem_base + as * Cfg::kAccStride;
-        for (int i = 0; i < iters_per_tile; ++i, ++it) {
-          const bool second = p.dual && i >= dual_first_iter;
-          const uint32_t d_tmem = d_tmem0 + (second ? BLOCK_N : 0);
-          const bool fresh = (i == 0) || (i == dual_first_iter);
-          const uint32_t s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte chunk
-#pragma unroll
-            for (int nb = 0; nb < BLOCK_N / Cfg::kUmmaN; ++nb) {
-              umma_ss<Act<T>::kBytes>(d_tmem + nb * Cfg::kUmmaN, adesc + (uint64_t)(k * 2),
-                                      bdesc + (uint64_t)(k * 2 + nb * (Cfg::kUmmaN * 128 / 16)),
-                                      idesc, (fresh && k == 0) ? 0u : 1u);
-            }
-          }
-          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
-        }
-        tc_commit(&acc_full[as]);  // accumulator complete -> epilogue
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    // Each thread owns one accumulator row (tcgen05.ld 32x32b).  Global traffic never uses that
-    // row-per-thread shape: 32-column chunks go through a per-warp XOR-swizzled staging tile so that
-    // every global load/store instruction covers whole contiguous row segments (4 rows x 128 B for
-    // fp32, 8 rows x 64 B for bf16) -- fully coalesced, conflict-free in shared memory.
-    constexpr int kRowBytes = 32 * (int)sizeof(T);       // one staged row: 32 columns
-    constexpr int kCh = kRowBytes / 16;                  // 16-byte pieces per row (8 | 4)
-    constexpr int kRpi = 32 / kCh;                       // rows covered by one warp instruction (4 | 8)
-    constexpr int kIt = kCh;                             // instructions per 32-row chunk (8 | 4)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row_in_tile = q * 32 + lane;
-    float2* stats = reinterpret_cast<float2*>(smem + kStages * Cfg::kStageBytes + 256);   // [kAcc][128] (CL)
-    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + 2048 + q * 4096;
-    const int piece = lane % kCh;
-    const int srow0 = lane / kCh;
-    auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
-    const T* res = reinterpret_cast<const T*>(p.res);
-    uint32_t lt = 0;
-    for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
-      const int mt = CL ? tile : tile / p.n_tiles;
-      const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
-      const uint32_t as = lt % kAcc;
-      const uint32_t aph = (lt / kAcc) & 1;
-      const int n0 = nt * BLOCK_N;
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
+                                              uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
+                                              int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
+                                              uint32_t cta_rank) {
+  constexpr int kRowBytes = 32 * (int)sizeof(T);       // one staged row: 32 columns
+  constexpr int kCh = kRowBytes / 16;                  // 16-byte pieces per row (8 | 4)
+  constexpr int kRpi = 32 / kCh;                       // rows covered by one warp instruction (4 | 8)
+  constexpr int kIt = kCh;                             // instructions per 32-row chunk (8 | 4)
+  const int row_in_tile = q * 32 + lane;
+  const int piece = lane % kCh;
+  const int srow0 = lane / kCh;
+  auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
+  const T* res = reinterpret_cast<const T*>(p.res);
+  {
       // rows this lane serves in the coalesced phases
       T* optr[kIt];
       const T* rptr[kIt];
@@ -323,9 +201,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
       };
 
-      mbar_wait(&acc_full[as], aph);
+      mbar_wait(acc_full_bar, aph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * Cfg::kAccStride + ((uint32_t)(q * 32) << 16);
 
       if ((p.flags & AITB_EPI_LN) == 0) {
         // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead
@@ -454,8 +331,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // send (sum, M2) of my half-row to the peer, wait for the peer's, combine (Chan et al.)
           const uint32_t peer = cta_rank ^ 1u;
           st_cluster_f32x2(mapa_u32(smem_u32(&stats[as * 128 + row_in_tile]), peer), sum, ssq);
-          mbar_arrive_cluster(mapa_u32(smem_u32(&stats_full[as]), peer));
-          mbar_wait_cluster(&stats_full[as], aph);
+          mbar_arrive_cluster(mapa_u32(smem_u32(stats_full_bar), peer));
+          mbar_wait_cluster(stats_full_bar, aph);
           const float2 ps = stats[as * 128 + row_in_tile];
           const float mean_p = ps.x * (1.f / BLOCK_N);
           const float mean_all = (sum + ps.x) * (0.5f / BLOCK_N);
@@ -487,6 +364,145 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stage_store(c0, v);
         }
       }
+  }
+}
+
+// CL = true: "cluster LayerNorm" variant.  A 2-CTA cluster shares one 128-row m-tile; CTA rank r owns the
+// output columns [256 r, 256 r + 256) of the N = 512 row (BLOCK_N = 256 machinery: 4-stage ring, double-
+// buffered accumulator).  The LayerNorm row statistics are combined across the two CTAs through
+// distributed shared memory (partial sum + centred M2 per row, Chan's parallel-variance formula).
+template <typename T, int BLOCK_N, bool CL>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kAcc = Cfg::kAccStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;    // [kAcc]
+  uint64_t* acc_empty = acc_full + kAcc;      // [kAcc]
+  uint64_t* stats_full = acc_empty + kAcc;    // [kAcc]  (CL only) peer's row statistics have landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stats_full + kAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+      mbar_init(&stats_full[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CL) cluster_sync_all();  // peer's mbarriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // tile schedule: plain = tiles round-robin over CTAs (n fastest); CL = m-tiles round-robin over clusters
+  const uint32_t cta_rank = CL ? cluster_ctarank() : 0u;
+  const int t_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_tiles_total = CL ? p.m_tiles : p.m_tiles * p.n_tiles;
+  const int n_taps = p.taps + (p.dual ? 1 : 0);
+  const int iters_per_tile = n_taps * p.k_chunks;
+  const int dual_first_iter = p.dual ? p.taps * p.k_chunks : -1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step) {
+        const int mt = CL ? tile : tile / p.n_tiles;
+        const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
+        const int a_c_base = nt * p.a_group_c;
+        for (int tap = 0; tap < n_taps; ++tap) {
+          int c1 = tap < p.taps ? p.tap_dx[tap] : 0, c2 = tap < p.taps ? p.tap_dy[tap] : 0, c3 = 0;
+          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_4d(sa, &tmA, &full_bar[s], a_c_base + kc * p.ke, c1, c2, c3);
+            const int kb = (tap * p.k_chunks + kc) * p.ke;
+            tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
+            if constexpr (BLOCK_N > 256)
+              tma_load_2d(sb + 256 * 128, &tmB, &full_bar[s], kb, nt * BLOCK_N + 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, kBlockM, Cfg::kUmmaN);
+      uint32_t it = 0;
+      uint32_t lt = 0;  // local tile counter
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
+        const uint32_t as = lt % kAcc;
+        const uint32_t aph = (lt / kAcc) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem0 = tmem_base + as * Cfg::kAccStride;
+        for (int i = 0; i < iters_per_tile; ++i, ++it) {
+          const bool second = p.dual && i >= dual_first_iter;
+          const uint32_t d_tmem = d_tmem0 + (second ? BLOCK_N : 0);
+          const bool fresh = (i == 0) || (i == dual_first_iter);
+          const uint32_t s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte chunk
+#pragma unroll
+            for (int nb = 0; nb < BLOCK_N / Cfg::kUmmaN; ++nb) {
+              umma_ss<Act<T>::kBytes>(d_tmem + nb * Cfg::kUmmaN, adesc + (uint64_t)(k * 2),
+                                      bdesc + (uint64_t)(k * 2 + nb * (Cfg::kUmmaN * 128 / 16)),
+                                      idesc, (fresh && k == 0) ? 0u : 1u);
+            }
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
+        tc_commit(&acc_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    float2* stats = reinterpret_cast<float2*>(smem + kStages * Cfg::kStageBytes + 256);   // [kAcc][128] (CL)
+    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + 2048 + q * 4096;
+    uint32_t lt = 0;
+    for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
+      const int mt = CL ? tile : tile / p.n_tiles;
+      const int nt = CL ? (int)cta_rank : tile - mt * p.n_tiles;
+      const uint32_t as = lt % kAcc;
+      const uint32_t aph = (lt / kAcc) & 1;
+      const uint32_t t_row = tmem_base + as * Cfg::kAccStride + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<T, BLOCK_N, CL>(p, stg, stats, &stats_full[as], &acc_full[as], t_row, q, lane, mt, nt * BLOCK_N,
+                                    as, aph, cta_rank);
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
@@ -498,6 +514,145 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2) for the wide plain GEMMs: a cluster of two CTAs computes a 256 x 256
+// tile.  Each CTA stages its own 128 rows of A and HALF of the weight tile (128 of the 256 W rows);
+// the leader's single tcgen05.mma (M = 256, N = 256) reads both halves, so every CTA moves
+// 32 KB instead of 48 KB per K chunk from L2 (-33 % bytes per MAC) and the ring is 6 deep.
+//   full barrier  : in the leader, count 2 (one arrive per CTA's producer) + 64 KB of TMA bytes
+//   empty / acc_full : tcgen05.commit multicast to both CTAs
+//   acc_empty     : in the leader, count 256 (both CTAs' epilogue threads)
+// ---------------------------------------------------------------------------------------------
+static constexpr int k2Stages = 6;
+static constexpr int k2StageBytes = kABytes + 128 * 128;  // A (own 128 rows) + half of B
+static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + 2048 + 4 * 4096;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmKParams p) {
+  constexpr int BLOCK_N = 256;
+  constexpr int kAcc = 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint64_t* full_bar = bars;                 // [k2Stages]  (used in the leader)
+  uint64_t* empty_bar = bars + k2Stages;     // [k2Stages]  (local in each CTA)
+  uint64_t* acc_full = bars + 2 * k2Stages;  // [kAcc]      (local in each CTA)
+  uint64_t* acc_empty = acc_full + kAcc;     // [kAcc]      (used in the leader)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_holder, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int n_tiles_total = m_pairs * p.n_tiles;
+  const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
+  const int iters_per_tile = p.taps * p.k_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step) {
+        const int mp = tile / p.n_tiles;
+        const int nt = tile - mp * p.n_tiles;
+        const int mt = mp * 2 + (int)rank;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
+          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % k2Stages;
+            const uint32_t ph = (it / k2Stages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * k2StageBytes;
+            uint8_t* sb = sa + kABytes;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * k2StageBytes);
+            else mbar_arrive_remote(&full_bar[s], 0);
+            tma2_load_4d(sa, &tmA, &full_bar[s], kc * p.ke, c1, c2, c3);
+            const int kb = (tap * p.k_chunks + kc) * p.ke;
+            tma2_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N + (int)rank * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, 256, BLOCK_N);
+      uint32_t it = 0, lt = 0;
+      for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
+        const uint32_t as = lt % kAcc;
+        const uint32_t aph = (lt / kAcc) & 1;
+        mbar_wait_cluster(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int i = 0; i < iters_per_tile; ++i, ++it) {
+          const uint32_t s = it % k2Stages;
+          const uint32_t ph = (it / k2Stages) & 1;
+          mbar_wait_cluster(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * k2StageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma2_ss<Act<T>::kBytes>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                     (i | k) != 0 ? 1u : 0u);
+          tc_commit2(&empty_bar[s]);
+        }
+        tc_commit2(&acc_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint8_t* stg = smem + k2Stages * k2StageBytes + 256 + 2048 + q * 4096;
+    uint32_t lt = 0;
+    for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
+      const int mp = tile / p.n_tiles;
+      const int nt = tile - mp * p.n_tiles;
+      const uint32_t as = lt % kAcc;
+      const uint32_t aph = (lt / kAcc) & 1;
+      const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<T, BLOCK_N, false>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane, mp * 2 + (int)rank,
+                                       nt * BLOCK_N, as, aph, rank);
+      tc_fence_before();
+      mbar_arrive_remote(&acc_empty[as], 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -605,6 +760,42 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
 }
 
+template <typename T>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm2_tcgen05_kernel<T>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
+  const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = k2SmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp);
+  if (e != cudaSuccess) {
+    set_error("gemm2_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 1;
+  }
+  return check_launch("gemm2_tcgen05_kernel");
+}
+
 int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d != nullptr, "aitb_gemm: null descriptor");
   AITB_REQUIRE(d->dtype == AITB_F32 || d->dtype == AITB_BF16, "aitb_gemm: bad dtype %d", d->dtype);
@@ -645,8 +836,11 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, d->a.box, "A")) return 1;
   const uint64_t wdims[2] = {(uint64_t)w_taps * d->k_per_tap, (uint64_t)d->N};
   const uint64_t wstr[1] = {(uint64_t)w_taps * d->k_per_tap * eb};
-  const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(d->block_n > 256 ? 256 : d->block_n)};
   const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
+  static const bool no_2cta = getenv("AITB_NO_2CTA") != nullptr;
+  const bool two_cta = !cluster_ln && !no_2cta && d->block_n == 256 && d->a_group_c == 0 && !d->dual &&
+                       (d->M + kBlockM - 1) / kBlockM >= 2;
+  const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(two_cta ? 128 : (d->block_n > 256 ? 256 : d->block_n))};
   if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
 
   GemmKParams kp;
@@ -690,6 +884,9 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   if (cluster_ln)
     return d->dtype == AITB_F32 ? launch_gemm<float, 256, true>(tmA, tmB, kp, stream)
                                 : launch_gemm<__nv_bfloat16, 256, true>(tmA, tmB, kp, stream);
+  if (two_cta)
+    return d->dtype == AITB_F32 ? launch_gemm2<float>(tmA, tmB, kp, stream)
+                                : launch_gemm2<__nv_bfloat16>(tmA, tmB, kp, stream);
   switch (d->block_n) {
     case 64: return AITB_DISPATCH(64);
     case 128: return AITB_DISPATCH(128);
