@@ -199,10 +199,11 @@ __device__ __forceinline__ void tc_commit2(uint64_t* bar) {
       "h"((uint16_t)3)
       : "memory");
 }
-// plain (no tx) arrive on a barrier living in CTA `rank` of the cluster
+// plain (no tx) arrive on a barrier living in CTA `rank` of the cluster.  Default (cta-scope) semantics on
+// purpose: a `.release.cluster` arrive carries a cluster-wide fence that stalls the issuing thread for
+// ~1000 cycles -- measured: it halved the 2-CTA main loop when the peer's producer used it per stage.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank))
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), rank)) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -610,13 +610,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
         const uint32_t as = lt % kAcc;
         const uint32_t aph = (lt / kAcc) & 1;
-        mbar_wait_cluster(&acc_empty[as], aph ^ 1);
+        mbar_wait(&acc_empty[as], aph ^ 1);  // plain (cta-scope) wait: a cluster-scope acquire costs ~500 clk per poll
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int i = 0; i < iters_per_tile; ++i, ++it) {
           const uint32_t s = it % k2Stages;
           const uint32_t ph = (it / k2Stages) & 1;
-          mbar_wait_cluster(&full_bar[s], ph);
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * k2StageBytes);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
