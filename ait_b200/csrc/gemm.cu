@@ -97,7 +97,7 @@ template <typename T, int BLOCK_N, bool CL>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
                                               uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
                                               int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
-                                              uint32_t cta_rank) {
+                                              uint32_t cta_rank, int c_begin = 0, int c_end = BLOCK_N) {
   constexpr int kRowBytes = 32 * (int)sizeof(T);       // one staged row: 32 columns
   constexpr int kCh = kRowBytes / 16;                  // 16-byte pieces per row (8 | 4)
   constexpr int kRpi = 32 / kCh;                       // rows covered by one warp instruction (4 | 8)
@@ -209,17 +209,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
         const bool aux_acc = !aux_res && (p.flags & AITB_EPI_ACCUM) != 0;
         uint4 pre[kIt];
-        if (aux_res) issue_loads(rptr, 0, pre);
-        if (aux_acc) issue_loads(optr, 0, pre);
+        if (aux_res) issue_loads(rptr, c_begin, pre);
+        if (aux_acc) issue_loads(optr, c_begin, pre);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
           uint4 cur[kIt];
           if (aux_res || aux_acc) {
 #pragma unroll
             for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
-            if (c0 + 32 < BLOCK_N) {
+            if (c0 + 32 < c_end) {
               if (aux_res) issue_loads(rptr, c0 + 32, pre); else issue_loads(optr, c0 + 32, pre);
             }
           }
@@ -528,10 +528,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 static constexpr int k2Stages = 6;
 static constexpr int k2StageBytes = kABytes + 128 * 128;  // A (own 128 rows) + half of B
-static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + 2048 + 4 * 4096;
+static constexpr int k2Threads = 384;  // warpgroup 0: TMA / MMA (+2 idle warps); warpgroups 1, 2: epilogue
+static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + 8 * 4096;
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const GemmKParams p) {
   constexpr int BLOCK_N = 256;
@@ -559,7 +560,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int s = 0; s < kAcc; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 256);
+      mbar_init(&acc_empty[s], 512);  // 2 CTAs x 8 epilogue warps
     }
     fence_mbar_init();
   }
@@ -578,6 +579,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
   const int iters_per_tile = p.taps * p.k_chunks;
 
+  // register re-balancing: the epilogue is instruction-bound (one accumulator row per thread, ~150
+  // instructions per 32-column chunk), so it gets two warpgroups and most of the register file
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
@@ -630,9 +635,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_commit2(&acc_full[as]);
       }
     }
+  }
   } else {
-    const int q = warp & 3;
-    uint8_t* stg = smem + k2Stages * k2StageBytes + 256 + 2048 + q * 4096;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;            // TMEM lane quadrant
+    const int half = (warp - 4) >> 2;  // which 128 columns of the 256-wide tile this warp drains
+    uint8_t* stg = smem + k2Stages * k2StageBytes + 256 + (warp - 4) * 4096;
     uint32_t lt = 0;
     for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
       const int mp = tile / p.n_tiles;
@@ -641,7 +649,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
       epilogue_tile<T, BLOCK_N, false>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane, mp * 2 + (int)rank,
-                                       nt * BLOCK_N, as, aph, rank);
+                                       nt * BLOCK_N, as, aph, rank, half * 128, half * 128 + 128);
       tc_fence_before();
       mbar_arrive_remote(&acc_empty[as], 0);
     }
@@ -777,7 +785,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(k2Threads);
   cfg.dynamicSmemBytes = k2SmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -197,7 +197,26 @@ class HeadEngine:
     def workspace_bytes(self, B, P):
         return L.load().aitb_head_workspace_bytes(B, P, self.dt)
 
+    # units processed per library call: bounds the activation workspace (~0.87 GB fp32 / 0.44 GB bf16 per
+    # unit at P = 300) without changing any result -- units are independent
+    MAX_UNITS_PER_CALL = 16
+
     def head_forward(self, non_img, non_qry, rois, taps=False, out=None):
+        B = non_img.shape[0]
+        if B > self.MAX_UNITS_PER_CALL and not taps:
+            P = rois.shape[1]
+            if out is None:
+                out = (torch.empty((B, P, 1), dtype=torch.float32, device=non_img.device),
+                       torch.empty((B, P, 4), dtype=torch.float32, device=non_img.device))
+            for u0 in range(0, B, self.MAX_UNITS_PER_CALL):
+                u1 = min(B, u0 + self.MAX_UNITS_PER_CALL)
+                r = rois[u0:u1].clone()
+                r[..., 0] -= u0                       # roi batch index is relative to the chunk's maps
+                self._head_forward_chunk(non_img[u0:u1], non_qry[u0:u1], r, False, (out[0][u0:u1], out[1][u0:u1]))
+            return out
+        return self._head_forward_chunk(non_img, non_qry, rois, taps, out)
+
+    def _head_forward_chunk(self, non_img, non_qry, rois, taps=False, out=None):
         if not (self.has_ait and self.has_sk and self.has_top and self.has_heads):
             raise RuntimeError("engine built without the full head")
         lib = L.load()

@@ -141,3 +141,21 @@ def test_benchmark_shape_properties():
     perm = torch.randperm(P, generator=torch.Generator().manual_seed(0)).to(DEV)
     cp, bpred = head(non_img[5:6], non_qry[5:6], r5[:, perm])
     assert torch.equal(cp[0], c5[0][perm]) and torch.equal(bpred[0], b5[0][perm])
+
+
+def test_unit_chunking_is_invisible():
+    """More units than one library call takes (workspace bound): identical to running the chunks by hand."""
+    head, _ = golden_head()
+    head = head.to(DEV)
+    eng = head.engine()
+    B, P = 5, 6
+    non_img, non_qry, rois = head_inputs(B, P, first_unit=30)
+    non_img, non_qry, rois = non_img.to(DEV), non_qry.to(DEV), rois.to(DEV)
+    ref_c, ref_b = eng.head_forward(non_img, non_qry, rois)
+    old = eng.MAX_UNITS_PER_CALL
+    try:
+        eng.MAX_UNITS_PER_CALL = 2
+        c, b = eng.head_forward(non_img, non_qry, rois)
+    finally:
+        eng.MAX_UNITS_PER_CALL = old
+    assert torch.equal(c, ref_c) and torch.equal(b, ref_b)
