@@ -17,9 +17,14 @@
 //   sum_h O_h * gate_h = sum_h P_h (V_h * gate_h)   (the gate scales V's columns; heads
 //                                                    accumulate into ONE 64x64 register tile)
 // Pass A computes P_h, its column sums and s; pass B recomputes P_h (cheap: 64x64x64) and
-// accumulates the gated PV product.  Shared memory drops to ~72 KB -> 3 CTAs per SM.
-// The 64x64x64 products run on mma.sync m16n8k8 TF32 (fp32 accumulate); this block is ~1% of the
-// head's FLOPs, the tcgen05 kernels carry the projections around it.
+// accumulates the gated PV product, with P kept in registers (the m16n8k16 C fragment IS the next
+// A fragment).  Shared memory is ~31 KB -> 7 CTAs per SM.
+// The 64x64x64 products run on mma.sync m16n8k16 with fp16 operands fed by ldmatrix: fp16 carries the
+// same 11-bit significand as tf32 (and holds bf16 inputs exactly), with half the shared-memory traffic
+// and twice the MMA width; Q/K/V are LayerNorm-bounded projections, conversions saturate at 65504, the
+// accumulation is fp32.  This block is ~1% of the head's FLOPs; the tcgen05 kernels carry the
+// projections around it.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,8 +36,7 @@ namespace aitb {
 static constexpr int kT = 64;    // tokens
 static constexpr int kD = 64;    // head dim
 static constexpr int kH = 8;     // heads
-static constexpr int kQS = 68;   // smem row stride (floats) of Q, K, P tiles (conflict-free frags)
-static constexpr int kVS = 72;   // smem row stride of V
+static constexpr int kHS = 72;   // smem row stride in halves (144 B: 16-B aligned rows, conflict-free ldmatrix)
 static constexpr int kAttnThreads = 128;
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -41,12 +45,28 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+// fp16 operands (11-bit significand = the tf32 operand precision, and exact for bf16 inputs), fp32 accumulate
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float sat_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 
 __device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
@@ -56,43 +76,38 @@ __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// 64x64 tile global -> smem (tf32-rounded), optional per-column scale (the head gate)
+// 64x64 tile global -> smem as fp16 (saturating), rows of kHS halves
 template <typename T>
-__device__ __forceinline__ void load_tile(const T* __restrict__ g, int ld, float* __restrict__ s, int stride,
-                                          const float* __restrict__ colscale) {
+__device__ __forceinline__ void load_tile(const T* __restrict__ g, int ld, __half* __restrict__ s) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int f = threadIdx.x + kAttnThreads * i;
     const int r = f >> 4, c4 = (f & 15) * 4;
-    float4 v = load4(g + (size_t)r * ld + c4);
-    if (colscale) {
-      v.x *= colscale[c4 + 0]; v.y *= colscale[c4 + 1]; v.z *= colscale[c4 + 2]; v.w *= colscale[c4 + 3];
-    }
-    float* d = s + r * stride + c4;
-    d[0] = to_tf32(v.x); d[1] = to_tf32(v.y); d[2] = to_tf32(v.z); d[3] = to_tf32(v.w);
+    const float4 v = load4(g + (size_t)r * ld + c4);
+    uint2 o;
+    o.x = pack_h2(sat_h(v.x), sat_h(v.y));
+    o.y = pack_h2(sat_h(v.z), sat_h(v.w));
+    *reinterpret_cast<uint2*>(s + r * kHS + c4) = o;
   }
 }
 
-// S = Q K^T / 8 for this warp's 16 rows, mask, softmax in registers.  p[nt][0..3] follows the mma
-// C layout: rows (g, g+8), cols nt*8 + 2t, +1.
-__device__ __forceinline__ void scores_softmax(const float* __restrict__ Qs, const float* __restrict__ Ks, int row0,
+// S = Q K^T / 8 for this warp's 16 rows (m16n8k16 fp16 MMAs fed by ldmatrix), mask, softmax in registers.
+// p[nt][0..3] follows the mma C layout: rows (g, g+8), cols nt*8 + 2t, +1.
+__device__ __forceinline__ void scores_softmax(const __half* __restrict__ Qs, const __half* __restrict__ Ks, int row0,
                                                int mask_mode, int n_keys, float (&p)[8][4]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
 #pragma unroll
-  for (int k0 = 0; k0 < kD; k0 += 8) {
+  for (int k0 = 0; k0 < kD; k0 += 16) {
     uint32_t a[4];
-    a[0] = __float_as_uint(Qs[(row0 + g) * kQS + k0 + t]);
-    a[1] = __float_as_uint(Qs[(row0 + g + 8) * kQS + k0 + t]);
-    a[2] = __float_as_uint(Qs[(row0 + g) * kQS + k0 + t + 4]);
-    a[3] = __float_as_uint(Qs[(row0 + g + 8) * kQS + k0 + t + 4]);
+    ldsm_x4(a, Qs + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + k0 + 8 * (lane >> 4));
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t b[2];
-      b[0] = __float_as_uint(Ks[(nt * 8 + g) * kQS + k0 + t]);
-      b[1] = __float_as_uint(Ks[(nt * 8 + g) * kQS + k0 + t + 4]);
-      mma_tf32(p[nt], a, b);
+    for (int j = 0; j < 8; j += 2) {  // two key tiles per ldmatrix.x4
+      uint32_t b[4];
+      ldsm_x4(b, Ks + (8 * j + (lane & 7) + 8 * (lane >> 4)) * kHS + k0 + 8 * ((lane >> 3) & 1));
+      mma_f16(p[j], a, b[0], b[1]);
+      mma_f16(p[j + 1], a, b[2], b[3]);
     }
   }
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
@@ -133,18 +148,16 @@ __device__ __forceinline__ void scores_softmax(const float* __restrict__ Qs, con
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 4)
 attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
                  int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
                  T* __restrict__ out, int round_tf) {
-  extern __shared__ float sm[];
-  float* Qs = sm;                    // [64][68]
-  float* Ks = Qs + kT * kQS;         // [64][68]
-  float* Vs = Ks + kT * kQS;         // [64][72]
-  float* Ps = Vs + kT * kVS;         // [4 warps][16][68]
-  float* colsum = Ps + 4 * 16 * kQS; // [4][64]
-  float* svec = colsum + 4 * kD;     // [2][64] partial s, then s
-  float* gate = svec + 2 * kD;       // [8][64]
+  __shared__ __align__(16) __half Qs[kT * kHS];
+  __shared__ __align__(16) __half Ks[kT * kHS];
+  __shared__ __align__(16) __half Vs[kT * kHS];
+  __shared__ float colsum[4 * kD];  // per-warp column sums of P_h
+  __shared__ float svec[2 * kD];    // partial s, then s
+  __shared__ float gate[kH * kD];
 
   const int grp = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -157,9 +170,9 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
   float s_part = 0.f;  // thread (half = tid >> 6, c = tid & 63)
   for (int h = 0; h < kH; ++h) {
     __syncthreads();
-    load_tile(qg + h * kD, ldq, Qs, kQS, nullptr);
-    load_tile(kg + h * kD, ldkv, Ks, kQS, nullptr);
-    load_tile(vg + h * kD, ldkv, Vs, kVS, nullptr);
+    load_tile(qg + h * kD, ldq, Qs);
+    load_tile(kg + h * kD, ldkv, Ks);
+    load_tile(vg + h * kD, ldkv, Vs);
     __syncthreads();
     float p[8][4];
     scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
@@ -183,7 +196,7 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
 #pragma unroll 8
       for (int j = half * 32; j < half * 32 + 32; ++j) {
         const float cs = colsum[j] + colsum[kD + j] + colsum[2 * kD + j] + colsum[3 * kD + j];
-        acc += cs * Vs[j * kVS + c];
+        acc += cs * __half2float(Vs[j * kHS + c]);
       }
       s_part += acc;
     }
@@ -217,43 +230,42 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
     for (int h = 0; h < kH; ++h) gate[h * kD + c] = e[h] * inv;
   }
 
-  // ---------------- pass B: out = sum_h P_h (V_h * gate_h)
+  // ---------------- pass B: out = sum_h (P_h V_h) * gate_h ; P stays in registers (C fragment -> A fragment)
   float o_acc[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
-  float* Pw = Ps + warp * 16 * kQS;
   for (int h = 0; h < kH; ++h) {
     __syncthreads();
-    load_tile(qg + h * kD, ldq, Qs, kQS, nullptr);
-    load_tile(kg + h * kD, ldkv, Ks, kQS, nullptr);
-    load_tile(vg + h * kD, ldkv, Vs, kVS, gate + h * kD);
+    load_tile(qg + h * kD, ldq, Qs);
+    load_tile(kg + h * kD, ldkv, Ks);
+    load_tile(vg + h * kD, ldkv, Vs);
     __syncthreads();
     float p[8][4];
     scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
+    float oh[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      Pw[g * kQS + nt * 8 + 2 * t] = to_tf32(p[nt][0]);
-      Pw[g * kQS + nt * 8 + 2 * t + 1] = to_tf32(p[nt][1]);
-      Pw[(g + 8) * kQS + nt * 8 + 2 * t] = to_tf32(p[nt][2]);
-      Pw[(g + 8) * kQS + nt * 8 + 2 * t + 1] = to_tf32(p[nt][3]);
-    }
-    __syncwarp();
+    for (int nt = 0; nt < 8; ++nt) oh[nt][0] = oh[nt][1] = oh[nt][2] = oh[nt][3] = 0.f;
 #pragma unroll
-    for (int k0 = 0; k0 < kT; k0 += 8) {
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
       uint32_t a[4];
-      a[0] = __float_as_uint(Pw[g * kQS + k0 + t]);
-      a[1] = __float_as_uint(Pw[(g + 8) * kQS + k0 + t]);
-      a[2] = __float_as_uint(Pw[g * kQS + k0 + t + 4]);
-      a[3] = __float_as_uint(Pw[(g + 8) * kQS + k0 + t + 4]);
+      a[0] = pack_h2(p[2 * kk][0], p[2 * kk][1]);
+      a[1] = pack_h2(p[2 * kk][2], p[2 * kk][3]);
+      a[2] = pack_h2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+      a[3] = pack_h2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t b[2];
-        b[0] = __float_as_uint(Vs[(k0 + t) * kVS + nt * 8 + g]);
-        b[1] = __float_as_uint(Vs[(k0 + t + 4) * kVS + nt * 8 + g]);
-        mma_tf32(o_acc[nt], a, b);
+      for (int j = 0; j < 8; j += 2) {  // two d tiles per transposed ldmatrix.x4
+        uint32_t b[4];
+        ldsm_x4_trans(b, Vs + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + 8 * j + 8 * (lane >> 4));
+        mma_f16(oh[j], a, b[0], b[1]);
+        mma_f16(oh[j + 1], a, b[2], b[3]);
       }
     }
-    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 gv = *reinterpret_cast<const float2*>(&gate[h * kD + nt * 8 + 2 * t]);
+      o_acc[nt][0] += oh[nt][0] * gv.x; o_acc[nt][1] += oh[nt][1] * gv.y;
+      o_acc[nt][2] += oh[nt][2] * gv.x; o_acc[nt][3] += oh[nt][3] * gv.y;
+    }
   }
   T* og = out + (size_t)grp * kT * kD;
 #pragma unroll
@@ -270,9 +282,6 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
   }
 }
 
-static constexpr size_t kAttnSmem =
-    (size_t)(2 * kT * kQS + kT * kVS + 4 * 16 * kQS + 4 * kD + 2 * kD + kH * kD) * sizeof(float);
-
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
                   int round_tf) {
@@ -282,26 +291,14 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
   AITB_REQUIRE(mask_mode == 0 || mask_mode == 1, "aitb_attn_core: mask_mode must be 0 (key padding) or 1 (causal)");
   AITB_REQUIRE(n_keys >= 1 && n_keys <= kT, "aitb_attn_core: n_keys=%d out of range", n_keys);
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "aitb_attn_core: leading dimensions must be multiples of 4");
-  static bool attr[2] = {false, false};
   if (dtype == AITB_F32) {
-    auto kern = attn_core_kernel<float>;
-    if (!attr[0]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem);
-      AITB_REQUIRE(e == cudaSuccess, "aitb_attn_core: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      attr[0] = true;
-    }
-    kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const float*)q, ldq, q_rep, (const float*)k, (const float*)v, ldkv,
-                                                 w_sk, b_sk, mask_mode, n_keys, (float*)out, round_tf);
+    attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
+                                                            (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
+                                                            (float*)out, round_tf);
   } else if (dtype == AITB_BF16) {
-    auto kern = attn_core_kernel<__nv_bfloat16>;
-    if (!attr[1]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem);
-      AITB_REQUIRE(e == cudaSuccess, "aitb_attn_core: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      attr[1] = true;
-    }
-    kern<<<G, kAttnThreads, kAttnSmem, stream>>>((const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k,
-                                                 (const __nv_bfloat16*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
-                                                 (__nv_bfloat16*)out, 0);
+    attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
+        (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
+        mask_mode, n_keys, (__nv_bfloat16*)out, 0);
   } else {
     set_error("aitb_attn_core: bad dtype %d", dtype);
     return 1;
