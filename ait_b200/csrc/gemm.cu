@@ -1,16 +1,24 @@
 // tcgen05 GEMM for the AIT head:  out[M,N] = epilogue( A[M,K] * W[N,K]^T )
 //
-//   * A and W tiles arrive by TMA (128-byte swizzle) into a 4-stage shared-memory ring.
+//   * A and W tiles arrive by TMA (128-byte swizzle) into a shared-memory mbarrier ring.
 //     A is addressed through a 4-D strided view, so a 3x3 convolution on an 8x8 / 4x4 map is a
 //     loop over 9 shifted boxes (out-of-bounds rows are zero-filled by TMA = the conv padding)
 //     and a stride-2 1x1 convolution is just a strided view.  No im2col buffer exists.
-//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N<=256 per instruction,
-//     K = 32 bytes per instruction: 8 x tf32 or 16 x bf16); accumulators live in TMEM.
-//   * persistent CTAs (one per SM) walk the tile list; with BLOCK_N <= 256 the accumulator is
-//     double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-//   * 4 epilogue warps read TMEM with tcgen05.ld (one output row per thread) and apply the fused
-//     epilogue: bias, ReLU / ReLU^2, residual, positional table, full-row LayerNorm (N = 512
-//     held entirely in TMEM: mean / variance are per-thread reductions, no shuffles needed).
+//   * one elected thread issues tcgen05.mma (K = 32 bytes per instruction: 8 x tf32 or 16 x bf16);
+//     accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of
+//     tile i+1; persistent CTAs walk the tile list.
+//   * the epilogue warps read TMEM with tcgen05.ld (one output row per thread) and apply the fused
+//     epilogue: bias, ReLU / ReLU^2, dual-accumulator sum, residual, positional table, LayerNorm.
+//
+// Three kernels share that machinery (and `epilogue_tile`):
+//   gemm2_tcgen05_kernel          2-CTA pairs (cta_group::2): 256x256 tile, each CTA stages its 128 rows of A
+//                                 and HALF of the W tile, 6-stage ring, two epilogue warpgroups (setmaxnreg).
+//                                 All wide plain / conv GEMMs (QKV, FFN w_1, K/V, dec_trans, layer4).
+//   gemm_tcgen05_kernel<.., CL>   "cluster LayerNorm": the N = 512 row is split over a 2-CTA cluster
+//                                 (2 x 256 columns); partial row statistics travel through DSMEM.
+//                                 enc_emb / dec_emb, attention fc, FFN w_2.
+//   gemm_tcgen05_kernel<.., !CL>  single-CTA (cta_group::1, M = 128): grouped SKBlock convolutions with the
+//                                 dual accumulator (BLOCK_N = 128) and the tiny query-branch GEMMs.
 //
 // Reference ops this replaces (all plain torch calls into cuBLAS/cuDNN in the reference):
 //   nn.Conv2d 1x1 (system/Models.py:188-209), nn.Linear in MultiHeadAttention / FFN
@@ -74,9 +82,9 @@ template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 512) ? 2 : 4;
-  static constexpr int kAccStages = (BLOCK_N == 512) ? 1 : 2;
-  static constexpr int kUmmaN = (BLOCK_N > 256) ? 256 : BLOCK_N;
+  static constexpr int kStages = 4;
+  static constexpr int kAccStages = 2;
+  static constexpr int kUmmaN = BLOCK_N;
   // accumulator stage stride in TMEM columns; BLOCK_N = 128 reserves room for the dual accumulator
   static constexpr int kAccStride = (BLOCK_N == 128) ? 256 : BLOCK_N;
   static constexpr int kTmemCols = (kAccStride * kAccStages < 32) ? 32 : kAccStride * kAccStages;
@@ -446,8 +454,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_4d(sa, &tmA, &full_bar[s], a_c_base + kc * p.ke, c1, c2, c3);
             const int kb = (tap * p.k_chunks + kc) * p.ke;
             tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
-            if constexpr (BLOCK_N > 256)
-              tma_load_2d(sb + 256 * 128, &tmB, &full_bar[s], kb, nt * BLOCK_N + 256);
           }
         }
       }

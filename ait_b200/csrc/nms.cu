@@ -17,7 +17,8 @@
 //
 // IoU arithmetic follows devIoU (nms.cu:13-21) with the legacy +1 convention; every operation
 // is an explicitly rounded IEEE op (__fadd_rn/__fmul_rn/__fdiv_rn) so no FMA contraction can
-// change a comparison: results are bit-exact against the C oracle (oracle/oracle_ops.c).
+// change a comparison: results are bit-exact against the C oracle (oracle/oracle_ops.c).  The
+// IEEE division is only executed when inter / den is within 4e-6 of the threshold (iou_gt).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,17 +28,6 @@
 namespace aitb {
 
 typedef unsigned long long u64;
-
-__device__ __forceinline__ float iou_legacy(const float4 a, const float4 b) {
-  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
-  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
-  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
-  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
-  const float inter = __fmul_rn(width, height);
-  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
-  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
-}
 
 __global__ void nms_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ order,
                                   float4* __restrict__ sorted, int n_total, int n) {
