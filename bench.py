@@ -33,6 +33,7 @@ PRE_NMS, NMS_THR = 6000, 0.7
 FLOP_PER_PAIR = 1.494e9          # de-duplicated algorithmic FLOPs per pair (SURVEY 8d / BASELINE.md section 3)
 FLOP_PER_UNIT_SHARED = 0.214e9 + 0.646e9
 METRIC = "proposal-query pairs/sec (ROIAlign+AIT head+NMS)"
+FFN_W1_DRAM_BYTES = {"tf32": 0.343995e9 + 1.210071e9, "bf16": None}   # measured with ncu, see profiles/
 
 
 def parse():
@@ -345,9 +346,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (FFN w_1: M=%d N=%d K=%d, bias+ReLU epilogue)" % (M, N, K),
+            "roofline": {"bound": "tensor", "kernel": "gemm2_tcgen05_kernel (2-CTA tcgen05, FFN w_1: M=%d N=%d K=%d, bias+ReLU epilogue; "
+                                   "the largest single launch, 9%% of the step's FLOPs)" % (M, N, K),
                          "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed
+                         # `ncu --set full` capture (profiles/r01_ncu_full_selected.csv); algorithmic bytes are
+                         # A 314.6 MB + W 4.2 MB + out 1258.3 MB = 1.577e9 (fp32), so nothing is re-read
+                         "traffic": FFN_W1_DRAM_BYTES.get(args.dtype),
+                         "traffic_unit": "bytes/launch (ncu, tf32 capture)",
                          "peak_source": "%s bf16 cuBLAS burst %.1f TFLOP/s%s" % (src, tf_burst, "" if args.dtype == "bf16" else " / 2 (tf32 runs at half the bf16 rate; no tf32 figure in MEASURED_PEAKS.json)"),
                          "frac_of_bf16_peak": gemm_tflops / tf_burst,
                          "head_step_tflops": step_flops / (ms_head * 1e-3) / 1e12,
