@@ -6,7 +6,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaitb200.so")
 
-AITB_F32, AITB_BF16 = 0, 1
+AITB_F32, AITB_BF16, AITB_F32S = 0, 1, 2
+
+# Compute configurations of the engine (include/aitb200.h):
+#   "fp32"  AITB_F32S  split bf16 hi/lo planes, three bf16 tensor-core passes per product (fp32-class results:
+#                      the configuration that meets the reference's fp32 scores to 1e-3)
+#   "tf32"  AITB_F32   fp32 storage, tf32 tensor-core math (faster, 10-bit operand mantissa)
+#   "bf16"  AITB_BF16  bf16 storage and math
+MODES = {"fp32": AITB_F32S, "tf32": AITB_F32, "bf16": AITB_BF16}
 
 EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL = (
     1, 2, 4, 8, 16, 32, 64, 128, 256)
@@ -29,7 +36,7 @@ class GemmDesc(C.Structure):
         ("res_div", C.c_int), ("res_rep", C.c_int),
         ("pos", C.c_void_p), ("pos_rows", C.c_int),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
-        ("dual", C.c_int), ("bias2", C.c_void_p),
+        ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int),
     ]
 
 
@@ -144,6 +151,27 @@ def stream_ptr():
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def mode_name(compute_dtype):
+    """torch.float32 | "fp32" -> "fp32" (split, fp32-class); "tf32"; torch.bfloat16 | "bf16" -> "bf16"."""
+    import torch
+    if isinstance(compute_dtype, str):
+        if compute_dtype not in MODES:
+            raise RuntimeError("ait_b200: compute_dtype must be one of %s, torch.float32 or torch.bfloat16; got %r"
+                               % (sorted(MODES), compute_dtype))
+        return compute_dtype
+    if compute_dtype == torch.float32:
+        return "fp32"
+    if compute_dtype == torch.bfloat16:
+        return "bf16"
+    raise RuntimeError("ait_b200 supports float32 (fp32-class split or tf32 tensor-core math) and bfloat16 only, "
+                       "got %s (the reference's fp64 dispatch is not provided)" % (compute_dtype,))
+
+
+def storage_dtype(mode):
+    import torch
+    return torch.float32 if mode == "tf32" else torch.bfloat16
 
 
 def dtype_enum(torch_dtype):

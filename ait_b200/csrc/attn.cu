@@ -282,6 +282,250 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// AITB_F32S ("fp32-class") variant: Q / K / V arrive as split bf16 planes (x = hi + lo, 16 mantissa
+// bits) and every product runs as three bf16 m16n8k16 MMAs  hi*hi + hi*lo + lo*hi  with fp32
+// accumulation; P is split the same way in registers.  Same two-pass structure as above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 64x64 bf16 tile (one plane) global -> smem, rows of kHS elements; 16-byte copies
+__device__ __forceinline__ void load_plane(const __nv_bfloat16* __restrict__ g, int ld, __nv_bfloat16* __restrict__ s) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = threadIdx.x + kAttnThreads * i;
+    const int r = f >> 3, c8 = (f & 7) * 8;
+    *reinterpret_cast<uint4*>(s + r * kHS + c8) = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * ld + c8));
+  }
+}
+
+__device__ __forceinline__ void scores_softmax_split(const __nv_bfloat16* __restrict__ Qh, const __nv_bfloat16* __restrict__ Ql,
+                                                     const __nv_bfloat16* __restrict__ Kh, const __nv_bfloat16* __restrict__ Kl,
+                                                     int row0, int mask_mode, int n_keys, float (&p)[8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < kD; k0 += 16) {
+    uint32_t ah[4], al[4];
+    const int aoff = (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + k0 + 8 * (lane >> 4);
+    ldsm_x4(ah, Qh + aoff);
+    ldsm_x4(al, Ql + aoff);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint32_t bh[4], bl[4];
+      const int boff = (8 * j + (lane & 7) + 8 * (lane >> 4)) * kHS + k0 + 8 * ((lane >> 3) & 1);
+      ldsm_x4(bh, Kh + boff);
+      ldsm_x4(bl, Kl + boff);
+      mma_bf16(p[j], al, bh[0], bh[1]);
+      mma_bf16(p[j], ah, bl[0], bl[1]);
+      mma_bf16(p[j], ah, bh[0], bh[1]);
+      mma_bf16(p[j + 1], al, bh[2], bh[3]);
+      mma_bf16(p[j + 1], ah, bl[2], bl[3]);
+      mma_bf16(p[j + 1], ah, bh[2], bh[3]);
+    }
+  }
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + 2 * t + (e & 1);
+      const int row = (e < 2) ? r_lo : r_hi;
+      const bool masked = mask_mode == 0 ? (col >= n_keys) : (col > row);
+      const float v = masked ? -1e9f : p[nt][e] * 0.125f;  // masked_fill(mask == 0, -1e9)
+      p[nt][e] = v;
+      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
+    }
+  }
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] = expf(p[nt][0] - m_lo); p[nt][1] = expf(p[nt][1] - m_lo);
+    p[nt][2] = expf(p[nt][2] - m_hi); p[nt][3] = expf(p[nt][3] - m_hi);
+    s_lo += p[nt][0] + p[nt][1];
+    s_hi += p[nt][2] + p[nt][3];
+  }
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+  const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] *= i_lo; p[nt][1] *= i_lo; p[nt][2] *= i_hi; p[nt][3] *= i_hi;
+  }
+}
+
+static constexpr int kSplitSmem = 6 * kT * kHS * 2 + (4 * kD + 2 * kD + kH * kD) * 4;
+
+// q / k / v point at the hi planes; the lo planes start q_lo / kv_lo elements further; ldq / ldkv are the
+// physical (bf16) row pitches.  out: [G*64, hi 64 | lo 64].
+__global__ void __launch_bounds__(kAttnThreads, 3)
+attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, int q_rep,
+                       const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv, int kv_lo,
+                       const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
+                       __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* Ql = Qh + kT * kHS;
+  __nv_bfloat16* Kh = Ql + kT * kHS;
+  __nv_bfloat16* Kl = Kh + kT * kHS;
+  __nv_bfloat16* Vh = Kl + kT * kHS;
+  __nv_bfloat16* Vl = Vh + kT * kHS;
+  float* colsum = reinterpret_cast<float*>(Vl + kT * kHS);  // [4][kD]
+  float* svec = colsum + 4 * kD;                            // [2][kD]
+  float* gate = svec + 2 * kD;                              // [kH][kD]
+
+  const int grp = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16;
+  const __nv_bfloat16* qg = q + (size_t)(grp / q_rep) * kT * ldq;
+  const __nv_bfloat16* kg = k + (size_t)grp * kT * ldkv;
+  const __nv_bfloat16* vg = v + (size_t)grp * kT * ldkv;
+
+  auto load_head = [&](int h) {
+    load_plane(qg + h * kD, ldq, Qh);
+    load_plane(qg + q_lo + h * kD, ldq, Ql);
+    load_plane(kg + h * kD, ldkv, Kh);
+    load_plane(kg + kv_lo + h * kD, ldkv, Kl);
+    load_plane(vg + h * kD, ldkv, Vh);
+    load_plane(vg + kv_lo + h * kD, ldkv, Vl);
+  };
+
+  // ---------------- pass A
+  float s_part = 0.f;
+  for (int h = 0; h < kH; ++h) {
+    __syncthreads();
+    load_head(h);
+    __syncthreads();
+    float p[8][4];
+    scores_softmax_split(Qh, Ql, Kh, Kl, row0, mask_mode, n_keys, p);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float c0 = p[nt][0] + p[nt][2], c1 = p[nt][1] + p[nt][3];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      }
+      if (g == 0) {
+        colsum[warp * kD + nt * 8 + 2 * t] = c0;
+        colsum[warp * kD + nt * 8 + 2 * t + 1] = c1;
+      }
+    }
+    __syncthreads();
+    {
+      const int half = threadIdx.x >> 6, c = threadIdx.x & 63;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int j = half * 32; j < half * 32 + 32; ++j) {
+        const float cs = colsum[j] + colsum[kD + j] + colsum[2 * kD + j] + colsum[3 * kD + j];
+        acc += cs * (__bfloat162float(Vh[j * kHS + c]) + __bfloat162float(Vl[j * kHS + c]));
+      }
+      s_part += acc;
+    }
+  }
+  svec[(threadIdx.x >> 6) * kD + (threadIdx.x & 63)] = s_part;
+  __syncthreads();
+  if (threadIdx.x < kD) svec[threadIdx.x] = (svec[threadIdx.x] + svec[kD + threadIdx.x]) * (1.f / kT);
+  __syncthreads();
+  for (int o = threadIdx.x; o < kH * kD; o += kAttnThreads) {
+    const float* wr = w_sk + (size_t)o * kD;
+    float acc = __ldg(b_sk + o);
+#pragma unroll 8
+    for (int c = 0; c < kD; c += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
+      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
+    }
+    gate[o] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kD) {
+    const int c = threadIdx.x;
+    float m = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) m = fmaxf(m, gate[h * kD + c]);
+    float e[kH], sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) { e[h] = expf(gate[h * kD + c] - m); sum += e[h]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) gate[h * kD + c] = e[h] * inv;
+  }
+
+  // ---------------- pass B
+  float o_acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
+  for (int h = 0; h < kH; ++h) {
+    __syncthreads();
+    load_head(h);
+    __syncthreads();
+    float p[8][4];
+    scores_softmax_split(Qh, Ql, Kh, Kl, row0, mask_mode, n_keys, p);
+    float oh[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) oh[nt][0] = oh[nt][1] = oh[nt][2] = oh[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+      uint32_t ah[4], al[4];
+      split_pack(p[2 * kk][0], p[2 * kk][1], ah[0], al[0]);
+      split_pack(p[2 * kk][2], p[2 * kk][3], ah[1], al[1]);
+      split_pack(p[2 * kk + 1][0], p[2 * kk + 1][1], ah[2], al[2]);
+      split_pack(p[2 * kk + 1][2], p[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t bh[4], bl[4];
+        const int voff = (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + 8 * j + 8 * (lane >> 4);
+        ldsm_x4_trans(bh, Vh + voff);
+        ldsm_x4_trans(bl, Vl + voff);
+        mma_bf16(oh[j], al, bh[0], bh[1]);
+        mma_bf16(oh[j], ah, bl[0], bl[1]);
+        mma_bf16(oh[j], ah, bh[0], bh[1]);
+        mma_bf16(oh[j + 1], al, bh[2], bh[3]);
+        mma_bf16(oh[j + 1], ah, bl[2], bl[3]);
+        mma_bf16(oh[j + 1], ah, bh[2], bh[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 gv = *reinterpret_cast<const float2*>(&gate[h * kD + nt * 8 + 2 * t]);
+      o_acc[nt][0] += oh[nt][0] * gv.x; o_acc[nt][1] += oh[nt][1] * gv.y;
+      o_acc[nt][2] += oh[nt][2] * gv.x; o_acc[nt][3] += oh[nt][3] * gv.y;
+    }
+  }
+  __nv_bfloat16* og = out + (size_t)grp * kT * 2 * kD;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    uint32_t hi, lo;
+    split_pack(o_acc[nt][0], o_acc[nt][1], hi, lo);
+    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + c) = hi;
+    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + kD + c) = lo;
+    split_pack(o_acc[nt][2], o_acc[nt][3], hi, lo);
+    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + c) = hi;
+    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + kD + c) = lo;
+  }
+}
+
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
                   int round_tf) {
@@ -299,6 +543,18 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
         mask_mode, n_keys, (__nv_bfloat16*)out, 0);
+  } else if (dtype == AITB_F32S) {
+    AITB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "aitb_attn_core: split mode needs leading dimensions that are multiples of 8");
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmem);
+      AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn split) failed: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    // logical leading dimensions -> physical two-plane rows; the lo plane is one logical row width further
+    attn_core_split_kernel<<<G, kAttnThreads, kSplitSmem, stream>>>(
+        (const __nv_bfloat16*)q, 2 * ldq, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, 2 * ldkv, ldkv,
+        w_sk, b_sk, mask_mode, n_keys, (__nv_bfloat16*)out);
   } else {
     set_error("aitb_attn_core: bad dtype %d", dtype);
     return 1;

@@ -60,7 +60,7 @@ int check_launch(const char* what) {
 // (system/Models.py:268-270), so their encoder input is LayerNorm(pos_table[t]) -- independent of
 // the proposal.  One warp per row.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256)
 ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __restrict__ pos,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int round_tf) {
@@ -82,7 +82,7 @@ ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __r
 #pragma unroll
   for (int i = 0; i < 16; ++i) ssq += (v[i] - mean) * (v[i] - mean);
   const float rstd = rsqrtf(warp_sum(ssq) * (1.f / 512.f) + eps);
-  T* xr = x + ((size_t)pair * 64 + t) * 512;
+  T* xr = x + ((size_t)pair * 64 + t) * (SPLIT ? 1024 : 512);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int c = lane + 32 * i;
@@ -93,6 +93,7 @@ ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __r
       o = __uint_as_float(r);
     }
     Act<T>::st(xr + c, o);
+    if constexpr (SPLIT) Act<T>::st(xr + 512 + c, o - Act<T>::ld(xr + c));   // lo plane = x - bf16(x)
   }
 }
 
@@ -102,17 +103,24 @@ static int ln_pad_rows(void* x, int dtype, int n_pairs, int n_valid, const float
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
   if (dtype == AITB_F32)
-    ln_pad_rows_kernel<float><<<grid, 256, 0, st>>>((float*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta, 1e-6f, round_tf);
+    ln_pad_rows_kernel<float, false><<<grid, 256, 0, st>>>((float*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta, 1e-6f,
+                                                           round_tf);
+  else if (dtype == AITB_F32S)
+    ln_pad_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma,
+                                                                  ln.beta, 1e-6f, 0);
   else
-    ln_pad_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta,
-                                                            1e-6f, round_tf);
+    ln_pad_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma,
+                                                                   ln.beta, 1e-6f, round_tf);
   return check_launch("ln_pad_rows_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------
 // GEMM descriptor builders
 // ---------------------------------------------------------------------------------------------
-static inline int esize(int dtype) { return dtype == AITB_F32 ? 4 : 2; }
+// bytes per logical element of an activation / weight row (split mode: two bf16 planes), and bytes per
+// COLUMN step inside a row (split mode: the hi plane is bf16, the lo plane sits `ld` elements further)
+static inline int esize(int dtype) { return dtype == AITB_BF16 ? 2 : 4; }
+static inline int colsize(int dtype) { return dtype == AITB_F32 ? 4 : 2; }
 
 static aitb_gemm_desc gemm_base(int dtype, int M, int N, int K, const void* W, int block_n, void* out, int ldo,
                                 int round_tf) {
@@ -141,11 +149,15 @@ static void view_plain(aitb_gemm_desc& d, const void* A, int lda) {
   d.a.ptr = A;
   d.a.dims[0] = (uint64_t)d.k_per_tap * d.taps;
   if (d.a_group_c) d.a.dims[0] = (uint64_t)lda;  // grouped: the view spans all input channels
+  if (d.dtype == AITB_F32S) {                    // TMA elements are bf16; the lo plane starts lda further
+    d.a.dims[0] += (uint64_t)lda;
+    d.a_lo_off = lda;
+  }
   d.a.dims[1] = (uint64_t)d.M;
   d.a.dims[2] = d.a.dims[3] = 1;
   d.a.strides[0] = (uint64_t)lda * eb;
   d.a.strides[1] = d.a.strides[2] = (uint64_t)lda * eb * d.M;
-  d.a.box[0] = 128 / eb;
+  d.a.box[0] = 128 / colsize(d.dtype);
   d.a.box[1] = 128;
   d.a.box[2] = d.a.box[3] = 1;
   d.a_m_dim = 1;
@@ -157,12 +169,16 @@ static void view_map(aitb_gemm_desc& d, const void* A, int C, int S, int s, int 
   const int eb = esize(d.dtype);
   d.a.ptr = A;
   d.a.dims[0] = (uint64_t)C;
+  if (d.dtype == AITB_F32S) {
+    d.a.dims[0] = (uint64_t)2 * C;
+    d.a_lo_off = C;
+  }
   d.a.dims[1] = d.a.dims[2] = (uint64_t)s;
   d.a.dims[3] = (uint64_t)G;
   d.a.strides[0] = (uint64_t)stride * C * eb;
   d.a.strides[1] = (uint64_t)stride * S * C * eb;
   d.a.strides[2] = (uint64_t)S * S * C * eb;
-  d.a.box[0] = 128 / eb;
+  d.a.box[0] = 128 / colsize(d.dtype);
   d.a.box[1] = d.a.box[2] = (uint32_t)s;
   d.a.box[3] = (uint32_t)(128 / (s * s));
   d.a_m_dim = 3;
@@ -320,7 +336,7 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
 // query per proposal): dec_emb + pos + LN, causal self-attention block, cross-attention query projection.
 // Computed once per unit on the side stream while the encoder runs.
 static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaStream_t st) {
-  const int dt = w->dtype, eb = esize(dt), rt = w->round_tf32;
+  const int dt = w->dtype, cb = colsize(dt), rt = w->round_tf32;
   const int RQ = B * 64;
   aitb_gemm_desc d = gemm_base(dt, RQ, 512, 1024, w->dec_emb.w, 512, hb.T0, 512, rt);
   view_plain(d, hb.qtok, 1024);
@@ -335,7 +351,7 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
   view_plain(dq, hb.T0, 512);
   RUN(gemm_run(&dq, st));
   const uint8_t* qkv = (const uint8_t*)hb.QKVd;
-  RUN(mha_block(w, w->dec_slf, qkv, 1536, 1, qkv + 512 * eb, qkv + 1024 * eb, 1536, B, 1, 64, hb.AOd, hb.T0, 1,
+  RUN(mha_block(w, w->dec_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, B, 1, 64, hb.AOd, hb.T0, 1,
                 hb.T1, st));
   aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
   view_plain(dc, hb.T1, 512);
@@ -346,7 +362,7 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
 // cross attention.  NULL = the query side already ran on `st`.
 static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st,
                     cudaEvent_t query_ready) {
-  const int dt = w->dtype, eb = esize(dt), rt = w->round_tf32;
+  const int dt = w->dtype, eb = esize(dt), cb = colsize(dt), rt = w->round_tf32;
   const int bp = B * P, R = bp * 64;
   // ---- encoder input: enc_emb (1x1 conv 1024->512 + bias) on the 49 real rows, + pos, LayerNorm
   {
@@ -369,7 +385,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     view_plain(d, hb.X1, 512);
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
-    RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * eb, qkv + 1024 * eb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
+    RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
                   hb.X2, st));
   }
   RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st));
@@ -388,7 +404,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     view_plain(d, hb.ENC, 512);
     RUN(gemm_run(&d, st));
     const uint8_t* kv = (const uint8_t*)hb.KVc;
-    RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * eb, 1024, bp, 0, 49, hb.AO, hb.T1, P, hb.D1, st));
+    RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * cb, 1024, bp, 0, 49, hb.AO, hb.T1, P, hb.D1, st));
   }
   RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh, hb.DEC, st));
   // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
@@ -467,7 +483,7 @@ static int layer4(const aitb_head_weights* w, const void* x, int G, void* c1, vo
 
 static int check_weights(const aitb_head_weights* w, bool with_top) {
   AITB_REQUIRE(w != nullptr, "null weights");
-  AITB_REQUIRE(w->dtype == AITB_F32 || w->dtype == AITB_BF16, "bad dtype %d", w->dtype);
+  AITB_REQUIRE(w->dtype == AITB_F32 || w->dtype == AITB_BF16 || w->dtype == AITB_F32S, "bad dtype %d", w->dtype);
   AITB_REQUIRE(w->enc_emb.w && w->enc_emb.bias && w->dec_emb.w && w->dec_emb.bias && w->dec_trans.w &&
                    w->dec_trans.bias && w->enc_pos && w->dec_pos && w->enc_ln.gamma && w->dec_ln.gamma,
                "AIT embedding weights missing");
@@ -600,7 +616,8 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
   carve(b, hb, B, P, 64 * 64, dt, true, true);
 
   // a3: ROIAlign from a channels-last copy of the map, token-major output feeding enc_emb
-  RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt, B, 1024, H * W, 1, st));  // exact copy: ROIAlign parity
+  // exact copy (fp32 in the F32 and F32S configurations): ROIAlign parity
+  RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt == AITB_BF16 ? AITB_BF16 : AITB_F32, B, 1024, H * W, 1, st));
   for (int k0 = 0; k0 < bp; k0 += 32768) {
     const int kn = bp - k0 < 32768 ? bp - k0 : 32768;
     RUN(roi_align_fwd_run(hb.featT, rois + (size_t)k0 * 5, B, 1024, H, W, kn, 1.f / 16.f, 7, 7, 0, dt, 1,

@@ -64,6 +64,10 @@ struct GemmKParams {
   int round_tf32;
   int dual;  // extra centre tap into a second accumulator (BLOCK_N = 128)
   const float* bias2;
+  // split (bf16 hi/lo planes) mode: plane distances in bf16 elements
+  int a_lo, w_lo, o_lo, r_lo;
+  // split mode: compensation of the tensor core's round-toward-zero accumulation (see gemm_run)
+  float acc_scale, acc_scale2;
 };
 
 __device__ __forceinline__ uint4 ld_global_v4(const void* p) {
@@ -78,11 +82,12 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool SPLIT>
 struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 4;
+  static constexpr int kPlanes = SPLIT ? 2 : 1;  // split: [A_hi][A_lo][B_hi][B_lo] per stage
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStages = !SPLIT ? 4 : (BLOCK_N >= 256 ? 2 : (BLOCK_N >= 128 ? 3 : 4));
   static constexpr int kAccStages = 2;
   static constexpr int kUmmaN = BLOCK_N;
   // accumulator stage stride in TMEM columns; BLOCK_N = 128 reserves room for the dual accumulator
@@ -101,7 +106,7 @@ struct GemmCfg {
 //   mt : 128-row tile index (rows mt*128 ...), n0 : first output column, t_row : TMEM address of this
 //   warp's lane quadrant in the accumulator stage, stg : this warp's 4 KB staging tile.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BLOCK_N, bool CL>
+template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
                                               uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
                                               int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
@@ -181,8 +186,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
           v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
       };
-      // this thread's 32 values -> coalesced global store
-      auto stage_store = [&](int c0, const float (&v)[32]) {
+      // this thread's 32 values -> coalesced global store at column `c0` of the rows this warp covers
+      auto stage_store_raw = [&](int c0, const float (&v)[32]) {
 #pragma unroll
         for (int j = 0; j < kCh; ++j) {
           uint4 x;
@@ -208,6 +213,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
           if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val[it];
         __syncwarp();
       };
+      // split mode: hi = bf16(v) into the hi plane, lo = bf16(v - hi) into the lo plane (o_lo columns further)
+      auto stage_store = [&](int c0, const float (&v)[32]) {
+        stage_store_raw(c0, v);
+        if constexpr (SPLIT) {
+          float lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+          stage_store_raw(c0 + p.o_lo, lo);
+        }
+      };
+      // residual chunk (columns c0..c0+31 of this thread's row) from prefetched coalesced loads
+      auto add_residual = [&](const uint4 (&hi)[kIt], const uint4 (&lo)[kIt], float (&v)[32]) {
+        float r[32];
+        exchange(hi, r);
+        if constexpr (SPLIT) {
+          float r2[32];
+          exchange(lo, r2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j] + r2[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+      };
 
       mbar_wait(acc_full_bar, aph);
       tc_fence_after();
@@ -216,25 +245,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead
         const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
         const bool aux_acc = !aux_res && (p.flags & AITB_EPI_ACCUM) != 0;
-        uint4 pre[kIt];
+        uint4 pre[kIt], pre2[kIt];
         if (aux_res) issue_loads(rptr, c_begin, pre);
         if (aux_acc) issue_loads(optr, c_begin, pre);
+        if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c_begin + p.r_lo, pre2); }
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
-          uint4 cur[kIt];
+          uint4 cur[kIt], cur2[kIt];
           if (aux_res || aux_acc) {
 #pragma unroll
             for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
+            if constexpr (SPLIT) {
+#pragma unroll
+              for (int it = 0; it < kIt; ++it) cur2[it] = pre2[it];
+            }
             if (c0 + 32 < c_end) {
               if (aux_res) issue_loads(rptr, c0 + 32, pre); else issue_loads(optr, c0 + 32, pre);
+              if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c0 + 32 + p.r_lo, pre2); }
             }
           }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
+          }
           if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
           if (p.flags & AITB_EPI_RELU) {
 #pragma unroll
@@ -251,6 +290,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
               float u[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
+              if constexpr (SPLIT) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) u[j] *= p.acc_scale2;
+              }
               add_vec(p.bias2 + n0 + c0, u);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -260,12 +303,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
               }
             }
           }
-          if (aux_res) {
-            float r[32];
-            exchange(cur, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
-          }
+          if (aux_res) add_residual(cur, cur2, v);
           if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
           if (p.flags & AITB_EPI_ACCUM) {
             float r[32];
@@ -289,29 +327,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         //      CL: it holds half of the row; partial (sum, M2) are exchanged with the peer CTA via DSMEM.
         float sum = 0.f;
         const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
-        uint4 pre[kIt];
+        uint4 pre[kIt], pre2[kIt];
         if (aux_res) issue_loads(rptr, 0, pre);
+        if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, p.r_lo, pre2); }
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
-          uint4 cur[kIt];
+          uint4 cur[kIt], cur2[kIt];
           if (aux_res) {
 #pragma unroll
             for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
             if (c0 + 32 < BLOCK_N) issue_loads(rptr, c0 + 32, pre);
+            if constexpr (SPLIT) {
+#pragma unroll
+              for (int it = 0; it < kIt; ++it) cur2[it] = pre2[it];
+              if (c0 + 32 < BLOCK_N) issue_loads(rptr, c0 + 32 + p.r_lo, pre2);
+            }
           }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
-          if (aux_res) {
-            float r[32];
-            exchange(cur, r);
+          if constexpr (SPLIT) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
+            for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
           }
+          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
+          if (aux_res) add_residual(cur, cur2, v);
           if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -379,11 +422,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 // output columns [256 r, 256 r + 256) of the N = 512 row (BLOCK_N = 256 machinery: 4-stage ring, double-
 // buffered accumulator).  The LayerNorm row statistics are combined across the two CTAs through
 // distributed shared memory (partial sum + centred M2 per row, Chan's parallel-variance formula).
-template <typename T, int BLOCK_N, bool CL>
+template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, SPLIT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAcc = Cfg::kAccStages;
   extern __shared__ uint8_t smem_raw[];
@@ -449,11 +492,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t ph = (it / kStages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::kStageBytes;
-            uint8_t* sb = sa + kABytes;
+            uint8_t* sb = sa + Cfg::kPlanes * kABytes;
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
             tma_load_4d(sa, &tmA, &full_bar[s], a_c_base + kc * p.ke, c1, c2, c3);
             const int kb = (tap * p.k_chunks + kc) * p.ke;
             tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
+            if constexpr (SPLIT) {
+              tma_load_4d(sa + kABytes, &tmA, &full_bar[s], p.a_lo + a_c_base + kc * p.ke, c1, c2, c3);
+              tma_load_2d(sb + Cfg::kBBytes, &tmB, &full_bar[s], p.w_lo + kb, nt * BLOCK_N);
+            }
           }
         }
       }
@@ -480,14 +527,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kPlanes * kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte chunk
-#pragma unroll
-            for (int nb = 0; nb < BLOCK_N / Cfg::kUmmaN; ++nb) {
-              umma_ss<Act<T>::kBytes>(d_tmem + nb * Cfg::kUmmaN, adesc + (uint64_t)(k * 2),
-                                      bdesc + (uint64_t)(k * 2 + nb * (Cfg::kUmmaN * 128 / 16)),
-                                      idesc, (fresh && k == 0) ? 0u : 1u);
+            umma_ss<Act<T>::kBytes>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                    (fresh && k == 0) ? 0u : 1u);
+            if constexpr (SPLIT) {  // + A_hi * W_lo + A_lo * W_hi
+              umma_ss<2>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(Cfg::kBBytes / 16 + k * 2), idesc, 1u);
+              umma_ss<2>(d_tmem, adesc + (uint64_t)(kABytes / 16 + k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
             }
           }
           tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
@@ -507,8 +554,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * Cfg::kAccStride + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<T, BLOCK_N, CL>(p, stg, stats, &stats_full[as], &acc_full[as], t_row, q, lane, mt, nt * BLOCK_N,
-                                    as, aph, cta_rank);
+      epilogue_tile<T, BLOCK_N, CL, SPLIT>(p, stg, stats, &stats_full[as], &acc_full[as], t_row, q, lane, mt,
+                                           nt * BLOCK_N, as, aph, cta_rank);
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
@@ -532,16 +579,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   empty / acc_full : tcgen05.commit multicast to both CTAs
 //   acc_empty     : in the leader, count 256 (both CTAs' epilogue threads)
 // ---------------------------------------------------------------------------------------------
-static constexpr int k2Stages = 6;
-static constexpr int k2StageBytes = kABytes + 128 * 128;  // A (own 128 rows) + half of B
+static constexpr int k2HalfB = 128 * 128;  // this CTA's half of one W plane: 128 rows x 128 B
 static constexpr int k2Threads = 384;  // warpgroup 0: TMA / MMA (+2 idle warps); warpgroups 1, 2: epilogue
-static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + 8 * 4096;
+static constexpr int k2SmemBytes = 6 * (kABytes + k2HalfB) + 1024 + 256 + 8 * 4096;
 
-template <typename T>
+// SPLIT: a stage holds [A_hi][A_lo][W_hi half][W_lo half] (64 KB, 3 stages) and every K slice issues three MMAs.
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const GemmKParams p) {
   constexpr int BLOCK_N = 256;
+  constexpr int kPlanes = SPLIT ? 2 : 1;
+  constexpr int k2Stages = SPLIT ? 3 : 6;
+  constexpr int k2StageBytes = kPlanes * (kABytes + k2HalfB);  // A (own 128 rows) + half of B, per plane
   constexpr int kAcc = 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -604,12 +654,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t ph = (it / k2Stages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * k2StageBytes;
-            uint8_t* sb = sa + kABytes;
+            uint8_t* sb = sa + kPlanes * kABytes;
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * k2StageBytes);
             else mbar_arrive_remote(&full_bar[s], 0);
             tma2_load_4d(sa, &tmA, &full_bar[s], kc * p.ke, c1, c2, c3);
             const int kb = (tap * p.k_chunks + kc) * p.ke;
             tma2_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N + (int)rank * 128);
+            if constexpr (SPLIT) {
+              tma2_load_4d(sa + kABytes, &tmA, &full_bar[s], p.a_lo + kc * p.ke, c1, c2, c3);
+              tma2_load_2d(sb + k2HalfB, &tmB, &full_bar[s], p.w_lo + kb, nt * BLOCK_N + (int)rank * 128);
+            }
           }
         }
       }
@@ -631,11 +685,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * k2StageBytes);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kPlanes * kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k) {
             umma2_ss<Act<T>::kBytes>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                      (i | k) != 0 ? 1u : 0u);
+            if constexpr (SPLIT) {
+              umma2_ss<2>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k2HalfB / 16 + k * 2), idesc, 1u);
+              umma2_ss<2>(d_tmem, adesc + (uint64_t)(kABytes / 16 + k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            }
+          }
           tc_commit2(&empty_bar[s]);
         }
         tc_commit2(&acc_full[as]);
@@ -654,8 +713,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<T, BLOCK_N, false>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane, mp * 2 + (int)rank,
-                                       nt * BLOCK_N, as, aph, rank, half * 128, half * 128 + 128);
+      epilogue_tile<T, BLOCK_N, false, SPLIT>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
+                                              mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
+                                              half * 128 + 128);
       tc_fence_before();
       mbar_arrive_remote(&acc_empty[as], 0);
     }
@@ -730,12 +790,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <typename T, int BLOCK_N, bool CL>
+template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, SPLIT>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<T, BLOCK_N, CL>;
+  auto kern = gemm_tcgen05_kernel<T, BLOCK_N, CL, SPLIT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -774,10 +834,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
 }
 
-template <typename T>
+template <typename T, bool SPLIT>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm2_tcgen05_kernel<T>;
+  auto kern = gemm2_tcgen05_kernel<T, SPLIT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
     if (e != cudaSuccess) {
@@ -812,9 +872,15 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
 
 int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d != nullptr, "aitb_gemm: null descriptor");
-  AITB_REQUIRE(d->dtype == AITB_F32 || d->dtype == AITB_BF16, "aitb_gemm: bad dtype %d", d->dtype);
-  const int eb = d->dtype == AITB_F32 ? 4 : 2;
+  AITB_REQUIRE(d->dtype == AITB_F32 || d->dtype == AITB_BF16 || d->dtype == AITB_F32S, "aitb_gemm: bad dtype %d",
+               d->dtype);
+  const bool split = d->dtype == AITB_F32S;
+  const int eb = d->dtype == AITB_F32 ? 4 : 2;  // bytes per TMA element (split: bf16 planes)
   const int ke = 128 / eb;
+  if (split) {
+    AITB_REQUIRE(d->a_lo_off > 0 && d->a_lo_off % 8 == 0, "aitb_gemm: split mode needs a_lo_off (multiple of 8)");
+    AITB_REQUIRE((d->flags & AITB_EPI_ACCUM) == 0, "aitb_gemm: ACCUM epilogue is not available in split mode");
+  }
   AITB_REQUIRE(d->M > 0 && d->N > 0, "aitb_gemm: empty problem M=%d N=%d", d->M, d->N);
   AITB_REQUIRE(d->block_n == 128 || d->block_n == 256 || d->block_n == 512 || d->block_n == 64,
                "aitb_gemm: block_n %d unsupported", d->block_n);
@@ -848,14 +914,16 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   const int w_taps = d->taps + (d->dual ? 1 : 0);
   CUtensorMap tmA, tmB;
   if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, d->a.box, "A")) return 1;
-  const uint64_t wdims[2] = {(uint64_t)w_taps * d->k_per_tap, (uint64_t)d->N};
-  const uint64_t wstr[1] = {(uint64_t)w_taps * d->k_per_tap * eb};
+  const uint64_t w_k = (uint64_t)w_taps * d->k_per_tap;  // logical K of the weight matrix
+  const uint64_t wdims[2] = {w_k * (split ? 2 : 1), (uint64_t)d->N};
+  const uint64_t wstr[1] = {w_k * (split ? 4 : eb)};
   const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
   static const bool no_2cta = getenv("AITB_NO_2CTA") != nullptr;
   const bool two_cta = !cluster_ln && !no_2cta && d->block_n == 256 && d->a_group_c == 0 && !d->dual &&
                        (d->M + kBlockM - 1) / kBlockM >= 2;
   const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(two_cta ? 128 : (d->block_n > 256 ? 256 : d->block_n))};
   if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
+  const int pl = split ? 2 : 1;  // physical elements per logical element in out / res rows
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -875,12 +943,16 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.n_tiles = cluster_ln ? 2 : d->N / d->block_n;
   kp.flags = d->flags;
   kp.out = d->out;
-  kp.ldo = d->ldo;
+  kp.ldo = d->ldo * pl;
+  kp.o_lo = d->ldo;
+  kp.r_lo = d->ldr;
+  kp.a_lo = d->a_lo_off;
+  kp.w_lo = (int)w_k;
   kp.rows_in = d->rows_in;
   kp.rows_out = d->rows_out;
   kp.bias = d->bias;
   kp.res = d->res;
-  kp.ldr = d->ldr;
+  kp.ldr = d->ldr * pl;
   kp.res_div = d->res_div > 0 ? d->res_div : 1;
   kp.res_rep = d->res_rep > 0 ? d->res_rep : 1;
   kp.pos = d->pos;
@@ -891,16 +963,35 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.round_tf32 = d->round_tf32;
   kp.dual = d->dual ? 1 : 0;
   kp.bias2 = d->bias2;
+  // tcgen05.mma adds each K=16 slice into the fp32 accumulator with round-toward-ZERO (measured, tools/acc_bias.py:
+  // mean signed error -1.6e-8 .. -2.0e-8 of the result per accumulate step, growing linearly with the step
+  // count; the expectation for RZ on a growing partial sum is 0.18 * 2^-23 = 2.1e-8).  In the tf32 / bf16
+  // configurations that bias hides below the operand rounding; in the split configuration it would be the
+  // largest error left (1.5e-5 at K = 4096), so the epilogue scales the accumulator by 1 + c * steps.
+  {
+    static float comp = -1.f;
+    if (comp < 0.f) {
+      const char* e = getenv("AITB_ACC_COMP");
+      comp = e ? (float)atof(e) : 1.5e-8f;
+    }
+    const float steps = split ? 3.f * (float)(d->taps * d->k_per_tap / 16) : 0.f;
+    const float steps2 = split ? 3.f * (float)(d->k_per_tap / 16) : 0.f;
+    kp.acc_scale = 1.f + comp * steps;
+    kp.acc_scale2 = 1.f + comp * steps2;
+  }
 
-#define AITB_DISPATCH(BN)                                                                     \
-  (d->dtype == AITB_F32 ? launch_gemm<float, BN, false>(tmA, tmB, kp, stream)                 \
-                        : launch_gemm<__nv_bfloat16, BN, false>(tmA, tmB, kp, stream))
+#define AITB_DISPATCH(BN)                                                                          \
+  (d->dtype == AITB_F32 ? launch_gemm<float, BN, false, false>(tmA, tmB, kp, stream)               \
+   : split              ? launch_gemm<__nv_bfloat16, BN, false, true>(tmA, tmB, kp, stream)        \
+                        : launch_gemm<__nv_bfloat16, BN, false, false>(tmA, tmB, kp, stream))
   if (cluster_ln)
-    return d->dtype == AITB_F32 ? launch_gemm<float, 256, true>(tmA, tmB, kp, stream)
-                                : launch_gemm<__nv_bfloat16, 256, true>(tmA, tmB, kp, stream);
+    return d->dtype == AITB_F32 ? launch_gemm<float, 256, true, false>(tmA, tmB, kp, stream)
+           : split              ? launch_gemm<__nv_bfloat16, 256, true, true>(tmA, tmB, kp, stream)
+                                : launch_gemm<__nv_bfloat16, 256, true, false>(tmA, tmB, kp, stream);
   if (two_cta)
-    return d->dtype == AITB_F32 ? launch_gemm2<float>(tmA, tmB, kp, stream)
-                                : launch_gemm2<__nv_bfloat16>(tmA, tmB, kp, stream);
+    return d->dtype == AITB_F32 ? launch_gemm2<float, false>(tmA, tmB, kp, stream)
+           : split              ? launch_gemm2<__nv_bfloat16, true>(tmA, tmB, kp, stream)
+                                : launch_gemm2<__nv_bfloat16, false>(tmA, tmB, kp, stream);
   switch (d->block_n) {
     case 64: return AITB_DISPATCH(64);
     case 128: return AITB_DISPATCH(128);

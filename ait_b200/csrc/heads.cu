@@ -18,7 +18,8 @@ namespace aitb {
 static constexpr int kFeat = 2048;
 static constexpr int kPos = 16;
 
-template <typename T>
+// SPLIT: `top` is a split matrix [G*16, hi 2048 | lo 2048] (AITB_F32S)
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 pool_heads_kernel(const T* __restrict__ top, int P, const float* __restrict__ qfeat, const float* __restrict__ w_bbox,
                   const float* __restrict__ b_bbox, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -27,7 +28,8 @@ pool_heads_kernel(const T* __restrict__ top, int P, const float* __restrict__ qf
   __shared__ float feat[kFeat];
   __shared__ float dots[12];
   const int gidx = blockIdx.x;
-  const T* tg = top + (size_t)gidx * kPos * kFeat;
+  constexpr int kPitch = SPLIT ? 2 * kFeat : kFeat;
+  const T* tg = top + (size_t)gidx * kPos * kPitch;
   // thread owns 8 consecutive channels
   {
     const int c = threadIdx.x * 8;
@@ -35,7 +37,13 @@ pool_heads_kernel(const T* __restrict__ top, int P, const float* __restrict__ qf
 #pragma unroll 4
     for (int p = 0; p < kPos; ++p) {
       float v[8];
-      ld8(tg + (size_t)p * kFeat + c, v);
+      ld8(tg + (size_t)p * kPitch + c, v);
+      if constexpr (SPLIT) {
+        float u[8];
+        ld8(tg + (size_t)p * kPitch + kFeat + c, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += u[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
@@ -111,6 +119,9 @@ int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat,
   else if (dtype == AITB_BF16)
     pool_heads_kernel<__nv_bfloat16><<<G, 256, 0, stream>>>((const __nv_bfloat16*)top, P, qfeat, w_bbox, b_bbox, w1,
                                                             b1, w2, b2, feat_out, bbox_out, cls_out);
+  else if (dtype == AITB_F32S)
+    pool_heads_kernel<__nv_bfloat16, true><<<G, 256, 0, stream>>>((const __nv_bfloat16*)top, P, qfeat, w_bbox, b_bbox,
+                                                                  w1, b1, w2, b2, feat_out, bbox_out, cls_out);
   else {
     set_error("aitb_pool_heads: bad dtype %d", dtype);
     return 1;

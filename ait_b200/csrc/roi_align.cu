@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/aitb200.h"
 #include "common.cuh"
 
@@ -150,10 +152,12 @@ __device__ __forceinline__ bool build_foot(Foot& f, float start, int p, float bi
 
 // grid (ceil(C / 128), K); block 256 = 8 warps; lane owns 4 consecutive channels of the 128-channel slab,
 // warps stride over the ph*pw bins.
-template <typename T, bool NCHW_OUT>
+// OUT_SPLIT (token-major only): fp32 map in, output as two bf16 planes [K, ph*pw, hi C | lo C] (AITB_F32S)
+template <typename T, bool NCHW_OUT, bool OUT_SPLIT = false>
 __global__ void __launch_bounds__(256)
 roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
-                     int ph, int pw, int sampling_ratio, T* __restrict__ out, int round_tf) {
+                     int ph, int pw, int sampling_ratio, typename std::conditional<OUT_SPLIT, __nv_bfloat16, T>::type* __restrict__ out,
+                     int round_tf) {
   __shared__ Foot xf[kMaxPooled];
   __shared__ Foot yf[kMaxPooled];
   extern __shared__ float stage[];  // NCHW_OUT: [128][ph*pw + 1]
@@ -220,6 +224,11 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
       stage[(lane * 4 + 1) * s + bin] = acc.y;
       stage[(lane * 4 + 2) * s + bin] = acc.z;
       stage[(lane * 4 + 3) * s + bin] = acc.w;
+    } else if constexpr (OUT_SPLIT) {
+      __nv_bfloat16* o = out + ((size_t)k * nbins + bin) * 2 * C + c0 + lane * 4;
+      Vec4<__nv_bfloat16>::st(o, acc);
+      auto lo = [](float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); };
+      Vec4<__nv_bfloat16>::st(o + C, make_float4(lo(acc.x), lo(acc.y), lo(acc.z), lo(acc.w)));
     } else {
       Vec4<T>::st(out + ((size_t)k * nbins + bin) * C + c0 + lane * 4, acc);
     }
@@ -291,19 +300,25 @@ roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ r
 }
 
 // [G, C, S] -> [G, S, C] (to_cl) or back, 32x32 smem tiles, optional dtype conversion.
-template <typename TS, typename TD>
+// SS / SD: the source / destination is a split (two bf16 planes per row) matrix (AITB_F32S).
+template <typename TS, typename TD, bool SS = false, bool SD = false>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc, int round_tf) {
   // src [G, R, Cc] -> dst [G, Cc, R]
   __shared__ float tile[32][33];
   const int g = blockIdx.z;
-  const TS* s = src + (size_t)g * R * Cc;
-  TD* d = dst + (size_t)g * R * Cc;
+  constexpr int ps = SS ? 2 : 1, pd = SD ? 2 : 1;
+  const TS* s = src + (size_t)g * R * Cc * ps;
+  TD* d = dst + (size_t)g * R * Cc * pd;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int j = ty; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + tx;
-    if (r < R && c < Cc) tile[j][tx] = Act<TS>::ld(s + (size_t)r * Cc + c);
+    if (r < R && c < Cc) {
+      float v = Act<TS>::ld(s + (size_t)r * Cc * ps + c);
+      if constexpr (SS) v += Act<TS>::ld(s + (size_t)r * Cc * ps + Cc + c);
+      tile[j][tx] = v;
+    }
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
@@ -311,7 +326,9 @@ transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc
     if (r < R && c < Cc) {
       float v = tile[tx][j];
       if (sizeof(TD) == 4 && round_tf) v = rn_tf32(v);
-      Act<TD>::st(d + (size_t)c * R + r, v);
+      TD* o = d + (size_t)c * R * pd + r;
+      Act<TD>::st(o, v);
+      if constexpr (SD) Act<TD>::st(o + R, v - Act<TD>::ld(o));
     }
   }
 }
@@ -332,6 +349,12 @@ int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, in
   else if (sdt == AITB_BF16 && ddt == AITB_BF16)
     transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src,
                                                                               (__nv_bfloat16*)dst, R, Cc, 0);
+  else if (sdt == AITB_F32 && ddt == AITB_F32S)
+    transpose_kernel<float, __nv_bfloat16, false, true><<<grid, 256, 0, stream>>>((const float*)src,
+                                                                                   (__nv_bfloat16*)dst, R, Cc, 0);
+  else if (sdt == AITB_F32S && ddt == AITB_F32)
+    transpose_kernel<__nv_bfloat16, float, true, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src,
+                                                                                   (float*)dst, R, Cc, 0);
   else {
     set_error("aitb_transpose_cs: bad dtypes %d -> %d", sdt, ddt);
     return 1;
@@ -356,6 +379,10 @@ int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, 
     else
       roi_align_fwd_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
                                                                     sampling_ratio, (float*)out, round_tf);
+  } else if (dtype == AITB_F32S) {   // fp32 map -> split token-major output (engine-internal)
+    AITB_REQUIRE(out_layout == 1, "aitb_roi_align_forward: the split configuration writes token-major output only");
+    roi_align_fwd_kernel<float, false, true><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
+                                                                       sampling_ratio, (__nv_bfloat16*)out, 0);
   } else if (dtype == AITB_BF16) {
     if (out_layout == 0)
       roi_align_fwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, stream>>>(

@@ -21,26 +21,42 @@ def _need_cuda(*ts):
 # ---------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------
-def transpose_cs(src, to_channels_last, out_dtype=None):
-    """[G, C, S] -> [G, S, C] (to_channels_last) or [G, S, C] -> [G, C, S]."""
+def transpose_cs(src, to_channels_last, out_dtype=None, split_src=False, split_dst=False):
+    """[G, C, S] -> [G, S, C] (to_channels_last) or [G, S, C] -> [G, C, S].
+    split_dst: the (channels-last) destination is a two-plane bf16 matrix [G, S, hi C | lo C] (AITB_F32S);
+    split_src: the (channels-last) source is one."""
     lib = L.load()
     _need_cuda(src)
     src = src.contiguous()
-    out_dtype = out_dtype or src.dtype
+    out_dtype = torch.bfloat16 if split_dst else (out_dtype or (torch.float32 if split_src else src.dtype))
     G = src.shape[0]
     if to_channels_last:
         Cc, S = src.shape[1], src.shape[2]
-        dst = torch.empty((G, S, Cc), device=src.device, dtype=out_dtype)
+        dst = torch.empty((G, S, Cc * (2 if split_dst else 1)), device=src.device, dtype=out_dtype)
     else:
-        S, Cc = src.shape[1], src.shape[2]
+        S, Cc = src.shape[1], src.shape[2] // (2 if split_src else 1)
         dst = torch.empty((G, Cc, S), device=src.device, dtype=out_dtype)
+    sdt = L.AITB_F32S if split_src else _act_dtype(src)
+    ddt = L.AITB_F32S if split_dst else L.dtype_enum(out_dtype)
     step = 32768
     for g0 in range(0, G, step):
         gn = min(step, G - g0)
-        L.check(lib.aitb_transpose_cs(L.ptr(src[g0:]), _act_dtype(src), L.ptr(dst[g0:]),
-                                      L.dtype_enum(out_dtype), gn, Cc, S, 1 if to_channels_last else 0,
-                                      L.stream_ptr()))
+        L.check(lib.aitb_transpose_cs(L.ptr(src[g0:]), sdt, L.ptr(dst[g0:]), ddt, gn, Cc, S,
+                                      1 if to_channels_last else 0, L.stream_ptr()))
     return dst
+
+
+def split_planes(x):
+    """fp32 [..., C] -> bf16 [..., hi C | lo C] (host-side helper for tests / packing)."""
+    hi = x.float().to(torch.bfloat16)
+    lo = (x.float() - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def join_planes(x):
+    """bf16 [..., hi C | lo C] -> fp32 [..., C]."""
+    c = x.shape[-1] // 2
+    return x[..., :c].float() + x[..., c:].float()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -142,28 +158,33 @@ def _esize(dt):
 
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
-         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None):
+         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False):
     """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
-    map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels)."""
+    map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels).
+    split=True: AITB_F32S -- a / w / out / res are two-plane bf16 matrices (see split_planes); K, lda, ldr
+    and the map's C are LOGICAL element counts."""
     lib = L.load()
     d = L.GemmDesc()
-    dt = _act_dtype(a)
-    eb = _esize(dt)
+    dt = L.AITB_F32S if split else _act_dtype(a)
+    eb = 4 if split else _esize(dt)            # bytes per logical element of a row
+    cb = 2 if split else eb                    # bytes per TMA element
     d.dtype, d.M, d.N, d.k_per_tap, d.taps = dt, M, N, K, taps
     d.a.ptr = a.data_ptr()
     d.a_group_c = group_c
     if view == "plain":
         lda = lda or K
-        d.a.dims[:] = [lda if group_c else K * taps, M, 1, 1]
+        d.a.dims[:] = [(lda if group_c else K * taps) + (lda if split else 0), M, 1, 1]
         d.a.strides[:] = [lda * eb, lda * eb * M, lda * eb * M]
-        d.a.box[:] = [128 // eb, 128, 1, 1]
+        d.a.box[:] = [128 // cb, 128, 1, 1]
         d.a_m_dim, d.a_m_step = 1, 128
+        d.a_lo_off = lda if split else 0
     else:
         Cc, S, s, stride, G = map_args
-        d.a.dims[:] = [Cc, s, s, G]
+        d.a.dims[:] = [Cc * (2 if split else 1), s, s, G]
         d.a.strides[:] = [stride * Cc * eb, stride * S * Cc * eb, S * S * Cc * eb]
-        d.a.box[:] = [128 // eb, s, s, 128 // (s * s)]
+        d.a.box[:] = [128 // cb, s, s, 128 // (s * s)]
         d.a_m_dim, d.a_m_step = 3, 128 // (s * s)
+        d.a_lo_off = Cc if split else 0
     if taps == 9:
         for ky in range(3):
             for kx in range(3):
@@ -173,7 +194,7 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.block_n = block_n
     d.flags = flags
     d.out = out.data_ptr()
-    d.ldo = out.shape[-1]
+    d.ldo = out.shape[-1] // (2 if split else 1)
     d.rows_in = rows_in or M
     d.rows_out = rows_out or M
     d.bias = 0 if bias is None else bias.data_ptr()
@@ -191,14 +212,17 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     return out
 
 
-def attn_core(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, out):
+def attn_core(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, out, split=False):
+    """split=True: q / k / v / out are two-plane bf16 matrices, ldq / ldkv their LOGICAL row widths."""
     lib = L.load()
     L.check(lib.aitb_attn_core(L.ptr(q), ldq, q_rep, L.ptr(k), L.ptr(v), ldkv, L.ptr(w_sk), L.ptr(b_sk), G,
-                               mask_mode, n_keys, _act_dtype(q), L.ptr(out), L.stream_ptr()))
+                               mask_mode, n_keys, L.AITB_F32S if split else _act_dtype(q), L.ptr(out),
+                               L.stream_ptr()))
     return out
 
 
-def pool_heads(top, P, qfeat=None, w_bbox=None, b_bbox=None, w1=None, b1=None, w2=None, b2=None, want_feat=True):
+def pool_heads(top, P, qfeat=None, w_bbox=None, b_bbox=None, w1=None, b1=None, w2=None, b2=None, want_feat=True,
+               split=False):
     """top [G, 16, 2048] -> (feat [G, 2048] | None, bbox [G, 4] | None, cls_prob [G] | None)."""
     lib = L.load()
     G = top.shape[0]
@@ -207,7 +231,7 @@ def pool_heads(top, P, qfeat=None, w_bbox=None, b_bbox=None, w1=None, b1=None, w
     heads = w_bbox is not None
     bbox = torch.empty((G, 4), dtype=torch.float32, device=dev) if heads else None
     cls = torch.empty((G,), dtype=torch.float32, device=dev) if heads else None
-    L.check(lib.aitb_pool_heads(L.ptr(top), _act_dtype(top), G, P, L.ptr(qfeat), L.ptr(w_bbox), L.ptr(b_bbox),
+    L.check(lib.aitb_pool_heads(L.ptr(top), L.AITB_F32S if split else _act_dtype(top), G, P, L.ptr(qfeat), L.ptr(w_bbox), L.ptr(b_bbox),
                                 L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(feat), L.ptr(bbox), L.ptr(cls),
                                 L.stream_ptr()))
     return feat, bbox, cls

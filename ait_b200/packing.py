@@ -30,9 +30,12 @@ class HeadEngine:
     def __init__(self, transformer=None, sk=None, top=None, cls_score=None, bbox_pred=None,
                  dtype=torch.float32, round_acts=True):
         L.load()
-        self.dtype = dtype
-        self.dt = L.dtype_enum(dtype)
-        self.round_acts = bool(round_acts)
+        self.mode = L.mode_name(dtype)             # "fp32" (split bf16 x3) | "tf32" | "bf16"
+        self.dt = L.MODES[self.mode]
+        self.dtype = L.storage_dtype(self.mode)    # element type of the activation / weight buffers
+        self.split = self.mode == "fp32"
+        self.planes = 2 if self.split else 1
+        self.round_acts = bool(round_acts) and self.mode == "tf32"
         self._keep = []          # packed tensors stay alive as long as the engine
         self.w = L.HeadWeights()
         self.w.dtype = self.dt
@@ -67,7 +70,12 @@ class HeadEngine:
     def _mat(self, t):
         """[N, K] matrix in the compute dtype."""
         t = self._dev(t).detach().float().contiguous()
-        t = round_to_tf32(t) if self.dtype == torch.float32 else t.to(torch.bfloat16)
+        if self.mode == "tf32":
+            t = round_to_tf32(t)
+        elif self.mode == "bf16":
+            t = t.to(torch.bfloat16)
+        else:                                       # [N, hi K | lo K]
+            t = ops.split_planes(t)
         t = t.contiguous()
         self._keep.append(t)
         return t
@@ -244,11 +252,12 @@ class HeadEngine:
         if taps:
             tp = L.HeadTaps()
             bp = B * P
+            pl = self.planes
             tensors = dict(
-                pooled=torch.empty((bp, 49, 1024), dtype=self.dtype, device=dev),
-                enc_out=torch.empty((bp, 64, 512), dtype=self.dtype, device=dev),
-                ait_out=torch.empty((bp, 64, 1024), dtype=self.dtype, device=dev),
-                sk_out=torch.empty((bp, 64, 1024), dtype=self.dtype, device=dev),
+                pooled=torch.empty((bp, 49, 1024 * pl), dtype=self.dtype, device=dev),
+                enc_out=torch.empty((bp, 64, 512 * pl), dtype=self.dtype, device=dev),
+                ait_out=torch.empty((bp, 64, 1024 * pl), dtype=self.dtype, device=dev),
+                sk_out=torch.empty((bp, 64, 1024 * pl), dtype=self.dtype, device=dev),
                 feat=torch.empty((bp, 2048), dtype=torch.float32, device=dev),
                 qfeat=torch.empty((B, 2048), dtype=torch.float32, device=dev))
             for k, v in tensors.items():
@@ -260,6 +269,9 @@ class HeadEngine:
                                           L.ptr(cls_prob), L.ptr(bbox), C.byref(tp) if tp is not None else None,
                                           L.ptr(ws), nbytes, L.stream_ptr()))
         if taps:
+            if self.split:
+                for k in ("pooled", "enc_out", "ait_out", "sk_out"):
+                    tensors[k] = ops.join_planes(tensors[k])
             return cls_prob, bbox, tensors
         return cls_prob, bbox
 
@@ -267,13 +279,14 @@ class HeadEngine:
     def _sk_branch(self, x_nchw, which):
         m1, b1, m3, b3, mf = self._sk_mats[which]
         G = x_nchw.shape[0]
-        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype)
-        out = torch.empty((G, 64, 1024), dtype=self.dtype, device=x.device)
+        sp = self.split
+        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype, split_dst=sp)
+        out = torch.empty((G, 64, 1024 * self.planes), dtype=self.dtype, device=x.device)
         # one dual-accumulator GEMM: nine 3x3 taps -> acc0, the 1x1 conv (centre tap) -> acc1
         ops.gemm(x, mf, out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G),
                  taps=9, group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_DUAL, bias=b3,
-                 dual=True, bias2=b1)
-        return ops.transpose_cs(out, False, out_dtype=torch.float32).view(G, 1024, 8, 8)
+                 dual=True, bias2=b1, split=sp)
+        return ops.transpose_cs(out, False, out_dtype=torch.float32, split_src=sp).view(G, 1024, 8, 8)
 
     def sk_forward(self, x_props, x_query):
         if not self.has_sk:
@@ -286,33 +299,35 @@ class HeadEngine:
             raise RuntimeError("engine built without RCNN_top")
         G = x_nchw.shape[0]
         dev = x_nchw.device
-        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype)
+        sp, pl = self.split, self.planes
+        x = ops.transpose_cs(x_nchw.contiguous().float().reshape(G, 1024, 64), True, out_dtype=self.dtype, split_dst=sp)
         M = G * 16
-        c1 = torch.empty((M, 512), dtype=self.dtype, device=dev)
-        c2 = torch.empty((M, 512), dtype=self.dtype, device=dev)
-        ys = [torch.empty((M, 2048), dtype=self.dtype, device=dev) for _ in range(2)]
+        c1 = torch.empty((M, 512 * pl), dtype=self.dtype, device=dev)
+        c2 = torch.empty((M, 512 * pl), dtype=self.dtype, device=dev)
+        ys = [torch.empty((M, 2048 * pl), dtype=self.dtype, device=dev) for _ in range(2)]
         cur = x
         for i, mats in enumerate(self._top_mats):
             out = ys[i & 1]
             w1, b1 = mats["conv1"]
             if i == 0:
                 ops.gemm(cur, w1, c1, M=M, N=512, K=1024, block_n=256, view="map", map_args=(1024, 8, 4, 2, G),
-                         flags=L.EPI_BIAS | L.EPI_RELU, bias=b1)
+                         flags=L.EPI_BIAS | L.EPI_RELU, bias=b1, split=sp)
             else:
-                ops.gemm(cur, w1, c1, M=M, N=512, K=2048, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=b1)
+                ops.gemm(cur, w1, c1, M=M, N=512, K=2048, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=b1,
+                         split=sp)
             w2, b2 = mats["conv2"]
             ops.gemm(c1, w2, c2, M=M, N=512, K=512, block_n=256, view="map", map_args=(512, 4, 4, 1, G), taps=9,
-                     flags=L.EPI_BIAS | L.EPI_RELU, bias=b2)
+                     flags=L.EPI_BIAS | L.EPI_RELU, bias=b2, split=sp)
             res = cur
             if i == 0:
                 wd, bd = mats["down"]
-                ds = torch.empty((M, 2048), dtype=self.dtype, device=dev)
+                ds = torch.empty((M, 2048 * pl), dtype=self.dtype, device=dev)
                 ops.gemm(cur, wd, ds, M=M, N=2048, K=1024, block_n=256, view="map", map_args=(1024, 8, 4, 2, G),
-                         flags=L.EPI_BIAS, bias=bd)
+                         flags=L.EPI_BIAS, bias=bd, split=sp)
                 res = ds
             w3, b3 = mats["conv3"]
             ops.gemm(c2, w3, out, M=M, N=2048, K=512, block_n=256,
-                     flags=L.EPI_BIAS | L.EPI_RES | L.EPI_RES_RELU, bias=b3, res=res, ldr=2048)
+                     flags=L.EPI_BIAS | L.EPI_RES | L.EPI_RES_RELU, bias=b3, res=res, ldr=2048, split=sp)
             cur = out
-        feat, _, _ = ops.pool_heads(cur.view(G, 16, 2048), 1)
+        feat, _, _ = ops.pool_heads(cur.view(G, 16, 2048 * pl), 1, split=sp)
         return feat

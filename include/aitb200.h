@@ -29,7 +29,16 @@ extern "C" {
 
 typedef void* aitb_stream_t; /* cudaStream_t */
 
-enum { AITB_F32 = 0, AITB_BF16 = 1 }; /* activation storage; F32 computes on tf32 tensor cores */
+/* Compute configurations ("dtype" arguments):
+ *   AITB_F32   fp32 storage, tf32 tensor-core math (10-bit operand mantissa): the fast fp32-storage mode
+ *   AITB_BF16  bf16 storage, bf16 math
+ *   AITB_F32S  "fp32-class" split mode: every activation / weight x is stored as TWO bf16 planes
+ *              hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits together) and every product runs as three
+ *              bf16 tensor-core passes hi*hi + hi*lo + lo*hi with fp32 accumulation (error ~2^-16 per
+ *              operand instead of tf32's 2^-11).  This is the configuration that meets the reference's
+ *              fp32 results to 1e-3 on cls_prob.  Storage: a logical [rows, L] matrix is a bf16
+ *              [rows, 2L] matrix, hi plane in columns [0, L), lo plane in [L, 2L)  (4 bytes / element). */
+enum { AITB_F32 = 0, AITB_BF16 = 1, AITB_F32S = 2 };
 
 const char* aitb_last_error(void);
 int aitb_version(void);
@@ -115,14 +124,15 @@ enum {
 };
 
 typedef struct {
-  int dtype; /* AITB_F32 (tf32 MMA) | AITB_BF16 */
+  int dtype; /* AITB_F32 (tf32 MMA) | AITB_BF16 | AITB_F32S (split bf16 x3; the view, ldo and ldr are given in
+                LOGICAL elements of 4 bytes, i.e. strides in bytes of the physical two-plane rows) */
   int M, N, k_per_tap, taps;
   aitb_view4 a;
   int a_m_dim;   /* which A coordinate advances with the m-tile: 1 (plain rows) or 3 (conv) */
   int a_m_step;  /* coordinate step per 128-row m-tile                                      */
   int a_group_c; /* grouped conv: input-channel offset per n-tile (0 otherwise)             */
   int8_t tap_dx[9], tap_dy[9];
-  const void* w; /* [N, taps*k_per_tap] K-major, dtype `dtype` */
+  const void* w; /* [N, taps*k_per_tap] K-major, dtype `dtype` (F32S: [N, hi plane | lo plane]) */
   int block_n;   /* 128 | 256 | 512 */
   /* epilogue */
   int flags;
@@ -143,6 +153,9 @@ typedef struct {
    * follows them in `w` accumulates into a SECOND accumulator; combined by AITB_EPI_DUAL */
   int dual;
   const float* bias2;
+  /* AITB_F32S only: distance (bf16 elements along dims[0]) from the hi plane to the lo plane of A, i.e. the
+   * logical row width of the buffer A lives in.  out / res planes are ldo / ldr apart; W's are taps*k_per_tap apart. */
+  int a_lo_off;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);

@@ -1,0 +1,163 @@
+"""GPU parity of the "fp32-class" split configuration (AITB_F32S): every operand is two bf16 planes
+(hi + lo = 16 mantissa bits) and every product is three bf16 tensor-core passes.  References are fp64
+computed from the UNROUNDED fp32 operands, so the gates measure the full error of the scheme
+(operand split 2^-17 + fp32 accumulation), which must sit ~30x below tf32's 2^-11."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF = torch.bfloat16
+# max |err| relative to the output's scale.  tf32 measures ~3e-4 on the same problems.
+GATE = 2e-5
+
+
+def _err(out, ref):
+    return float((out.double() - ref.double()).abs().max() / ref.double().abs().max())
+
+
+def _sp(x):
+    from ait_b200 import ops
+    return ops.split_planes(x).to(DEV)
+
+
+def _jn(x):
+    from ait_b200 import ops
+    return ops.join_planes(x).cpu()
+
+
+def test_split_planes_roundtrip():
+    from ait_b200 import ops
+    x = torch.randn(64, 256, generator=torch.Generator().manual_seed(0)) * 37.0
+    y = ops.join_planes(ops.split_planes(x))
+    assert float((x - y).abs().max() / x.abs().max()) < 2 ** -16
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (300, 512, 512, 256), (1000, 1536, 512, 256),
+                                      (77, 128, 128, 128), (4096 + 5, 2048, 512, 256), (640, 256, 2048, 256),
+                                      (130, 64, 192, 64)])
+def test_split_gemm_plain_bias_relu(M, N, K, bn):
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = F.relu(a.double() @ w.double().t() + bias.double())
+    out = torch.full((M, 2 * N), float("nan"), dtype=BF, device=DEV)
+    ops.gemm(_sp(a), _sp(w), out, M=M, N=N, K=K, block_n=bn, flags=L.EPI_BIAS | L.EPI_RELU, bias=bias.to(DEV),
+             split=True)
+    assert _err(_jn(out), ref) < GATE
+
+
+def test_split_gemm_layernorm_residual_pos_rowmap():
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(1)
+    pairs, K = 11, 1024
+    M = pairs * 49
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(512, K, generator=g) / K ** 0.5
+    bias, pos = torch.randn(512, generator=g), torch.randn(64, 512, generator=g)
+    gamma, beta = torch.rand(512, generator=g) + 0.5, torch.randn(512, generator=g)
+    y = (a.double() @ w.double().t() + bias.double()).view(pairs, 49, 512) + pos[:49].double()
+    ref = F.layer_norm(y, (512,), gamma.double(), beta.double(), eps=1e-6)
+    out = torch.zeros((pairs * 64, 1024), dtype=BF, device=DEV)
+    ops.gemm(_sp(a), _sp(w), out, M=M, N=512, K=K, block_n=512, flags=L.EPI_BIAS | L.EPI_POS | L.EPI_LN,
+             bias=bias.to(DEV), pos=pos.to(DEV), pos_rows=64, gamma=gamma.to(DEV), beta=beta.to(DEV), rows_in=49,
+             rows_out=64, split=True)
+    o = _jn(out).view(pairs, 64, 512)
+    assert _err(o[:, :49], ref) < GATE
+    assert torch.all(o[:, 49:] == 0)
+
+
+def test_split_gemm_residual_broadcast_layernorm():
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(2)
+    B, P = 3, 5
+    M = B * P * 64
+    a = torch.randn(M, 64, generator=g)
+    w = torch.randn(512, 64, generator=g) / 8
+    res = torch.randn(B * 64, 512, generator=g)
+    gamma, beta = torch.rand(512, generator=g) + 0.5, torch.randn(512, generator=g)
+    y = (a.double() @ w.double().t()).view(B, P, 64, 512) + res.double().view(B, 1, 64, 512)
+    ref = F.layer_norm(y, (512,), gamma.double(), beta.double(), eps=1e-6).view(M, 512)
+    out = torch.zeros((M, 1024), dtype=BF, device=DEV)
+    ops.gemm(_sp(a), _sp(w), out, M=M, N=512, K=64, block_n=512, flags=L.EPI_RES | L.EPI_LN, res=_sp(res), ldr=512,
+             res_div=64, res_rep=P, gamma=gamma.to(DEV), beta=beta.to(DEV), split=True)
+    assert _err(_jn(out), ref) < GATE
+
+
+@pytest.mark.parametrize("G", [1, 19])
+def test_split_gemm_convs(G):
+    """3x3 on a 4x4 map (shifted TMA boxes), stride-2 1x1, residual + relu tail, grouped dual-accumulator SKBlock."""
+    from ait_b200 import _lib as L, ops
+    from ait_b200.packing import HeadEngine
+    g = torch.Generator().manual_seed(G)
+    x = torch.randn(G, 512, 4, 4, generator=g)
+    w = torch.randn(512, 512, 3, 3, generator=g) / 68.0
+    bias = torch.randn(512, generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=1)).permute(0, 2, 3, 1).reshape(G * 16, 512)
+    out = torch.zeros((G * 16, 1024), dtype=BF, device=DEV)
+    ops.gemm(_sp(x.permute(0, 2, 3, 1).contiguous()), _sp(HeadEngine._tap_major(w).contiguous()), out, M=G * 16,
+             N=512, K=512, block_n=256, view="map", map_args=(512, 4, 4, 1, G), taps=9,
+             flags=L.EPI_BIAS | L.EPI_RELU, bias=bias.to(DEV), split=True)
+    assert _err(_jn(out), ref) < GATE
+
+    x8 = torch.randn(G, 1024, 8, 8, generator=g)
+    xt = _sp(x8.permute(0, 2, 3, 1).contiguous())
+    w1 = torch.randn(2048, 1024, 1, 1, generator=g) / 32.0
+    res = torch.randn(G * 16, 2048, generator=g)
+    ref = F.relu(F.conv2d(x8.double(), w1.double(), stride=2).permute(0, 2, 3, 1).reshape(G * 16, 2048) + res.double())
+    out = torch.zeros((G * 16, 4096), dtype=BF, device=DEV)
+    ops.gemm(xt, _sp(w1.flatten(1).contiguous()), out, M=G * 16, N=2048, K=1024, block_n=256, view="map",
+             map_args=(1024, 8, 4, 2, G), flags=L.EPI_RES | L.EPI_RES_RELU, res=_sp(res), ldr=2048, split=True)
+    assert _err(_jn(out), ref) < GATE
+
+    k1 = torch.randn(1024, 128, 1, 1, generator=g) / 11.0
+    k3 = torch.randn(1024, 128, 3, 3, generator=g) / 34.0
+    b1, b3 = torch.randn(1024, generator=g) * 0.1, torch.randn(1024, generator=g) * 0.1
+    f1 = F.relu(F.conv2d(x8.double(), k1.double(), b1.double(), groups=8))
+    f3 = F.relu(F.conv2d(x8.double(), k3.double(), b3.double(), padding=1, groups=8))
+    ref = (f1 * f1 + f3 * f3).permute(0, 2, 3, 1).reshape(G * 64, 1024)
+    wf = torch.cat([HeadEngine._tap_major(k3), HeadEngine._tap_major(k1)], dim=1).contiguous()
+    out = torch.zeros((G * 64, 2048), dtype=BF, device=DEV)
+    ops.gemm(xt, _sp(wf), out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G), taps=9,
+             group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_DUAL, bias=b3.to(DEV), dual=True,
+             bias2=b1.to(DEV), split=True)
+    assert _err(_jn(out), ref) < 2 * GATE        # squared outputs double the relative error
+
+
+@pytest.mark.parametrize("mode", ["self_pad", "causal", "cross"])
+def test_split_attn_core(mode):
+    from ait_b200 import ops
+    from test_gpu_gemm_attn import _attn_ref
+    g = torch.Generator().manual_seed(5)
+    G, rep = (6, 1) if mode != "cross" else (6, 3)
+    q = torch.randn(G // rep, 64, 512, generator=g)
+    k = torch.randn(G, 64, 512, generator=g)
+    v = torch.randn(G, 64, 512, generator=g)
+    w_sk, b_sk = torch.randn(512, 64, generator=g) * 0.3, torch.randn(512, generator=g) * 0.1
+    if mode == "causal":
+        mask = torch.tril(torch.ones(64, 64))[None, None]
+    else:
+        mask = (torch.arange(64) < 49).float()[None, None, None, :]
+    ref = _attn_ref(q.double(), k.double(), v.double(), w_sk.double(), b_sk.double(), mask)
+    kv = _sp(torch.cat([k, v], dim=2).contiguous())                      # [G, 64, hi 1024 | lo 1024], like KVc
+    out = torch.zeros((G, 64, 128), dtype=BF, device=DEV)
+    ops.attn_core(_sp(q), 512, rep, kv, kv.view(-1)[512:], 1024, w_sk.to(DEV), b_sk.to(DEV), G,
+                  1 if mode == "causal" else 0, 64 if mode == "causal" else 49, out, split=True)
+    assert _err(_jn(out), ref) < 1e-4            # tf32/fp16 path: ~2e-3
+
+
+def test_split_transposes_and_pool_heads():
+    from ait_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 1024, 64, generator=g)
+    t = ops.transpose_cs(x.to(DEV), True, split_dst=True)
+    assert t.shape == (3, 64, 2048) and t.dtype == BF
+    assert _err(_jn(t), x.transpose(1, 2)) < 2 ** -16
+    back = ops.transpose_cs(t, False, split_src=True)
+    assert back.dtype == torch.float32 and _err(back.cpu(), x) < 2 ** -16
+    top = torch.randn(5, 16, 2048, generator=g)
+    feat, _, _ = ops.pool_heads(_sp(top), 1, split=True)
+    assert _err(feat.cpu(), top.mean(1)) < 1e-5

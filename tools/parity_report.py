@@ -20,8 +20,8 @@ def err(a, b):
 def main():
     B, P = 2, 4
     non_img, non_qry, rois = head_inputs(B, P)
-    for dtype in (torch.float32, torch.bfloat16):
-        for round_acts in ((False, True) if dtype == torch.float32 else (False,)):
+    for dtype in ("fp32", "tf32", "bf16"):
+        for round_acts in ((False, True) if dtype == "tf32" else (False,)):
             head, g = golden_head(compute_dtype=dtype)
             sd = head.state_dict()
             with torch.no_grad():
