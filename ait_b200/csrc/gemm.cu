@@ -106,7 +106,7 @@ struct GemmCfg {
 //   mt : 128-row tile index (rows mt*128 ...), n0 : first output column, t_row : TMEM address of this
 //   warp's lane quadrant in the accumulator stage, stg : this warp's 4 KB staging tile.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BLOCK_N, bool CL, bool SPLIT>
+template <typename T, int BLOCK_N, bool CL, bool SPLIT, int COLS = BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
                                               uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
                                               int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
@@ -115,306 +115,364 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   constexpr int kCh = kRowBytes / 16;                  // 16-byte pieces per row (8 | 4)
   constexpr int kRpi = 32 / kCh;                       // rows covered by one warp instruction (4 | 8)
   constexpr int kIt = kCh;                             // instructions per 32-row chunk (8 | 4)
+  constexpr uint32_t kFull = 0xffffffffu;
   const int row_in_tile = q * 32 + lane;
   const int piece = lane % kCh;
   const int srow0 = lane / kCh;
   auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
   const T* res = reinterpret_cast<const T*>(p.res);
-  {
-      // rows this lane serves in the coalesced phases
-      T* optr[kIt];
-      const T* rptr[kIt];
-      uint32_t vmask = 0;
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int m = mt * kBlockM + q * 32 + it * kRpi + srow0;
-        const bool ok = m < p.M;
-        const int mm = ok ? m : 0;
-        const int orow = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
-        optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
-        int rrow = 0;
-        if (p.flags & AITB_EPI_RES) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
-        rptr[it] = res + (size_t)rrow * p.ldr + n0 + piece * (16 / (int)sizeof(T));
-        vmask |= (ok ? 1u : 0u) << it;
-      }
-      // this thread's own row (for the fp32 positional table)
-      const int m_own = mt * kBlockM + row_in_tile;
-      const int mm_own = m_own < p.M ? m_own : 0;
-      const int orow_own = (mm_own / p.rows_in) * p.rows_out + (mm_own % p.rows_in);
-      const float* prow = p.pos + (size_t)((p.flags & AITB_EPI_POS) ? (orow_own % p.pos_rows) : 0) * p.N + n0;
 
-      // coalesced global -> this thread's 32 values of its row (columns c0 .. c0+31)
-      // issue this lane's share of a coalesced 32-row x 32-column global read (no dependent use yet)
-      auto issue_loads = [&](const T* const* ptrs, int c0, uint4 (&val)[kIt]) {
+  // rows this lane serves in the coalesced phases
+  T* optr[kIt];
+  const T* rptr[kIt];
+  uint32_t vmask = 0;
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-          val[it] = make_uint4(0u, 0u, 0u, 0u);
-          if ((vmask >> it) & 1u) val[it] = ld_global_v4(ptrs[it] + c0);
-        }
-      };
-      // ... and turn it into this thread's 32 values of its own row through the swizzled staging tile
-      auto exchange = [&](const uint4 (&val)[kIt], float (&r)[32]) {
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-          const int sr = it * kRpi + srow0;
-          *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val[it];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < kCh; ++j) {
-          const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16);
-          if constexpr (sizeof(T) == 4) {
-            r[4 * j + 0] = __uint_as_float(x.x); r[4 * j + 1] = __uint_as_float(x.y);
-            r[4 * j + 2] = __uint_as_float(x.z); r[4 * j + 3] = __uint_as_float(x.w);
-          } else {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              r[8 * j + 2 * e] = f.x;
-              r[8 * j + 2 * e + 1] = f.y;
-            }
-          }
-        }
-        __syncwarp();
-      };
-      // vectorised read-only loads of per-column parameters (bias / gamma / beta / pos): 8 x 128-bit
-      auto add_vec = [&](const float* src, float (&v)[32]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(src) + j);
-          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-        }
-      };
-      // this thread's 32 values -> coalesced global store at column `c0` of the rows this warp covers
-      auto stage_store_raw = [&](int c0, const float (&v)[32]) {
-#pragma unroll
-        for (int j = 0; j < kCh; ++j) {
-          uint4 x;
-          if constexpr (sizeof(T) == 4) {
-            x = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                           __float_as_uint(v[4 * j + 3]));
-          } else {
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-          }
-          *reinterpret_cast<uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16) = x;
-        }
-        __syncwarp();
-        uint4 val[kIt];
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-          const int sr = it * kRpi + srow0;
-          val[it] = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
-        }
-#pragma unroll
-        for (int it = 0; it < kIt; ++it)
-          if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val[it];
-        __syncwarp();
-      };
-      // split mode: hi = bf16(v) into the hi plane, lo = bf16(v - hi) into the lo plane (o_lo columns further)
-      auto stage_store = [&](int c0, const float (&v)[32]) {
-        stage_store_raw(c0, v);
-        if constexpr (SPLIT) {
-          float lo[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-          stage_store_raw(c0 + p.o_lo, lo);
-        }
-      };
-      // residual chunk (columns c0..c0+31 of this thread's row) from prefetched coalesced loads
-      auto add_residual = [&](const uint4 (&hi)[kIt], const uint4 (&lo)[kIt], float (&v)[32]) {
-        float r[32];
-        exchange(hi, r);
-        if constexpr (SPLIT) {
-          float r2[32];
-          exchange(lo, r2);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j] + r2[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
-      };
+  for (int it = 0; it < kIt; ++it) {
+    const int m = mt * kBlockM + q * 32 + it * kRpi + srow0;
+    const bool ok = m < p.M;
+    const int mm = ok ? m : 0;
+    const int orow = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
+    optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
+    int rrow = 0;
+    if (p.flags & AITB_EPI_RES) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
+    rptr[it] = res + (size_t)rrow * p.ldr + n0 + piece * (16 / (int)sizeof(T));
+    vmask |= (ok ? 1u : 0u) << it;
+  }
+  // this thread's own row (for the fp32 positional table)
+  const int m_own = mt * kBlockM + row_in_tile;
+  const int mm_own = m_own < p.M ? m_own : 0;
+  const int orow_own = (mm_own / p.rows_in) * p.rows_out + (mm_own % p.rows_in);
+  const float* prow = p.pos + (size_t)((p.flags & AITB_EPI_POS) ? (orow_own % p.pos_rows) : 0) * p.N + n0;
 
-      mbar_wait(acc_full_bar, aph);
-      tc_fence_after();
-
-      if ((p.flags & AITB_EPI_LN) == 0) {
-        // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead
-        const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
-        const bool aux_acc = !aux_res && (p.flags & AITB_EPI_ACCUM) != 0;
-        uint4 pre[kIt], pre2[kIt];
-        if (aux_res) issue_loads(rptr, c_begin, pre);
-        if (aux_acc) issue_loads(optr, c_begin, pre);
-        if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c_begin + p.r_lo, pre2); }
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(t_row + c0, raw);
-          uint4 cur[kIt], cur2[kIt];
-          if (aux_res || aux_acc) {
+  // issue this lane's share of a coalesced 32-row x 32-column global read (no dependent use yet)
+  auto issue_loads = [&](const T* const* ptrs, int c0, uint4 (&val)[kIt]) {
 #pragma unroll
-            for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
-            if constexpr (SPLIT) {
+    for (int it = 0; it < kIt; ++it) {
+      val[it] = make_uint4(0u, 0u, 0u, 0u);
+      if ((vmask >> it) & 1u) val[it] = ld_global_v4(ptrs[it] + c0);
+    }
+  };
+  // ... and turn it into this thread's 32 values of its own row through the swizzled staging tile
+  auto exchange = [&](const uint4 (&val)[kIt], float (&r)[32]) {
 #pragma unroll
-              for (int it = 0; it < kIt; ++it) cur2[it] = pre2[it];
-            }
-            if (c0 + 32 < c_end) {
-              if (aux_res) issue_loads(rptr, c0 + 32, pre); else issue_loads(optr, c0 + 32, pre);
-              if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c0 + 32 + p.r_lo, pre2); }
-            }
-          }
-          tmem_ld_wait();
-          float v[32];
+    for (int it = 0; it < kIt; ++it) {
+      const int sr = it * kRpi + srow0;
+      *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val[it];
+    }
+    __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if constexpr (SPLIT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
-          }
-          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
-          if (p.flags & AITB_EPI_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.flags & AITB_EPI_SQUARE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
-          }
-          if constexpr (BLOCK_N == 128) {
-            if (p.flags & AITB_EPI_DUAL) {  // second accumulator: same activation, then summed
-              tmem_ld32(t_row + BLOCK_N + c0, raw);
-              tmem_ld_wait();
-              float u[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
-              if constexpr (SPLIT) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) u[j] *= p.acc_scale2;
-              }
-              add_vec(p.bias2 + n0 + c0, u);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (p.flags & AITB_EPI_RELU) u[j] = fmaxf(u[j], 0.f);
-                if (p.flags & AITB_EPI_SQUARE) u[j] = u[j] * u[j];
-                v[j] += u[j];
-              }
-            }
-          }
-          if (aux_res) add_residual(cur, cur2, v);
-          if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
-          if (p.flags & AITB_EPI_ACCUM) {
-            float r[32];
-            if (!aux_acc) issue_loads(optr, c0, cur);   // RES and ACCUM together: second stream not prefetched
-            exchange(cur, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
-          }
-          if (p.flags & AITB_EPI_RES_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (sizeof(T) == 4 && p.round_tf32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-          }
-          stage_store(c0, v);
-        }
+    for (int j = 0; j < kCh; ++j) {
+      const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16);
+      if constexpr (sizeof(T) == 4) {
+        r[4 * j + 0] = __uint_as_float(x.x); r[4 * j + 1] = __uint_as_float(x.y);
+        r[4 * j + 2] = __uint_as_float(x.z); r[4 * j + 3] = __uint_as_float(x.w);
       } else {
-        // ---- full-row LayerNorm.  Plain: the CTA's accumulator holds all N = BLOCK_N columns of the row.
-        //      CL: it holds half of the row; partial (sum, M2) are exchanged with the peer CTA via DSMEM.
-        float sum = 0.f;
-        const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
-        uint4 pre[kIt], pre2[kIt];
-        if (aux_res) issue_loads(rptr, 0, pre);
-        if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, p.r_lo, pre2); }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(t_row + c0, raw);
-          uint4 cur[kIt], cur2[kIt];
-          if (aux_res) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
 #pragma unroll
-            for (int it = 0; it < kIt; ++it) cur[it] = pre[it];
-            if (c0 + 32 < BLOCK_N) issue_loads(rptr, c0 + 32, pre);
-            if constexpr (SPLIT) {
-#pragma unroll
-              for (int it = 0; it < kIt; ++it) cur2[it] = pre2[it];
-              if (c0 + 32 < BLOCK_N) issue_loads(rptr, c0 + 32 + p.r_lo, pre2);
-            }
-          }
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if constexpr (SPLIT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
-          }
-          if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
-          if (aux_res) add_residual(cur, cur2, v);
-          if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            sum += v[j];
-            raw[j] = __float_as_uint(v[j]);
-          }
-          tmem_st32(t_row + c0, raw);
-        }
-        tmem_st_wait();
-        float mean = sum * (1.f / BLOCK_N);
-        float ssq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(t_row + c0, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(raw[j]) - mean;
-            ssq += d * d;
-          }
-        }
-        float n_cols = (float)BLOCK_N;
-        if constexpr (CL) {
-          // send (sum, M2) of my half-row to the peer, wait for the peer's, combine (Chan et al.)
-          const uint32_t peer = cta_rank ^ 1u;
-          st_cluster_f32x2(mapa_u32(smem_u32(&stats[as * 128 + row_in_tile]), peer), sum, ssq);
-          mbar_arrive_cluster(mapa_u32(smem_u32(stats_full_bar), peer));
-          mbar_wait_cluster(stats_full_bar, aph);
-          const float2 ps = stats[as * 128 + row_in_tile];
-          const float mean_p = ps.x * (1.f / BLOCK_N);
-          const float mean_all = (sum + ps.x) * (0.5f / BLOCK_N);
-          const float da = mean - mean_all, db = mean_p - mean_all;
-          ssq = ssq + ps.y + (float)BLOCK_N * (da * da + db * db);
-          mean = mean_all;
-          n_cols = 2.f * BLOCK_N;
-        }
-        const float rstd = rsqrtf(ssq / n_cols + p.eps);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(t_row + c0, raw);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + c0) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + c0) + j);
-            v[4 * j + 0] = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * g4.x + b4.x;
-            v[4 * j + 1] = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-            v[4 * j + 2] = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
-            v[4 * j + 3] = (__uint_as_float(raw[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-          }
-          if (sizeof(T) == 4 && p.round_tf32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-          }
-          stage_store(c0, v);
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          r[8 * j + 2 * e] = f.x;
+          r[8 * j + 2 * e + 1] = f.y;
         }
       }
+    }
+    __syncwarp();
+  };
+  // Per-column parameters (bias / gamma / beta) of the columns this warp drains, [c_begin, c_end), are
+  // fetched ONCE per tile -- before the accumulator wait, so their latency hides behind the main loop --
+  // as one 128-bit load per lane and 128-column slice, and handed to the row-owning threads by shuffles.
+  // COLS = number of columns this warp drains (c_end - c_begin)
+  struct LaneVec { float4 s[COLS > 128 ? 2 : 1]; };
+  auto load_lane_vec = [&](const float* base) {  // base = parameter array + n0 + c_begin
+    LaneVec lv;
+    lv.s[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane * 4 < COLS) lv.s[0] = __ldg(reinterpret_cast<const float4*>(base) + lane);
+    if constexpr (COLS > 128) lv.s[1] = __ldg(reinterpret_cast<const float4*>(base + 128) + lane);
+    return lv;
+  };
+  // v[j] (+)= param[c_rel + j], c_rel = chunk offset from c_begin (multiple of 32)
+  auto lane_vec_chunk = [&](const LaneVec& lv, int c_rel, float (&o)[32]) {
+    float4 b = lv.s[0];
+    if constexpr (COLS > 128) {
+      if (c_rel & 128) b = lv.s[1];
+    }
+    const int sl = (c_rel & 127) >> 2;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      o[4 * jj + 0] = __shfl_sync(kFull, b.x, sl + jj);
+      o[4 * jj + 1] = __shfl_sync(kFull, b.y, sl + jj);
+      o[4 * jj + 2] = __shfl_sync(kFull, b.z, sl + jj);
+      o[4 * jj + 3] = __shfl_sync(kFull, b.w, sl + jj);
+    }
+  };
+  auto add_lane_vec = [&](const LaneVec& lv, int c_rel, float (&v)[32]) {
+    float o[32];
+    lane_vec_chunk(lv, c_rel, o);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += o[j];
+  };
+  // fp32 positional table rows differ per thread: direct vector loads
+  auto add_vec = [&](const float* src, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  };
+  // this thread's 32 values -> coalesced global store at column `c0` of the rows this warp covers
+  auto stage_store_raw = [&](int c0, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < kCh; ++j) {
+      uint4 x;
+      if constexpr (sizeof(T) == 4) {
+        x = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                       __float_as_uint(v[4 * j + 3]));
+      } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+      }
+      *reinterpret_cast<uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16) = x;
+    }
+    __syncwarp();
+    uint4 val[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int sr = it * kRpi + srow0;
+      val[it] = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it)
+      if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val[it];
+    __syncwarp();
+  };
+  // split mode: hi = bf16(v) into the hi plane, lo = bf16(v - hi) into the lo plane (o_lo columns further)
+  auto stage_store = [&](int c0, const float (&v)[32]) {
+    stage_store_raw(c0, v);
+    if constexpr (SPLIT) {
+      float lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      stage_store_raw(c0 + p.o_lo, lo);
+    }
+  };
+  // residual chunk (columns c0..c0+31 of this thread's row) from prefetched coalesced loads
+  auto add_residual = [&](const uint4 (&hi)[kIt], const uint4 (&lo)[kIt], float (&v)[32]) {
+    float r[32];
+    exchange(hi, r);
+    if constexpr (SPLIT) {
+      float r2[32];
+      exchange(lo, r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += r[j] + r2[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += r[j];
+    }
+  };
+  // pull this warp's residual rows towards L2 while the main loop of the tile is still running
+  auto prefetch_residual = [&]() {
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      if (!((vmask >> it) & 1u)) continue;
+      // the kCh lanes that share a row split its lines among themselves
+      for (int l = piece; l < (COLS * (int)sizeof(T) + 127) / 128; l += kCh) {
+        const T* a = rptr[it] - piece * (16 / (int)sizeof(T)) + c_begin + l * (128 / (int)sizeof(T));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        if constexpr (SPLIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + p.r_lo));
+      }
+    }
+  };
+
+  const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
+  LaneVec lv_bias, lv_bias2, lv_gamma, lv_beta;  // bias2: dual (BLOCK_N 128) only; gamma / beta: CL only
+  if (p.flags & AITB_EPI_BIAS) lv_bias = load_lane_vec(p.bias + n0 + c_begin);
+  if constexpr (BLOCK_N == 128) {
+    if (p.flags & AITB_EPI_DUAL) lv_bias2 = load_lane_vec(p.bias2 + n0 + c_begin);
+  }
+  if constexpr (CL) {
+    if (p.flags & AITB_EPI_LN) {
+      lv_gamma = load_lane_vec(p.gamma + n0 + c_begin);
+      lv_beta = load_lane_vec(p.beta + n0 + c_begin);
+    }
+  }
+  if (aux_res) prefetch_residual();
+
+  mbar_wait(acc_full_bar, aph);
+  tc_fence_after();
+
+  if (!CL || (p.flags & AITB_EPI_LN) == 0) {
+    // one auxiliary read stream (residual, or the output itself for ACCUM) is prefetched one chunk ahead;
+    // the TMEM read of chunk c+1 is in flight while chunk c is processed
+    const bool aux_acc = !aux_res && (p.flags & AITB_EPI_ACCUM) != 0;
+    const bool dual = BLOCK_N == 128 && (p.flags & AITB_EPI_DUAL) != 0;
+    uint4 pre[kIt], pre2[kIt];
+    if (aux_res) issue_loads(rptr, c_begin, pre);
+    if (aux_acc) issue_loads(optr, c_begin, pre);
+    if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c_begin + p.r_lo, pre2); }
+    uint32_t raw[32], raw2[32];
+    tmem_ld32(t_row + c_begin, raw);
+    if (dual) tmem_ld32(t_row + BLOCK_N + c_begin, raw2);
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      tmem_ld_wait();
+      float v[32], u[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if constexpr (BLOCK_N == 128) {
+        if (dual) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw2[j]);
+        }
+      }
+      if (c0 + 32 < c_end) {  // next chunk's TMEM read overlaps this chunk's math and stores
+        tmem_ld32(t_row + c0 + 32, raw);
+        if (dual) tmem_ld32(t_row + BLOCK_N + c0 + 32, raw2);
+      }
+      if constexpr (SPLIT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
+      }
+      if (p.flags & AITB_EPI_BIAS) add_lane_vec(lv_bias, c0 - c_begin, v);
+      if (p.flags & AITB_EPI_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.flags & AITB_EPI_SQUARE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+      }
+      if constexpr (BLOCK_N == 128) {
+        if (dual) {  // second accumulator: same activation, then summed
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u[j] *= p.acc_scale2;
+          }
+          add_lane_vec(lv_bias2, c0 - c_begin, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (p.flags & AITB_EPI_RELU) u[j] = fmaxf(u[j], 0.f);
+            if (p.flags & AITB_EPI_SQUARE) u[j] = u[j] * u[j];
+            v[j] += u[j];
+          }
+        }
+      }
+      if (aux_res) {
+        add_residual(pre, pre2, v);
+        if (c0 + 32 < c_end) {  // next chunk's residual (its lines were prefetched into L2 before the tile)
+          issue_loads(rptr, c0 + 32, pre);
+          if constexpr (SPLIT) issue_loads(rptr, c0 + 32 + p.r_lo, pre2);
+        }
+      }
+      if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
+      if (p.flags & AITB_EPI_ACCUM) {
+        float r[32];
+        if (!aux_acc) issue_loads(optr, c0, pre);   // RES and ACCUM together: second stream not prefetched
+        exchange(pre, r);
+        if (aux_acc && c0 + 32 < c_end) issue_loads(optr, c0 + 32, pre);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+      }
+      if (p.flags & AITB_EPI_RES_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (sizeof(T) == 4 && p.round_tf32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      }
+      stage_store(c0, v);
+    }
+  } else {
+    // ---- full-row LayerNorm.  Plain: the CTA's accumulator holds all N = BLOCK_N columns of the row.
+    //      CL: it holds half of the row; partial (sum, M2) are exchanged with the peer CTA via DSMEM.
+    // Pass 1 builds x = acc + bias + residual + pos, writes it back to TMEM and accumulates the shifted sums
+    // S1 = sum(x - s), S2 = sum((x - s)^2) with s = mean of the row's first 32 columns (so the variance
+    // M2 = S2 - S1^2 / n loses nothing to cancellation); pass 2 normalises.
+    float shift = 0.f, S1 = 0.f, S2 = 0.f;
+    uint4 pre[kIt], pre2[kIt];
+    if (aux_res) issue_loads(rptr, 0, pre);
+    if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, p.r_lo, pre2); }
+    uint32_t raw[32];
+    tmem_ld32(t_row, raw);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (c0 + 32 < BLOCK_N) tmem_ld32(t_row + c0 + 32, raw);
+      if constexpr (SPLIT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
+      }
+      if (p.flags & AITB_EPI_BIAS) add_lane_vec(lv_bias, c0, v);
+      if (aux_res) {
+        add_residual(pre, pre2, v);
+        if (c0 + 32 < BLOCK_N) {
+          issue_loads(rptr, c0 + 32, pre);
+          if constexpr (SPLIT) issue_loads(rptr, c0 + 32 + p.r_lo, pre2);
+        }
+      }
+      if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
+      if (c0 == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s += v[j];
+        shift = s * (1.f / 32.f);
+      }
+      uint32_t xo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] - shift;
+        S1 += d;
+        S2 += d * d;
+        xo[j] = __float_as_uint(v[j]);
+      }
+      // the next chunk's tcgen05.ld is in flight: a st to a DIFFERENT column range is independent of it
+      tmem_st32(t_row + c0, xo);
+    }
+    tmem_st_wait();
+    float mean = shift + S1 * (1.f / BLOCK_N);
+    float ssq = S2 - S1 * S1 * (1.f / BLOCK_N);  // centred M2 of my columns
+    float n_cols = (float)BLOCK_N;
+    if constexpr (CL) {
+      // send (sum, M2) of my half-row to the peer, wait for the peer's, combine (Chan et al.)
+      const float sum = mean * (float)BLOCK_N;
+      const uint32_t peer = cta_rank ^ 1u;
+      st_cluster_f32x2(mapa_u32(smem_u32(&stats[as * 128 + row_in_tile]), peer), sum, ssq);
+      mbar_arrive_cluster(mapa_u32(smem_u32(stats_full_bar), peer));
+      tmem_ld32(t_row, raw);  // first chunk of pass 2 travels while we wait for the peer
+      mbar_wait_cluster(stats_full_bar, aph);
+      const float2 ps = stats[as * 128 + row_in_tile];
+      const float mean_p = ps.x * (1.f / BLOCK_N);
+      const float mean_all = (sum + ps.x) * (0.5f / BLOCK_N);
+      const float da = mean - mean_all, db = mean_p - mean_all;
+      ssq = ssq + ps.y + (float)BLOCK_N * (da * da + db * db);
+      mean = mean_all;
+      n_cols = 2.f * BLOCK_N;
+    } else {
+      tmem_ld32(t_row, raw);
+    }
+    const float rstd = rsqrtf(fmaxf(ssq, 0.f) / n_cols + p.eps);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) - mean) * rstd;
+      if (c0 + 32 < BLOCK_N) tmem_ld32(t_row + c0 + 32, raw);
+      float g[32];
+      lane_vec_chunk(lv_gamma, c0, g);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= g[j];
+      add_lane_vec(lv_beta, c0, v);
+      if (sizeof(T) == 4 && p.round_tf32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      }
+      stage_store(c0, v);
+    }
   }
 }
 
@@ -713,7 +771,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<T, BLOCK_N, false, SPLIT>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
+      epilogue_tile<T, BLOCK_N, false, SPLIT, 128>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
                                               mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
                                               half * 128 + 128);
       tc_fence_before();
