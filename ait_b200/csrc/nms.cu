@@ -21,6 +21,7 @@
 // IEEE division is only executed when inter / den is within 4e-6 of the threshold (iou_gt).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/aitb200.h"
 #include "common.cuh"
@@ -231,6 +232,114 @@ nms_compact_kernel(const uint8_t* __restrict__ flags, int n_total, int max_out, 
   for (int i = total + threadIdx.x; i < max_out; i += blockDim.x) ko[i] = -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Proposal mode" fast path (mode 0, max_out <= kLazyMaxOut): greedy NMS only ever compares a
+// candidate with boxes that were KEPT before it, and the caller consumes just the first max_out
+// survivors (proposal_layer.py:156 takes keep[:post_nms_topN]).  So instead of the N^2/2 bitmask
+// (18 M IoU tests at N = 6000) one CTA per image walks the candidates in score order, 64 at a time,
+// with the kept boxes in shared memory:
+//   1. the 64 candidates against every box kept so far          (64 x kept tests, all threads)
+//   2. the 64 x 64 upper triangle inside the block              (bitmask words in shared memory)
+//   3. the serial resolve of the block from those words          (one thread, 64 steps)
+// and stops as soon as max_out boxes are kept: at most N x max_out tests (1.8 M), typically far
+// fewer, no mask in HBM, and the gather by `order` is fused into the candidate load.  Decisions use
+// the same iou_gt predicate in the same (kept, candidate) argument order as the bitmask path, so the
+// two paths and the C oracle agree bit for bit.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kLazyMaxOut = 1024;
+static constexpr int kLazyThreads = 512;
+
+__global__ void __launch_bounds__(kLazyThreads)
+nms_lazy_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ order, int n_total, int n, float thr,
+                int max_out, int64_t* __restrict__ keep_out, int32_t* __restrict__ n_keep,
+                float* __restrict__ rois_out) {
+  extern __shared__ __align__(16) uint8_t lazy_smem[];
+  float4* kb = reinterpret_cast<float4*>(lazy_smem);              // [max_out] kept boxes
+  float* ka = reinterpret_cast<float*>(kb + max_out);             // [max_out] their areas
+  int32_t* kpos = reinterpret_cast<int32_t*>(ka + max_out);       // [max_out] their positions in score order
+  __shared__ float4 cand[64];
+  __shared__ float cand_area[64];
+  __shared__ u64 diag[64];
+  __shared__ unsigned int supp[2];  // candidates suppressed by earlier kept boxes (bits 0-31, 32-63)
+  __shared__ int s_total;
+  const int b = blockIdx.x;
+  const float4* bx = boxes + (size_t)b * n_total;
+  const int64_t* ord = order ? order + (size_t)b * n : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+
+  for (int base = 0; base < n; base += 64) {
+    const int cnt = min(64, n - base);
+    const int nk = s_total;
+    if (tid < 64) {
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < cnt) c = bx[ord ? ord[base + tid] : (int64_t)(base + tid)];
+      cand[tid] = c;
+      cand_area[tid] = area_legacy(c);
+      diag[tid] = 0ULL;
+    }
+    if (tid < 2) supp[tid] = 0u;
+    __syncthreads();
+    // 1. candidates x kept: pair p -> (kept i = p / 64, candidate j = p % 64); a warp shares one kept box
+    for (int p = tid; p < nk * 64; p += kLazyThreads) {
+      const int i = p >> 6, j = p & 63;
+      const bool hit = j < cnt && iou_gt(kb[i], ka[i], cand[j], cand_area[j], thr);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && bal) atomicOr(&supp[j >> 5], bal);
+    }
+    // 2. upper triangle inside the block: (row r, column c > r), 8 threads per row
+    {
+      const int r = tid >> 3, c0 = tid & 7;
+      u64 bits = 0;
+      if (r < cnt) {
+        const float4 me = cand[r];
+        const float my_area = cand_area[r];
+        for (int c = r + 1 + c0; c < cnt; c += 8)
+          if (iou_gt(me, my_area, cand[c], cand_area[c], thr)) bits |= 1ULL << c;
+      }
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+      if (c0 == 0) diag[r] = bits;
+    }
+    __syncthreads();
+    // 3. serial resolve (same loop as nms_scan_kernel)
+    if (tid == 0) {
+      u64 cur = (u64)supp[0] | ((u64)supp[1] << 32);
+      if (cnt < 64) cur |= ~0ULL << cnt;
+      int total = nk;
+      for (int j = 0; j < 64; ++j) {
+        if (!((cur >> j) & 1ULL) && total < max_out) {
+          cur |= diag[j];
+          kb[total] = cand[j];
+          ka[total] = cand_area[j];
+          kpos[total] = base + j;
+          ++total;
+        }
+      }
+      s_total = total;
+    }
+    __syncthreads();
+    if (s_total >= max_out) break;
+  }
+  const int nk = s_total;
+  if (tid == 0) n_keep[b] = nk;
+  for (int i = tid; i < max_out; i += kLazyThreads) {
+    const bool live = i < nk;
+    keep_out[(size_t)b * max_out + i] = live ? kpos[i] : -1;
+    if (rois_out) {
+      const float4 k = live ? kb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* r = rois_out + ((size_t)b * max_out + i) * 5;
+      r[0] = (float)b;
+      r[1] = k.x;
+      r[2] = k.y;
+      r[3] = k.z;
+      r[4] = k.w;
+    }
+  }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct NmsWs {
@@ -261,6 +370,13 @@ int nms_run(const float* boxes, const int64_t* order, int B, int n_total, int n,
   AITB_REQUIRE(order != nullptr || n == n_total, "aitb_nms: order == NULL requires n == n_total");
   AITB_REQUIRE(boxes && keep_out && n_keep && ws, "aitb_nms: null pointer");
   AITB_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)ws & 255) == 0, "aitb_nms: misaligned boxes/workspace");
+  static const bool no_lazy = getenv("AITB_NMS_NO_LAZY") != nullptr;   // debug: force the bitmask path
+  if (mode == 0 && max_out <= kLazyMaxOut && !no_lazy) {
+    const size_t smem = (size_t)max_out * (16 + 4 + 4);
+    nms_lazy_kernel<<<B, kLazyThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), order, n_total, n, thr,
+                                                       max_out, keep_out, n_keep, rois_out);
+    return check_launch("nms_lazy_kernel");
+  }
   const NmsWs L = nms_layout(B, n_total, n);
   AITB_REQUIRE(ws_bytes >= L.total, "aitb_nms: workspace too small (%zu < %zu)", ws_bytes, L.total);
   const int nblk = (n + 63) / 64;

@@ -90,6 +90,21 @@ def test_proposal_tail_matches_oracle_bit_exact(scales, pre, post):
         assert torch.equal(rois[0].cpu(), load_golden("nms_rpn_unit0.pt")["rois"])
 
 
+@pytest.mark.parametrize("pre,post", [(6000, 1), (6000, 5), (6000, 64), (1000, 65), (130, 300), (6000, 1024), (6000, 1025)])
+def test_proposal_tail_early_stop_paths(pre, post):
+    """post <= 1024 takes the kept-list kernel (tests only against boxes kept so far, stops at `post`);
+    1025 takes the bitmask + scan path.  Both must reproduce the reference loop bit for bit."""
+    from ait_b200 import synth
+    from ait_b200.proposal import propose_rois
+    data = [synth.rpn_outputs(40 + u) for u in range(2)]
+    boxes = torch.stack([d[0] for d in data])
+    scores = torch.stack([d[1] for d in data])
+    rois, n_keep = propose_rois(boxes.to(DEV), scores.to(DEV), pre, post, 0.7)
+    ref, counts = head_oracle.propose_rois(boxes, scores, pre, post, 0.7)
+    assert n_keep.tolist() == counts
+    assert torch.equal(rois.cpu(), ref)
+
+
 def test_proposal_tail_zero_padding_when_few_survive():
     from ait_b200.proposal import propose_rois
     boxes = torch.tensor([[10, 10, 50, 50]], dtype=torch.float32).repeat(200, 1)[None].repeat(2, 1, 1)
