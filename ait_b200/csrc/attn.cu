@@ -301,189 +301,157 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// 64x64 bf16 tile (one plane) global -> smem, rows of kHS elements; 16-byte copies
-__device__ __forceinline__ void load_plane(const __nv_bfloat16* __restrict__ g, int ld, __nv_bfloat16* __restrict__ s) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int f = threadIdx.x + kAttnThreads * i;
-    const int r = f >> 3, c8 = (f & 7) * 8;
-    *reinterpret_cast<uint4*>(s + r * kHS + c8) = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * ld + c8));
-  }
-}
+// ---- one-pass kernel: 8 warps per pair, the eight O_h tiles stay in REGISTERS ----------------------------
+// warp w owns query rows 16 (w & 3) .. +15 of heads 4 (w >> 2) .. +3, so its four O_h fragments are
+// 4 x 32 = 128 registers and Q / K / V are read from global memory exactly once (the two-pass kernel above
+// reads them twice).  Each 4-warp head group streams its heads through a double-buffered set of six 64x64 bf16
+// planes (Q, K, V x hi, lo; 128-byte rows, 16-byte chunks XOR-swizzled by row for conflict-free ldmatrix)
+// filled with cp.async one head ahead; one named barrier per head and group.
+static constexpr int kPlaneBytes = kT * 128;                // 64 rows x 64 bf16
+static constexpr int kBufBytes = 6 * kPlaneBytes;           // Qh Ql Kh Kl Vh Vl
+static constexpr int kSplitThreads = 256;
+static constexpr int kPartStride = kD + 2;                  // padded row of the head-group exchange tile (floats)
+// 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
+static constexpr int kSplitSmem = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
 
-__device__ __forceinline__ void scores_softmax_split(const __nv_bfloat16* __restrict__ Qh, const __nv_bfloat16* __restrict__ Ql,
-                                                     const __nv_bfloat16* __restrict__ Kh, const __nv_bfloat16* __restrict__ Kl,
-                                                     int row0, int mask_mode, int n_keys, float (&p)[8][4]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
-#pragma unroll
-  for (int k0 = 0; k0 < kD; k0 += 16) {
-    uint32_t ah[4], al[4];
-    const int aoff = (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + k0 + 8 * (lane >> 4);
-    ldsm_x4(ah, Qh + aoff);
-    ldsm_x4(al, Ql + aoff);
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      uint32_t bh[4], bl[4];
-      const int boff = (8 * j + (lane & 7) + 8 * (lane >> 4)) * kHS + k0 + 8 * ((lane >> 3) & 1);
-      ldsm_x4(bh, Kh + boff);
-      ldsm_x4(bl, Kl + boff);
-      mma_bf16(p[j], al, bh[0], bh[1]);
-      mma_bf16(p[j], ah, bl[0], bl[1]);
-      mma_bf16(p[j], ah, bh[0], bh[1]);
-      mma_bf16(p[j + 1], al, bh[2], bh[3]);
-      mma_bf16(p[j + 1], ah, bl[2], bl[3]);
-      mma_bf16(p[j + 1], ah, bh[2], bh[3]);
-    }
-  }
-  const int r_lo = row0 + g, r_hi = row0 + g + 8;
-  float m_lo = -INFINITY, m_hi = -INFINITY;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int col = nt * 8 + 2 * t + (e & 1);
-      const int row = (e < 2) ? r_lo : r_hi;
-      const bool masked = mask_mode == 0 ? (col >= n_keys) : (col > row);
-      const float v = masked ? -1e9f : p[nt][e] * 0.125f;  // masked_fill(mask == 0, -1e9)
-      p[nt][e] = v;
-      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
-    }
-  }
-  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
-  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
-  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
-  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
-  float s_lo = 0.f, s_hi = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    p[nt][0] = expf(p[nt][0] - m_lo); p[nt][1] = expf(p[nt][1] - m_lo);
-    p[nt][2] = expf(p[nt][2] - m_hi); p[nt][3] = expf(p[nt][3] - m_hi);
-    s_lo += p[nt][0] + p[nt][1];
-    s_hi += p[nt][2] + p[nt][3];
-  }
-  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
-  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
-  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
-  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
-  const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    p[nt][0] *= i_lo; p[nt][1] *= i_lo; p[nt][2] *= i_hi; p[nt][3] *= i_hi;
-  }
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {  // byte offset of 16-byte chunk `chunk` of row `row`
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
-
-static constexpr int kSplitSmem = 6 * kT * kHS * 2 + (4 * kD + 2 * kD + kH * kD) * 4;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_a(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void group_bar(int id) {  // named barrier of one 4-warp head group
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
 
 // q / k / v point at the hi planes; the lo planes start q_lo / kv_lo elements further; ldq / ldkv are the
-// physical (bf16) row pitches.  out: [G*64, hi 64 | lo 64].
-__global__ void __launch_bounds__(kAttnThreads, 3)
+// physical (bf16) row pitches.  out: [G*64, hi 64 | lo 64].  Persistent: CTA c handles pairs c, c + grid, ...;
+// the first head of the next pair is fetched while the current pair finishes (gate, head sum, store).
+__global__ void __launch_bounds__(kSplitThreads, 1)
 attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, int q_rep,
                        const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv, int kv_lo,
-                       const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
+                       const float* __restrict__ w_sk, const float* __restrict__ b_sk, int G, int mask_mode, int n_keys,
                        __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t smem_attn[];
-  __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* Ql = Qh + kT * kHS;
-  __nv_bfloat16* Kh = Ql + kT * kHS;
-  __nv_bfloat16* Kl = Kh + kT * kHS;
-  __nv_bfloat16* Vh = Kl + kT * kHS;
-  __nv_bfloat16* Vl = Vh + kT * kHS;
-  float* colsum = reinterpret_cast<float*>(Vl + kT * kHS);  // [4][kD]
-  float* svec = colsum + 4 * kD;                            // [2][kD]
-  float* gate = svec + 2 * kD;                              // [kH][kD]
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  float* part = reinterpret_cast<float*>(smem_attn + 4 * kBufBytes);  // [kT][kPartStride] head-group exchange
+  float* colsum = part + kT * kPartStride;                            // [8 warps][kD]
+  float* svec = colsum + 8 * kD;                                      // [kD]
+  float* gate = svec + kD;                                            // [kH][kD]
 
-  const int grp = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int row0 = warp * 16;
-  const __nv_bfloat16* qg = q + (size_t)(grp / q_rep) * kT * ldq;
-  const __nv_bfloat16* kg = k + (size_t)grp * kT * ldkv;
-  const __nv_bfloat16* vg = v + (size_t)grp * kT * ldkv;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int hg = warp >> 2, rb = warp & 3, gt = tid & 127;  // head group, row block, thread index inside the group
+  const int row0 = rb * 16;
+  const uint32_t buf0 = smem_u32(smem_attn) + hg * 2 * kBufBytes;
 
-  auto load_head = [&](int h) {
-    load_plane(qg + h * kD, ldq, Qh);
-    load_plane(qg + q_lo + h * kD, ldq, Ql);
-    load_plane(kg + h * kD, ldkv, Kh);
-    load_plane(kg + kv_lo + h * kD, ldkv, Kl);
-    load_plane(vg + h * kD, ldkv, Vh);
-    load_plane(vg + kv_lo + h * kD, ldkv, Vl);
+  auto issue_head = [&](int grp, int h, int slot) {  // cp.async the six planes of head h of pair grp into `slot`
+    const __nv_bfloat16* qg = q + (size_t)(grp / q_rep) * kT * ldq;
+    const __nv_bfloat16* kg = k + (size_t)grp * kT * ldkv;
+    const __nv_bfloat16* vg = v + (size_t)grp * kT * ldkv;
+    const uint32_t base = buf0 + slot * kBufBytes;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = gt + 128 * i;
+      const int r = idx >> 3, ch = idx & 7;
+      const uint32_t d = base + sw_off(r, ch);
+      const size_t qo = (size_t)r * ldq + h * kD + ch * 8, ko = (size_t)r * ldkv + h * kD + ch * 8;
+      cp_async16(d, qg + qo);
+      cp_async16(d + kPlaneBytes, qg + q_lo + qo);
+      cp_async16(d + 2 * kPlaneBytes, kg + ko);
+      cp_async16(d + 3 * kPlaneBytes, kg + kv_lo + ko);
+      cp_async16(d + 4 * kPlaneBytes, vg + ko);
+      cp_async16(d + 5 * kPlaneBytes, vg + kv_lo + ko);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  // ---------------- pass A
-  float s_part = 0.f;
-  for (int h = 0; h < kH; ++h) {
-    __syncthreads();
-    load_head(h);
-    __syncthreads();
-    float p[8][4];
-    scores_softmax_split(Qh, Ql, Kh, Kl, row0, mask_mode, n_keys, p);
+  if ((int)blockIdx.x < G) issue_head(blockIdx.x, hg * 4, 0);
+#pragma unroll 1
+  for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
+  float o[4][8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      float c0 = p[nt][0] + p[nt][2], c1 = p[nt][1] + p[nt][3];
+  for (int h = 0; h < 4; ++h)
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-      }
-      if (g == 0) {
-        colsum[warp * kD + nt * 8 + 2 * t] = c0;
-        colsum[warp * kD + nt * 8 + 2 * t + 1] = c1;
-      }
-    }
-    __syncthreads();
-    {
-      const int half = threadIdx.x >> 6, c = threadIdx.x & 63;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int j = half * 32; j < half * 32 + 32; ++j) {
-        const float cs = colsum[j] + colsum[kD + j] + colsum[2 * kD + j] + colsum[3 * kD + j];
-        acc += cs * (__bfloat162float(Vh[j * kHS + c]) + __bfloat162float(Vl[j * kHS + c]));
-      }
-      s_part += acc;
-    }
-  }
-  svec[(threadIdx.x >> 6) * kD + (threadIdx.x & 63)] = s_part;
-  __syncthreads();
-  if (threadIdx.x < kD) svec[threadIdx.x] = (svec[threadIdx.x] + svec[kD + threadIdx.x]) * (1.f / kT);
-  __syncthreads();
-  for (int o = threadIdx.x; o < kH * kD; o += kAttnThreads) {
-    const float* wr = w_sk + (size_t)o * kD;
-    float acc = __ldg(b_sk + o);
-#pragma unroll 8
-    for (int c = 0; c < kD; c += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
-      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
-    }
-    gate[o] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < kD) {
-    const int c = threadIdx.x;
-    float m = -INFINITY;
-#pragma unroll
-    for (int h = 0; h < kH; ++h) m = fmaxf(m, gate[h * kD + c]);
-    float e[kH], sum = 0.f;
-#pragma unroll
-    for (int h = 0; h < kH; ++h) { e[h] = expf(gate[h * kD + c] - m); sum += e[h]; }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int h = 0; h < kH; ++h) gate[h * kD + c] = e[h] * inv;
-  }
+    for (int nt = 0; nt < 8; ++nt) o[h][nt][0] = o[h][nt][1] = o[h][nt][2] = o[h][nt][3] = 0.f;
 
-  // ---------------- pass B
-  float o_acc[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
-  for (int h = 0; h < kH; ++h) {
-    __syncthreads();
-    load_head(h);
-    __syncthreads();
+  for (int hl = 0; hl < 4; ++hl) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    group_bar(1 + hg);  // head hl has landed for every thread of the group; everyone is done with head hl - 1
+    if (hl + 1 < 4) issue_head(grp, hg * 4 + hl + 1, (hl + 1) & 1);
+    else if (grp + (int)gridDim.x < G) issue_head(grp + gridDim.x, hg * 4, 0);  // next pair's first head
+    const uint32_t base = buf0 + (hl & 1) * kBufBytes;
+    const uint32_t Qh = base, Ql = base + kPlaneBytes, Kh = base + 2 * kPlaneBytes, Kl = base + 3 * kPlaneBytes;
+    const uint32_t Vh = base + 4 * kPlaneBytes, Vl = base + 5 * kPlaneBytes;
+    // ---- S = Q K^T (three bf16 passes), mask, softmax in registers
     float p[8][4];
-    scores_softmax_split(Qh, Ql, Kh, Kl, row0, mask_mode, n_keys, p);
-    float oh[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) oh[nt][0] = oh[nt][1] = oh[nt][2] = oh[nt][3] = 0.f;
+    for (int nt = 0; nt < 8; ++nt) p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {  // 16 channels per step = chunks 2 ks, 2 ks + 1
+      uint32_t ah[4], al[4];
+      const uint32_t ao = sw_off(row0 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4));
+      ldsm_x4_a(ah, Qh + ao);
+      ldsm_x4_a(al, Ql + ao);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t bh[4], bl[4];
+        const uint32_t bo = sw_off(8 * j + (lane & 7) + 8 * (lane >> 4), 2 * ks + ((lane >> 3) & 1));
+        ldsm_x4_a(bh, Kh + bo);
+        ldsm_x4_a(bl, Kl + bo);
+        mma_bf16(p[j], al, bh[0], bh[1]);
+        mma_bf16(p[j], ah, bl[0], bl[1]);
+        mma_bf16(p[j], ah, bh[0], bh[1]);
+        mma_bf16(p[j + 1], al, bh[2], bh[3]);
+        mma_bf16(p[j + 1], ah, bl[2], bl[3]);
+        mma_bf16(p[j + 1], ah, bh[2], bh[3]);
+      }
+    }
+    {
+      const int r_lo = row0 + g, r_hi = row0 + g + 8;
+      float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * t + (e & 1);
+          const int row = (e < 2) ? r_lo : r_hi;
+          const bool masked = mask_mode == 0 ? (col >= n_keys) : (col > row);
+          const float x = masked ? -1e9f : p[nt][e] * 0.125f;  // masked_fill(mask == 0, -1e9)
+          p[nt][e] = x;
+          if (e < 2) m_lo = fmaxf(m_lo, x); else m_hi = fmaxf(m_hi, x);
+        }
+      }
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+      float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        p[nt][0] = expf(p[nt][0] - m_lo); p[nt][1] = expf(p[nt][1] - m_lo);
+        p[nt][2] = expf(p[nt][2] - m_hi); p[nt][3] = expf(p[nt][3] - m_hi);
+        s_lo += p[nt][0] + p[nt][1];
+        s_hi += p[nt][2] + p[nt][3];
+      }
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+      const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        p[nt][0] *= i_lo; p[nt][1] *= i_lo; p[nt][2] *= i_hi; p[nt][3] *= i_hi;
+      }
+    }
+    // ---- O_h = P V (three bf16 passes), accumulated straight into this head's register tile
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
       uint32_t ah[4], al[4];
@@ -494,36 +462,107 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         uint32_t bh[4], bl[4];
-        const int voff = (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * kHS + 8 * j + 8 * (lane >> 4);
-        ldsm_x4_trans(bh, Vh + voff);
-        ldsm_x4_trans(bl, Vl + voff);
-        mma_bf16(oh[j], al, bh[0], bh[1]);
-        mma_bf16(oh[j], ah, bl[0], bl[1]);
-        mma_bf16(oh[j], ah, bh[0], bh[1]);
-        mma_bf16(oh[j + 1], al, bh[2], bh[3]);
-        mma_bf16(oh[j + 1], ah, bl[2], bl[3]);
-        mma_bf16(oh[j + 1], ah, bh[2], bh[3]);
+        const uint32_t vo = sw_off(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), j + (lane >> 4));
+        ldsm_x4_t(bh, Vh + vo);
+        ldsm_x4_t(bl, Vl + vo);
+        mma_bf16(o[hl][j], al, bh[0], bh[1]);
+        mma_bf16(o[hl][j], ah, bl[0], bl[1]);
+        mma_bf16(o[hl][j], ah, bh[0], bh[1]);
+        mma_bf16(o[hl][j + 1], al, bh[2], bh[3]);
+        mma_bf16(o[hl][j + 1], ah, bl[2], bl[3]);
+        mma_bf16(o[hl][j + 1], ah, bh[2], bh[3]);
       }
     }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float2 gv = *reinterpret_cast<const float2*>(&gate[h * kD + nt * 8 + 2 * t]);
-      o_acc[nt][0] += oh[nt][0] * gv.x; o_acc[nt][1] += oh[nt][1] * gv.y;
-      o_acc[nt][2] += oh[nt][2] * gv.x; o_acc[nt][3] += oh[nt][3] * gv.y;
-    }
   }
-  __nv_bfloat16* og = out + (size_t)grp * kT * 2 * kD;
+  // ---------------- s = mean_T(sum_h O_h): column sums of this warp's rows and heads -> shared accumulator
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    const int c = nt * 8 + 2 * t;
-    uint32_t hi, lo;
-    split_pack(o_acc[nt][0], o_acc[nt][1], hi, lo);
-    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + c) = hi;
-    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + kD + c) = lo;
-    split_pack(o_acc[nt][2], o_acc[nt][3], hi, lo);
-    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + c) = hi;
-    *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + kD + c) = lo;
+    float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      c0 += o[h][nt][0] + o[h][nt][2];
+      c1 += o[h][nt][1] + o[h][nt][3];
+    }
+#pragma unroll
+    for (int sft = 4; sft < 32; sft <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, sft);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, sft);
+    }
+    if (g == 0) *reinterpret_cast<float2*>(&colsum[warp * kD + nt * 8 + 2 * t]) = make_float2(c0, c1);
   }
+  __syncthreads();
+  if (tid < kD) {  // fixed summation order: results do not depend on scheduling
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += colsum[w * kD + tid];
+    svec[tid] = a;
+  }
+  __syncthreads();
+  // ---------------- gate = softmax_h(W_sk s + b_sk)
+  for (int oi = tid; oi < kH * kD; oi += kSplitThreads) {
+    const float* wr = w_sk + (size_t)oi * kD;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < kD; c += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
+      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
+    }
+    gate[oi] = acc * (1.f / kT) + __ldg(b_sk + oi);
+  }
+  __syncthreads();
+  if (tid < kD) {
+    const int c = tid;
+    float m = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) m = fmaxf(m, gate[h * kD + c]);
+    float e[kH], sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) { e[h] = expf(gate[h * kD + c] - m); sum += e[h]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int h = 0; h < kH; ++h) gate[h * kD + c] = e[h] * inv;
+  }
+  __syncthreads();
+  // ---------------- out = sum_h O_h * gate_h: each warp folds its four heads, the two head groups meet in smem
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 gv = *reinterpret_cast<const float2*>(&gate[(hg * 4 + h) * kD + nt * 8 + 2 * t]);
+      acc[nt][0] += o[h][nt][0] * gv.x; acc[nt][1] += o[h][nt][1] * gv.y;
+      acc[nt][2] += o[h][nt][2] * gv.x; acc[nt][3] += o[h][nt][3] * gv.y;
+    }
+  }
+  constexpr int kPS = kPartStride;
+  if (hg == 1) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      *reinterpret_cast<float2*>(&part[(row0 + g) * kPS + c]) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(&part[(row0 + g + 8) * kPS + c]) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+  __syncthreads();
+  if (hg == 0) {
+    __nv_bfloat16* og = out + (size_t)grp * kT * 2 * kD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      const float2 a = *reinterpret_cast<const float2*>(&part[(row0 + g) * kPS + c]);
+      const float2 b = *reinterpret_cast<const float2*>(&part[(row0 + g + 8) * kPS + c]);
+      uint32_t hi, lo;
+      split_pack(acc[nt][0] + a.x, acc[nt][1] + a.y, hi, lo);
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + c) = hi;
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + kD + c) = lo;
+      split_pack(acc[nt][2] + b.x, acc[nt][3] + b.y, hi, lo);
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + c) = hi;
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + kD + c) = lo;
+    }
+  }
+  // the next pair's gate / exchange writes are ordered after these reads by its own __syncthreads chain
+  }  // persistent loop over pairs
 }
 
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
@@ -552,9 +591,12 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
       attr_set = true;
     }
     // logical leading dimensions -> physical two-plane rows; the lo plane is one logical row width further
-    attn_core_split_kernel<<<G, kAttnThreads, kSplitSmem, stream>>>(
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attn_core_split_kernel<<<G < sms ? G : sms, kSplitThreads, kSplitSmem, stream>>>(
         (const __nv_bfloat16*)q, 2 * ldq, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, 2 * ldkv, ldkv,
-        w_sk, b_sk, mask_mode, n_keys, (__nv_bfloat16*)out);
+        w_sk, b_sk, G, mask_mode, n_keys, (__nv_bfloat16*)out);
   } else {
     set_error("aitb_attn_core: bad dtype %d", dtype);
     return 1;
