@@ -248,6 +248,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
   return d;
 }
 
+// Same, generalised over the operand-row size: ROW_BYTES = 128 (SWIZZLE_128B, 8-row groups 1024 B apart) or
+// 64 (SWIZZLE_64B, 8-row groups 512 B apart; tile base 512-byte aligned).
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "operand rows are 128 or 64 bytes");
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;   // layout: SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
+
 // Instruction descriptor for kind::tf32 / kind::f16 with fp32 accumulation, K-major A and B.
 //   fmt: 0 = F16, 1 = BF16, 2 = TF32
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {

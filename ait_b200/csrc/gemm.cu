@@ -82,12 +82,17 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BLOCK_N, bool SPLIT>
+// HALF (the split cluster-LayerNorm kernel): a stage holds 64-byte operand rows (32 bf16 of K, 64-byte swizzle)
+// instead of 128-byte ones, so the four planes of a stage are 48 KB and the ring stays four deep.
+template <int BLOCK_N, bool SPLIT, bool HALF = false>
 struct GemmCfg {
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kRowBytes = HALF ? 64 : 128;   // bytes of K per operand row and stage
+  static constexpr int kKSlices = kRowBytes / 32;     // 32-byte K slices (one tcgen05.mma each) per stage
+  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kBBytes = BLOCK_N * kRowBytes;
   static constexpr int kPlanes = SPLIT ? 2 : 1;  // split: [A_hi][A_lo][B_hi][B_lo] per stage
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStages = !SPLIT ? 4 : (BLOCK_N >= 256 ? 2 : (BLOCK_N >= 128 ? 3 : 4));
+  static constexpr int kStages = (!SPLIT || HALF) ? 4 : (BLOCK_N >= 256 ? 2 : (BLOCK_N >= 128 ? 3 : 4));
   static constexpr int kAccStages = 2;
   static constexpr int kUmmaN = BLOCK_N;
   // accumulator stage stride in TMEM columns; BLOCK_N = 128 reserves room for the dual accumulator
@@ -484,9 +489,10 @@ template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKParams p) {
-  using Cfg = GemmCfg<BLOCK_N, SPLIT>;
+  using Cfg = GemmCfg<BLOCK_N, SPLIT, CL && SPLIT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAcc = Cfg::kAccStages;
+  constexpr int kABytes = Cfg::kABytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -584,10 +590,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kPlanes * kABytes);
+          const uint64_t adesc = make_kmajor_desc<Cfg::kRowBytes>(sa);
+          const uint64_t bdesc = make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kPlanes * kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte chunk
+          for (int k = 0; k < Cfg::kKSlices; ++k) {  // 32-byte K slices of the stage's operand rows
             umma_ss<Act<T>::kBytes>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                     (fresh && k == 0) ? 0u : 1u);
             if constexpr (SPLIT) {  // + A_hi * W_lo + A_lo * W_hi
@@ -811,7 +817,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   cuuint64_t gdims[4];
@@ -825,7 +831,7 @@ static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, con
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(tm, dtype == AITB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(ptr), gdims, gstr, gbox, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
@@ -851,7 +857,7 @@ static int num_sms() {
 template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, SPLIT>;
+  using Cfg = GemmCfg<BLOCK_N, SPLIT, CL && SPLIT>;
   static bool attr_set = false;
   auto kern = gemm_tcgen05_kernel<T, BLOCK_N, CL, SPLIT>;
   if (!attr_set) {
@@ -970,29 +976,33 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
                      (d->flags & (AITB_EPI_LN | AITB_EPI_RES | AITB_EPI_ACCUM)) == 0,
                  "aitb_gemm: dual accumulator needs block_n 128, bias2 and the DUAL epilogue");
   const int w_taps = d->taps + (d->dual ? 1 : 0);
+  const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
+  // the split cluster-LayerNorm kernel stages 64-byte operand rows (32 bf16 of K per stage, 64-byte swizzle)
+  const bool half_rows = cluster_ln && split;
+  const int kes = half_rows ? ke / 2 : ke;  // K elements per pipeline stage
   CUtensorMap tmA, tmB;
-  if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, d->a.box, "A")) return 1;
+  uint32_t abox[4] = {(uint32_t)kes, d->a.box[1], d->a.box[2], d->a.box[3]};
+  if (encode_map(&tmA, d->dtype, d->a.ptr, 4, d->a.dims, d->a.strides, abox, "A", half_rows)) return 1;
   const uint64_t w_k = (uint64_t)w_taps * d->k_per_tap;  // logical K of the weight matrix
   const uint64_t wdims[2] = {w_k * (split ? 2 : 1), (uint64_t)d->N};
   const uint64_t wstr[1] = {w_k * (split ? 4 : eb)};
-  const bool cluster_ln = (d->flags & AITB_EPI_LN) != 0;   // N = 512 split over a 2-CTA cluster
   static const bool no_2cta = getenv("AITB_NO_2CTA") != nullptr;
   const bool two_cta = !cluster_ln && !no_2cta && d->block_n == 256 && d->a_group_c == 0 && !d->dual &&
                        (d->M + kBlockM - 1) / kBlockM >= 2;
-  const uint32_t wbox[2] = {(uint32_t)ke, (uint32_t)(two_cta ? 128 : (d->block_n > 256 ? 256 : d->block_n))};
-  if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W")) return 1;
+  const uint32_t wbox[2] = {(uint32_t)kes, (uint32_t)(two_cta ? 128 : (d->block_n > 256 ? 256 : d->block_n))};
+  if (encode_map(&tmB, d->dtype, d->w, 2, wdims, wstr, wbox, "W", half_rows)) return 1;
   const int pl = split ? 2 : 1;  // physical elements per logical element in out / res rows
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.M = d->M;
   kp.N = d->N;
-  kp.k_chunks = d->k_per_tap / ke;
+  kp.k_chunks = d->k_per_tap / kes;
   kp.taps = d->taps;
   kp.a_m_dim = d->a_m_dim;
   kp.a_m_step = d->a_m_step;
   kp.a_group_c = d->a_group_c;
-  kp.ke = ke;
+  kp.ke = kes;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = d->tap_dx[i];
     kp.tap_dy[i] = d->tap_dy[i];
