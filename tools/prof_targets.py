@@ -1,5 +1,9 @@
-"""Launch the three hot kernels in isolation on benchmark-shaped data (for `ncu --set full`):
-FFN w_1 GEMM, encoder self-attention core, ROIAlign (token-major)."""
+"""Launch the hot kernels in isolation on benchmark-shaped data (for `ncu --set full`):
+FFN w_1 GEMM (2-CTA), FFN w_2 GEMM (cluster LayerNorm), attention fc GEMM (K = 64, LayerNorm), encoder
+self-attention core, ROIAlign (token-major), proposal top-n + NMS.
+
+    python tools/prof_targets.py [reps] [fp32|tf32|bf16]
+"""
 import os
 import sys
 
@@ -12,27 +16,60 @@ from ait_b200.proposal import propose_rois  # noqa: E402
 dev = "cuda:0"
 B, P = 8, 300
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+mode = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+split = mode == "fp32"
+dt = torch.bfloat16 if mode == "bf16" else torch.float32
+
+
+def act(x):
+    """fp32 tensor -> activation / weight buffer of the mode."""
+    return ops.split_planes(x) if split else x.to(dt)
+
+
+def buf(rows, cols):
+    return torch.empty(rows, cols * (2 if split else 1), device=dev, dtype=torch.bfloat16 if split else dt)
+
+
 # ROIAlign inputs
 maps = torch.stack([synth.c4_map(u) for u in range(B)]).to(dev)
 rpn = [synth.rpn_outputs(u) for u in range(B)]
-rois, _ = propose_rois(torch.stack([r[0] for r in rpn]).to(dev), torch.stack([r[1] for r in rpn]).to(dev))
-nhwc = ops.transpose_cs(maps.reshape(B, 1024, -1), True).view(B, 38, 63, 1024)
-# GEMM inputs (FFN w_1)
-M, N, K = B * P * 64, 2048, 512
-a = torch.randn(M, K, device=dev)
-w = torch.randn(N, K, device=dev) / K ** 0.5
-o = torch.empty(M, N, device=dev)
-bias = torch.zeros(N, device=dev)
+boxes, scores = torch.stack([r[0] for r in rpn]).to(dev), torch.stack([r[1] for r in rpn]).to(dev)
+rois, _ = propose_rois(boxes, scores)
+nhwc = ops.transpose_cs(maps.reshape(B, 1024, -1), True, out_dtype=dt).view(B, 38, 63, 1024)
+# GEMM inputs
+M = B * P * 64
+x512 = act(torch.randn(M, 512, device=dev))
+x64 = act(torch.randn(M, 64, device=dev))
+w1 = act(torch.randn(2048, 512, device=dev) / 512 ** 0.5)
+w2 = act(torch.randn(512, 2048, device=dev) / 2048 ** 0.5)
+wfc = act(torch.randn(512, 64, device=dev) / 8)
+hid = buf(M, 2048)
+o512 = buf(M, 512)
+b2048 = torch.zeros(2048, device=dev)
+b512 = torch.zeros(512, device=dev)
+gamma = torch.ones(512, device=dev)
 # attention inputs
 G = B * P
-qkv = torch.randn(G * 64, 1536, device=dev)
+qkv = act(torch.randn(G * 64, 1536, device=dev))
 w_sk = torch.randn(512, 64, device=dev) * 0.1
 b_sk = torch.zeros(512, device=dev)
-ao = torch.empty(G, 64, 64, device=dev)
+ao = buf(G * 64, 64)
+cb = 1 if split else 1  # column offsets below are in storage elements of the hi plane
 torch.cuda.synchronize()
 for _ in range(reps):
-    ops.gemm(a, w, o, M=M, N=N, K=K, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=bias)
-    ops.attn_core(qkv, 1536, 1, qkv.view(-1)[512:], qkv.view(-1)[1024:], 1536, w_sk, b_sk, G, 0, 49, ao)
-    ops.roi_align_forward(nhwc, rois.view(-1, 5), 1 / 16.0, 7, 7, 0, token_major=True)
+    ops.gemm(x512, w1, hid, M=M, N=2048, K=512, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=b2048, split=split)
+    ops.gemm(hid, w2, o512, M=M, N=512, K=2048, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN, bias=b512,
+             res=x512, ldr=512, gamma=gamma, beta=b512, split=split)
+    ops.gemm(x64, wfc, o512, M=M, N=512, K=64, block_n=512, flags=L.EPI_RES | L.EPI_LN, res=x512, ldr=512,
+             res_div=64, gamma=gamma, beta=b512, split=split)
+    ops.attn_core(qkv, 1536, 1, qkv.view(-1)[512:], qkv.view(-1)[1024:], 1536, w_sk, b_sk, G, 0, 49, ao, split=split)
+    if split:
+        lib = L.load()
+        pooled = torch.empty(G, 49, 2048, device=dev, dtype=torch.bfloat16)
+        L.check(lib.aitb_roi_align_forward(L.ptr(nhwc), L.ptr(rois.view(-1, 5)), B, 1024, 38, 63, G, 1 / 16.0, 7, 7, 0,
+                                           L.AITB_F32S, 1, L.ptr(pooled), L.stream_ptr()))
+    else:
+        ops.roi_align_forward(nhwc, rois.view(-1, 5), 1 / 16.0, 7, 7, 0, token_major=True)
+    propose_rois(boxes, scores)
 torch.cuda.synchronize()
 print("done")
