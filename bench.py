@@ -33,7 +33,7 @@ PRE_NMS, NMS_THR = 6000, 0.7
 FLOP_PER_PAIR = 1.494e9          # de-duplicated algorithmic FLOPs per pair (SURVEY 8d / BASELINE.md section 3)
 FLOP_PER_UNIT_SHARED = 0.214e9 + 0.646e9
 METRIC = "proposal-query pairs/sec (ROIAlign+AIT head+NMS)"
-FFN_W1_DRAM_BYTES = {"tf32": 0.343995e9 + 1.210071e9, "bf16": None}   # measured with ncu, see profiles/
+FFN_W1_DRAM_BYTES = {"tf32": 0.343995e9 + 1.210071e9, "fp32": 0.325247e9 + 1.210583e9, "bf16": None}   # ncu --set full, see profiles/
 
 
 def parse():
@@ -366,7 +366,7 @@ def run_ours(args):
                          # `ncu --set full` capture (profiles/r01_ncu_full_selected.csv); algorithmic bytes are
                          # A 314.6 MB + W 4.2 MB + out 1258.3 MB = 1.577e9 (fp32), so nothing is re-read
                          "traffic": FFN_W1_DRAM_BYTES.get(args.dtype),
-                         "traffic_unit": "bytes/launch (ncu, tf32 capture)",
+                         "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/*_ncu_full_selected.csv)",
                          "peak_source": "%s bf16 cuBLAS burst %.1f TFLOP/s%s" % (src, tf_burst, {
                              "bf16": "", "tf32": " / 2 (tf32 runs at half the bf16 rate; no tf32 figure in MEASURED_PEAKS.json)",
                              "fp32": " / 3 (split mode: three bf16 MMA passes hi*hi + hi*lo + lo*hi per algorithmic product)"}[mode]),
