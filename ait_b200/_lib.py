@@ -108,6 +108,7 @@ SIGNATURES = {
                                C.POINTER(HeadTaps), _vp, _sz, _vp]),
     "aitb_ait_workspace_bytes": (_sz, [_i, _i, _i]),
     "aitb_ait_forward": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "aitb_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -32,6 +32,9 @@ int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat,
                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
 
+int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
+              cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // error string + launch counter (thread-local)
 // ---------------------------------------------------------------------------------------------
@@ -583,6 +586,11 @@ int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat
                     float* feat_out, float* bbox_out, float* cls_prob_out, aitb_stream_t stream) {
   return pool_heads_run(top, dtype, G, P, qfeat, w_bbox, b_bbox, w1, b1, w2, b2, feat_out, bbox_out, cls_prob_out,
                         (cudaStream_t)stream);
+}
+
+int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
+               aitb_stream_t stream) {
+  return wgrad_run(dy, ldy, x, ldx, M, N, K, dw, ldw, (cudaStream_t)stream);
 }
 
 size_t aitb_head_workspace_bytes(int B, int P, int dtype) {

@@ -817,7 +817,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle64 = false) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle64 = false,
+                      bool swizzle128_atom32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   cuuint64_t gdims[4];
@@ -831,7 +832,9 @@ static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, con
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(tm, dtype == AITB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(ptr), gdims, gstr, gbox, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                    : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
@@ -841,6 +844,12 @@ static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, con
     return 1;
   }
   return 0;
+}
+
+// fp32 map with the "128-byte swizzle, 32-byte atom" pattern (the only layout tcgen05 accepts for MN-major tf32 operands)
+int encode_map_f32_mn(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const char* what) {
+  return encode_map(tm, AITB_F32, ptr, rank, dims, strides_bytes, box, what, false, true);
 }
 
 static int g_num_sms = 0;

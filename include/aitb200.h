@@ -277,6 +277,16 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
                      int B, int P, float* out_nchw, void* workspace, size_t workspace_bytes,
                      aitb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training (BASELINE config 4): backward building blocks.  fp32 storage, tf32 tensor-core math.
+ * The reference obtains these from torch autograd over the modules of a5-a9.
+ * ---------------------------------------------------------------------------------------- */
+
+/* weight gradient of out = x * w^T:  dw[N, ldw] += dy[M, 0..N)^T * x[M, 0..K)   (row-major activations with
+ * leading dimensions ldy / ldx; dw must be initialised by the caller, e.g. zeroed).  N % 128 == 0, K % 64 == 0. */
+int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
+               aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 
