@@ -15,8 +15,8 @@ AITB_F32, AITB_BF16, AITB_F32S = 0, 1, 2
 #   "bf16"  AITB_BF16  bf16 storage and math
 MODES = {"fp32": AITB_F32S, "tf32": AITB_F32, "bf16": AITB_BF16}
 
-EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL = (
-    1, 2, 4, 8, 16, 32, 64, 128, 256)
+EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256, 512)
 
 
 class View4(C.Structure):
@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("res_div", C.c_int), ("res_rep", C.c_int),
         ("pos", C.c_void_p), ("pos_rows", C.c_int),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
-        ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int),
+        ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int), ("ln_rstd", C.c_void_p),
     ]
 
 
@@ -81,6 +81,27 @@ class HeadWeights(C.Structure):
     ]
 
 
+class LinearG(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class MHAG(C.Structure):
+    _fields_ = [("w_qkv", C.c_void_p), ("w_sk", C.c_void_p), ("b_sk", C.c_void_p), ("w_fc", C.c_void_p),
+                ("ln", LNorm)]
+
+
+class FFNG(C.Structure):
+    _fields_ = [("w1", LinearG), ("w2", LinearG), ("ln", LNorm)]
+
+
+class AITGrads(C.Structure):
+    """aitb_ait_grads: fp32 gradient buffers of the AIT parameters (include/aitb200.h)."""
+    _fields_ = [("enc_emb", LinearG), ("dec_emb", LinearG), ("dec_trans", LinearG),
+                ("enc_ln", LNorm), ("dec_ln", LNorm),
+                ("enc_slf", MHAG), ("dec_slf", MHAG), ("dec_enc", MHAG),
+                ("enc_ffn", FFNG), ("dec_ffn", FFNG)]
+
+
 class HeadTaps(C.Structure):
     _fields_ = [("pooled", C.c_void_p), ("enc_out", C.c_void_p), ("ait_out", C.c_void_p),
                 ("sk_out", C.c_void_p), ("feat", C.c_void_p), ("qfeat", C.c_void_p)]
@@ -109,6 +130,15 @@ SIGNATURES = {
     "aitb_ait_workspace_bytes": (_sz, [_i, _i, _i]),
     "aitb_ait_forward": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "aitb_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "aitb_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "aitb_colsum": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "aitb_bsum": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "aitb_attn_bwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "aitb_ait_saved_bytes": (_sz, [_i, _i]),
+    "aitb_ait_backward_workspace_bytes": (_sz, [_i, _i]),
+    "aitb_ait_forward_train": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "aitb_ait_backward": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _sz, C.POINTER(AITGrads), _vp, _vp, _vp, _sz,
+                               _vp]),
 }
 
 _lib = None

@@ -167,6 +167,340 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Selective-head attention backward, one CTA (4 warps) per proposal-query pair.
+//
+// Forward (attn.cu; system/Modules.py:16-29, SubLayers.py:22-39,89-92):
+//   P_h = softmax(mask(Q_h K_h^T / 8)),  O_h = P_h V_h,  s = mean_T(sum_h O_h),
+//   z = W_sk s + b_sk,  g = softmax over h of z,  out = sum_h O_h * g_h
+// Backward, given dOut [64, 64]:
+//   dg_h[c] = sum_t dOut[t,c] O_h[t,c];  dz_h = g_h * (dg_h - sum_h' g_h' dg_h');  ds = W_sk^T dz
+//   dO_h[t,c] = dOut[t,c] g_h[c] + ds[c] / T
+//   dV_h = P_h^T dO_h;  dP = dO_h V_h^T;  dS = P * (dP - rowsum(dP * P));  dQ_h = dS K_h / 8;  dK_h = dS^T Q_h / 8
+// Pass A recomputes P_h / O_h of every head for dg and s; pass B recomputes P_h again and forms the five
+// products.  64^3 products run on mma.sync.m16n8k8 tf32 with fp32 tiles in shared memory; (dz, s) are
+// written per pair so that d(W_sk) = dz^T s and d(b_sk) = colsum(dz) become one small wgrad / column sum.
+// Masked keys have P = 0, hence dS = 0 and zero dK / dV rows: no special casing.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kBT = 64;        // tokens == head dim == 64
+static constexpr int kBS = 68;        // fp32 tile row stride (conflict-free A-fragment reads)
+static constexpr int kBH = 8;
+static constexpr int kAttnBwdThreads = 128;
+static constexpr int kAttnBwdSmem = (6 * kBT * kBS + 4 * kBT /*col partials*/ + 2 * kBH * kBT /*gate, dg -> dz*/ + 2 * kBT) * 4;
+
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C[16 x 64] (this warp's rows r0..r0+15) = A * B over a contraction of 64.
+//   A(i, k) = TA ? a[k * kBS + i] : a[i * kBS + k]        (i = output row)
+//   B(k, n) = BKN ? b[k * kBS + n] : b[n * kBS + k]       (n = output column)
+template <bool TA, bool BKN>
+__device__ __forceinline__ void mm64(const float* __restrict__ a, const float* __restrict__ b, int r0, float (&c)[8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < kBT; k0 += 8) {
+    uint32_t af[4];
+    auto A = [&](int i, int k) { return __float_as_uint(TA ? a[k * kBS + i] : a[i * kBS + k]); };
+    af[0] = A(r0 + g, k0 + t);
+    af[1] = A(r0 + g + 8, k0 + t);
+    af[2] = A(r0 + g, k0 + t + 4);
+    af[3] = A(r0 + g + 8, k0 + t + 4);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      auto B = [&](int k, int n) { return __float_as_uint(BKN ? b[k * kBS + n] : b[n * kBS + k]); };
+      mma_tf32(c[nt], af, B(k0 + t, nt * 8 + g), B(k0 + t + 4, nt * 8 + g));
+    }
+  }
+}
+
+// global [64 rows, ld] fp32 (64 columns from `g`) -> shared tile, rounded to tf32
+__device__ __forceinline__ void load_tile_f32(const float* __restrict__ g, int ld, float* __restrict__ s) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = threadIdx.x + kAttnBwdThreads * i;
+    const int r = f >> 4, c4 = (f & 15) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * ld + c4));
+    *reinterpret_cast<float4*>(s + r * kBS + c4) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
+  }
+}
+
+// this warp's C fragment -> global rows r0.., 64 columns
+__device__ __forceinline__ void store_frag(const float (&c)[8][4], float* __restrict__ gp, int ld, int r0, float scale) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<float2*>(gp + (size_t)(r0 + g) * ld + nt * 8 + 2 * t) =
+        make_float2(tf32r(c[nt][0] * scale), tf32r(c[nt][1] * scale));
+    *reinterpret_cast<float2*>(gp + (size_t)(r0 + g + 8) * ld + nt * 8 + 2 * t) =
+        make_float2(tf32r(c[nt][2] * scale), tf32r(c[nt][3] * scale));
+  }
+}
+
+// mask + softmax of this warp's 16 score rows, in the mma C layout (as in attn.cu)
+__device__ __forceinline__ void softmax_frag(float (&p)[8][4], int row0, int mask_mode, int n_keys) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + 2 * t + (e & 1);
+      const int row = (e < 2) ? r_lo : r_hi;
+      const bool masked = mask_mode == 0 ? (col >= n_keys) : (col > row);
+      const float v = masked ? -1e9f : p[nt][e] * 0.125f;
+      p[nt][e] = v;
+      if (e < 2) m_lo = fmaxf(m_lo, v); else m_hi = fmaxf(m_hi, v);
+    }
+  }
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] = expf(p[nt][0] - m_lo); p[nt][1] = expf(p[nt][1] - m_lo);
+    p[nt][2] = expf(p[nt][2] - m_hi); p[nt][3] = expf(p[nt][3] - m_hi);
+    s_lo += p[nt][0] + p[nt][1];
+    s_hi += p[nt][2] + p[nt][3];
+  }
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+  s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+  s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+  const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    p[nt][0] *= i_lo; p[nt][1] *= i_lo; p[nt][2] *= i_hi; p[nt][3] *= i_hi;
+  }
+}
+
+// fragment -> shared tile rows r0.. (rounded to tf32: it is an MMA operand next)
+__device__ __forceinline__ void frag_to_smem(const float (&c)[8][4], float* __restrict__ s, int r0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<float2*>(s + (r0 + g) * kBS + nt * 8 + 2 * t) = make_float2(tf32r(c[nt][0]), tf32r(c[nt][1]));
+    *reinterpret_cast<float2*>(s + (r0 + g + 8) * kBS + nt * 8 + 2 * t) = make_float2(tf32r(c[nt][2]), tf32r(c[nt][3]));
+  }
+}
+
+// column sums over this warp's 16 rows of a fragment -> part[warp][64]
+__device__ __forceinline__ void frag_colsum(const float (&c)[8][4], float* __restrict__ part) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    float c0 = c[nt][0] + c[nt][2], c1 = c[nt][1] + c[nt][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    }
+    if (g == 0) {
+      part[warp * kBT + nt * 8 + 2 * t] = c0;
+      part[warp * kBT + nt * 8 + 2 * t + 1] = c1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAttnBwdThreads, 2)
+attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __restrict__ k, const float* __restrict__ v,
+                int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, const float* __restrict__ dout,
+                int mask_mode, int n_keys, float* __restrict__ dq, int lddq, float* __restrict__ dk,
+                float* __restrict__ dv, int lddkv, float* __restrict__ dz_out, float* __restrict__ s_out) {
+  extern __shared__ __align__(16) float bsm[];
+  float* sQ = bsm;
+  float* sK = sQ + kBT * kBS;
+  float* sV = sK + kBT * kBS;
+  float* sDOut = sV + kBT * kBS;   // dOut of the pair (all heads)
+  float* sP = sDOut + kBT * kBS;   // P_h, later reused for dO_h^T-free products
+  float* sX = sP + kBT * kBS;      // dO_h (pass B), then dS
+  float* part = sX + kBT * kBS;    // [4][64]
+  float* gate = part + 4 * kBT;    // [8][64]
+  float* dgv = gate + kBH * kBT;   // [8][64] dg, then dz
+  float* svec = dgv + kBH * kBT;   // [64] s
+  float* dsv = svec + kBT;         // [64] ds / T
+
+  const int grp = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16;
+  const float* qg = q + (size_t)(grp / q_rep) * kBT * ldq;
+  const float* kg = k + (size_t)grp * kBT * ldkv;
+  const float* vg = v + (size_t)grp * kBT * ldkv;
+  {  // dOut tile (kept in fp32: it is multiplied elementwise, rounded where it becomes an MMA operand)
+    const float* dg_ = dout + (size_t)grp * kBT * kBT;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = tid + kAttnBwdThreads * i;
+      const int r = f >> 4, c4 = (f & 15) * 4;
+      *reinterpret_cast<float4*>(sDOut + r * kBS + c4) = __ldg(reinterpret_cast<const float4*>(dg_ + (size_t)r * kBT + c4));
+    }
+  }
+  float s_acc = 0.f;  // thread c < 64: sum_h sum_t O_h[t, c]
+
+  // ---------------- pass A: dg_h and s
+  for (int h = 0; h < kBH; ++h) {
+    __syncthreads();
+    load_tile_f32(qg + h * kBT, ldq, sQ);
+    load_tile_f32(kg + h * kBT, ldkv, sK);
+    load_tile_f32(vg + h * kBT, ldkv, sV);
+    __syncthreads();
+    float p[8][4], o[8][4];
+    mm64<false, false>(sQ, sK, row0, p);            // S = Q K^T
+    softmax_frag(p, row0, mask_mode, n_keys);
+    frag_to_smem(p, sP, row0);
+    __syncwarp();
+    mm64<false, true>(sP, sV, row0, o);             // O_h = P V   (only this warp's rows of P are read)
+    frag_colsum(o, part);
+    __syncthreads();
+    if (tid < kBT) s_acc += part[tid] + part[kBT + tid] + part[2 * kBT + tid] + part[3 * kBT + tid];
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {                // o *= dOut  (elementwise), then column sums = dg_h
+      const float2 a = *reinterpret_cast<const float2*>(sDOut + (row0 + g) * kBS + nt * 8 + 2 * t);
+      const float2 b = *reinterpret_cast<const float2*>(sDOut + (row0 + g + 8) * kBS + nt * 8 + 2 * t);
+      o[nt][0] *= a.x; o[nt][1] *= a.y; o[nt][2] *= b.x; o[nt][3] *= b.y;
+    }
+    frag_colsum(o, part);
+    __syncthreads();
+    if (tid < kBT) dgv[h * kBT + tid] = part[tid] + part[kBT + tid] + part[2 * kBT + tid] + part[3 * kBT + tid];
+  }
+  if (tid < kBT) svec[tid] = s_acc * (1.f / kBT);
+  __syncthreads();
+  // ---------------- gate forward + backward
+  for (int o = tid; o < kBH * kBT; o += kAttnBwdThreads) {
+    const float* wr = w_sk + (size_t)o * kBT;
+    float acc = __ldg(b_sk + o);
+#pragma unroll 8
+    for (int c = 0; c < kBT; c += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
+      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
+    }
+    gate[o] = acc;
+  }
+  __syncthreads();
+  if (tid < kBT) {
+    const int c = tid;
+    float m = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kBH; ++h) m = fmaxf(m, gate[h * kBT + c]);
+    float e[kBH], sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < kBH; ++h) { e[h] = expf(gate[h * kBT + c] - m); sum += e[h]; }
+    const float inv = 1.f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int h = 0; h < kBH; ++h) { e[h] *= inv; dot += e[h] * dgv[h * kBT + c]; }
+#pragma unroll
+    for (int h = 0; h < kBH; ++h) {
+      gate[h * kBT + c] = e[h];
+      const float dzv = e[h] * (dgv[h * kBT + c] - dot);
+      dgv[h * kBT + c] = dzv;                                   // dz
+      dz_out[(size_t)grp * kBH * kBT + h * kBT + c] = dzv;
+    }
+    s_out[(size_t)grp * kBT + c] = svec[c];
+  }
+  __syncthreads();
+  if (tid < kBT) {   // ds[c'] = sum_o W_sk[o, c'] dz[o]; stored as ds / T (the mean over T rows)
+    float acc = 0.f;
+    for (int o = 0; o < kBH * kBT; ++o) acc += __ldg(w_sk + (size_t)o * kBT + tid) * dgv[o];
+    dsv[tid] = acc * (1.f / kBT);
+  }
+
+  // ---------------- pass B
+  for (int h = 0; h < kBH; ++h) {
+    __syncthreads();
+    load_tile_f32(qg + h * kBT, ldq, sQ);
+    load_tile_f32(kg + h * kBT, ldkv, sK);
+    load_tile_f32(vg + h * kBT, ldkv, sV);
+    // dO_h = dOut * g_h + ds / T  -> sX (tf32)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = tid + kAttnBwdThreads * i;
+      const int r = f >> 4, c4 = (f & 15) * 4;
+      const float4 d4 = *reinterpret_cast<const float4*>(sDOut + r * kBS + c4);
+      const float4 g4 = *reinterpret_cast<const float4*>(gate + h * kBT + c4);
+      const float4 s4 = *reinterpret_cast<const float4*>(dsv + c4);
+      *reinterpret_cast<float4*>(sX + r * kBS + c4) = make_float4(tf32r(d4.x * g4.x + s4.x), tf32r(d4.y * g4.y + s4.y),
+                                                                  tf32r(d4.z * g4.z + s4.z), tf32r(d4.w * g4.w + s4.w));
+    }
+    __syncthreads();
+    float p[8][4], dp[8][4];
+    mm64<false, false>(sQ, sK, row0, p);
+    softmax_frag(p, row0, mask_mode, n_keys);
+    frag_to_smem(p, sP, row0);
+    mm64<false, false>(sX, sV, row0, dp);           // dP = dO_h V^T
+    // dS = P * (dP - rowsum(dP * P))
+    float r_lo = 0.f, r_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      r_lo += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
+      r_hi += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+    }
+    r_lo += __shfl_xor_sync(0xffffffffu, r_lo, 1);
+    r_lo += __shfl_xor_sync(0xffffffffu, r_lo, 2);
+    r_hi += __shfl_xor_sync(0xffffffffu, r_hi, 1);
+    r_hi += __shfl_xor_sync(0xffffffffu, r_hi, 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      dp[nt][0] = p[nt][0] * (dp[nt][0] - r_lo); dp[nt][1] = p[nt][1] * (dp[nt][1] - r_lo);
+      dp[nt][2] = p[nt][2] * (dp[nt][2] - r_hi); dp[nt][3] = p[nt][3] * (dp[nt][3] - r_hi);
+    }
+    __syncthreads();                                // every warp is done reading sX (dO_h) as the A operand of dP ...
+    // dV_h = P^T dO_h needs sX (dO_h) and sP from all warps; dS goes to a separate tile: reuse sQ? no -- Q is
+    // still needed for dK.  Write dS over sDS = sX only after dV is done; so: dV first.
+    {
+      float dvf[8][4];
+      mm64<true, true>(sP, sX, row0, dvf);          // [j, c] = sum_t P[t, j] dO[t, c]
+      store_frag(dvf, dv + (size_t)grp * kBT * lddkv + h * kBT, lddkv, row0, 1.f);
+    }
+    __syncthreads();
+    frag_to_smem(dp, sX, row0);                     // dS (this warp's rows)
+    __syncwarp();
+    {
+      float dqf[8][4];
+      mm64<false, true>(sX, sK, row0, dqf);         // dQ = dS K / 8  (own rows of dS only)
+      store_frag(dqf, dq + (size_t)grp * kBT * lddq + h * kBT, lddq, row0, 0.125f);
+    }
+    __syncthreads();
+    {
+      float dkf[8][4];
+      mm64<true, true>(sX, sQ, row0, dkf);          // [j, d] = sum_t dS[t, j] Q[t, d] / 8
+      store_frag(dkf, dk + (size_t)grp * kBT * lddkv + h * kBT, lddkv, row0, 0.125f);
+    }
+  }
+}
+
+int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
+                 const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
+                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream) {
+  AITB_REQUIRE(G > 0 && q && k && v && w_sk && b_sk && dout && dq && dk && dv && dz && s_out, "aitb_attn_bwd: bad arguments");
+  AITB_REQUIRE(q_rep >= 1 && (mask_mode == 0 || mask_mode == 1) && n_keys >= 1 && n_keys <= kBT, "aitb_attn_bwd: bad mode");
+  AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && lddq % 2 == 0 && lddkv % 2 == 0, "aitb_attn_bwd: bad leading dimensions");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem);
+    AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn_bwd) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  attn_bwd_kernel<<<G, kAttnBwdThreads, kAttnBwdSmem, stream>>>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, mask_mode,
+                                                               n_keys, dq, lddq, dk, dv, lddkv, dz, s_out);
+  return check_launch("attn_bwd_kernel");
+}
+
 static int g_sms_bwd = 0;
 static int sms_bwd() {
   if (g_sms_bwd == 0) {
@@ -176,6 +510,144 @@ static int sms_bwd() {
     if (g_sms_bwd <= 0) g_sms_bwd = 148;
   }
   return g_sms_bwd;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward from the saved output:  y = x_hat * gamma + beta,  x_hat = (x - mean) * rstd
+//   a = g * gamma;  dx = rstd * (a - mean(a) - x_hat * mean(a * x_hat));  dgamma += g * x_hat;  dbeta += g
+// x_hat is recovered as (y - beta) / gamma (the forward keeps y and 1/sigma only; a channel whose gamma is
+// exactly 0 contributes x_hat = 0).  One warp per row (512 channels, 16 per lane), persistent over rows so the
+// parameter gradients are reduced in registers and leave the CTA as 2 x 512 atomics.
+// Row compaction: rows are grouped by `grp` (64 tokens); only the first `valid` rows of a group store dx, at
+// row (group * valid + t) -- the encoder's 64 -> 49 un-padding (system/Models.py:268-270); the pad rows still
+// feed dgamma / dbeta (their x_hat is LayerNorm(pos_table[t])).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ rstd, int rows, int grp, int valid,
+              float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][512];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gm[16], bt[16], ig[16], dg_acc[16], db_acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = (i >> 2) * 128 + lane * 4 + (i & 3);
+    gm[i] = gamma[c];
+    bt[i] = beta[c];
+    ig[i] = gm[i] != 0.f ? 1.f / gm[i] : 0.f;
+    dg_acc[i] = db_acc[i] = 0.f;
+  }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    float gv[16], xh[16];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * 512 + j * 128 + lane * 4));
+      const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + (size_t)row * 512 + j * 128 + lane * 4));
+      gv[4 * j] = g4.x; gv[4 * j + 1] = g4.y; gv[4 * j + 2] = g4.z; gv[4 * j + 3] = g4.w;
+      xh[4 * j] = y4.x; xh[4 * j + 1] = y4.y; xh[4 * j + 2] = y4.z; xh[4 * j + 3] = y4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      xh[i] = (xh[i] - bt[i]) * ig[i];
+      dg_acc[i] += gv[i] * xh[i];
+      db_acc[i] += gv[i];
+      gv[i] *= gm[i];           // a
+      m1 += gv[i];
+      m2 += gv[i] * xh[i];
+    }
+    m1 = warp_sum(m1) * (1.f / 512.f);
+    m2 = warp_sum(m2) * (1.f / 512.f);
+    const int t = row % grp;
+    if (t < valid) {
+      const float rs = rstd[row];
+      float* o = dx + ((size_t)(row / grp) * valid + t) * 512;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 r;
+        r.x = tf32r(rs * (gv[4 * j] - m1 - xh[4 * j] * m2));          // rounded (RN): dx feeds tf32 MMAs next
+        r.y = tf32r(rs * (gv[4 * j + 1] - m1 - xh[4 * j + 1] * m2));
+        r.z = tf32r(rs * (gv[4 * j + 2] - m1 - xh[4 * j + 2] * m2));
+        r.w = tf32r(rs * (gv[4 * j + 3] - m1 - xh[4 * j + 3] * m2));
+        *reinterpret_cast<float4*>(o + j * 128 + lane * 4) = r;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = (i >> 2) * 128 + lane * 4 + (i & 3);
+    red[0][warp][c] = dg_acc[i];
+    red[1][warp][c] = db_acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[0][w][c]; b += red[1][w][c]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+int ln_bwd_run(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows,
+               int grp, int valid, float* dx, float* dgamma, float* dbeta, cudaStream_t stream) {
+  AITB_REQUIRE(g && y && gamma && beta && rstd && dx && dgamma && dbeta, "aitb_ln_bwd: null pointer");
+  AITB_REQUIRE(rows > 0 && grp > 0 && valid > 0 && valid <= grp && rows % grp == 0, "aitb_ln_bwd: bad row grouping");
+  int grid = (rows + 7) / 8;
+  if (grid > 4 * sms_bwd()) grid = 4 * sms_bwd();
+  ln_bwd_kernel<<<grid, 256, 0, stream>>>(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta);
+  return check_launch("ln_bwd_kernel");
+}
+
+// out[c] += sum over rows of x[row, c]   (bias gradients), x row-major [rows, ld], c < cols (cols % 4 == 0)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, int rows_per_cta, float* __restrict__ out) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ld + c));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  atomicAdd(out + c, acc.x);
+  atomicAdd(out + c + 1, acc.y);
+  atomicAdd(out + c + 2, acc.z);
+  atomicAdd(out + c + 3, acc.w);
+}
+
+int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStream_t stream) {
+  AITB_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0, "aitb_colsum: bad arguments");
+  const int gx = (cols / 4 + 255) / 256;
+  int gy = (4 * sms_bwd() + gx - 1) / gx;
+  if (gy > (rows + 31) / 32) gy = (rows + 31) / 32;
+  if (gy < 1) gy = 1;
+  const int rpc = (rows + gy - 1) / gy;
+  gy = (rows + rpc - 1) / rpc;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>(x, ld, rows, cols, rpc, out);
+  return check_launch("colsum_kernel");
+}
+
+// out[b, l] = sum_p x[b, p, l]   (gradient of the unit -> proposal broadcast), l < L (L % 4 == 0)
+__global__ void __launch_bounds__(256)
+bsum_kernel(const float* __restrict__ x, int P, int L, float* __restrict__ out) {
+  const int l = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (l >= L) return;
+  const float* xb = x + (size_t)blockIdx.y * P * L + l;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = 0; p < P; ++p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * L));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)blockIdx.y * L + l) = acc;
+}
+
+int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t stream) {
+  AITB_REQUIRE(x && out && B > 0 && P > 0 && L > 0 && L % 4 == 0, "aitb_bsum: bad arguments");
+  bsum_kernel<<<dim3((L / 4 + 255) / 256, B), 256, 0, stream>>>(x, P, L, out);
+  return check_launch("bsum_kernel");
 }
 
 // dw [N, ldw] += dy[M, ldy (cols n_off .. n_off + N)]^T * x[M, ldx (cols 0 .. K)]

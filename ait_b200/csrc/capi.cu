@@ -34,6 +34,13 @@ int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat,
 
 int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
               cudaStream_t stream);
+int ln_bwd_run(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows,
+               int grp, int valid, float* dx, float* dgamma, float* dbeta, cudaStream_t stream);
+int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStream_t stream);
+int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t stream);
+int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
+                 const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
+                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // error string + launch counter (thread-local)
@@ -218,6 +225,10 @@ struct HeadBufs {
   void *SKq, *qc1, *qc2, *qds, *qy0, *qy1;
   float *feat, *qfeat;
   void* in_tok;  // ait_forward only: token-major copy of x_props
+  // training forward: separate buffers where inference reuses one (AOc / H2 alias AO / Hh in inference), and
+  // 1 / sigma of every LayerNorm row (NULL in inference)
+  void *AOc, *Hh2;
+  float *r_X1, *r_X2, *r_ENC, *r_T0, *r_T1, *r_D1, *r_DEC;
 };
 
 static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool with_roi, bool with_top) {
@@ -259,6 +270,8 @@ static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool w
     hb.feat = (float*)b.take(bp * 2048 * 4);
     hb.qfeat = (float*)b.take((size_t)B * 2048 * 4);
   }
+  hb.AOc = hb.AO;
+  hb.Hh2 = hb.Hh;
 }
 
 // Side stream for the proposal-independent query branch (a few tiny launches that would otherwise sit
@@ -299,7 +312,7 @@ static int side_stream(SideStream** out) {
 // ---------------------------------------------------------------------------------------------
 static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* qbuf, int ldq, int q_rep,
                      const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode, int n_keys, void* ao,
-                     const void* res, int res_rep, void* out, cudaStream_t st) {
+                     const void* res, int res_rep, void* out, cudaStream_t st, float* rstd = nullptr) {
   const int dt = w->dtype;
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32));
@@ -313,11 +326,12 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   d.res_rep = res_rep;
   d.gamma = m.ln.gamma;
   d.beta = m.ln.beta;
+  d.ln_rstd = rstd;
   return gemm_run(&d, st);
 }
 
 static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* x, int M, void* hidden, void* out,
-                     cudaStream_t st) {
+                     cudaStream_t st, float* rstd = nullptr) {
   const int dt = w->dtype;
   aitb_gemm_desc d1 = gemm_base(dt, M, 2048, 512, f.w1.w, 256, hidden, 2048, w->round_tf32);
   view_plain(d1, x, 512);
@@ -332,6 +346,7 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
   d2.ldr = 512;
   d2.gamma = f.ln.gamma;
   d2.beta = f.ln.beta;
+  d2.ln_rstd = rstd;
   return gemm_run(&d2, st);
 }
 
@@ -349,13 +364,14 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
   d.pos_rows = 64;
   d.gamma = w->dec_ln.gamma;
   d.beta = w->dec_ln.beta;
+  d.ln_rstd = hb.r_T0;
   RUN(gemm_run(&d, st));
   aitb_gemm_desc dq = gemm_base(dt, RQ, 1536, 512, w->dec_slf.w_qkv, 256, hb.QKVd, 1536, rt);
   view_plain(dq, hb.T0, 512);
   RUN(gemm_run(&dq, st));
   const uint8_t* qkv = (const uint8_t*)hb.QKVd;
   RUN(mha_block(w, w->dec_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, B, 1, 64, hb.AOd, hb.T0, 1,
-                hb.T1, st));
+                hb.T1, st, hb.r_T1));
   aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
   view_plain(dc, hb.T1, 512);
   return gemm_run(&dc, st);
@@ -379,6 +395,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     d.rows_out = 64;
     d.gamma = w->enc_ln.gamma;
     d.beta = w->enc_ln.beta;
+    d.ln_rstd = hb.r_X1;
     RUN(gemm_run(&d, st));
     RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st));
   }
@@ -389,9 +406,9 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
     RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
-                  hb.X2, st));
+                  hb.X2, st, hb.r_X2));
   }
-  RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st));
+  RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st, hb.r_ENC));
   if (enc_tap) {
     cudaError_t e = cudaMemcpyAsync(enc_tap, hb.ENC, (size_t)R * 512 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "enc tap copy failed: %s", cudaGetErrorString(e));
@@ -407,9 +424,10 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     view_plain(d, hb.ENC, 512);
     RUN(gemm_run(&d, st));
     const uint8_t* kv = (const uint8_t*)hb.KVc;
-    RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * cb, 1024, bp, 0, 49, hb.AO, hb.T1, P, hb.D1, st));
+    RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * cb, 1024, bp, 0, 49, hb.AOc, hb.T1, P, hb.D1, st,
+                  hb.r_D1));
   }
-  RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh, hb.DEC, st));
+  RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh2, hb.DEC, st, hb.r_DEC));
   // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
   {
     aitb_gemm_desc d = gemm_base(dt, R, 1024, 512, w->dec_trans.w, 256, hb.AIT, 1024, rt);
@@ -507,6 +525,296 @@ static int check_weights(const aitb_head_weights* w, bool with_top) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Training step of the AIT module (config 4): forward keeping activations, then the backward.
+// fp32 storage + tf32 tensor-core math.  The reference gets this from torch autograd over
+// system/Models.py:231-280; the op order below is the exact reverse of ait_query_side / ait_core.
+// ---------------------------------------------------------------------------------------------
+static void carve_train(Bump& b, HeadBufs& hb, int B, int P) {
+  const size_t bp = (size_t)B * P, R = bp * 64, RQ = (size_t)B * 64;
+  memset(&hb, 0, sizeof(hb));
+  auto f = [&](size_t n) { return b.take(n * 4); };
+  hb.pooled = f(bp * 49 * 1024);
+  hb.qtok = f(RQ * 1024);
+  hb.X1 = f(R * 512);
+  hb.QKV = f(R * 1536);
+  hb.AO = f(R * 64);
+  hb.X2 = f(R * 512);
+  hb.Hh = f(R * 2048);
+  hb.ENC = f(R * 512);
+  hb.T0 = f(RQ * 512);
+  hb.QKVd = f(RQ * 1536);
+  hb.AOd = f(RQ * 64);
+  hb.T1 = f(RQ * 512);
+  hb.Qc = f(RQ * 512);
+  hb.KVc = f(R * 1024);
+  hb.AOc = f(R * 64);
+  hb.D1 = f(R * 512);
+  hb.Hh2 = f(R * 2048);
+  hb.DEC = f(R * 512);
+  hb.AIT = f(R * 1024);
+  hb.r_X1 = (float*)f(R);
+  hb.r_X2 = (float*)f(R);
+  hb.r_ENC = (float*)f(R);
+  hb.r_T0 = (float*)f(RQ);
+  hb.r_T1 = (float*)f(RQ);
+  hb.r_D1 = (float*)f(R);
+  hb.r_DEC = (float*)f(R);
+}
+
+// dX[M, Np] = epilogue( dY[M, Kp] * W[Kp, Np] )  with W^T ([Np, Kp], K-major) in `wt`: the forward GEMM kernel
+static int dgrad(const float* dy, int M, int Kp, int Np, const float* wt, float* out, int flags, const float* res,
+                 int ldr, cudaStream_t st) {
+  const int bn = Np % 256 == 0 ? 256 : (Np % 128 == 0 ? 128 : 64);
+  // gradients are rounded to tf32 (RN) where they are produced: the next MMA would otherwise truncate them
+  aitb_gemm_desc d = gemm_base(AITB_F32, M, Np, Kp, wt, bn, out, Np, 1);
+  view_plain(d, dy, Kp);
+  d.flags = flags;
+  d.res = res;
+  d.ldr = ldr;
+  return gemm_run(&d, st);
+}
+
+// W [N, K] -> W^T [K, N]
+static int transpose_w(const void* w, int N, int K, float* out, cudaStream_t st) {
+  return transpose_run(w, AITB_F32, out, AITB_F32, 1, N, K, 1, st);
+}
+
+struct FfnBwd {
+  const aitb_ffn* w;
+  const aitb_ffn_g* g;
+  const float *x, *hid, *y, *rstd;   // saved: input [R,512], hidden [R,2048], output (post-LN) [R,512], 1/sigma
+};
+
+// backward of y = LN(relu(x W1^T + b1) W2^T + b2 + x); gy -> gx (both [R, 512]); gf / gh are scratch
+static int ffn_backward(const FfnBwd& f, int R, const float* gy, float* gf, float* gh, float* gx, float* w1t, float* w2t,
+                        cudaStream_t st) {
+  RUN(ln_bwd_run(gy, f.y, f.w->ln.gamma, f.w->ln.beta, f.rstd, R, 64, 64, gf, f.g->ln.gamma, f.g->ln.beta, st));
+  RUN(colsum_run(gf, 512, R, 512, f.g->w2.bias, st));
+  RUN(wgrad_run(gf, 512, f.hid, 2048, R, 512, 2048, f.g->w2.w, 2048, st));
+  RUN(transpose_w(f.w->w2.w, 512, 2048, w2t, st));                       // [2048, 512]
+  RUN(dgrad(gf, R, 512, 2048, w2t, gh, AITB_EPI_RELU_MASK, f.hid, 2048, st));
+  RUN(colsum_run(gh, 2048, R, 2048, f.g->w1.bias, st));
+  RUN(wgrad_run(gh, 2048, f.x, 512, R, 2048, 512, f.g->w1.w, 512, st));
+  RUN(transpose_w(f.w->w1.w, 2048, 512, w1t, st));                       // [512, 2048]
+  return dgrad(gh, R, 2048, 512, w1t, gx, AITB_EPI_RES, gf, 512, st);
+}
+
+}  // namespace aitb
+
+using namespace aitb;
+
+extern "C" {
+
+size_t aitb_ait_saved_bytes(int B, int P) {
+  Bump b{nullptr, 0};
+  HeadBufs hb;
+  carve_train(b, hb, B, P);
+  return b.off + 1024;
+}
+
+size_t aitb_ait_backward_workspace_bytes(int B, int P) {
+  const size_t bp = (size_t)B * P, R = bp * 64, RQ = (size_t)B * 64;
+  // per-row widths of the gradient buffers taken in aitb_ait_backward (+ transposed weights, attention dz / s)
+  size_t n = R * (1024 + 512 + 512 + 2048 + 512 + 512 + 64 + 512 + 1024 + 512 + 512 + 512 + 64 + 1536 + 512) +
+             bp * 49 * (512 + 1024) + RQ * (512 * 6 + 64 + 1536 + 1024) + 2 * (bp + B) * (512 + 64) +
+             (size_t)4 * 1024 * 1024 /* largest W^T pair */;
+  return n * 4 + 64 * 1024 /* alignment slack of ~40 buffers */ + 1024;
+}
+
+int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, const float* x_query, int B, int P,
+                           float* out_nchw, void* saved, size_t saved_bytes, aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(check_weights(w, false));
+  AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_forward_train: the training path runs in the fp32-storage / tf32 configuration");
+  AITB_REQUIRE(B > 0 && P > 0 && x_props && x_query && out_nchw && saved, "aitb_ait_forward_train: bad arguments");
+  AITB_REQUIRE(((uintptr_t)saved & 1023) == 0 && saved_bytes >= aitb_ait_saved_bytes(B, P),
+               "aitb_ait_forward_train: `saved` must be 1024-byte aligned and aitb_ait_saved_bytes large");
+  const int bp = B * P;
+  Bump b{(uint8_t*)saved, 0};
+  HeadBufs hb;
+  carve_train(b, hb, B, P);
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (float*)hb.pooled + (size_t)g0 * 49 * 1024, AITB_F32, gn,
+                      1024, 49, 1, st, w->round_tf32));
+  }
+  RUN(transpose_run(x_query, AITB_F32, hb.qtok, AITB_F32, B, 1024, 64, 1, st, w->round_tf32));
+  RUN(ait_query_side(w, hb, B, st));
+  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr));
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run((const float*)hb.AIT + (size_t)g0 * 64 * 1024, AITB_F32, out_nchw + (size_t)g0 * 1024 * 64, AITB_F32,
+                      gn, 1024, 64, 0, st));
+  }
+  return 0;
+}
+
+int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
+                      size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
+                      void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(check_weights(w, false));
+  AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_backward: the training path runs in the fp32-storage / tf32 configuration");
+  AITB_REQUIRE(B > 0 && P > 0 && grad_out_nchw && saved && g && grad_props && grad_query && workspace,
+               "aitb_ait_backward: bad arguments");
+  AITB_REQUIRE(((uintptr_t)saved & 1023) == 0 && saved_bytes >= aitb_ait_saved_bytes(B, P), "aitb_ait_backward: bad `saved`");
+  AITB_REQUIRE(((uintptr_t)workspace & 1023) == 0 && workspace_bytes >= aitb_ait_backward_workspace_bytes(B, P),
+               "aitb_ait_backward: workspace too small or misaligned");
+  const int bp = B * P, R = bp * 64, RQ = B * 64, R49 = bp * 49;
+  Bump sb{(uint8_t*)const_cast<void*>(saved), 0};
+  HeadBufs hb;
+  carve_train(sb, hb, B, P);
+  Bump b{(uint8_t*)workspace, 0};
+  auto f = [&](size_t n) { return (float*)b.take(n * 4); };
+  const float* S_pooled = (const float*)hb.pooled; const float* S_qtok = (const float*)hb.qtok;
+  const float* S_X1 = (const float*)hb.X1; const float* S_QKV = (const float*)hb.QKV; const float* S_AO = (const float*)hb.AO;
+  const float* S_X2 = (const float*)hb.X2; const float* S_H1 = (const float*)hb.Hh; const float* S_ENC = (const float*)hb.ENC;
+  const float* S_T0 = (const float*)hb.T0; const float* S_QKVd = (const float*)hb.QKVd; const float* S_AOd = (const float*)hb.AOd;
+  const float* S_T1 = (const float*)hb.T1; const float* S_Qc = (const float*)hb.Qc; const float* S_KVc = (const float*)hb.KVc;
+  const float* S_AOc = (const float*)hb.AOc; const float* S_D1 = (const float*)hb.D1; const float* S_H2 = (const float*)hb.Hh2;
+  const float* S_DEC = (const float*)hb.DEC;
+
+  float* wta = f((size_t)2048 * 1024);   // transposed-weight scratch (two slots)
+  float* wtb = f((size_t)2048 * 1024);
+  // ---- dec_trans: AIT = DEC Wt^T + b
+  float* gAIT = f((size_t)R * 1024);
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run(grad_out_nchw + (size_t)g0 * 1024 * 64, AITB_F32, gAIT + (size_t)g0 * 64 * 1024, AITB_F32, gn, 1024, 64,
+                      1, st, 1));
+  }
+  RUN(colsum_run(gAIT, 1024, R, 1024, g->dec_trans.bias, st));
+  RUN(wgrad_run(gAIT, 1024, S_DEC, 512, R, 1024, 512, g->dec_trans.w, 512, st));
+  float* gDEC = f((size_t)R * 512);
+  RUN(transpose_w(w->dec_trans.w, 1024, 512, wta, st));                  // [512, 1024]
+  RUN(dgrad(gAIT, R, 1024, 512, wta, gDEC, 0, nullptr, 0, st));
+  // ---- decoder FFN
+  float* gF = f((size_t)R * 512);
+  float* gH = f((size_t)R * 2048);
+  float* gD1 = f((size_t)R * 512);
+  {
+    FfnBwd fb{&w->dec_ffn, &g->dec_ffn, S_D1, S_H2, S_DEC, hb.r_DEC};
+    RUN(ffn_backward(fb, R, gDEC, gF, gH, gD1, wta, wtb, st));
+  }
+  // ---- cross attention: D1 = LN(AOc Wfc^T + T1[unit])
+  float* gC1 = f((size_t)R * 512);
+  RUN(ln_bwd_run(gD1, S_D1, w->dec_enc.ln.gamma, w->dec_enc.ln.beta, hb.r_D1, R, 64, 64, gC1, g->dec_enc.ln.gamma,
+                 g->dec_enc.ln.beta, st));
+  RUN(wgrad_run(gC1, 512, S_AOc, 64, R, 512, 64, g->dec_enc.w_fc, 64, st));
+  float* gAO = f((size_t)R * 64);
+  RUN(transpose_w(w->dec_enc.w_fc, 512, 64, wta, st));                   // [64, 512]
+  RUN(dgrad(gC1, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
+  float* gT1res = f((size_t)RQ * 512);
+  RUN(bsum_run(gC1, B, P, 64 * 512, gT1res, st));                        // residual T1 is shared by the unit's P pairs
+  float* dQpp = f((size_t)R * 512);
+  float* gKVc = f((size_t)R * 1024);
+  float* dz = f((size_t)(bp + B) * 512);
+  float* sv = f((size_t)(bp + B) * 64);
+  RUN(attn_bwd_run(S_Qc, 512, P, S_KVc, S_KVc + 512, 1024, w->dec_enc.w_sk, w->dec_enc.b_sk, gAO, bp, 0, 49, dQpp, 512,
+                   gKVc, gKVc + 512, 1024, dz, sv, st));
+  RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->dec_enc.w_sk, 64, st));
+  RUN(colsum_run(dz, 512, bp, 512, g->dec_enc.b_sk, st));
+  float* gQc = f((size_t)RQ * 512);
+  RUN(bsum_run(dQpp, B, P, 64 * 512, gQc, st));
+  const float* Wq = (const float*)w->dec_enc.w_qkv;
+  const float* Wkv = Wq + (size_t)512 * 512;
+  RUN(wgrad_run(gKVc, 1024, S_ENC, 512, R, 1024, 512, g->dec_enc.w_qkv + (size_t)512 * 512, 512, st));
+  float* gENC = f((size_t)R * 512);
+  RUN(transpose_w(Wkv, 1024, 512, wta, st));                             // [512, 1024]
+  RUN(dgrad(gKVc, R, 1024, 512, wta, gENC, 0, nullptr, 0, st));
+  RUN(wgrad_run(gQc, 512, S_T1, 512, RQ, 512, 512, g->dec_enc.w_qkv, 512, st));
+  float* gT1 = f((size_t)RQ * 512);
+  RUN(transpose_w(Wq, 512, 512, wta, st));
+  RUN(dgrad(gQc, RQ, 512, 512, wta, gT1, AITB_EPI_RES, gT1res, 512, st));
+  // ---- encoder FFN
+  float* gX2 = f((size_t)R * 512);
+  {
+    FfnBwd fb{&w->enc_ffn, &g->enc_ffn, S_X2, S_H1, S_ENC, hb.r_ENC};
+    RUN(ffn_backward(fb, R, gENC, gF, gH, gX2, wta, wtb, st));
+  }
+  // ---- encoder self attention: X2 = LN(AO Wfc^T + X1)
+  float* gA1 = f((size_t)R * 512);
+  RUN(ln_bwd_run(gX2, S_X2, w->enc_slf.ln.gamma, w->enc_slf.ln.beta, hb.r_X2, R, 64, 64, gA1, g->enc_slf.ln.gamma,
+                 g->enc_slf.ln.beta, st));
+  RUN(wgrad_run(gA1, 512, S_AO, 64, R, 512, 64, g->enc_slf.w_fc, 64, st));
+  RUN(transpose_w(w->enc_slf.w_fc, 512, 64, wta, st));
+  RUN(dgrad(gA1, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
+  float* gQKV = f((size_t)R * 1536);
+  RUN(attn_bwd_run(S_QKV, 1536, 1, S_QKV + 512, S_QKV + 1024, 1536, w->enc_slf.w_sk, w->enc_slf.b_sk, gAO, bp, 0, 49, gQKV,
+                   1536, gQKV + 512, gQKV + 1024, 1536, dz, sv, st));
+  RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->enc_slf.w_sk, 64, st));
+  RUN(colsum_run(dz, 512, bp, 512, g->enc_slf.b_sk, st));
+  RUN(wgrad_run(gQKV, 1536, S_X1, 512, R, 1536, 512, g->enc_slf.w_qkv, 512, st));
+  float* gX1 = f((size_t)R * 512);
+  RUN(transpose_w(w->enc_slf.w_qkv, 1536, 512, wta, st));                // [512, 1536]
+  RUN(dgrad(gQKV, R, 1536, 512, wta, gX1, AITB_EPI_RES, gA1, 512, st));
+  // ---- encoder input: X1 = LN(enc_emb(pooled) + b + pos) on the 49 real rows (pad rows: LN(pos) -> dgamma / dbeta only)
+  float* gE0 = f((size_t)R49 * 512);
+  RUN(ln_bwd_run(gX1, S_X1, w->enc_ln.gamma, w->enc_ln.beta, hb.r_X1, R, 64, 49, gE0, g->enc_ln.gamma, g->enc_ln.beta, st));
+  RUN(colsum_run(gE0, 512, R49, 512, g->enc_emb.bias, st));
+  RUN(wgrad_run(gE0, 512, S_pooled, 1024, R49, 512, 1024, g->enc_emb.w, 1024, st));
+  float* gPooled = f((size_t)R49 * 1024);
+  RUN(transpose_w(w->enc_emb.w, 512, 1024, wta, st));                    // [1024, 512]
+  RUN(dgrad(gE0, R49, 512, 1024, wta, gPooled, 0, nullptr, 0, st));
+  for (int g0 = 0; g0 < bp; g0 += 32768) {
+    const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
+    RUN(transpose_run(gPooled + (size_t)g0 * 49 * 1024, AITB_F32, grad_props + (size_t)g0 * 1024 * 49, AITB_F32, gn, 1024, 49,
+                      0, st));
+  }
+  // ---- query side: T1 = LN(AOd Wfc^T + T0), T0 = LN(dec_emb(q) + b + pos), Qc = T1 Wq^T
+  float* gS1 = f((size_t)RQ * 512);
+  RUN(ln_bwd_run(gT1, S_T1, w->dec_slf.ln.gamma, w->dec_slf.ln.beta, hb.r_T1, RQ, 64, 64, gS1, g->dec_slf.ln.gamma,
+                 g->dec_slf.ln.beta, st));
+  RUN(wgrad_run(gS1, 512, S_AOd, 64, RQ, 512, 64, g->dec_slf.w_fc, 64, st));
+  float* gAOd = f((size_t)RQ * 64);
+  RUN(transpose_w(w->dec_slf.w_fc, 512, 64, wta, st));
+  RUN(dgrad(gS1, RQ, 512, 64, wta, gAOd, 0, nullptr, 0, st));
+  float* gQKVd = f((size_t)RQ * 1536);
+  float* dzd = dz + (size_t)bp * 512;
+  float* svd = sv + (size_t)bp * 64;
+  RUN(attn_bwd_run(S_QKVd, 1536, 1, S_QKVd + 512, S_QKVd + 1024, 1536, w->dec_slf.w_sk, w->dec_slf.b_sk, gAOd, B, 1, 64, gQKVd,
+                   1536, gQKVd + 512, gQKVd + 1024, 1536, dzd, svd, st));
+  RUN(wgrad_run(dzd, 512, svd, 64, B, 512, 64, g->dec_slf.w_sk, 64, st));
+  RUN(colsum_run(dzd, 512, B, 512, g->dec_slf.b_sk, st));
+  RUN(wgrad_run(gQKVd, 1536, S_T0, 512, RQ, 1536, 512, g->dec_slf.w_qkv, 512, st));
+  float* gT0 = f((size_t)RQ * 512);
+  RUN(transpose_w(w->dec_slf.w_qkv, 1536, 512, wta, st));
+  RUN(dgrad(gQKVd, RQ, 1536, 512, wta, gT0, AITB_EPI_RES, gS1, 512, st));
+  float* gQ0 = f((size_t)RQ * 512);
+  RUN(ln_bwd_run(gT0, S_T0, w->dec_ln.gamma, w->dec_ln.beta, hb.r_T0, RQ, 64, 64, gQ0, g->dec_ln.gamma, g->dec_ln.beta, st));
+  RUN(colsum_run(gQ0, 512, RQ, 512, g->dec_emb.bias, st));
+  RUN(wgrad_run(gQ0, 512, S_qtok, 1024, RQ, 512, 1024, g->dec_emb.w, 1024, st));
+  float* gQtok = f((size_t)RQ * 1024);
+  RUN(transpose_w(w->dec_emb.w, 512, 1024, wta, st));
+  RUN(dgrad(gQ0, RQ, 512, 1024, wta, gQtok, 0, nullptr, 0, st));
+  RUN(transpose_run(gQtok, AITB_F32, grad_query, AITB_F32, B, 1024, 64, 0, st));
+  AITB_REQUIRE(b.off <= workspace_bytes, "aitb_ait_backward: internal workspace accounting error (%zu > %zu)", b.off,
+               workspace_bytes);
+  return 0;
+}
+
+int aitb_ln_bwd(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows, int grp,
+                int valid, float* dx, float* dgamma, float* dbeta, aitb_stream_t stream) {
+  return ln_bwd_run(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta, (cudaStream_t)stream);
+}
+int aitb_colsum(const float* x, int ld, int rows, int cols, float* out, aitb_stream_t stream) {
+  return colsum_run(x, ld, rows, cols, out, (cudaStream_t)stream);
+}
+int aitb_bsum(const float* x, int B, int P, int L, float* out, aitb_stream_t stream) {
+  return bsum_run(x, B, P, L, out, (cudaStream_t)stream);
+}
+int aitb_attn_bwd(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
+                  const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
+                  float* dv, int lddkv, float* dz, float* s, aitb_stream_t stream) {
+  return attn_bwd_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, G, mask_mode, n_keys, dq, lddq, dk, dv, lddkv, dz, s,
+                      (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace aitb {
 }  // namespace aitb
 
 using namespace aitb;

@@ -64,6 +64,7 @@ struct GemmKParams {
   int round_tf32;
   int dual;  // extra centre tap into a second accumulator (BLOCK_N = 128)
   const float* bias2;
+  float* ln_rstd;  // optional [rows_out space]: 1 / sigma of every LayerNorm row (saved for the backward pass)
   // split (bf16 hi/lo planes) mode: plane distances in bf16 elements
   int a_lo, w_lo, o_lo, r_lo;
   // split mode: compensation of the tensor core's round-toward-zero accumulation (see gemm_run)
@@ -139,7 +140,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     const int orow = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
     optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
     int rrow = 0;
-    if (p.flags & AITB_EPI_RES) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
+    if (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
     rptr[it] = res + (size_t)rrow * p.ldr + n0 + piece * (16 / (int)sizeof(T));
     vmask |= (ok ? 1u : 0u) << it;
   }
@@ -265,6 +266,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   auto add_residual = [&](const uint4 (&hi)[kIt], const uint4 (&lo)[kIt], float (&v)[32]) {
     float r[32];
     exchange(hi, r);
+    if (p.flags & AITB_EPI_RELU_MASK) {   // backward of ReLU: the "residual" stream is the saved activation
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = r[j] > 0.f ? v[j] : 0.f;
+      return;
+    }
     if constexpr (SPLIT) {
       float r2[32];
       exchange(lo, r2);
@@ -289,7 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     }
   };
 
-  const bool aux_res = (p.flags & AITB_EPI_RES) != 0;
+  const bool aux_res = (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) != 0;
   LaneVec lv_bias, lv_bias2, lv_gamma, lv_beta;  // bias2: dual (BLOCK_N 128) only; gamma / beta: CL only
   if (p.flags & AITB_EPI_BIAS) lv_bias = load_lane_vec(p.bias + n0 + c_begin);
   if constexpr (BLOCK_N == 128) {
@@ -460,6 +466,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       tmem_ld32(t_row, raw);
     }
     const float rstd = rsqrtf(fmaxf(ssq, 0.f) / n_cols + p.eps);
+    if (p.ln_rstd != nullptr && cta_rank == 0 && m_own < p.M) p.ln_rstd[orow_own] = rstd;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       tmem_ld_wait();
@@ -972,7 +979,9 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d->ldo % 8 == 0, "aitb_gemm: ldo must be a multiple of 8 elements");
   AITB_REQUIRE(((uintptr_t)d->out & 31) == 0 && ((uintptr_t)d->a.ptr & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
                "aitb_gemm: pointers must be 16/32-byte aligned");
-  if (d->flags & AITB_EPI_RES)
+  AITB_REQUIRE((d->flags & AITB_EPI_RELU_MASK) == 0 || (!split && (d->flags & (AITB_EPI_RES | AITB_EPI_LN)) == 0),
+               "aitb_gemm: RELU_MASK excludes RES / LN and the split configuration");
+  if (d->flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK))
     AITB_REQUIRE(d->res != nullptr && d->res_div > 0 && d->res_rep > 0 && d->ldr % 8 == 0 &&
                      ((uintptr_t)d->res & 31) == 0,
                  "aitb_gemm: bad residual spec");
@@ -1040,6 +1049,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.round_tf32 = d->round_tf32;
   kp.dual = d->dual ? 1 : 0;
   kp.bias2 = d->bias2;
+  kp.ln_rstd = d->ln_rstd;
   // tcgen05.mma adds each K=16 slice into the fp32 accumulator with round-toward-ZERO (measured, tools/acc_bias.py:
   // mean signed error -1.6e-8 .. -2.0e-8 of the result per accumulate step, growing linearly with the step
   // count; the expectation for RZ on a growing partial sum is 0.18 * 2^-23 = 2.1e-8).  In the tf32 / bf16

@@ -158,7 +158,7 @@ def _esize(dt):
 
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
-         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False):
+         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False, ln_rstd=None):
     """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
     map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels).
     split=True: AITB_F32S -- a / w / out / res are two-plane bf16 matrices (see split_planes); K, lda, ldr
@@ -208,6 +208,7 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.round_tf32 = 1 if round_tf32 else 0
     d.dual = 1 if dual else 0
     d.bias2 = 0 if bias2 is None else bias2.data_ptr()
+    d.ln_rstd = 0 if ln_rstd is None else ln_rstd.data_ptr()
     L.check(lib.aitb_gemm(C.byref(d), L.stream_ptr()))
     return out
 
@@ -255,6 +256,50 @@ def wgrad(dy, x, dw=None, N=None, K=None):
     L.check(lib.aitb_wgrad(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw), dw.stride(0),
                            L.stream_ptr()))
     return dw
+
+
+def ln_bwd(g, y, gamma, beta, rstd, grp=64, valid=64):
+    """LayerNorm backward from the saved output y [rows, 512] and 1/sigma [rows] -> (dx [rows/grp*valid, 512], dgamma, dbeta)."""
+    lib = L.load()
+    rows = g.shape[0]
+    dx = torch.empty((rows // grp * valid, 512), dtype=torch.float32, device=g.device)
+    dgamma = torch.zeros(512, dtype=torch.float32, device=g.device)
+    dbeta = torch.zeros(512, dtype=torch.float32, device=g.device)
+    L.check(lib.aitb_ln_bwd(L.ptr(g), L.ptr(y), L.ptr(gamma), L.ptr(beta), L.ptr(rstd), rows, grp, valid, L.ptr(dx),
+                            L.ptr(dgamma), L.ptr(dbeta), L.stream_ptr()))
+    return dx, dgamma, dbeta
+
+
+def colsum(x, cols=None):
+    lib = L.load()
+    cols = cols or x.shape[1]
+    out = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    L.check(lib.aitb_colsum(L.ptr(x), x.stride(0), x.shape[0], cols, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def bsum(x):
+    """[B, P, L] -> [B, L]"""
+    lib = L.load()
+    B, P, Ln = x.shape
+    out = torch.empty((B, Ln), dtype=torch.float32, device=x.device)
+    L.check(lib.aitb_bsum(L.ptr(x.contiguous()), B, P, Ln, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def attn_bwd(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, G, mask_mode, n_keys):
+    """-> (dq [G*64, 512] per pair, dk [G*64, 512], dv [G*64, 512], dz [G, 512], s [G, 64])"""
+    lib = L.load()
+    dev = dout.device
+    dq = torch.empty((G * 64, 512), dtype=torch.float32, device=dev)
+    dk = torch.empty((G * 64, 512), dtype=torch.float32, device=dev)
+    dv = torch.empty((G * 64, 512), dtype=torch.float32, device=dev)
+    dz = torch.empty((G, 512), dtype=torch.float32, device=dev)
+    s = torch.empty((G, 64), dtype=torch.float32, device=dev)
+    L.check(lib.aitb_attn_bwd(L.ptr(q), ldq, q_rep, L.ptr(k), L.ptr(v), ldkv, L.ptr(w_sk), L.ptr(b_sk), L.ptr(dout), G,
+                              mask_mode, n_keys, L.ptr(dq), 512, L.ptr(dk), L.ptr(dv), 512, L.ptr(dz), L.ptr(s),
+                              L.stream_ptr()))
+    return dq, dk, dv, dz, s
 
 
 def launch_count(reset=False):

@@ -202,6 +202,93 @@ class HeadEngine:
                                          L.ptr(ws), nbytes, L.stream_ptr()))
         return out
 
+    # ------------------------------------------------------------------ training (config 4)
+    # parameter order of the gradient tuple returned by ait_backward (names relative to the Transformer module)
+    @staticmethod
+    def ait_param_names():
+        names = ["enc_emb.0.weight", "enc_emb.0.bias", "dec_emb.0.weight", "dec_emb.0.bias",
+                 "dec_trans.0.weight", "dec_trans.0.bias",
+                 "encoder.layer_norm.weight", "encoder.layer_norm.bias",
+                 "decoder.layer_norm.weight", "decoder.layer_norm.bias"]
+        for m in ("encoder.layer_stack.0.slf_attn", "decoder.layer_stack.0.slf_attn", "decoder.layer_stack.0.enc_attn"):
+            names += [m + s for s in (".w_qs.weight", ".w_ks.weight", ".w_vs.weight", ".sh.sk.weight", ".sh.sk.bias",
+                                      ".fc.weight", ".layer_norm.weight", ".layer_norm.bias")]
+        for m in ("encoder.layer_stack.0.pos_ffn", "decoder.layer_stack.0.pos_ffn"):
+            names += [m + s for s in (".w_1.weight", ".w_1.bias", ".w_2.weight", ".w_2.bias", ".layer_norm.weight",
+                                      ".layer_norm.bias")]
+        return names
+
+    def ait_forward_train(self, x_props, x_query):
+        """Transformer.forward keeping the activations the backward needs -> (out, saved buffer)."""
+        if self.mode != "tf32":
+            raise RuntimeError("ait_b200: the training path runs in the fp32-storage / tf32 configuration")
+        lib = L.load()
+        ops._need_cuda(x_props, x_query)
+        x_props = x_props.contiguous().float()
+        x_query = x_query.contiguous().float()
+        bp, bs = x_props.shape[0], x_query.shape[0]
+        P = bp // bs
+        out = torch.empty((bp, 1024, 8, 8), dtype=torch.float32, device=x_props.device)
+        nbytes = lib.aitb_ait_saved_bytes(bs, P)
+        saved = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=x_props.device)
+        sv = saved[(-saved.data_ptr()) % 1024:]
+        with torch.cuda.device(x_props.device):
+            L.check(lib.aitb_ait_forward_train(C.byref(self.w), L.ptr(x_props), L.ptr(x_query), bs, P, L.ptr(out),
+                                               L.ptr(sv), nbytes, L.stream_ptr()))
+        return out, sv
+
+    def ait_backward(self, grad_out, saved, bs, P):
+        """-> (grad_props [bp,1024,7,7], grad_query [bs,1024,8,8], [gradient per name of ait_param_names()])."""
+        lib = L.load()
+        dev = grad_out.device
+        grad_out = grad_out.contiguous().float()
+        bp = bs * P
+        g_props = torch.empty((bp, 1024, 7, 7), dtype=torch.float32, device=dev)
+        g_query = torch.empty((bs, 1024, 8, 8), dtype=torch.float32, device=dev)
+        shapes = []                      # (struct path, numel) in C-struct order; one flat zeroed buffer behind all
+        lin = lambda n, k: [("w", n * k), ("bias", n)]        # noqa: E731
+        ln = [("gamma", 512), ("beta", 512)]
+        spec = [("enc_emb", lin(512, 1024)), ("dec_emb", lin(512, 1024)), ("dec_trans", lin(1024, 512)),
+                ("enc_ln", ln), ("dec_ln", ln)]
+        for m in ("enc_slf", "dec_slf", "dec_enc"):
+            spec.append((m, [("w_qkv", 1536 * 512), ("w_sk", 512 * 64), ("b_sk", 512), ("w_fc", 512 * 64),
+                             ("ln.gamma", 512), ("ln.beta", 512)]))
+        for m in ("enc_ffn", "dec_ffn"):
+            spec.append((m, [("w1.w", 2048 * 512), ("w1.bias", 2048), ("w2.w", 512 * 2048), ("w2.bias", 512),
+                             ("ln.gamma", 512), ("ln.beta", 512)]))
+        total = sum(n for _, fs in spec for _, n in fs)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        G = L.AITGrads()
+        views, off = {}, 0
+        for top, fs in spec:
+            for path, n in fs:
+                obj = getattr(G, top)
+                parts = path.split(".")
+                for a in parts[:-1]:
+                    obj = getattr(obj, a)
+                v = flat[off:off + n]
+                setattr(obj, parts[-1], v.data_ptr())
+                views[top + "." + path] = v
+                off += n
+        nbytes = lib.aitb_ait_backward_workspace_bytes(bs, P)
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(dev):
+            L.check(lib.aitb_ait_backward(C.byref(self.w), L.ptr(grad_out), bs, P, L.ptr(saved),
+                                          lib.aitb_ait_saved_bytes(bs, P), C.byref(G), L.ptr(g_props), L.ptr(g_query),
+                                          L.ptr(ws), nbytes, L.stream_ptr()))
+        v = views
+        out = [v["enc_emb.w"].view(512, 1024, 1, 1), v["enc_emb.bias"], v["dec_emb.w"].view(512, 1024, 1, 1),
+               v["dec_emb.bias"], v["dec_trans.w"].view(1024, 512, 1, 1), v["dec_trans.bias"],
+               v["enc_ln.gamma"], v["enc_ln.beta"], v["dec_ln.gamma"], v["dec_ln.beta"]]
+        for m in ("enc_slf", "dec_slf", "dec_enc"):
+            wqkv = v[m + ".w_qkv"].view(1536, 512)
+            out += [wqkv[:512], wqkv[512:1024], wqkv[1024:], v[m + ".w_sk"].view(512, 64), v[m + ".b_sk"],
+                    v[m + ".w_fc"].view(512, 64), v[m + ".ln.gamma"], v[m + ".ln.beta"]]
+        for m in ("enc_ffn", "dec_ffn"):
+            out += [v[m + ".w1.w"].view(2048, 512), v[m + ".w1.bias"], v[m + ".w2.w"].view(512, 2048),
+                    v[m + ".w2.bias"], v[m + ".ln.gamma"], v[m + ".ln.beta"]]
+        return g_props, g_query, out
+
     def workspace_bytes(self, B, P):
         return L.load().aitb_head_workspace_bytes(B, P, self.dt)
 

@@ -106,6 +106,27 @@ class Decoder(_Holder):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
 
 
+class _AITTrainFunction(torch.autograd.Function):
+    """Transformer.forward with a hand-written backward (libaitb200: tcgen05 dgrad / wgrad GEMMs, LayerNorm /
+    attention / selective-head-gate backward kernels).  The reference relies on torch autograd over
+    system/Models.py:231-280; gradients match it to tf32 accuracy (tests/test_gpu_train.py)."""
+
+    @staticmethod
+    def forward(ctx, x_props, x_query, module, *params):
+        engine = packing.HeadEngine(transformer=module, dtype="tf32")     # weights change every step: repack
+        out, saved = engine.ait_forward_train(x_props, x_query)
+        ctx.engine, ctx.saved = engine, saved
+        ctx.bs, ctx.num_props = x_query.shape[0], x_props.shape[0] // x_query.shape[0]
+        ctx.in_dtypes = (x_props.dtype, x_query.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g_props, g_query, g_params = ctx.engine.ait_backward(grad_out, ctx.saved, ctx.bs, ctx.num_props)
+        ctx.saved = None
+        return (g_props.to(ctx.in_dtypes[0]), g_query.to(ctx.in_dtypes[1]), None) + tuple(g_params)
+
+
 class Transformer(nn.Module):
     """Same constructor as the reference (Models.py:177-181).  Supported envelope of the fused engine:
     d_model = d_word_vec = 512, d_inner = 2048, n_layers = 1, n_head = 8, d_k = d_v = 64,
@@ -156,10 +177,11 @@ class Transformer(nn.Module):
 
     def forward(self, x_props, x_query):
         """x_props [bs*num_props, 1024, 7, 7], x_query [bs, 1024, 8, 8] -> [bs*num_props, 1024, 8, 8]
-        (Models.py:231-280).  Inference semantics (dropout = identity), like the reference in .eval()."""
+        (Models.py:231-280).  .eval(): inference engine (no autograd graph, dropout = identity, like the reference in
+        .eval()).  .train() with dropout = 0.0: differentiable training step with the library's own backward."""
         if self.training and any(m.p_dropout > 0 for m in self.modules() if hasattr(m, "p_dropout")):
             raise RuntimeError("ait_b200.Transformer: training-mode dropout is not implemented in the fused "
-                               "engine; call .eval() (or construct with dropout=0.0 for forward parity)")
+                               "engine; call .eval() (or construct with dropout=0.0, BASELINE config 4)")
         if x_props.dim() != 4 or x_query.dim() != 4:
             raise RuntimeError("expected x_props [bp,1024,7,7] and x_query [bs,1024,8,8]")
         bp, c_p, h_p, w_p = x_props.shape
@@ -169,6 +191,13 @@ class Transformer(nn.Module):
                                "[bs,1024,8,8]; got %s and %s" % (tuple(x_props.shape), tuple(x_query.shape)))
         if bs == 0 or bp == 0 or bp % bs != 0:
             raise RuntimeError("bp=%d must be a positive multiple of bs=%d (num_props = bp // bs)" % (bp, bs))
+        if self.training and torch.is_grad_enabled() and (
+                x_props.requires_grad or x_query.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training step (BASELINE config 4): forward keeping activations + hand-written backward, fp32 storage with
+            # tf32 tensor-core math
+            sd = dict(self.named_parameters())
+            params = [sd[n] for n in packing.HeadEngine.ait_param_names()]
+            return _AITTrainFunction.apply(x_props, x_query, self, *params)
         if self._engine is None:
             self._engine = packing.HeadEngine(transformer=self, dtype=self.compute_dtype)
         return self._engine.ait_forward(x_props, x_query)

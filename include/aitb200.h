@@ -119,8 +119,10 @@ enum {
   AITB_EPI_LN = 32,     /* LayerNorm over the full row (requires block_n == N == 512) */
   AITB_EPI_ACCUM = 64,  /* v += out (read-modify-write)                            */
   AITB_EPI_RES_RELU = 128, /* relu applied AFTER the residual add (bottleneck tail) */
-  AITB_EPI_DUAL = 256      /* two accumulators (see `dual`): v = f(acc0 + bias) + f(acc1 + bias2),
+  AITB_EPI_DUAL = 256,     /* two accumulators (see `dual`): v = f(acc0 + bias) + f(acc1 + bias2),
                               f = the RELU / SQUARE flags (SKBlock: relu(conv1x1)^2 + relu(conv3x3)^2) */
+  AITB_EPI_RELU_MASK = 512 /* backward of ReLU: v = residual[res_row, n] > 0 ? v : 0  (`res` = the saved activation;
+                              excludes RES / LN / split) */
 };
 
 typedef struct {
@@ -156,6 +158,8 @@ typedef struct {
   /* AITB_F32S only: distance (bf16 elements along dims[0]) from the hi plane to the lo plane of A, i.e. the
    * logical row width of the buffer A lives in.  out / res planes are ldo / ldr apart; W's are taps*k_per_tap apart. */
   int a_lo_off;
+  /* optional (LN epilogue): 1 / sigma of every normalised row, written at the row's OUTPUT index (training) */
+  float* ln_rstd;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
@@ -286,6 +290,42 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
  * leading dimensions ldy / ldx; dw must be initialised by the caller, e.g. zeroed).  N % 128 == 0, K % 64 == 0. */
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
                aitb_stream_t stream);
+
+/* The other backward pieces (exported for unit tests; see ait_b200/csrc/bwd.cu) */
+int aitb_ln_bwd(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd,
+                int rows, int grp, int valid, float* dx, float* dgamma, float* dbeta, aitb_stream_t stream);
+int aitb_colsum(const float* x, int ld, int rows, int cols, float* out, aitb_stream_t stream);
+int aitb_bsum(const float* x, int B, int P, int L, float* out, aitb_stream_t stream);
+/* selective-head attention backward (one launch per attention block): q / k / v as in aitb_attn_core (fp32),
+ * dout [G, 64, 64] -> dq [G*64, lddq] (PER PAIR even when q_rep > 1: sum over the unit's pairs with aitb_bsum),
+ * dk / dv [G*64, lddkv] (head h in columns h*64..), dz [G, 512] = d(W_sk s + b_sk), s [G, 64] */
+int aitb_attn_bwd(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv,
+                  const float* w_sk, const float* b_sk, const float* dout, int G, int mask_mode, int n_keys,
+                  float* dq, int lddq, float* dk, float* dv, int lddkv, float* dz, float* s,
+                  aitb_stream_t stream);
+
+/* AIT training step (config 4): Transformer.forward with the activations the backward needs kept in `saved`
+ * (caller-owned, aitb_ait_saved_bytes), then the backward producing the gradients of both inputs and of all
+ * parameters the forward uses.  dtype must be AITB_F32; dropout is not modelled (p = 0, as config 4 states). */
+typedef struct { float* w; float* bias; } aitb_linear_g;
+typedef struct { float* gamma; float* beta; } aitb_lnorm_g;
+typedef struct { float* w_qkv; float* w_sk; float* b_sk; float* w_fc; aitb_lnorm_g ln; } aitb_mha_g;
+typedef struct { aitb_linear_g w1, w2; aitb_lnorm_g ln; } aitb_ffn_g;
+typedef struct {
+  aitb_linear_g enc_emb, dec_emb, dec_trans; /* [512,1024]+[512], [512,1024]+[512], [1024,512]+[1024] */
+  aitb_lnorm_g enc_ln, dec_ln;
+  aitb_mha_g enc_slf, dec_slf, dec_enc;      /* w_qkv [1536,512] = rows(w_qs; w_ks; w_vs) */
+  aitb_ffn_g enc_ffn, dec_ffn;
+} aitb_ait_grads; /* every buffer fp32, zero-initialised by the caller; gradients are ACCUMULATED into them */
+
+size_t aitb_ait_saved_bytes(int B, int P);
+size_t aitb_ait_backward_workspace_bytes(int B, int P);
+int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, const float* x_query, int B, int P,
+                           float* out_nchw, void* saved, size_t saved_bytes, aitb_stream_t stream);
+/* grad_out [bp,1024,8,8] -> grad_props [bp,1024,7,7], grad_query [B,1024,8,8] (both overwritten), grads accumulated */
+int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
+                      size_t saved_bytes, const aitb_ait_grads* grads, float* grad_props, float* grad_query,
+                      void* workspace, size_t workspace_bytes, aitb_stream_t stream);
 
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);

@@ -139,3 +139,30 @@ def test_state_dict_loads_into_reference_strict():
     ref_import.ref_transformer().load_state_dict(head.transformer.state_dict(), strict=True)
     ref_import.ref_sknet().load_state_dict(head.sk.state_dict(), strict=True)
     ref_import.ref_layer4().load_state_dict(head.RCNN_top.state_dict(), strict=True)
+
+
+def test_oracle_autograd_matches_reference_golden_gradients():
+    """config 4: the oracle restatement differentiated by torch autograd reproduces the gradients of the
+    unmodified reference Transformer (tests/golden/ait_grad.pt, made by tests/golden/make_golden_grad.py)."""
+    import torch
+    from conftest import load_golden
+    from ait_b200 import synth
+    from oracle import head_oracle
+    gold = load_golden("ait_grad.pt")
+    g = torch.Generator().manual_seed(13)
+    xp = torch.rand(2, 1024, 7, 7, generator=g).requires_grad_()
+    xq = torch.rand(1, 1024, 8, 8, generator=g).requires_grad_()
+    gout = torch.randn(2, 1024, 8, 8, generator=g)
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+    sd = {k: v.detach().clone().requires_grad_("pos_table" not in k) for k, v in head.transformer.state_dict().items()}
+    out = head_oracle.ait_forward(sd, xp, xq)
+    out.backward(gout)
+    assert torch.allclose(out.detach()[:, ::8], gold["out_s"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xp.grad[:, ::4], gold["grad_props_s"], rtol=1e-3, atol=1e-5)
+    assert torch.allclose(xq.grad[:, ::4], gold["grad_query_s"], rtol=1e-3, atol=1e-5)
+    assert len(gold["params"]) == 46
+    for name, ref in gold["params"].items():
+        gr = sd[name].grad.reshape(-1)
+        sample = gr[::ref["stride"]][:ref["sample"].numel()]
+        err = float((sample - ref["sample"]).norm() / ref["sample"].norm())
+        assert err < 1e-3, (name, err)
