@@ -129,6 +129,10 @@ SIGNATURES = {
                                C.POINTER(HeadTaps), _vp, _sz, _vp]),
     "aitb_ait_workspace_bytes": (_sz, [_i, _i, _i]),
     "aitb_ait_forward": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "aitb_rpn_decode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "aitb_box_decode": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _f, _i,
+                             _vp, _vp, _vp, _vp]),
+    "aitb_det_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "aitb_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "aitb_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "aitb_colsum": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -42,6 +42,15 @@ int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float
                  const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
                  float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream);
 
+int rpn_decode_run(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,
+                   int B, int A, int H, int W, float feat_stride, float* proposals, float* fg_scores, cudaStream_t st);
+int box_decode_run(const float* boxes, int boxes_stride, int boxes_off, const float* deltas, const float* cls,
+                   const float* im_info, int B, int N, const float* stds, const float* means, float thresh,
+                   int divide_by_scale, float* pred, float* key, int32_t* n_valid, cudaStream_t st);
+int det_assemble_run(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
+                     const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
+                     int32_t* n_det, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // error string + launch counter (thread-local)
 // ---------------------------------------------------------------------------------------------
@@ -894,6 +903,25 @@ int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat
                     float* feat_out, float* bbox_out, float* cls_prob_out, aitb_stream_t stream) {
   return pool_heads_run(top, dtype, G, P, qfeat, w_bbox, b_bbox, w1, b1, w2, b2, feat_out, bbox_out, cls_prob_out,
                         (cudaStream_t)stream);
+}
+
+int aitb_rpn_decode(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,
+                    int B, int A, int H, int W, float feat_stride, float* proposals, float* fg_scores,
+                    aitb_stream_t stream) {
+  return rpn_decode_run(scores_nchw, deltas_nchw, base_anchors, im_info, B, A, H, W, feat_stride, proposals, fg_scores,
+                        (cudaStream_t)stream);
+}
+int aitb_box_decode(const float* boxes, int boxes_stride, int boxes_off, const float* deltas, const float* cls,
+                    const float* im_info, int B, int N, const float* h_stds, const float* h_means, float thresh,
+                    int divide_by_scale, float* pred, float* key, int32_t* n_valid, aitb_stream_t stream) {
+  return box_decode_run(boxes, boxes_stride, boxes_off, deltas, cls, im_info, B, N, h_stds, h_means, thresh,
+                        divide_by_scale, pred, key, n_valid, (cudaStream_t)stream);
+}
+int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
+                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
+                      int32_t* n_det, aitb_stream_t stream) {
+  return det_assemble_run(pred, cls, order, keep_pos, n_keep, n_valid, B, N, max_per_image, dets, n_det,
+                          (cudaStream_t)stream);
 }
 
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,

@@ -5,13 +5,25 @@ bbox_transform.py:77-133, generate_anchors.py:45-105).
 scores, NMS (IoU > thr), first post_nms_topN survivors, zero-padded [B, post, 5] roi tensor --
 three library calls for the whole batch, no python per-image loop, no host round trip.
 
-Anchor enumeration / box decoding (the "next" row f1) are plain torch host-side helpers here; they
-produce the synthetic RPN outputs for the benchmark and are not on the timed path.
+`ProposalLayer` is the drop-in for the reference's `_ProposalLayer` (same constructor and input tuple): the
+"next" row f1 -- anchor enumeration, bbox_transform_inv, clip_boxes and the NCHW re-ordering run in one
+kernel (`aitb_rpn_decode`) in front of the top-n / NMS, so the whole layer is four library calls.
+
+The torch helpers below (`shifted_anchors`, `decode_boxes`, `clip_boxes`) only produce the synthetic RPN
+outputs of the benchmark; they are not on any timed path.
 """
+import ctypes as C
+
 import numpy as np
 import torch
+import torch.nn as nn
 
+from . import _lib as L
 from . import ops
+
+# cfg[cfg_key].RPN_{PRE,POST}_NMS_TOP_N / RPN_NMS_THRESH (lib/model/utils/config.py:146-150,196-201)
+RPN_CFG = {"TEST": dict(pre_nms_topN=6000, post_nms_topN=300, nms_thresh=0.7),
+           "TRAIN": dict(pre_nms_topN=12000, post_nms_topN=2000, nms_thresh=0.7)}
 
 
 def generate_anchors(base_size=16, ratios=(0.5, 1, 2), scales=(8, 16, 32)):
@@ -73,3 +85,76 @@ def propose_rois(proposals, scores, pre_nms_topN=6000, post_nms_topN=300, nms_th
     order = ops.topk_desc(scores, n)
     _, n_keep, rois = ops.nms_batched(proposals, order, nms_thresh, post_nms_topN, mode=0, want_rois=True)
     return rois, n_keep
+
+
+def rpn_decode(rpn_cls_prob, rpn_bbox_pred, base_anchors, im_info, feat_stride):
+    """rpn_cls_prob [B, 2A, H, W], rpn_bbox_pred [B, 4A, H, W], base_anchors [A, 4], im_info [B, 3]
+    -> proposals [B, H*W*A, 4] (decoded, clipped), fg scores [B, H*W*A]  (proposal_layer.py:66-118)."""
+    lib = L.load()
+    ops._need_cuda(rpn_cls_prob, rpn_bbox_pred, base_anchors, im_info)
+    scores = rpn_cls_prob.contiguous().float()
+    deltas = rpn_bbox_pred.contiguous().float()
+    B, c2, H, W = scores.shape
+    A = c2 // 2
+    if deltas.shape != (B, 4 * A, H, W) or base_anchors.shape != (A, 4) or im_info.shape != (B, 3):
+        raise RuntimeError("rpn_decode: expected scores [B,2A,H,W], deltas [B,4A,H,W], anchors [A,4], im_info [B,3]")
+    props = torch.empty((B, H * W * A, 4), dtype=torch.float32, device=scores.device)
+    fg = torch.empty((B, H * W * A), dtype=torch.float32, device=scores.device)
+    L.check(lib.aitb_rpn_decode(L.ptr(scores), L.ptr(deltas), L.ptr(base_anchors.contiguous().float()),
+                                L.ptr(im_info.contiguous().float()), B, A, H, W, float(feat_stride), L.ptr(props),
+                                L.ptr(fg), L.stream_ptr()))
+    return props, fg
+
+
+class ProposalLayer(nn.Module):
+    """Drop-in for `_ProposalLayer` (lib/model/rpn/proposal_layer.py:28-166): forward(input) with
+    input = (rpn_cls_prob [B,2A,H,W], rpn_bbox_pred [B,4A,H,W], im_info [B,3], cfg_key) -> rois [B, post_nms_topN, 5]."""
+
+    def __init__(self, feat_stride, scales, ratios, cfg=None):
+        super().__init__()
+        self._feat_stride = feat_stride
+        self.register_buffer("_anchors", torch.from_numpy(
+            generate_anchors(scales=np.array(scales), ratios=np.array(ratios))).float(), persistent=False)
+        self._num_anchors = self._anchors.size(0)
+        self.cfg = cfg or RPN_CFG
+
+    def forward(self, input):
+        scores, bbox_deltas, im_info, cfg_key = input[0], input[1], input[2], input[3]
+        c = self.cfg[cfg_key]
+        proposals, fg = rpn_decode(scores, bbox_deltas, self._anchors.to(scores.device), im_info, self._feat_stride)
+        rois, _ = propose_rois(proposals, fg, c["pre_nms_topN"], c["post_nms_topN"], c["nms_thresh"])
+        return rois
+
+
+# cfg.TRAIN.BBOX_NORMALIZE_{STDS,MEANS}, cfg.TEST.NMS (config.py:123-124,180)
+BBOX_NORMALIZE_STDS = (0.1, 0.1, 0.2, 0.2)
+BBOX_NORMALIZE_MEANS = (0.0, 0.0, 0.0, 0.0)
+
+
+def detections(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
+               stds=BBOX_NORMALIZE_STDS, means=BBOX_NORMALIZE_MEANS, rescale=True):
+    """Detection post-processing of test_net_voc.py:380-446 for a batch of units, on the device (row f2):
+    de-normalise + decode + clip (+ rescale) the boxes, drop scores <= thresh, sort by score, NMS, keep the
+    top max_per_image.  rois [B,P,5], cls_prob [B,P,1], bbox_pred [B,P,4], im_info [B,3]
+    -> dets [B, P, 5] = (x1, y1, x2, y2, score) in descending score order (zero-padded), n_det [B] int32."""
+    lib = L.load()
+    ops._need_cuda(rois, cls_prob, bbox_pred, im_info)
+    B, P = rois.shape[0], rois.shape[1]
+    dev = rois.device
+    rois = rois.contiguous().float()
+    cls = cls_prob.reshape(B, P).contiguous().float()
+    deltas = bbox_pred.reshape(B, P, 4).contiguous().float()
+    pred = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    key = torch.empty((B, P), dtype=torch.float32, device=dev)
+    n_valid = torch.empty((B,), dtype=torch.int32, device=dev)
+    f4 = C.c_float * 4
+    L.check(lib.aitb_box_decode(L.ptr(rois), 5, 1, L.ptr(deltas), L.ptr(cls), L.ptr(im_info.contiguous().float()), B, P,
+                                f4(*stds), f4(*means), float(thresh), 1 if rescale else 0, L.ptr(pred), L.ptr(key),
+                                L.ptr(n_valid), L.stream_ptr()))
+    order = ops.topk_desc(key, P)
+    keep, n_keep, _ = ops.nms_batched(pred, order, nms_thresh, P, mode=0)
+    dets = torch.empty((B, P, 5), dtype=torch.float32, device=dev)
+    n_det = torch.empty((B,), dtype=torch.int32, device=dev)
+    L.check(lib.aitb_det_assemble(L.ptr(pred), L.ptr(cls), L.ptr(order), L.ptr(keep), L.ptr(n_keep), L.ptr(n_valid), B, P,
+                                  int(max_per_image), L.ptr(dets), L.ptr(n_det), L.stream_ptr()))
+    return dets, n_det

@@ -282,6 +282,33 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
                      aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f1  front of the proposal layer (rpn/proposal_layer.py:66-118, rpn/bbox_transform.py:77-133):
+ * anchors (base anchors [A,4] + cell shifts * feat_stride), bbox_transform_inv, clip_boxes and the
+ * `permute(0,2,3,1)` re-ordering of the RPN outputs, in one kernel.
+ *   scores_nchw [B, 2A, H, W] (foreground = channels A..2A), deltas_nchw [B, 4A, H, W], im_info [B, 3] (h, w, scale)
+ *   -> proposals [B, H*W*A, 4], fg_scores [B, H*W*A]   (then aitb_topk_desc + aitb_nms_batched)
+ * ---------------------------------------------------------------------------------------- */
+int aitb_rpn_decode(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors,
+                    const float* im_info, int B, int A, int H, int W, float feat_stride, float* proposals,
+                    float* fg_scores, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f2  detection post-processing (test_net_voc.py:380-446)
+ *   aitb_box_decode: pred = clip(bbox_transform_inv(box, delta * h_stds + h_means)) [/ im_scale];
+ *     boxes rows have `boxes_stride` floats with the box at column `boxes_off` (rois [B,N,5]: stride 5, offset 1);
+ *     key [B,N] = score > thresh ? score : -inf (sort key), n_valid [B] = number of scores above thresh
+ *   aitb_det_assemble: after aitb_topk_desc(key) -> order and aitb_nms_batched(pred, order, nms_thresh, mode 0)
+ *     -> keep_pos / n_keep: dets [B, N, 5] = (x1,y1,x2,y2,score) in descending score order, zero-padded,
+ *     limited to max_per_image (> 0) with the reference's `>=` rule at the cut; n_det [B]
+ * ---------------------------------------------------------------------------------------- */
+int aitb_box_decode(const float* boxes, int boxes_stride, int boxes_off, const float* deltas, const float* cls,
+                    const float* im_info, int B, int N, const float* h_stds, const float* h_means, float thresh,
+                    int divide_by_scale, float* pred, float* key, int32_t* n_valid, aitb_stream_t stream);
+int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
+                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
+                      int32_t* n_det, aitb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training (BASELINE config 4): backward building blocks.  fp32 storage, tf32 tensor-core math.
  * The reference obtains these from torch autograd over the modules of a5-a9.
  * ---------------------------------------------------------------------------------------- */

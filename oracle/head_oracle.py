@@ -187,3 +187,84 @@ def propose_rois(proposals, scores, pre_nms_topN=6000, post_nms_topN=300, thr=0.
         out[i, : len(keep), 1:] = torch.from_numpy(boxes[keep])
         counts.append(len(keep))
     return out, counts
+
+
+# ------------------------------------------------------------------------------------------------
+# f1: the whole proposal layer (lib/model/rpn/proposal_layer.py:51-166, bbox_transform.py:77-133)
+# ------------------------------------------------------------------------------------------------
+def bbox_transform_inv(boxes, deltas):
+    """bbox_transform.py:77-106 (class-agnostic: deltas [B, N, 4])."""
+    widths = boxes[:, :, 2] - boxes[:, :, 0] + 1.0
+    heights = boxes[:, :, 3] - boxes[:, :, 1] + 1.0
+    ctr_x = boxes[:, :, 0] + 0.5 * widths
+    ctr_y = boxes[:, :, 1] + 0.5 * heights
+    pcx = deltas[:, :, 0] * widths + ctr_x
+    pcy = deltas[:, :, 1] * heights + ctr_y
+    pw = torch.exp(deltas[:, :, 2]) * widths
+    ph = torch.exp(deltas[:, :, 3]) * heights
+    return torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=2)
+
+
+def clip_boxes(boxes, im_info):
+    """bbox_transform.py:125-133."""
+    out = boxes.clone()
+    for i in range(out.shape[0]):
+        out[i, :, 0].clamp_(0, float(im_info[i, 1]) - 1)
+        out[i, :, 1].clamp_(0, float(im_info[i, 0]) - 1)
+        out[i, :, 2].clamp_(0, float(im_info[i, 1]) - 1)
+        out[i, :, 3].clamp_(0, float(im_info[i, 0]) - 1)
+    return out
+
+
+def proposal_layer(rpn_cls_prob, rpn_bbox_pred, im_info, base_anchors, feat_stride=16, pre_nms_topN=6000,
+                   post_nms_topN=300, nms_thresh=0.7, return_decoded=False):
+    """_ProposalLayer.forward (proposal_layer.py:51-166).  NMS with the CUDA `>` rule (the path replaced)."""
+    B, c2, H, W = rpn_cls_prob.shape
+    A = c2 // 2
+    scores = rpn_cls_prob[:, A:, :, :]
+    sx = torch.arange(W, dtype=torch.float32) * feat_stride
+    sy = torch.arange(H, dtype=torch.float32) * feat_stride
+    yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+    shifts = torch.stack([xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)], dim=1)
+    K = shifts.shape[0]
+    anchors = (base_anchors.view(1, A, 4) + shifts.view(K, 1, 4)).view(1, K * A, 4).expand(B, K * A, 4)
+    deltas = rpn_bbox_pred.permute(0, 2, 3, 1).contiguous().view(B, -1, 4)
+    scores = scores.permute(0, 2, 3, 1).contiguous().view(B, -1)
+    proposals = clip_boxes(bbox_transform_inv(anchors, deltas), im_info)
+    if return_decoded:
+        return proposals, scores
+    rois, _ = propose_rois(proposals, scores, pre_nms_topN, post_nms_topN, nms_thresh)
+    return rois
+
+
+# ------------------------------------------------------------------------------------------------
+# f2: detection post-processing (test_net_voc.py:380-446), one unit at a time like the reference
+# ------------------------------------------------------------------------------------------------
+def detections(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
+               stds=(0.1, 0.1, 0.2, 0.2), means=(0.0, 0.0, 0.0, 0.0), rescale=True):
+    """-> list (per unit) of [n_det, 5] tensors (x1, y1, x2, y2, score), descending score."""
+    import numpy as np
+    out = []
+    for b in range(rois.shape[0]):
+        scores = cls_prob[b].reshape(-1)
+        boxes = rois[b:b + 1, :, 1:5]
+        deltas = bbox_pred[b].view(-1, 4) * torch.tensor(stds) + torch.tensor(means)          # :393-396
+        pred = clip_boxes(bbox_transform_inv(boxes, deltas.view(1, -1, 4)), im_info[b:b + 1])  # :404-405
+        if rescale:
+            pred = pred / float(im_info[b, 2])                                                 # :410
+        pred = pred[0]
+        inds = torch.nonzero(scores > thresh).view(-1)                                         # :422
+        if inds.numel() == 0:
+            out.append(torch.zeros(0, 5))
+            continue
+        cls_scores, cls_boxes = scores[inds], pred[inds]
+        cls_dets = torch.cat((cls_boxes, cls_scores.unsqueeze(1)), 1)
+        _, order = torch.sort(cls_scores, stable=True, dim=0, descending=True)
+        cls_dets = cls_dets[order]
+        keep = c_ops.nms_sorted(cls_boxes[order].contiguous().numpy(), nms_thresh, False, 0)   # `>` rule
+        dets = cls_dets[torch.from_numpy(np.asarray(keep).astype(np.int64))]
+        if max_per_image > 0 and dets.shape[0] > max_per_image:                               # :437-446
+            image_thresh = np.sort(dets[:, -1].numpy())[-max_per_image]
+            dets = dets[dets[:, -1] >= float(image_thresh)]
+        out.append(dets)
+    return out

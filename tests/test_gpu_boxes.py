@@ -1,0 +1,63 @@
+"""GPU parity of the rows either side of the head: the whole proposal layer (f1) and the
+detection post-processing (f2), against the CPU oracle and the reference golden."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import head_oracle
+from test_oracle_pins import _proposal_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_rpn_decode_matches_oracle():
+    """anchors + bbox_transform_inv + clip + NCHW re-ordering in one kernel; exp is the only op that is not
+    bit-identical to the host (expf vs libm): a 1-ulp difference of exp(dw) * width is up to 6e-5 px on a 1000 px box, gate 5e-4 px."""
+    from ait_b200.proposal import generate_anchors, rpn_decode
+    cls_prob, bbox_pred, im_info = _proposal_inputs(5, B=3, A=9, H=38, W=63)
+    im_info = torch.tensor([[600.0, 1000.0, 1.0], [580.0, 990.0, 1.2], [600.0, 800.0, 0.9]])
+    base = torch.from_numpy(generate_anchors()).float()
+    ref_p, ref_s = head_oracle.proposal_layer(cls_prob, bbox_pred, im_info, base, 16, return_decoded=True)
+    props, fg = rpn_decode(cls_prob.to(DEV), bbox_pred.to(DEV), base.to(DEV), im_info.to(DEV), 16)
+    assert torch.equal(fg.cpu(), ref_s)
+    assert torch.allclose(props.cpu(), ref_p, rtol=2e-6, atol=5e-4)
+    assert float((props.cpu() - ref_p).abs().max()) < 1e-3
+
+
+def test_proposal_layer_matches_reference_golden():
+    """the drop-in ProposalLayer on the reference's golden rois (unmodified _ProposalLayer, CPU)."""
+    from ait_b200.proposal import ProposalLayer
+    gold = load_golden("proposal_layer.pt")
+    cls_prob, bbox_pred, im_info = _proposal_inputs(gold["seed"])
+    layer = ProposalLayer(16, [8, 16, 32], [0.5, 1, 2],
+                          cfg={"TEST": dict(pre_nms_topN=gold["pre"], post_nms_topN=gold["post"], nms_thresh=gold["thr"])})
+    assert torch.equal(layer._anchors, gold["anchors"])
+    rois = layer((cls_prob.to(DEV), bbox_pred.to(DEV), im_info.to(DEV), "TEST")).cpu()
+    assert rois.shape == gold["rois"].shape
+    # box coordinates can differ in the last ulp where exp() does (expf vs libm); the kept set and its order must not
+    assert torch.equal(rois[..., 0], gold["rois"][..., 0])
+    assert torch.allclose(rois, gold["rois"], rtol=2e-6, atol=5e-4)
+
+
+@pytest.mark.parametrize("thresh,max_per_image", [(0.0, 100), (0.5, 100), (0.0, 7), (0.999, 100)])
+def test_detection_postprocessing_matches_oracle(thresh, max_per_image):
+    from ait_b200 import synth
+    from ait_b200.proposal import detections
+    g = torch.Generator().manual_seed(31)
+    B, P = 3, 300
+    rois = torch.stack([synth.random_rois(u, P, batch_index=u) for u in range(B)])
+    cls_prob = torch.rand(B, P, 1, generator=g)
+    cls_prob[1, 10:14] = cls_prob[1, 10]                # ties, also around the max_per_image cut
+    bbox_pred = 0.5 * torch.randn(B, P, 4, generator=g)
+    im_info = torch.tensor([[600.0, 1000.0, 1.6], [600.0, 1000.0, 1.0], [600.0, 900.0, 0.75]])
+    ref = head_oracle.detections(rois, cls_prob, bbox_pred, im_info, thresh, 0.3, max_per_image)
+    dets, n_det = detections(rois.to(DEV), cls_prob.to(DEV), bbox_pred.to(DEV), im_info.to(DEV), thresh, 0.3,
+                             max_per_image)
+    dets, n_det = dets.cpu(), n_det.cpu()
+    for b in range(B):
+        n = int(n_det[b])
+        assert n == ref[b].shape[0], (b, n, ref[b].shape)
+        assert torch.equal(dets[b, :n, 4], ref[b][:, 4])                      # same detections, same order
+        assert torch.allclose(dets[b, :n, :4], ref[b][:, :4], rtol=2e-6, atol=5e-4)
+        assert torch.all(dets[b, n:] == 0)

@@ -166,3 +166,25 @@ def test_oracle_autograd_matches_reference_golden_gradients():
         sample = gr[::ref["stride"]][:ref["sample"].numel()]
         err = float((sample - ref["sample"]).norm() / ref["sample"].norm())
         assert err < 1e-3, (name, err)
+
+
+def _proposal_inputs(seed=21, B=2, A=9, H=19, W=31):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cls_prob = torch.rand(B, 2 * A, H, W, generator=g)
+    bbox_pred = 0.3 * torch.randn(B, 4 * A, H, W, generator=g)
+    im_info = torch.tensor([[300.0, 500.0, 1.5], [280.0, 480.0, 0.8]])[:B]
+    return cls_prob, bbox_pred, im_info
+
+
+def test_oracle_proposal_layer_matches_reference_golden():
+    """row f1: the restated proposal layer (anchors, bbox_transform_inv, clip, sort, top-n, NMS, pad) reproduces the
+    rois of the unmodified `_ProposalLayer` bit for bit (tests/golden/make_golden_proposal.py)."""
+    import torch
+    from conftest import load_golden
+    from oracle import head_oracle
+    gold = load_golden("proposal_layer.pt")
+    cls_prob, bbox_pred, im_info = _proposal_inputs(gold["seed"])
+    rois = head_oracle.proposal_layer(cls_prob, bbox_pred, im_info, gold["anchors"], 16, gold["pre"], gold["post"],
+                                      gold["thr"])
+    assert torch.equal(rois, gold["rois"])
