@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/aitb200.h"
 #include "common.cuh"
@@ -308,11 +309,15 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
 // planes (Q, K, V x hi, lo; 128-byte rows, 16-byte chunks XOR-swizzled by row for conflict-free ldmatrix)
 // filled with cp.async one head ahead; one named barrier per head and group.
 static constexpr int kPlaneBytes = kT * 128;                // 64 rows x 64 bf16
-static constexpr int kBufBytes = 6 * kPlaneBytes;           // Qh Ql Kh Kl Vh Vl
 static constexpr int kSplitThreads = 256;
 static constexpr int kPartStride = kD + 2;                  // padded row of the head-group exchange tile (floats)
-// 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
-static constexpr int kSplitSmem = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
+// per head buffer: SPLIT Qh Ql Kh Kl Vh Vl (6 planes), plain bf16 Q K V (3 planes)
+template <bool SPLIT> struct OnePass {
+  static constexpr int kPlanes = SPLIT ? 6 : 3;
+  static constexpr int kBufBytes = kPlanes * kPlaneBytes;
+  // 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
+  static constexpr int kSmem = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
+};
 
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {  // byte offset of 16-byte chunk `chunk` of row `row`
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
@@ -335,11 +340,15 @@ __device__ __forceinline__ void group_bar(int id) {  // named barrier of one 4-w
 // q / k / v point at the hi planes; the lo planes start q_lo / kv_lo elements further; ldq / ldkv are the
 // physical (bf16) row pitches.  out: [G*64, hi 64 | lo 64].  Persistent: CTA c handles pairs c, c + grid, ...;
 // the first head of the next pair is fetched while the current pair finishes (gate, head sum, store).
+// SPLIT = false is the plain bf16 configuration: one plane per operand, one MMA per product, out [G*64, 64].
+template <bool SPLIT>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, int q_rep,
                        const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv, int kv_lo,
                        const float* __restrict__ w_sk, const float* __restrict__ b_sk, int G, int mask_mode, int n_keys,
                        __nv_bfloat16* __restrict__ out) {
+  constexpr int kBufBytes = OnePass<SPLIT>::kBufBytes;
+  constexpr int kP = SPLIT ? 2 : 1;   // planes per operand
   extern __shared__ __align__(128) uint8_t smem_attn[];
   float* part = reinterpret_cast<float*>(smem_attn + 4 * kBufBytes);  // [kT][kPartStride] head-group exchange
   float* colsum = part + kT * kPartStride;                            // [8 warps][kD]
@@ -363,11 +372,13 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       const uint32_t d = base + sw_off(r, ch);
       const size_t qo = (size_t)r * ldq + h * kD + ch * 8, ko = (size_t)r * ldkv + h * kD + ch * 8;
       cp_async16(d, qg + qo);
-      cp_async16(d + kPlaneBytes, qg + q_lo + qo);
-      cp_async16(d + 2 * kPlaneBytes, kg + ko);
-      cp_async16(d + 3 * kPlaneBytes, kg + kv_lo + ko);
-      cp_async16(d + 4 * kPlaneBytes, vg + ko);
-      cp_async16(d + 5 * kPlaneBytes, vg + kv_lo + ko);
+      cp_async16(d + kP * kPlaneBytes, kg + ko);
+      cp_async16(d + 2 * kP * kPlaneBytes, vg + ko);
+      if constexpr (SPLIT) {
+        cp_async16(d + kPlaneBytes, qg + q_lo + qo);
+        cp_async16(d + 3 * kPlaneBytes, kg + kv_lo + ko);
+        cp_async16(d + 5 * kPlaneBytes, vg + kv_lo + ko);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -388,8 +399,8 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
     if (hl + 1 < 4) issue_head(grp, hg * 4 + hl + 1, (hl + 1) & 1);
     else if (grp + (int)gridDim.x < G) issue_head(grp + gridDim.x, hg * 4, 0);  // next pair's first head
     const uint32_t base = buf0 + (hl & 1) * kBufBytes;
-    const uint32_t Qh = base, Ql = base + kPlaneBytes, Kh = base + 2 * kPlaneBytes, Kl = base + 3 * kPlaneBytes;
-    const uint32_t Vh = base + 4 * kPlaneBytes, Vl = base + 5 * kPlaneBytes;
+    const uint32_t Qh = base, Ql = base + kPlaneBytes, Kh = base + kP * kPlaneBytes, Kl = Kh + kPlaneBytes;
+    const uint32_t Vh = base + 2 * kP * kPlaneBytes, Vl = Vh + kPlaneBytes;
     // ---- S = Q K^T (three bf16 passes), mask, softmax in registers
     float p[8][4];
 #pragma unroll
@@ -399,18 +410,20 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       uint32_t ah[4], al[4];
       const uint32_t ao = sw_off(row0 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4));
       ldsm_x4_a(ah, Qh + ao);
-      ldsm_x4_a(al, Ql + ao);
+      if constexpr (SPLIT) ldsm_x4_a(al, Ql + ao);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         uint32_t bh[4], bl[4];
         const uint32_t bo = sw_off(8 * j + (lane & 7) + 8 * (lane >> 4), 2 * ks + ((lane >> 3) & 1));
         ldsm_x4_a(bh, Kh + bo);
-        ldsm_x4_a(bl, Kl + bo);
-        mma_bf16(p[j], al, bh[0], bh[1]);
-        mma_bf16(p[j], ah, bl[0], bl[1]);
+        if constexpr (SPLIT) {
+          ldsm_x4_a(bl, Kl + bo);
+          mma_bf16(p[j], al, bh[0], bh[1]);
+          mma_bf16(p[j], ah, bl[0], bl[1]);
+          mma_bf16(p[j + 1], al, bh[2], bh[3]);
+          mma_bf16(p[j + 1], ah, bl[2], bl[3]);
+        }
         mma_bf16(p[j], ah, bh[0], bh[1]);
-        mma_bf16(p[j + 1], al, bh[2], bh[3]);
-        mma_bf16(p[j + 1], ah, bl[2], bl[3]);
         mma_bf16(p[j + 1], ah, bh[2], bh[3]);
       }
     }
@@ -464,12 +477,14 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
         uint32_t bh[4], bl[4];
         const uint32_t vo = sw_off(16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), j + (lane >> 4));
         ldsm_x4_t(bh, Vh + vo);
-        ldsm_x4_t(bl, Vl + vo);
-        mma_bf16(o[hl][j], al, bh[0], bh[1]);
-        mma_bf16(o[hl][j], ah, bl[0], bl[1]);
+        if constexpr (SPLIT) {
+          ldsm_x4_t(bl, Vl + vo);
+          mma_bf16(o[hl][j], al, bh[0], bh[1]);
+          mma_bf16(o[hl][j], ah, bl[0], bl[1]);
+          mma_bf16(o[hl][j + 1], al, bh[2], bh[3]);
+          mma_bf16(o[hl][j + 1], ah, bl[2], bl[3]);
+        }
         mma_bf16(o[hl][j], ah, bh[0], bh[1]);
-        mma_bf16(o[hl][j + 1], al, bh[2], bh[3]);
-        mma_bf16(o[hl][j + 1], ah, bl[2], bl[3]);
         mma_bf16(o[hl][j + 1], ah, bh[2], bh[3]);
       }
     }
@@ -546,7 +561,8 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   }
   __syncthreads();
   if (hg == 0) {
-    __nv_bfloat16* og = out + (size_t)grp * kT * 2 * kD;
+    constexpr int kOut = SPLIT ? 2 * kD : kD;   // output row pitch (bf16 elements)
+    __nv_bfloat16* og = out + (size_t)grp * kT * kOut;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = nt * 8 + 2 * t;
@@ -554,11 +570,11 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       const float2 b = *reinterpret_cast<const float2*>(&part[(row0 + g + 8) * kPS + c]);
       uint32_t hi, lo;
       split_pack(acc[nt][0] + a.x, acc[nt][1] + a.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + c) = hi;
-      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * 2 * kD + kD + c) = lo;
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * kOut + c) = hi;
+      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g) * kOut + kD + c) = lo;
       split_pack(acc[nt][2] + b.x, acc[nt][3] + b.y, hi, lo);
-      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + c) = hi;
-      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * 2 * kD + kD + c) = lo;
+      *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * kOut + c) = hi;
+      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(og + (size_t)(row0 + g + 8) * kOut + kD + c) = lo;
     }
   }
   // the next pair's gate / exchange writes are ordered after these reads by its own __syncthreads chain
@@ -578,15 +594,31 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
                                                             (float*)out, round_tf);
-  } else if (dtype == AITB_BF16) {
+  } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || getenv("AITB_ATTN_TWO_PASS") != nullptr)) {
+    // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch)
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
         mask_mode, n_keys, (__nv_bfloat16*)out, 0);
+  } else if (dtype == AITB_BF16) {   // one-pass kernel, plain bf16 planes, persistent CTAs (128 accumulator registers per thread)
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           OnePass<false>::kSmem);
+      AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn one-pass) failed: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attn_core_split_kernel<false><<<G < sms ? G : sms, kSplitThreads, OnePass<false>::kSmem, stream>>>(
+        (const __nv_bfloat16*)q, ldq, 0, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, 0, w_sk, b_sk, G,
+        mask_mode, n_keys, (__nv_bfloat16*)out);
   } else if (dtype == AITB_F32S) {
     AITB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "aitb_attn_core: split mode needs leading dimensions that are multiples of 8");
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmem);
+      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           OnePass<true>::kSmem);
       AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn split) failed: %s", cudaGetErrorString(e));
       attr_set = true;
     }
@@ -594,7 +626,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    attn_core_split_kernel<<<G < sms ? G : sms, kSplitThreads, kSplitSmem, stream>>>(
+    attn_core_split_kernel<true><<<G < sms ? G : sms, kSplitThreads, OnePass<true>::kSmem, stream>>>(
         (const __nv_bfloat16*)q, 2 * ldq, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, 2 * ldkv, ldkv,
         w_sk, b_sk, G, mask_mode, n_keys, (__nv_bfloat16*)out);
   } else {
