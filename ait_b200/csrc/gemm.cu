@@ -112,7 +112,9 @@ struct GemmCfg {
 //   mt : 128-row tile index (rows mt*128 ...), n0 : first output column, t_row : TMEM address of this
 //   warp's lane quadrant in the accumulator stage, stg : this warp's 4 KB staging tile.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int BLOCK_N, bool CL, bool SPLIT, int COLS = BLOCK_N>
+// PARTS (CL LayerNorm): partial row statistics combined per row -- 2 = one per CTA of the cluster (each thread
+// drains all BLOCK_N columns of its CTA), 4 = two epilogue warpgroups per CTA, each draining COLS = BLOCK_N / 2.
+template <typename T, int BLOCK_N, bool CL, bool SPLIT, int COLS = BLOCK_N, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
                                               uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
                                               int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
@@ -402,31 +404,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     // M2 = S2 - S1^2 / n loses nothing to cancellation); pass 2 normalises.
     float shift = 0.f, S1 = 0.f, S2 = 0.f;
     uint4 pre[kIt], pre2[kIt];
-    if (aux_res) issue_loads(rptr, 0, pre);
-    if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, p.r_lo, pre2); }
+    if (aux_res) issue_loads(rptr, c_begin, pre);
+    if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c_begin + p.r_lo, pre2); }
     uint32_t raw[32];
-    tmem_ld32(t_row, raw);
+    tmem_ld32(t_row + c_begin, raw);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (c0 + 32 < BLOCK_N) tmem_ld32(t_row + c0 + 32, raw);
+      if (c0 + 32 < c_end) tmem_ld32(t_row + c0 + 32, raw);
       if constexpr (SPLIT) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
       }
-      if (p.flags & AITB_EPI_BIAS) add_lane_vec(lv_bias, c0, v);
+      if (p.flags & AITB_EPI_BIAS) add_lane_vec(lv_bias, c0 - c_begin, v);
       if (aux_res) {
         add_residual(pre, pre2, v);
-        if (c0 + 32 < BLOCK_N) {
+        if (c0 + 32 < c_end) {
           issue_loads(rptr, c0 + 32, pre);
           if constexpr (SPLIT) issue_loads(rptr, c0 + 32 + p.r_lo, pre2);
         }
       }
       if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
-      if (c0 == 0) {
+      if (c0 == c_begin) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) s += v[j];
@@ -444,10 +446,40 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       tmem_st32(t_row + c0, xo);
     }
     tmem_st_wait();
-    float mean = shift + S1 * (1.f / BLOCK_N);
-    float ssq = S2 - S1 * S1 * (1.f / BLOCK_N);  // centred M2 of my columns
-    float n_cols = (float)BLOCK_N;
-    if constexpr (CL) {
+    float mean = shift + S1 * (1.f / COLS);
+    float ssq = S2 - S1 * S1 * (1.f / COLS);  // centred M2 of my columns
+    float n_cols = (float)COLS;
+    if constexpr (CL && PARTS == 4) {
+      // four partials per row: (cluster rank, column half).  Every epilogue thread of the cluster publishes its
+      // (sum, M2) in BOTH CTAs' statistics tables and arrives on both barriers (count 512), then combines.
+      const float sum = mean * (float)COLS;
+      const uint32_t peer = cta_rank ^ 1u;
+      const int slot = (int)cta_rank * 2 + (c_begin != 0 ? 1 : 0);
+      float2* mine = &stats[(as * 4 + slot) * 128 + row_in_tile];
+      *mine = make_float2(sum, ssq);
+      st_cluster_f32x2(mapa_u32(smem_u32(mine), peer), sum, ssq);
+      mbar_arrive(stats_full_bar);
+      mbar_arrive_cluster(mapa_u32(smem_u32(stats_full_bar), peer));
+      tmem_ld32(t_row + c_begin, raw);  // first chunk of pass 2 travels while we wait
+      mbar_wait_cluster(stats_full_bar, aph);
+      float2 ps[4];
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ps[i] = stats[(as * 4 + i) * 128 + row_in_tile];
+        tot += ps[i].x;
+      }
+      const float mean_all = tot * (1.f / (4 * COLS));
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dm = ps[i].x * (1.f / COLS) - mean_all;
+        m2 += ps[i].y + (float)COLS * dm * dm;
+      }
+      ssq = m2;
+      mean = mean_all;
+      n_cols = 4.f * COLS;
+    } else if constexpr (CL) {
       // send (sum, M2) of my half-row to the peer, wait for the peer's, combine (Chan et al.)
       const float sum = mean * (float)BLOCK_N;
       const uint32_t peer = cta_rank ^ 1u;
@@ -466,19 +498,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       tmem_ld32(t_row, raw);
     }
     const float rstd = rsqrtf(fmaxf(ssq, 0.f) / n_cols + p.eps);
-    if (p.ln_rstd != nullptr && cta_rank == 0 && m_own < p.M) p.ln_rstd[orow_own] = rstd;
+    if (p.ln_rstd != nullptr && cta_rank == 0 && c_begin == 0 && m_own < p.M) p.ln_rstd[orow_own] = rstd;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) - mean) * rstd;
-      if (c0 + 32 < BLOCK_N) tmem_ld32(t_row + c0 + 32, raw);
+      if (c0 + 32 < c_end) tmem_ld32(t_row + c0 + 32, raw);
       float g[32];
-      lane_vec_chunk(lv_gamma, c0, g);
+      lane_vec_chunk(lv_gamma, c0 - c_begin, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= g[j];
-      add_lane_vec(lv_beta, c0, v);
+      add_lane_vec(lv_beta, c0 - c_begin, v);
       if (sizeof(T) == 4 && p.round_tf32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
@@ -638,6 +670,165 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster LayerNorm, two epilogue warpgroups (the production LN kernel).  Same tile schedule and main loop
+// as gemm_tcgen05_kernel<.., CL = true>: a 2-CTA cluster shares a 128-row m-tile, CTA rank r owns columns
+// [256 r, 256 r + 256) of the N = 512 row.  The LayerNorm epilogue is instruction/latency-bound (two passes over
+// TMEM per row, residual exchange, staged stores), so it gets EIGHT warps: warpgroup 1 drains columns 0..127 of
+// the CTA's accumulator, warpgroup 2 columns 128..255; the row statistics are four partials per row combined
+// through shared memory + DSMEM.  Measured on the K = 64 attention-fc GEMM (pure epilogue): see DESIGN.md.
+//   threads: warp 0 TMA, warp 1 MMA (warps 2, 3 idle, 40 registers), warps 4..11 epilogue (232 registers)
+// ---------------------------------------------------------------------------------------------
+static constexpr int kLnThreads = 384;
+
+template <typename T, bool SPLIT>
+struct LnCfg {
+  using Base = GemmCfg<256, SPLIT, SPLIT>;
+  static constexpr int kStages = (sizeof(T) == 4) ? 3 : 4;   // fp32 staging tiles are twice as large
+  static constexpr int kStageBytes = Base::kStageBytes;
+  static constexpr int kStatsBytes = 2 * 4 * 128 * 8;         // [acc stage][part][row] float2
+  static constexpr int kStgBytes = 8 * 32 * 32 * (int)sizeof(T);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStatsBytes + kStgBytes;
+};
+
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(kLnThreads, 1)
+gemm_ln2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmKParams p) {
+  constexpr int BLOCK_N = 256;
+  using Cfg = GemmCfg<BLOCK_N, SPLIT, SPLIT>;
+  using L = LnCfg<T, SPLIT>;
+  constexpr int kStages = L::kStages;
+  constexpr int kAcc = 2;
+  constexpr int kABytes = Cfg::kABytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* acc_empty = acc_full + kAcc;
+  uint64_t* stats_full = acc_empty + kAcc;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stats_full + kAcc);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 256);
+      mbar_init(&stats_full[s], 512);   // both CTAs' 256 epilogue threads
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
+  const int iters_per_tile = p.taps * p.k_chunks;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int tile = t_first; tile < p.m_tiles; tile += t_step) {
+          const int nt = (int)cta_rank;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
+            if (p.a_m_dim == 1) c1 += tile * p.a_m_step; else c3 += tile * p.a_m_step;
+            for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+              const uint32_t s = it % kStages;
+              const uint32_t ph = (it / kStages) & 1;
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* sa = smem + s * Cfg::kStageBytes;
+              uint8_t* sb = sa + Cfg::kPlanes * kABytes;
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+              tma_load_4d(sa, &tmA, &full_bar[s], kc * p.ke, c1, c2, c3);
+              const int kb = (tap * p.k_chunks + kc) * p.ke;
+              tma_load_2d(sb, &tmB, &full_bar[s], kb, nt * BLOCK_N);
+              if constexpr (SPLIT) {
+                tma_load_4d(sa + kABytes, &tmA, &full_bar[s], p.a_lo + kc * p.ke, c1, c2, c3);
+                tma_load_2d(sb + Cfg::kBBytes, &tmB, &full_bar[s], p.w_lo + kb, nt * BLOCK_N);
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(Act<T>::kFmt, kBlockM, BLOCK_N);
+        uint32_t it = 0, lt = 0;
+        for (int tile = t_first; tile < p.m_tiles; tile += t_step, ++lt) {
+          const uint32_t as = lt % kAcc;
+          const uint32_t aph = (lt / kAcc) & 1;
+          mbar_wait(&acc_empty[as], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+          for (int i = 0; i < iters_per_tile; ++i, ++it) {
+            const uint32_t s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint64_t adesc = make_kmajor_desc<Cfg::kRowBytes>(sa);
+            const uint64_t bdesc = make_kmajor_desc<Cfg::kRowBytes>(sa + Cfg::kPlanes * kABytes);
+#pragma unroll
+            for (int k = 0; k < Cfg::kKSlices; ++k) {
+              umma_ss<Act<T>::kBytes>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                      (i | k) != 0 ? 1u : 0u);
+              if constexpr (SPLIT) {
+                umma_ss<2>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(Cfg::kBBytes / 16 + k * 2), idesc, 1u);
+                umma_ss<2>(d_tmem, adesc + (uint64_t)(kABytes / 16 + k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+              }
+            }
+            tc_commit(&empty_bar[s]);
+          }
+          tc_commit(&acc_full[as]);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float2* stats = reinterpret_cast<float2*>(smem + kStages * Cfg::kStageBytes + 256);
+    uint8_t* stg = smem + kStages * Cfg::kStageBytes + 256 + L::kStatsBytes + (warp - 4) * (32 * 32 * (int)sizeof(T));
+    uint32_t lt = 0;
+    for (int tile = t_first; tile < p.m_tiles; tile += t_step, ++lt) {
+      const uint32_t as = lt % kAcc;
+      const uint32_t aph = (lt / kAcc) & 1;
+      const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<T, BLOCK_N, true, SPLIT, 128, 4>(p, stg, stats, &stats_full[as], &acc_full[as], t_row, q, lane, tile,
+                                                      (int)cta_rank * BLOCK_N, as, aph, cta_rank, half * 128,
+                                                      half * 128 + 128);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -950,6 +1141,42 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   return check_launch("gemm2_tcgen05_kernel");
 }
 
+template <typename T, bool SPLIT>
+static int launch_gemm_ln2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
+  using L = LnCfg<T, SPLIT>;
+  static bool attr_set = false;
+  auto kern = gemm_ln2_tcgen05_kernel<T, SPLIT>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_ln2) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int clusters = kp.m_tiles < num_sms() / 2 ? kp.m_tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kLnThreads);
+  cfg.dynamicSmemBytes = L::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp);
+  if (e != cudaSuccess) {
+    set_error("gemm_ln2_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 1;
+  }
+  return check_launch("gemm_ln2_tcgen05_kernel");
+}
+
 int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d != nullptr, "aitb_gemm: null descriptor");
   AITB_REQUIRE(d->dtype == AITB_F32 || d->dtype == AITB_BF16 || d->dtype == AITB_F32S, "aitb_gemm: bad dtype %d",
@@ -1071,6 +1298,11 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   (d->dtype == AITB_F32 ? launch_gemm<float, BN, false, false>(tmA, tmB, kp, stream)               \
    : split              ? launch_gemm<__nv_bfloat16, BN, false, true>(tmA, tmB, kp, stream)        \
                         : launch_gemm<__nv_bfloat16, BN, false, false>(tmA, tmB, kp, stream))
+  static const bool ln_one_wg = getenv("AITB_LN_ONE_WG") != nullptr;   // A/B: the single-warpgroup LayerNorm epilogue
+  if (cluster_ln && !ln_one_wg && d->a_group_c == 0)
+    return d->dtype == AITB_F32 ? launch_gemm_ln2<float, false>(tmA, tmB, kp, stream)
+           : split              ? launch_gemm_ln2<__nv_bfloat16, true>(tmA, tmB, kp, stream)
+                                : launch_gemm_ln2<__nv_bfloat16, false>(tmA, tmB, kp, stream);
   if (cluster_ln)
     return d->dtype == AITB_F32 ? launch_gemm<float, 256, true, false>(tmA, tmB, kp, stream)
            : split              ? launch_gemm<__nv_bfloat16, 256, true, true>(tmA, tmB, kp, stream)
