@@ -143,6 +143,83 @@ det_assemble_kernel(const float4* __restrict__ pred, const float* __restrict__ c
   }
 }
 
+// RPN head outputs in token-major layout (the [rows, ld] output of the fused RPN_cls_score | RPN_bbox_pred GEMM:
+// columns 0..A-1 background scores, A..2A-1 foreground scores, 2A..6A-1 box deltas; lib/model/rpn/rpn.py:70-85)
+// -> pair softmax (rpn.py:76-78: reshape(x, 2) + softmax over the bg / fg pair of every anchor), anchors,
+// bbox_transform_inv, clip: proposals [B, H*W*A, 4], fg [B, H*W*A]; optionally also the reference's NCHW tensors
+// rpn_cls_prob [B, 2A, H, W] and rpn_bbox_pred [B, 4A, H, W].
+// MODE: AITB_F32 (fp32 rows), AITB_BF16, AITB_F32S (two bf16 planes per row, lo plane `ld` elements further)
+template <int MODE>
+__device__ __forceinline__ float tok_load(const void* base, size_t row, int ld, int col) {
+  if constexpr (MODE == AITB_F32) {
+    return reinterpret_cast<const float*>(base)[row * ld + col];
+  } else if constexpr (MODE == AITB_BF16) {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[row * ld + col]);
+  } else {
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(base) + row * 2 * (size_t)ld;
+    return __bfloat162float(r[col]) + __bfloat162float(r[ld + col]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+rpn_head_decode_kernel(const void* __restrict__ heads, int ld, const float* __restrict__ base, const float* __restrict__ im_info,
+                       int A, int H, int W, float stride, float4* __restrict__ proposals, float* __restrict__ fg,
+                       float* __restrict__ cls_prob_nchw, float* __restrict__ bbox_pred_nchw) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // = cell * A + a: the candidate index of the proposal layer
+  const int cells = H * W;
+  if (i >= A * cells) return;
+  const int cell = i / A, a = i - cell * A;
+  const int y = cell / W, x = cell - y * W;
+  const size_t row = (size_t)b * cells + cell;
+  const float bg = tok_load<MODE>(heads, row, ld, a), fgs = tok_load<MODE>(heads, row, ld, A + a);
+  const float m = fmaxf(bg, fgs);
+  const float e0 = expf(__fsub_rn(bg, m)), e1 = expf(__fsub_rn(fgs, m));
+  const float den = __fadd_rn(e0, e1);
+  const float p1 = __fdiv_rn(e1, den);
+  float d[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = tok_load<MODE>(heads, row, ld, 2 * A + 4 * a + j);
+  const float sx = (float)x * stride, sy = (float)y * stride;
+  float4 an;
+  an.x = __fadd_rn(base[a * 4 + 0], sx);
+  an.y = __fadd_rn(base[a * 4 + 1], sy);
+  an.z = __fadd_rn(base[a * 4 + 2], sx);
+  an.w = __fadd_rn(base[a * 4 + 3], sy);
+  const size_t out = (size_t)b * cells * A + i;
+  proposals[out] = decode_clip(an, d[0], d[1], d[2], d[3], im_info[b * 3 + 0], im_info[b * 3 + 1]);
+  fg[out] = p1;
+  if (cls_prob_nchw) {
+    cls_prob_nchw[((size_t)b * 2 * A + a) * cells + cell] = __fdiv_rn(e0, den);
+    cls_prob_nchw[((size_t)b * 2 * A + A + a) * cells + cell] = p1;
+  }
+  if (bbox_pred_nchw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bbox_pred_nchw[((size_t)b * 4 * A + 4 * a + j) * cells + cell] = d[j];
+  }
+}
+
+int rpn_head_decode_run(const void* heads, int dtype, int ld, const float* base_anchors, const float* im_info, int B, int A,
+                        int H, int W, float feat_stride, float* proposals, float* fg_scores, float* cls_prob_nchw,
+                        float* bbox_pred_nchw, cudaStream_t st) {
+  AITB_REQUIRE(heads && base_anchors && im_info && proposals && fg_scores, "aitb_rpn_forward: null pointer");
+  AITB_REQUIRE(B > 0 && A > 0 && H > 0 && W > 0 && 6 * A <= ld, "aitb_rpn_forward: bad sizes");
+  const int n = A * H * W;
+  dim3 grid((n + 255) / 256, B);
+  float4* pr = reinterpret_cast<float4*>(proposals);
+  if (dtype == AITB_F32)
+    rpn_head_decode_kernel<AITB_F32><<<grid, 256, 0, st>>>(heads, ld, base_anchors, im_info, A, H, W, feat_stride, pr,
+                                                           fg_scores, cls_prob_nchw, bbox_pred_nchw);
+  else if (dtype == AITB_BF16)
+    rpn_head_decode_kernel<AITB_BF16><<<grid, 256, 0, st>>>(heads, ld, base_anchors, im_info, A, H, W, feat_stride, pr,
+                                                            fg_scores, cls_prob_nchw, bbox_pred_nchw);
+  else
+    rpn_head_decode_kernel<AITB_F32S><<<grid, 256, 0, st>>>(heads, ld, base_anchors, im_info, A, H, W, feat_stride, pr,
+                                                            fg_scores, cls_prob_nchw, bbox_pred_nchw);
+  return check_launch("rpn_head_decode_kernel");
+}
+
 int rpn_decode_run(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,
                    int B, int A, int H, int W, float feat_stride, float* proposals, float* fg_scores, cudaStream_t st) {
   AITB_REQUIRE(scores_nchw && deltas_nchw && base_anchors && im_info && proposals && fg_scores, "aitb_rpn_decode: null pointer");

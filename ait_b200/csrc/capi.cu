@@ -47,6 +47,9 @@ int rpn_decode_run(const float* scores_nchw, const float* deltas_nchw, const flo
 int box_decode_run(const float* boxes, int boxes_stride, int boxes_off, const float* deltas, const float* cls,
                    const float* im_info, int B, int N, const float* stds, const float* means, float thresh,
                    int divide_by_scale, float* pred, float* key, int32_t* n_valid, cudaStream_t st);
+int rpn_head_decode_run(const void* heads, int dtype, int ld, const float* base_anchors, const float* im_info, int B, int A,
+                        int H, int W, float feat_stride, float* proposals, float* fg_scores, float* cls_prob_nchw,
+                        float* bbox_pred_nchw, cudaStream_t st);
 int det_assemble_run(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
                      int32_t* n_det, cudaStream_t st);
@@ -903,6 +906,70 @@ int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat
                     float* feat_out, float* bbox_out, float* cls_prob_out, aitb_stream_t stream) {
   return pool_heads_run(top, dtype, G, P, qfeat, w_bbox, b_bbox, w1, b1, w2, b2, feat_out, bbox_out, cls_prob_out,
                         (cudaStream_t)stream);
+}
+
+size_t aitb_rpn_workspace_bytes(int B, int H, int W, int dtype) {
+  const size_t eb = esize(dtype), rows = (size_t)B * H * W;
+  return ((rows * 1024 * eb + 1023) & ~(size_t)1023) + ((rows * 512 * eb + 1023) & ~(size_t)1023) +
+         ((rows * 128 * eb + 1023) & ~(size_t)1023) + 1024;
+}
+
+int aitb_rpn_forward(const aitb_rpn_weights* w, const float* feat_nchw, int B, int H, int W, const float* base_anchors,
+                     const float* im_info, float feat_stride, float* proposals, float* fg_scores, float* rpn_cls_prob,
+                     float* rpn_bbox_pred, void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AITB_REQUIRE(w && w->conv.w && w->conv.bias && w->heads.w && w->heads.bias, "aitb_rpn_forward: weights missing");
+  AITB_REQUIRE(w->dtype == AITB_F32 || w->dtype == AITB_BF16 || w->dtype == AITB_F32S, "aitb_rpn_forward: bad dtype");
+  AITB_REQUIRE(w->A > 0 && (w->n_pad == 64 || w->n_pad == 128) && 6 * w->A <= w->n_pad, "aitb_rpn_forward: bad head width");
+  AITB_REQUIRE(B > 0 && H > 0 && W > 0 && W <= 128, "aitb_rpn_forward: map %dx%d unsupported (width <= 128)", H, W);
+  AITB_REQUIRE(feat_nchw && workspace && ((uintptr_t)workspace & 1023) == 0 &&
+                   workspace_bytes >= aitb_rpn_workspace_bytes(B, H, W, w->dtype),
+               "aitb_rpn_forward: bad input / workspace");
+  const int dt = w->dtype, rows = B * H * W;
+  const size_t eb = esize(dt);
+  Bump b{(uint8_t*)workspace, 0};
+  void* featT = b.take((size_t)rows * 1024 * eb);
+  void* conv = b.take((size_t)rows * 512 * eb);
+  void* heads = b.take((size_t)rows * 128 * eb);
+  RUN(transpose_run(feat_nchw, AITB_F32, featT, dt, B, 1024, H * W, 1, st, w->round_tf32));
+  {  // RPN_Conv 3x3 + bias + ReLU: the map is tiled by boxes of bx x by = 128 positions of one image
+    const int bx = W <= 64 ? 64 : 128, by = 128 / bx;
+    const int tpg = (H + by - 1) / by;
+    aitb_gemm_desc d = gemm_base(dt, B * tpg * 128, 512, 1024, w->conv.w, 256, conv, 512, w->round_tf32);
+    d.a.ptr = featT;
+    d.a.dims[0] = 1024;
+    if (dt == AITB_F32S) {
+      d.a.dims[0] = 2048;
+      d.a_lo_off = 1024;
+    }
+    d.a.dims[1] = (uint64_t)W;
+    d.a.dims[2] = (uint64_t)H;
+    d.a.dims[3] = (uint64_t)B;
+    d.a.strides[0] = (uint64_t)1024 * eb;
+    d.a.strides[1] = (uint64_t)W * 1024 * eb;
+    d.a.strides[2] = (uint64_t)H * W * 1024 * eb;
+    d.a.box[0] = 128 / colsize(dt);
+    d.a.box[1] = (uint32_t)bx;
+    d.a.box[2] = (uint32_t)by;
+    d.a.box[3] = 1;
+    d.a_m_dim = 2;
+    d.a_m_step = 1;
+    d.map_w = W;
+    d.map_h = H;
+    taps3x3(d);
+    d.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
+    d.bias = w->conv.bias;
+    RUN(gemm_run(&d, st));
+  }
+  {  // RPN_cls_score | RPN_bbox_pred as one 1x1 GEMM
+    aitb_gemm_desc d = gemm_base(dt, rows, w->n_pad, 512, w->heads.w, w->n_pad, heads, w->n_pad, 0);
+    view_plain(d, conv, 512);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->heads.bias;
+    RUN(gemm_run(&d, st));
+  }
+  return rpn_head_decode_run(heads, dt, w->n_pad, base_anchors, im_info, B, w->A, H, W, feat_stride, proposals, fg_scores,
+                             rpn_cls_prob, rpn_bbox_pred, st);
 }
 
 int aitb_rpn_decode(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,

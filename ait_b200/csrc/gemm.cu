@@ -45,6 +45,10 @@ struct GemmKParams {
   int k_chunks;  // 128-byte K chunks per tap
   int taps;
   int a_m_dim, a_m_step, a_group_c;
+  // a_m_dim == 2 ("map" mode: a W x H map tiled by boxes of map_bx x map_by = 128 positions, one image per
+  // coordinate 3): m-tile t -> image t / map_tpg, first map row (t % map_tpg) * map_by; tile row r -> position
+  // (x = r % map_bx, y = y0 + r / map_bx), valid while x < map_w and y < map_h; output row = image * map_w * map_h + y * map_w + x
+  int map_bx, map_by, map_tpg, map_w, map_h;
   int ke;  // elements per 128-byte chunk
   int8_t tap_dx[9], tap_dy[9];
   int m_tiles, n_tiles;
@@ -75,6 +79,20 @@ __device__ __forceinline__ uint4 ld_global_v4(const void* p) {
   uint4 v;
   asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
+}
+
+// GEMM row m (tile-major) -> output row; *ok = the row exists.  Plain: optional rows_in -> rows_out regrouping.
+// Map mode: see GemmKParams.
+__device__ __forceinline__ int out_row_of(const GemmKParams& p, int m, bool* ok) {
+  if (p.a_m_dim == 2) {
+    const int t = m >> 7, r = m & 127;
+    const int g = t / p.map_tpg, y = (t - g * p.map_tpg) * p.map_by + r / p.map_bx, x = r % p.map_bx;
+    *ok = m < p.M && x < p.map_w && y < p.map_h;
+    return *ok ? (g * p.map_h + y) * p.map_w + x : 0;
+  }
+  *ok = m < p.M;
+  const int mm = *ok ? m : 0;
+  return (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -137,9 +155,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
   for (int it = 0; it < kIt; ++it) {
     const int m = mt * kBlockM + q * 32 + it * kRpi + srow0;
-    const bool ok = m < p.M;
-    const int mm = ok ? m : 0;
-    const int orow = (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
+    bool ok;
+    const int orow = out_row_of(p, m, &ok);
     optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
     int rrow = 0;
     if (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
@@ -148,8 +165,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   }
   // this thread's own row (for the fp32 positional table)
   const int m_own = mt * kBlockM + row_in_tile;
-  const int mm_own = m_own < p.M ? m_own : 0;
-  const int orow_own = (mm_own / p.rows_in) * p.rows_out + (mm_own % p.rows_in);
+  bool ok_own;
+  const int orow_own = out_row_of(p, m_own, &ok_own);
   const float* prow = p.pos + (size_t)((p.flags & AITB_EPI_POS) ? (orow_own % p.pos_rows) : 0) * p.N + n0;
 
   // issue this lane's share of a coalesced 32-row x 32-column global read (no dependent use yet)
@@ -498,7 +515,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       tmem_ld32(t_row, raw);
     }
     const float rstd = rsqrtf(fmaxf(ssq, 0.f) / n_cols + p.eps);
-    if (p.ln_rstd != nullptr && cta_rank == 0 && c_begin == 0 && m_own < p.M) p.ln_rstd[orow_own] = rstd;
+    if (p.ln_rstd != nullptr && cta_rank == 0 && c_begin == 0 && ok_own) p.ln_rstd[orow_own] = rstd;
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       tmem_ld_wait();
@@ -589,7 +606,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int a_c_base = nt * p.a_group_c;
         for (int tap = 0; tap < n_taps; ++tap) {
           int c1 = tap < p.taps ? p.tap_dx[tap] : 0, c2 = tap < p.taps ? p.tap_dy[tap] : 0, c3 = 0;
-          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
+          if (p.a_m_dim == 1) c1 += mt * p.a_m_step;
+          else if (p.a_m_dim == 3) c3 += mt * p.a_m_step;
+          else { c2 += (mt % p.map_tpg) * p.map_by; c3 += mt / p.map_tpg; }
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
             const uint32_t s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
@@ -753,7 +772,9 @@ gemm_ln2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const int nt = (int)cta_rank;
           for (int tap = 0; tap < p.taps; ++tap) {
             int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
-            if (p.a_m_dim == 1) c1 += tile * p.a_m_step; else c3 += tile * p.a_m_step;
+            if (p.a_m_dim == 1) c1 += tile * p.a_m_step;
+          else if (p.a_m_dim == 3) c3 += tile * p.a_m_step;
+          else { c2 += (tile % p.map_tpg) * p.map_by; c3 += tile / p.map_tpg; }
             for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
               const uint32_t s = it % kStages;
               const uint32_t ph = (it / kStages) & 1;
@@ -910,7 +931,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int mt = mp * 2 + (int)rank;
         for (int tap = 0; tap < p.taps; ++tap) {
           int c1 = p.tap_dx[tap], c2 = p.tap_dy[tap], c3 = 0;
-          if (p.a_m_dim == 1) c1 += mt * p.a_m_step; else c3 += mt * p.a_m_step;
+          if (p.a_m_dim == 1) c1 += mt * p.a_m_step;
+          else if (p.a_m_dim == 3) c3 += mt * p.a_m_step;
+          else { c2 += (mt % p.map_tpg) * p.map_by; c3 += mt / p.map_tpg; }
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
             const uint32_t s = it % k2Stages;
             const uint32_t ph = (it / k2Stages) & 1;
@@ -1197,7 +1220,11 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d->taps >= 1 && d->taps <= 9, "aitb_gemm: taps=%d", d->taps);
   AITB_REQUIRE(d->a.box[0] == (uint32_t)ke, "aitb_gemm: A box[0] must span 128 bytes");
   AITB_REQUIRE(d->a.box[1] * d->a.box[2] * d->a.box[3] == 128, "aitb_gemm: A box must cover 128 rows");
-  AITB_REQUIRE(d->a_m_dim == 1 || d->a_m_dim == 3, "aitb_gemm: a_m_dim must be 1 or 3");
+  AITB_REQUIRE(d->a_m_dim == 1 || d->a_m_dim == 2 || d->a_m_dim == 3, "aitb_gemm: a_m_dim must be 1, 2 or 3");
+  if (d->a_m_dim == 2)
+    AITB_REQUIRE(d->map_w > 0 && d->map_h > 0 && d->a.box[1] * d->a.box[2] == 128 && d->a.box[3] == 1 &&
+                     d->map_w <= (int)d->a.box[1] && d->M % 128 == 0 && d->rows_in == d->rows_out,
+                 "aitb_gemm: bad map-mode view (box x * y must be 128 positions of one image, width <= box x)");
   AITB_REQUIRE((d->flags & AITB_EPI_LN) == 0 || (d->block_n == 512 && d->N == 512),
                "aitb_gemm: the LayerNorm epilogue needs block_n == N == 512");
   AITB_REQUIRE((d->flags & AITB_EPI_LN) != 0 || d->block_n != 512, "aitb_gemm: block_n 512 is the LayerNorm variant");
@@ -1246,6 +1273,13 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   kp.taps = d->taps;
   kp.a_m_dim = d->a_m_dim;
   kp.a_m_step = d->a_m_step;
+  if (d->a_m_dim == 2) {
+    kp.map_bx = (int)d->a.box[1];
+    kp.map_by = (int)d->a.box[2];
+    kp.map_w = d->map_w;
+    kp.map_h = d->map_h;
+    kp.map_tpg = (d->map_h + kp.map_by - 1) / kp.map_by;
+  }
   kp.a_group_c = d->a_group_c;
   kp.ke = kes;
   for (int i = 0; i < 9; ++i) {

@@ -130,7 +130,8 @@ typedef struct {
                 LOGICAL elements of 4 bytes, i.e. strides in bytes of the physical two-plane rows) */
   int M, N, k_per_tap, taps;
   aitb_view4 a;
-  int a_m_dim;   /* which A coordinate advances with the m-tile: 1 (plain rows) or 3 (conv) */
+  int a_m_dim;   /* which A coordinate advances with the m-tile: 1 (plain rows), 3 (small maps: whole maps per tile) or
+                    2 (large map, see map_w / map_h) */
   int a_m_step;  /* coordinate step per 128-row m-tile                                      */
   int a_group_c; /* grouped conv: input-channel offset per n-tile (0 otherwise)             */
   int8_t tap_dx[9], tap_dy[9];
@@ -160,6 +161,10 @@ typedef struct {
   int a_lo_off;
   /* optional (LN epilogue): 1 / sigma of every normalised row, written at the row's OUTPUT index (training) */
   float* ln_rstd;
+  /* a_m_dim == 2: A is a channels-last map [G, map_h, map_w, C] (view dims {C, map_w, map_h, G}) tiled by boxes of
+   * box[1] x box[2] = 128 positions of one image (box[1] >= map_w); M = G * ceil(map_h / box[2]) * 128 tile rows;
+   * output row = g * map_h * map_w + y * map_w + x (positions outside the map are computed on zero fill and dropped) */
+  int map_w, map_h;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
@@ -291,6 +296,23 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
 int aitb_rpn_decode(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors,
                     const float* im_info, int B, int A, int H, int W, float feat_stride, float* proposals,
                     float* fg_scores, aitb_stream_t stream);
+
+/* f3 (first half): the RPN head in front of the proposal layer (lib/model/rpn/rpn.py:34-85): 3x3 conv 1024 -> 512 +
+ * ReLU on the whole C4 map (nine shifted TMA boxes per K chunk, zero fill = padding), RPN_cls_score | RPN_bbox_pred as
+ * ONE 1x1 GEMM, the bg/fg pair softmax, anchors, bbox_transform_inv and clip_boxes.
+ *   conv.w  [512, 9*1024] tap-major (dtype), conv.bias [512] f32
+ *   heads.w [n_pad, 512] (dtype): rows 0..2A-1 = RPN_cls_score, 2A..6A-1 = RPN_bbox_pred, zero rows up to
+ *           n_pad = 64 (6A <= 64) or 128; heads.bias [n_pad] f32
+ *   feat_nchw [B, 1024, H, W] f32 (W <= 128) -> proposals [B, H*W*A, 4], fg_scores [B, H*W*A];
+ *   optional reference-layout outputs rpn_cls_prob [B, 2A, H, W], rpn_bbox_pred [B, 4A, H, W] (NULL = skip) */
+typedef struct {
+  int dtype, round_tf32, A, n_pad;
+  aitb_linear conv, heads;
+} aitb_rpn_weights;
+size_t aitb_rpn_workspace_bytes(int B, int H, int W, int dtype);
+int aitb_rpn_forward(const aitb_rpn_weights* w, const float* feat_nchw, int B, int H, int W, const float* base_anchors,
+                     const float* im_info, float feat_stride, float* proposals, float* fg_scores, float* rpn_cls_prob,
+                     float* rpn_bbox_pred, void* workspace, size_t workspace_bytes, aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f2  detection post-processing (test_net_voc.py:380-446)

@@ -268,3 +268,21 @@ def detections(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, m
             dets = dets[dets[:, -1] >= float(image_thresh)]
         out.append(dets)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# f3 (first half): the RPN head, inference path (lib/model/rpn/rpn.py:64-94)
+# ------------------------------------------------------------------------------------------------
+def rpn_forward(sd, base_feat, im_info, base_anchors, feat_stride=16, pre_nms_topN=6000, post_nms_topN=300,
+                nms_thresh=0.7, dtype=torch.float32):
+    """sd: RPN_Conv.*, RPN_cls_score.*, RPN_bbox_pred.* -> (rois, rpn_cls_prob, rpn_bbox_pred)."""
+    w = _cast(sd, dtype)
+    x = base_feat.to(dtype)
+    conv1 = F.relu(F.conv2d(x, w["RPN_Conv.weight"], w["RPN_Conv.bias"], padding=1))          # :69
+    score = F.conv2d(conv1, w["RPN_cls_score.weight"], w["RPN_cls_score.bias"])                 # :73
+    B, c2, H, W = score.shape
+    prob = F.softmax(score.contiguous().view(B, 2, c2 * H // 2, W), 1).view(B, c2, H, W)      # reshape(x, 2) :75-78
+    bbox = F.conv2d(conv1, w["RPN_bbox_pred.weight"], w["RPN_bbox_pred.bias"])                  # :82
+    rois = proposal_layer(prob.float(), bbox.float(), im_info, base_anchors, feat_stride, pre_nms_topN, post_nms_topN,
+                          nms_thresh)
+    return rois, prob, bbox

@@ -188,3 +188,35 @@ def test_oracle_proposal_layer_matches_reference_golden():
     rois = head_oracle.proposal_layer(cls_prob, bbox_pred, im_info, gold["anchors"], 16, gold["pre"], gold["post"],
                                       gold["thr"])
     assert torch.equal(rois, gold["rois"])
+
+
+def _rpn_inputs(seed=23, B=2, H=19, W=31):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    base_feat = torch.randn(B, 1024, H, W, generator=g).relu()
+    im_info = torch.tensor([[300.0, 500.0, 1.5], [280.0, 480.0, 0.8]])[:B]
+    g = torch.Generator().manual_seed(seed + 1)
+    sd = {"RPN_Conv.weight": torch.randn(512, 1024, 3, 3, generator=g) * 0.01,
+          "RPN_Conv.bias": torch.randn(512, generator=g) * 0.1,
+          "RPN_cls_score.weight": torch.randn(18, 512, 1, 1, generator=g) * 0.05,
+          "RPN_cls_score.bias": torch.randn(18, generator=g) * 0.1,
+          "RPN_bbox_pred.weight": torch.randn(36, 512, 1, 1, generator=g) * 0.01,
+          "RPN_bbox_pred.bias": torch.randn(36, generator=g) * 0.05}
+    return base_feat, im_info, sd
+
+
+def test_oracle_rpn_head_matches_reference_golden():
+    """row f3 (RPN head): conv 3x3 + ReLU, cls / bbox 1x1 heads, pair softmax, proposal layer -- the restatement
+    reproduces the unmodified `_RPN` (tests/golden/make_golden_rpn.py): rois bit for bit."""
+    import torch
+    from conftest import load_golden
+    from oracle import head_oracle
+    gold = load_golden("rpn_head.pt")
+    base_feat, im_info, sd = _rpn_inputs(gold["seed"])
+    torch.set_num_threads(8)
+    rois, prob, bbox = head_oracle.rpn_forward(sd, base_feat, im_info, gold["anchors"], 16, gold["pre"], gold["post"],
+                                               gold["thr"])
+    assert torch.allclose(prob, gold["cls_prob"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bbox[:, ::3], gold["bbox_pred_s"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(rois[..., 0], gold["rois"][..., 0])
+    assert torch.allclose(rois, gold["rois"], rtol=1e-5, atol=1e-3)
