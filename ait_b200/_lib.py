@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("res_div", C.c_int), ("res_rep", C.c_int),
         ("pos", C.c_void_p), ("pos_rows", C.c_int),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
-        ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int), ("ln_rstd", C.c_void_p), ("map_w", C.c_int), ("map_h", C.c_int),
+        ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int), ("ln_rstd", C.c_void_p), ("map_w", C.c_int), ("map_h", C.c_int), ("out_scale", C.c_float),
     ]
 
 
@@ -129,6 +129,8 @@ SIGNATURES = {
                                C.POINTER(HeadTaps), _vp, _sz, _vp]),
     "aitb_ait_workspace_bytes": (_sz, [_i, _i, _i]),
     "aitb_ait_forward": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "aitb_coattention_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aitb_coattention_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "aitb_rpn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "aitb_rpn_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_rpn_decode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),

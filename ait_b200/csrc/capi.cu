@@ -50,6 +50,8 @@ int box_decode_run(const float* boxes, int boxes_stride, int boxes_off, const fl
 int rpn_head_decode_run(const void* heads, int dtype, int ld, const float* base_anchors, const float* im_info, int B, int A,
                         int H, int W, float feat_stride, float* proposals, float* fg_scores, float* cls_prob_nchw,
                         float* bbox_pred_nchw, cudaStream_t st);
+int group_norm_residual_run(const float* x, const float* identity, const float* gamma, const float* beta, int B, int N,
+                            int groups, float eps, double* sums, float* out, cudaStream_t st);
 int det_assemble_run(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
                      int32_t* n_det, cudaStream_t st);
@@ -906,6 +908,113 @@ int aitb_pool_heads(const void* top, int dtype, int G, int P, const float* qfeat
                     float* feat_out, float* bbox_out, float* cls_prob_out, aitb_stream_t stream) {
   return pool_heads_run(top, dtype, G, P, qfeat, w_bbox, b_bbox, w1, b1, w2, b2, feat_out, bbox_out, cls_prob_out,
                         (cudaStream_t)stream);
+}
+
+size_t aitb_coattention_workspace_bytes(int B, int H, int W) {
+  const size_t rows = (size_t)B * H * W, rq = (size_t)B * 64;
+  const size_t floats = rows * (1024 * 5 + 64 + 512) + rq * (1024 * 4 + 512 * 4) + (size_t)B * 64 * 2 * 2;
+  return floats * 4 + 32 * 1024;
+}
+
+int aitb_coattention_forward(const aitb_coatt_weights* w, const float* x_img, const float* x_qry, int B, int H, int W,
+                             float* non_img, float* non_qry, void* workspace, size_t workspace_bytes,
+                             aitb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AITB_REQUIRE(w && w->dtype == AITB_F32, "aitb_coattention_forward: runs in the fp32-storage / tf32 configuration");
+  AITB_REQUIRE(w->w_emb_phi && w->b_emb_phi && w->emb.w && w->emb.bias && w->rho.w && w->rho.bias && w->theta.w &&
+                   w->theta.bias && w->omega.w && w->omega.bias && w->theta_gn.gamma && w->theta_gn.beta &&
+                   w->omega_gn.gamma && w->omega_gn.beta,
+               "aitb_coattention_forward: weights missing");
+  AITB_REQUIRE(B > 0 && H > 0 && W > 0 && x_img && x_qry && non_img && non_qry && workspace, "aitb_coattention_forward: bad arguments");
+  AITB_REQUIRE(((uintptr_t)workspace & 1023) == 0 && workspace_bytes >= aitb_coattention_workspace_bytes(B, H, W),
+               "aitb_coattention_forward: workspace too small or misaligned");
+  const int Ni = H * W, rows = B * Ni, rq = B * 64, rt = 1;
+  Bump b{(uint8_t*)workspace, 0};
+  auto f = [&](size_t n) { return (float*)b.take(n * 4); };
+  float* Xi = f((size_t)rows * 1024);    // exact tokens (residual)
+  float* Xir = f((size_t)rows * 1024);   // tf32-rounded tokens (MMA operand)
+  float* EP = f((size_t)rows * 1024);    // [emb | phi] of the image
+  float* coT = f((size_t)rows * 64);     // co_attention^T per image: [Ni, 64]
+  float* NI = f((size_t)rows * 512);
+  float* TH = f((size_t)rows * 1024);
+  float* Xq = f((size_t)rq * 1024);
+  float* Xqr = f((size_t)rq * 1024);
+  float* Eq = f((size_t)rq * 512);
+  float* Rq = f((size_t)rq * 512);
+  float* EqT = f((size_t)rq * 512);
+  float* NQT = f((size_t)rq * 512);
+  float* NQ = Eq;                        // Eq is dead once EqT exists
+  float* OM = f((size_t)rq * 1024);
+  float* OUTq = f((size_t)rq * 1024);
+  double* sums = (double*)b.take((size_t)B * 32 * 2 * sizeof(double) * 2);
+  float* OUTi = EP;                      // EP is dead after the per-image products
+
+  RUN(transpose_run(x_img, AITB_F32, Xi, AITB_F32, B, 1024, Ni, 1, st, 0));
+  RUN(transpose_run(x_img, AITB_F32, Xir, AITB_F32, B, 1024, Ni, 1, st, rt));
+  RUN(transpose_run(x_qry, AITB_F32, Xq, AITB_F32, B, 1024, 64, 1, st, 0));
+  RUN(transpose_run(x_qry, AITB_F32, Xqr, AITB_F32, B, 1024, 64, 1, st, rt));
+  {  // emb | phi of the image, one GEMM  (blocks_coatt...:70-79)
+    aitb_gemm_desc d = gemm_base(AITB_F32, rows, 1024, 1024, w->w_emb_phi, 256, EP, 1024, rt);
+    view_plain(d, Xir, 1024);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->b_emb_phi;
+    RUN(gemm_run(&d, st));
+  }
+  {  // emb and rho of the query (:73-77)
+    aitb_gemm_desc d = gemm_base(AITB_F32, rq, 512, 1024, w->emb.w, 256, Eq, 512, rt);
+    view_plain(d, Xqr, 1024);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->emb.bias;
+    RUN(gemm_run(&d, st));
+    aitb_gemm_desc d2 = gemm_base(AITB_F32, rq, 512, 1024, w->rho.w, 256, Rq, 512, rt);
+    view_plain(d2, Xqr, 1024);
+    d2.flags = AITB_EPI_BIAS;
+    d2.bias = w->rho.bias;
+    RUN(gemm_run(&d2, st));
+  }
+  RUN(transpose_run(Eq, AITB_F32, EqT, AITB_F32, B, 64, 512, 1, st, 0));   // [B, 64, 512] -> [B, 512, 64]
+  cudaError_t e = cudaMemsetAsync(NQT, 0, (size_t)rq * 512 * 4, st);
+  AITB_REQUIRE(e == cudaSuccess, "aitb_coattention_forward: memset failed: %s", cudaGetErrorString(e));
+  for (int i = 0; i < B; ++i) {
+    float* EPb = EP + (size_t)i * Ni * 1024;
+    float* coTb = coT + (size_t)i * Ni * 64;
+    {  // co_attention^T = phi_img^T-major product: [Ni, 64] = phi_img[Ni, 512] . rho_qry[64, 512]^T  (:81)
+      aitb_gemm_desc d = gemm_base(AITB_F32, Ni, 64, 512, Rq + (size_t)i * 64 * 512, 64, coTb, 64, rt);
+      view_plain(d, EPb + 512, 1024);
+      RUN(gemm_run(&d, st));
+    }
+    {  // non_img = (co^T / N_q) . emb_qry: [Ni, 512]  (:92-93,99)
+      aitb_gemm_desc d = gemm_base(AITB_F32, Ni, 512, 64, EqT + (size_t)i * 512 * 64, 256, NI + (size_t)i * Ni * 512, 512, rt);
+      view_plain(d, coTb, 64);
+      d.out_scale = 1.f / 64.f;
+      RUN(gemm_run(&d, st));
+    }
+    // non_qry^T = emb_img^T . co^T: [512, 64], contraction over the Ni image positions (:104) -- the MN-major
+    // row-contraction kernel of the training path; the 1 / N_i of :91 is applied by the omega GEMM
+    RUN(wgrad_run(EPb, 1024, coTb, 64, Ni, 512, 64, NQT + (size_t)i * 512 * 64, 64, st));
+  }
+  {  // theta: 1x1 conv 512 -> 1024, GroupNorm(32), + identity_img  (:100-102)
+    aitb_gemm_desc d = gemm_base(AITB_F32, rows, 1024, 512, w->theta.w, 256, TH, 1024, 0);
+    view_plain(d, NI, 512);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->theta.bias;
+    RUN(gemm_run(&d, st));
+    RUN(group_norm_residual_run(TH, Xi, w->theta_gn.gamma, w->theta_gn.beta, B, Ni, 32, 1e-5f, sums, OUTi, st));
+    RUN(transpose_run(OUTi, AITB_F32, non_img, AITB_F32, B, 1024, Ni, 0, st, 0));
+  }
+  {  // omega on the query side (:104-110)
+    RUN(transpose_run(NQT, AITB_F32, NQ, AITB_F32, B, 512, 64, 1, st, rt));   // [B, 512, 64] -> [B, 64, 512]
+    aitb_gemm_desc d = gemm_base(AITB_F32, rq, 1024, 512, w->omega.w, 256, OM, 1024, 0);
+    view_plain(d, NQ, 512);
+    d.flags = AITB_EPI_BIAS;
+    d.bias = w->omega.bias;
+    d.out_scale = 1.f / (float)Ni;
+    RUN(gemm_run(&d, st));
+    RUN(group_norm_residual_run(OM, Xq, w->omega_gn.gamma, w->omega_gn.beta, B, 64, 32, 1e-5f, sums + (size_t)B * 64, OUTq, st));
+    RUN(transpose_run(OUTq, AITB_F32, non_qry, AITB_F32, B, 1024, 64, 0, st, 0));
+  }
+  AITB_REQUIRE(b.off <= workspace_bytes, "aitb_coattention_forward: internal workspace accounting error");
+  return 0;
 }
 
 size_t aitb_rpn_workspace_bytes(int B, int H, int W, int dtype) {

@@ -359,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         tmem_ld32(t_row + c0 + 32, raw);
         if (dual) tmem_ld32(t_row + BLOCK_N + c0 + 32, raw2);
       }
-      if constexpr (SPLIT) {
+      if (SPLIT || p.acc_scale != 1.f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
       }
@@ -1233,6 +1233,8 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE(d->ldo % 8 == 0, "aitb_gemm: ldo must be a multiple of 8 elements");
   AITB_REQUIRE(((uintptr_t)d->out & 31) == 0 && ((uintptr_t)d->a.ptr & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
                "aitb_gemm: pointers must be 16/32-byte aligned");
+  AITB_REQUIRE(d->out_scale == 0.f || d->out_scale == 1.f || (d->flags & AITB_EPI_LN) == 0 || split,
+               "aitb_gemm: out_scale is not applied by the LayerNorm epilogue of the non-split configurations");
   AITB_REQUIRE((d->flags & AITB_EPI_RELU_MASK) == 0 || (!split && (d->flags & (AITB_EPI_RES | AITB_EPI_LN)) == 0),
                "aitb_gemm: RELU_MASK excludes RES / LN and the split configuration");
   if (d->flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK))
@@ -1324,8 +1326,9 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     }
     const float steps = split ? 3.f * (float)(d->taps * d->k_per_tap / 16) : 0.f;
     const float steps2 = split ? 3.f * (float)(d->k_per_tap / 16) : 0.f;
-    kp.acc_scale = 1.f + comp * steps;
-    kp.acc_scale2 = 1.f + comp * steps2;
+    const float user_scale = d->out_scale != 0.f ? d->out_scale : 1.f;   // 0 = unset
+    kp.acc_scale = (1.f + comp * steps) * user_scale;
+    kp.acc_scale2 = (1.f + comp * steps2) * user_scale;
   }
 
 #define AITB_DISPATCH(BN)                                                                          \

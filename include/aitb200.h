@@ -165,6 +165,8 @@ typedef struct {
    * box[1] x box[2] = 128 positions of one image (box[1] >= map_w); M = G * ceil(map_h / box[2]) * 128 tile rows;
    * output row = g * map_h * map_w + y * map_w + x (positions outside the map are computed on zero fill and dropped) */
   int map_w, map_h;
+  /* the accumulator is multiplied by out_scale before bias / activation (0 = unset = 1) */
+  float out_scale;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
@@ -313,6 +315,23 @@ size_t aitb_rpn_workspace_bytes(int B, int H, int W, int dtype);
 int aitb_rpn_forward(const aitb_rpn_weights* w, const float* feat_nchw, int B, int H, int W, const float* base_anchors,
                      const float* im_info, float feat_stride, float* proposals, float* fg_scores, float* rpn_cls_prob,
                      float* rpn_bbox_pred, void* workspace, size_t workspace_bytes, aitb_stream_t stream);
+
+/* f3 (second half): the co-attention block in front of the RPN (`CoAttention`, in_ch 1024, c_hidden 512, residual,
+ * 'division' normalisation: lib/model/modules/blocks_coatt_transformer_sk.py:17-122, as built by CoAttentionModule,
+ * faster_rcnn_coatt_transformer_sk.py:104-124).  fp32 storage + tf32 tensor-core math (dtype must be AITB_F32).
+ *   x_img [B,1024,H,W] f32, x_qry [B,1024,8,8] f32 -> non_img [B,1024,H,W], non_qry [B,1024,8,8] */
+typedef struct {
+  int dtype, round_tf32;
+  const void* w_emb_phi;  /* [1024, 1024] = rows(emb.weight; phi.weight), tf32-rounded */
+  const float* b_emb_phi; /* [1024] */
+  aitb_linear emb, rho;   /* [512, 1024] + bias */
+  aitb_linear theta, omega; /* [1024, 512] + bias (theta.0 / omega.0) */
+  aitb_lnorm theta_gn, omega_gn; /* GroupNorm(32, 1024) weight / bias (theta.1 / omega.1) */
+} aitb_coatt_weights;
+size_t aitb_coattention_workspace_bytes(int B, int H, int W);
+int aitb_coattention_forward(const aitb_coatt_weights* w, const float* x_img, const float* x_qry, int B, int H, int W,
+                             float* non_img, float* non_qry, void* workspace, size_t workspace_bytes,
+                             aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f2  detection post-processing (test_net_voc.py:380-446)

@@ -286,3 +286,29 @@ def rpn_forward(sd, base_feat, im_info, base_anchors, feat_stride=16, pre_nms_to
     rois = proposal_layer(prob.float(), bbox.float(), im_info, base_anchors, feat_stride, pre_nms_topN, post_nms_topN,
                           nms_thresh)
     return rois, prob, bbox
+
+
+# ------------------------------------------------------------------------------------------------
+# f3 (second half): CoAttention, 'division' normalisation (lib/model/modules/blocks_coatt_transformer_sk.py:60-112)
+# ------------------------------------------------------------------------------------------------
+def coattention_forward(sd, x_img, x_qry, dtype=torch.float32):
+    """sd: emb.*, rho.*, phi.*, omega.0.*, omega.1.*, theta.0.*, theta.1.* -> (non_img, non_qry)."""
+    w = _cast(sd, dtype)
+    x_img, x_qry = x_img.to(dtype), x_qry.to(dtype)
+    bz, _, h_i, w_i = x_img.shape
+    _, _, h_q, w_q = x_qry.shape
+    emb_img = F.conv2d(x_img, w["emb.weight"], w["emb.bias"]).view(bz, 512, -1).permute(0, 2, 1).contiguous()   # :70-71
+    emb_qry = F.conv2d(x_qry, w["emb.weight"], w["emb.bias"]).view(bz, 512, -1).permute(0, 2, 1).contiguous()   # :73-74
+    rho_qry = F.conv2d(x_qry, w["rho.weight"], w["rho.bias"]).view(bz, 512, -1).permute(0, 2, 1)                 # :76-77
+    phi_img = F.conv2d(x_img, w["phi.weight"], w["phi.bias"]).view(bz, 512, -1)                                   # :79
+    co = torch.matmul(rho_qry, phi_img)                                                                          # :81
+    n_q, n_i = co.size(1), co.size(2)
+    q2i = co / n_i                                                                                               # :91
+    i2q = co.permute(0, 2, 1).contiguous() / n_q                                                                 # :92
+    non_img = torch.matmul(i2q, emb_qry).permute(0, 2, 1).contiguous().view(bz, 512, h_i, w_i)                   # :99-101
+    non_img = F.group_norm(F.conv2d(non_img, w["theta.0.weight"], w["theta.0.bias"]), 32, w["theta.1.weight"],
+                           w["theta.1.bias"], eps=1e-5) + x_img                                                  # :102-104
+    non_qry = torch.matmul(q2i, emb_img).permute(0, 2, 1).contiguous().view(bz, 512, h_q, w_q)                   # :106-108
+    non_qry = F.group_norm(F.conv2d(non_qry, w["omega.0.weight"], w["omega.0.bias"]), 32, w["omega.1.weight"],
+                           w["omega.1.bias"], eps=1e-5) + x_qry                                                  # :109-111
+    return non_img, non_qry

@@ -220,3 +220,34 @@ def test_oracle_rpn_head_matches_reference_golden():
     assert torch.allclose(bbox[:, ::3], gold["bbox_pred_s"], rtol=1e-5, atol=1e-6)
     assert torch.equal(rois[..., 0], gold["rois"][..., 0])
     assert torch.allclose(rois, gold["rois"], rtol=1e-5, atol=1e-3)
+
+
+def _coatt_inputs(seed=29, B=2, H=19, W=31):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x_img, x_qry = torch.randn(B, 1024, H, W, generator=g).relu(), torch.randn(B, 1024, 8, 8, generator=g).relu()
+    g = torch.Generator().manual_seed(seed + 1)
+    sd = {}
+    for name in ("emb", "rho", "phi"):
+        sd[name + ".weight"] = torch.randn(512, 1024, 1, 1, generator=g) * 0.03
+        sd[name + ".bias"] = torch.randn(512, generator=g) * 0.1
+    for name in ("omega", "theta"):
+        sd[name + ".0.weight"] = torch.randn(1024, 512, 1, 1, generator=g) * 0.05
+        sd[name + ".0.bias"] = torch.randn(1024, generator=g) * 0.1
+        sd[name + ".1.weight"] = torch.rand(1024, generator=g) + 0.5
+        sd[name + ".1.bias"] = torch.randn(1024, generator=g) * 0.2
+    return x_img, x_qry, sd
+
+
+def test_oracle_coattention_matches_reference_golden():
+    """row f3 (co-attention): the restatement reproduces the unmodified `B.CoAttention` (make_golden_coatt.py)."""
+    import torch
+    from conftest import load_golden
+    from oracle import head_oracle
+    gold = load_golden("coattention.pt")
+    x_img, x_qry, sd = _coatt_inputs(gold["seed"])
+    assert sorted(sd) == gold["keys"]
+    torch.set_num_threads(8)
+    non_img, non_qry = head_oracle.coattention_forward(sd, x_img, x_qry)
+    assert torch.allclose(non_img[:, ::32], gold["non_img_s"], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(non_qry[:, ::16], gold["non_qry_s"], rtol=1e-4, atol=1e-4)
