@@ -581,6 +581,9 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   }  // persistent loop over pairs
 }
 
+int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
+                const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream);
+
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
                   int round_tf) {
@@ -590,6 +593,12 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
   AITB_REQUIRE(mask_mode == 0 || mask_mode == 1, "aitb_attn_core: mask_mode must be 0 (key padding) or 1 (causal)");
   AITB_REQUIRE(n_keys >= 1 && n_keys <= kT, "aitb_attn_core: n_keys=%d out of range", n_keys);
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "aitb_attn_core: leading dimensions must be multiples of 4");
+  if ((dtype == AITB_BF16 || dtype == AITB_F32S) && getenv("AITB_ATTN_TC") != nullptr) {
+    // opt-in tcgen05 kernel (attn_tc.cu): Q K^T and P V on the 5th-generation tensor cores, TMEM accumulators, TMA
+    // operands -- correct, but measured slower than the kernels below on the benchmark shape (see its header)
+    const int rc = attn_tc_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, stream);
+    if (rc >= 0) return rc;    // -1: shape / alignment outside its envelope -> the mma.sync kernels below
+  }
   if (dtype == AITB_F32) {
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
@@ -600,32 +609,18 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
         mask_mode, n_keys, (__nv_bfloat16*)out, 0);
   } else if (dtype == AITB_BF16) {   // one-pass kernel, plain bf16 planes, persistent CTAs (128 accumulator registers per thread)
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           OnePass<false>::kSmem);
-      AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn one-pass) failed: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem((const void*)attn_core_split_kernel<false>, OnePass<false>::kSmem, once, "attn_core one-pass")) return 1;
+    const int sms = current_sm_count();
     attn_core_split_kernel<false><<<G < sms ? G : sms, kSplitThreads, OnePass<false>::kSmem, stream>>>(
         (const __nv_bfloat16*)q, ldq, 0, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, 0, w_sk, b_sk, G,
         mask_mode, n_keys, (__nv_bfloat16*)out);
   } else if (dtype == AITB_F32S) {
     AITB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "aitb_attn_core: split mode needs leading dimensions that are multiples of 8");
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_core_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           OnePass<true>::kSmem);
-      AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn split) failed: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    static SmemAttrOnce once;
+    if (ensure_dyn_smem((const void*)attn_core_split_kernel<true>, OnePass<true>::kSmem, once, "attn_core split")) return 1;
     // logical leading dimensions -> physical two-plane rows; the lo plane is one logical row width further
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = current_sm_count();
     attn_core_split_kernel<true><<<G < sms ? G : sms, kSplitThreads, OnePass<true>::kSmem, stream>>>(
         (const __nv_bfloat16*)q, 2 * ldq, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, 2 * ldkv, ldkv,
         w_sk, b_sk, G, mask_mode, n_keys, (__nv_bfloat16*)out);

@@ -490,27 +490,14 @@ int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float
   AITB_REQUIRE(G > 0 && q && k && v && w_sk && b_sk && dout && dq && dk && dv && dz && s_out, "aitb_attn_bwd: bad arguments");
   AITB_REQUIRE(q_rep >= 1 && (mask_mode == 0 || mask_mode == 1) && n_keys >= 1 && n_keys <= kBT, "aitb_attn_bwd: bad mode");
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && lddq % 2 == 0 && lddkv % 2 == 0, "aitb_attn_bwd: bad leading dimensions");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem);
-    AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn_bwd) failed: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;
+  if (ensure_dyn_smem((const void*)attn_bwd_kernel, kAttnBwdSmem, once, "attn_bwd_kernel")) return 1;
   attn_bwd_kernel<<<G, kAttnBwdThreads, kAttnBwdSmem, stream>>>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, mask_mode,
                                                                n_keys, dq, lddq, dk, dv, lddkv, dz, s_out);
   return check_launch("attn_bwd_kernel");
 }
 
-static int g_sms_bwd = 0;
-static int sms_bwd() {
-  if (g_sms_bwd == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms_bwd, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms_bwd <= 0) g_sms_bwd = 148;
-  }
-  return g_sms_bwd;
-}
+static int sms_bwd() { return current_sm_count(); }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -692,13 +679,10 @@ int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, i
     if (encode_map_f32_mn(&tmX, x, 2, dims, str, box, "wgrad X")) return 1;
   }
   const int smem = kWgStages * (kWgABytes + (bn / 32) * kWgRows * 128) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kWgStages * (kWgABytes + 8 * kWgRows * 128) + 1024 + 256);
-    AITB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(wgrad) failed: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;
+  if (ensure_dyn_smem((const void*)wgrad_tcgen05_kernel, kWgStages * (kWgABytes + 8 * kWgRows * 128) + 1024 + 256, once,
+                      "wgrad_tcgen05_kernel"))
+    return 1;
   wgrad_tcgen05_kernel<<<tiles * p.splits, kWgThreads, smem, stream>>>(tmY, tmX, p);
   return check_launch("wgrad_tcgen05_kernel");
 }

@@ -69,6 +69,36 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int ensure_dyn_smem(const void* func, int bytes, SmemAttrOnce& once, const char* what) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("%s: cudaGetDevice failed", what);
+    return 1;
+  }
+  if ((__atomic_load_n(&once.done_mask, __ATOMIC_ACQUIRE) >> dev) & 1ULL) return 0;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s, %d bytes) failed: %s", what, bytes, cudaGetErrorString(e));
+    return 1;
+  }
+  __atomic_fetch_or(&once.done_mask, 1ULL << dev, __ATOMIC_RELEASE);
+  return 0;
+}
+
+int current_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
+  }
+  return n;
+}
+
 int check_launch(const char* what) {
   ++g_launches;
   cudaError_t e = cudaGetLastError();

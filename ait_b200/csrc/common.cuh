@@ -13,6 +13,15 @@ namespace aitb {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember which devices a kernel has been configured
+// on (one process may drive several GPUs, e.g. nn.DataParallel worker threads).  Returns non-zero on failure.
+struct SmemAttrOnce {
+  unsigned long long done_mask = 0;
+};
+int ensure_dyn_smem(const void* func, int bytes, SmemAttrOnce& once, const char* what);
+// multiprocessor count of the CURRENT device (cached per device)
+int current_sm_count();
+
 #define AITB_REQUIRE(cond, ...)            \
   do {                                     \
     if (!(cond)) {                         \

@@ -1067,37 +1067,27 @@ static int encode_map(CUtensorMap* tm, int dtype, const void* ptr, int rank, con
   return 0;
 }
 
+// bf16 2-D map, 128-byte swizzle (attention operand tiles)
+int encode_map_bf16(CUtensorMap* tm, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const char* what) {
+  return encode_map(tm, AITB_BF16, ptr, 2, dims, strides_bytes, box, what);
+}
+
 // fp32 map with the "128-byte swizzle, 32-byte atom" pattern (the only layout tcgen05 accepts for MN-major tf32 operands)
 int encode_map_f32_mn(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, const char* what) {
   return encode_map(tm, AITB_F32, ptr, rank, dims, strides_bytes, box, what, false, true);
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return current_sm_count(); }
 
 template <typename T, int BLOCK_N, bool CL, bool SPLIT>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, SPLIT, CL && SPLIT>;
-  static bool attr_set = false;
+  static SmemAttrOnce once;
   auto kern = gemm_tcgen05_kernel<T, BLOCK_N, CL, SPLIT>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm<%d>) failed: %s", BLOCK_N, cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
+  if (ensure_dyn_smem((const void*)kern, Cfg::kSmemBytes, once, "gemm_tcgen05_kernel")) return 1;
   if constexpr (CL) {
     const int clusters = kp.m_tiles < num_sms() / 2 ? kp.m_tiles : num_sms() / 2;
     cudaLaunchConfig_t cfg;
@@ -1130,16 +1120,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 template <typename T, bool SPLIT>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttrOnce once;
   auto kern = gemm2_tcgen05_kernel<T, SPLIT>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm2) failed: %s", cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
+  if (ensure_dyn_smem((const void*)kern, k2SmemBytes, once, "gemm2_tcgen05_kernel")) return 1;
   const int tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg;
@@ -1167,16 +1150,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
 template <typename T, bool SPLIT>
 static int launch_gemm_ln2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
   using L = LnCfg<T, SPLIT>;
-  static bool attr_set = false;
+  static SmemAttrOnce once;
   auto kern = gemm_ln2_tcgen05_kernel<T, SPLIT>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_ln2) failed: %s", cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
+  if (ensure_dyn_smem((const void*)kern, L::kSmemBytes, once, "gemm_ln2_tcgen05_kernel")) return 1;
   const int clusters = kp.m_tiles < num_sms() / 2 ? kp.m_tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

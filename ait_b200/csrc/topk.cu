@@ -148,13 +148,9 @@ int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, voi
   if (check_launch("topk_hist_kernel")) return 1;
   topk_compact_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(scores, n_total, thr_bin, cand_count, cand);
   if (check_launch("topk_compact_kernel")) return 1;
-  static bool attr_set = false;
+  static SmemAttrOnce once;
   const int smem = kSortMax * 8;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(topk_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    AITB_REQUIRE(e == cudaSuccess, "aitb_topk_desc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (ensure_dyn_smem((const void*)topk_bitonic_kernel, smem, once, "topk_bitonic_kernel")) return 1;
   topk_bitonic_kernel<<<B, 1024, smem, stream>>>(cand_count, cand, n_total, n, order);
   if (check_launch("topk_bitonic_kernel")) return 1;
   if (n_total > kSortMax) {  // only then can an image have more candidates than the smem sort holds

@@ -174,3 +174,42 @@ def test_attn_core(dtype, mode):
                   1 if mode == "causal" else 0, 64 if mode == "causal" else 49, out)
     tol = dict(rtol=2e-3, atol=2e-3) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(out.float().cpu().double(), ref, **tol)
+
+
+@pytest.mark.parametrize("mode", ["self_pad", "causal", "cross"])
+@pytest.mark.parametrize("split", [False, True])
+def test_attn_core_tcgen05_variant(mode, split, monkeypatch):
+    """The opt-in tcgen05 attention kernel (attn_tc.cu: Q K^T and P V as tcgen05.mma with TMEM accumulators, V consumed
+    MN-major, couples of pairs per M = 128 tile) against the same fp64 reference, odd pair counts included."""
+    from ait_b200 import ops
+    monkeypatch.setenv("AITB_ATTN_TC", "1")
+    g = torch.Generator().manual_seed(7)
+    G, rep = (7, 1) if mode != "cross" else (9, 3)
+    bf = lambda x: x.to(torch.bfloat16).float()                                  # noqa: E731
+    q = torch.randn(G // rep, 64, 512, generator=g)
+    k = torch.randn(G, 64, 512, generator=g)
+    v = torch.randn(G, 64, 512, generator=g)
+    if not split:
+        q, k, v = bf(q), bf(k), bf(v)
+    w_sk, b_sk = torch.randn(512, 64, generator=g) * 0.3, torch.randn(512, generator=g) * 0.1
+    if mode == "causal":
+        mask = torch.tril(torch.ones(64, 64))[None, None]
+    else:
+        mask = (torch.arange(64) < 49).float()[None, None, None, :]
+    ref = _attn_ref(q.double(), k.double(), v.double(), w_sk.double(), b_sk.double(), mask)
+    kv = torch.cat([k, v], dim=2).contiguous()
+    if split:
+        qd, kvd = ops.split_planes(q).to(DEV), ops.split_planes(kv).to(DEV)
+        out = torch.zeros((G * 64, 128), dtype=torch.bfloat16, device=DEV)
+        ops.attn_core(qd, 512, rep, kvd, kvd.view(-1)[512:], 1024, w_sk.to(DEV), b_sk.to(DEV), G,
+                      1 if mode == "causal" else 0, 64 if mode == "causal" else 49, out, split=True)
+        got = ops.join_planes(out).cpu().view(G, 64, 64)
+        tol = dict(rtol=1e-4, atol=1e-4)
+    else:
+        qd, kvd = q.to(DEV, torch.bfloat16), kv.to(DEV, torch.bfloat16)
+        out = torch.zeros((G, 64, 64), dtype=torch.bfloat16, device=DEV)
+        ops.attn_core(qd, 512, rep, kvd, kvd.view(-1)[512:], 1024, w_sk.to(DEV), b_sk.to(DEV), G,
+                      1 if mode == "causal" else 0, 64 if mode == "causal" else 49, out)
+        got = out.float().cpu()
+        tol = dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(got.double(), ref, **tol)
