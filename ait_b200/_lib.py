@@ -15,8 +15,8 @@ AITB_F32, AITB_BF16, AITB_F32S = 0, 1, 2
 #   "bf16"  AITB_BF16  bf16 storage and math
 MODES = {"fp32": AITB_F32S, "tf32": AITB_F32, "bf16": AITB_BF16}
 
-EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK = (
-    1, 2, 4, 8, 16, 32, 64, 128, 256, 512)
+EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK, EPI_RES_ROW_M = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
 
 
 class View4(C.Structure):

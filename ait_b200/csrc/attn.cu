@@ -152,7 +152,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnThreads, 4)
 attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
                  int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
-                 T* __restrict__ out, int round_tf) {
+                 T* __restrict__ out, int round_tf, int kv_rows) {
   __shared__ __align__(16) __half Qs[kT * kHS];
   __shared__ __align__(16) __half Ks[kT * kHS];
   __shared__ __align__(16) __half Vs[kT * kHS];
@@ -164,8 +164,10 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
   const T* qg = q + (size_t)(grp / q_rep) * kT * ldq;
-  const T* kg = k + (size_t)grp * kT * ldkv;
-  const T* vg = v + (size_t)grp * kT * ldkv;
+  // kv_rows = rows per pair in the K / V buffers: 64, or 49 for the compact encoder output (the 64-row tile then
+  // overlaps the next pair's first rows, which the key mask n_keys <= kv_rows discards)
+  const T* kg = k + (size_t)grp * kv_rows * ldkv;
+  const T* vg = v + (size_t)grp * kv_rows * ldkv;
 
   // ---------------- pass A: s = mean_T(sum_h O_h) via column sums of P_h
   float s_part = 0.f;  // thread (half = tid >> 6, c = tid & 63)
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1)
 attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, int q_rep,
                        const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int ldkv, int kv_lo,
                        const float* __restrict__ w_sk, const float* __restrict__ b_sk, int G, int mask_mode, int n_keys,
-                       __nv_bfloat16* __restrict__ out) {
+                       __nv_bfloat16* __restrict__ out, int kv_rows) {
   constexpr int kBufBytes = OnePass<SPLIT>::kBufBytes;
   constexpr int kP = SPLIT ? 2 : 1;   // planes per operand
   extern __shared__ __align__(128) uint8_t smem_attn[];
@@ -362,8 +364,8 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
 
   auto issue_head = [&](int grp, int h, int slot) {  // cp.async the six planes of head h of pair grp into `slot`
     const __nv_bfloat16* qg = q + (size_t)(grp / q_rep) * kT * ldq;
-    const __nv_bfloat16* kg = k + (size_t)grp * kT * ldkv;
-    const __nv_bfloat16* vg = v + (size_t)grp * kT * ldkv;
+    const __nv_bfloat16* kg = k + (size_t)grp * kv_rows * ldkv;
+    const __nv_bfloat16* vg = v + (size_t)grp * kv_rows * ldkv;
     const uint32_t base = buf0 + slot * kBufBytes;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -582,39 +584,44 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
 }
 
 int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
-                const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream);
+                const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
+                int kv_rows);
 
+// kv_rows: rows per pair in the K / V buffers (64; 49 = compact encoder rows, needs mask_mode 0 and n_keys <= 49, and
+// 64 - kv_rows readable finite rows after the last pair)
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
-                  int round_tf) {
+                  int round_tf, int kv_rows) {
   AITB_REQUIRE(G > 0, "aitb_attn_core: G must be positive");
   AITB_REQUIRE(q && k && v && w_sk && b_sk && out, "aitb_attn_core: null pointer");
   AITB_REQUIRE(q_rep >= 1, "aitb_attn_core: q_rep must be >= 1");
   AITB_REQUIRE(mask_mode == 0 || mask_mode == 1, "aitb_attn_core: mask_mode must be 0 (key padding) or 1 (causal)");
   AITB_REQUIRE(n_keys >= 1 && n_keys <= kT, "aitb_attn_core: n_keys=%d out of range", n_keys);
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "aitb_attn_core: leading dimensions must be multiples of 4");
+  AITB_REQUIRE(kv_rows == kT || (kv_rows > 0 && kv_rows < kT && mask_mode == 0 && n_keys <= kv_rows),
+               "aitb_attn_core: compact K/V rows need the key-padding mask with n_keys <= kv_rows");
   if ((dtype == AITB_BF16 || dtype == AITB_F32S) && getenv("AITB_ATTN_TC") != nullptr) {
     // opt-in tcgen05 kernel (attn_tc.cu): Q K^T and P V on the 5th-generation tensor cores, TMEM accumulators, TMA
     // operands -- correct, but measured slower than the kernels below on the benchmark shape (see its header)
-    const int rc = attn_tc_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, stream);
+    const int rc = attn_tc_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, stream, kv_rows);
     if (rc >= 0) return rc;    // -1: shape / alignment outside its envelope -> the mma.sync kernels below
   }
   if (dtype == AITB_F32) {
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
-                                                            (float*)out, round_tf);
+                                                            (float*)out, round_tf, kv_rows);
   } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || getenv("AITB_ATTN_TWO_PASS") != nullptr)) {
     // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch)
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
-        mask_mode, n_keys, (__nv_bfloat16*)out, 0);
+        mask_mode, n_keys, (__nv_bfloat16*)out, 0, kv_rows);
   } else if (dtype == AITB_BF16) {   // one-pass kernel, plain bf16 planes, persistent CTAs (128 accumulator registers per thread)
     static SmemAttrOnce once;
     if (ensure_dyn_smem((const void*)attn_core_split_kernel<false>, OnePass<false>::kSmem, once, "attn_core one-pass")) return 1;
     const int sms = current_sm_count();
     attn_core_split_kernel<false><<<G < sms ? G : sms, kSplitThreads, OnePass<false>::kSmem, stream>>>(
         (const __nv_bfloat16*)q, ldq, 0, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, 0, w_sk, b_sk, G,
-        mask_mode, n_keys, (__nv_bfloat16*)out);
+        mask_mode, n_keys, (__nv_bfloat16*)out, kv_rows);
   } else if (dtype == AITB_F32S) {
     AITB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "aitb_attn_core: split mode needs leading dimensions that are multiples of 8");
     static SmemAttrOnce once;
@@ -623,7 +630,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     const int sms = current_sm_count();
     attn_core_split_kernel<true><<<G < sms ? G : sms, kSplitThreads, OnePass<true>::kSmem, stream>>>(
         (const __nv_bfloat16*)q, 2 * ldq, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, 2 * ldkv, ldkv,
-        w_sk, b_sk, G, mask_mode, n_keys, (__nv_bfloat16*)out);
+        w_sk, b_sk, G, mask_mode, n_keys, (__nv_bfloat16*)out, kv_rows);
   } else {
     set_error("aitb_attn_core: bad dtype %d", dtype);
     return 1;

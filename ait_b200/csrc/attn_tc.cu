@@ -60,6 +60,7 @@ struct TcParams {
   int q_rep;        // pairs sharing one Q block
   int mask_mode, n_keys;
   int q_lo, kv_lo;  // split: element offset of the lo plane inside a row (0 otherwise)
+  int kv_rows;      // rows per pair in the K / V buffers (64, or 49: compact encoder rows)
   const float* w_sk;
   const float* b_sk;
   __nv_bfloat16* out;
@@ -154,8 +155,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int qc = h * 64 + pl * p.q_lo, kc = h * 64 + pl * p.kv_lo;
           tma_load_2d(sq + pl * kTile, &tmQ, &qk_full[buf], qc, qrow0);
           tma_load_2d(sq + pl * kTile + 64 * 128, &tmQ, &qk_full[buf], qc, qrow1);
-          tma_load_2d(sk + pl * kTile, &tmK, &qk_full[buf], kc, pair0 * 64);
-          tma_load_2d(sk + pl * kTile + 64 * 128, &tmK, &qk_full[buf], kc, pair1 * 64);
+          tma_load_2d(sk + pl * kTile, &tmK, &qk_full[buf], kc, pair0 * p.kv_rows);
+          tma_load_2d(sk + pl * kTile + 64 * 128, &tmK, &qk_full[buf], kc, pair1 * p.kv_rows);
         }
         mbar_wait(v_empty, (n & 1) ^ 1);
         uint8_t* sv = smem + Cfg::kOffV;
@@ -163,8 +164,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int pl = 0; pl < kP; ++pl) {
           const int vc = h * 64 + pl * p.kv_lo;
-          tma_load_2d(sv + pl * kVTile, &tmV, v_full, vc, pair0 * 64);
-          tma_load_2d(sv + pl * kVTile + 64 * 128, &tmV, v_full, vc, pair1 * 64);
+          tma_load_2d(sv + pl * kVTile, &tmV, v_full, vc, pair0 * p.kv_rows);
+          tma_load_2d(sv + pl * kVTile + 64 * 128, &tmV, v_full, vc, pair1 * p.kv_rows);
         }
       }
     }
@@ -392,7 +393,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // q / k / v: bf16 matrices (split: two planes per row, the lo plane `ld` LOGICAL elements further); ldq / ldkv are
 // LOGICAL row widths like in attn_core_run.  Returns -1 when this kernel does not apply (caller falls back).
 int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
-                const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream) {
+                const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
+                int kv_rows) {
   const bool split = dtype == AITB_F32S;
   if (dtype != AITB_BF16 && !split) return -1;
   if (ldq % 8 != 0 || ldkv % 8 != 0) return -1;
@@ -407,7 +409,7 @@ int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v,
     if (encode_map_bf16(&tmQ, q, dims, str, box, "attention Q")) return 1;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)64 * 8 * pl + (split ? (uint64_t)(ldkv - 512) : 0), (uint64_t)G * 64};
+    const uint64_t dims[2] = {(uint64_t)64 * 8 * pl + (split ? (uint64_t)(ldkv - 512) : 0), (uint64_t)G * kv_rows};
     const uint64_t str[1] = {(uint64_t)ldkv * pl * 2};
     if (encode_map_bf16(&tmK, k, dims, str, box, "attention K")) return 1;
     if (encode_map_bf16(&tmV, v, dims, str, box, "attention V")) return 1;
@@ -420,6 +422,7 @@ int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v,
   p.n_keys = n_keys;
   p.q_lo = split ? ldq : 0;
   p.kv_lo = split ? ldkv : 0;
+  p.kv_rows = kv_rows;
   p.w_sk = w_sk;
   p.b_sk = b_sk;
   p.out = (__nv_bfloat16*)out;

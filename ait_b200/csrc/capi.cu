@@ -27,7 +27,7 @@ int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H,
                       int pw, int sampling_ratio, float* gfeat, cudaStream_t stream);
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
-                  int round_tf = 0);
+                  int round_tf = 0, int kv_rows = 64);
 int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat, const float* w_bbox,
                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
@@ -354,12 +354,15 @@ static int side_stream(SideStream** out) {
 // AIT: Transformer.forward (system/Models.py:231-280) on token-major inputs
 //   pooled [bp*49, 1024], qtok [B*64, 1024]  ->  hb.AIT [bp*64, 1024]
 // ---------------------------------------------------------------------------------------------
+// out_rows: rows of every 64-token group that are stored (49 = drop the encoder's dead pad rows);
+// kv_rows: rows per pair in the K / V buffers
 static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* qbuf, int ldq, int q_rep,
                      const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode, int n_keys, void* ao,
-                     const void* res, int res_rep, void* out, cudaStream_t st, float* rstd = nullptr) {
+                     const void* res, int res_rep, void* out, cudaStream_t st, float* rstd = nullptr, int out_rows = 64,
+                     int kv_rows = 64) {
   const int dt = w->dtype;
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
-                    w->round_tf32));
+                    w->round_tf32, kv_rows));
   // fc (64 -> 512, no bias) + residual + LayerNorm   (SubLayers.py:97-100)
   aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 512, out, 512, w->round_tf32);
   view_plain(d, ao, 64);
@@ -371,6 +374,11 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   d.gamma = m.ln.gamma;
   d.beta = m.ln.beta;
   d.ln_rstd = rstd;
+  if (out_rows != 64) {   // compaction: the residual stays indexed by the 64-row GEMM row
+    d.rows_in = 64;
+    d.rows_out = out_rows;
+    d.flags |= AITB_EPI_RES_ROW_M;
+  }
   return gemm_run(&d, st);
 }
 
@@ -423,10 +431,14 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
 
 // `query_ready` (optional): event recorded on the side stream after ait_query_side; waited on before the
 // cross attention.  NULL = the query side already ran on `st`.
+// compact: after the encoder self-attention the 15 pad rows of every pair are dead (they are masked as keys
+// everywhere and never read as queries again: SURVEY fact 7, bit-identical output), so the encoder FFN and the
+// cross-attention K / V projection run on 49 rows per pair.  The training path keeps the 64-row layout.
 static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st,
-                    cudaEvent_t query_ready) {
+                    cudaEvent_t query_ready, bool compact = true) {
   const int dt = w->dtype, eb = esize(dt), cb = colsize(dt), rt = w->round_tf32;
   const int bp = B * P, R = bp * 64;
+  const int er = compact ? 49 : 64, RE = bp * er;   // encoder rows per pair / in total after the self-attention block
   // ---- encoder input: enc_emb (1x1 conv 1024->512 + bias) on the 49 real rows, + pos, LayerNorm
   {
     aitb_gemm_desc d = gemm_base(dt, bp * 49, 512, 1024, w->enc_emb.w, 512, hb.X1, 512, rt);
@@ -450,11 +462,12 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
     RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
-                  hb.X2, st, hb.r_X2));
+                  hb.X2, st, hb.r_X2, er));
   }
-  RUN(ffn_block(w, w->enc_ffn, hb.X2, R, hb.Hh, hb.ENC, st, hb.r_ENC));
-  if (enc_tap) {
-    cudaError_t e = cudaMemcpyAsync(enc_tap, hb.ENC, (size_t)R * 512 * eb, cudaMemcpyDeviceToDevice, st);
+  RUN(ffn_block(w, w->enc_ffn, hb.X2, RE, hb.Hh, hb.ENC, st, hb.r_ENC));
+  if (enc_tap) {   // [bp, 64, 512] tap: the rows that exist (pad rows of the tap are left untouched when compact)
+    cudaError_t e = cudaMemcpy2DAsync(enc_tap, (size_t)64 * 512 * eb, hb.ENC, (size_t)er * 512 * eb, (size_t)er * 512 * eb, bp,
+                                      cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "enc tap copy failed: %s", cudaGetErrorString(e));
   }
   if (query_ready) {
@@ -464,12 +477,16 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
   // ---- cross attention: K, V from the encoder output of each pair, Q shared by the unit's P pairs
   {
     const uint8_t* wkv = (const uint8_t*)w->dec_enc.w_qkv + (size_t)512 * 512 * eb;
-    aitb_gemm_desc d = gemm_base(dt, R, 1024, 512, wkv, 256, hb.KVc, 1024, rt);
+    aitb_gemm_desc d = gemm_base(dt, RE, 1024, 512, wkv, 256, hb.KVc, 1024, rt);
     view_plain(d, hb.ENC, 512);
     RUN(gemm_run(&d, st));
+    if (compact) {   // the last pair's 64-row K / V tile reads 15 rows past the compact buffer: keep them finite
+      cudaError_t e = cudaMemsetAsync((uint8_t*)hb.KVc + (size_t)RE * 1024 * eb, 0, (size_t)(64 - er) * 1024 * eb, st);
+      AITB_REQUIRE(e == cudaSuccess, "KV pad memset failed: %s", cudaGetErrorString(e));
+    }
     const uint8_t* kv = (const uint8_t*)hb.KVc;
     RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * cb, 1024, bp, 0, 49, hb.AOc, hb.T1, P, hb.D1, st,
-                  hb.r_D1));
+                  hb.r_D1, 64, er));
   }
   RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh2, hb.DEC, st, hb.r_DEC));
   // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
@@ -686,7 +703,7 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
   }
   RUN(transpose_run(x_query, AITB_F32, hb.qtok, AITB_F32, B, 1024, 64, 1, st, w->round_tf32));
   RUN(ait_query_side(w, hb, B, st));
-  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr));
+  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr, false));
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
     RUN(transpose_run((const float*)hb.AIT + (size_t)g0 * 64 * 1024, AITB_F32, out_nchw + (size_t)g0 * 1024 * 64, AITB_F32,

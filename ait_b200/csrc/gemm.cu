@@ -92,7 +92,9 @@ __device__ __forceinline__ int out_row_of(const GemmKParams& p, int m, bool* ok)
   }
   *ok = m < p.M;
   const int mm = *ok ? m : 0;
-  return (mm / p.rows_in) * p.rows_out + (mm % p.rows_in);
+  const int grp = mm / p.rows_in, r = mm - grp * p.rows_in;
+  if (r >= p.rows_out) *ok = false;   // rows_out < rows_in: only the first rows_out rows of every group are stored
+  return *ok ? grp * p.rows_out + r : 0;
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -159,7 +161,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     const int orow = out_row_of(p, m, &ok);
     optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
     int rrow = 0;
-    if (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) rrow = ((orow / p.res_div) / p.res_rep) * p.res_div + (orow % p.res_div);
+    if (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) {
+      const int rb = (p.flags & AITB_EPI_RES_ROW_M) ? (ok ? m : 0) : orow;   // residual indexed by GEMM row or by output row
+      rrow = ((rb / p.res_div) / p.res_rep) * p.res_div + (rb % p.res_div);
+    }
     rptr[it] = res + (size_t)rrow * p.ldr + n0 + piece * (16 / (int)sizeof(T));
     vmask |= (ok ? 1u : 0u) << it;
   }
@@ -1204,8 +1209,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   AITB_REQUIRE((d->flags & AITB_EPI_LN) == 0 || (d->block_n == 512 && d->N == 512),
                "aitb_gemm: the LayerNorm epilogue needs block_n == N == 512");
   AITB_REQUIRE((d->flags & AITB_EPI_LN) != 0 || d->block_n != 512, "aitb_gemm: block_n 512 is the LayerNorm variant");
-  AITB_REQUIRE(d->rows_in > 0 && d->rows_out >= d->rows_in, "aitb_gemm: bad row remap %d->%d", d->rows_in,
-               d->rows_out);
+  AITB_REQUIRE(d->rows_in > 0 && d->rows_out > 0, "aitb_gemm: bad row remap %d->%d", d->rows_in, d->rows_out);
   AITB_REQUIRE(d->ldo % 8 == 0, "aitb_gemm: ldo must be a multiple of 8 elements");
   AITB_REQUIRE(((uintptr_t)d->out & 31) == 0 && ((uintptr_t)d->a.ptr & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
                "aitb_gemm: pointers must be 16/32-byte aligned");

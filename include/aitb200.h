@@ -121,8 +121,9 @@ enum {
   AITB_EPI_RES_RELU = 128, /* relu applied AFTER the residual add (bottleneck tail) */
   AITB_EPI_DUAL = 256,     /* two accumulators (see `dual`): v = f(acc0 + bias) + f(acc1 + bias2),
                               f = the RELU / SQUARE flags (SKBlock: relu(conv1x1)^2 + relu(conv3x3)^2) */
-  AITB_EPI_RELU_MASK = 512 /* backward of ReLU: v = residual[res_row, n] > 0 ? v : 0  (`res` = the saved activation;
+  AITB_EPI_RELU_MASK = 512, /* backward of ReLU: v = residual[res_row, n] > 0 ? v : 0  (`res` = the saved activation;
                               excludes RES / LN / split) */
+  AITB_EPI_RES_ROW_M = 1024 /* the residual row is derived from the GEMM row m instead of the (remapped) output row */
 };
 
 typedef struct {
@@ -141,7 +142,8 @@ typedef struct {
   int flags;
   void* out;
   int ldo;
-  int rows_in, rows_out; /* out_row = (m / rows_in) * rows_out + m % rows_in */
+  int rows_in, rows_out; /* out_row = (m / rows_in) * rows_out + m % rows_in; with rows_out < rows_in only the first
+                            rows_out rows of every group of rows_in are stored (compaction) */
   const float* bias;
   const void* res;
   int ldr;
