@@ -251,3 +251,93 @@ def test_oracle_coattention_matches_reference_golden():
     non_img, non_qry = head_oracle.coattention_forward(sd, x_img, x_qry)
     assert torch.allclose(non_img[:, ::32], gold["non_img_s"], rtol=1e-4, atol=1e-4)
     assert torch.allclose(non_qry[:, ::16], gold["non_qry_s"], rtol=1e-4, atol=1e-4)
+
+
+def _target_inputs(gold):
+    import torch
+    from oracle import target_oracle as T
+    B, A, H, W, R = gold["shape"]
+    gt, nb = T.synth_gt_boxes(gold["seeds"]["gt"], B)
+    rois = T.synth_rois(gold["seeds"]["rois"], B, R, gt)
+    im_info = torch.tensor([[300.0, 500.0, 1.0]] * B)
+    return gt, nb, rois, im_info
+
+
+def _loss_inputs(gold):
+    import torch
+    B, A, H, W, R = gold["shape"]
+    g = torch.Generator().manual_seed(gold["seeds"]["loss"])
+    return (torch.randn(B, 2 * A, H, W, generator=g), 0.4 * torch.randn(B, 4 * A, H, W, generator=g),
+            torch.randn(B * 128, 2, generator=g), 0.8 * torch.randn(B * 128, 4, generator=g))
+
+
+def test_oracle_target_layers_match_reference_golden():
+    """row f4: the restated `_AnchorTargetLayer` / `_ProposalTargetLayer` consume numpy's global stream like the
+    unmodified reference and reproduce its outputs bit for bit (tests/golden/make_golden_targets.py)."""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from oracle import target_oracle as T
+    gold = load_golden("targets.pt")
+    gt, nb, rois, im_info = _target_inputs(gold)
+    B, A, H, W, R = gold["shape"]
+    np.random.seed(gold["seeds"]["anchor_np"])
+    out = T.anchor_target(gold["anchors"], H, W, 16, gt, im_info)
+    for got, ref in zip(out, gold["anchor_target"]):
+        assert torch.equal(got, ref)
+    np.random.seed(gold["seeds"]["proposal_np"])
+    out = T.proposal_target(rois, gt)
+    for got, ref in zip(out, gold["proposal_target"]):
+        assert torch.equal(got, ref)
+
+
+def test_oracle_losses_match_reference_golden():
+    """row f4: the five training losses and their gradients w.r.t. the network outputs."""
+    import torch
+    from conftest import load_golden
+    from oracle import target_oracle as T
+    gold = load_golden("targets.pt")
+    B = gold["shape"][0]
+    rpn_cls_score, rpn_bbox_pred, score, bbox_pred = [t.requires_grad_() for t in _loss_inputs(gold)]
+    a, p = gold["anchor_target"], gold["proposal_target"]
+    l_rc, l_rb = T.rpn_losses(rpn_cls_score, rpn_bbox_pred, *a)
+    l_c, l_m, l_b = T.rcnn_losses(score, bbox_pred, p[1], p[2], p[3], p[4], B, margin=gold["margin"])
+    for got, key in ((l_rc, "rpn_cls"), (l_rb, "rpn_box"), (l_c, "cls"), (l_m, "margin"), (l_b, "bbox")):
+        assert torch.allclose(got, gold["losses"][key], rtol=1e-6, atol=0), key
+    (l_rc + l_rb + l_c + l_m + l_b).backward()
+    for t, key in ((rpn_cls_score, "rpn_cls_score"), (rpn_bbox_pred, "rpn_bbox_pred"), (score, "score"),
+                   (bbox_pred, "bbox_pred")):
+        assert torch.allclose(t.grad, gold["grads"][key], rtol=1e-5, atol=1e-9), key
+
+
+def test_oracle_target_layers_vs_reference_live():
+    """Other shapes / seeds against the reference itself where /root/reference exists (sub-sampling of both fg and
+    bg anchors, images without foreground rois)."""
+    import numpy as np
+    import pytest
+    import torch
+    from oracle import ref_import, target_oracle as T
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ref_import.install()
+    from model.rpn.anchor_target_layer import _AnchorTargetLayer
+    from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+    at, pt = _AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2]), _ProposalTargetLayer(2)
+    for seed, B, H, W, imh, imw, n_max in ((1, 2, 38, 63, 600.0, 1000.0, 6), (2, 4, 25, 40, 400.0, 640.0, 14)):
+        gt, nb = T.synth_gt_boxes(seed, B, im_h=imh, im_w=imw, n_min=1, n_max=n_max)
+        if seed == 2:
+            gt[1, :, :4] *= 0.1          # tiny boxes: few foreground rois / anchors in image 1
+        rois = T.synth_rois(seed + 100, B, 300, gt, im_h=imh, im_w=imw)
+        im_info = torch.tensor([[imh, imw, 1.0]] * B)
+        np.random.seed(seed)
+        ref = at((torch.zeros(B, 18, H, W), gt, im_info, nb))
+        np.random.seed(seed)
+        got = T.anchor_target(at._anchors, H, W, 16, gt, im_info)
+        for g_, r_ in zip(got, ref):
+            assert torch.equal(g_, r_)
+        np.random.seed(seed + 1)
+        ref = pt(rois, gt, nb)
+        np.random.seed(seed + 1)
+        got = T.proposal_target(rois, gt)
+        for g_, r_ in zip(got, ref):
+            assert torch.equal(g_, r_)
