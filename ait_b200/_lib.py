@@ -147,6 +147,14 @@ SIGNATURES = {
     "aitb_ait_forward_train": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "aitb_ait_backward": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _sz, C.POINTER(AITGrads), _vp, _vp, _vp, _sz,
                                _vp]),
+    "aitb_anchor_target_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "aitb_anchor_target_assign": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "aitb_anchor_target_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_proposal_target_assign": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_proposal_target_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_rpn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_rcnn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,278 @@
+"""Training-only samplers and losses around the head, on the device.
+
+Drop-ins for the reference's
+  `_AnchorTargetLayer`   (lib/model/rpn/anchor_target_layer.py:33-199)          -> `AnchorTargetLayer`
+  `_ProposalTargetLayer` (lib/model/rpn/proposal_target_layer_cascade.py:20-220) -> `ProposalTargetLayer`
+  the RPN loss lines of `_RPN.forward` (lib/model/rpn/rpn.py:99-126)            -> `rpn_losses`
+  the detection-loss lines of `_fasterRCNN.forward`
+  (lib/model/faster_rcnn/faster_rcnn_coatt_transformer_sk.py:334-361)           -> `rcnn_losses`
+  `_smooth_l1_loss` (lib/model/utils/net_utils.py:75-89) lives inside both loss kernels.
+
+Random sub-sampling.  The reference draws from numpy's GLOBAL generator with data-dependent lengths
+(`np.random.permutation(fg_inds.size(0))`, ...), which forces one device->host read of the per-image candidate
+counts (the reference pays the same synchronisation in `.numel()` / `nonzero`).  `rng="numpy"` (default) makes
+exactly the reference's calls in the reference's order, so after `np.random.seed(s)` the layers pick the same
+anchors and rois as the reference, bit for bit.  The candidate lists never leave the device: the host only sends
+RANKS (positions in the ascending candidate lists), 128 ints or a byte mask per image.
+`rng=<np.random.Generator>` draws from a private generator instead (same distribution, independent stream).
+
+There is no CPU fallback: CPU tensors raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .proposal import generate_anchors
+
+# cfg.TRAIN.* (lib/model/utils/config.py:23,81-158)
+TRAIN_CFG = dict(BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.1,
+                 BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0), BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2),
+                 BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0), BBOX_NORMALIZE_TARGETS_PRECOMPUTED=True,
+                 RPN_POSITIVE_OVERLAP=0.7, RPN_NEGATIVE_OVERLAP=0.3, RPN_CLOBBER_POSITIVES=False,
+                 RPN_FG_FRACTION=0.5, RPN_BATCHSIZE=256, RPN_BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0),
+                 RPN_POSITIVE_WEIGHT=-1.0, MARGIN=-0.3)
+
+
+def _rng(rng):
+    if rng == "numpy":
+        return np.random           # the module-level functions share the global MT19937 stream with the reference
+    if isinstance(rng, np.random.Generator):
+        class _G:                  # same call names on a private generator
+            permutation = staticmethod(rng.permutation)
+            rand = staticmethod(lambda n: rng.random(n))
+        return _G
+    raise RuntimeError("rng must be \"numpy\" (the reference's global stream) or a numpy.random.Generator")
+
+
+class AnchorTargetLayer(nn.Module):
+    """forward(input) with input = (rpn_cls_score [B,2A,H,W], gt_boxes [B,K,5], im_info [B,3], num_boxes) ->
+    [labels [B,1,A*H,W], bbox_targets [B,4A,H,W], bbox_inside_weights, bbox_outside_weights] (CUDA fp32)."""
+
+    def __init__(self, feat_stride, scales, ratios, cfg=None, rng="numpy"):
+        super().__init__()
+        self._feat_stride = feat_stride
+        self._scales = scales
+        self.register_buffer("_anchors", torch.from_numpy(
+            generate_anchors(scales=np.array(scales), ratios=np.array(ratios))).float(), persistent=False)
+        self._num_anchors = self._anchors.size(0)
+        self._allowed_border = 0
+        self.cfg = dict(TRAIN_CFG, **(cfg or {}))
+        self.rng = rng
+        if self.cfg["RPN_POSITIVE_WEIGHT"] >= 0:
+            raise RuntimeError("AnchorTargetLayer: only the uniform weighting (RPN_POSITIVE_WEIGHT < 0) exists in the "
+                               "reference (anchor_target_layer.py:162-171 leaves the other branch undefined)")
+
+    def forward(self, input):
+        rpn_cls_score, gt_boxes, im_info = input[0], input[1], input[2]
+        lib = L.load()
+        ops._need_cuda(gt_boxes, im_info)
+        cfg = self.cfg
+        dev = gt_boxes.device
+        H, W = int(rpn_cls_score.size(2)), int(rpn_cls_score.size(3))
+        A = self._num_anchors
+        gt = gt_boxes.contiguous().float()
+        info = im_info.contiguous().float()
+        B, K = gt.shape[0], gt.shape[1]
+        total = A * H * W
+        base = self._anchors.to(dev)
+        labels = torch.empty((B, total), dtype=torch.int8, device=dev)
+        argmax = torch.empty((B, total), dtype=torch.int32, device=dev)
+        counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        ws_bytes = lib.aitb_anchor_target_workspace_bytes(B, A, H, W, K)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        L.check(lib.aitb_anchor_target_assign(L.ptr(base), L.ptr(gt), L.ptr(info), B, A, H, W, K, float(self._feat_stride),
+                                              float(cfg["RPN_NEGATIVE_OVERLAP"]), float(cfg["RPN_POSITIVE_OVERLAP"]),
+                                              1 if cfg["RPN_CLOBBER_POSITIVES"] else 0, L.ptr(labels), L.ptr(argmax),
+                                              L.ptr(counts), L.ptr(ws), ws_bytes, L.stream_ptr()))
+        # the one host round trip: (#fg, #bg) per image decide how many random numbers the reference draws (:130-152)
+        cnt = counts.cpu().numpy()
+        rnd = _rng(self.rng)
+        num_fg = int(cfg["RPN_FG_FRACTION"] * cfg["RPN_BATCHSIZE"])
+        ld = int(max(1, cnt.max()))
+        drop = np.zeros((B, 2, ld), dtype=np.uint8)
+        any_drop = False
+        for i in range(B):
+            n_f, n_b = int(cnt[i, 0]), int(cnt[i, 1])
+            fg_left = n_f
+            if n_f > num_fg:
+                perm = rnd.permutation(n_f)
+                drop[i, 0, perm[:n_f - num_fg]] = 1
+                fg_left = num_fg
+                any_drop = True
+            num_bg = cfg["RPN_BATCHSIZE"] - fg_left
+            if n_b > num_bg:
+                perm = rnd.permutation(n_b)
+                drop[i, 1, perm[:n_b - num_bg]] = 1
+                any_drop = True
+        drop_d = torch.from_numpy(drop).to(dev, non_blocking=False) if any_drop else None
+        n_examples = torch.empty((B,), dtype=torch.int32, device=dev)
+        labels_out = torch.empty((B, 1, A * H, W), dtype=torch.float32, device=dev)
+        targets = torch.empty((B, 4 * A, H, W), dtype=torch.float32, device=dev)
+        inside = torch.empty_like(targets)
+        outside = torch.empty_like(targets)
+        L.check(lib.aitb_anchor_target_finish(L.ptr(base), L.ptr(gt), B, A, H, W, K, float(self._feat_stride), L.ptr(labels),
+                                              L.ptr(argmax), L.ptr(drop_d), ld, float(cfg["RPN_BBOX_INSIDE_WEIGHTS"][0]),
+                                              L.ptr(n_examples), L.ptr(labels_out), L.ptr(targets), L.ptr(inside),
+                                              L.ptr(outside), L.stream_ptr()))
+        return [labels_out, targets, inside, outside]
+
+
+class ProposalTargetLayer(nn.Module):
+    """forward(all_rois [B,R,5], gt_boxes [B,K,5], num_boxes) -> rois [B,128,5], labels [B,128], bbox_targets,
+    bbox_inside_weights, bbox_outside_weights [B,128,4] (CUDA fp32)."""
+
+    def __init__(self, nclasses, cfg=None, rng="numpy"):
+        super().__init__()
+        self._num_classes = nclasses
+        self.cfg = dict(TRAIN_CFG, **(cfg or {}))
+        self.rng = rng
+
+    def forward(self, all_rois, gt_boxes, num_boxes=None):
+        lib = L.load()
+        ops._need_cuda(all_rois, gt_boxes)
+        cfg = self.cfg
+        dev = gt_boxes.device
+        rois = all_rois.contiguous().float()
+        gt = gt_boxes.contiguous().float()
+        B, R, K = rois.shape[0], rois.shape[1], gt.shape[1]
+        if rois.shape[2] != 5 or gt.shape[2] != 5 or gt.shape[0] != B:
+            raise RuntimeError("ProposalTargetLayer: expected all_rois [B,R,5] and gt_boxes [B,K,5]")
+        N = R + K
+        S = int(cfg["BATCH_SIZE"] / 1)                                   # num_images = 1 (:47-48)
+        fg_per_image = int(np.round(cfg["FG_FRACTION"] * S)) or 1
+        max_ov = torch.empty((B, N), dtype=torch.float32, device=dev)
+        assign = torch.empty((B, N), dtype=torch.int32, device=dev)
+        cls = torch.empty((B, N), dtype=torch.int8, device=dev)
+        counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        L.check(lib.aitb_proposal_target_assign(L.ptr(rois), L.ptr(gt), B, R, K, float(cfg["FG_THRESH"]),
+                                                float(cfg["BG_THRESH_HI"]), float(cfg["BG_THRESH_LO"]), L.ptr(max_ov),
+                                                L.ptr(assign), L.ptr(cls), L.ptr(counts), L.stream_ptr()))
+        cnt = counts.cpu().numpy()                                        # the one host round trip (see module doc)
+        rnd = _rng(self.rng)
+        picks = np.zeros((B, S), dtype=np.int32)
+        n_fg_pick = np.zeros((B,), dtype=np.int32)
+        for i in range(B):                                                # :154-199, the same draws in the same order
+            nf, nb = int(cnt[i, 0]), int(cnt[i, 1])
+            if nf > 0 and nb > 0:
+                fg_this = min(fg_per_image, nf)
+                picks[i, :fg_this] = rnd.permutation(nf)[:fg_this]
+                picks[i, fg_this:] = np.floor(rnd.rand(S - fg_this) * nb)
+            elif nf > 0:
+                fg_this = S
+                picks[i] = np.floor(rnd.rand(S) * nf)
+            elif nb > 0:
+                fg_this = 0
+                picks[i] = np.floor(rnd.rand(S) * nb)
+            else:
+                raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+            n_fg_pick[i] = fg_this
+        picks_d = torch.from_numpy(picks).to(dev)
+        nfp_d = torch.from_numpy(n_fg_pick).to(dev)
+        lists = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+        bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        rois_out = torch.zeros((B, S, 5), dtype=torch.float32, device=dev)
+        labels = torch.zeros((B, S), dtype=torch.float32, device=dev)
+        targets = torch.zeros((B, S, 4), dtype=torch.float32, device=dev)
+        inside = torch.zeros_like(targets)
+        outside = torch.zeros_like(targets)
+        f4 = C.c_float * 4
+        means = cfg["BBOX_NORMALIZE_MEANS"] if cfg["BBOX_NORMALIZE_TARGETS_PRECOMPUTED"] else (0.0,) * 4
+        stds = cfg["BBOX_NORMALIZE_STDS"] if cfg["BBOX_NORMALIZE_TARGETS_PRECOMPUTED"] else (1.0,) * 4
+        L.check(lib.aitb_proposal_target_sample(L.ptr(rois), L.ptr(gt), B, R, K, L.ptr(cls), L.ptr(assign), L.ptr(picks_d),
+                                                L.ptr(nfp_d), S, f4(*means), f4(*stds), f4(*cfg["BBOX_INSIDE_WEIGHTS"]),
+                                                L.ptr(lists), L.ptr(rois_out), L.ptr(labels), L.ptr(targets), L.ptr(inside),
+                                                L.ptr(outside), L.ptr(bad), L.stream_ptr()))
+        self.last_bad_flag = bad   # device flag: non-zero only if a pick fell outside its list (never with our draws)
+        return rois_out, labels, targets, inside, outside
+
+
+_AnchorTargetLayer = AnchorTargetLayer
+_ProposalTargetLayer = ProposalTargetLayer
+
+
+class _RPNLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside, sigma):
+        lib = L.load()
+        ops._need_cuda(rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside)
+        B, c2, H, W = rpn_cls_score.shape
+        A = c2 // 2
+        if rpn_bbox_pred.shape != (B, 4 * A, H, W) or labels.numel() != B * A * H * W or targets.shape != rpn_bbox_pred.shape:
+            raise RuntimeError("rpn_losses: expected rpn_cls_score [B,2A,H,W], rpn_bbox_pred [B,4A,H,W], labels [B,1,A*H,W]")
+        t = [x.detach().contiguous().float() for x in (rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside)]
+        losses = torch.empty((2,), dtype=torch.float32, device=t[0].device)
+        acc = torch.empty((3,), dtype=torch.float64, device=t[0].device)
+        L.check(lib.aitb_rpn_loss(*[L.ptr(x) for x in t], B, A, H, W, float(sigma), None, L.ptr(losses), None, None,
+                                  L.ptr(acc), L.stream_ptr()))
+        ctx.save_for_backward(*t)
+        ctx.meta = (B, A, H, W, float(sigma))
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box):
+        lib = L.load()
+        t = ctx.saved_tensors
+        B, A, H, W, sigma = ctx.meta
+        dev = t[0].device
+        gscale = torch.stack([g_cls.reshape(()).float(), g_box.reshape(()).float()]).contiguous()
+        losses = torch.empty((2,), dtype=torch.float32, device=dev)
+        acc = torch.empty((3,), dtype=torch.float64, device=dev)
+        d_score, d_bbox = torch.empty_like(t[0]), torch.empty_like(t[1])
+        L.check(lib.aitb_rpn_loss(*[L.ptr(x) for x in t], B, A, H, W, sigma, L.ptr(gscale), L.ptr(losses), L.ptr(d_score),
+                                  L.ptr(d_bbox), L.ptr(acc), L.stream_ptr()))
+        return d_score, d_bbox, None, None, None, None, None
+
+
+def rpn_losses(rpn_cls_score, rpn_bbox_pred, rpn_data, sigma=3.0):
+    """rpn.py:99-126: (rpn_loss_cls, rpn_loss_box) from the raw RPN outputs (rpn_cls_score [B,2A,H,W] with the
+    background channels first, rpn_bbox_pred [B,4A,H,W]) and the anchor-target outputs `rpn_data`."""
+    labels, targets, inside, outside = rpn_data
+    return _RPNLossFn.apply(rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside, sigma)
+
+
+class _RCNNLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, bbox_pred, labels, targets, inside, outside, bs, margin, margin_scale):
+        lib = L.load()
+        ops._need_cuda(score, bbox_pred, labels, targets, inside, outside)
+        n = score.shape[0]
+        if score.shape != (n, 2) or bbox_pred.shape != (n, 4) or labels.numel() != n or n % bs:
+            raise RuntimeError("rcnn_losses: expected score [bs*P,2], bbox_pred [bs*P,4], rois_label [bs*P]")
+        P = n // bs
+        t = [score.detach().contiguous().float(), bbox_pred.detach().contiguous().float(),
+             labels.detach().reshape(-1).contiguous().float(), targets.detach().reshape(n, 4).contiguous().float(),
+             inside.detach().reshape(n, 4).contiguous().float(), outside.detach().reshape(n, 4).contiguous().float()]
+        dev = t[0].device
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        acc = torch.empty((3,), dtype=torch.float64, device=dev)
+        L.check(lib.aitb_rcnn_loss(*[L.ptr(x) for x in t], bs, P, float(margin), float(margin_scale), None, L.ptr(losses),
+                                   None, None, None, L.ptr(acc), L.stream_ptr()))
+        ctx.save_for_backward(*t)
+        ctx.meta = (bs, P, float(margin), float(margin_scale))
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_margin, g_bbox):
+        lib = L.load()
+        t = ctx.saved_tensors
+        bs, P, margin, margin_scale = ctx.meta
+        dev = t[0].device
+        gscale = torch.stack([g_cls.reshape(()).float(), g_margin.reshape(()).float(), g_bbox.reshape(()).float()]).contiguous()
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        acc = torch.empty((3,), dtype=torch.float64, device=dev)
+        d_score, d_bbox = torch.empty_like(t[0]), torch.empty_like(t[1])
+        L.check(lib.aitb_rcnn_loss(*[L.ptr(x) for x in t], bs, P, margin, margin_scale, L.ptr(gscale), L.ptr(losses), None,
+                                   L.ptr(d_score), L.ptr(d_bbox), L.ptr(acc), L.stream_ptr()))
+        return d_score, d_bbox, None, None, None, None, None, None, None
+
+
+def rcnn_losses(score, bbox_pred, rois_label, rois_target, rois_inside_ws, rois_outside_ws, bs, margin=TRAIN_CFG["MARGIN"],
+                margin_scale=3.0):
+    """faster_rcnn_coatt_transformer_sk.py:340-361: (RCNN_loss_cls, margin_loss, RCNN_loss_bbox) from score [bs*P,2],
+    bbox_pred [bs*P,4] and the proposal-target outputs."""
+    return _RCNNLossFn.apply(score, bbox_pred, rois_label, rois_target, rois_inside_ws, rois_outside_ws, int(bs),
+                             margin, margin_scale)

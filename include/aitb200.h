@@ -397,6 +397,59 @@ int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, in
                       size_t saved_bytes, const aitb_ait_grads* grads, float* grad_props, float* grad_query,
                       void* workspace, size_t workspace_bytes, aitb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f4  training-only samplers and losses (ait_b200/csrc/targets.cu)
+ *
+ * Anchor target layer (lib/model/rpn/anchor_target_layer.py:49-199), two phases around the random sub-sampling:
+ *   aitb_anchor_target_assign: anchors = base_anchors [A,4] + cell shifts (cell-major, index cell*A + a); anchors inside
+ *     the image of im_info[0] get max / argmax IoU over gt_boxes [B,K,5] and the pre-sampling label
+ *     (-1 don't care, 0 bg: max < neg_thr, 1 fg: max >= pos_thr or equal to a gt box's best IoU);
+ *     labels [B, H*W*A] int8 (outside anchors -1), argmax [B, H*W*A] (outside -1), counts [B,2] = (#fg, #bg).
+ *   aitb_anchor_target_finish: drop [B, 2, ld_drop] bytes (NULL = keep all): drop[b][0][r] != 0 disables the r-th
+ *     foreground anchor of image b in ascending anchor order (= `fg_inds[r]`, :132-140), drop[b][1][r] the r-th
+ *     background anchor (:146-152); then the reference's four outputs: labels_out [B,1,A*H,W], bbox_targets /
+ *     inside_w / outside_w [B,4A,H,W]; n_examples [B] = anchors with label >= 0 (outside weight = 1 / n_examples[B-1],
+ *     the reference's `labels[i]` after its loop, :163).
+ * Proposal target layer (lib/model/rpn/proposal_target_layer_cascade.py:33-220):
+ *   aitb_proposal_target_assign: candidates = rois [B,R,5] ++ gt boxes; max_overlaps / assignment [B,R+K],
+ *     cls [B,R+K] int8 (1 fg: max >= fg_thr, 0 bg: bg_lo <= max < bg_hi, -1 neither), counts [B,2].
+ *   aitb_proposal_target_sample: picks [B,S] ranks within the image's ascending fg list (first n_fg_pick[b] slots) and
+ *     bg list (the rest) -> rois_out [B,S,5], labels_out [B,S], bbox_targets / inside_w / outside_w [B,S,4] (targets
+ *     normalised by h_means / h_stds); lists: scratch [B,2,R+K] int32; *bad_flag set to 1 on an out-of-range pick.
+ * Losses with their gradients (rpn.py:99-126; faster_rcnn_coatt_transformer_sk.py:334-361; net_utils.py:75-89):
+ *   aitb_rpn_loss: losses[0] = cross entropy over anchors with label != -1, losses[1] = smooth L1 (sigma), and
+ *     d(gscale[0]*losses[0] + gscale[1]*losses[1]) / d(rpn_cls_score [B,2A,H,W]), / d(rpn_bbox_pred [B,4A,H,W])
+ *     (gradient outputs and gscale may be NULL; gscale NULL = ones); acc: 3 doubles of scratch.
+ *   aitb_rcnn_loss: score [bs*P,2], bbox_pred [bs*P,4], labels [bs*P] -> losses[0] = cross entropy, losses[1] =
+ *     margin_scale * MarginRankingLoss(margin)(|p_i-p_j|, |l_i-l_j|, target), losses[2] = smooth L1 (sigma 1);
+ *     cls_prob [bs*P] = softmax(score)[:,1]; gradients as above with gscale[3]; acc: 3 doubles of scratch.
+ * ---------------------------------------------------------------------------------------- */
+size_t aitb_anchor_target_workspace_bytes(int B, int A, int H, int W, int K);
+int aitb_anchor_target_assign(const float* base_anchors, const float* gt_boxes, const float* im_info, int B, int A, int H,
+                              int W, int K, float feat_stride, float neg_thr, float pos_thr, int clobber_positives,
+                              int8_t* labels, int32_t* argmax, int32_t* counts, void* workspace, size_t workspace_bytes,
+                              aitb_stream_t stream);
+int aitb_anchor_target_finish(const float* base_anchors, const float* gt_boxes, int B, int A, int H, int W, int K,
+                              float feat_stride, int8_t* labels, const int32_t* argmax, const uint8_t* drop, int ld_drop,
+                              float inside_weight, int32_t* n_examples, float* labels_out, float* bbox_targets,
+                              float* inside_w, float* outside_w, aitb_stream_t stream);
+int aitb_proposal_target_assign(const float* rois, const float* gt_boxes, int B, int R, int K, float fg_thr, float bg_hi,
+                                float bg_lo, float* max_overlaps, int32_t* assignment, int8_t* cls, int32_t* counts,
+                                aitb_stream_t stream);
+int aitb_proposal_target_sample(const float* rois, const float* gt_boxes, int B, int R, int K, const int8_t* cls,
+                                const int32_t* assignment, const int32_t* picks, const int32_t* n_fg_pick, int S,
+                                const float* h_means, const float* h_stds, const float* h_inside_w, int32_t* lists,
+                                float* rois_out, float* labels_out, float* bbox_targets, float* inside_w, float* outside_w,
+                                int32_t* bad_flag, aitb_stream_t stream);
+int aitb_rpn_loss(const float* rpn_cls_score, const float* rpn_bbox_pred, const float* labels, const float* bbox_targets,
+                  const float* inside_w, const float* outside_w, int B, int A, int H, int W, float sigma,
+                  const float* gscale, float* losses, float* d_cls_score, float* d_bbox_pred, double* acc,
+                  aitb_stream_t stream);
+int aitb_rcnn_loss(const float* score, const float* bbox_pred, const float* labels, const float* bbox_targets,
+                   const float* inside_w, const float* outside_w, int bs, int P, float margin, float margin_scale,
+                   const float* gscale, float* losses, float* cls_prob, float* d_score, float* d_bbox_pred, double* acc,
+                   aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 
