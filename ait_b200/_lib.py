@@ -153,6 +153,7 @@ SIGNATURES = {
     "aitb_proposal_target_assign": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "aitb_proposal_target_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_fc_ln": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aitb_rpn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aitb_rcnn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -52,6 +52,8 @@ int rpn_head_decode_run(const void* heads, int dtype, int ld, const float* base_
                         float* bbox_pred_nchw, cudaStream_t st);
 int group_norm_residual_run(const float* x, const float* identity, const float* gamma, const float* beta, int B, int N,
                             int groups, float eps, double* sums, float* out, cudaStream_t st);
+int fc_ln_run(int dtype, const void* a, const void* w, const void* res, const float* gamma, const float* beta, float eps,
+              void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, cudaStream_t st);
 int det_assemble_run(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
                      int32_t* n_det, cudaStream_t st);
@@ -364,6 +366,12 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32, kv_rows));
   // fc (64 -> 512, no bias) + residual + LayerNorm   (SubLayers.py:97-100)
+  // bf16 / split storage: the dedicated streaming kernel (fc_ln.cu); tf32 storage and the training forward (which
+  // saves 1/sigma) keep the tcgen05 GEMM with the LayerNorm epilogue.  AITB_FC_GEMM=1 forces the GEMM for A/B runs.
+  static const bool force_gemm = getenv("AITB_FC_GEMM") != nullptr;
+  if (dt != AITB_F32 && rstd == nullptr && !force_gemm)
+    return fc_ln_run(dt, ao, m.w_fc, res, m.ln.gamma, m.ln.beta, 1e-6f, out, G * 64, out_rows != 64 ? 64 : G * 64, out_rows != 64 ? out_rows : G * 64,
+                     out_rows != 64 ? 1 : 0, 64, res_rep, st);
   aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 512, out, 512, w->round_tf32);
   view_plain(d, ao, 64);
   d.flags = AITB_EPI_RES | AITB_EPI_LN;

@@ -213,6 +213,17 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     return out
 
 
+def fc_ln(a, w_fc, res, gamma, beta, out, *, M, split=False, rows_in=None, rows_out=None, res_row_m=False, res_div=1,
+          res_rep=1, eps=1e-6):
+    """out = LayerNorm(a w_fc^T + res) (N = 512, K = 64) by the streaming kernel; bf16 storage or split planes."""
+    lib = L.load()
+    _need_cuda(a, w_fc, res, gamma, beta, out)
+    L.check(lib.aitb_fc_ln(L.AITB_F32S if split else L.AITB_BF16, L.ptr(a), L.ptr(w_fc), L.ptr(res), L.ptr(gamma), L.ptr(beta),
+                           float(eps), L.ptr(out), M, rows_in or M, rows_out or M, 1 if res_row_m else 0, res_div, res_rep,
+                           L.stream_ptr()))
+    return out
+
+
 def attn_core(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, out, split=False):
     """split=True: q / k / v / out are two-plane bf16 matrices, ldq / ldkv their LOGICAL row widths."""
     lib = L.load()

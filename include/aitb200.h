@@ -450,6 +450,14 @@ int aitb_rcnn_loss(const float* score, const float* bbox_pred, const float* labe
                    const float* gscale, float* losses, float* cls_prob, float* d_score, float* d_bbox_pred, double* acc,
                    aitb_stream_t stream);
 
+/* Attention output projection + residual + LayerNorm (lib/model/system/SubLayers.py:97-100) as one streaming kernel
+ * (ait_b200/csrc/fc_ln.cu): out[o(m), :] = LN(a[m, 0..64) * w_fc^T + res[r(m), :]) * gamma + beta, N = 512, K = 64.
+ * dtype AITB_BF16 or AITB_F32S (two bf16 planes per row: a [M, 64 | 64], w [512, 64 | 64], res / out [*, 512 | 512]).
+ * Row maps as in aitb_gemm: o(m) = (m / rows_in) * rows_out + m % rows_in for m % rows_in < rows_out (other rows are
+ * dropped); r(m) = ((b / res_div) / res_rep) * res_div + b % res_div with b = m (res_row_m) or o(m). */
+int aitb_fc_ln(int dtype, const void* a, const void* w_fc, const void* res, const float* gamma, const float* beta, float eps,
+               void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 

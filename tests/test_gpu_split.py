@@ -161,3 +161,54 @@ def test_split_transposes_and_pool_heads():
     top = torch.randn(5, 16, 2048, generator=g)
     feat, _, _ = ops.pool_heads(_sp(top), 1, split=True)
     assert _err(feat.cpu(), top.mean(1)) < 1e-5
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("case", ["plain", "broadcast", "compact"])
+def test_fc_ln_streaming_kernel(split, case):
+    """fc (64 -> 512) + residual + LayerNorm as the streaming kernel (fc_ln.cu): plain rows, the cross-attention
+    residual broadcast (one residual block per unit, P pairs), and the encoder's 64 -> 49 row compaction with the
+    residual indexed by the 64-row layout; ragged M (not a multiple of the 64-row CTA block)."""
+    from ait_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, P = 3, 5
+    pairs = B * P
+    M = pairs * 64
+    a = torch.randn(M, 64, generator=g)
+    w = torch.randn(512, 64, generator=g) / 8
+    gamma, beta = torch.rand(512, generator=g) + 0.5, torch.randn(512, generator=g)
+    kw = {}
+    if case == "broadcast":
+        res = torch.randn(B * 64, 512, generator=g)
+        y = (a.double() @ w.double().t()).view(B, P, 64, 512) + res.double().view(B, 1, 64, 512)
+        kw = dict(res_div=64, res_rep=P)
+        rows = M
+    elif case == "compact":
+        res = torch.randn(M, 512, generator=g)
+        y = ((a.double() @ w.double().t()) + res.double()).view(pairs, 64, 512)[:, :49]
+        kw = dict(rows_in=64, rows_out=49, res_row_m=True, res_div=64, res_rep=1)
+        rows = pairs * 49
+    else:
+        M = M - 40          # ragged tail
+        a, res = a[:M], torch.randn(M, 512, generator=g)
+        y = a.double() @ w.double().t() + res.double()
+        kw = dict(res_div=64, res_rep=1)
+        rows = M
+    ref = F.layer_norm(y, (512,), gamma.double(), beta.double(), eps=1e-6).reshape(rows, 512)
+    conv = _sp if split else (lambda x: x.to(BF).to(DEV))
+    out = torch.zeros((rows + 3, 1024 if split else 512), dtype=BF, device=DEV)
+    ops.fc_ln(conv(a), conv(w), conv(res), gamma.to(DEV), beta.to(DEV), out, M=M, split=split, **kw)
+    o = _jn(out) if split else out.float().cpu()
+    assert torch.all(o[rows:] == 0), "rows past the output were written"
+    if split:
+        assert _err(o[:rows], ref) < GATE
+    else:   # bf16 storage: compare against the same computation on bf16-rounded operands, bf16 output rounding
+        ab, wb, rb = a.to(BF).double(), w.to(BF).double(), res.to(BF).double()
+        if case == "broadcast":
+            yb = (ab @ wb.t()).view(B, P, 64, 512) + rb.view(B, 1, 64, 512)
+        elif case == "compact":
+            yb = ((ab @ wb.t()) + rb).view(pairs, 64, 512)[:, :49]
+        else:
+            yb = ab @ wb.t() + rb
+        refb = F.layer_norm(yb, (512,), gamma.double(), beta.double(), eps=1e-6).reshape(rows, 512)
+        assert _err(o[:rows], refb) < 6e-3
