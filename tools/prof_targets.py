@@ -1,5 +1,5 @@
 """Launch the hot kernels in isolation on benchmark-shaped data (for `ncu --set full`):
-FFN w_1 GEMM (2-CTA), FFN w_2 GEMM (cluster LayerNorm), attention fc GEMM (K = 64, LayerNorm), encoder
+FFN w_1 GEMM (2-CTA), FFN w_2 GEMM (cluster LayerNorm), attention fc GEMM (K = 64, LayerNorm) and its streaming replacement (fc_ln), encoder
 self-attention core, ROIAlign (token-major), proposal top-n + NMS.
 
     python tools/prof_targets.py [reps] [fp32|tf32|bf16]
@@ -62,6 +62,8 @@ for _ in range(reps):
              res=x512, ldr=512, gamma=gamma, beta=b512, split=split)
     ops.gemm(x64, wfc, o512, M=M, N=512, K=64, block_n=512, flags=L.EPI_RES | L.EPI_LN, res=x512, ldr=512,
              res_div=64, gamma=gamma, beta=b512, split=split)
+    if mode != "tf32":   # the streaming fc + residual + LayerNorm kernel that replaced the K = 64 GEMM above on the hot path
+        ops.fc_ln(x64, wfc, x512, gamma, b512, o512, M=M, split=split, res_div=64, res_rep=1)
     ops.attn_core(qkv, 1536, 1, qkv.view(-1)[512:], qkv.view(-1)[1024:], 1536, w_sk, b_sk, G, 0, 49, ao, split=split)
     if split:
         lib = L.load()
