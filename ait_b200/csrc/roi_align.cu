@@ -150,11 +150,35 @@ __device__ __forceinline__ bool build_foot(Foot& f, float start, int p, float bi
   return true;
 }
 
+// acc += sum over ny rows x NX columns of wy[cy] * wx[cx] * feat[r + cy*rowC + cx*uC]  (this lane's 4 channels)
+template <typename T, int NX>
+__device__ __forceinline__ void foot_rows(float4& acc, const T* __restrict__ fb, uint32_t r, uint32_t rowC, uint32_t uC, int ny,
+                                          const float* __restrict__ wy_tab, const float* __restrict__ wx_tab) {
+  float wx[NX];
+#pragma unroll
+  for (int j = 0; j < NX; ++j) wx[j] = wx_tab[j];
+#pragma unroll 1
+  for (int cy = 0; cy < ny; ++cy, r += rowC) {
+    const float wy = wy_tab[cy];
+    float4 v[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) v[j] = Vec4<T>::ld(fb + r + (uint32_t)j * uC);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      const float w = wy * wx[j];
+      acc.x += w * v[j].x; acc.y += w * v[j].y; acc.z += w * v[j].z; acc.w += w * v[j].w;
+    }
+  }
+}
+
 // grid (ceil(C / 128), K); block 256 = 8 warps; lane owns 4 consecutive channels of the 128-channel slab,
 // warps stride over the ph*pw bins.
 // OUT_SPLIT (token-major only): fp32 map in, output as two bf16 planes [K, ph*pw, hi C | lo C] (AITB_F32S)
+#ifndef AITB_ROI_MINB
+#define AITB_ROI_MINB 5
+#endif
 template <typename T, bool NCHW_OUT, bool OUT_SPLIT = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AITB_ROI_MINB)
 roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
                      int ph, int pw, int sampling_ratio, typename std::conditional<OUT_SPLIT, __nv_bfloat16, T>::type* __restrict__ out,
                      int round_tf) {
@@ -176,21 +200,40 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
   const int cvalid = min(128, C - c0);          // last slab may be partial (C % 4 == 0)
   const bool lane_on = lane * 4 < cvalid;
   const T* fb = feat + (size_t)g.batch * H * W * C + c0 + (lane_on ? lane * 4 : 0);
-  const float count = (float)(g.grid_h * g.grid_w);
+  // output_val /= count (:118) as a multiply by 1/count: <= 1 ulp from the division, and the four IEEE divisions per
+  // bin were 14 % of the kernel (XU pipe); ncu: 41 executed instructions per tap with a 9-instruction inner loop, so
+  // the per-bin bookkeeping is kept division-free and 32-bit (the map of one image is < 2^31 elements, checked on the host)
+  const float inv_count = __frcp_rn((float)(g.grid_h * g.grid_w));
   const int nbins = ph * pw;
+  const uint32_t uC = (uint32_t)C, rowC = (uint32_t)W * (uint32_t)C;
+  int py = warp / pw, px = warp - py * pw;   // bin = warp, then += 8 without dividing again (pw <= 8)
   for (int bin = warp; bin < nbins; bin += 8) {
-    const int py = bin / pw, px = bin - py * pw;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tables) {
       const int ny = yf[py].n, nx = xf[px].n;
-      const T* r = fb + ((size_t)yf[py].c0 * W + xf[px].c0) * C;
-      for (int cy = 0; cy < ny; ++cy, r += (size_t)W * C) {
-        const float wy = yf[py].w[cy];
-        const T* q = r;
-        for (int cx = 0; cx < nx; ++cx, q += C) {
-          const float w = wy * xf[px].w[cx];
-          const float4 v = Vec4<T>::ld(q);
-          acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+      const uint32_t r = (uint32_t)yf[py].c0 * rowC + (uint32_t)xf[px].c0 * uC;
+      // footprints are 2-7 cells wide at RPN proposal sizes: one fully unrolled row body per width (x weights in
+      // registers, the row's loads issued back to back) instead of a 3-4 trip inner loop -- 26 -> ~8 instructions per tap
+      switch (nx) {
+        case 1: foot_rows<T, 1>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 2: foot_rows<T, 2>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 3: foot_rows<T, 3>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 4: foot_rows<T, 4>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 5: foot_rows<T, 5>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 6: foot_rows<T, 6>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 7: foot_rows<T, 7>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        case 8: foot_rows<T, 8>(acc, fb, r, rowC, uC, ny, yf[py].w, xf[px].w); break;
+        default: {
+          uint32_t rr = r;
+          for (int cy = 0; cy < ny; ++cy, rr += rowC) {
+            const float wy = yf[py].w[cy];
+            uint32_t q = rr;
+            for (int cx = 0; cx < nx; ++cx, q += uC) {
+              const float w = wy * xf[px].w[cx];
+              const float4 v = Vec4<T>::ld(fb + q);
+              acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+            }
+          }
         }
       }
     } else {
@@ -212,8 +255,9 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
         }
       }
     }
-    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);   // output_val /= count (:118)
-    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+    acc.x *= inv_count; acc.y *= inv_count; acc.z *= inv_count; acc.w *= inv_count;
+    px += 8;                                   // advance (py, px) to bin + 8
+    while (px >= pw) { px -= pw; ++py; }
     if (!lane_on) continue;
     if (sizeof(T) == 4 && round_tf) {  // engine-internal: the consumer is a tf32 MMA (RN beats HW truncation)
       acc.x = rn_tf32(acc.x); acc.y = rn_tf32(acc.y); acc.z = rn_tf32(acc.z); acc.w = rn_tf32(acc.w);
@@ -225,10 +269,19 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
       stage[(lane * 4 + 2) * s + bin] = acc.z;
       stage[(lane * 4 + 3) * s + bin] = acc.w;
     } else if constexpr (OUT_SPLIT) {
+      // hi = bf16(x), lo = bf16(x - hi) with the packed conversion (F2FP.PACK_AB, FMA-class pipe) and the hi values
+      // recovered by shifts: the scalar F2F.BF16 conversions of the naive form were 25 % of the kernel's instructions
       __nv_bfloat16* o = out + ((size_t)k * nbins + bin) * 2 * C + c0 + lane * 4;
-      Vec4<__nv_bfloat16>::st(o, acc);
-      auto lo = [](float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); };
-      Vec4<__nv_bfloat16>::st(o + C, make_float4(lo(acc.x), lo(acc.y), lo(acc.z), lo(acc.w)));
+      uint2 hi;
+      *reinterpret_cast<__nv_bfloat162*>(&hi.x) = __floats2bfloat162_rn(acc.x, acc.y);
+      *reinterpret_cast<__nv_bfloat162*>(&hi.y) = __floats2bfloat162_rn(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(o) = hi;
+      const float lx = acc.x - __uint_as_float(hi.x << 16), ly = acc.y - __uint_as_float(hi.x & 0xffff0000u);
+      const float lz = acc.z - __uint_as_float(hi.y << 16), lw = acc.w - __uint_as_float(hi.y & 0xffff0000u);
+      uint2 lo;
+      *reinterpret_cast<__nv_bfloat162*>(&lo.x) = __floats2bfloat162_rn(lx, ly);
+      *reinterpret_cast<__nv_bfloat162*>(&lo.y) = __floats2bfloat162_rn(lz, lw);
+      *reinterpret_cast<uint2*>(o + C) = lo;
     } else {
       Vec4<T>::st(out + ((size_t)k * nbins + bin) * C + c0 + lane * 4, acc);
     }
@@ -370,6 +423,7 @@ int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, 
   AITB_REQUIRE(ph >= 1 && pw >= 1 && ph <= kMaxPooled && pw <= kMaxPooled, "aitb_roi_align_forward: pooled size %dx%d unsupported", ph, pw);
   AITB_REQUIRE(K <= 65535, "aitb_roi_align_forward: K=%d exceeds one launch (chunk the rois)", K);
   AITB_REQUIRE(out_layout == 0 || out_layout == 1, "aitb_roi_align_forward: out_layout must be 0 or 1");
+  AITB_REQUIRE((size_t)H * W * C < ((size_t)1 << 31), "aitb_roi_align_forward: one image's map must stay below 2^31 elements");
   dim3 grid((C + 127) / 128, K);
   const size_t smem = out_layout == 0 ? (size_t)128 * (ph * pw + 1) * 4 : 0;
   if (dtype == AITB_F32) {
