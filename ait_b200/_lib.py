@@ -154,6 +154,10 @@ SIGNATURES = {
     "aitb_proposal_target_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aitb_fc_ln": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "aitb_heads_forward_train": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_heads_backward_workspace_bytes": (_sz, [_i, _i]),
+    "aitb_heads_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "aitb_mean_pool_backward": (_i, [_vp, _i, _vp, _vp]),
     "aitb_rpn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aitb_rcnn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -276,3 +276,63 @@ def rcnn_losses(score, bbox_pred, rois_label, rois_target, rois_inside_ws, rois_
     bbox_pred [bs*P,4] and the proposal-target outputs."""
     return _RCNNLossFn.apply(score, bbox_pred, rois_label, rois_target, rois_inside_ws, rois_outside_ws, int(bs),
                              margin, margin_scale)
+
+
+class _ScoreHeadsFn(torch.autograd.Function):
+    """score / bbox heads on the pooled features, differentiable w.r.t. both feature inputs and the six parameters."""
+
+    @staticmethod
+    def forward(ctx, feat, qfeat, P, w_bbox, b_bbox, w1, b1, w2, b2):
+        lib = L.load()
+        ops._need_cuda(feat, qfeat, w_bbox, b_bbox, w1, b1, w2, b2)
+        G = feat.shape[0]
+        if feat.shape != (G, 2048) or G % P or qfeat.shape != (G // P, 2048) or w1.shape != (8, 4096) or w2.shape != (2, 8) \
+                or w_bbox.shape != (4, 2048):
+            raise RuntimeError("score_heads: expected feat [G,2048], qfeat [G/P,2048], RCNN_bbox_pred Linear(2048,4), "
+                               "RCNN_cls_score = Linear(4096,8), Linear(8,2)")
+        t = [x.detach().contiguous().float() for x in (feat, qfeat, w_bbox, b_bbox, w1, b1, w2, b2)]
+        dev = t[0].device
+        bbox = torch.empty((G, 4), dtype=torch.float32, device=dev)
+        hidden = torch.empty((G, 8), dtype=torch.float32, device=dev)
+        score = torch.empty((G, 2), dtype=torch.float32, device=dev)
+        L.check(lib.aitb_heads_forward_train(L.ptr(t[0]), L.ptr(t[1]), G, P, *[L.ptr(x) for x in t[2:]], L.ptr(bbox),
+                                             L.ptr(hidden), L.ptr(score), L.stream_ptr()))
+        ctx.save_for_backward(t[0], t[1], hidden, t[2], t[4], t[6])
+        ctx.P = P
+        return score, bbox
+
+    @staticmethod
+    def backward(ctx, d_score, d_bbox):
+        lib = L.load()
+        feat, qfeat, hidden, w_bbox, w1, w2 = ctx.saved_tensors
+        G, P, dev = feat.shape[0], ctx.P, feat.device
+        d_score = (torch.zeros((G, 2), device=dev) if d_score is None else d_score).contiguous().float()
+        d_bbox = (torch.zeros((G, 4), device=dev) if d_bbox is None else d_bbox).contiguous().float()
+        d_feat, d_qfeat = torch.empty_like(feat), torch.empty_like(qfeat)
+        g = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ((4, 2048), (4,), (8, 4096), (8,), (2, 8), (2,))]
+        nb = lib.aitb_heads_backward_workspace_bytes(G, P)
+        ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        L.check(lib.aitb_heads_backward(L.ptr(feat), L.ptr(qfeat), L.ptr(hidden), L.ptr(d_score), L.ptr(d_bbox), G, P, L.ptr(w_bbox),
+                                        L.ptr(w1), L.ptr(w2), L.ptr(d_feat), L.ptr(d_qfeat), *[L.ptr(x) for x in g], L.ptr(ws), nb,
+                                        L.stream_ptr()))
+        return d_feat, d_qfeat, None, g[0], g[1], g[2], g[3], g[4], g[5]
+
+
+def score_heads(feat, qfeat, P, RCNN_bbox_pred, RCNN_cls_score):
+    """faster_rcnn_coatt_transformer_sk.py:318-332 in training: (score [G,2] logits, bbox_pred [G,4]) from the pooled
+    layer-4 features feat [G,2048] of the pairs and qfeat [G/P,2048] of the units' queries; RCNN_bbox_pred = nn.Linear(2048, 4),
+    RCNN_cls_score = nn.Sequential(nn.Linear(4096, 8), nn.Linear(8, 2)) (the reference's modules, ordinary Parameters).
+    Differentiable: feeds `rcnn_losses`, back-propagates to both feature inputs and the six parameters."""
+    return _ScoreHeadsFn.apply(feat, qfeat, int(P), RCNN_bbox_pred.weight, RCNN_bbox_pred.bias, RCNN_cls_score[0].weight,
+                               RCNN_cls_score[0].bias, RCNN_cls_score[1].weight, RCNN_cls_score[1].bias)
+
+
+def mean_pool_backward(d_feat):
+    """Adjoint of `_head_to_tail`'s spatial mean: d_feat [G,2048] -> d_top [G,16,2048] (token-major 4x4 map)."""
+    lib = L.load()
+    ops._need_cuda(d_feat)
+    d_feat = d_feat.contiguous().float()
+    G = d_feat.shape[0]
+    d_top = torch.empty((G, 16, 2048), dtype=torch.float32, device=d_feat.device)
+    L.check(lib.aitb_mean_pool_backward(L.ptr(d_feat), G, L.ptr(d_top), L.stream_ptr()))
+    return d_top

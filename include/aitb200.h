@@ -458,6 +458,22 @@ int aitb_rcnn_loss(const float* score, const float* bbox_pred, const float* labe
 int aitb_fc_ln(int dtype, const void* a, const void* w_fc, const void* res, const float* gamma, const float* beta, float eps,
                void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, aitb_stream_t stream);
 
+/* Training of the head's last layers on the pooled layer-4 features (ait_b200/csrc/heads_train.cu; rows a12 + f4):
+ *   forward: feat [G,2048], qfeat [G/P,2048] -> bbox [G,4], hidden [G,8] (kept for the backward), score [G,2] (the LOGITS
+ *            the losses of faster_rcnn_coatt_transformer_sk.py:340-361 are taken on)
+ *   backward: d_score [G,2], d_bbox [G,4] -> d_feat [G,2048], d_qfeat [G/P,2048] (overwritten) and the parameter gradients
+ *            dw_bbox [4,2048], db_bbox [4], dw1 [8,4096], db1 [8], dw2 [2,8], db2 [2], ACCUMULATED (caller zero-initialises)
+ *   aitb_mean_pool_backward: d_top [G,16,2048] = d_feat / 16 (adjoint of `_head_to_tail`'s 4x4 mean) */
+int aitb_heads_forward_train(const float* feat, const float* qfeat, int G, int P, const float* w_bbox, const float* b_bbox,
+                             const float* w1, const float* b1, const float* w2, const float* b2, float* bbox, float* hidden,
+                             float* score, aitb_stream_t stream);
+size_t aitb_heads_backward_workspace_bytes(int G, int P);
+int aitb_heads_backward(const float* feat, const float* qfeat, const float* hidden, const float* d_score, const float* d_bbox,
+                        int G, int P, const float* w_bbox, const float* w1, const float* w2, float* d_feat, float* d_qfeat,
+                        float* dw_bbox, float* db_bbox, float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+                        size_t workspace_bytes, aitb_stream_t stream);
+int aitb_mean_pool_backward(const float* d_feat, int G, float* d_top, aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 

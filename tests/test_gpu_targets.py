@@ -173,3 +173,52 @@ def test_losses_weighted_sum_and_oracle_other_shapes():
         assert abs(a_ - b_) <= 3e-6 * abs(b_)
     for a_, b_ in zip(got_g, ref_g):
         assert float((a_ - b_).abs().max()) <= 2e-5 * float(b_.abs().max())
+
+
+def test_score_heads_training_step_matches_autograd():
+    """feat / qfeat -> score heads -> the three detection losses -> backward: every gradient (both feature inputs, six
+    parameter tensors) against torch autograd over the reference's nn.Linear modules + the loss oracle; and the adjoint
+    of the 4x4 mean."""
+    import torch.nn as nn
+    from ait_b200.targets import score_heads, rcnn_losses, mean_pool_backward
+    from oracle import target_oracle as T
+    g = torch.Generator().manual_seed(11)
+    bs, P = 3, 128
+    G = bs * P
+    feat, qfeat = torch.randn(G, 2048, generator=g).relu(), torch.randn(bs, 2048, generator=g).relu()
+    lab = (torch.rand(bs, P, generator=g) < 0.25).float()
+    tgt = torch.randn(bs, P, 4, generator=g) * lab.unsqueeze(2)
+    wi = lab.unsqueeze(2).expand(bs, P, 4).contiguous()
+
+    def make():
+        torch.manual_seed(3)
+        bb, cs = nn.Linear(2048, 4), nn.Sequential(nn.Linear(4096, 8), nn.Linear(8, 2))
+        for m, std in ((bb, 0.01), (cs[0], 0.02), (cs[1], 0.3)):
+            m.weight.data.normal_(0, std)
+            m.bias.data.normal_(0, 0.1)
+        return bb, cs
+
+    def run(dev, ours):
+        bb, cs = make()
+        bb, cs = bb.to(dev), cs.to(dev)
+        f, q = feat.clone().to(dev).requires_grad_(), qfeat.clone().to(dev).requires_grad_()
+        if ours:
+            score, bbox = score_heads(f, q, P, bb, cs)
+            losses = rcnn_losses(score, bbox, lab.view(-1).to(dev), tgt.to(dev), wi.to(dev), wi.to(dev), bs)
+        else:
+            bbox = bb(f)
+            score = cs(torch.cat((f.view(bs, P, -1), q.unsqueeze(1).repeat(1, P, 1)), 2).view(-1, 4096))
+            losses = T.rcnn_losses(score, bbox, lab.view(-1), tgt, wi, wi, bs)
+        (losses[0] + losses[1] + 2.0 * losses[2]).backward()
+        grads = [f.grad, q.grad] + [p.grad for p in list(bb.parameters()) + list(cs.parameters())]
+        return score.detach().cpu(), bbox.detach().cpu(), [x.cpu() for x in grads]
+
+    s_ref, b_ref, g_ref = run("cpu", False)
+    s, b, g_got = run(DEV, True)
+    assert torch.allclose(s, s_ref, rtol=1e-4, atol=1e-5) and torch.allclose(b, b_ref, rtol=1e-4, atol=1e-5)
+    names = ["d_feat", "d_qfeat", "bbox.weight", "bbox.bias", "cls0.weight", "cls0.bias", "cls1.weight", "cls1.bias"]
+    for n, a_, r_ in zip(names, g_got, g_ref):
+        err = float((a_ - r_).abs().max() / r_.abs().max())
+        assert err < 1e-4, (n, err)
+    d_top = mean_pool_backward(g_got[0].to(DEV)).cpu()
+    assert torch.equal(d_top, (g_got[0] / 16).unsqueeze(1).expand(G, 16, 2048))
