@@ -33,7 +33,7 @@ PRE_NMS, NMS_THR = 6000, 0.7
 FLOP_PER_PAIR = 1.494e9          # de-duplicated algorithmic FLOPs per pair (SURVEY 8d / BASELINE.md section 3)
 FLOP_PER_UNIT_SHARED = 0.214e9 + 0.646e9
 METRIC = "proposal-query pairs/sec (ROIAlign+AIT head+NMS)"
-FFN_W1_DRAM_BYTES = {"tf32": 0.343995e9 + 1.210071e9, "fp32": 0.331552e9 + 1.212555e9, "bf16": 0.159692e9 + 0.576510e9}   # ncu --set full: profiles/r01c_{fp32,bf16}_ncu_full_selected.csv (tf32: r01)
+FFN_W1_DRAM_BYTES = {"tf32": 0.343995e9 + 1.210071e9, "fp32": 0.396144e9 + 1.210431e9, "bf16": 0.159469e9 + 0.578038e9}   # ncu --set full: profiles/r01d_{fp32,bf16}_ncu_full_selected.csv (tf32: r01)
 
 
 def parse():

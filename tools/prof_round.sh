@@ -1,6 +1,6 @@
 set -x
-mkdir -p gpurun_out/r01c
-O=gpurun_out/r01c
+mkdir -p gpurun_out/r01d
+O=gpurun_out/r01d
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err
 python bench.py > $O/bench_fp32.json 2> $O/bench_fp32.err
 python bench.py --dtype tf32 > $O/bench_tf32.json 2> $O/bench_tf32.err
