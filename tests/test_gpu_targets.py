@@ -222,3 +222,42 @@ def test_score_heads_training_step_matches_autograd():
         assert err < 1e-4, (n, err)
     d_top = mean_pool_backward(g_got[0].to(DEV)).cpu()
     assert torch.equal(d_top, (g_got[0] / 16).unsqueeze(1).expand(G, 16, 2048))
+
+
+def test_target_layer_edge_cases():
+    """An image without ground truth (anchor layer: all background, sampled to 256; proposal layer: the reference's
+    ValueError), foreground-only and background-only images (the with-replacement branches), a single gt slot."""
+    from ait_b200.targets import AnchorTargetLayer, ProposalTargetLayer
+    from ait_b200.proposal import generate_anchors
+    from oracle import target_oracle as T
+    base = torch.from_numpy(generate_anchors(scales=np.array([8, 16, 32]), ratios=np.array([0.5, 1, 2]))).float()
+    H, W = 19, 31
+    im_info = torch.tensor([[300.0, 500.0, 1.0]] * 2)
+    gt, nb = T.synth_gt_boxes(21, 2)
+    gt[1] = 0                                        # image 1: no ground truth at all
+    at = AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2]).to(DEV)
+    np.random.seed(5)
+    ref = T.anchor_target(base, H, W, 16, gt, im_info)
+    np.random.seed(5)
+    out = at((torch.zeros(2, 18, H, W, device=DEV), gt.to(DEV), im_info.to(DEV), nb.to(DEV)))
+    _check_anchor(out, ref)
+    assert int((ref[0][1] == 1).sum()) == 0 and int((ref[0][1] == 0).sum()) == 256
+    rois = T.synth_rois(22, 2, 100, gt)
+    pt = ProposalTargetLayer(2)
+    with pytest.raises(ValueError):
+        pt(rois.to(DEV), gt.to(DEV), nb.to(DEV))
+    # foreground only (every roi sits on a gt box) / background only (rois overlap the gt a little, never >= 0.5)
+    gt1 = torch.zeros(2, 1, 5)
+    gt1[:, 0] = torch.tensor([100.0, 80.0, 260.0, 220.0, 1.0])
+    r = torch.zeros(2, 60, 5)
+    r[0, :, 1:] = gt1[0, 0, :4] + torch.randn(60, 4, generator=torch.Generator().manual_seed(1)) * 2.0
+    r[1, :, 1:] = torch.tensor([180.0, 150.0, 420.0, 290.0]) + torch.randn(60, 4, generator=torch.Generator().manual_seed(2)) * 3.0
+    r[1, :, 0] = 1
+    stage = {}
+    np.random.seed(6)
+    ref = T.proposal_target(r, gt1, stage=stage)
+    assert float(stage["max_overlaps"][0].min()) >= 0.5            # image 0: no background candidate
+    np.random.seed(6)
+    out = pt(r.to(DEV), gt1.to(DEV), None)
+    _check_proposal(out, ref)
+    assert bool((ref[1][0] == 1).all())
