@@ -150,6 +150,8 @@ SIGNATURES = {
     "aitb_anchor_target_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "aitb_anchor_target_assign": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_anchor_target_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aitb_anchor_target_subsample_device": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_uint64, _vp]),
+    "aitb_proposal_target_picks_device": (_i, [_vp, _i, _i, _i, C.c_uint64, _vp, _vp, _vp, _vp]),
     "aitb_proposal_target_assign": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "aitb_proposal_target_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

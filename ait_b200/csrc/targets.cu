@@ -236,6 +236,133 @@ anchor_subsample_kernel(int8_t* __restrict__ labels, int total, const uint8_t* _
   if (threadIdx.x == 0) n_examples[b] = s_left;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side sampling (no host round trip): the same selections drawn from a counter-based generator instead of
+// numpy's stream.  Philox4x32-10 keyed by (seed, image, list, candidate index) gives every candidate an independent
+// uniform 32-bit key; "a uniformly random subset of size k" = the k smallest keys (radix select in shared memory),
+// "rand * n with replacement" = a key per output slot.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ uint32_t cand_key(uint64_t seed, int image, int list, int idx) {
+  return philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)image, (uint32_t)list, 0x5eedu),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x;
+}
+
+// keep the `keep` candidates (lab[i] == L) with the smallest keys, set the others to -1.  Whole CTA; s_hist[256], s_sel[3].
+__device__ void keep_smallest_keys(int8_t* __restrict__ lab, int total, int L, int n_cand, int keep, uint64_t seed, int image,
+                                   int* s_hist, int* s_sel) {
+  if (n_cand <= keep) return;                       // CTA-uniform
+  uint32_t prefix = 0;
+  int remaining = keep;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+      if (lab[i] == L) {
+        const uint32_t k = cand_key(seed, image, L, i);
+        if (pass == 3 || (k >> (8 * (pass + 1))) == prefix) atomicAdd(&s_hist[(k >> (8 * pass)) & 255u], 1);
+      }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, b = 0;
+      for (; b < 256; ++b) {
+        if (cum + s_hist[b] >= remaining) break;
+        cum += s_hist[b];
+      }
+      s_sel[0] = b;
+      s_sel[1] = remaining - cum;                  // how many to take from bin b
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | (uint32_t)s_sel[0];
+    remaining = s_sel[1];
+    __syncthreads();
+  }
+  // keys < prefix stay; keys == prefix: `remaining` of them (32-bit ties are ~n^2 / 2^33 rare; any of them is a valid draw)
+  if (threadIdx.x == 0) s_sel[2] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    if (lab[i] == L) {
+      const uint32_t k = cand_key(seed, image, L, i);
+      if (k > prefix || (k == prefix && atomicAdd(&s_sel[2], 1) >= remaining)) lab[i] = -1;
+    }
+  __syncthreads();
+}
+
+// anchor target sub-sampling on the device (anchor_target_layer.py:130-152): at most num_fg foreground anchors, then
+// rpn_batch - (#fg kept) background anchors.  One CTA per image; counts [B, 2] from the assign phase.
+__global__ void __launch_bounds__(1024)
+anchor_subsample_device_kernel(int8_t* __restrict__ labels, int total, const int32_t* __restrict__ counts, int num_fg, int rpn_batch,
+                               uint64_t seed) {
+  __shared__ int s_hist[256];
+  __shared__ int s_sel[3];
+  const int b = blockIdx.x;
+  int8_t* lab = labels + (size_t)b * total;
+  const int n_f = counts[b * 2], n_b = counts[b * 2 + 1];
+  keep_smallest_keys(lab, total, 1, n_f, num_fg, seed, b, s_hist, s_sel);
+  const int fg_left = min(n_f, num_fg);
+  keep_smallest_keys(lab, total, 0, n_b, rpn_batch - fg_left, seed, b, s_hist, s_sel);
+}
+
+// proposal target picks on the device (proposal_target_layer_cascade.py:154-199): fg_this = min(fg_per_image, nf)
+// distinct foreground ranks in random order (rank of the rank's key among all nf keys), the other slots background
+// ranks with replacement (floor(u * nb)); foreground-only / background-only images fill all S slots with replacement.
+// picks [B, S], n_fg_pick [B]; *bad = 1 for an image with no candidate at all (the reference raises there).
+__global__ void __launch_bounds__(1024)
+proposal_picks_device_kernel(const int32_t* __restrict__ counts, int S, int fg_per_image, uint64_t seed, int32_t* __restrict__ picks,
+                             int32_t* __restrict__ n_fg_pick, int32_t* __restrict__ bad) {
+  const int b = blockIdx.x;
+  const int nf = counts[b * 2], nb = counts[b * 2 + 1];
+  int fg_this;
+  if (nf > 0 && nb > 0) fg_this = min(fg_per_image, nf);
+  else if (nf > 0) fg_this = S;
+  else fg_this = 0;
+  if (threadIdx.x == 0) {
+    n_fg_pick[b] = fg_this;
+    if (nf == 0 && nb == 0) *bad = 1;
+  }
+  int32_t* pk = picks + (size_t)b * S;
+  if (nf == 0 && nb == 0) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) pk[j] = -1;
+    return;
+  }
+  const bool distinct_fg = nf > 0 && nb > 0;
+  __shared__ uint32_t s_key[4096];
+  if (distinct_fg) {
+    // position of rank r in the key order; the first fg_this positions are the sample (a uniform permutation prefix)
+    const bool cached = nf <= 4096;
+    if (cached)
+      for (int r = threadIdx.x; r < nf; r += blockDim.x) s_key[r] = cand_key(seed, b, 2, r);
+    __syncthreads();
+    for (int r = threadIdx.x; r < nf; r += blockDim.x) {
+      const uint32_t kr = cached ? s_key[r] : cand_key(seed, b, 2, r);
+      int pos = 0;
+      for (int q = 0; q < nf; ++q) {
+        const uint32_t kq = cached ? s_key[q] : cand_key(seed, b, 2, q);
+        pos += (kq < kr) || (kq == kr && q < r);
+      }
+      if (pos < fg_this) pk[pos] = r;
+    }
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const bool is_fg = j < fg_this;
+    if (is_fg && distinct_fg) continue;
+    const int n = is_fg ? nf : nb;
+    const uint32_t u = cand_key(seed, b, 3, j);
+    pk[j] = (int)(((uint64_t)u * (uint64_t)n) >> 32);         // floor(u / 2^32 * n)
+  }
+}
+
 // phase 2b: the four outputs in the reference's layouts (anchor_target_layer.py:155-197):
 //   labels [B, 1, A*H, W] (index a*H*W + cell), bbox_targets / inside / outside weights [B, 4A, H, W] (channel a*4 + j)
 // outside weight = 1 / (examples of the LAST image) for every sampled anchor (:161-168, RPN_POSITIVE_WEIGHT < 0)
@@ -615,6 +742,20 @@ int aitb_anchor_target_finish(const float* base_anchors, const float* gt_boxes, 
                                                                    n_examples, B, inside_weight, labels_out, bbox_targets,
                                                                    inside_w, outside_w);
   return check_launch("anchor_emit_kernel");
+}
+
+int aitb_anchor_target_subsample_device(int8_t* labels, const int32_t* counts, int B, int total, int num_fg, int rpn_batch,
+                                        uint64_t seed, aitb_stream_t stream) {
+  AITB_REQUIRE(labels && counts && B > 0 && total > 0 && num_fg >= 0 && rpn_batch >= num_fg, "aitb_anchor_target_subsample_device: bad arguments");
+  anchor_subsample_device_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(labels, total, counts, num_fg, rpn_batch, seed);
+  return check_launch("anchor_subsample_device_kernel");
+}
+
+int aitb_proposal_target_picks_device(const int32_t* counts, int B, int S, int fg_per_image, uint64_t seed, int32_t* picks,
+                                      int32_t* n_fg_pick, int32_t* bad_flag, aitb_stream_t stream) {
+  AITB_REQUIRE(counts && picks && n_fg_pick && bad_flag && B > 0 && S > 0 && fg_per_image > 0, "aitb_proposal_target_picks_device: bad arguments");
+  proposal_picks_device_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(counts, S, fg_per_image, seed, picks, n_fg_pick, bad_flag);
+  return check_launch("proposal_picks_device_kernel");
 }
 
 int aitb_proposal_target_assign(const float* rois, const float* gt_boxes, int B, int R, int K, float fg_thr, float bg_hi,

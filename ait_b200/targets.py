@@ -15,6 +15,9 @@ exactly the reference's calls in the reference's order, so after `np.random.seed
 anchors and rois as the reference, bit for bit.  The candidate lists never leave the device: the host only sends
 RANKS (positions in the ascending candidate lists), 128 ints or a byte mask per image.
 `rng=<np.random.Generator>` draws from a private generator instead (same distribution, independent stream).
+`rng="device"` keeps the whole layer on the device: the selections are drawn by a counter-based generator inside the
+library (Philox4x32-10 keyed by `seed`, the call counter, the image and the candidate), so there is NO device->host
+read and no synchronisation -- the mode for training throughput when bit parity with numpy's stream is not needed.
 
 There is no CPU fallback: CPU tensors raise.
 """
@@ -45,15 +48,16 @@ def _rng(rng):
             permutation = staticmethod(rng.permutation)
             rand = staticmethod(lambda n: rng.random(n))
         return _G
-    raise RuntimeError("rng must be \"numpy\" (the reference's global stream) or a numpy.random.Generator")
+    raise RuntimeError("rng must be \"numpy\" (the reference's global stream), a numpy.random.Generator or \"device\"")
 
 
 class AnchorTargetLayer(nn.Module):
     """forward(input) with input = (rpn_cls_score [B,2A,H,W], gt_boxes [B,K,5], im_info [B,3], num_boxes) ->
     [labels [B,1,A*H,W], bbox_targets [B,4A,H,W], bbox_inside_weights, bbox_outside_weights] (CUDA fp32)."""
 
-    def __init__(self, feat_stride, scales, ratios, cfg=None, rng="numpy"):
+    def __init__(self, feat_stride, scales, ratios, cfg=None, rng="numpy", seed=0):
         super().__init__()
+        self.seed, self._calls = int(seed), 0
         self._feat_stride = feat_stride
         self._scales = scales
         self.register_buffer("_anchors", torch.from_numpy(
@@ -88,10 +92,16 @@ class AnchorTargetLayer(nn.Module):
                                               float(cfg["RPN_NEGATIVE_OVERLAP"]), float(cfg["RPN_POSITIVE_OVERLAP"]),
                                               1 if cfg["RPN_CLOBBER_POSITIVES"] else 0, L.ptr(labels), L.ptr(argmax),
                                               L.ptr(counts), L.ptr(ws), ws_bytes, L.stream_ptr()))
+        num_fg = int(cfg["RPN_FG_FRACTION"] * cfg["RPN_BATCHSIZE"])
+        if self.rng == "device":
+            self._calls += 1
+            L.check(lib.aitb_anchor_target_subsample_device(L.ptr(labels), L.ptr(counts), B, total, num_fg, int(cfg["RPN_BATCHSIZE"]),
+                                                            C.c_uint64((self.seed * 0x9E3779B97F4A7C15 + self._calls) & (2 ** 64 - 1)),
+                                                            L.stream_ptr()))
+            return self._finish(lib, base, gt, B, A, H, W, K, labels, argmax, None, 1, cfg, dev)
         # the one host round trip: (#fg, #bg) per image decide how many random numbers the reference draws (:130-152)
         cnt = counts.cpu().numpy()
         rnd = _rng(self.rng)
-        num_fg = int(cfg["RPN_FG_FRACTION"] * cfg["RPN_BATCHSIZE"])
         ld = int(max(1, cnt.max()))
         drop = np.zeros((B, 2, ld), dtype=np.uint8)
         any_drop = False
@@ -109,6 +119,9 @@ class AnchorTargetLayer(nn.Module):
                 drop[i, 1, perm[:n_b - num_bg]] = 1
                 any_drop = True
         drop_d = torch.from_numpy(drop).to(dev, non_blocking=False) if any_drop else None
+        return self._finish(lib, base, gt, B, A, H, W, K, labels, argmax, drop_d, ld, cfg, dev)
+
+    def _finish(self, lib, base, gt, B, A, H, W, K, labels, argmax, drop_d, ld, cfg, dev):
         n_examples = torch.empty((B,), dtype=torch.int32, device=dev)
         labels_out = torch.empty((B, 1, A * H, W), dtype=torch.float32, device=dev)
         targets = torch.empty((B, 4 * A, H, W), dtype=torch.float32, device=dev)
@@ -125,8 +138,9 @@ class ProposalTargetLayer(nn.Module):
     """forward(all_rois [B,R,5], gt_boxes [B,K,5], num_boxes) -> rois [B,128,5], labels [B,128], bbox_targets,
     bbox_inside_weights, bbox_outside_weights [B,128,4] (CUDA fp32)."""
 
-    def __init__(self, nclasses, cfg=None, rng="numpy"):
+    def __init__(self, nclasses, cfg=None, rng="numpy", seed=0):
         super().__init__()
+        self.seed, self._calls = int(seed), 0
         self._num_classes = nclasses
         self.cfg = dict(TRAIN_CFG, **(cfg or {}))
         self.rng = rng
@@ -151,6 +165,15 @@ class ProposalTargetLayer(nn.Module):
         L.check(lib.aitb_proposal_target_assign(L.ptr(rois), L.ptr(gt), B, R, K, float(cfg["FG_THRESH"]),
                                                 float(cfg["BG_THRESH_HI"]), float(cfg["BG_THRESH_LO"]), L.ptr(max_ov),
                                                 L.ptr(assign), L.ptr(cls), L.ptr(counts), L.stream_ptr()))
+        if self.rng == "device":
+            self._calls += 1
+            picks_d = torch.empty((B, S), dtype=torch.int32, device=dev)
+            nfp_d = torch.empty((B,), dtype=torch.int32, device=dev)
+            bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+            L.check(lib.aitb_proposal_target_picks_device(L.ptr(counts), B, S, fg_per_image,
+                                                          C.c_uint64((self.seed * 0x9E3779B97F4A7C15 + self._calls) & (2 ** 64 - 1)),
+                                                          L.ptr(picks_d), L.ptr(nfp_d), L.ptr(bad), L.stream_ptr()))
+            return self._sample(lib, rois, gt, B, R, K, N, S, cls, assign, picks_d, nfp_d, bad, cfg, dev)
         cnt = counts.cpu().numpy()                                        # the one host round trip (see module doc)
         rnd = _rng(self.rng)
         picks = np.zeros((B, S), dtype=np.int32)
@@ -172,8 +195,11 @@ class ProposalTargetLayer(nn.Module):
             n_fg_pick[i] = fg_this
         picks_d = torch.from_numpy(picks).to(dev)
         nfp_d = torch.from_numpy(n_fg_pick).to(dev)
-        lists = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
         bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        return self._sample(lib, rois, gt, B, R, K, N, S, cls, assign, picks_d, nfp_d, bad, cfg, dev)
+
+    def _sample(self, lib, rois, gt, B, R, K, N, S, cls, assign, picks_d, nfp_d, bad, cfg, dev):
+        lists = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
         rois_out = torch.zeros((B, S, 5), dtype=torch.float32, device=dev)
         labels = torch.zeros((B, S), dtype=torch.float32, device=dev)
         targets = torch.zeros((B, S, 4), dtype=torch.float32, device=dev)
@@ -186,7 +212,9 @@ class ProposalTargetLayer(nn.Module):
                                                 L.ptr(nfp_d), S, f4(*means), f4(*stds), f4(*cfg["BBOX_INSIDE_WEIGHTS"]),
                                                 L.ptr(lists), L.ptr(rois_out), L.ptr(labels), L.ptr(targets), L.ptr(inside),
                                                 L.ptr(outside), L.ptr(bad), L.stream_ptr()))
-        self.last_bad_flag = bad   # device flag: non-zero only if a pick fell outside its list (never with our draws)
+        # device flag: non-zero if a pick fell outside its list (never with our draws) or, in the "device" mode, if an
+        # image had neither foreground nor background candidates (where the host modes raise like the reference)
+        self.last_bad_flag = bad
         return rois_out, labels, targets, inside, outside
 
 

@@ -423,7 +423,17 @@ int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, in
  *   aitb_rcnn_loss: score [bs*P,2], bbox_pred [bs*P,4], labels [bs*P] -> losses[0] = cross entropy, losses[1] =
  *     margin_scale * MarginRankingLoss(margin)(|p_i-p_j|, |l_i-l_j|, target), losses[2] = smooth L1 (sigma 1);
  *     cls_prob [bs*P] = softmax(score)[:,1]; gradients as above with gscale[3]; acc: 3 doubles of scratch.
+ * Device-side sampling (no host round trip; Philox4x32-10 keyed by seed / image / candidate, same distributions as the
+ * reference's numpy draws but an independent stream):
+ *   aitb_anchor_target_subsample_device: between _assign and _finish(drop = NULL): keeps the num_fg foreground and
+ *     rpn_batch - #fg background anchors with the smallest keys, disables the rest in `labels`.
+ *   aitb_proposal_target_picks_device: fills picks / n_fg_pick for aitb_proposal_target_sample from counts; an image
+ *     without any candidate sets *bad_flag and -1 picks (the reference raises).
  * ---------------------------------------------------------------------------------------- */
+int aitb_anchor_target_subsample_device(int8_t* labels, const int32_t* counts, int B, int total, int num_fg, int rpn_batch,
+                                        uint64_t seed, aitb_stream_t stream);
+int aitb_proposal_target_picks_device(const int32_t* counts, int B, int S, int fg_per_image, uint64_t seed, int32_t* picks,
+                                      int32_t* n_fg_pick, int32_t* bad_flag, aitb_stream_t stream);
 size_t aitb_anchor_target_workspace_bytes(int B, int A, int H, int W, int K);
 int aitb_anchor_target_assign(const float* base_anchors, const float* gt_boxes, const float* im_info, int B, int A, int H,
                               int W, int K, float feat_stride, float neg_thr, float pos_thr, int clobber_positives,

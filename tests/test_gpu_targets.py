@@ -261,3 +261,77 @@ def test_target_layer_edge_cases():
     out = pt(r.to(DEV), gt1.to(DEV), None)
     _check_proposal(out, ref)
     assert bool((ref[1][0] == 1).all())
+
+
+def test_device_rng_sampling():
+    """rng="device": no host round trip.  Same invariants as the reference's sampling (counts, subset of the candidates,
+    <= 32 distinct foreground rois first), deterministic per (seed, call), different across calls and seeds, and
+    uniform: over many draws every candidate is kept about equally often."""
+    from ait_b200.targets import AnchorTargetLayer, ProposalTargetLayer
+    from ait_b200.proposal import generate_anchors
+    from oracle import target_oracle as T
+    B, H, W = 4, 38, 63
+    gt, nb = T.synth_gt_boxes(9, B, im_h=600.0, im_w=1000.0, n_min=3, n_max=12)
+    rois = T.synth_rois(10, B, 2000, gt, im_h=600.0, im_w=1000.0)
+    im_info = torch.tensor([[600.0, 1000.0, 1.0]] * B)
+    base = torch.from_numpy(generate_anchors(scales=np.array([8, 16, 32]), ratios=np.array([0.5, 1, 2]))).float()
+    stage = {}
+    T.anchor_target(base, H, W, 16, gt, im_info, stage=stage)
+    pre = torch.full((B, H * W * 9), -1.0)
+    pre[:, stage["inds_inside"]] = stage["labels_presample"]
+    pre = pre.view(B, H, W, 9).permute(0, 3, 1, 2).reshape(B, -1)
+    args = (torch.zeros(B, 18, H, W, device=DEV), gt.to(DEV), im_info.to(DEV), nb.to(DEV))
+
+    def run_anchor(seed, calls=1):
+        at = AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2], rng="device", seed=seed).to(DEV)
+        return [[t.cpu() for t in at(args)] for _ in range(calls)]
+
+    a1, a2, a3 = run_anchor(1, 2), run_anchor(1, 2), run_anchor(2, 1)
+    for x, y in zip(a1, a2):
+        assert all(torch.equal(p, q) for p, q in zip(x, y)), "not deterministic for the same (seed, call)"
+    assert not torch.equal(a1[0][0], a1[1][0]) and not torch.equal(a1[0][0], a3[0][0])
+    lab = a1[0][0].view(B, -1)
+    assert bool(((lab == pre) | (lab == -1)).all())
+    for b in range(B):
+        n_f, n_b = int((lab[b] == 1).sum()), int((lab[b] == 0).sum())
+        assert n_f == min(128, int((pre[b] == 1).sum())) and n_f + n_b == min(256, n_f + int((pre[b] == 0).sum()))
+    n_ex = int((lab[B - 1] >= 0).sum())
+    assert torch.equal(a1[0][3] > 0, (lab >= 0).view(B, 9, 1, H, W).expand(B, 9, 4, H, W).reshape(B, 36, H, W))
+    assert abs(float(a1[0][3].max()) - 1.0 / n_ex) < 1e-9
+    # uniformity of the background draw of image 0: 60 calls, every candidate kept with frequency ~ k / n
+    at = AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2], rng="device", seed=7).to(DEV)
+    cand = pre[0] == 0
+    hits = torch.zeros(int(cand.sum()))
+    calls = 60
+    for _ in range(calls):
+        hits += (at(args)[0].cpu().view(B, -1)[0][cand] == 0).float()
+    n, k = hits.numel(), float(hits.sum()) / calls
+    p = k / n
+    z = (hits - calls * p) / (calls * p * (1 - p)) ** 0.5
+    assert float(z.abs().max()) < 6.0 and abs(float(z.std()) - 1.0) < 0.15, (float(z.abs().max()), float(z.std()))
+
+    pt = ProposalTargetLayer(2, rng="device", seed=3)
+    r, l, t, wi, wo = [x.cpu() for x in pt(rois.to(DEV), gt.to(DEV), nb.to(DEV))]
+    assert int(pt.last_bad_flag.item()) == 0
+    assert r.shape == (B, 128, 5) and bool((l[:, 32:] == 0).all()) and bool((wi == wo).all())
+    cand_boxes = torch.cat([rois[..., 1:], gt[..., :4]], 1)
+    ref_stage = {}
+    np.random.seed(0)
+    T.proposal_target(rois, gt, stage=ref_stage)
+    for b in range(B):
+        assert bool((r[b, :, 0] == b).all())
+        match = (r[b, :, None, 1:] == cand_boxes[b, None]).all(-1)
+        assert bool(match.any(-1).all()), "sampled roi is not a candidate"
+        idx = match.float().argmax(-1)
+        mo = ref_stage["max_overlaps"][b][idx]
+        n_fg = min(32, int((ref_stage["max_overlaps"][b] >= 0.5).sum()))
+        assert bool((mo[:n_fg] >= 0.5).all()) and bool(((mo[n_fg:] < 0.5) & (mo[n_fg:] >= 0.1)).all())
+        assert len(set(idx[:n_fg].tolist())) == n_fg, "foreground rois must be drawn without replacement"
+        assert bool((l[b, :n_fg] == 1).all())
+    # an image without any candidate: flagged on the device instead of raised (no synchronisation in this mode)
+    gt0 = gt.clone()
+    gt0[1] = 0
+    rois0 = rois.clone()
+    rois0[1, :, 1:] = 0
+    pt(rois0.to(DEV), gt0.to(DEV), nb.to(DEV))
+    assert int(pt.last_bad_flag.item()) == 1
