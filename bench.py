@@ -166,7 +166,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = n_units * n_props / dt
     sample = "%d unit x %d proposals per step (top-%d NMS + head), %s" % (n_units, n_props, PRE_NMS, what)
-    print(json.dumps({
+    _emit(json.dumps({
         "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -222,9 +222,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout by default; stdout carries the one
-        # JSON line of this benchmark, so NCCL's log goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -417,13 +414,35 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+# stdout carries exactly ONE JSON line.  Libraries may print there too (NCCL writes its version banner with printf when
+# the communicator is created), so the process-level stdout is pointed at stderr for the whole run and the result line is
+# written to the original descriptor.
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    _quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
