@@ -160,6 +160,10 @@ SIGNATURES = {
     "aitb_heads_backward_workspace_bytes": (_sz, [_i, _i]),
     "aitb_heads_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_mean_pool_backward": (_i, [_vp, _i, _vp, _vp]),
+    "aitb_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "aitb_im2col3x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "aitb_map_subsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "aitb_map_upsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "aitb_rpn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aitb_rcnn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -1,0 +1,98 @@
+// Small data-movement kernels of the layer-4 (`RCNN_top`) training path (lib/model/faster_rcnn/
+// resnet_coatt_transformer_sk.py:73-109, 476-485; the reference gets the backward from torch autograd):
+//   relu_bwd        g = dy where the saved activation y > 0, else 0
+//   im2col3x3       [G, s, s, C] -> [G*s*s, 9*C] tap-major rows (zero padding): the 3x3 weight gradient then is ONE
+//                   wgrad GEMM dW[out, 9*C] += dY^T * cols, in the same tap-major layout the forward packs its weights in
+//   map_subsample   [G, S, S, C] -> [G, s, s, C] every `stride`-th position (the stride-2 1x1 convolutions of the first
+//                   bottleneck read exactly these rows)
+//   map_upsample    its adjoint: scatter to the strided positions, zeros elsewhere
+// fp32, HBM-bound, 128-bit accesses (C % 4 == 0).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aitb200.h"
+#include "common.cuh"
+
+namespace aitb {
+
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 d = dy[i], a = y[i];
+    out[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+  }
+}
+
+// one CTA per output row (g, y, x); thread -> (tap, channel quad)
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, int s, int C, float* __restrict__ out) {
+  const int row = blockIdx.x;
+  const int g = row / (s * s), p = row - g * s * s, py = p / s, px = p - py * s;
+  const int c4 = C / 4;
+  float4* o = reinterpret_cast<float4*>(out + (size_t)row * 9 * C);
+  for (int i = threadIdx.x; i < 9 * c4; i += blockDim.x) {
+    const int tap = i / c4, c = i - tap * c4;
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < s && xx >= 0 && xx < s)
+      v = reinterpret_cast<const float4*>(x + ((size_t)(g * s + yy) * s + xx) * C)[c];
+    o[i] = v;
+  }
+}
+
+// gather = 1: out [G, s, s, C] = x [G, S, S, C] at (stride*y, stride*x); gather = 0: out [G, S, S, C] = scatter of x [G, s, s, C]
+__global__ void __launch_bounds__(256)
+map_resample_kernel(const float* __restrict__ x, int S, int s, int stride, int C, int gather, float* __restrict__ out) {
+  const int c4 = C / 4;
+  if (gather) {
+    const int row = blockIdx.x;                       // (g, y, x) of the small map
+    const int g = row / (s * s), p = row - g * s * s, py = p / s, px = p - py * s;
+    const float4* src = reinterpret_cast<const float4*>(x + ((size_t)(g * S + py * stride) * S + px * stride) * C);
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * C);
+    for (int i = threadIdx.x; i < c4; i += blockDim.x) dst[i] = src[i];
+  } else {
+    const int row = blockIdx.x;                       // (g, y, x) of the large map
+    const int g = row / (S * S), p = row - g * S * S, py = p / S, px = p - py * S;
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * C);
+    const bool hit = py % stride == 0 && px % stride == 0 && py / stride < s && px / stride < s;
+    const float4* src = reinterpret_cast<const float4*>(x + ((size_t)(g * s + py / stride) * s + px / stride) * C);
+    for (int i = threadIdx.x; i < c4; i += blockDim.x) dst[i] = hit ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+}  // namespace aitb
+
+using namespace aitb;
+
+extern "C" {
+
+int aitb_relu_bwd(const float* dy, const float* y, float* out, size_t n, aitb_stream_t stream) {
+  AITB_REQUIRE(dy && y && out && n > 0 && n % 4 == 0, "aitb_relu_bwd: bad arguments (n must be a positive multiple of 4)");
+  AITB_REQUIRE((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)out) & 15) == 0, "aitb_relu_bwd: pointers must be 16-byte aligned");
+  const size_t n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < (size_t)(8 * current_sm_count()) ? (n4 + 255) / 256 : 8 * current_sm_count());
+  relu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y),
+                                                            reinterpret_cast<float4*>(out), n4);
+  return check_launch("relu_bwd_kernel");
+}
+
+int aitb_im2col3x3(const float* x, int G, int s, int C, float* out, aitb_stream_t stream) {
+  AITB_REQUIRE(x && out && G > 0 && s > 0 && C > 0 && C % 4 == 0, "aitb_im2col3x3: bad arguments");
+  AITB_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "aitb_im2col3x3: pointers must be 16-byte aligned");
+  im2col3x3_kernel<<<G * s * s, 256, 0, (cudaStream_t)stream>>>(x, s, C, out);
+  return check_launch("im2col3x3_kernel");
+}
+
+int aitb_map_subsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream) {
+  AITB_REQUIRE(x && out && G > 0 && S > 0 && s > 0 && stride > 0 && (s - 1) * stride < S && C % 4 == 0, "aitb_map_subsample: bad arguments");
+  map_resample_kernel<<<G * s * s, 256, 0, (cudaStream_t)stream>>>(x, S, s, stride, C, 1, out);
+  return check_launch("map_resample_kernel");
+}
+
+int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream) {
+  AITB_REQUIRE(x && out && G > 0 && S > 0 && s > 0 && stride > 0 && (s - 1) * stride < S && C % 4 == 0, "aitb_map_upsample: bad arguments");
+  map_resample_kernel<<<G * S * S, 256, 0, (cudaStream_t)stream>>>(x, S, s, stride, C, 0, out);
+  return check_launch("map_resample_kernel");
+}
+
+}  // extern "C"

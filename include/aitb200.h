@@ -484,6 +484,16 @@ int aitb_heads_backward(const float* feat, const float* qfeat, const float* hidd
                         size_t workspace_bytes, aitb_stream_t stream);
 int aitb_mean_pool_backward(const float* d_feat, int G, float* d_top, aitb_stream_t stream);
 
+/* Data-movement helpers of the layer-4 (`RCNN_top`) training path (ait_b200/csrc/train_aux.cu, composed with aitb_gemm /
+ * aitb_wgrad by ait_b200/top_train.py), fp32, C % 4 == 0:
+ *   aitb_relu_bwd      out[i] = y[i] > 0 ? dy[i] : 0
+ *   aitb_im2col3x3     x [G,s,s,C] -> out [G*s*s, 9*C], tap-major (ky, kx, c), zero padding
+ *   aitb_map_subsample x [G,S,S,C] -> out [G,s,s,C] at (stride*y, stride*x);  aitb_map_upsample: its adjoint (zeros elsewhere) */
+int aitb_relu_bwd(const float* dy, const float* y, float* out, size_t n, aitb_stream_t stream);
+int aitb_im2col3x3(const float* x, int G, int s, int C, float* out, aitb_stream_t stream);
+int aitb_map_subsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
+int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 

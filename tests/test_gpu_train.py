@@ -203,3 +203,75 @@ def test_ait_training_step_matches_reference_golden_gradients():
         sample = gr[::ref["stride"]][:ref["sample"].numel()]
         assert _l2rel(sample, ref["sample"].double()) < 6e-2, name
         assert abs(float(gr.double().norm()) / ref["norm"] - 1.0) < 4e-2, name
+
+
+@pytest.mark.parametrize("G", [19, 48])
+def test_head_to_tail_training_matches_oracle_autograd(G):
+    """`_head_to_tail` (layer4 with frozen, randomised BatchNorm + 4x4 mean) forward and backward on the device
+    (tf32 tensor-core math): output, input gradient and the gradients of all ten convolution weights; ragged row
+    counts (G*16 not a multiple of the 128-row tiles).  Two references: (1) fp64 autograd over the oracle restatement
+    -- gate 6e-2, because a tf32 forward flips the ReLU mask of the units whose pre-activation is within tf32 error
+    of zero (nine ReLUs deep; measured 0.7 % at the last block growing to 4.7 % at the input); (2) the same fp64 graph
+    with ReLU(x) = x * mask and the masks taken from the device forward -- gate 2e-3 (measured 4-8e-4): the
+    arithmetic itself."""
+    import torch.nn.functional as F
+    from ait_b200 import synth, top_train
+    from ait_b200.top_train import head_to_tail_train
+    from oracle import head_oracle
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+    top = head.RCNN_top
+    sd = {k: v.clone() for k, v in top.state_dict().items()}
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(G, 1024, 8, 8, generator=g).relu()
+    gy = torch.randn(G, 2048, generator=g)
+    names = [k for k in sd if k.endswith("weight") and sd[k].dim() == 4]
+    assert len(names) == 10
+    ref_w = {k: sd[k].double().requires_grad_() for k in names}
+    xr = x.double().requires_grad_()
+    sd64 = {k: (ref_w[k] if k in ref_w else v.double()) for k, v in sd.items()}
+    ref = head_oracle.head_to_tail(sd64, xr, dtype=torch.float64)
+    ref.backward(gy.double())
+    # device
+    top = top.to(DEV)
+    for p in top.parameters():
+        p.requires_grad_(p.dim() == 4)
+    xd = x.to(DEV).requires_grad_()
+    out = head_to_tail_train(top, xd)
+    out.backward(gy.to(DEV))
+    got = dict(top.named_parameters())
+
+    def rel(a, b):
+        return float((a.double().cpu() - b).norm() / b.norm())
+
+    assert rel(out.detach(), ref.detach()) < 2e-3
+    assert rel(xd.grad, xr.grad) < 6e-2
+    for k in names:
+        assert rel(got[k].grad, ref_w[k].grad) < 6e-2, k
+    # (2) the reference with the device's masks
+    masks = [[(t > 0).double().cpu() for t in blk] for blk in top_train._last_saved_for_tests]
+
+    def tok2map(m):  # [G*16, C] token-major -> [G, C, 4, 4]
+        return m.view(G, 4, 4, -1).permute(0, 3, 1, 2)
+
+    def bn(t, pre):
+        w, b, rm, rv = (sd[pre + e].double() for e in (".weight", ".bias", ".running_mean", ".running_var"))
+        return (t - rm.view(1, -1, 1, 1)) / torch.sqrt(rv.view(1, -1, 1, 1) + 1e-5) * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+
+    w2 = {k: sd[k].double().requires_grad_() for k in names}
+    x2 = x.double().requires_grad_()
+    cur = x2
+    for b in range(3):
+        pre = "0.%d." % b
+        m1, m2, m3 = (tok2map(m) for m in masks[b])
+        o = bn(F.conv2d(cur, w2[pre + "conv1.weight"], stride=2 if b == 0 else 1), pre + "bn1") * m1
+        o = bn(F.conv2d(o, w2[pre + "conv2.weight"], padding=1), pre + "bn2") * m2
+        o = bn(F.conv2d(o, w2[pre + "conv3.weight"]), pre + "bn3")
+        res = bn(F.conv2d(cur, w2[pre + "downsample.0.weight"], stride=2), pre + "downsample.1") if b == 0 else cur
+        cur = (o + res) * m3
+    ref2 = cur.mean(3).mean(2)
+    ref2.backward(gy.double())
+    assert rel(out.detach(), ref2.detach()) < 2e-3
+    assert rel(xd.grad, x2.grad) < 2e-3, rel(xd.grad, x2.grad)
+    for k in names:
+        e = rel(got[k].grad, w2[k].grad)
+        assert e < 2e-3, (k, e)
