@@ -59,5 +59,36 @@ class DetectionHead(nn.Module):
         """non_img [B,1024,H,W] C4 map, non_qry [B,1024,8,8], rois [B,P,5] (batch idx, x1,y1,x2,y2)
         -> cls_prob [B,P,1], bbox_pred [B,P,4]   (+ dict of intermediates when taps=True)."""
         if self.training:
-            raise RuntimeError("ait_b200.DetectionHead: inference only in this round (call .eval())")
+            raise RuntimeError("ait_b200.DetectionHead: .forward is the inference engine (call .eval()); the training step "
+                               "is .forward_train / .training_losses")
         return self.engine().head_forward(non_img, non_qry, rois, taps=taps)
+
+    def forward_train(self, non_img, non_qry, rois):
+        """The same slice of `_fasterRCNN.forward` (:273-335) as a differentiable training step (BASELINE config 4):
+        ROIAlign -> AIT -> SKNet -> `_head_to_tail` (pairs and queries) -> bbox / score heads, every stage with the
+        library's own forward-keeping-activations + backward (`_ROIAlign`, `_AITTrainFunction`, sk_train, top_train,
+        targets.score_heads; fp32 storage, tf32 tensor-core math, dropout 0).  Returns (score [B*P,2] logits,
+        bbox_pred [B*P,4]) -- what the reference's losses consume (:349-361).  Gradients reach non_img, non_qry and
+        every trainable parameter (AIT 46, the four SK convolutions + biases, the ten layer-4 convolutions -- BatchNorm is
+        frozen like `set_bn_fix` --, the three Linear layers); `sk.*.fc` / `sk.*.sk` get none, as in the reference,
+        whose SKBlock.forward discards them."""
+        from . import sk_train, targets, top_train
+        if not self.training:
+            raise RuntimeError("ait_b200.DetectionHead.forward_train: call .train() first")
+        if rois.dim() != 3 or rois.shape[2] != 5 or rois.shape[0] != non_qry.shape[0]:
+            raise RuntimeError("forward_train: rois must be [B,P,5] with B = number of (image, query) units")
+        P = rois.shape[1]
+        props = self.RCNN_roi_align(non_img, rois.reshape(-1, 5))                 # :279
+        props = self.transformer(x_props=props, x_query=non_qry)                  # :289
+        props, query = sk_train.sknet_train(self.sk, props, non_qry)              # :294
+        pf = top_train.head_to_tail_train(self.RCNN_top, props)                   # :299
+        qf = top_train.head_to_tail_train(self.RCNN_top, query)                   # :300
+        return targets.score_heads(pf, qf, P, self.RCNN_bbox_pred, self.RCNN_cls_score)   # :318-335
+
+    def training_losses(self, non_img, non_qry, rois, rois_label, rois_target, rois_inside_ws, rois_outside_ws):
+        """(RCNN_loss_cls, margin_loss, RCNN_loss_bbox) of faster_rcnn_coatt_transformer_sk.py:340-361 for the units'
+        sampled rois (the outputs of `ProposalTargetLayer`)."""
+        from . import targets
+        score, bbox_pred = self.forward_train(non_img, non_qry, rois)
+        return targets.rcnn_losses(score, bbox_pred, rois_label, rois_target, rois_inside_ws, rois_outside_ws,
+                                   rois.shape[0])

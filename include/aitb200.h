@@ -494,6 +494,16 @@ int aitb_im2col3x3(const float* x, int G, int s, int C, float* out, aitb_stream_
 int aitb_map_subsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
 int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
 
+/* SKNet training path (lib/model/modules/blocks_coatt_transformer_sk.py:960-998; composed with aitb_gemm / aitb_wgrad by
+ * ait_b200/sk_train.py; the reference gets the backward from torch autograd):
+ *   aitb_im2col3x3_grouped  like aitb_im2col3x3 with columns ordered (group, ky, kx, channel in group): the weight gradient
+ *                           of a grouped 3x3 convolution is one aitb_wgrad per group on a [rows, 9*group_c] slice
+ *   aitb_sk_combine         out = r1^2 + r3^2   (r1, r3: the post-ReLU 1x1 / 3x3 branch maps)
+ *   aitb_sk_combine_bwd     d1 = 2 dv r1, d3 = 2 dv r3, rounded to tf32 (nearest) */
+int aitb_im2col3x3_grouped(const float* x, int G, int s, int C, int group_c, float* out, aitb_stream_t stream);
+int aitb_sk_combine(const float* r1, const float* r3, float* out, size_t n, aitb_stream_t stream);
+int aitb_sk_combine_bwd(const float* dv, const float* r1, const float* r3, float* d1, float* d3, size_t n, aitb_stream_t stream);
+
 /* number of kernels launched by this thread through the library since the last reset */
 long long aitb_launch_count(int reset);
 
