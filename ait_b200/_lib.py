@@ -121,6 +121,7 @@ SIGNATURES = {
     "aitb_roi_align_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp]),
     "aitb_roi_align_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp]),
     "aitb_transpose_cs": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "aitb_transpose_cs_round": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aitb_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "aitb_attn_core": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "aitb_pool_heads": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -165,7 +166,7 @@ SIGNATURES = {
     "aitb_map_subsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "aitb_map_upsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "aitb_im2col3x3_grouped": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
-    "aitb_sk_combine": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "aitb_sk_combine": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "aitb_sk_combine_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_rpn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aitb_rcnn_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -951,6 +951,11 @@ int aitb_transpose_cs(const void* src, int src_dtype, void* dst, int dst_dtype, 
   return transpose_run(src, src_dtype, dst, dst_dtype, G, C, S, to_channels_last, (cudaStream_t)stream);
 }
 
+int aitb_transpose_cs_round(const void* src, int src_dtype, void* dst, int dst_dtype, int G, int C, int S,
+                            int to_channels_last, int round_tf32, aitb_stream_t stream) {
+  return transpose_run(src, src_dtype, dst, dst_dtype, G, C, S, to_channels_last, (cudaStream_t)stream, round_tf32);
+}
+
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream) { return gemm_run(d, (cudaStream_t)stream); }
 
 int aitb_attn_core(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,

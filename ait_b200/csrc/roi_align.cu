@@ -21,6 +21,7 @@
 //   of the (up to 4*grid) products differs (FMA), well inside the 1e-5 relative tolerance.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -301,7 +302,7 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
 // Backward (ROIAlign_cuda.cu:178-254): scatter g*w/count to the 4 taps.  Same CTA shape as the
 // forward; the NCHW grad slab is staged through shared memory, and the accumulation target is
 // channels-last so each atomic warp instruction hits 32 consecutive floats (red.global.add.v4
-// is not available for fp32 vectors before sm_90+ PTX; plain atomicAdd per component).
+// is used by the footprint kernel below; this per-tap scalar-atomic form stays for C % 4 != 0).
 __global__ void __launch_bounds__(256)
 roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ rois, int C, int H, int W, float scale,
                      int ph, int pw, int sampling_ratio, float* __restrict__ gfeat) {
@@ -347,6 +348,78 @@ roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ r
         atomicAdd(fb + ((size_t)ty.lo * W + tx.hi) * C, g2);
         atomicAdd(fb + ((size_t)ty.hi * W + tx.lo) * C, g3);
         atomicAdd(fb + ((size_t)ty.hi * W + tx.hi) * C, g4);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Footprint backward (C % 4 == 0): the adjoint of the forward kernel above, same CTA shape (roi, 128-channel slab; lane = 4
+// channels).  The 4*gh*gw bilinear taps of a bin land on (gh+1)(gw+1) distinct cells; their weights are folded per axis
+// (the forward's Foot tables), so a bin issues ONE 128-bit vector reduction (red.global.add.v4.f32, sm_90+) per footprint
+// cell into the channels-last gradient map instead of 4*gh*gw scalar atomics per channel: ~2x fewer bytes through the L2
+// atomic units and 4x fewer instructions than roi_align_bwd_kernel (kept for C % 4 != 0).  g*w/count (:238-246) becomes
+// g*(1/count)*Wy*Wx -- the same real-number sum re-associated; accumulation order is nondeterministic as in the reference.
+__global__ void __launch_bounds__(256)
+roi_align_bwd_foot_kernel(const float* __restrict__ grad, const float* __restrict__ rois, int C, int H, int W, float scale,
+                          int ph, int pw, int sampling_ratio, float* __restrict__ gfeat) {
+  __shared__ Foot xf[kMaxPooled];
+  __shared__ Foot yf[kMaxPooled];
+  extern __shared__ float stage[];  // [nbins][132]: the roi's gradient slab, bin-major so a lane reads its 4 channels as one float4
+  constexpr int kS = 132;
+  const int k = blockIdx.y;
+  const int c0 = blockIdx.x * 128;
+  const int nbins = ph * pw;
+  const RoiGeom g = roi_geometry(rois + (size_t)k * 5, scale, ph, pw, sampling_ratio);
+  const int gw = g.grid_w, gh = g.grid_h;
+  bool fits = true;
+  if ((int)threadIdx.x < pw) fits = build_foot(xf[threadIdx.x], g.start_w, threadIdx.x, g.bin_w, gw, W);
+  else if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + ph)
+    fits = build_foot(yf[threadIdx.x - 32], g.start_h, threadIdx.x - 32, g.bin_h, gh, H);
+  const int cvalid = min(128, C - c0);
+  const float* gb = grad + ((size_t)k * C + c0) * nbins;   // NCHW: the slab's cvalid * nbins values are contiguous
+  for (int i = threadIdx.x; i < cvalid * nbins; i += blockDim.x) {
+    const int c = i / nbins, bin = i - c * nbins;
+    stage[bin * kS + c] = __ldg(gb + i);
+  }
+  const bool tables = __syncthreads_and(fits) != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane * 4 >= cvalid) return;
+  float* fb = gfeat + (size_t)g.batch * H * W * C + c0 + lane * 4;
+  const float inv_count = __frcp_rn((float)(gh * gw));
+  const uint32_t uC = (uint32_t)C, rowC = (uint32_t)W * (uint32_t)C;
+  for (int bin = warp; bin < nbins; bin += 8) {
+    const int py = bin / pw, px = bin - py * pw;
+    float4 gv = *reinterpret_cast<const float4*>(stage + bin * kS + lane * 4);
+    gv.x *= inv_count; gv.y *= inv_count; gv.z *= inv_count; gv.w *= inv_count;
+    if (tables) {
+      const int ny = yf[py].n, nx = xf[px].n;
+      uint32_t r = (uint32_t)yf[py].c0 * rowC + (uint32_t)xf[px].c0 * uC;
+      for (int cy = 0; cy < ny; ++cy, r += rowC) {
+        const float wy = yf[py].w[cy];
+        if (wy == 0.f) continue;
+        uint32_t q = r;
+        for (int cx = 0; cx < nx; ++cx, q += uC) {
+          const float w = wy * xf[px].w[cx];
+          if (w != 0.f) red_add_v4(fb + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
+        }
+      }
+    } else {   // footprint wider than the tables (fixed sampling_ratio on a huge roi): per-sample taps
+      for (int iy = 0; iy < gh; ++iy) {
+        const Tap ty = make_tap(sample_coord(g.start_h, py, g.bin_h, iy, gh), H);
+        if (ty.wlo == 0.f && ty.whi == 0.f) continue;
+        for (int ix = 0; ix < gw; ++ix) {
+          const Tap tx = make_tap(sample_coord(g.start_w, px, g.bin_w, ix, gw), W);
+          if (tx.wlo == 0.f && tx.whi == 0.f) continue;
+          const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+          red_add_v4(fb + ((size_t)ty.lo * W + tx.lo) * C, make_float4(gv.x * w1, gv.y * w1, gv.z * w1, gv.w * w1));
+          red_add_v4(fb + ((size_t)ty.lo * W + tx.hi) * C, make_float4(gv.x * w2, gv.y * w2, gv.z * w2, gv.w * w2));
+          red_add_v4(fb + ((size_t)ty.hi * W + tx.lo) * C, make_float4(gv.x * w3, gv.y * w3, gv.z * w3, gv.w * w3));
+          red_add_v4(fb + ((size_t)ty.hi * W + tx.hi) * C, make_float4(gv.x * w4, gv.y * w4, gv.z * w4, gv.w * w4));
+        }
       }
     }
   }
@@ -458,6 +531,13 @@ int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H,
   AITB_REQUIRE(C >= 1, "aitb_roi_align_backward: bad C");
   AITB_REQUIRE(ph >= 1 && pw >= 1 && ph <= kMaxPooled && pw <= kMaxPooled, "aitb_roi_align_backward: pooled size unsupported");
   AITB_REQUIRE(K <= 65535, "aitb_roi_align_backward: K=%d exceeds one launch", K);
+  static const bool scalar_atomics = getenv("AITB_ROI_BWD_SCALAR") != nullptr;   // A/B: the per-tap scalar-atomic kernel
+  if (C % 4 == 0 && (((uintptr_t)gfeat) & 15) == 0 && (size_t)H * W * C < ((size_t)1 << 31) && !scalar_atomics) {
+    dim3 grid((C + 127) / 128, K);
+    const size_t smem = (size_t)ph * pw * 132 * 4;
+    roi_align_bwd_foot_kernel<<<grid, 256, smem, stream>>>(grad, rois, C, H, W, scale, ph, pw, sampling_ratio, gfeat);
+    return check_launch("roi_align_bwd_foot_kernel");
+  }
   dim3 grid((C + 31) / 32, K);
   const size_t smem = (size_t)32 * (ph * pw + 1) * 4;
   roi_align_bwd_kernel<<<grid, 256, smem, stream>>>(grad, rois, C, H, W, scale, ph, pw, sampling_ratio, gfeat);

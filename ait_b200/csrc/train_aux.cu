@@ -1,6 +1,6 @@
 // Small data-movement kernels of the layer-4 (`RCNN_top`) training path (lib/model/faster_rcnn/
 // resnet_coatt_transformer_sk.py:73-109, 476-485; the reference gets the backward from torch autograd):
-//   relu_bwd        g = dy where the saved activation y > 0, else 0
+//   relu_bwd        g = dy (rounded to tf32, nearest: it only feeds tensor-core GEMMs) where the saved activation y > 0, else 0
 //   im2col3x3       [G, s, s, C] -> [G*s*s, 9*C] tap-major rows (zero padding): the 3x3 weight gradient then is ONE
 //                   wgrad GEMM dW[out, 9*C] += dY^T * cols, in the same tap-major layout the forward packs its weights in
 //   map_subsample   [G, S, S, C] -> [G, s, s, C] every `stride`-th position (the stride-2 1x1 convolutions of the first
@@ -21,11 +21,18 @@
 
 namespace aitb {
 
+__device__ __forceinline__ float rn_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ out, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 d = dy[i], a = y[i];
-    out[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+    out[i] = make_float4(a.x > 0.f ? rn_tf32(d.x) : 0.f, a.y > 0.f ? rn_tf32(d.y) : 0.f, a.z > 0.f ? rn_tf32(d.z) : 0.f,
+                         a.w > 0.f ? rn_tf32(d.w) : 0.f);
   }
 }
 
@@ -47,17 +54,13 @@ im2col3x3_kernel(const float* __restrict__ x, int s, int C, int gc4, float* __re
   }
 }
 
-__device__ __forceinline__ float rn_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
 __global__ void __launch_bounds__(256)
-sk_combine_kernel(const float4* __restrict__ r1, const float4* __restrict__ r3, float4* __restrict__ out, size_t n4) {
+sk_combine_kernel(const float4* __restrict__ r1, const float4* __restrict__ r3, float4* __restrict__ out, size_t n4, int round_tf) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = r1[i], b = r3[i];
-    out[i] = make_float4(a.x * a.x + b.x * b.x, a.y * a.y + b.y * b.y, a.z * a.z + b.z * b.z, a.w * a.w + b.w * b.w);
+    float4 v = make_float4(a.x * a.x + b.x * b.x, a.y * a.y + b.y * b.y, a.z * a.z + b.z * b.z, a.w * a.w + b.w * b.w);
+    if (round_tf) v = make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+    out[i] = v;
   }
 }
 
@@ -125,11 +128,11 @@ static int ew_blocks(size_t n4) {
   return (int)(want < cap ? want : cap);
 }
 
-int aitb_sk_combine(const float* r1, const float* r3, float* out, size_t n, aitb_stream_t stream) {
+int aitb_sk_combine(const float* r1, const float* r3, float* out, size_t n, int round_tf32, aitb_stream_t stream) {
   AITB_REQUIRE(r1 && r3 && out && n > 0 && n % 4 == 0, "aitb_sk_combine: bad arguments (n must be a positive multiple of 4)");
   AITB_REQUIRE((((uintptr_t)r1 | (uintptr_t)r3 | (uintptr_t)out) & 15) == 0, "aitb_sk_combine: pointers must be 16-byte aligned");
   sk_combine_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(r1), reinterpret_cast<const float4*>(r3),
-                                                                       reinterpret_cast<float4*>(out), n / 4);
+                                                                       reinterpret_cast<float4*>(out), n / 4, round_tf32);
   return check_launch("sk_combine_kernel");
 }
 

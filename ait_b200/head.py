@@ -80,9 +80,10 @@ class DetectionHead(nn.Module):
         P = rois.shape[1]
         props = self.RCNN_roi_align(non_img, rois.reshape(-1, 5))                 # :279
         props = self.transformer(x_props=props, x_query=non_qry)                  # :289
-        props, query = sk_train.sknet_train(self.sk, props, non_qry)              # :294
-        pf = top_train.head_to_tail_train(self.RCNN_top, props)                   # :299
-        qf = top_train.head_to_tail_train(self.RCNN_top, query)                   # :300
+        # SKNet hands layer4 its GEMM operand layout (channels-last, tf32-rounded): no NCHW round trip, forward or backward
+        props, query = sk_train.sknet_train(self.sk, props, non_qry, channels_last_out=True)   # :294
+        pf = top_train.head_to_tail_train(self.RCNN_top, props, channels_last=True)            # :299
+        qf = top_train.head_to_tail_train(self.RCNN_top, query, channels_last=True)            # :300
         return targets.score_heads(pf, qf, P, self.RCNN_bbox_pred, self.RCNN_cls_score)   # :318-335
 
     def training_losses(self, non_img, non_qry, rois, rois_label, rois_target, rois_inside_ws, rois_outside_ws):

@@ -21,10 +21,10 @@ def _need_cuda(*ts):
 # ---------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------
-def transpose_cs(src, to_channels_last, out_dtype=None, split_src=False, split_dst=False):
+def transpose_cs(src, to_channels_last, out_dtype=None, split_src=False, split_dst=False, round_tf32=False):
     """[G, C, S] -> [G, S, C] (to_channels_last) or [G, S, C] -> [G, C, S].
     split_dst: the (channels-last) destination is a two-plane bf16 matrix [G, S, hi C | lo C] (AITB_F32S);
-    split_src: the (channels-last) source is one."""
+    split_src: the (channels-last) source is one.  round_tf32: an fp32 destination is rounded to tf32 (nearest)."""
     lib = L.load()
     _need_cuda(src)
     src = src.contiguous()
@@ -41,8 +41,8 @@ def transpose_cs(src, to_channels_last, out_dtype=None, split_src=False, split_d
     step = 32768
     for g0 in range(0, G, step):
         gn = min(step, G - g0)
-        L.check(lib.aitb_transpose_cs(L.ptr(src[g0:]), sdt, L.ptr(dst[g0:]), ddt, gn, Cc, S,
-                                      1 if to_channels_last else 0, L.stream_ptr()))
+        L.check(lib.aitb_transpose_cs_round(L.ptr(src[g0:]), sdt, L.ptr(dst[g0:]), ddt, gn, Cc, S,
+                                            1 if to_channels_last else 0, 1 if round_tf32 else 0, L.stream_ptr()))
     return dst
 
 

@@ -42,10 +42,12 @@ def _grouped(x, w, out, G, taps, flags=0, bias=None):
 
 
 class _SKBlockFn(torch.autograd.Function):
-    """forward(x [G,1024,8,8], w1 [1024,128,1,1], b1 [1024], w3 [1024,128,3,3], b3 [1024]) -> [G,1024,8,8]"""
+    """forward(x [G,1024,8,8], w1 [1024,128,1,1], b1 [1024], w3 [1024,128,3,3], b3 [1024], cl_out) -> [G,1024,8,8], or --
+    cl_out: the consumer is `top_train` -- the channels-last token-major map [G,64,1024] rounded to tf32 (its GEMM operand;
+    saves the NCHW round trip in both directions: the incoming gradient then is channels-last too)."""
 
     @staticmethod
-    def forward(ctx, x_nchw, w1, b1, w3, b3):
+    def forward(ctx, x_nchw, w1, b1, w3, b3, cl_out=False):
         ops._need_cuda(x_nchw, w1, b1, w3, b3)
         if tuple(x_nchw.shape[1:]) != (1024, 8, 8) or tuple(w1.shape) != (1024, GC, 1, 1) or tuple(w3.shape) != (1024, GC, 3, 3):
             raise RuntimeError("sk_block_train: expected x [G,1024,8,8] and the grouped (groups=8) 1x1 / 3x3 convolution weights")
@@ -53,8 +55,8 @@ class _SKBlockFn(torch.autograd.Function):
         G = x_nchw.shape[0]
         dev = x_nchw.device
         M = G * 64
-        x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32)
-        x0 = round_to_tf32(x0.view(M, 1024))
+        x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32,
+                              round_tf32=True).view(M, 1024)
         m1 = round_to_tf32(_tap_major(w1.detach().float()).contiguous())          # [1024, 128]
         m3 = round_to_tf32(_tap_major(w3.detach().float()).contiguous())          # [1024, 9*128] tap-major
         r1 = torch.empty((M, 1024), dtype=torch.float32, device=dev)
@@ -63,8 +65,10 @@ class _SKBlockFn(torch.autograd.Function):
         _grouped(x0, m1, r1, G, 1, fl, b1.detach().float().contiguous())
         _grouped(x0, m3, r3, G, 9, fl, b3.detach().float().contiguous())
         v = torch.empty((M, 1024), dtype=torch.float32, device=dev)
-        _call(lib.aitb_sk_combine, L.ptr(r1), L.ptr(r3), L.ptr(v), C.c_size_t(v.numel()))
-        ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3 = G, x0, m1, m3, r1, r3
+        _call(lib.aitb_sk_combine, L.ptr(r1), L.ptr(r3), L.ptr(v), C.c_size_t(v.numel()), 1 if cl_out else 0)
+        ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3, ctx.cl_out = G, x0, m1, m3, r1, r3, cl_out
+        if cl_out:
+            return v.view(G, 64, 1024)
         return ops.transpose_cs(v.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
 
     @staticmethod
@@ -73,11 +77,14 @@ class _SKBlockFn(torch.autograd.Function):
         G, x0, m1, m3, r1, r3 = ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3
         dev = x0.device
         M = G * 64
-        dv = ops.transpose_cs(d_out.contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32).view(M, 1024)
+        if ctx.cl_out:
+            dv = d_out.contiguous().float().view(M, 1024)
+        else:
+            dv = ops.transpose_cs(d_out.contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32).view(M, 1024)
         d1 = torch.empty_like(dv)
         d3 = torch.empty_like(dv)
         _call(lib.aitb_sk_combine_bwd, L.ptr(dv), L.ptr(r1), L.ptr(r3), L.ptr(d1), L.ptr(d3), C.c_size_t(dv.numel()))
-        need_x, need_w1, need_b1, need_w3, need_b3 = ctx.needs_input_grad
+        need_x, need_w1, need_b1, need_w3, need_b3 = ctx.needs_input_grad[:5]
         db1 = ops.colsum(d1) if need_b1 else None
         db3 = ops.colsum(d3) if need_b3 else None
         dw1 = dw3 = None
@@ -108,15 +115,16 @@ class _SKBlockFn(torch.autograd.Function):
             _grouped(d3, w3t, dx, G, 9)
             _grouped(d1, w1t, dx, G, 1, L.EPI_ACCUM)
             dx_nchw = ops.transpose_cs(dx.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
-        return dx_nchw, dw1, db1, dw3, db3
+        return dx_nchw, dw1, db1, dw3, db3, None
 
 
-def sk_block_train(blk, x):
-    """Differentiable `SKBlock.forward(x)` (blocks_...sk.py:960-984): x [G,1024,8,8] -> [G,1024,8,8]."""
+def sk_block_train(blk, x, channels_last_out=False):
+    """Differentiable `SKBlock.forward(x)` (blocks_...sk.py:960-984): x [G,1024,8,8] -> [G,1024,8,8]
+    (channels_last_out: [G,64,1024] token-major, tf32-rounded -- only for `top_train.head_to_tail_train(..., channels_last=True)`)."""
     c1, c3 = blk.convs[0][0], blk.convs[1][0]
-    return _SKBlockFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias)
+    return _SKBlockFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, bool(channels_last_out))
 
 
-def sknet_train(sk, x_props, x_query):
+def sknet_train(sk, x_props, x_query, channels_last_out=False):
     """Differentiable `SKNet.forward(x_props, x_query)` (blocks_...sk.py:993-998) -> (f_props, f_query)."""
-    return sk_block_train(sk.sk_props, x_props), sk_block_train(sk.sk_query, x_query)
+    return (sk_block_train(sk.sk_props, x_props, channels_last_out), sk_block_train(sk.sk_query, x_query, channels_last_out))

@@ -59,20 +59,24 @@ def _upsample(x, G, S, s, stride, Cc):
 
 
 class _HeadToTailFn(torch.autograd.Function):
-    """forward(x_nchw [G,1024,8,8], consts, *conv_weights) -> feat [G,2048].
+    """forward(x_nchw [G,1024,8,8] (cl_in: the channels-last, tf32-rounded [G,64,1024] map `sk_train` hands over), consts,
+    cl_in, *conv_weights) -> feat [G,2048].
     consts: per block a dict of BN scales / folded biases (not differentiated); conv_weights in the order
     (b0.conv1, b0.conv2, b0.conv3, b0.downsample.0, b1.conv1, b1.conv2, b1.conv3, b2.conv1, b2.conv2, b2.conv3)."""
 
     @staticmethod
-    def forward(ctx, x_nchw, consts, *weights):
+    def forward(ctx, x_nchw, consts, cl_in, *weights):
         ops._need_cuda(x_nchw, *weights)
         G = x_nchw.shape[0]
-        if tuple(x_nchw.shape[1:]) != (1024, 8, 8) or len(weights) != 10:
+        if tuple(x_nchw.shape[1:]) != ((64, 1024) if cl_in else (1024, 8, 8)) or len(weights) != 10:
             raise RuntimeError("head_to_tail_train: expected x [G,1024,8,8] and the ten layer4 convolution weights")
         dev = x_nchw.device
         M = G * 16
-        x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32)
-        x0 = round_to_tf32(x0.view(G * 64, 1024))
+        if cl_in:
+            x0 = x_nchw.detach().contiguous().float().view(G * 64, 1024)
+        else:
+            x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32,
+                                  round_tf32=True).view(G * 64, 1024)
         names = [("conv1", "conv2", "conv3", "down"), ("conv1", "conv2", "conv3"), ("conv1", "conv2", "conv3")]
         wi = iter(weights)
         packed, saved = [], []
@@ -104,7 +108,7 @@ class _HeadToTailFn(torch.autograd.Function):
             saved.append((o1, o2, y))
             cur = y
         feat, _, _ = ops.pool_heads(cur.view(G, 16, 2048), 1)
-        ctx.G, ctx.consts, ctx.packed, ctx.saved, ctx.x0 = G, consts, packed, saved, x0
+        ctx.G, ctx.consts, ctx.packed, ctx.saved, ctx.x0, ctx.cl_in = G, consts, packed, saved, x0, cl_in
         global _last_saved_for_tests
         _last_saved_for_tests = saved   # the parity test rebuilds the reference with exactly these ReLU masks
         ctx.wshapes = [tuple(w.shape) for w in weights]
@@ -122,41 +126,44 @@ class _HeadToTailFn(torch.autograd.Function):
         dy = dy.view(M, 2048)
         grads = {}
 
-        def wg(dyv, xv, N, K):
-            return ops.wgrad(round_to_tf32(dyv), xv, N=N, K=K)
+        def wg(dyv, xv, N, K):      # both operands are already tf32-rounded where they were produced
+            return ops.wgrad(dyv, xv, N=N, K=K)
 
         for b in (2, 1, 0):
             o1, o2, y = saved[b]
             wd = packed[b]
             cin = 1024 if b == 0 else 2048
             xin = _subsample(x0, G, 8, 4, 2, 1024) if b == 0 else saved[b - 1][2]
-            g = round_to_tf32(_relu_bwd(dy, y))                              # through the block's final ReLU
+            g = _relu_bwd(dy, y)                                             # through the block's final ReLU (tf32-rounded)
             # conv3 (1x1, 512 -> 2048)
             grads[(b, "conv3")] = wg(g, o2, 2048, 512)
             d_o2 = torch.empty((M, 512), dtype=torch.float32, device=dev)
-            ops.gemm(g, round_to_tf32(wd["conv3"].t().contiguous()), d_o2, M=M, N=512, K=2048, block_n=256,
+            ops.gemm(g, wd["conv3"].t().contiguous(), d_o2, M=M, N=512, K=2048, block_n=256,
                      flags=L.EPI_RELU_MASK, res=o2, ldr=512, round_tf32=True)
             # conv2 (3x3, 512 -> 512): weight gradient against the tap-major im2col of its input
             grads[(b, "conv2")] = wg(d_o2, _im2col(o1, G, 4, 512), 512, 9 * 512)
             w2 = wd["conv2"].view(512, 9, 512)
-            w2d = round_to_tf32(w2.flip(1).permute(2, 1, 0).contiguous().view(512, 9 * 512))   # [in, flipped tap, out]
+            w2d = w2.flip(1).permute(2, 1, 0).contiguous().view(512, 9 * 512)                  # [in, flipped tap, out]
             d_o1 = torch.empty((M, 512), dtype=torch.float32, device=dev)
             ops.gemm(d_o2, w2d, d_o1, M=M, N=512, K=512, block_n=256, view="map", map_args=(512, 4, 4, 1, G), taps=9,
                      flags=L.EPI_RELU_MASK, res=o1, ldr=512, round_tf32=True)
             # conv1 (1x1, cin -> 512) and the shortcut
             grads[(b, "conv1")] = wg(d_o1, xin, 512, cin)
             dx = torch.empty((M, cin), dtype=torch.float32, device=dev)
-            w1t = round_to_tf32(wd["conv1"].t().contiguous())
+            w1t = wd["conv1"].t().contiguous()
             if b > 0:   # identity shortcut: dx = d_o1 W1 + g
                 ops.gemm(d_o1, w1t, dx, M=M, N=cin, K=512, block_n=256, flags=L.EPI_RES, res=g, ldr=2048, round_tf32=True)
                 dy = dx
             else:       # projection shortcut (1x1, stride 2) on the same strided rows
                 grads[(b, "down")] = wg(g, xin, 2048, 1024)
                 ops.gemm(d_o1, w1t, dx, M=M, N=1024, K=512, block_n=256, round_tf32=False)
-                ops.gemm(g, round_to_tf32(wd["down"].t().contiguous()), dx, M=M, N=1024, K=2048, block_n=256,
+                ops.gemm(g, wd["down"].t().contiguous(), dx, M=M, N=1024, K=2048, block_n=256,
                          flags=L.EPI_ACCUM, round_tf32=False)
                 dx0 = _upsample(dx, G, 8, 4, 2, 1024)                        # [G*64, 1024], zeros off the stride-2 grid
-        dx_nchw = ops.transpose_cs(dx0.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
+        if ctx.cl_in:
+            dx_nchw = dx0.view(G, 64, 1024)
+        else:
+            dx_nchw = ops.transpose_cs(dx0.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
         order = [(0, "conv1"), (0, "conv2"), (0, "conv3"), (0, "down"), (1, "conv1"), (1, "conv2"), (1, "conv3"),
                  (2, "conv1"), (2, "conv2"), (2, "conv3")]
         outs = []
@@ -164,12 +171,13 @@ class _HeadToTailFn(torch.autograd.Function):
             gw = grads[(b, n)] * consts[b][n + "_scale"].view(-1, 1)         # d(folded) -> d(conv.weight): BN scale per row
             o, i, kh, kw = shp
             outs.append(gw.view(o, kh, kw, i).permute(0, 3, 1, 2).contiguous())
-        return (dx_nchw, None) + tuple(outs)
+        return (dx_nchw, None, None) + tuple(outs)
 
 
-def head_to_tail_train(RCNN_top, pool5):
+def head_to_tail_train(RCNN_top, pool5, channels_last=False):
     """Differentiable `_head_to_tail(pool5)` for the reference's `RCNN_top = nn.Sequential(resnet.layer4)` with frozen
-    BatchNorm: pool5 [G,1024,8,8] -> [G,2048].  Gradients flow to pool5 and to the ten convolution weights."""
+    BatchNorm: pool5 [G,1024,8,8] -> [G,2048].  Gradients flow to pool5 and to the ten convolution weights.
+    channels_last: pool5 is the [G,64,1024] token-major, tf32-rounded map of `sk_train.sknet_train(..., channels_last_out=True)`."""
     layer4 = RCNN_top[0]
     consts, weights = [], []
     for blk in layer4:
@@ -186,4 +194,4 @@ def head_to_tail_train(RCNN_top, pool5):
             c[n + "_bias"] = (bn.bias.detach().float() - bn.running_mean.float() * scale).contiguous()
             weights.append(cv.weight)
         consts.append(c)
-    return _HeadToTailFn.apply(pool5, consts, *weights)
+    return _HeadToTailFn.apply(pool5, consts, bool(channels_last), *weights)

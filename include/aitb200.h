@@ -97,6 +97,9 @@ int aitb_roi_align_backward(const float* grad, const float* rois, int B, int C, 
 /* layout helpers: [G, C, S] <-> [G, S, C] with optional dtype conversion (src/dst dtype enums) */
 int aitb_transpose_cs(const void* src, int src_dtype, void* dst, int dst_dtype, int G, int C,
                       int S, int to_channels_last, aitb_stream_t stream);
+/* same, fp32 destination rounded to tf32 (nearest) when round_tf32 != 0: the consumer is a tf32 tensor-core GEMM */
+int aitb_transpose_cs_round(const void* src, int src_dtype, void* dst, int dst_dtype, int G, int C, int S,
+                            int to_channels_last, int round_tf32, aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * tcgen05 GEMM building block (used by the head engine below; exported for unit tests)
@@ -486,7 +489,7 @@ int aitb_mean_pool_backward(const float* d_feat, int G, float* d_top, aitb_strea
 
 /* Data-movement helpers of the layer-4 (`RCNN_top`) training path (ait_b200/csrc/train_aux.cu, composed with aitb_gemm /
  * aitb_wgrad by ait_b200/top_train.py), fp32, C % 4 == 0:
- *   aitb_relu_bwd      out[i] = y[i] > 0 ? dy[i] : 0
+ *   aitb_relu_bwd      out[i] = y[i] > 0 ? tf32(dy[i]) : 0   (rounded to nearest: the result only feeds tf32 GEMMs)
  *   aitb_im2col3x3     x [G,s,s,C] -> out [G*s*s, 9*C], tap-major (ky, kx, c), zero padding
  *   aitb_map_subsample x [G,S,S,C] -> out [G,s,s,C] at (stride*y, stride*x);  aitb_map_upsample: its adjoint (zeros elsewhere) */
 int aitb_relu_bwd(const float* dy, const float* y, float* out, size_t n, aitb_stream_t stream);
@@ -498,10 +501,10 @@ int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, fl
  * ait_b200/sk_train.py; the reference gets the backward from torch autograd):
  *   aitb_im2col3x3_grouped  like aitb_im2col3x3 with columns ordered (group, ky, kx, channel in group): the weight gradient
  *                           of a grouped 3x3 convolution is one aitb_wgrad per group on a [rows, 9*group_c] slice
- *   aitb_sk_combine         out = r1^2 + r3^2   (r1, r3: the post-ReLU 1x1 / 3x3 branch maps)
+ *   aitb_sk_combine         out = r1^2 + r3^2   (r1, r3: the post-ReLU 1x1 / 3x3 branch maps; round_tf32: the consumer is a tf32 GEMM)
  *   aitb_sk_combine_bwd     d1 = 2 dv r1, d3 = 2 dv r3, rounded to tf32 (nearest) */
 int aitb_im2col3x3_grouped(const float* x, int G, int s, int C, int group_c, float* out, aitb_stream_t stream);
-int aitb_sk_combine(const float* r1, const float* r3, float* out, size_t n, aitb_stream_t stream);
+int aitb_sk_combine(const float* r1, const float* r3, float* out, size_t n, int round_tf32, aitb_stream_t stream);
 int aitb_sk_combine_bwd(const float* dv, const float* r1, const float* r3, float* d1, float* d3, size_t n, aitb_stream_t stream);
 
 /* number of kernels launched by this thread through the library since the last reset */
