@@ -46,6 +46,12 @@ struct WgradParams {
   int rows_per_split;   // multiple of kWgRows
   float* dw;
   int ldw;
+  // X addressing.  conv_S = 0: X is a row-major matrix, columns [nt * x_group_stride + k, ...).  conv_S = S > 0: X is a
+  // channels-last S x S map [G, S, S, C] read through a 4-D TMA view, dW column k = tap * conv_cg + c (tap-major 3x3):
+  // the rows of a stage are the map positions shifted by the tap, out-of-map positions zero-filled by TMA (= the padding)
+  // -- the weight gradient of a 3x3 convolution without an im2col buffer.  x_group_stride: grouped convolution, n-tile
+  // nt (128 output channels = one group) reads input channels [nt * x_group_stride, + conv_cg).
+  int conv_S, conv_cg, x_group_stride;
 };
 
 // MN-major tf32 operand.  tcgen05 accepts exactly one shared-memory layout for it: "128-byte swizzle with a
@@ -116,8 +122,17 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         // are zero-filled by TMA
         const int r = row0 + it * kWgRows;
         for (int g = 0; g < 4; ++g) tma_load_2d(sa + g * (kWgRows * 128), &tmY, &full_bar[s], nt * 128 + g * 32, r);
-        for (int g = 0; g < p.bn / 32; ++g)
-          tma_load_2d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], kt * p.bn + g * 32, r);
+        const int xc = kt * p.bn;
+        if (p.conv_S == 0) {
+          for (int g = 0; g < p.bn / 32; ++g)
+            tma_load_2d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], nt * p.x_group_stride + xc + g * 32, r);
+        } else {
+          const int tap = xc / p.conv_cg, cc = xc - tap * p.conv_cg + nt * p.x_group_stride;
+          const int ss = p.conv_S * p.conv_S;
+          const int gi = r / ss, y0 = (r - gi * ss) / p.conv_S;
+          for (int g = 0; g < p.bn / 32; ++g)
+            tma_load_4d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], cc + g * 32, tap % 3 - 1, y0 + tap / 3 - 1, gi);
+        }
       }
     }
   } else if (warp == 1) {
@@ -638,6 +653,45 @@ int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t strea
 }
 
 // dw [N, ldw] += dy[M, ldy (cols n_off .. n_off + N)]^T * x[M, ldx (cols 0 .. K)]
+// shared tail of the two entry points: tiling, split over row chunks, launch
+static int wgrad_launch(const float* dy, int ldy, const CUtensorMap& tmX, int M, int N, int K, int bn, float* dw, int ldw,
+                        int conv_S, int conv_cg, int x_group_stride, cudaStream_t stream) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bn = bn;
+  p.n_tiles = N / 128;
+  p.k_tiles = K / bn;
+  p.conv_S = conv_S;
+  p.conv_cg = conv_cg;
+  p.x_group_stride = x_group_stride;
+  const int tiles = p.n_tiles * p.k_tiles;
+  const int chunks = (M + kWgRows - 1) / kWgRows;
+  int splits = (2 * sms_bwd() + tiles - 1) / tiles;           // ~2 waves of CTAs
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  p.rows_per_split = ((chunks + splits - 1) / splits) * kWgRows;
+  p.splits = (M + p.rows_per_split - 1) / p.rows_per_split;
+  p.dw = dw;
+  p.ldw = ldw;
+  CUtensorMap tmY;
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)ldy * 4};
+    const uint32_t box[2] = {32, (uint32_t)kWgRows};
+    if (encode_map_f32_mn(&tmY, dy, 2, dims, str, box, "wgrad dY")) return 1;
+  }
+  const int smem = kWgStages * (kWgABytes + (bn / 32) * kWgRows * 128) + 1024 + 256;
+  static SmemAttrOnce once;
+  if (ensure_dyn_smem((const void*)wgrad_tcgen05_kernel, kWgStages * (kWgABytes + 8 * kWgRows * 128) + 1024 + 256, once,
+                      "wgrad_tcgen05_kernel"))
+    return 1;
+  wgrad_tcgen05_kernel<<<tiles * p.splits, kWgThreads, smem, stream>>>(tmY, tmX, p);
+  return check_launch("wgrad_tcgen05_kernel");
+}
+
 int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
               cudaStream_t stream) {
   AITB_REQUIRE(dy && x && dw, "aitb_wgrad: null pointer");
@@ -648,43 +702,47 @@ int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, i
   AITB_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dw & 15) == 0,
                "aitb_wgrad: pointers must be 16-byte aligned");
   const int bn = K % 256 == 0 ? 256 : (K % 128 == 0 ? 128 : 64);
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = M;
-  p.N = N;
-  p.K = K;
-  p.bn = bn;
-  p.n_tiles = N / 128;
-  p.k_tiles = K / bn;
-  const int tiles = p.n_tiles * p.k_tiles;
-  const int chunks = (M + kWgRows - 1) / kWgRows;
-  int splits = (2 * sms_bwd() + tiles - 1) / tiles;           // ~2 waves of CTAs
-  if (splits > chunks) splits = chunks;
-  if (splits < 1) splits = 1;
-  p.rows_per_split = ((chunks + splits - 1) / splits) * kWgRows;
-  p.splits = (M + p.rows_per_split - 1) / p.rows_per_split;
-  p.dw = dw;
-  p.ldw = ldw;
-  CUtensorMap tmY, tmX;
-  {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)ldy * 4};
+  CUtensorMap tmX;
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+  const uint64_t str[1] = {(uint64_t)ldx * 4};
+  const uint32_t box[2] = {32, (uint32_t)kWgRows};
+  if (encode_map_f32_mn(&tmX, x, 2, dims, str, box, "wgrad X")) return 1;
+  return wgrad_launch(dy, ldy, tmX, M, N, K, bn, dw, ldw, 0, 0, 0, stream);
+}
+
+// Weight gradient of a (grouped) 1x1 or 3x3 stride-1 "same" convolution on a channels-last S x S map, no im2col:
+//   dW[n, tap * Cg + c] += sum over (g, y, x) of dY[(g, y, x), n] * X[g, y + ky - 1, x + kx - 1, group(n) * Cg + c]
+// (tap = ky * 3 + kx; Cg = C / groups; taps = 1: the 1x1 case, dW [N, Cg]).  groups > 1 needs N / groups == 128 (one
+// n-tile per group).  dY is [G * S * S, ldy] row-major; X [G, S, S, C]; dW [N, taps * Cg] with leading dimension ldw.
+int wgrad_conv_run(const float* dy, int ldy, const float* x, int G, int S, int C, int N, int groups, int taps, float* dw,
+                   int ldw, cudaStream_t stream) {
+  AITB_REQUIRE(dy && x && dw, "aitb_wgrad_conv: null pointer");
+  AITB_REQUIRE(G > 0 && C > 0 && N > 0 && groups > 0 && C % groups == 0, "aitb_wgrad_conv: bad sizes");
+  AITB_REQUIRE(taps == 1 || taps == 9, "aitb_wgrad_conv: taps must be 1 (1x1) or 9 (3x3)");
+  AITB_REQUIRE(S == 4 || S == 8, "aitb_wgrad_conv: S=%d (4x4 and 8x8 maps: a 32-row stage must be whole map rows)", S);
+  AITB_REQUIRE(N % 128 == 0 && (groups == 1 || N / groups == 128),
+               "aitb_wgrad_conv: N=%d must be a multiple of 128, and 128 per group for a grouped convolution", N);
+  const int cg = C / groups;
+  AITB_REQUIRE(cg % 64 == 0, "aitb_wgrad_conv: %d channels per group must be a multiple of 64", cg);
+  AITB_REQUIRE(ldy % 4 == 0 && ldw % 4 == 0, "aitb_wgrad_conv: leading dimensions must be multiples of 4");
+  AITB_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dw & 15) == 0,
+               "aitb_wgrad_conv: pointers must be 16-byte aligned");
+  AITB_REQUIRE((long long)G * S * S < (1ll << 31), "aitb_wgrad_conv: too many rows");
+  const int M = G * S * S, K = taps * cg;
+  const int bn = cg % 256 == 0 ? 256 : (cg % 128 == 0 ? 128 : 64);   // a k-tile never straddles two taps
+  CUtensorMap tmX;
+  if (taps == 1) {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)C * 4};
     const uint32_t box[2] = {32, (uint32_t)kWgRows};
-    if (encode_map_f32_mn(&tmY, dy, 2, dims, str, box, "wgrad dY")) return 1;
+    if (encode_map_f32_mn(&tmX, x, 2, dims, str, box, "wgrad_conv X")) return 1;
+  } else {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)S, (uint64_t)S, (uint64_t)G};
+    const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)S * C * 4, (uint64_t)S * S * C * 4};
+    const uint32_t box[4] = {32, (uint32_t)S, (uint32_t)(S == 8 ? 4 : 4), (uint32_t)(S == 8 ? 1 : 2)};   // 32 rows per stage
+    if (encode_map_f32_mn(&tmX, x, 4, dims, str, box, "wgrad_conv X map")) return 1;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)ldx * 4};
-    const uint32_t box[2] = {32, (uint32_t)kWgRows};
-    if (encode_map_f32_mn(&tmX, x, 2, dims, str, box, "wgrad X")) return 1;
-  }
-  const int smem = kWgStages * (kWgABytes + (bn / 32) * kWgRows * 128) + 1024 + 256;
-  static SmemAttrOnce once;
-  if (ensure_dyn_smem((const void*)wgrad_tcgen05_kernel, kWgStages * (kWgABytes + 8 * kWgRows * 128) + 1024 + 256, once,
-                      "wgrad_tcgen05_kernel"))
-    return 1;
-  wgrad_tcgen05_kernel<<<tiles * p.splits, kWgThreads, smem, stream>>>(tmY, tmX, p);
-  return check_launch("wgrad_tcgen05_kernel");
+  return wgrad_launch(dy, ldy, tmX, M, N, K, bn, dw, ldw, taps == 9 ? S : 0, cg, groups > 1 ? cg : 0, stream);
 }
 
 }  // namespace aitb

@@ -32,6 +32,8 @@ int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat,
                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
 
+int wgrad_conv_run(const float* dy, int ldy, const float* x, int G, int S, int C, int N, int groups, int taps, float* dw,
+                   int ldw, cudaStream_t stream);
 int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
               cudaStream_t stream);
 int ln_bwd_run(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows,
@@ -1163,6 +1165,11 @@ int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order,
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
                aitb_stream_t stream) {
   return wgrad_run(dy, ldy, x, ldx, M, N, K, dw, ldw, (cudaStream_t)stream);
+}
+
+int aitb_wgrad_conv(const float* dy, int ldy, const float* x, int G, int S, int C, int N, int groups, int taps, float* dw,
+                    int ldw, aitb_stream_t stream) {
+  return wgrad_conv_run(dy, ldy, x, G, S, C, N, groups, taps, dw, ldw, (cudaStream_t)stream);
 }
 
 size_t aitb_head_workspace_bytes(int B, int P, int dtype) {

@@ -269,6 +269,23 @@ def wgrad(dy, x, dw=None, N=None, K=None):
     return dw
 
 
+def wgrad_conv(dy, x_map, G, S, Cc, N, groups=1, taps=9, dw=None):
+    """Weight gradient of a (grouped) 1x1 / 3x3 "same" convolution without im2col: dy [G*S*S, >=N] row-major fp32,
+    x_map the channels-last input [G*S*S, Cc]; -> dw [N, taps * Cc / groups] (tap-major), accumulated when given."""
+    lib = L.load()
+    _need_cuda(dy, x_map)
+    if dy.dtype != torch.float32 or x_map.dtype != torch.float32 or dy.stride(-1) != 1 or not x_map.is_contiguous():
+        raise RuntimeError("ait_b200.wgrad_conv: float32 row-major dy and a contiguous channels-last map required")
+    if dy.shape[0] != G * S * S or x_map.numel() != G * S * S * Cc:
+        raise RuntimeError("ait_b200.wgrad_conv: dy / x_map do not match G=%d S=%d C=%d" % (G, S, Cc))
+    K = taps * (Cc // groups)
+    if dw is None:
+        dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+    L.check(lib.aitb_wgrad_conv(L.ptr(dy), dy.stride(0), L.ptr(x_map), G, S, Cc, N, groups, taps, L.ptr(dw), dw.stride(0),
+                                L.stream_ptr()))
+    return dw
+
+
 def ln_bwd(g, y, gamma, beta, rstd, grp=64, valid=64):
     """LayerNorm backward from the saved output y [rows, 512] and 1/sigma [rows] -> (dx [rows/grp*valid, 512], dgamma, dbeta)."""
     lib = L.load()

@@ -10,8 +10,8 @@ tensor-core math, like the AIT and layer-4 training steps):
             kept; `aitb_sk_combine` squares and sums them
   backward  relu(z)**2 is C1 (derivative 2 relu(z)): d_branch = 2 dv r, no mask.  dgrad = the same grouped GEMM with
             the per-group transposed (3x3: tap-flipped) weights, the 1x1 branch accumulated onto the 3x3 one;
-            wgrad = one `aitb_wgrad` per group (N = 128; K = 128, or 9*128 against the group-major im2col of the
-            saved input, chunked over pairs so the column buffer stays below ~1.2 GB); bias gradients = column sums
+            wgrad = ONE `aitb_wgrad_conv` launch per branch (n-tile = group; the 3x3 input read through a 4-D TMA view, one
+            shifted box per tap, zero-filled outside the map -- no im2col buffer); bias gradients = column sums
 
 No CPU / eager fallback.
 """
@@ -25,7 +25,6 @@ from .packing import round_to_tf32
 
 GROUPS = 8
 GC = 128                     # channels per group (1024 / 8)
-_IM2COL_PAIRS = 512          # pairs per im2col chunk: 512 * 64 rows * 9216 floats = 1.2 GB
 
 
 def _call(fn, *args):
@@ -88,23 +87,12 @@ class _SKBlockFn(torch.autograd.Function):
         db1 = ops.colsum(d1) if need_b1 else None
         db3 = ops.colsum(d3) if need_b3 else None
         dw1 = dw3 = None
+        # one launch per branch for all eight groups: n-tile = group, X read through the (shifted) TMA map view -- no im2col
         if need_w1:
-            dw1 = torch.zeros((1024, GC), dtype=torch.float32, device=dev)
-            for g in range(GROUPS):
-                sl = slice(g * GC, (g + 1) * GC)
-                ops.wgrad(d1[:, sl], x0[:, sl], dw=dw1[sl], N=GC, K=GC)
+            dw1 = ops.wgrad_conv(d1, x0, G, 8, 1024, 1024, groups=GROUPS, taps=1)
             dw1 = dw1.view(1024, 1, 1, GC).permute(0, 3, 1, 2).contiguous()
         if need_w3:
-            dw3 = torch.zeros((1024, 9 * GC), dtype=torch.float32, device=dev)
-            for p0 in range(0, G, _IM2COL_PAIRS):
-                n = min(_IM2COL_PAIRS, G - p0)
-                cols = torch.empty((n * 64, GROUPS, 9 * GC), dtype=torch.float32, device=dev)
-                _call(lib.aitb_im2col3x3_grouped, L.ptr(x0[p0 * 64:]), n, 8, 1024, GC, L.ptr(cols))
-                dy = d3[p0 * 64:(p0 + n) * 64]
-                for g in range(GROUPS):
-                    sl = slice(g * GC, (g + 1) * GC)
-                    ops.wgrad(dy[:, sl], cols[:, g], dw=dw3[sl], N=GC, K=9 * GC)
-                del cols
+            dw3 = ops.wgrad_conv(d3, x0, G, 8, 1024, 1024, groups=GROUPS, taps=9)
             dw3 = dw3.view(1024, 3, 3, GC).permute(0, 3, 1, 2).contiguous()
         dx_nchw = None
         if need_x:

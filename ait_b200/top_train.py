@@ -7,8 +7,8 @@ composed from the library's building blocks (fp32 storage, tf32 tensor-core math
             bias + ReLU / residual + ReLU epilogues), every activation the backward needs kept
   dgrad     the same tcgen05 GEMM with a transposed weight: 1x1 -> W^T; 3x3 -> the nine taps flipped and transposed
             (a 3x3 convolution of the gradient map); ReLU masks and the residual sum fused into the epilogues
-  wgrad     `aitb_wgrad` (dW += dY^T X on MN-major operands); the 3x3 weight gradient is ONE wgrad against the
-            tap-major im2col of the saved input, which lands directly in the layout the weights are packed in
+  wgrad     `aitb_wgrad` (dW += dY^T X on MN-major operands); the 3x3 weight gradient is ONE `aitb_wgrad_conv` launch reading
+            the saved 4x4 map through nine shifted, zero-filled TMA boxes -- tap-major, the layout the weights are packed in
   stride 2  the first bottleneck's 1x1 convolutions read every second position: gather / zero-fill scatter kernels
 
 Gradients are returned for the ten convolution weights (BatchNorm is frozen: `set_bn_fix`, its parameters do not
@@ -140,8 +140,8 @@ class _HeadToTailFn(torch.autograd.Function):
             d_o2 = torch.empty((M, 512), dtype=torch.float32, device=dev)
             ops.gemm(g, wd["conv3"].t().contiguous(), d_o2, M=M, N=512, K=2048, block_n=256,
                      flags=L.EPI_RELU_MASK, res=o2, ldr=512, round_tf32=True)
-            # conv2 (3x3, 512 -> 512): weight gradient against the tap-major im2col of its input
-            grads[(b, "conv2")] = wg(d_o2, _im2col(o1, G, 4, 512), 512, 9 * 512)
+            # conv2 (3x3, 512 -> 512): weight gradient straight from the saved 4x4 map (nine shifted TMA boxes, no im2col)
+            grads[(b, "conv2")] = ops.wgrad_conv(d_o2, o1, G, 4, 512, 512, groups=1, taps=9)
             w2 = wd["conv2"].view(512, 9, 512)
             w2d = w2.flip(1).permute(2, 1, 0).contiguous().view(512, 9 * 512)                  # [in, flipped tap, out]
             d_o1 = torch.empty((M, 512), dtype=torch.float32, device=dev)

@@ -363,6 +363,13 @@ int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order,
  * leading dimensions ldy / ldx; dw must be initialised by the caller, e.g. zeroed).  N % 128 == 0, K % 64 == 0. */
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
                aitb_stream_t stream);
+/* Weight gradient of a (grouped) 1x1 / 3x3 stride-1 "same" convolution on a channels-last S x S map (S = 4 | 8) WITHOUT an
+ * im2col buffer: x [G,S,S,C] is read through a 4-D TMA view, one shifted box per tap, out-of-map rows zero-filled (= the
+ * padding); dW [N, taps*Cg] (tap-major, Cg = C / groups) += dY^T * shifted X.  groups > 1: N / groups must be 128 (one
+ * 128-row tile of dW per group).  taps = 1 | 9.  The reference gets this from torch autograd over nn.Conv2d
+ * (blocks_coatt_transformer_sk.py:929, resnet_coatt_transformer_sk.py:80). */
+int aitb_wgrad_conv(const float* dy, int ldy, const float* x, int G, int S, int C, int N, int groups, int taps, float* dw,
+                    int ldw, aitb_stream_t stream);
 
 /* The other backward pieces (exported for unit tests; see ait_b200/csrc/bwd.cu) */
 int aitb_ln_bwd(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd,

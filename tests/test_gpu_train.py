@@ -281,8 +281,9 @@ def test_head_to_tail_training_matches_oracle_autograd(G):
 
 @pytest.mark.parametrize("G", [3, 10])
 def test_sknet_training_matches_oracle_autograd(G):
-    """SKBlock / SKNet forward + backward on the device (grouped tcgen05 GEMMs, per-group wgrad, im2col chunking) against
-    fp64 autograd of the oracle restatement (blocks_coatt_transformer_sk.py:960-998).  relu(z)**2 is C1, so -- unlike
+    """SKBlock / SKNet forward + backward on the device (grouped tcgen05 GEMMs, im2col-free grouped wgrad) against
+    fp64 autograd of the oracle restatement (blocks_coatt_transformer_sk.py:960-998); odd pair counts leave a ragged last
+    128-row tile.  relu(z)**2 is C1, so -- unlike
     layer4 -- no ReLU-mask flips: tf32 arithmetic only, gate 3e-3 relative L2.  `fc` / `sk` get no gradient, as in the
     reference (its forward discards the selective-kernel attention)."""
     from ait_b200 import sk_train, synth
@@ -304,15 +305,10 @@ def test_sknet_training_matches_oracle_autograd(G):
     rp, rq = head_oracle.sknet_forward(sd64, xp64, xq64, dtype=torch.float64)
     (rp * gp.double()).sum().add((rq * gq.double()).sum()).backward()
     sk = sk.to(DEV).train()
-    old = sk_train._IM2COL_PAIRS
-    sk_train._IM2COL_PAIRS = 4          # exercise the chunked weight gradient (G = 10 -> 3 chunks, ragged tail)
-    try:
-        xpd, xqd = xp.to(DEV).requires_grad_(), xq.to(DEV).requires_grad_()
-        op, oq = sk_train.sknet_train(sk, xpd, xqd)
-        torch.autograd.backward([op, oq], [gp.to(DEV), gq.to(DEV)])
-        torch.cuda.synchronize()
-    finally:
-        sk_train._IM2COL_PAIRS = old
+    xpd, xqd = xp.to(DEV).requires_grad_(), xq.to(DEV).requires_grad_()
+    op, oq = sk_train.sknet_train(sk, xpd, xqd)
+    torch.autograd.backward([op, oq], [gp.to(DEV), gq.to(DEV)])
+    torch.cuda.synchronize()
     assert _l2rel(op, rp.detach()) < 2e-3 and _l2rel(oq, rq.detach()) < 2e-3
     assert _l2rel(xpd.grad, xp64.grad) < 3e-3, _l2rel(xpd.grad, xp64.grad)
     assert _l2rel(xqd.grad, xq64.grad) < 3e-3
@@ -406,3 +402,38 @@ def test_whole_head_training_step_matches_oracle_autograd():
     assert len(errs) == 2 + 46 + 8 + 10 + 6, len(errs)
     bad = {k: v for k, v in errs.items() if v[0] > 1e-1 or v[1] < 0.995}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("G,S,Cc,N,groups", [(5, 4, 512, 512, 1), (3, 8, 1024, 1024, 8), (1, 8, 256, 256, 2), (67, 4, 128, 128, 1)])
+@pytest.mark.parametrize("taps", [1, 9])
+def test_wgrad_conv_without_im2col(G, S, Cc, N, groups, taps):
+    """aitb_wgrad_conv (X read through a shifted 4-D TMA view, zero-filled outside the map; n-tile = group) against
+    (1) F.conv2d's weight gradient in fp64 on tf32-rounded operands and (2) the im2col + aitb_wgrad route it replaces
+    (same products, same tensor-core path -> 1e-5).  Ragged: G*S*S not a multiple of the 32-row stages' 128-row splits."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(G * 100 + S + taps)
+    x = _tf32(torch.randn(G, S, S, Cc, generator=g)).to(DEV)
+    dy = _tf32(torch.randn(G * S * S, N, generator=g)).to(DEV)
+    cg = Cc // groups
+    dw = ops.wgrad_conv(dy, x.view(G * S * S, Cc), G, S, Cc, N, groups=groups, taps=taps)
+    torch.cuda.synchronize()
+    assert dw.shape == (N, taps * cg)
+    k = 3 if taps == 9 else 1
+    w = torch.zeros(N, cg, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x.cpu().double().permute(0, 3, 1, 2), w, padding=k // 2, groups=groups)
+    (y * dy.cpu().double().view(G, S, S, N).permute(0, 3, 1, 2)).sum().backward()
+    ref = w.grad.permute(0, 2, 3, 1).reshape(N, taps * cg)           # tap-major
+    assert _l2rel(dw, ref) < 2e-5, _l2rel(dw, ref)
+    # accumulation into a given dW
+    dw2 = ops.wgrad_conv(dy, x.view(G * S * S, Cc), G, S, Cc, N, groups=groups, taps=taps, dw=dw.clone())
+    assert _l2rel(dw2, 2 * ref) < 2e-5
+    if taps == 9:                                                     # the replaced route
+        cols = torch.empty((G * S * S, groups, 9 * cg), dtype=torch.float32, device=DEV)
+        L.check(L.load().aitb_im2col3x3_grouped(L.ptr(x), G, S, Cc, cg, L.ptr(cols), L.stream_ptr()))
+        old = torch.zeros_like(dw)
+        npg = N // groups
+        for gi in range(groups):
+            ops.wgrad(dy[:, gi * npg:(gi + 1) * npg], cols[:, gi], dw=old[gi * npg:(gi + 1) * npg], N=npg, K=9 * cg)
+        assert _l2rel(dw, old.cpu().double()) < 1e-5
