@@ -437,3 +437,22 @@ def test_wgrad_conv_without_im2col(G, S, Cc, N, groups, taps):
         for gi in range(groups):
             ops.wgrad(dy[:, gi * npg:(gi + 1) * npg], cols[:, gi], dw=old[gi * npg:(gi + 1) * npg], N=npg, K=9 * cg)
         assert _l2rel(dw, old.cpu().double()) < 1e-5
+
+
+def test_head_training_loop_reduces_the_loss():
+    """End to end on the device (tools/train_demo.py): device-side ProposalTargetLayer sample -> DetectionHead.training_losses
+    -> backward -> plain torch.optim.SGD (lr 1e-2, no momentum) over the head's own nn.Parameters with the reference's
+    stock init, eight steps on one fixed sample.  Gradient descent with a small step must go downhill: the total loss falls
+    at EVERY step (measured 2.056 -> 2.007, classification 0.697 -> 0.660, box regression 0.571 -> 0.559) -- the gradients
+    point downhill through the whole chain (ROIAlign, AIT, SKNet, layer4, heads, losses)."""
+    import math
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import train_demo
+    hist = train_demo.run(B=2, steps=8, lr=1e-2, dev=DEV, verbose=True, mom=0.0)
+    tot = [sum(h) for h in hist]
+    assert all(math.isfinite(t) for t in tot), tot
+    assert all(b < a + 1e-4 for a, b in zip(tot, tot[1:])), tot
+    assert tot[-1] < tot[0] - 0.03, tot
+    assert hist[-1][0] < hist[0][0] - 0.02 and hist[-1][2] < hist[0][2] - 0.005, hist
