@@ -149,6 +149,9 @@ SIGNATURES = {
     "aitb_ait_forward_train": (_i, [C.POINTER(HeadWeights), _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "aitb_ait_backward": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _sz, C.POINTER(AITGrads), _vp, _vp, _vp, _sz,
                                _vp]),
+    "aitb_ait_backward_tm": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _sz, C.POINTER(AITGrads), _vp, _vp, _vp, _sz,
+                                  _vp]),
+    "aitb_ait_saved_offset": (_sz, [_i, _i, _i]),
     "aitb_anchor_target_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "aitb_anchor_target_assign": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_anchor_target_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

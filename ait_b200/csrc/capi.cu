@@ -699,7 +699,7 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
   cudaStream_t st = (cudaStream_t)stream;
   RUN(check_weights(w, false));
   AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_forward_train: the training path runs in the fp32-storage / tf32 configuration");
-  AITB_REQUIRE(B > 0 && P > 0 && x_props && x_query && out_nchw && saved, "aitb_ait_forward_train: bad arguments");
+  AITB_REQUIRE(B > 0 && P > 0 && x_props && x_query && saved, "aitb_ait_forward_train: bad arguments");
   AITB_REQUIRE(((uintptr_t)saved & 1023) == 0 && saved_bytes >= aitb_ait_saved_bytes(B, P),
                "aitb_ait_forward_train: `saved` must be 1024-byte aligned and aitb_ait_saved_bytes large");
   const int bp = B * P;
@@ -714,7 +714,8 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
   RUN(transpose_run(x_query, AITB_F32, hb.qtok, AITB_F32, B, 1024, 64, 1, st, w->round_tf32));
   RUN(ait_query_side(w, hb, B, st));
   RUN(ait_core(w, hb, B, P, nullptr, st, nullptr, false));
-  for (int g0 = 0; g0 < bp; g0 += 32768) {
+  // out_nchw == NULL: the caller consumes the token-major result in place (aitb_ait_saved_offset(B, P, 1)) -- no NCHW copy
+  for (int g0 = 0; out_nchw && g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
     RUN(transpose_run((const float*)hb.AIT + (size_t)g0 * 64 * 1024, AITB_F32, out_nchw + (size_t)g0 * 1024 * 64, AITB_F32,
                       gn, 1024, 64, 0, st));
@@ -722,9 +723,18 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
   return 0;
 }
 
-int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
-                      size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
-                      void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+size_t aitb_ait_saved_offset(int B, int P, int which) {
+  if (B <= 0 || P <= 0) return 0;
+  uint8_t* const base = reinterpret_cast<uint8_t*>((uintptr_t)1 << 20);   // Bump hands out pointers only from a non-null base
+  Bump b{base, 0};
+  HeadBufs hb;
+  carve_train(b, hb, B, P);
+  return (size_t)((const uint8_t*)(which == 1 ? hb.AIT : hb.pooled) - base);
+}
+
+static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_nchw, int grad_token_major, int B, int P,
+                             const void* saved, size_t saved_bytes, const aitb_ait_grads* g, float* grad_props,
+                             float* grad_query, void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RUN(check_weights(w, false));
   AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_backward: the training path runs in the fp32-storage / tf32 configuration");
@@ -750,10 +760,11 @@ int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, in
   float* wta = f((size_t)2048 * 1024);   // transposed-weight scratch (two slots)
   float* wtb = f((size_t)2048 * 1024);
   // ---- dec_trans: AIT = DEC Wt^T + b
-  float* gAIT = f((size_t)R * 1024);
-  for (int g0 = 0; g0 < bp; g0 += 32768) {
+  float* gAIT_buf = f((size_t)R * 1024);
+  const float* gAIT = grad_token_major ? grad_out_nchw : gAIT_buf;   // token-major: already [bp*64, 1024], tf32-rounded
+  for (int g0 = 0; !grad_token_major && g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
-    RUN(transpose_run(grad_out_nchw + (size_t)g0 * 1024 * 64, AITB_F32, gAIT + (size_t)g0 * 64 * 1024, AITB_F32, gn, 1024, 64,
+    RUN(transpose_run(grad_out_nchw + (size_t)g0 * 1024 * 64, AITB_F32, gAIT_buf + (size_t)g0 * 64 * 1024, AITB_F32, gn, 1024, 64,
                       1, st, 1));
   }
   RUN(colsum_run(gAIT, 1024, R, 1024, g->dec_trans.bias, st));
@@ -864,6 +875,21 @@ int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, in
   AITB_REQUIRE(b.off <= workspace_bytes, "aitb_ait_backward: internal workspace accounting error (%zu > %zu)", b.off,
                workspace_bytes);
   return 0;
+}
+
+int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
+                      size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
+                      void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  return ait_backward_impl(w, grad_out_nchw, 0, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
+                           stream);
+}
+
+int aitb_ait_backward_tm(const aitb_head_weights* w, const float* grad_out_tm, int B, int P, const void* saved,
+                         size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
+                         void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
+  AITB_REQUIRE(((uintptr_t)grad_out_tm & 15) == 0, "aitb_ait_backward_tm: grad_out must be 16-byte aligned");
+  return ait_backward_impl(w, grad_out_tm, 1, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
+                           stream);
 }
 
 int aitb_ln_bwd(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows, int grp,

@@ -79,9 +79,10 @@ class DetectionHead(nn.Module):
             raise RuntimeError("forward_train: rois must be [B,P,5] with B = number of (image, query) units")
         P = rois.shape[1]
         props = self.RCNN_roi_align(non_img, rois.reshape(-1, 5))                 # :279
-        props = self.transformer(x_props=props, x_query=non_qry)                  # :289
-        # SKNet hands layer4 its GEMM operand layout (channels-last, tf32-rounded): no NCHW round trip, forward or backward
-        props, query = sk_train.sknet_train(self.sk, props, non_qry, channels_last_out=True)   # :294
+        # stage-to-stage hand-over in the GEMM operand layout (token-major / channels-last, tf32-rounded): AIT -> SKNet -> layer4
+        # without an NCHW round trip, forward or backward
+        props = self.transformer(x_props=props, x_query=non_qry, token_major_out=True)         # :289
+        props, query = sk_train.sknet_train(self.sk, props, non_qry, channels_last_out=True, channels_last_in=True)   # :294
         pf = top_train.head_to_tail_train(self.RCNN_top, props, channels_last=True)            # :299
         qf = top_train.head_to_tail_train(self.RCNN_top, query, channels_last=True)            # :300
         return targets.score_heads(pf, qf, P, self.RCNN_bbox_pred, self.RCNN_cls_score)   # :318-335

@@ -218,8 +218,10 @@ class HeadEngine:
                                       ".layer_norm.bias")]
         return names
 
-    def ait_forward_train(self, x_props, x_query):
-        """Transformer.forward keeping the activations the backward needs -> (out, saved buffer)."""
+    def ait_forward_train(self, x_props, x_query, token_major_out=False):
+        """Transformer.forward keeping the activations the backward needs -> (out, saved buffer).
+        token_major_out: no NCHW copy -- `out` is the [bp,64,1024] token-major, tf32-rounded result living inside the saved
+        buffer (the operand layout of the next stage's GEMMs)."""
         if self.mode != "tf32":
             raise RuntimeError("ait_b200: the training path runs in the fp32-storage / tf32 configuration")
         lib = L.load()
@@ -228,17 +230,24 @@ class HeadEngine:
         x_query = x_query.contiguous().float()
         bp, bs = x_props.shape[0], x_query.shape[0]
         P = bp // bs
-        out = torch.empty((bp, 1024, 8, 8), dtype=torch.float32, device=x_props.device)
         nbytes = lib.aitb_ait_saved_bytes(bs, P)
         saved = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=x_props.device)
         sv = saved[(-saved.data_ptr()) % 1024:]
+        if token_major_out:
+            off = int(lib.aitb_ait_saved_offset(bs, P, 1))
+            out = sv[off:off + bp * 64 * 1024 * 4].view(torch.float32).view(bp, 64, 1024)
+            out_ptr = L.ptr(None)
+        else:
+            out = torch.empty((bp, 1024, 8, 8), dtype=torch.float32, device=x_props.device)
+            out_ptr = L.ptr(out)
         with torch.cuda.device(x_props.device):
-            L.check(lib.aitb_ait_forward_train(C.byref(self.w), L.ptr(x_props), L.ptr(x_query), bs, P, L.ptr(out),
+            L.check(lib.aitb_ait_forward_train(C.byref(self.w), L.ptr(x_props), L.ptr(x_query), bs, P, out_ptr,
                                                L.ptr(sv), nbytes, L.stream_ptr()))
         return out, sv
 
-    def ait_backward(self, grad_out, saved, bs, P):
-        """-> (grad_props [bp,1024,7,7], grad_query [bs,1024,8,8], [gradient per name of ait_param_names()])."""
+    def ait_backward(self, grad_out, saved, bs, P, token_major_grad=False):
+        """-> (grad_props [bp,1024,7,7], grad_query [bs,1024,8,8], [gradient per name of ait_param_names()]).
+        token_major_grad: grad_out is [bp,64,1024] token-major and already tf32-rounded (see ait_forward_train)."""
         lib = L.load()
         dev = grad_out.device
         grad_out = grad_out.contiguous().float()
@@ -273,9 +282,9 @@ class HeadEngine:
         nbytes = lib.aitb_ait_backward_workspace_bytes(bs, P)
         ws = self._workspace(nbytes)
         with torch.cuda.device(dev):
-            L.check(lib.aitb_ait_backward(C.byref(self.w), L.ptr(grad_out), bs, P, L.ptr(saved),
-                                          lib.aitb_ait_saved_bytes(bs, P), C.byref(G), L.ptr(g_props), L.ptr(g_query),
-                                          L.ptr(ws), nbytes, L.stream_ptr()))
+            fn = lib.aitb_ait_backward_tm if token_major_grad else lib.aitb_ait_backward
+            L.check(fn(C.byref(self.w), L.ptr(grad_out), bs, P, L.ptr(saved), lib.aitb_ait_saved_bytes(bs, P), C.byref(G),
+                       L.ptr(g_props), L.ptr(g_query), L.ptr(ws), nbytes, L.stream_ptr()))
         v = views
         out = [v["enc_emb.w"].view(512, 1024, 1, 1), v["enc_emb.bias"], v["dec_emb.w"].view(512, 1024, 1, 1),
                v["dec_emb.bias"], v["dec_trans.w"].view(1024, 512, 1, 1), v["dec_trans.bias"],

@@ -35,9 +35,9 @@ def _tap_major(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-def _grouped(x, w, out, G, taps, flags=0, bias=None):
+def _grouped(x, w, out, G, taps, flags=0, bias=None, round_tf32=False):
     return ops.gemm(x, w, out, M=G * 64, N=1024, K=GC, block_n=128, view="map", map_args=(1024, 8, 8, 1, G), taps=taps,
-                    group_c=GC, flags=flags, bias=bias)
+                    group_c=GC, flags=flags, bias=bias, round_tf32=round_tf32)
 
 
 class _SKBlockFn(torch.autograd.Function):
@@ -46,16 +46,19 @@ class _SKBlockFn(torch.autograd.Function):
     saves the NCHW round trip in both directions: the incoming gradient then is channels-last too)."""
 
     @staticmethod
-    def forward(ctx, x_nchw, w1, b1, w3, b3, cl_out=False):
+    def forward(ctx, x_nchw, w1, b1, w3, b3, cl_out=False, cl_in=False):
         ops._need_cuda(x_nchw, w1, b1, w3, b3)
-        if tuple(x_nchw.shape[1:]) != (1024, 8, 8) or tuple(w1.shape) != (1024, GC, 1, 1) or tuple(w3.shape) != (1024, GC, 3, 3):
+        if tuple(x_nchw.shape[1:]) != ((64, 1024) if cl_in else (1024, 8, 8)) or tuple(w1.shape) != (1024, GC, 1, 1) or tuple(w3.shape) != (1024, GC, 3, 3):
             raise RuntimeError("sk_block_train: expected x [G,1024,8,8] and the grouped (groups=8) 1x1 / 3x3 convolution weights")
         lib = L.load()
         G = x_nchw.shape[0]
         dev = x_nchw.device
         M = G * 64
-        x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32,
-                              round_tf32=True).view(M, 1024)
+        if cl_in:   # the token-major, tf32-rounded map the AIT training forward left in its saved buffer
+            x0 = x_nchw.detach().contiguous().float().view(M, 1024)
+        else:
+            x0 = ops.transpose_cs(x_nchw.detach().contiguous().float().reshape(G, 1024, 64), True, out_dtype=torch.float32,
+                                  round_tf32=True).view(M, 1024)
         m1 = round_to_tf32(_tap_major(w1.detach().float()).contiguous())          # [1024, 128]
         m3 = round_to_tf32(_tap_major(w3.detach().float()).contiguous())          # [1024, 9*128] tap-major
         r1 = torch.empty((M, 1024), dtype=torch.float32, device=dev)
@@ -65,7 +68,7 @@ class _SKBlockFn(torch.autograd.Function):
         _grouped(x0, m3, r3, G, 9, fl, b3.detach().float().contiguous())
         v = torch.empty((M, 1024), dtype=torch.float32, device=dev)
         _call(lib.aitb_sk_combine, L.ptr(r1), L.ptr(r3), L.ptr(v), C.c_size_t(v.numel()), 1 if cl_out else 0)
-        ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3, ctx.cl_out = G, x0, m1, m3, r1, r3, cl_out
+        ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3, ctx.cl_out, ctx.cl_in = G, x0, m1, m3, r1, r3, cl_out, cl_in
         if cl_out:
             return v.view(G, 64, 1024)
         return ops.transpose_cs(v.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
@@ -101,18 +104,24 @@ class _SKBlockFn(torch.autograd.Function):
             w1t = m1.view(GROUPS, GC, GC).transpose(1, 2).contiguous().view(1024, GC)
             dx = torch.empty((M, 1024), dtype=torch.float32, device=dev)
             _grouped(d3, w3t, dx, G, 9)
-            _grouped(d1, w1t, dx, G, 1, L.EPI_ACCUM)
-            dx_nchw = ops.transpose_cs(dx.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
-        return dx_nchw, dw1, db1, dw3, db3, None
+            _grouped(d1, w1t, dx, G, 1, L.EPI_ACCUM, round_tf32=ctx.cl_in)   # cl_in: the consumer is the AIT backward's GEMMs
+            if ctx.cl_in:
+                dx_nchw = dx.view(G, 64, 1024)
+            else:
+                dx_nchw = ops.transpose_cs(dx.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
+        return dx_nchw, dw1, db1, dw3, db3, None, None
 
 
-def sk_block_train(blk, x, channels_last_out=False):
+def sk_block_train(blk, x, channels_last_out=False, channels_last_in=False):
     """Differentiable `SKBlock.forward(x)` (blocks_...sk.py:960-984): x [G,1024,8,8] -> [G,1024,8,8]
-    (channels_last_out: [G,64,1024] token-major, tf32-rounded -- only for `top_train.head_to_tail_train(..., channels_last=True)`)."""
+    (channels_last_out: [G,64,1024] token-major, tf32-rounded -- only for `top_train.head_to_tail_train(..., channels_last=True)`;
+    channels_last_in: x is such a map, from `Transformer(..., token_major_out=True)`)."""
     c1, c3 = blk.convs[0][0], blk.convs[1][0]
-    return _SKBlockFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, bool(channels_last_out))
+    return _SKBlockFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, bool(channels_last_out), bool(channels_last_in))
 
 
-def sknet_train(sk, x_props, x_query, channels_last_out=False):
-    """Differentiable `SKNet.forward(x_props, x_query)` (blocks_...sk.py:993-998) -> (f_props, f_query)."""
-    return (sk_block_train(sk.sk_props, x_props, channels_last_out), sk_block_train(sk.sk_query, x_query, channels_last_out))
+def sknet_train(sk, x_props, x_query, channels_last_out=False, channels_last_in=False):
+    """Differentiable `SKNet.forward(x_props, x_query)` (blocks_...sk.py:993-998) -> (f_props, f_query).
+    channels_last_in applies to x_props only (x_query is the detector's NCHW query feature)."""
+    return (sk_block_train(sk.sk_props, x_props, channels_last_out, channels_last_in),
+            sk_block_train(sk.sk_query, x_query, channels_last_out))

@@ -112,19 +112,20 @@ class _AITTrainFunction(torch.autograd.Function):
     system/Models.py:231-280; gradients match it to tf32 accuracy (tests/test_gpu_train.py)."""
 
     @staticmethod
-    def forward(ctx, x_props, x_query, module, *params):
+    def forward(ctx, x_props, x_query, module, tm_out, *params):
         engine = packing.HeadEngine(transformer=module, dtype="tf32")     # weights change every step: repack
-        out, saved = engine.ait_forward_train(x_props, x_query)
-        ctx.engine, ctx.saved = engine, saved
+        out, saved = engine.ait_forward_train(x_props, x_query, token_major_out=tm_out)
+        ctx.engine, ctx.saved, ctx.tm_out = engine, saved, tm_out
         ctx.bs, ctx.num_props = x_query.shape[0], x_props.shape[0] // x_query.shape[0]
         ctx.in_dtypes = (x_props.dtype, x_query.dtype)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        g_props, g_query, g_params = ctx.engine.ait_backward(grad_out, ctx.saved, ctx.bs, ctx.num_props)
+        g_props, g_query, g_params = ctx.engine.ait_backward(grad_out, ctx.saved, ctx.bs, ctx.num_props,
+                                                             token_major_grad=ctx.tm_out)
         ctx.saved = None
-        return (g_props.to(ctx.in_dtypes[0]), g_query.to(ctx.in_dtypes[1]), None) + tuple(g_params)
+        return (g_props.to(ctx.in_dtypes[0]), g_query.to(ctx.in_dtypes[1]), None, None) + tuple(g_params)
 
 
 class Transformer(nn.Module):
@@ -175,8 +176,10 @@ class Transformer(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
-    def forward(self, x_props, x_query):
+    def forward(self, x_props, x_query, token_major_out=False):
         """x_props [bs*num_props, 1024, 7, 7], x_query [bs, 1024, 8, 8] -> [bs*num_props, 1024, 8, 8]
+        (token_major_out, training step only: the [bs*num_props, 64, 1024] token-major, tf32-rounded result without the NCHW
+        copy, for `sk_train.sknet_train(..., channels_last_in=True)`; its gradient comes back in the same layout)
         (Models.py:231-280).  .eval(): inference engine (no autograd graph, dropout = identity, like the reference in
         .eval()).  .train() with dropout = 0.0: differentiable training step with the library's own backward."""
         if self.training and any(m.p_dropout > 0 for m in self.modules() if hasattr(m, "p_dropout")):
@@ -197,7 +200,9 @@ class Transformer(nn.Module):
             # tf32 tensor-core math
             sd = dict(self.named_parameters())
             params = [sd[n] for n in packing.HeadEngine.ait_param_names()]
-            return _AITTrainFunction.apply(x_props, x_query, self, *params)
+            return _AITTrainFunction.apply(x_props, x_query, self, bool(token_major_out), *params)
+        if token_major_out:
+            raise RuntimeError("ait_b200.Transformer: token_major_out is a training-step hand-over (module in .train(), grad enabled)")
         if self._engine is None:
             self._engine = packing.HeadEngine(transformer=self, dtype=self.compute_dtype)
         return self._engine.ait_forward(x_props, x_query)

@@ -406,6 +406,14 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
 int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
                       size_t saved_bytes, const aitb_ait_grads* grads, float* grad_props, float* grad_query,
                       void* workspace, size_t workspace_bytes, aitb_stream_t stream);
+/* Layout hand-over inside a training step (no NCHW round trip between AIT and the next stage): aitb_ait_forward_train
+ * accepts out_nchw == NULL and leaves the token-major result [bp*64, 1024] (row = pair*64 + y*8 + x, tf32-rounded) in
+ * `saved` at byte offset aitb_ait_saved_offset(B, P, 1) (which = 0: the token-major pooled input [bp*49, 1024]);
+ * aitb_ait_backward_tm takes the incoming gradient in that same token-major layout, already rounded to tf32. */
+size_t aitb_ait_saved_offset(int B, int P, int which);
+int aitb_ait_backward_tm(const aitb_head_weights* w, const float* grad_out_tm, int B, int P, const void* saved,
+                         size_t saved_bytes, const aitb_ait_grads* grads, float* grad_props, float* grad_query,
+                         void* workspace, size_t workspace_bytes, aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4  training-only samplers and losses (ait_b200/csrc/targets.cu)
