@@ -92,9 +92,23 @@ __device__ __forceinline__ int out_row_of(const GemmKParams& p, int m, bool* ok)
   }
   *ok = m < p.M;
   const int mm = *ok ? m : 0;
+  // no regrouping (every GEMM but the 49 <-> 64 row remaps): skip the integer division -- ncu showed 408 instructions of
+  // per-tile set-up per epilogue warp (nine division sequences) against 4 x 226 for the tile's four chunks
+  if (p.rows_in == p.rows_out) return mm;
   const int grp = mm / p.rows_in, r = mm - grp * p.rows_in;
   if (r >= p.rows_out) *ok = false;   // rows_out < rows_in: only the first rows_out rows of every group are stored
   return *ok ? grp * p.rows_out + r : 0;
+}
+
+// staging-tile accesses with shared-space instructions: through a generic pointer they compile to LD.E / ST.E
+// (ncu: the first staged read of every chunk was the top long-scoreboard stall of the bf16 epilogue)
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -148,6 +162,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   const int piece = lane % kCh;
   const int srow0 = lane / kCh;
   auto phys = [](int r, int j) { return j ^ ((r / (8 / kCh)) % kCh); };
+  const uint32_t stg_s = smem_u32(stg);
   const T* res = reinterpret_cast<const T*>(p.res);
 
   // rows this lane serves in the coalesced phases
@@ -187,12 +202,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
       const int sr = it * kRpi + srow0;
-      *reinterpret_cast<uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16) = val[it];
+      sts128(stg_s + sr * kRowBytes + phys(sr, piece) * 16, val[it]);
     }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kCh; ++j) {
-      const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16);
+      const uint4 x = lds128(stg_s + lane * kRowBytes + phys(lane, j) * 16);
       if constexpr (sizeof(T) == 4) {
         r[4 * j + 0] = __uint_as_float(x.x); r[4 * j + 1] = __uint_as_float(x.y);
         r[4 * j + 2] = __uint_as_float(x.z); r[4 * j + 3] = __uint_as_float(x.w);
@@ -262,14 +277,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
       }
-      *reinterpret_cast<uint4*>(stg + lane * kRowBytes + phys(lane, j) * 16) = x;
+      sts128(stg_s + lane * kRowBytes + phys(lane, j) * 16, x);
     }
     __syncwarp();
     uint4 val[kIt];
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
       const int sr = it * kRpi + srow0;
-      val[it] = *reinterpret_cast<const uint4*>(stg + sr * kRowBytes + phys(sr, piece) * 16);
+      val[it] = lds128(stg_s + sr * kRowBytes + phys(sr, piece) * 16);
     }
 #pragma unroll
     for (int it = 0; it < kIt; ++it)
@@ -320,10 +335,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   };
 
   const bool aux_res = (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) != 0;
-  LaneVec lv_bias, lv_bias2, lv_gamma, lv_beta;  // bias2: dual (BLOCK_N 128) only; gamma / beta: CL only
-  if (p.flags & AITB_EPI_BIAS) lv_bias = load_lane_vec(p.bias + n0 + c_begin);
-  if constexpr (BLOCK_N == 128) {
-    if (p.flags & AITB_EPI_DUAL) lv_bias2 = load_lane_vec(p.bias2 + n0 + c_begin);
+  LaneVec lv_bias, lv_gamma, lv_beta;  // CL (LayerNorm path) only
+  if constexpr (CL) {   // the LayerNorm path hands bias / gamma / beta to the row owners by shuffles; the plain path loads them
+    if ((p.flags & AITB_EPI_BIAS) && (p.flags & AITB_EPI_LN)) lv_bias = load_lane_vec(p.bias + n0 + c_begin);
   }
   if constexpr (CL) {
     if (p.flags & AITB_EPI_LN) {
@@ -368,7 +382,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
       }
-      if (p.flags & AITB_EPI_BIAS) add_lane_vec(lv_bias, c0 - c_begin, v);
+      // bias: eight uniform-address 128-bit loads (one L1 wavefront each) instead of 32 shuffles through the MIO pipe
+      if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
       if (p.flags & AITB_EPI_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -383,7 +398,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
             for (int j = 0; j < 32; ++j) u[j] *= p.acc_scale2;
           }
-          add_lane_vec(lv_bias2, c0 - c_begin, u);
+          add_vec(p.bias2 + n0 + c0, u);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (p.flags & AITB_EPI_RELU) u[j] = fmaxf(u[j], 0.f);
