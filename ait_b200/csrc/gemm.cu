@@ -45,7 +45,6 @@ struct GemmKParams {
   int k_chunks;  // 128-byte K chunks per tap
   int taps;
   int a_m_dim, a_m_step, a_group_c;
-  int bias_ahead;   // plain epilogue: fetch the bias one chunk ahead (A/B: AITB_NO_BIAS_AHEAD=1)
   // a_m_dim == 2 ("map" mode: a W x H map tiled by boxes of map_bx x map_by = 128 positions, one image per
   // coordinate 3): m-tile t -> image t / map_tpg, first map row (t % map_tpg) * map_by; tile row r -> position
   // (x = r % map_bx, y = y0 + r / map_bx), valid while x < map_w and y < map_h; output row = image * map_w * map_h + y * map_w + x
@@ -347,22 +346,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     }
   }
   if (aux_res) prefetch_residual();
-  // plain path: the bias of a chunk is eight uniform-address 128-bit loads (one L1 wavefront each) instead of 32 shuffles
-  // through the MIO pipe, fetched ONE CHUNK AHEAD -- the first chunk's before the accumulator wait (ncu: loaded at the
-  // point of use, the dependent FADDs were 35 % of the chunk loop's stall samples)
-  // (compile-time off in the LayerNorm and dual-accumulator kernels: 32 more live registers spill there; they add the
-  // bias at the point of use)
-  constexpr bool kBiasAhead = !CL && BLOCK_N != 128;
-  const bool plain_bias = (p.flags & AITB_EPI_BIAS) != 0 && (!CL || (p.flags & AITB_EPI_LN) == 0);
-  float4 bq[kBiasAhead ? 8 : 1];
-  auto load_bias = [&](int c0) {
-    if constexpr (kBiasAhead) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
-    }
-  };
-  const bool bias_ahead = kBiasAhead && plain_bias && p.bias_ahead;
-  if (bias_ahead) load_bias(c_begin);
 
   mbar_wait(acc_full_bar, aph);
   tc_fence_after();
@@ -399,18 +382,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
       }
-      if constexpr (kBiasAhead) {
-        if (plain_bias && !bias_ahead) add_vec(p.bias + n0 + c0, v);
-        if (bias_ahead) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += bq[j].x; v[4 * j + 1] += bq[j].y; v[4 * j + 2] += bq[j].z; v[4 * j + 3] += bq[j].w;
-          }
-          if (c0 + 32 < c_end) load_bias(c0 + 32);
-        }
-      } else {
-        if (plain_bias) add_vec(p.bias + n0 + c0, v);
-      }
+      // bias: eight uniform-address 128-bit loads (one L1 wavefront each) instead of 32 shuffles through the MIO pipe
+      if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
       if (p.flags & AITB_EPI_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -1305,7 +1278,6 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     kp.map_tpg = (d->map_h + kp.map_by - 1) / kp.map_by;
   }
   kp.a_group_c = d->a_group_c;
-  kp.bias_ahead = getenv("AITB_NO_BIAS_AHEAD") == nullptr;
   kp.ke = kes;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = d->tap_dx[i];
