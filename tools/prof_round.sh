@@ -16,6 +16,6 @@ rm -f $O/fp32_full.ncu-rep $O/bf16_full.ncu-rep      # gpurun_out/ travels back 
 python tools/train_step_bench.py > $O/train_step.txt 2>&1
 python tools/head_train_bench.py 16 128 5 --graph > $O/head_train_step.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/head_train_launches_raw.csv python tools/head_train_bench.py 16 128 1 > $O/ncu_train.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'roi_align_bwd|wgrad|attn_bwd|im2col|sk_combine' -s 300 -c 12 -o $O/train_full python tools/head_train_bench.py 16 128 1 > $O/ncu_train_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'roi_align_bwd|wgrad|attn_bwd|sk_combine' -s 60 -c 14 -o $O/train_full python tools/head_train_bench.py 16 128 1 > $O/ncu_train_full.log 2>&1
 python tools/ncu_select.py $O/train_full.ncu-rep > $O/train_ncu_full_selected.csv
 ls -la $O; du -sh gpurun_out
