@@ -40,12 +40,6 @@ def _relu_bwd(dy, y):
     return out
 
 
-def _im2col(x, G, s, Cc):
-    out = torch.empty((G * s * s, 9 * Cc), dtype=torch.float32, device=x.device)
-    _call(L.load().aitb_im2col3x3, L.ptr(x), G, s, Cc, L.ptr(out))
-    return out
-
-
 def _subsample(x, G, S, s, stride, Cc):
     out = torch.empty((G * s * s, Cc), dtype=torch.float32, device=x.device)
     _call(L.load().aitb_map_subsample, L.ptr(x), G, S, s, stride, Cc, L.ptr(out))

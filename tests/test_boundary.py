@@ -123,3 +123,26 @@ def test_unit_sharding_is_a_partition():
             flat = [u for p in parts for u in p]
             assert flat == list(range(n_units))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_workspace_and_saved_buffer_accounting():
+    """Host-only size queries of the C ABI (no device call): the training forward's saved-activation buffer holds the
+    token-major pooled input at offset 0 and the token-major AIT result ([bp*64, 1024] fp32) entirely inside the buffer, at
+    a 1024-byte-aligned offset that grows with the problem -- `Transformer(..., token_major_out=True)` hands out a view at
+    that offset, so a wrong offset silently feeds the next stage the wrong tensor."""
+    from ait_b200 import _lib
+    lib = _lib.load(check_device=False)
+    prev = 0
+    for B, P in [(1, 1), (2, 3), (16, 128)]:
+        total = int(lib.aitb_ait_saved_bytes(B, P))
+        off_pooled = int(lib.aitb_ait_saved_offset(B, P, 0))
+        off_ait = int(lib.aitb_ait_saved_offset(B, P, 1))
+        assert off_pooled == 0
+        assert off_ait % 1024 == 0 and off_ait >= B * P * 49 * 1024 * 4          # behind the pooled input at least
+        assert off_ait + B * P * 64 * 1024 * 4 <= total
+        assert off_ait > prev
+        prev = off_ait
+        assert int(lib.aitb_ait_backward_workspace_bytes(B, P)) > 0
+    assert int(lib.aitb_ait_saved_offset(0, 4, 1)) == 0                            # bad sizes: 0, no crash
+    for dt in (_lib.AITB_F32, _lib.AITB_BF16, _lib.AITB_F32S):
+        assert int(lib.aitb_head_workspace_bytes(8, 300, dt)) > int(lib.aitb_head_workspace_bytes(1, 300, dt)) > 0
