@@ -45,6 +45,7 @@ struct GemmKParams {
   int k_chunks;  // 128-byte K chunks per tap
   int taps;
   int a_m_dim, a_m_step, a_group_c;
+  int bias_smem;   // 2-byte-output plain epilogue: per-warp shared-memory copy of the tile's bias slice (A/B: AITB_BIAS_GLOBAL=1)
   // a_m_dim == 2 ("map" mode: a W x H map tiled by boxes of map_bx x map_by = 128 positions, one image per
   // coordinate 3): m-tile t -> image t / map_tpg, first map row (t % map_tpg) * map_by; tile row r -> position
   // (x = r % map_bx, y = y0 + r / map_bx), valid while x < map_w and y < map_h; output row = image * map_w * map_h + y * map_w + x
@@ -109,6 +110,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
+}
+
+__device__ __forceinline__ uint4 __float4_as_uint4(float4 f) {
+  return make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -346,6 +351,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     }
   }
   if (aux_res) prefetch_residual();
+  // 2-byte outputs use only the lower 2 KB of the warp's 4 KB staging tile (32 rows x 64 B): the upper half keeps this
+  // warp's private copy of the tile's bias slice, fetched here -- before the accumulator wait -- so the chunk loop reads it
+  // with broadcast ld.shared (~25 clk) instead of global loads at the point of use (ncu: those missed L1 next to 225 KB of
+  // shared memory and cost an L2 round trip per chunk, ~35 % of the loop's stall samples).  AITB_BIAS_GLOBAL=1: A/B.
+  constexpr bool kBiasSmem = sizeof(T) == 2 && !CL && COLS <= 256;
+  const uint32_t bias_s = stg_s + 2048;
+  const bool bias_smem = kBiasSmem && (p.flags & AITB_EPI_BIAS) != 0 && p.bias_smem;
+  if constexpr (kBiasSmem) {
+    if (bias_smem) {
+      const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0 + c_begin);
+      if (lane * 4 < COLS) sts128(bias_s + lane * 16, __float4_as_uint4(__ldg(bsrc + lane)));
+      if constexpr (COLS > 128) sts128(bias_s + 512 + lane * 16, __float4_as_uint4(__ldg(bsrc + 32 + lane)));
+      __syncwarp();
+    }
+  }
 
   mbar_wait(acc_full_bar, aph);
   tc_fence_after();
@@ -383,7 +403,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
       }
       // bias: eight uniform-address 128-bit loads (one L1 wavefront each) instead of 32 shuffles through the MIO pipe
-      if (p.flags & AITB_EPI_BIAS) add_vec(p.bias + n0 + c0, v);
+      if (bias_smem) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 b = lds128(bias_s + (uint32_t)(c0 - c_begin) * 4u + (uint32_t)j * 16u);
+          v[4 * j] += __uint_as_float(b.x); v[4 * j + 1] += __uint_as_float(b.y);
+          v[4 * j + 2] += __uint_as_float(b.z); v[4 * j + 3] += __uint_as_float(b.w);
+        }
+      } else if (p.flags & AITB_EPI_BIAS) {
+        add_vec(p.bias + n0 + c0, v);
+      }
       if (p.flags & AITB_EPI_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -1278,6 +1307,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     kp.map_tpg = (d->map_h + kp.map_by - 1) / kp.map_by;
   }
   kp.a_group_c = d->a_group_c;
+  kp.bias_smem = getenv("AITB_BIAS_GLOBAL") == nullptr;
   kp.ke = kes;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = d->tap_dx[i];
