@@ -40,6 +40,15 @@ def _grouped(x, w, out, G, taps, flags=0, bias=None, round_tf32=False):
                     group_c=GC, flags=flags, bias=bias, round_tf32=round_tf32)
 
 
+def dgrad_weights(m1, m3):
+    """Packed forward weights (tap-major, [1024 out, taps*128 in-of-group]) -> the weights of the input-gradient convolution,
+    in the same packed form: within each group the in / out roles swap, and the 3x3 taps flip (the adjoint of a 'same'
+    correlation is the correlation with the 180-degree rotated kernel).  Pure tensor re-indexing (host logic; CPU-testable)."""
+    w3t = m3.view(GROUPS, GC, 9, GC).flip(2).permute(0, 3, 2, 1).contiguous().view(GROUPS * GC, 9 * GC)
+    w1t = m1.view(GROUPS, GC, GC).transpose(1, 2).contiguous().view(GROUPS * GC, GC)
+    return w1t, w3t
+
+
 class _SKBlockFn(torch.autograd.Function):
     """forward(x [G,1024,8,8], w1 [1024,128,1,1], b1 [1024], w3 [1024,128,3,3], b3 [1024], cl_out) -> [G,1024,8,8], or --
     cl_out: the consumer is `top_train` -- the channels-last token-major map [G,64,1024] rounded to tf32 (its GEMM operand;
@@ -100,8 +109,7 @@ class _SKBlockFn(torch.autograd.Function):
         dx_nchw = None
         if need_x:
             # per group: dx[:, in] = sum_taps shift(d3)[:, out] W3[out, flipped tap, in] + d1[:, out] W1[out, in]
-            w3t = m3.view(GROUPS, GC, 9, GC).flip(2).permute(0, 3, 2, 1).contiguous().view(1024, 9 * GC)
-            w1t = m1.view(GROUPS, GC, GC).transpose(1, 2).contiguous().view(1024, GC)
+            w1t, w3t = dgrad_weights(m1, m3)
             dx = torch.empty((M, 1024), dtype=torch.float32, device=dev)
             _grouped(d3, w3t, dx, G, 9)
             _grouped(d1, w1t, dx, G, 1, L.EPI_ACCUM, round_tf32=ctx.cl_in)   # cl_in: the consumer is the AIT backward's GEMMs

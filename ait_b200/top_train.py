@@ -52,6 +52,12 @@ def _upsample(x, G, S, s, stride, Cc):
     return out
 
 
+def dgrad_weight_3x3(w_packed, c_out, c_in):
+    """Tap-major packed 3x3 weight [c_out, 9*c_in] -> the packed weight [c_in, 9*c_out] of the input-gradient convolution
+    (taps flipped, in / out swapped).  Pure tensor re-indexing (host logic; CPU-testable)."""
+    return w_packed.view(c_out, 9, c_in).flip(1).permute(2, 1, 0).contiguous().view(c_in, 9 * c_out)
+
+
 class _HeadToTailFn(torch.autograd.Function):
     """forward(x_nchw [G,1024,8,8] (cl_in: the channels-last, tf32-rounded [G,64,1024] map `sk_train` hands over), consts,
     cl_in, *conv_weights) -> feat [G,2048].
@@ -136,8 +142,7 @@ class _HeadToTailFn(torch.autograd.Function):
                      flags=L.EPI_RELU_MASK, res=o2, ldr=512, round_tf32=True)
             # conv2 (3x3, 512 -> 512): weight gradient straight from the saved 4x4 map (nine shifted TMA boxes, no im2col)
             grads[(b, "conv2")] = ops.wgrad_conv(d_o2, o1, G, 4, 512, 512, groups=1, taps=9)
-            w2 = wd["conv2"].view(512, 9, 512)
-            w2d = w2.flip(1).permute(2, 1, 0).contiguous().view(512, 9 * 512)                  # [in, flipped tap, out]
+            w2d = dgrad_weight_3x3(wd["conv2"], 512, 512)
             d_o1 = torch.empty((M, 512), dtype=torch.float32, device=dev)
             ops.gemm(d_o2, w2d, d_o1, M=M, N=512, K=512, block_n=256, view="map", map_args=(512, 4, 4, 1, G), taps=9,
                      flags=L.EPI_RELU_MASK, res=o1, ldr=512, round_tf32=True)

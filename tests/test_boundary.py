@@ -146,3 +146,39 @@ def test_workspace_and_saved_buffer_accounting():
     assert int(lib.aitb_ait_saved_offset(0, 4, 1)) == 0                            # bad sizes: 0, no crash
     for dt in (_lib.AITB_F32, _lib.AITB_BF16, _lib.AITB_F32S):
         assert int(lib.aitb_head_workspace_bytes(8, 300, dt)) > int(lib.aitb_head_workspace_bytes(1, 300, dt)) > 0
+
+
+def test_training_weight_repacking_host_logic():
+    """The dgrad weights of the training path are pure re-indexings of the packed forward weights (sk_train.dgrad_weights,
+    top_train.dgrad_weight_3x3).  Checked on the CPU against torch autograd: a convolution of the output gradient with
+    the re-packed weight (tap-major, the layout the GEMM kernels consume) must equal the input gradient of the forward
+    convolution -- dense 3x3 (layer4 conv2) and grouped 1x1 / 3x3 (SKBlock, groups = 8)."""
+    import torch
+    import torch.nn.functional as F
+    from ait_b200 import sk_train, top_train
+
+    def tap_major(w):
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+    def unpack(m, c_out, c_in, k):          # packed [c_out, k*k*c_in] -> conv weight [c_out, c_in, k, k]
+        return m.view(c_out, k, k, c_in).permute(0, 3, 1, 2).contiguous()
+
+    g = torch.Generator().manual_seed(3)
+    # dense 3x3, 512 -> 512 on a 4x4 map
+    w = torch.randn(512, 512, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 512, 4, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(2, 512, 4, 4, generator=g, dtype=torch.float64)
+    F.conv2d(x, w, padding=1).backward(gy)
+    wd = top_train.dgrad_weight_3x3(tap_major(w), 512, 512)
+    got = F.conv2d(gy, unpack(wd, 512, 512, 3), padding=1)
+    assert torch.allclose(got, x.grad, rtol=1e-10, atol=1e-10)
+    # grouped (8 x 128 -> 128) 1x1 and 3x3 on an 8x8 map
+    w1 = torch.randn(1024, 128, 1, 1, generator=g, dtype=torch.float64)
+    w3 = torch.randn(1024, 128, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(1, 1024, 8, 8, generator=g, dtype=torch.float64, requires_grad=True)
+    g1 = torch.randn(1, 1024, 8, 8, generator=g, dtype=torch.float64)
+    g3 = torch.randn(1, 1024, 8, 8, generator=g, dtype=torch.float64)
+    (F.conv2d(x, w1, groups=8) * g1).sum().add((F.conv2d(x, w3, padding=1, groups=8) * g3).sum()).backward()
+    w1t, w3t = sk_train.dgrad_weights(tap_major(w1), tap_major(w3))
+    got = F.conv2d(g1, unpack(w1t, 1024, 128, 1), groups=8) + F.conv2d(g3, unpack(w3t, 1024, 128, 3), padding=1, groups=8)
+    assert torch.allclose(got, x.grad, rtol=1e-10, atol=1e-10)
