@@ -46,7 +46,63 @@ def parse():
                     help="fp32 = split bf16 hi/lo planes, 3 tensor-core passes per product (meets the reference's "
                          "fp32 scores to 1e-3); tf32 = fp32 storage + tf32 math; bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the supplementary BASELINE configs[3] line (whole-head training step, N=1 only)")
     return ap.parse_args()
+
+
+def train_step_extra(dev, tf_burst):
+    """Supplementary, outside the timed region of the headline metric: BASELINE configs[3] -- the whole-head training step
+    (ROIAlign -> AIT -> SKNet -> layer4 -> heads -> RCNN losses, forward + backward in libaitb200), batch 16 units x 128
+    proposals, fp32 storage / tf32 math, dropout 0; 2 warm-up + 3 timed steps, CUDA events.  Never fails the bench line."""
+    try:
+        import torch
+        from ait_b200 import synth
+        B, P = 16, 128
+        head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+        for mod in head.modules():
+            if hasattr(mod, "p_dropout"):
+                mod.p_dropout = 0.0
+        head = head.to(dev).train()
+        maps = torch.stack([synth.c4_map(u) for u in range(B)]).to(dev).requires_grad_()
+        qrys = torch.stack([synth.query_feat(u) for u in range(B)]).to(dev).requires_grad_()
+        rois = torch.stack([synth.random_rois(u, P, batch_index=u) for u in range(B)]).to(dev)
+        g = torch.Generator().manual_seed(3)
+        label = (torch.rand(B * P, generator=g) < 0.25).long().to(dev)
+        tgt = (0.3 * torch.randn(B * P, 4, generator=g)).to(dev)
+        inw = (label > 0).float().view(-1, 1).expand(-1, 4).contiguous()
+
+        def step():
+            head.zero_grad(set_to_none=True)
+            maps.grad = None
+            qrys.grad = None
+            losses = head.training_losses(maps, qrys, rois, label, tgt, inw, inw)
+            sum(losses).backward()
+            return losses
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        for _ in range(3):
+            losses = step()
+        en.record()
+        torch.cuda.synchronize()
+        ms = st.elapsed_time(en) / 3
+        flops = 3 * (B * P * FLOP_PER_PAIR + B * FLOP_PER_UNIT_SHARED)      # backward = 2 x forward (dgrad + wgrad)
+        n_grads = sum(1 for p_ in head.parameters() if p_.grad is not None) + 2
+        out = {"workload": "BASELINE configs[3]: whole-head training step forward+backward, %d units x %d proposals, fp32 storage / "
+                           "tf32 tensor-core math, dropout 0 (eager launches; tools/head_train_bench.py --graph replays it as one CUDA graph)" % (B, P),
+               "ms_per_step": ms, "pairs_per_s": B * P / (ms * 1e-3), "tflops_tf32_equivalent": flops / (ms * 1e-3) / 1e12,
+               "frac_of_tf32_peak": flops / (ms * 1e-3) / 1e12 / (tf_burst / 2.0), "gradients": n_grads,
+               "losses": [float(x.detach()) for x in losses],
+               "finite": bool(all(torch.isfinite(p_.grad).all() for p_ in head.parameters() if p_.grad is not None))}
+        del head, maps, qrys, losses
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # supplementary: report, never break the headline line
+        return {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
 def peaks():
@@ -383,6 +439,10 @@ def run_ours(args):
                         "sample": "2 units x %d proposals, one pass after one warm-up (top-%d NMS + head); %s"
                                   % (P, PRE_NMS, what)}
 
+    train_extra = None
+    if rank == 0 and world == 1 and not args.no_train_step:
+        train_extra = train_step_extra(dev, tf_burst)
+
     results = gather_results([(u, float(h_out["cls"][i].mean())) for i, u in enumerate(units)], world)
     if rank == 0:
         h2d = sum(t.numel() * t.element_size() for t in (h_maps, h_qrys, h_boxes, h_scores))
@@ -444,6 +504,8 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if train_extra is not None:
+            line["train_step_config4"] = train_extra
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
