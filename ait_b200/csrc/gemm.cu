@@ -45,6 +45,7 @@ struct GemmKParams {
   int k_chunks;  // 128-byte K chunks per tap
   int taps;
   int a_m_dim, a_m_step, a_group_c;
+  int simple_rows_ok;   // host: AITB_NO_SIMPLE_ROWS unset (A/B of the strided-row epilogue addressing)
   int bias_smem;   // 2-byte-output plain epilogue: per-warp shared-memory copy of the tile's bias slice (A/B: AITB_BIAS_GLOBAL=1)
   // a_m_dim == 2 ("map" mode: a W x H map tiled by boxes of map_bx x map_by = 128 positions, one image per
   // coordinate 3): m-tile t -> image t / map_tpg, first map row (t % map_tpg) * map_by; tile row r -> position
@@ -153,7 +154,10 @@ struct GemmCfg {
 // ---------------------------------------------------------------------------------------------
 // PARTS (CL LayerNorm): partial row statistics combined per row -- 2 = one per CTA of the cluster (each thread
 // drains all BLOCK_N columns of its CTA), 4 = two epilogue warpgroups per CTA, each draining COLS = BLOCK_N / 2.
-template <typename T, int BLOCK_N, bool CL, bool SPLIT, int COLS = BLOCK_N, int PARTS = 2>
+// SIMPLE (compile-time, chosen per launch by the 2-CTA kernel): output rows are the GEMM rows (no 49 <-> 64 regrouping, no
+// map mode), so the rows a lane stores are a fixed stride apart -- one base pointer + it * stride instead of kIt live
+// 64-bit pointers that the compiler otherwise re-derives from the kernel parameters inside the chunk loop.
+template <typename T, int BLOCK_N, bool CL, bool SPLIT, int COLS = BLOCK_N, int PARTS = 2, bool SIMPLE = false>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, float2* stats,
                                               uint64_t* stats_full_bar, uint64_t* acc_full_bar, uint32_t t_row,
                                               int q, int lane, int mt, int n0, uint32_t as, uint32_t aph,
@@ -171,15 +175,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   const T* res = reinterpret_cast<const T*>(p.res);
 
   // rows this lane serves in the coalesced phases
-  T* optr[kIt];
+  T* optr[SIMPLE ? 1 : kIt];
   const T* rptr[kIt];
   uint32_t vmask = 0;
+  // SIMPLE: row of it = 0; rows at or beyond M are masked by vmask, so their (never dereferenced) addresses do not matter
+  T* const optr0 = reinterpret_cast<T*>(p.out) + (size_t)(mt * kBlockM + q * 32 + srow0) * p.ldo + n0 + piece * (16 / (int)sizeof(T));
+  const size_t ostep = (size_t)kRpi * p.ldo;
+  auto optr_of = [&](int it) -> T* {
+    if constexpr (SIMPLE) return optr0 + (size_t)it * ostep;
+    else return optr[it];
+  };
 #pragma unroll
   for (int it = 0; it < kIt; ++it) {
     const int m = mt * kBlockM + q * 32 + it * kRpi + srow0;
     bool ok;
     const int orow = out_row_of(p, m, &ok);
-    optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
+    if constexpr (!SIMPLE) optr[it] = reinterpret_cast<T*>(p.out) + (size_t)orow * p.ldo + n0 + piece * (16 / (int)sizeof(T));
     int rrow = 0;
     if (p.flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK)) {
       const int rb = (p.flags & AITB_EPI_RES_ROW_M) ? (ok ? m : 0) : orow;   // residual indexed by GEMM row or by output row
@@ -200,6 +211,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     for (int it = 0; it < kIt; ++it) {
       val[it] = make_uint4(0u, 0u, 0u, 0u);
       if ((vmask >> it) & 1u) val[it] = ld_global_v4(ptrs[it] + c0);
+    }
+  };
+  // the same from the output rows themselves (ACCUM epilogue)
+  auto issue_out_loads = [&](int c0, uint4 (&val)[kIt]) {
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      val[it] = make_uint4(0u, 0u, 0u, 0u);
+      if ((vmask >> it) & 1u) val[it] = ld_global_v4(optr_of(it) + c0);
     }
   };
   // ... and turn it into this thread's 32 values of its own row through the swizzled staging tile
@@ -293,7 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     }
 #pragma unroll
     for (int it = 0; it < kIt; ++it)
-      if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr[it] + c0) = val[it];
+      if ((vmask >> it) & 1u) *reinterpret_cast<uint4*>(optr_of(it) + c0) = val[it];
     __syncwarp();
   };
   // split mode: hi = bf16(v) into the hi plane, lo = bf16(v - hi) into the lo plane (o_lo columns further)
@@ -377,7 +396,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     const bool dual = BLOCK_N == 128 && (p.flags & AITB_EPI_DUAL) != 0;
     uint4 pre[kIt], pre2[kIt];
     if (aux_res) issue_loads(rptr, c_begin, pre);
-    if (aux_acc) issue_loads(optr, c_begin, pre);
+    if (aux_acc) issue_out_loads(c_begin, pre);
     if constexpr (SPLIT) { if (aux_res) issue_loads(rptr, c_begin + p.r_lo, pre2); }
     uint32_t raw[32], raw2[32];
     tmem_ld32(t_row + c_begin, raw);
@@ -446,9 +465,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       if (p.flags & AITB_EPI_POS) add_vec(prow + c0, v);
       if (p.flags & AITB_EPI_ACCUM) {
         float r[32];
-        if (!aux_acc) issue_loads(optr, c0, pre);   // RES and ACCUM together: second stream not prefetched
+        if (!aux_acc) issue_out_loads(c0, pre);   // RES and ACCUM together: second stream not prefetched
         exchange(pre, r);
-        if (aux_acc && c0 + 32 < c_end) issue_loads(optr, c0 + 32, pre);
+        if (aux_acc && c0 + 32 < c_end) issue_out_loads(c0 + 32, pre);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += r[j];
       }
@@ -916,7 +935,9 @@ static constexpr int k2Threads = 384;  // warpgroup 0: TMA / MMA (+2 idle warps)
 static constexpr int k2SmemBytes = 6 * (kABytes + k2HalfB) + 1024 + 256 + 8 * 4096;
 
 // SPLIT: a stage holds [A_hi][A_lo][W_hi half][W_lo half] (64 KB, 3 stages) and every K slice issues three MMAs.
-template <typename T, bool SPLIT>
+// SIMPLE: see epilogue_tile -- a separate kernel instantiation per addressing mode, chosen on the host (two epilogue
+// copies inside one kernel were measured slower than either alone).
+template <typename T, bool SPLIT, bool SIMPLE = false>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const GemmKParams p) {
@@ -1047,9 +1068,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<T, BLOCK_N, false, SPLIT, 128>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
-                                              mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
-                                              half * 128 + 128);
+      epilogue_tile<T, BLOCK_N, false, SPLIT, 128, 2, SIMPLE>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
+                                                              mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
+                                                              half * 128 + 128);
       tc_fence_before();
       mbar_arrive_remote(&acc_empty[as], 0);
     }
@@ -1167,10 +1188,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
 }
 
-template <typename T, bool SPLIT>
+template <typename T, bool SPLIT, bool SIMPLE>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
   static SmemAttrOnce once;
-  auto kern = gemm2_tcgen05_kernel<T, SPLIT>;
+  auto kern = gemm2_tcgen05_kernel<T, SPLIT, SIMPLE>;
   if (ensure_dyn_smem((const void*)kern, k2SmemBytes, once, "gemm2_tcgen05_kernel")) return 1;
   const int tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -1308,6 +1329,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
   }
   kp.a_group_c = d->a_group_c;
   kp.bias_smem = getenv("AITB_BIAS_GLOBAL") == nullptr;
+  kp.simple_rows_ok = getenv("AITB_NO_SIMPLE_ROWS") == nullptr;
   kp.ke = kes;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = d->tap_dx[i];
@@ -1370,9 +1392,16 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
            : split              ? launch_gemm<__nv_bfloat16, 256, true, true>(tmA, tmB, kp, stream)
                                 : launch_gemm<__nv_bfloat16, 256, true, false>(tmA, tmB, kp, stream);
   if (two_cta)
-    return d->dtype == AITB_F32 ? launch_gemm2<float, false>(tmA, tmB, kp, stream)
-           : split              ? launch_gemm2<__nv_bfloat16, true>(tmA, tmB, kp, stream)
-                                : launch_gemm2<__nv_bfloat16, false>(tmA, tmB, kp, stream);
+  {
+    // output rows = GEMM rows (no regrouping, no large-map mode): the strided-row epilogue instantiation -- for 4-byte
+    // outputs only.  Measured on the FFN w_1 shape (ncu, same box): fp32 storage 920.8 k -> 855.5 k cycles (eight live
+    // 64-bit row pointers become one), bf16 435.3 k -> 468.7 k (four pointers: the array form is faster there).
+    const bool simple = kp.a_m_dim != 2 && kp.rows_in == kp.rows_out && kp.simple_rows_ok && d->dtype == AITB_F32;
+    if (simple) return launch_gemm2<float, false, true>(tmA, tmB, kp, stream);
+    return d->dtype == AITB_F32 ? launch_gemm2<float, false, false>(tmA, tmB, kp, stream)
+           : split              ? launch_gemm2<__nv_bfloat16, true, false>(tmA, tmB, kp, stream)
+                                : launch_gemm2<__nv_bfloat16, false, false>(tmA, tmB, kp, stream);
+  }
   switch (d->block_n) {
     case 64: return AITB_DISPATCH(64);
     case 128: return AITB_DISPATCH(128);
