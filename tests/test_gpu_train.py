@@ -456,3 +456,52 @@ def test_head_training_loop_reduces_the_loss():
     assert all(b < a + 1e-4 for a, b in zip(tot, tot[1:])), tot
     assert tot[-1] < tot[0] - 0.03, tot
     assert hist[-1][0] < hist[0][0] - 0.02 and hist[-1][2] < hist[0][2] - 0.005, hist
+
+
+def test_whole_head_training_step_matches_reference_golden_gradients():
+    """tests/golden/head_grad.pt: losses and gradients of the UNMODIFIED reference modules (CPU fp32 autograd,
+    tests/golden/make_golden_head_grad.py) on the inputs of the whole-head test above.  The device step (ROIAlign included,
+    tf32 tensor-core math) must reproduce the three losses to 2e-3 relative and every one of the 70 parameter gradients and
+    the query-feature gradient to 1e-1 relative L2 on the committed strided samples (ReLU-mask flips of a tf32 forward, see
+    above), with norms within 10 %."""
+    from conftest import load_golden
+    from ait_b200 import synth
+    gold = load_golden("head_grad.pt")
+    B, P = gold["B"], gold["P"]
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+    for mod in head.modules():
+        if hasattr(mod, "p_dropout"):
+            mod.p_dropout = 0.0
+    g = torch.Generator().manual_seed(gold["seed"])
+    maps = torch.stack([synth.c4_map(u) for u in range(B)])
+    qrys = torch.stack([synth.query_feat(u) for u in range(B)])
+    rois = torch.stack([synth.random_rois(u, P, batch_index=u) for u in range(B)])
+    label = torch.tensor([[1, 0, 0, 1], [0, 0, 1, 0]]).view(-1)
+    tgt = 0.3 * torch.randn(B * P, 4, generator=g)
+    inw = (label > 0).float().view(-1, 1).expand(-1, 4).contiguous()
+    head = head.to(DEV).train()
+    md, qd = maps.to(DEV).requires_grad_(), qrys.to(DEV).requires_grad_()
+    losses = head.training_losses(md, qd, rois.to(DEV), label.to(DEV), tgt.to(DEV), inw.to(DEV), inw.to(DEV))
+    sum(losses).backward()
+    torch.cuda.synchronize()
+    for a, b in zip(losses, gold["losses"]):
+        a = float(a.detach())
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (a, b)
+
+    def check(name, grad, entry):
+        assert grad is not None, name
+        f = grad.detach().double().cpu().reshape(-1)
+        s = f[::entry["stride"]][:entry["sample"].numel()]
+        r = entry["sample"].double()
+        e = float((s - r).norm() / r.norm())
+        assert e < 1e-1, (name, e)
+        assert abs(float(f.norm()) / entry["norm"] - 1.0) < 1e-1, name
+        return e
+
+    errs = {"non_qry": check("non_qry", qd.grad, gold["grad_query"])}
+    params = dict(head.named_parameters())
+    assert len(gold["params"]) == 70
+    for name, entry in gold["params"].items():
+        errs[name] = check(name, params[name].grad, entry)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print("whole-head train vs reference golden: worst rel-L2", [(k, "%.1e" % v) for k, v in worst])
