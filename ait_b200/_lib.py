@@ -214,6 +214,46 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _first_cuda_device(objs):
+    import torch
+    for a in objs:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (tuple, list)):
+            d = _first_cuda_device(a)
+            if d is not None:
+                return d
+    return None
+
+
+def on_tensor_device(fn):
+    """Decorator of every Python entry point that hands raw pointers to the library: run it with the CUDA device of its
+    first CUDA tensor argument current, so `stream_ptr()` (evaluated inside) is that device's current stream, the output
+    allocations land there and the launches go to the device that owns the pointers -- also when the caller's current
+    device is another one (`model.to('cuda:1')` without `torch.cuda.set_device`).  No-op when the devices already agree."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        import torch
+        dev = _first_cuda_device(args) or _first_cuda_device(kwargs.values())
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
+
+
+def guard_module_functions(namespace, module_name, skip=()):
+    """Apply `on_tensor_device` to every public function defined in a module (called at the bottom of ops.py)."""
+    import types
+    for name, obj in list(namespace.items()):
+        if isinstance(obj, types.FunctionType) and obj.__module__ == module_name and not name.startswith("_") \
+                and name not in skip:
+            namespace[name] = on_tensor_device(obj)
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return C.c_void_p(0 if t is None else t.data_ptr())

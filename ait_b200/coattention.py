@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .packing import round_to_tf32
+from .packing import fingerprint, round_to_tf32
 
 
 class CoattWeights(C.Structure):
@@ -93,7 +93,11 @@ class CoAttention(nn.Module):
         B, c, H, W = x_img.shape
         if c != 1024 or tuple(x_qry.shape) != (B, 1024, 8, 8):
             raise RuntimeError("ait_b200.CoAttention: expected x_img [B,1024,H,W] and x_qry [B,1024,8,8]")
-        w = self._packed[0] if self._packed is not None else self._pack()
+        fp = fingerprint(self)                  # in-place parameter updates since the last packing?
+        if self._packed is None or self._packed_fp != fp:
+            self._packed_fp = fp
+            self._pack()
+        w = self._packed[0]
         x_img, x_qry = x_img.contiguous(), x_qry.contiguous()
         non_img, non_qry = torch.empty_like(x_img), torch.empty_like(x_qry)
         nbytes = lib.aitb_coattention_workspace_bytes(B, H, W)

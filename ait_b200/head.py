@@ -49,7 +49,9 @@ class DetectionHead(nn.Module):
         self._engine = None
 
     def engine(self):
-        if self._engine is None:
+        fp = packing.fingerprint(self)          # in-place parameter updates since the last packing?
+        if self._engine is None or self._engine_fp != fp:
+            self._engine_fp = fp
             self._engine = packing.HeadEngine(transformer=self.transformer, sk=self.sk, top=self.RCNN_top,
                                               cls_score=self.RCNN_cls_score, bbox_pred=self.RCNN_bbox_pred,
                                               dtype=self.compute_dtype)

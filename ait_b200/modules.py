@@ -55,7 +55,9 @@ class SKNet(nn.Module):
 
     def forward(self, x_props, x_query):
         """x_props [bp,1024,8,8], x_query [bs,1024,8,8] -> same shapes (blocks_...sk.py:993-998)."""
-        if self._engine is None:
+        fp = packing.fingerprint(self)          # in-place parameter updates since the last packing?
+        if self._engine is None or self._engine_fp != fp:
+            self._engine_fp = fp
             self._engine = packing.HeadEngine(sk=self, dtype=self.compute_dtype)
         return self._engine.sk_forward(x_props, x_query)
 

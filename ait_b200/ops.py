@@ -332,3 +332,7 @@ def attn_bwd(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, G, mask_mode, n_keys):
 
 def launch_count(reset=False):
     return int(L.load(check_device=False).aitb_launch_count(1 if reset else 0))
+
+
+# every wrapper above runs on the device of its first CUDA tensor argument (one device guard, in one place)
+L.guard_module_functions(globals(), __name__, skip=("split_planes", "join_planes", "launch_count"))

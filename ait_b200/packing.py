@@ -26,6 +26,14 @@ def round_to_tf32(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def fingerprint(module):
+    """(storage pointer, version counter) of every parameter / buffer of a module tree.  The packed GEMM-ready copies are
+    snapshots: an in-place update (optimizer.step(), param.data.copy_(), BatchNorm statistics) bumps `_version`, a
+    re-assignment changes the pointer -- either makes the cached engine stale, and every cache checks this before use."""
+    import itertools
+    return tuple((t.data_ptr(), t._version) for t in itertools.chain(module.parameters(), module.buffers()))
+
+
 class HeadEngine:
     def __init__(self, transformer=None, sk=None, top=None, cls_score=None, bbox_pred=None,
                  dtype=torch.float32, round_acts=True):

@@ -71,6 +71,7 @@ def clip_boxes(boxes, im_h, im_w):
     return out
 
 
+@L.on_tensor_device
 def propose_rois(proposals, scores, pre_nms_topN=6000, post_nms_topN=300, nms_thresh=0.7):
     """proposals [B, K*A, 4], scores [B, K*A] (CUDA fp32) -> rois [B, post_nms_topN, 5], n_valid [B].
 
@@ -87,6 +88,7 @@ def propose_rois(proposals, scores, pre_nms_topN=6000, post_nms_topN=300, nms_th
     return rois, n_keep
 
 
+@L.on_tensor_device
 def rpn_decode(rpn_cls_prob, rpn_bbox_pred, base_anchors, im_info, feat_stride):
     """rpn_cls_prob [B, 2A, H, W], rpn_bbox_pred [B, 4A, H, W], base_anchors [A, 4], im_info [B, 3]
     -> proposals [B, H*W*A, 4] (decoded, clipped), fg scores [B, H*W*A]  (proposal_layer.py:66-118)."""
@@ -118,6 +120,7 @@ class ProposalLayer(nn.Module):
         self._num_anchors = self._anchors.size(0)
         self.cfg = cfg or RPN_CFG
 
+    @L.on_tensor_device
     def forward(self, input):
         scores, bbox_deltas, im_info, cfg_key = input[0], input[1], input[2], input[3]
         c = self.cfg[cfg_key]
@@ -131,6 +134,7 @@ BBOX_NORMALIZE_STDS = (0.1, 0.1, 0.2, 0.2)
 BBOX_NORMALIZE_MEANS = (0.0, 0.0, 0.0, 0.0)
 
 
+@L.on_tensor_device
 def detections(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
                stds=BBOX_NORMALIZE_STDS, means=BBOX_NORMALIZE_MEANS, rescale=True):
     """Detection post-processing of test_net_voc.py:380-446 for a batch of units, on the device (row f2):

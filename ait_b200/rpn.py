@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .packing import round_to_tf32
+from .packing import fingerprint, round_to_tf32
 from .proposal import RPN_CFG, generate_anchors, propose_rois
 
 
@@ -87,7 +87,11 @@ class _RPN(nn.Module):
         ops._need_cuda(base_feat, im_info)
         if base_feat.dtype != torch.float32 or base_feat.dim() != 4 or base_feat.shape[1] != self.din:
             raise RuntimeError("ait_b200._RPN: base_feat must be float32 [B, %d, H, W]" % self.din)
-        w = self._packed[0] if self._packed is not None else self._pack()
+        fp = fingerprint(self)                  # in-place parameter updates since the last packing?
+        if self._packed is None or self._packed_fp != fp:
+            self._packed_fp = fp
+            self._pack()
+        w = self._packed[0]
         base_feat = base_feat.contiguous()
         B, _, H, W = base_feat.shape
         A, dev = w.A, base_feat.device

@@ -55,6 +55,7 @@ class _SKBlockFn(torch.autograd.Function):
     saves the NCHW round trip in both directions: the incoming gradient then is channels-last too)."""
 
     @staticmethod
+    @L.on_tensor_device
     def forward(ctx, x_nchw, w1, b1, w3, b3, cl_out=False, cl_in=False):
         ops._need_cuda(x_nchw, w1, b1, w3, b3)
         if tuple(x_nchw.shape[1:]) != ((64, 1024) if cl_in else (1024, 8, 8)) or tuple(w1.shape) != (1024, GC, 1, 1) or tuple(w3.shape) != (1024, GC, 3, 3):
@@ -83,6 +84,7 @@ class _SKBlockFn(torch.autograd.Function):
         return ops.transpose_cs(v.view(G, 64, 1024), False, out_dtype=torch.float32).view(G, 1024, 8, 8)
 
     @staticmethod
+    @L.on_tensor_device
     def backward(ctx, d_out):
         lib = L.load()
         G, x0, m1, m3, r1, r3 = ctx.G, ctx.x0, ctx.m1, ctx.m3, ctx.r1, ctx.r3

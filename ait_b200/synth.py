@@ -48,9 +48,12 @@ def random_rois(unit, n, batch_index=0):
 
 
 def make_head(seed=0, calibrated=False, randomize_bn=False, compute_dtype=torch.float32):
-    """Random-init DetectionHead (reference init distributions).  `calibrated` rescales RCNN_cls_score
-    so cls_prob is spread over (0.05, 0.95) instead of the degenerate 0.0057 +- 1e-6 of the stock init
-    (SURVEY fact 10); `randomize_bn` gives the frozen BatchNorms non-trivial statistics."""
+    """Random-init DetectionHead (reference init distributions).  `calibrated` raises the scale of the RCNN_cls_score /
+    RCNN_bbox_pred weights above the stock init's degenerate 0.0057 +- 1e-6 scores -- but a random
+    direction saturates instead (cls_prob 0.9991 .. 0.9999 on the benchmark inputs: measured), so a score comparison on
+    it is still near-vacuous.  `spread_score_layer(head)` installs the score layer that does spread cls_prob (the one
+    fitted for tests/golden/head_b2p4.pt); smoke(), bench.py and the parity tests use it.  `randomize_bn` gives the
+    frozen BatchNorms non-trivial statistics."""
     from .head import DetectionHead
     torch.manual_seed(seed)
     head = DetectionHead(compute_dtype=compute_dtype)
@@ -69,3 +72,19 @@ def make_head(seed=0, calibrated=False, randomize_bn=False, compute_dtype=torch.
             head.RCNN_cls_score[1].bias.copy_(torch.randn(2, generator=g) * 0.1)
             head.RCNN_bbox_pred.weight.copy_(torch.randn(4, 2048, generator=g) * 0.01)
     return head.eval()
+
+
+def spread_score_layer(head, path=None):
+    """Install the spread-calibrated RCNN_cls_score of tests/golden/head_b2p4.pt (make_golden.py: first layer = the three
+    principal directions of the golden pairs' features, unit spread) on a `make_head(seed=0, calibrated=True,
+    randomize_bn=True)` head: cls_prob then spans 0.05 .. 0.99 on the smoke inputs and 0.03 .. 0.3 within one 300-proposal
+    benchmark unit (different offsets per unit), so an absolute 1e-3 gate on it carries signal.  Returns the head."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "head_b2p4.pt")
+    state = torch.load(path, map_location="cpu", weights_only=False)["cls_score_state"]
+    dev = head.RCNN_cls_score[0].weight.device
+    head.RCNN_cls_score.load_state_dict({k: v.to(dev) for k, v in state.items()})
+    if hasattr(head, "invalidate"):
+        head.invalidate()
+    return head

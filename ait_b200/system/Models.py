@@ -203,6 +203,8 @@ class Transformer(nn.Module):
             return _AITTrainFunction.apply(x_props, x_query, self, bool(token_major_out), *params)
         if token_major_out:
             raise RuntimeError("ait_b200.Transformer: token_major_out is a training-step hand-over (module in .train(), grad enabled)")
-        if self._engine is None:
+        fp = packing.fingerprint(self)          # in-place parameter updates since the last packing?
+        if self._engine is None or self._engine_fp != fp:
+            self._engine_fp = fp
             self._engine = packing.HeadEngine(transformer=self, dtype=self.compute_dtype)
         return self._engine.ait_forward(x_props, x_query)

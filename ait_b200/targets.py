@@ -31,8 +31,9 @@ from . import _lib as L
 from . import ops
 from .proposal import generate_anchors
 
-# cfg.TRAIN.* (lib/model/utils/config.py:23,81-158)
-TRAIN_CFG = dict(BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.1,
+# cfg.TRAIN.* as the reference trains: lib/model/utils/config.py:23,81-158 merged with cfgs/res50.yml (trainval_net_voc.py:206-209
+# always loads one of cfgs/res50*.yml / res101.yml; all of them override BG_THRESH_LO to 0.0 -- config.py's 0.1 is never in effect)
+TRAIN_CFG = dict(BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.0,
                  BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0), BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2),
                  BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0), BBOX_NORMALIZE_TARGETS_PRECOMPUTED=True,
                  RPN_POSITIVE_OVERLAP=0.7, RPN_NEGATIVE_OVERLAP=0.3, RPN_CLOBBER_POSITIVES=False,
@@ -70,6 +71,7 @@ class AnchorTargetLayer(nn.Module):
             raise RuntimeError("AnchorTargetLayer: only the uniform weighting (RPN_POSITIVE_WEIGHT < 0) exists in the "
                                "reference (anchor_target_layer.py:162-171 leaves the other branch undefined)")
 
+    @L.on_tensor_device
     def forward(self, input):
         rpn_cls_score, gt_boxes, im_info = input[0], input[1], input[2]
         lib = L.load()
@@ -145,6 +147,7 @@ class ProposalTargetLayer(nn.Module):
         self.cfg = dict(TRAIN_CFG, **(cfg or {}))
         self.rng = rng
 
+    @L.on_tensor_device
     def forward(self, all_rois, gt_boxes, num_boxes=None):
         lib = L.load()
         ops._need_cuda(all_rois, gt_boxes)
@@ -224,6 +227,7 @@ _ProposalTargetLayer = ProposalTargetLayer
 
 class _RPNLossFn(torch.autograd.Function):
     @staticmethod
+    @L.on_tensor_device
     def forward(ctx, rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside, sigma):
         lib = L.load()
         ops._need_cuda(rpn_cls_score, rpn_bbox_pred, labels, targets, inside, outside)
@@ -241,6 +245,7 @@ class _RPNLossFn(torch.autograd.Function):
         return losses[0], losses[1]
 
     @staticmethod
+    @L.on_tensor_device
     def backward(ctx, g_cls, g_box):
         lib = L.load()
         t = ctx.saved_tensors
@@ -264,6 +269,7 @@ def rpn_losses(rpn_cls_score, rpn_bbox_pred, rpn_data, sigma=3.0):
 
 class _RCNNLossFn(torch.autograd.Function):
     @staticmethod
+    @L.on_tensor_device
     def forward(ctx, score, bbox_pred, labels, targets, inside, outside, bs, margin, margin_scale):
         lib = L.load()
         ops._need_cuda(score, bbox_pred, labels, targets, inside, outside)
@@ -284,6 +290,7 @@ class _RCNNLossFn(torch.autograd.Function):
         return losses[0], losses[1], losses[2]
 
     @staticmethod
+    @L.on_tensor_device
     def backward(ctx, g_cls, g_margin, g_bbox):
         lib = L.load()
         t = ctx.saved_tensors
@@ -310,6 +317,7 @@ class _ScoreHeadsFn(torch.autograd.Function):
     """score / bbox heads on the pooled features, differentiable w.r.t. both feature inputs and the six parameters."""
 
     @staticmethod
+    @L.on_tensor_device
     def forward(ctx, feat, qfeat, P, w_bbox, b_bbox, w1, b1, w2, b2):
         lib = L.load()
         ops._need_cuda(feat, qfeat, w_bbox, b_bbox, w1, b1, w2, b2)
@@ -330,6 +338,7 @@ class _ScoreHeadsFn(torch.autograd.Function):
         return score, bbox
 
     @staticmethod
+    @L.on_tensor_device
     def backward(ctx, d_score, d_bbox):
         lib = L.load()
         feat, qfeat, hidden, w_bbox, w1, w2 = ctx.saved_tensors
@@ -355,6 +364,7 @@ def score_heads(feat, qfeat, P, RCNN_bbox_pred, RCNN_cls_score):
                                RCNN_cls_score[0].bias, RCNN_cls_score[1].weight, RCNN_cls_score[1].bias)
 
 
+@L.on_tensor_device
 def mean_pool_backward(d_feat):
     """Adjoint of `_head_to_tail`'s spatial mean: d_feat [G,2048] -> d_top [G,16,2048] (token-major 4x4 map)."""
     lib = L.load()

@@ -65,6 +65,7 @@ class _HeadToTailFn(torch.autograd.Function):
     (b0.conv1, b0.conv2, b0.conv3, b0.downsample.0, b1.conv1, b1.conv2, b1.conv3, b2.conv1, b2.conv2, b2.conv3)."""
 
     @staticmethod
+    @L.on_tensor_device
     def forward(ctx, x_nchw, consts, cl_in, *weights):
         ops._need_cuda(x_nchw, *weights)
         G = x_nchw.shape[0]
@@ -115,6 +116,7 @@ class _HeadToTailFn(torch.autograd.Function):
         return feat
 
     @staticmethod
+    @L.on_tensor_device
     def backward(ctx, d_feat):
         lib = L.load()
         G, consts, packed, saved, x0 = ctx.G, ctx.consts, ctx.packed, ctx.saved, ctx.x0

@@ -78,10 +78,11 @@ def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False):
     src = xp.view(bp, 512, -1).permute(0, 2, 1)                                   # [bp, 49, 512]
     trg = rq.view(bp, 512, -1).permute(0, 2, 1)                                   # [bp, 64, 512]
     n_s, n_t = src.size(1), trg.size(1)
-    src_mask = torch.cat([torch.ones(bp, 1, n_s, dtype=torch.uint8),
-                          torch.zeros(bp, 1, n_t - n_s, dtype=torch.uint8)], dim=2)            # :258-260
-    trg_mask = (1 - torch.triu(torch.ones(1, n_t, n_t), diagonal=1)).to(torch.uint8).expand(bp, n_t, n_t)  # :262-263
-    src = torch.cat([src, torch.zeros(bp, n_t - n_s, 512, dtype=dtype)], dim=1)   # :268-270
+    dev = x_props.device   # the reference builds masks / padding on the CPU and moves them (.to(device), :258-269)
+    src_mask = torch.cat([torch.ones(bp, 1, n_s, dtype=torch.uint8, device=dev),
+                          torch.zeros(bp, 1, n_t - n_s, dtype=torch.uint8, device=dev)], dim=2)            # :258-260
+    trg_mask = (1 - torch.triu(torch.ones(1, n_t, n_t, device=dev), diagonal=1)).to(torch.uint8).expand(bp, n_t, n_t)  # :262-263
+    src = torch.cat([src, torch.zeros(bp, n_t - n_s, 512, dtype=dtype, device=dev)], dim=1)   # :268-270
     # Encoder.forward (:83-111)
     e = src + w["encoder.position_enc.pos_table"][:, :n_t]
     e = F.layer_norm(e, (512,), w["encoder.layer_norm.weight"], w["encoder.layer_norm.bias"], eps=1e-6)

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 
 # lib/model/utils/config.py:81-158 (cfg.TRAIN.*) and :23 (MARGIN)
-TRAIN = dict(BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.1,
+TRAIN = dict(BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.0,
              BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0), BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2),
              BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0),
              RPN_POSITIVE_OVERLAP=0.7, RPN_NEGATIVE_OVERLAP=0.3, RPN_CLOBBER_POSITIVES=False, RPN_FG_FRACTION=0.5,

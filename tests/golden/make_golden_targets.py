@@ -38,7 +38,11 @@ def main():
     from model.rpn.anchor_target_layer import _AnchorTargetLayer
     from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
     from model.utils.net_utils import _smooth_l1_loss
-    from model.utils.config import cfg
+    from model.utils.config import cfg, cfg_from_file
+    # the EFFECTIVE training configuration: trainval_net_voc.py:206-209 always merges one of cfgs/res50*.yml / res101.yml
+    # over the config.py defaults, and every one of them sets TRAIN.BG_THRESH_LO: 0.0 (config.py's 0.1 is never used)
+    cfg_from_file(os.path.join(ref_import.REF_ROOT, "cfgs", "res50.yml"))
+    assert cfg.TRAIN.BG_THRESH_LO == 0.0 and cfg.TRAIN.BATCH_SIZE == 128
     gt, nb = T.synth_gt_boxes(41, B)
     im_info = torch.tensor([[300.0, 500.0, 1.0]] * B)
     rois = T.synth_rois(43, B, R, gt)
@@ -71,7 +75,7 @@ def main():
     loss_bbox = _smooth_l1_loss(bbox_pred, p_out[2].view(-1, 4), p_out[3].view(-1, 4), p_out[4].view(-1, 4))
     total = rpn_loss_cls + rpn_loss_box + loss_cls + margin_loss + loss_bbox
     total.backward()
-    torch.save(dict(seeds=dict(gt=41, rois=43, anchor_np=7, proposal_np=11, loss=47), shape=(B, A, H, W, R),
+    torch.save(dict(cfg_file="cfgs/res50.yml", bg_thresh_lo=float(cfg.TRAIN.BG_THRESH_LO), seeds=dict(gt=41, rois=43, anchor_np=7, proposal_np=11, loss=47), shape=(B, A, H, W, R),
                     margin=float(cfg.TRAIN.MARGIN), anchors=at._anchors.clone(),
                     anchor_target=[t.clone() for t in a_out], proposal_target=[t.clone() for t in p_out],
                     losses=dict(rpn_cls=rpn_loss_cls.detach(), rpn_box=rpn_loss_box.detach(), cls=loss_cls.detach(),

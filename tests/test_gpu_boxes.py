@@ -63,6 +63,23 @@ def test_detection_postprocessing_matches_oracle(thresh, max_per_image):
         assert torch.all(dets[b, n:] == 0)
 
 
+def test_detection_postprocessing_matches_reference_golden():
+    """Row f2 against the reference's own script lines (tests/golden/detections.pt, make_golden_detections.py executes
+    test_net_voc.py:380-450 unmodified): same detections, same order, coordinates to 5e-4 px (expf vs libm)."""
+    from conftest import load_golden
+    from ait_b200.proposal import detections
+    g = load_golden("detections.pt")
+    for case in g["cases"]:
+        dets, n_det = detections(g["rois"].to(DEV), g["cls_prob"].to(DEV), g["bbox_pred"].to(DEV), g["im_info"].to(DEV),
+                                 case["thresh"], g["nms_thresh"], case["max_per_image"])
+        dets, n_det = dets.cpu(), n_det.cpu()
+        for b, ref in enumerate(case["dets"]):
+            n = int(n_det[b])
+            assert n == ref.shape[0], (case["thresh"], case["max_per_image"], b, n, ref.shape)
+            assert torch.equal(dets[b, :n, 4], ref[:, 4])
+            assert torch.allclose(dets[b, :n, :4], ref[:, :4], rtol=2e-6, atol=5e-4)
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", 3e-5), ("tf32", 2e-3), ("bf16", 3e-2)])
 @pytest.mark.parametrize("H,W", [(19, 31), (38, 63), (21, 100)])
 def test_rpn_head_matches_oracle(mode, tol, H, W):

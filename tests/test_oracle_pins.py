@@ -322,6 +322,10 @@ def test_oracle_target_layers_vs_reference_live():
     ref_import.install()
     from model.rpn.anchor_target_layer import _AnchorTargetLayer
     from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+    from model.utils.config import cfg_from_file
+    import os
+    # the effective training configuration (trainval_net_voc.py:206-209): config.py merged with cfgs/res50.yml -> BG_THRESH_LO 0.0
+    cfg_from_file(os.path.join(ref_import.REF_ROOT, "cfgs", "res50.yml"))
     at, pt = _AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2]), _ProposalTargetLayer(2)
     for seed, B, H, W, imh, imw, n_max in ((1, 2, 38, 63, 600.0, 1000.0, 6), (2, 4, 25, 40, 400.0, 640.0, 14)):
         gt, nb = T.synth_gt_boxes(seed, B, im_h=imh, im_w=imw, n_min=1, n_max=n_max)
@@ -396,3 +400,17 @@ def test_oracle_whole_head_training_step_matches_reference_golden_gradients():
     for name in rest:
         if name.startswith("sk."):
             assert sd[name].grad is None or float(sd[name].grad.abs().max()) == 0.0, name
+
+
+def test_detection_postprocessing_oracle_matches_reference_golden():
+    """Row f2 pin: tests/golden/detections.pt holds what the reference's OWN script lines (test_net_voc.py:380-450, exec'd
+    unmodified by make_golden_detections.py with the reference's cfg / bbox_transform_inv / clip_boxes / nms) produce; the
+    restatement `head_oracle.detections` must give the same detections in the same order."""
+    g = load_golden("detections.pt")
+    for case in g["cases"]:
+        mine = head_oracle.detections(g["rois"], g["cls_prob"], g["bbox_pred"], g["im_info"], case["thresh"],
+                                      g["nms_thresh"], case["max_per_image"])
+        for b, ref in enumerate(case["dets"]):
+            assert mine[b].shape == ref.shape, (case["thresh"], case["max_per_image"], b, mine[b].shape, ref.shape)
+            assert torch.equal(mine[b][:, 4], ref[:, 4])
+            torch.testing.assert_close(mine[b][:, :4], ref[:, :4], rtol=1e-6, atol=1e-5)
