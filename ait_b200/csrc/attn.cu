@@ -600,7 +600,9 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0, "aitb_attn_core: leading dimensions must be multiples of 4");
   AITB_REQUIRE(kv_rows == kT || (kv_rows > 0 && kv_rows < kT && mask_mode == 0 && n_keys <= kv_rows),
                "aitb_attn_core: compact K/V rows need the key-padding mask with n_keys <= kv_rows");
-  if ((dtype == AITB_BF16 || dtype == AITB_F32S) && getenv("AITB_ATTN_TC") != nullptr) {
+  static const bool want_tc = getenv("AITB_ATTN_TC") != nullptr;            // A/B switches: read once per process
+  static const bool want_two_pass = getenv("AITB_ATTN_TWO_PASS") != nullptr;
+  if ((dtype == AITB_BF16 || dtype == AITB_F32S) && want_tc) {
     // opt-in tcgen05 kernel (attn_tc.cu): Q K^T and P V on the 5th-generation tensor cores, TMEM accumulators, TMA
     // operands -- correct, but measured slower than the kernels below on the benchmark shape (see its header)
     const int rc = attn_tc_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, stream, kv_rows);
@@ -610,7 +612,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
                                                             (float*)out, round_tf, kv_rows);
-  } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || getenv("AITB_ATTN_TWO_PASS") != nullptr)) {
+  } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || want_two_pass)) {
     // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch)
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,

@@ -1328,8 +1328,11 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     kp.map_tpg = (d->map_h + kp.map_by - 1) / kp.map_by;
   }
   kp.a_group_c = d->a_group_c;
-  kp.bias_smem = getenv("AITB_BIAS_GLOBAL") == nullptr;
-  kp.simple_rows_ok = getenv("AITB_NO_SIMPLE_ROWS") == nullptr;
+  // A/B switches of the epilogue variants: read once per process, not per launch
+  static const bool bias_smem_on = getenv("AITB_BIAS_GLOBAL") == nullptr;
+  static const bool simple_rows_on = getenv("AITB_NO_SIMPLE_ROWS") == nullptr;
+  kp.bias_smem = bias_smem_on;
+  kp.simple_rows_ok = simple_rows_on;
   kp.ke = kes;
   for (int i = 0; i < 9; ++i) {
     kp.tap_dx[i] = d->tap_dx[i];

@@ -13,6 +13,7 @@
 //      depends on the (arbitrary) compaction order.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/aitb200.h"
 #include "common.cuh"
@@ -73,11 +74,11 @@ static constexpr int kSortMax = 16384;
 
 __global__ void __launch_bounds__(1024)
 topk_bitonic_kernel(const int32_t* __restrict__ cand_count, const unsigned long long* __restrict__ cand, int n_total,
-                    int n, int64_t* __restrict__ order) {
+                    int n, int max_nc, int64_t* __restrict__ order) {
   extern __shared__ unsigned long long sk[];
   const int b = blockIdx.x;
   const int nc = cand_count[b];
-  if (nc > kSortMax) return;  // handled by topk_rank_kernel
+  if (nc > max_nc) return;  // handled by topk_rank_kernel
   int S = 1024;
   while (S < nc) S <<= 1;
   const unsigned long long* c = cand + (size_t)b * n_total;
@@ -101,26 +102,34 @@ topk_bitonic_kernel(const int32_t* __restrict__ cand_count, const unsigned long 
   for (int r = threadIdx.x; r < n; r += blockDim.x) order[(size_t)b * n + r] = (int64_t)(~(uint32_t)sk[r]);
 }
 
-// fallback for nc > kSortMax: exact rank by counting over shared-memory tiles
+// Exact rank by counting: the position of a candidate in the descending order is the number of candidates that compare
+// greater (keys are distinct: the index is part of the key).  Quadratic, but embarrassingly parallel -- nc^2 = 36 M
+// compare-and-count steps per image at nc = 6000 spread over every SM finish in a fraction of the time one CTA needs to
+// walk the 91 barrier-separated stages of the shared-memory bitonic network (measured 80 us -> see DESIGN), and the
+// result cannot depend on the (arbitrary) compaction order.  min_nc: images with fewer candidates are left to the bitonic kernel.
 __global__ void __launch_bounds__(256)
 topk_rank_kernel(const int32_t* __restrict__ cand_count, const unsigned long long* __restrict__ cand, int n_total,
-                 int n, int64_t* __restrict__ order) {
-  __shared__ unsigned long long tk[1024];
+                 int n, int min_nc, int64_t* __restrict__ order) {
+  constexpr int kTile = 2048;
+  __shared__ __align__(16) unsigned long long tk[kTile];
   const int b = blockIdx.y;
   const int nc = cand_count[b];
-  if (nc <= kSortMax || (int)(blockIdx.x * blockDim.x) >= nc) return;  // uniform per CTA
+  if (nc <= min_nc || (int)(blockIdx.x * blockDim.x) >= nc) return;  // uniform per CTA
   const unsigned long long* c = cand + (size_t)b * n_total;
   const int me = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = me < nc;
-  const unsigned long long mk = live ? c[me] : 0ULL;
+  const unsigned long long mk = live ? c[me] : ~0ULL;
   int rank = 0;
-  for (int t0 = 0; t0 < nc; t0 += 1024) {
+  for (int t0 = 0; t0 < nc; t0 += kTile) {
     __syncthreads();
-    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tk[j] = t0 + j < nc ? c[t0 + j] : 0ULL;
+    for (int j = threadIdx.x; j < kTile; j += blockDim.x) tk[j] = t0 + j < nc ? c[t0 + j] : 0ULL;   // padding never counts
     __syncthreads();
-    const int lim = min(1024, nc - t0);
+    const int lim = min(kTile, (nc - t0 + 1) & ~1);
 #pragma unroll 8
-    for (int j = 0; j < lim; ++j) rank += tk[j] > mk;
+    for (int j = 0; j < lim; j += 2) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tk[j]);
+      rank += (v.x > mk) + (v.y > mk);
+    }
   }
   if (live && rank < n) order[(size_t)b * n + rank] = (int64_t)(~(uint32_t)mk);
 }
@@ -148,13 +157,19 @@ int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, voi
   if (check_launch("topk_hist_kernel")) return 1;
   topk_compact_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(scores, n_total, thr_bin, cand_count, cand);
   if (check_launch("topk_compact_kernel")) return 1;
-  static SmemAttrOnce once;
-  const int smem = kSortMax * 8;
-  if (ensure_dyn_smem((const void*)topk_bitonic_kernel, smem, once, "topk_bitonic_kernel")) return 1;
-  topk_bitonic_kernel<<<B, 1024, smem, stream>>>(cand_count, cand, n_total, n, order);
-  if (check_launch("topk_bitonic_kernel")) return 1;
-  if (n_total > kSortMax) {  // only then can an image have more candidates than the smem sort holds
-    topk_rank_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(cand_count, cand, n_total, n, order);
+  // ordering: rank-by-counting across all SMs (default); the one-CTA-per-image shared-memory bitonic network stays as the
+  // A/B path (AITB_TOPK_BITONIC=1: it then takes every image with <= kSortMax candidates, the rank kernel the rest)
+  static const bool use_bitonic = getenv("AITB_TOPK_BITONIC") != nullptr;
+  const int split_nc = use_bitonic ? kSortMax : 0;   // images with nc <= split_nc -> bitonic, others -> rank
+  if (use_bitonic) {
+    static SmemAttrOnce once;
+    const int smem = kSortMax * 8;
+    if (ensure_dyn_smem((const void*)topk_bitonic_kernel, smem, once, "topk_bitonic_kernel")) return 1;
+    topk_bitonic_kernel<<<B, 1024, smem, stream>>>(cand_count, cand, n_total, n, split_nc, order);
+    if (check_launch("topk_bitonic_kernel")) return 1;
+  }
+  if (!use_bitonic || n_total > kSortMax) {
+    topk_rank_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(cand_count, cand, n_total, n, split_nc, order);
     if (check_launch("topk_rank_kernel")) return 1;
   }
   return 0;

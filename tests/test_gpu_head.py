@@ -231,7 +231,7 @@ def test_packed_weight_cache_follows_in_place_updates():
     with torch.no_grad():
         t.dec_trans[0].bias.add_(1.0)
     o1 = t(x_props=xp, x_query=xq)
-    torch.testing.assert_close(o1, o0 + 1.0, rtol=0, atol=2e-5)
+    torch.testing.assert_close(o1, o0 + 1.0, rtol=2e-5, atol=2e-5)   # two-plane output: 2^-17 relative
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")

@@ -244,8 +244,15 @@ def test_target_layer_edge_cases():
     assert int((ref[0][1] == 1).sum()) == 0 and int((ref[0][1] == 0).sum()) == 256
     rois = T.synth_rois(22, 2, 100, gt)
     pt = ProposalTargetLayer(2)
+    # effective training cfg (cfgs/res50.yml: BG_THRESH_LO 0.0): the rois of a gt-less image overlap nothing (0 >= 0.0), so they
+    # are all background candidates -- same samples as the oracle; with config.py's never-used 0.1 the reference raises
+    np.random.seed(8)
+    ref = T.proposal_target(rois, gt)
+    np.random.seed(8)
+    _check_proposal(pt(rois.to(DEV), gt.to(DEV), nb.to(DEV)), ref)
+    assert int((ref[1][1] > 0).sum()) == 0
     with pytest.raises(ValueError):
-        pt(rois.to(DEV), gt.to(DEV), nb.to(DEV))
+        ProposalTargetLayer(2, cfg=dict(BG_THRESH_LO=0.1))(rois.to(DEV), gt.to(DEV), nb.to(DEV))
     # foreground only (every roi sits on a gt box) / background only (rois overlap the gt a little, never >= 0.5)
     gt1 = torch.zeros(2, 1, 5)
     gt1[:, 0] = torch.tensor([100.0, 80.0, 260.0, 220.0, 1.0])
@@ -325,7 +332,7 @@ def test_device_rng_sampling():
         idx = match.float().argmax(-1)
         mo = ref_stage["max_overlaps"][b][idx]
         n_fg = min(32, int((ref_stage["max_overlaps"][b] >= 0.5).sum()))
-        assert bool((mo[:n_fg] >= 0.5).all()) and bool(((mo[n_fg:] < 0.5) & (mo[n_fg:] >= 0.1)).all())
+        assert bool((mo[:n_fg] >= 0.5).all()) and bool(((mo[n_fg:] < 0.5) & (mo[n_fg:] >= 0.0)).all())
         assert len(set(idx[:n_fg].tolist())) == n_fg, "foreground rois must be drawn without replacement"
         assert bool((l[b, :n_fg] == 1).all())
     # an image without any candidate: flagged on the device instead of raised (no synchronisation in this mode)
