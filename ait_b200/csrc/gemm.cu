@@ -605,6 +605,81 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast epilogue of the 2-CTA kernel for 2-byte (bf16) outputs whose rows are the GEMM rows and whose epilogue is at most
+// bias + ReLU (QKV / K,V projections, FFN w_1, dec_trans, the layer-4 1x1 / 3x3 convolutions): the single-pass bf16 GEMMs
+// were measured EPILOGUE-bound (tensor pipe 58-64 % active; 196 SASS instructions per 32-column chunk and warp, 408 more
+// per tile: profiles/r01f_bf16_gemm2_epilogue.txt).  Here a chunk is: tcgen05.ld -> 32 FADD with the bias slice (broadcast
+// ld.shared.v4) -> 16 cvt.rn[.relu].bf16x2.f32 (the ReLU rides in the conversion) -> 4 st.shared.v4 into a 32 x 64 B tile in
+// the TMA 64-byte-swizzle pattern -> ONE cp.async.bulk.tensor store issued by lane 0.  No per-row global pointers, no
+// staged read-back, no bounds masks (TMA clips rows >= M), every chunk of a tile has its own staging tile so nothing waits
+// for a store inside a tile.
+//   stg_s   : this warp's 4 x 2 KB staging tiles (1024-byte aligned)
+//   bias_s  : this warpgroup's bias slice [2][128] floats (double-buffered by accumulator stage)
+//   n0      : first output column of this warp's 128 columns;   row0 : first output row of this warp's 32 rows
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const CUtensorMap* tmO, uint32_t stg_s, uint32_t bias_s,
+                                                   int bar_id, uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t aph,
+                                                   uint32_t t_row, int lane, int wg_tid, int row0, int n0, uint32_t as) {
+  const bool has_bias = (p.flags & AITB_EPI_BIAS) != 0;
+  const bool relu = (p.flags & AITB_EPI_RELU) != 0;
+  const uint32_t bias_buf = bias_s + as * 512u;
+  if (lane == 0) bulk_wait_read_all();            // the previous tile's stores no longer read the staging tiles
+  if (has_bias) {
+    const float b = __ldg(p.bias + n0 + wg_tid);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_buf + (uint32_t)wg_tid * 4u), "f"(b) : "memory");
+    named_bar_sync(bar_id, 128);                  // the slice is complete (and lane 0's wait above is ordered before our writes)
+  } else {
+    __syncwarp();
+  }
+  mbar_wait(acc_full_bar, aph);
+  tc_fence_after();
+  uint32_t raw[32];
+  tmem_ld32(t_row, raw);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (c + 1 < 4) {
+      tmem_ld32(t_row + (uint32_t)(c + 1) * 32u, raw);
+    } else {                                      // the accumulator stage is drained: hand it back before the stores
+      tc_fence_before();
+      mbar_arrive_remote(acc_empty_bar, 0);
+    }
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 b = lds128(bias_buf + (uint32_t)c * 128u + (uint32_t)j * 16u);
+        v[4 * j] += __uint_as_float(b.x); v[4 * j + 1] += __uint_as_float(b.y);
+        v[4 * j + 2] += __uint_as_float(b.z); v[4 * j + 3] += __uint_as_float(b.w);
+      }
+    }
+    const uint32_t tile = stg_s + (uint32_t)c * 2048u;
+    const uint32_t rowb = tile + (uint32_t)lane * 64u;
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 x;
+      if (relu) {
+        x.x = pack_bf16x2_relu(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
+        x.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
+      } else {
+        x.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        x.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      }
+      sts128(rowb + (((uint32_t)j ^ sw) << 4), x);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmO, tile, n0 + c * 32, row0);
+      bulk_commit_group();
+    }
+  }
+}
+
 // CL = true: "cluster LayerNorm" variant.  A 2-CTA cluster shares one 128-row m-tile; CTA rank r owns the
 // output columns [256 r, 256 r + 256) of the N = 512 row (BLOCK_N = 256 machinery: 4-stage ring, double-
 // buffered accumulator).  The LayerNorm row statistics are combined across the two CTAs through
@@ -937,19 +1012,31 @@ static constexpr int k2SmemBytes = 6 * (kABytes + k2HalfB) + 1024 + 256 + 8 * 40
 // SPLIT: a stage holds [A_hi][A_lo][W_hi half][W_lo half] (64 KB, 3 stages) and every K slice issues three MMAs.
 // SIMPLE: see epilogue_tile -- a separate kernel instantiation per addressing mode, chosen on the host (two epilogue
 // copies inside one kernel were measured slower than either alone).
-template <typename T, bool SPLIT, bool SIMPLE = false>
+// FAST (bf16, not split): the bias + ReLU fast epilogue with TMA stores (epilogue_fast_tile).  Shared memory: 5 stages (160 KB)
+// | 8 warps x 4 staging tiles (64 KB) | barriers | 2 warpgroups x 2 x 512 B bias slices.
+static constexpr int k2FastStages = 5;
+// (no alignment slack: the dynamic shared memory of this kernel is declared __align__(1024); checked at run time)
+static constexpr int k2FastSmemBytes = k2FastStages * (kABytes + k2HalfB) + 8 * 8192 + 128 + 2048;
+static_assert(k2FastSmemBytes <= 232448, "fast 2-CTA kernel exceeds the 227 KB shared-memory limit");
+
+template <typename T, bool SPLIT, bool SIMPLE = false, bool FAST = false>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const GemmKParams p) {
+                     const __grid_constant__ CUtensorMap tmO, const GemmKParams p) {
+  static_assert(!FAST || (!SPLIT && !SIMPLE && sizeof(T) == 2), "FAST epilogue: plain bf16 only");
   constexpr int BLOCK_N = 256;
   constexpr int kPlanes = SPLIT ? 2 : 1;
-  constexpr int k2Stages = SPLIT ? 3 : 6;
+  constexpr int k2Stages = FAST ? k2FastStages : (SPLIT ? 3 : 6);
   constexpr int k2StageBytes = kPlanes * (kABytes + k2HalfB);  // A (own 128 rows) + half of B, per plane
   constexpr int kAcc = 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  extern __shared__ __align__(1024) uint8_t smem2_raw[];
+  uint8_t* smem = FAST ? smem2_raw
+                       : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem2_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  if constexpr (FAST) {
+    if ((smem_u32(smem2_raw) & 1023u) != 0u) __trap();   // the layout below has no slack to re-align
+  }
+  // FAST: the staging tiles follow the stages (1024-byte aligned: they are TMA-store sources in the 64-byte swizzle pattern)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes + (FAST ? 8 * 8192 : 0));
   uint64_t* full_bar = bars;                 // [k2Stages]  (used in the leader)
   uint64_t* empty_bar = bars + k2Stages;     // [k2Stages]  (local in each CTA)
   uint64_t* acc_full = bars + 2 * k2Stages;  // [kAcc]      (local in each CTA)
@@ -963,6 +1050,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (FAST) tma_prefetch_desc(&tmO);
     for (int s = 0; s < k2Stages; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&empty_bar[s], 1);
@@ -1060,7 +1148,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int q = warp & 3;            // TMEM lane quadrant
     const int half = (warp - 4) >> 2;  // which 128 columns of the 256-wide tile this warp drains
-    uint8_t* stg = smem + k2Stages * k2StageBytes + 256 + (warp - 4) * 4096;
+    uint8_t* stg = smem + k2Stages * k2StageBytes + (FAST ? (warp - 4) * 8192 : 256 + (warp - 4) * 4096);
     uint32_t lt = 0;
     for (int tile = t_first; tile < n_tiles_total; tile += t_step, ++lt) {
       const int mp = tile / p.n_tiles;
@@ -1068,11 +1156,21 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t as = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<T, BLOCK_N, false, SPLIT, 128, 2, SIMPLE>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
-                                                              mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
-                                                              half * 128 + 128);
-      tc_fence_before();
-      mbar_arrive_remote(&acc_empty[as], 0);
+      if constexpr (FAST) {
+        const uint32_t bias_s = smem_u32(smem + k2Stages * k2StageBytes + 8 * 8192 + 128) + (uint32_t)half * 1024u;
+        epilogue_fast_tile(p, &tmO, smem_u32(stg), bias_s, 1 + half, &acc_full[as], &acc_empty[as], aph,
+                           t_row + (uint32_t)(half * 128), lane, q * 32 + lane, (mp * 2 + (int)rank) * kBlockM + q * 32,
+                           nt * BLOCK_N + half * 128, as);
+      } else {
+        epilogue_tile<T, BLOCK_N, false, SPLIT, 128, 2, SIMPLE>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
+                                                                mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
+                                                                half * 128 + 128);
+        tc_fence_before();
+        mbar_arrive_remote(&acc_empty[as], 0);
+      }
+    }
+    if constexpr (FAST) {
+      if (lane == 0) bulk_wait_all();   // this warp's last stores have completed before the CTA may exit
     }
   }
 
@@ -1188,10 +1286,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
 }
 
-template <typename T, bool SPLIT, bool SIMPLE>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t stream) {
+template <typename T, bool SPLIT, bool SIMPLE, bool FAST = false>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& kp,
+                        cudaStream_t stream) {
   static SmemAttrOnce once;
-  auto kern = gemm2_tcgen05_kernel<T, SPLIT, SIMPLE>;
+  auto kern = gemm2_tcgen05_kernel<T, SPLIT, SIMPLE, FAST>;
+  constexpr int k2SmemBytes = FAST ? k2FastSmemBytes : aitb::k2SmemBytes;
   if (ensure_dyn_smem((const void*)kern, k2SmemBytes, once, "gemm2_tcgen05_kernel")) return 1;
   const int tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -1208,7 +1308,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, kp);
   if (e != cudaSuccess) {
     set_error("gemm2_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -1400,10 +1500,23 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     // outputs only.  Measured on the FFN w_1 shape (ncu, same box): fp32 storage 920.8 k -> 855.5 k cycles (eight live
     // 64-bit row pointers become one), bf16 435.3 k -> 468.7 k (four pointers: the array form is faster there).
     const bool simple = kp.a_m_dim != 2 && kp.rows_in == kp.rows_out && kp.simple_rows_ok && d->dtype == AITB_F32;
-    if (simple) return launch_gemm2<float, false, true>(tmA, tmB, kp, stream);
-    return d->dtype == AITB_F32 ? launch_gemm2<float, false, false>(tmA, tmB, kp, stream)
-           : split              ? launch_gemm2<__nv_bfloat16, true, false>(tmA, tmB, kp, stream)
-                                : launch_gemm2<__nv_bfloat16, false, false>(tmA, tmB, kp, stream);
+    if (simple) return launch_gemm2<float, false, true>(tmA, tmB, tmA, kp, stream);
+    // bf16 outputs, rows = GEMM rows, epilogue at most bias + ReLU: the TMA-store fast epilogue (A/B: AITB_NO_FAST_EPI=1)
+    static const bool fast_on = getenv("AITB_NO_FAST_EPI") == nullptr;
+    const bool fast = fast_on && d->dtype == AITB_BF16 && kp.a_m_dim != 2 && kp.rows_in == kp.rows_out &&
+                      (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU)) == 0 && kp.acc_scale == 1.f &&
+                      (((uintptr_t)d->out) & 15) == 0 && ((size_t)d->ldo * 2) % 16 == 0;
+    if (fast) {
+      CUtensorMap tmO;
+      const uint64_t odims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+      const uint64_t ostr[1] = {(uint64_t)d->ldo * 2};
+      const uint32_t obox[2] = {32u, 32u};
+      if (encode_map(&tmO, AITB_BF16, d->out, 2, odims, ostr, obox, "O", true)) return 1;
+      return launch_gemm2<__nv_bfloat16, false, false, true>(tmA, tmB, tmO, kp, stream);
+    }
+    return d->dtype == AITB_F32 ? launch_gemm2<float, false, false>(tmA, tmB, tmA, kp, stream)
+           : split              ? launch_gemm2<__nv_bfloat16, true, false>(tmA, tmB, tmA, kp, stream)
+                                : launch_gemm2<__nv_bfloat16, false, false>(tmA, tmB, tmA, kp, stream);
   }
   switch (d->block_n) {
     case 64: return AITB_DISPATCH(64);

@@ -455,7 +455,7 @@ int nms_run(const float* boxes, const int64_t* order, int B, int n_total, int n,
   AITB_REQUIRE(boxes && keep_out && n_keep && ws, "aitb_nms: null pointer");
   AITB_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)ws & 255) == 0, "aitb_nms: misaligned boxes/workspace");
   static const bool no_lazy = getenv("AITB_NMS_NO_LAZY") != nullptr;   // debug: force the bitmask path
-  static const bool resolve_rounds = getenv("AITB_NMS_ROUNDS") != nullptr;   // A/B: round-based block resolve
+  static const bool resolve_rounds = getenv("AITB_NMS_SERIAL") == nullptr;   // default: round-based block resolve (measured 48.7 vs 71.1 us for 8 images; mask-mode scan 215 vs 315 us); A/B: AITB_NMS_SERIAL=1
   if (mode == 0 && max_out <= kLazyMaxOut && !no_lazy) {
     const size_t smem = (size_t)max_out * (16 + 4 + 4);
     nms_lazy_kernel<<<B, kLazyThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), order, n_total, n, thr,

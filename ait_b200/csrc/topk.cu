@@ -159,7 +159,7 @@ int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, voi
   if (check_launch("topk_compact_kernel")) return 1;
   // ordering: rank-by-counting across all SMs (default); the one-CTA-per-image shared-memory bitonic network stays as the
   // A/B path (AITB_TOPK_BITONIC=1: it then takes every image with <= kSortMax candidates, the rank kernel the rest)
-  static const bool use_bitonic = getenv("AITB_TOPK_BITONIC") != nullptr;
+  static const bool use_bitonic = getenv("AITB_TOPK_RANK") == nullptr;   // default: bitonic (measured 100 us vs 177 us for rank counting, 8 images x 6000 of 21546)
   const int split_nc = use_bitonic ? kSortMax : 0;   // images with nc <= split_nc -> bitonic, others -> rank
   if (use_bitonic) {
     static SmemAttrOnce once;
