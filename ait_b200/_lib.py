@@ -15,6 +15,8 @@ AITB_F32, AITB_BF16, AITB_F32S = 0, 1, 2
 #   "bf16"  AITB_BF16  bf16 storage and math
 MODES = {"fp32": AITB_F32S, "tf32": AITB_F32, "bf16": AITB_BF16}
 
+PLAN_ENC_ONEPASS = 1
+
 EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK, EPI_RES_ROW_M = (
     1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
 
@@ -37,6 +39,7 @@ class GemmDesc(C.Structure):
         ("pos", C.c_void_p), ("pos_rows", C.c_int),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("round_tf32", C.c_int),
         ("dual", C.c_int), ("bias2", C.c_void_p), ("a_lo_off", C.c_int), ("ln_rstd", C.c_void_p), ("map_w", C.c_int), ("map_h", C.c_int), ("out_scale", C.c_float),
+        ("passes", C.c_int), ("in_f16", C.c_int), ("out_f16", C.c_int), ("res_f16", C.c_int),
     ]
 
 
@@ -67,7 +70,7 @@ class SKBlock(C.Structure):
 
 class HeadWeights(C.Structure):
     _fields_ = [
-        ("dtype", C.c_int), ("round_tf32", C.c_int),
+        ("dtype", C.c_int), ("round_tf32", C.c_int), ("plan", C.c_int),
         ("enc_emb", Linear), ("dec_emb", Linear), ("dec_trans", Linear),
         ("enc_pos", C.c_void_p), ("dec_pos", C.c_void_p),
         ("enc_ln", LNorm), ("dec_ln", LNorm),

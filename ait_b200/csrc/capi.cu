@@ -20,9 +20,10 @@ size_t topk_workspace_bytes(int B, int n_total, int n);
 int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, void* ws, size_t ws_bytes,
              cudaStream_t stream);
 int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream,
-                  int round_tf = 0);
+                  int round_tf = 0, int dst_f16 = 0);
 int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
-                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf = 0);
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf = 0,
+                      int out_f16 = 0);
 int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
                       int pw, int sampling_ratio, float* gfeat, cudaStream_t stream);
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
@@ -55,7 +56,8 @@ int rpn_head_decode_run(const void* heads, int dtype, int ld, const float* base_
 int group_norm_residual_run(const float* x, const float* identity, const float* gamma, const float* beta, int B, int N,
                             int groups, float eps, double* sums, float* out, cudaStream_t st);
 int fc_ln_run(int dtype, const void* a, const void* w, const void* res, const float* gamma, const float* beta, float eps,
-              void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, cudaStream_t st);
+              void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, cudaStream_t st,
+              int res_f16 = 0, int out_f16 = 0);
 int det_assemble_run(const float* pred, const float* cls, const int64_t* order, const int64_t* keep_pos,
                      const int32_t* n_keep, const int32_t* n_valid, int B, int N, int max_per_image, float* dets,
                      int32_t* n_det, cudaStream_t st);
@@ -121,7 +123,7 @@ int check_launch(const char* what) {
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256)
 ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __restrict__ pos,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int round_tf) {
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int round_tf, int out_f16) {
   const int n_pad = 64 - n_valid;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -150,25 +152,36 @@ ln_pad_rows_kernel(T* __restrict__ x, int n_pairs, int n_valid, const float* __r
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(o));
       o = __uint_as_float(r);
     }
-    Act<T>::st(xr + c, o);
-    if constexpr (SPLIT) Act<T>::st(xr + 512 + c, o - Act<T>::ld(xr + c));   // lo plane = x - bf16(x)
+    if constexpr (SPLIT) {
+      if (out_f16) {   // fp16 planes (precision plan): 16-bit containers written through __half
+        const float os = sat_f16(o);
+        const __half hi = __float2half_rn(os);
+        reinterpret_cast<__half*>(xr)[c] = hi;
+        reinterpret_cast<__half*>(xr)[512 + c] = __float2half_rn(os - __half2float(hi));
+      } else {
+        Act<T>::st(xr + c, o);
+        Act<T>::st(xr + 512 + c, o - Act<T>::ld(xr + c));   // lo plane = x - bf16(x)
+      }
+    } else {
+      Act<T>::st(xr + c, o);
+    }
   }
 }
 
 static int ln_pad_rows(void* x, int dtype, int n_pairs, int n_valid, const float* pos, const aitb_lnorm& ln,
-                       int round_tf, cudaStream_t st) {
+                       int round_tf, cudaStream_t st, int out_f16 = 0) {
   const int rows = n_pairs * (64 - n_valid);
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
   if (dtype == AITB_F32)
     ln_pad_rows_kernel<float, false><<<grid, 256, 0, st>>>((float*)x, n_pairs, n_valid, pos, ln.gamma, ln.beta, 1e-6f,
-                                                           round_tf);
+                                                           round_tf, 0);
   else if (dtype == AITB_F32S)
     ln_pad_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma,
-                                                                  ln.beta, 1e-6f, 0);
+                                                                  ln.beta, 1e-6f, 0, out_f16);
   else
     ln_pad_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n_pairs, n_valid, pos, ln.gamma,
-                                                                   ln.beta, 1e-6f, round_tf);
+                                                                   ln.beta, 1e-6f, round_tf, 0);
   return check_launch("ln_pad_rows_kernel");
 }
 
@@ -363,7 +376,7 @@ static int side_stream(SideStream** out) {
 static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* qbuf, int ldq, int q_rep,
                      const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode, int n_keys, void* ao,
                      const void* res, int res_rep, void* out, cudaStream_t st, float* rstd = nullptr, int out_rows = 64,
-                     int kv_rows = 64) {
+                     int kv_rows = 64, int res_f16 = 0, int out_f16 = 0) {
   const int dt = w->dtype;
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32, kv_rows));
@@ -373,7 +386,7 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   static const bool force_gemm = getenv("AITB_FC_GEMM") != nullptr;
   if (dt != AITB_F32 && rstd == nullptr && !force_gemm)
     return fc_ln_run(dt, ao, m.w_fc, res, m.ln.gamma, m.ln.beta, 1e-6f, out, G * 64, out_rows != 64 ? 64 : G * 64, out_rows != 64 ? out_rows : G * 64,
-                     out_rows != 64 ? 1 : 0, 64, res_rep, st);
+                     out_rows != 64 ? 1 : 0, 64, res_rep, st, res_f16, out_f16);
   aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 512, out, 512, w->round_tf32);
   view_plain(d, ao, 64);
   d.flags = AITB_EPI_RES | AITB_EPI_LN;
@@ -384,6 +397,8 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   d.gamma = m.ln.gamma;
   d.beta = m.ln.beta;
   d.ln_rstd = rstd;
+  d.res_f16 = res_f16;
+  d.out_f16 = out_f16;
   if (out_rows != 64) {   // compaction: the residual stays indexed by the 64-row GEMM row
     d.rows_in = 64;
     d.rows_out = out_rows;
@@ -392,15 +407,18 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
   return gemm_run(&d, st);
 }
 
+// onepass (precision plan, AITB_F32S): x, the hidden tensor and the output are fp16 planes, both GEMMs run one pass
 static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* x, int M, void* hidden, void* out,
-                     cudaStream_t st, float* rstd = nullptr) {
+                     cudaStream_t st, float* rstd = nullptr, bool onepass = false) {
   const int dt = w->dtype;
   aitb_gemm_desc d1 = gemm_base(dt, M, 2048, 512, f.w1.w, 256, hidden, 2048, w->round_tf32);
   view_plain(d1, x, 512);
   d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
   d1.bias = f.w1.bias;
+  if (onepass) { d1.passes = 1; d1.in_f16 = 1; d1.out_f16 = 1; }
   RUN(gemm_run(&d1, st));
   aitb_gemm_desc d2 = gemm_base(dt, M, 512, 2048, f.w2.w, 512, out, 512, w->round_tf32);
+  if (onepass) { d2.passes = 1; d2.in_f16 = 1; d2.out_f16 = 1; d2.res_f16 = 1; }
   view_plain(d2, hidden, 2048);
   d2.flags = AITB_EPI_BIAS | AITB_EPI_RES | AITB_EPI_LN;
   d2.bias = f.w2.bias;
@@ -449,6 +467,9 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
   const int dt = w->dtype, eb = esize(dt), cb = colsize(dt), rt = w->round_tf32;
   const int bp = B * P, R = bp * 64;
   const int er = compact ? 49 : 64, RE = bp * er;   // encoder rows per pair / in total after the self-attention block
+  // precision plan: the encoder-side tensors pooled / X1 / X2 / Hh / ENC are fp16 planes and the GEMMs that read
+  // them run one tensor-core pass on the hi planes (11-bit operands); everything downstream keeps three bf16 passes
+  const bool plan = dt == AITB_F32S && (w->plan & AITB_PLAN_ENC_ONEPASS) != 0;
   // ---- encoder input: enc_emb (1x1 conv 1024->512 + bias) on the 49 real rows, + pos, LayerNorm
   {
     aitb_gemm_desc d = gemm_base(dt, bp * 49, 512, 1024, w->enc_emb.w, 512, hb.X1, 512, rt);
@@ -462,19 +483,21 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     d.gamma = w->enc_ln.gamma;
     d.beta = w->enc_ln.beta;
     d.ln_rstd = hb.r_X1;
+    if (plan) { d.passes = 1; d.in_f16 = 1; d.out_f16 = 1; }
     RUN(gemm_run(&d, st));
-    RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st));
+    RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st, plan ? 1 : 0));
   }
   // ---- encoder self-attention
   {
     aitb_gemm_desc d = gemm_base(dt, R, 1536, 512, w->enc_slf.w_qkv, 256, hb.QKV, 1536, rt);
     view_plain(d, hb.X1, 512);
+    if (plan) { d.passes = 1; d.in_f16 = 1; }   // Q / K / V themselves stay bf16 planes (the attention core's format)
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
     RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
-                  hb.X2, st, hb.r_X2, er));
+                  hb.X2, st, hb.r_X2, er, 64, plan ? 1 : 0, plan ? 1 : 0));
   }
-  RUN(ffn_block(w, w->enc_ffn, hb.X2, RE, hb.Hh, hb.ENC, st, hb.r_ENC));
+  RUN(ffn_block(w, w->enc_ffn, hb.X2, RE, hb.Hh, hb.ENC, st, hb.r_ENC, plan));
   if (enc_tap) {   // [bp, 64, 512] tap: the rows that exist (pad rows of the tap are left untouched when compact)
     cudaError_t e = cudaMemcpy2DAsync(enc_tap, (size_t)64 * 512 * eb, hb.ENC, (size_t)er * 512 * eb, (size_t)er * 512 * eb, bp,
                                       cudaMemcpyDeviceToDevice, st);
@@ -489,6 +512,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     const uint8_t* wkv = (const uint8_t*)w->dec_enc.w_qkv + (size_t)512 * 512 * eb;
     aitb_gemm_desc d = gemm_base(dt, RE, 1024, 512, wkv, 256, hb.KVc, 1024, rt);
     view_plain(d, hb.ENC, 512);
+    if (plan) { d.passes = 1; d.in_f16 = 1; }   // K / V stay bf16 planes
     RUN(gemm_run(&d, st));
     if (compact) {   // the last pair's 64-row K / V tile reads 15 rows past the compact buffer: keep them finite
       cudaError_t e = cudaMemsetAsync((uint8_t*)hb.KVc + (size_t)RE * 1024 * eb, 0, (size_t)(64 - er) * 1024 * eb, st);
@@ -1234,7 +1258,8 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
   for (int k0 = 0; k0 < bp; k0 += 32768) {
     const int kn = bp - k0 < 32768 ? bp - k0 : 32768;
     RUN(roi_align_fwd_run(hb.featT, rois + (size_t)k0 * 5, B, 1024, H, W, kn, 1.f / 16.f, 7, 7, 0, dt, 1,
-                          (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st, taps && taps->pooled ? 0 : w->round_tf32));
+                          (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st, taps && taps->pooled ? 0 : w->round_tf32,
+                          (dt == AITB_F32S && (w->plan & AITB_PLAN_ENC_ONEPASS)) ? 1 : 0));
   }
   RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   if (taps && taps->pooled) {
@@ -1300,7 +1325,7 @@ int aitb_ait_forward(const aitb_head_weights* w, const float* x_props, const flo
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
     RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (uint8_t*)hb.pooled + (size_t)g0 * 49 * 1024 * esize(dt),
-                      dt, gn, 1024, 49, 1, st, w->round_tf32));
+                      dt, gn, 1024, 49, 1, st, w->round_tf32, (dt == AITB_F32S && (w->plan & AITB_PLAN_ENC_ONEPASS)) ? 1 : 0));
   }
   RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   RUN(ait_query_side(w, hb, B, st));

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace aitb {
@@ -414,6 +415,43 @@ template <> struct Act<__nv_bfloat16> {
     *p = __float2bfloat16_rn(v);
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// two-plane (split) storage, element format of the planes: bf16 (default) or IEEE fp16 (precision plan: 11-bit
+// significand per plane, saturating at +-65504).  x ~ hi + lo with hi = rn(x), lo = rn(x - hi).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+// (a, b) -> packed hi pair; la / lb receive the remainders a - hi(a), b - hi(b)
+__device__ __forceinline__ uint32_t split_hi2(float a, float b, bool f16, float& la, float& lb) {
+  uint32_t r;
+  if (f16) {
+    a = sat_f16(a);
+    b = sat_f16(b);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    la = a - f.x;
+    lb = b - f.y;
+    r = *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    r = *reinterpret_cast<const uint32_t*>(&h);
+    la = a - __uint_as_float(r << 16);
+    lb = b - __uint_as_float(r & 0xffff0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_plane2(float a, float b, bool f16) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_plane2(uint32_t x, bool f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&x));
+  return make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+}
 
 // load / store 8 consecutive activation elements (16-byte aligned for bf16, 32 for fp32)
 __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {

@@ -42,6 +42,15 @@ __device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
     f[2 * e + 1] = v.y;
   }
 }
+__device__ __forceinline__ void unpack8f(const uint4& x, float (&f)[8], bool f16) {
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 v = unpack_plane2(w[e], f16);
+    f[2 * e] = v.x;
+    f[2 * e + 1] = v.y;
+  }
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 x;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
@@ -59,6 +68,7 @@ struct FcLnParams {
   const float* beta;
   float eps;
   int M, rows_in, rows_out, res_row_m, res_div, res_rep;
+  int res_f16, out_f16;   // split mode: plane element format of the residual read / the output written (0 = bf16, 1 = fp16)
 };
 
 // dynamic smem: Wf [64 n-tiles][2 k-pairs][PL][32 lanes] uint4, then gamma[512], beta[512], st1[4][4][16], st2[4][4][16],
@@ -197,10 +207,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_ln_kernel(const FcLnParams p
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float f[8];
-        unpack8(r[h][0], f);
+        unpack8f(r[h][0], f, SPLIT && p.res_f16 != 0);
         if constexpr (SPLIT) {
           float f2[8];
-          unpack8(r[h][1], f2);
+          unpack8f(r[h][1], f2, p.res_f16 != 0);
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] += f2[e];
         }
@@ -286,14 +296,20 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_ln_kernel(const FcLnParams p
             y[2 * j + e] = (acc[sb][j][2 * h + e] - mean[h]) * rstd[h] * gm[2 * j + e] + bt[2 * j + e];
         if (!ok[h]) continue;
         __nv_bfloat16* o = p.out + orow[h] * (PL * kFcN) + col;
-        const uint4 hi = pack8(y);
-        *reinterpret_cast<uint4*>(o) = hi;
         if constexpr (SPLIT) {
-          float fh[8], lo[8];
-          unpack8(hi, fh);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) lo[e] = y[e] - fh[e];
-          *reinterpret_cast<uint4*>(o + kFcN) = pack8(lo);
+          const bool of16 = p.out_f16 != 0;
+          float lo[8];
+          uint4 hi, lw;
+          hi.x = split_hi2(y[0], y[1], of16, lo[0], lo[1]);
+          hi.y = split_hi2(y[2], y[3], of16, lo[2], lo[3]);
+          hi.z = split_hi2(y[4], y[5], of16, lo[4], lo[5]);
+          hi.w = split_hi2(y[6], y[7], of16, lo[6], lo[7]);
+          lw.x = pack_plane2(lo[0], lo[1], of16); lw.y = pack_plane2(lo[2], lo[3], of16);
+          lw.z = pack_plane2(lo[4], lo[5], of16); lw.w = pack_plane2(lo[6], lo[7], of16);
+          *reinterpret_cast<uint4*>(o) = hi;
+          *reinterpret_cast<uint4*>(o + kFcN) = lw;
+        } else {
+          *reinterpret_cast<uint4*>(o) = pack8(y);
         }
       }
     }
@@ -304,7 +320,8 @@ static SmemAttrOnce g_fc_once[2];
 
 // dtype AITB_BF16 or AITB_F32S; a [M, 64] (planes), w [512, 64] (planes), res / out rows of 512 (planes)
 int fc_ln_run(int dtype, const void* a, const void* w, const void* res, const float* gamma, const float* beta, float eps,
-              void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, cudaStream_t st) {
+              void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep, cudaStream_t st,
+              int res_f16, int out_f16) {
   AITB_REQUIRE(dtype == AITB_BF16 || dtype == AITB_F32S, "fc_ln: bf16 / split storage only");
   AITB_REQUIRE(a && w && res && gamma && beta && out && M > 0 && rows_in > 0 && rows_out > 0 && rows_out <= rows_in &&
                    res_div > 0 && res_rep > 0, "fc_ln: bad arguments");
@@ -326,6 +343,8 @@ int fc_ln_run(int dtype, const void* a, const void* w, const void* res, const fl
   p.res_row_m = res_row_m;
   p.res_div = res_div;
   p.res_rep = res_rep;
+  p.res_f16 = split ? res_f16 : 0;
+  p.out_f16 = split ? out_f16 : 0;
   const int n_blk = (M + 63) / 64;
   const int grid = n_blk < current_sm_count() ? n_blk : current_sm_count();
   if (split) {
@@ -344,5 +363,5 @@ extern "C" int aitb_fc_ln(int dtype, const void* a, const void* w_fc, const void
                           float eps, void* out, int M, int rows_in, int rows_out, int res_row_m, int res_div, int res_rep,
                           aitb_stream_t stream) {
   return aitb::fc_ln_run(dtype, a, w_fc, res, gamma, beta, eps, out, M, rows_in, rows_out, res_row_m, res_div, res_rep,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, 0, 0);
 }

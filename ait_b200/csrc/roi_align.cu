@@ -216,7 +216,7 @@ template <typename T, bool NCHW_OUT, bool OUT_SPLIT = false>
 __global__ void __launch_bounds__(256, AITB_ROI_MINB)
 roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois, int C, int H, int W, float scale,
                      int ph, int pw, int sampling_ratio, typename std::conditional<OUT_SPLIT, __nv_bfloat16, T>::type* __restrict__ out,
-                     int round_tf) {
+                     int round_tf, int out_f16) {
   __shared__ Foot xf[kMaxPooled];
   __shared__ Foot yf[kMaxPooled];
   extern __shared__ float stage[];  // NCHW_OUT: [128][ph*pw + 1]
@@ -306,16 +306,15 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const float* __restrict__ rois,
     } else if constexpr (OUT_SPLIT) {
       // hi = bf16(x), lo = bf16(x - hi) with the packed conversion (F2FP.PACK_AB, FMA-class pipe) and the hi values
       // recovered by shifts: the scalar F2F.BF16 conversions of the naive form were 25 % of the kernel's instructions
+      // (out_f16: fp16 planes, the A operand of a one-pass enc_emb GEMM -- aitb_head_weights.plan)
       __nv_bfloat16* o = out + ((size_t)k * nbins + bin) * 2 * C + c0 + lane * 4;
-      uint2 hi;
-      *reinterpret_cast<__nv_bfloat162*>(&hi.x) = __floats2bfloat162_rn(acc.x, acc.y);
-      *reinterpret_cast<__nv_bfloat162*>(&hi.y) = __floats2bfloat162_rn(acc.z, acc.w);
+      float lx, ly, lz, lw;
+      uint2 hi, lo;
+      hi.x = split_hi2(acc.x, acc.y, out_f16 != 0, lx, ly);
+      hi.y = split_hi2(acc.z, acc.w, out_f16 != 0, lz, lw);
       *reinterpret_cast<uint2*>(o) = hi;
-      const float lx = acc.x - __uint_as_float(hi.x << 16), ly = acc.y - __uint_as_float(hi.x & 0xffff0000u);
-      const float lz = acc.z - __uint_as_float(hi.y << 16), lw = acc.w - __uint_as_float(hi.y & 0xffff0000u);
-      uint2 lo;
-      *reinterpret_cast<__nv_bfloat162*>(&lo.x) = __floats2bfloat162_rn(lx, ly);
-      *reinterpret_cast<__nv_bfloat162*>(&lo.y) = __floats2bfloat162_rn(lz, lw);
+      lo.x = pack_plane2(lx, ly, out_f16 != 0);
+      lo.y = pack_plane2(lz, lw, out_f16 != 0);
       *reinterpret_cast<uint2*>(o + C) = lo;
     } else {
       Vec4<T>::st(out + ((size_t)k * nbins + bin) * C + c0 + lane * 4, acc);
@@ -543,7 +542,7 @@ roi_align_bwd_foot_kernel(const float* __restrict__ grad, const float* __restric
 // SS / SD: the source / destination is a split (two bf16 planes per row) matrix (AITB_F32S).
 template <typename TS, typename TD, bool SS = false, bool SD = false>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc, int round_tf) {
+transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc, int round_tf, int dst_f16 = 0) {
   // src [G, R, Cc] -> dst [G, Cc, R]
   __shared__ float tile[32][33];
   const int g = blockIdx.z;
@@ -567,14 +566,25 @@ transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int Cc
       float v = tile[tx][j];
       if (sizeof(TD) == 4 && round_tf) v = rn_tf32(v);
       TD* o = d + (size_t)c * R * pd + r;
-      Act<TD>::st(o, v);
-      if constexpr (SD) Act<TD>::st(o + R, v - Act<TD>::ld(o));
+      if constexpr (SD) {
+        if (dst_f16) {   // fp16 planes (precision plan): the 16-bit containers are written through __half
+          const float vs = sat_f16(v);
+          const __half hi = __float2half_rn(vs);
+          reinterpret_cast<__half*>(o)[0] = hi;
+          reinterpret_cast<__half*>(o)[R] = __float2half_rn(vs - __half2float(hi));
+        } else {
+          Act<TD>::st(o, v);
+          Act<TD>::st(o + R, v - Act<TD>::ld(o));
+        }
+      } else {
+        Act<TD>::st(o, v);
+      }
     }
   }
 }
 
 int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, int S, int to_cl, cudaStream_t stream,
-                  int round_tf) {
+                  int round_tf, int dst_f16) {
   AITB_REQUIRE(G > 0 && C > 0 && S > 0, "aitb_transpose_cs: empty tensor");
   AITB_REQUIRE(G <= 65535, "aitb_transpose_cs: G=%d exceeds grid.z", G);
   // to_cl: src [G, C, S] -> dst [G, S, C]  => R = C, Cc = S ; else src [G, S, C] -> dst [G, C, S] => R = S, Cc = C
@@ -591,7 +601,7 @@ int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, in
                                                                               (__nv_bfloat16*)dst, R, Cc, 0);
   else if (sdt == AITB_F32 && ddt == AITB_F32S)
     transpose_kernel<float, __nv_bfloat16, false, true><<<grid, 256, 0, stream>>>((const float*)src,
-                                                                                   (__nv_bfloat16*)dst, R, Cc, 0);
+                                                                                   (__nv_bfloat16*)dst, R, Cc, 0, dst_f16);
   else if (sdt == AITB_F32S && ddt == AITB_F32)
     transpose_kernel<__nv_bfloat16, float, true, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src,
                                                                                    (float*)dst, R, Cc, 0);
@@ -603,7 +613,8 @@ int transpose_run(const void* src, int sdt, void* dst, int ddt, int G, int C, in
 }
 
 int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, int W, int K, float scale, int ph,
-                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf) {
+                      int pw, int sampling_ratio, int dtype, int out_layout, void* out, cudaStream_t stream, int round_tf,
+                      int out_f16) {
   AITB_REQUIRE(K >= 0 && B > 0, "aitb_roi_align_forward: bad sizes");
   if (K == 0) return 0;
   AITB_REQUIRE(C % 4 == 0, "aitb_roi_align_forward: C=%d must be a multiple of 4 (128-bit channel vectors)", C);
@@ -617,24 +628,24 @@ int roi_align_fwd_run(const void* feat, const float* rois, int B, int C, int H, 
   if (dtype == AITB_F32) {
     if (out_layout == 0)
       roi_align_fwd_kernel<float, true><<<grid, 256, smem, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
-                                                                      sampling_ratio, (float*)out, round_tf);
+                                                                      sampling_ratio, (float*)out, round_tf, 0);
     else
       roi_align_fwd_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
-                                                                    sampling_ratio, (float*)out, round_tf);
+                                                                    sampling_ratio, (float*)out, round_tf, 0);
   } else if (dtype == AITB_F32S) {   // fp32 map -> split token-major output (engine-internal)
     AITB_REQUIRE(out_layout == 1, "aitb_roi_align_forward: the split configuration writes token-major output only");
     roi_align_fwd_kernel<float, false, true><<<grid, 256, 0, stream>>>((const float*)feat, rois, C, H, W, scale, ph, pw,
-                                                                       sampling_ratio, (__nv_bfloat16*)out, 0);
+                                                                       sampling_ratio, (__nv_bfloat16*)out, 0, out_f16);
   } else if (dtype == AITB_BF16) {
     if (out_layout == 0)
       roi_align_fwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, stream>>>(
-          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0);
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0, 0);
     else if (C % 8 == 0 && (((uintptr_t)feat | (uintptr_t)out) & 15) == 0 && !no_fwd8)
       roi_align_fwd8_kernel<<<dim3((C + 255) / 256, K), 256, 0, stream>>>((const __nv_bfloat16*)feat, rois, C, H, W, scale, ph,
                                                                           pw, sampling_ratio, (__nv_bfloat16*)out);
     else
       roi_align_fwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(
-          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0);
+          (const __nv_bfloat16*)feat, rois, C, H, W, scale, ph, pw, sampling_ratio, (__nv_bfloat16*)out, 0, 0);
   } else {
     set_error("aitb_roi_align_forward: bad dtype %d", dtype);
     return 1;

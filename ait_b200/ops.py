@@ -46,15 +46,24 @@ def transpose_cs(src, to_channels_last, out_dtype=None, split_src=False, split_d
     return dst
 
 
-def split_planes(x):
-    """fp32 [..., C] -> bf16 [..., hi C | lo C] (host-side helper for tests / packing)."""
-    hi = x.float().to(torch.bfloat16)
-    lo = (x.float() - hi.float()).to(torch.bfloat16)
+def split_planes(x, f16=False):
+    """fp32 [..., C] -> two 16-bit planes [..., hi C | lo C] (host-side helper for tests / packing).  f16: the planes hold
+    IEEE fp16 (the precision plan's operand format: 11-bit significand, saturating) inside the same bfloat16-typed container."""
+    x = x.float()
+    if f16:
+        x = x.clamp(-65504.0, 65504.0)
+        hi = x.to(torch.float16)
+        lo = (x - hi.float()).to(torch.float16)
+        return torch.cat([hi, lo], dim=-1).contiguous().view(torch.bfloat16)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
     return torch.cat([hi, lo], dim=-1).contiguous()
 
 
-def join_planes(x):
-    """bf16 [..., hi C | lo C] -> fp32 [..., C]."""
+def join_planes(x, f16=False):
+    """[..., hi C | lo C] -> fp32 [..., C]  (f16: the container holds fp16 planes, see split_planes)."""
+    if f16:
+        x = x.contiguous().view(torch.float16)
     c = x.shape[-1] // 2
     return x[..., :c].float() + x[..., c:].float()
 
@@ -158,7 +167,8 @@ def _esize(dt):
 
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
-         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False, ln_rstd=None):
+         rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False, ln_rstd=None,
+         passes=0, in_f16=False, out_f16=False, res_f16=False):
     """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
     map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels).
     split=True: AITB_F32S -- a / w / out / res are two-plane bf16 matrices (see split_planes); K, lda, ldr
@@ -209,6 +219,7 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.dual = 1 if dual else 0
     d.bias2 = 0 if bias2 is None else bias2.data_ptr()
     d.ln_rstd = 0 if ln_rstd is None else ln_rstd.data_ptr()
+    d.passes, d.in_f16, d.out_f16, d.res_f16 = int(passes), int(bool(in_f16)), int(bool(out_f16)), int(bool(res_f16))
     L.check(lib.aitb_gemm(C.byref(d), L.stream_ptr()))
     return out
 

@@ -35,10 +35,20 @@ def fingerprint(module):
 
 
 class HeadEngine:
+    # Precision plan of the "fp32" configuration (include/aitb200.h AITB_PLAN_*): PLAN_ENC_ONEPASS runs the five
+    # encoder-side GEMMs as one tensor-core pass on fp16 hi planes.  AITB_PRECISION_PLAN=0 in the environment (read when the
+    # engine is built) restores three passes everywhere -- the A/B switch of tools/ and the tests.
+    DEFAULT_PLAN = L.PLAN_ENC_ONEPASS
+
     def __init__(self, transformer=None, sk=None, top=None, cls_score=None, bbox_pred=None,
-                 dtype=torch.float32, round_acts=True):
+                 dtype=torch.float32, round_acts=True, plan=None):
+        import os
         L.load()
         self.mode = L.mode_name(dtype)             # "fp32" (split bf16 x3) | "tf32" | "bf16"
+        if plan is None:
+            plan = int(os.environ.get("AITB_PRECISION_PLAN", self.DEFAULT_PLAN))
+        self.plan = int(plan) if self.mode == "fp32" else 0
+        self.enc_f16 = bool(self.plan & L.PLAN_ENC_ONEPASS)      # pooled / enc_out taps and the encoder weights are fp16 planes
         self.dt = L.MODES[self.mode]
         self.dtype = L.storage_dtype(self.mode)    # element type of the activation / weight buffers
         self.split = self.mode == "fp32"
@@ -48,6 +58,7 @@ class HeadEngine:
         self.w = L.HeadWeights()
         self.w.dtype = self.dt
         self.w.round_tf32 = 1 if self.round_acts else 0
+        self.w.plan = self.plan
         self.device = None
         self.has_ait = transformer is not None
         self.has_sk = sk is not None
@@ -75,15 +86,15 @@ class HeadEngine:
             raise RuntimeError("ait_b200: all parameters must be on the same device")
         return t
 
-    def _mat(self, t):
-        """[N, K] matrix in the compute dtype."""
+    def _mat(self, t, f16=False):
+        """[N, K] matrix in the compute dtype (f16: fp16 planes -- the operand of a one-pass GEMM of the precision plan)."""
         t = self._dev(t).detach().float().contiguous()
         if self.mode == "tf32":
             t = round_to_tf32(t)
         elif self.mode == "bf16":
             t = t.to(torch.bfloat16)
         else:                                       # [N, hi K | lo K]
-            t = ops.split_planes(t)
+            t = ops.split_planes(t, f16=f16 and self.enc_f16)
         t = t.contiguous()
         self._keep.append(t)
         return t
@@ -93,8 +104,8 @@ class HeadEngine:
         self._keep.append(t)
         return t
 
-    def _linear(self, dst, w, b=None):
-        m = self._mat(w)
+    def _linear(self, dst, w, b=None, f16=False):
+        m = self._mat(w, f16=f16)
         bt = self._f32(b) if b is not None else None
         dst.w = m.data_ptr()
         dst.bias = bt.data_ptr() if bt is not None else None
@@ -104,22 +115,31 @@ class HeadEngine:
         dst.gamma = self._f32(ln.weight).data_ptr()
         dst.beta = self._f32(ln.bias).data_ptr()
 
-    def _mha(self, dst, m):
-        wqkv = self._mat(torch.cat([m.w_qs.weight, m.w_ks.weight, m.w_vs.weight], dim=0))
+    def _mha(self, dst, m, f16_rows=None):
+        """f16_rows: (first, last) rows of the stacked [w_qs; w_ks; w_vs] matrix read by a one-pass GEMM (fp16 planes)."""
+        wcat = torch.cat([m.w_qs.weight, m.w_ks.weight, m.w_vs.weight], dim=0)
+        if f16_rows is not None and self.split and self.enc_f16:
+            a, b = f16_rows
+            parts = [ops.split_planes(self._dev(wcat[:a]).detach().float()), ops.split_planes(self._dev(wcat[a:b]).detach().float(), f16=True),
+                     ops.split_planes(self._dev(wcat[b:]).detach().float())]
+            wqkv = torch.cat([p_ for p_ in parts if p_.shape[0] > 0], dim=0).contiguous()
+            self._keep.append(wqkv)
+        else:
+            wqkv = self._mat(wcat)
         dst.w_qkv = wqkv.data_ptr()
         dst.w_sk = self._f32(m.sh.sk.weight).data_ptr()
         dst.b_sk = self._f32(m.sh.sk.bias).data_ptr()
         dst.w_fc = self._mat(m.fc.weight).data_ptr()
         self._ln(dst.ln, m.layer_norm)
 
-    def _ffn(self, dst, f):
-        self._linear(dst.w1, f.w_1.weight, f.w_1.bias)
-        self._linear(dst.w2, f.w_2.weight, f.w_2.bias)
+    def _ffn(self, dst, f, f16=False):
+        self._linear(dst.w1, f.w_1.weight, f.w_1.bias, f16=f16)
+        self._linear(dst.w2, f.w_2.weight, f.w_2.bias, f16=f16)
         self._ln(dst.ln, f.layer_norm)
 
     def _pack_transformer(self, t):
         w = self.w
-        self._linear(w.enc_emb, t.enc_emb[0].weight.flatten(1), t.enc_emb[0].bias)
+        self._linear(w.enc_emb, t.enc_emb[0].weight.flatten(1), t.enc_emb[0].bias, f16=True)   # one-pass GEMM (plan)
         self._linear(w.dec_emb, t.dec_emb[0].weight.flatten(1), t.dec_emb[0].bias)
         self._linear(w.dec_trans, t.dec_trans[0].weight.flatten(1), t.dec_trans[0].bias)
         enc_pos = t.encoder.position_enc.pos_table
@@ -131,10 +151,10 @@ class HeadEngine:
         self._ln(w.enc_ln, t.encoder.layer_norm)
         self._ln(w.dec_ln, t.decoder.layer_norm)
         el, dl = t.encoder.layer_stack[0], t.decoder.layer_stack[0]
-        self._mha(w.enc_slf, el.slf_attn)
-        self._ffn(w.enc_ffn, el.pos_ffn)
+        self._mha(w.enc_slf, el.slf_attn, f16_rows=(0, 1536))      # encoder QKV projection: one pass (plan)
+        self._ffn(w.enc_ffn, el.pos_ffn, f16=True)                 # encoder FFN: one pass (plan)
         self._mha(w.dec_slf, dl.slf_attn)
-        self._mha(w.dec_enc, dl.enc_attn)
+        self._mha(w.dec_enc, dl.enc_attn, f16_rows=(512, 1536))    # cross attention: K / V rows one pass, the Q rows (query side) three
         self._ffn(w.dec_ffn, dl.pos_ffn)
 
     @staticmethod
@@ -375,7 +395,7 @@ class HeadEngine:
         if taps:
             if self.split:
                 for k in ("pooled", "enc_out", "ait_out", "sk_out"):
-                    tensors[k] = ops.join_planes(tensors[k])
+                    tensors[k] = ops.join_planes(tensors[k], f16=self.enc_f16 and k in ("pooled", "enc_out"))
             return cls_prob, bbox, tensors
         return cls_prob, bbox
 

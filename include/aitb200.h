@@ -172,6 +172,13 @@ typedef struct {
   int map_w, map_h;
   /* the accumulator is multiplied by out_scale before bias / activation (0 = unset = 1) */
   float out_scale;
+  /* AITB_F32S only -- the per-stage precision plan of the fp32-class configuration:
+   *   passes : 0 / 3 = three MMA passes hi*hi + hi*lo + lo*hi (both operands 16+ bits);  1 = one pass on the hi planes
+   *            (honoured by the 2-CTA and the cluster-LayerNorm kernels; other launches run three passes)
+   *   in_f16 : the planes of A and W hold IEEE fp16 (11-bit significand; hi alone = tf32-class operands) instead of bf16
+   *   out_f16 / res_f16 : element format of the output planes this launch writes / the residual planes it reads
+   * fp16 planes saturate at +-65504; they are used only for LayerNorm-bounded AIT tensors (precision plan). */
+  int passes, in_f16, out_f16, res_f16;
 } aitb_gemm_desc;
 
 int aitb_gemm(const aitb_gemm_desc* d, aitb_stream_t stream);
@@ -244,9 +251,16 @@ typedef struct {
   const void* w_fused; /* [1024, 10*128] = conv3x3 taps followed by the conv1x1 block (dual-accumulator GEMM) */
 } aitb_skblock;
 
+/* aitb_head_weights.plan bits (AITB_F32S configuration only; see DESIGN.md "precision plan") */
+#define AITB_PLAN_ENC_ONEPASS 1 /* encoder-side GEMMs (enc_emb, encoder QKV, encoder FFN w_1 / w_2, cross-attention K/V) run ONE
+                                   tensor-core pass on fp16 hi planes (11-bit operands) instead of three on bf16 planes; their
+                                   weights (enc_emb.w, enc_slf.w_qkv, enc_ffn.w1/w2.w, rows 512.. of dec_enc.w_qkv) must then be
+                                   packed as fp16 planes */
+
 typedef struct {
   int dtype;
   int round_tf32;
+  int plan; /* AITB_PLAN_* bits, 0 = three passes everywhere */
   /* AIT (system/Models.py:177-220) */
   aitb_linear enc_emb, dec_emb, dec_trans;
   const float* enc_pos; /* [64, 512] f32 (encoder.position_enc.pos_table) */

@@ -29,8 +29,11 @@ def _scaled_err(out, ref):
     return float((out.double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("dtype", MODES)
-def test_head_matches_reference_golden(dtype):
+@pytest.mark.parametrize("dtype", MODES + ["fp32-three-pass"])
+def test_head_matches_reference_golden(dtype, monkeypatch):
+    if dtype == "fp32-three-pass":        # the fp32 configuration without the precision plan (A/B switch)
+        monkeypatch.setenv("AITB_PRECISION_PLAN", "0")
+        dtype = "fp32"
     head, g = golden_head(compute_dtype=dtype)
     head = head.to(DEV)
     non_img, non_qry, rois = head_inputs(g["B"], g["P"])
@@ -53,18 +56,29 @@ def test_head_matches_reference_golden(dtype):
     torch.testing.assert_close(cls_prob.cpu(), g["cls_prob"], rtol=0, atol=CLS_ATOL[dtype])
 
 
+# enc_out sits INSIDE the one-pass region of the fp32 configuration's precision plan (encoder GEMMs on 11-bit fp16 hi planes,
+# DESIGN.md): tf32-class at that tap by design (measured 3.4e-4 of scale); every tensor downstream of the decoder -- ait_out,
+# sk_out, the layer-4 features, bbox_pred, cls_prob -- keeps its gate.  With the plan off (three passes everywhere) enc_out
+# meets REL["fp32"] too.
+ENC_REL = {"plan": 6e-4, "three-pass": REL["fp32"]}
+
+
+@pytest.mark.parametrize("plan", ["plan", "three-pass"])
 @pytest.mark.parametrize("B,P", [(1, 1), (3, 5), (2, 37)])
-def test_head_matches_oracle_ragged_sizes(B, P):
+def test_head_matches_oracle_ragged_sizes(B, P, plan, monkeypatch):
     """sizes that do not fill the 128-row GEMM tiles / straddle pairs and units."""
+    if plan == "three-pass":
+        monkeypatch.setenv("AITB_PRECISION_PLAN", "0")
     head, _ = golden_head()
     sd = head.state_dict()
     head = head.to(DEV)
+    assert head.engine().plan == (1 if plan == "plan" else 0)
     non_img, non_qry, rois = head_inputs(B, P, first_unit=10)
     with torch.no_grad():
         ref = head_oracle.head_forward(sd, non_img, non_qry, rois)
     cls_prob, bbox, taps = head(non_img.to(DEV), non_qry.to(DEV), rois.to(DEV), taps=True)
     enc = taps["enc_out"].float().cpu()
-    assert _scaled_err(enc[:, :49], ref["enc_out"][:, :49]) < REL["fp32"]     # pad rows are dead after enc self-attn
+    assert _scaled_err(enc[:, :49], ref["enc_out"][:, :49]) < ENC_REL[plan]    # pad rows are dead after enc self-attn
     ait = taps["ait_out"].float().cpu().permute(0, 2, 1).reshape(B * P, 1024, 8, 8)
     assert _scaled_err(ait, ref["ait_out"]) < REL["fp32"]
     assert _scaled_err(taps["feat"].cpu(), ref["feat"]) < 2 * REL["fp32"]

@@ -212,3 +212,73 @@ def test_fc_ln_streaming_kernel(split, case):
             yb = ab @ wb.t() + rb
         refb = F.layer_norm(yb, (512,), gamma.double(), beta.double(), eps=1e-6).reshape(rows, 512)
         assert _err(o[:rows], refb) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# precision plan: one tensor-core pass on fp16 hi planes (aitb_gemm_desc.passes = 1, in_f16 / out_f16 / res_f16)
+# ---------------------------------------------------------------------------------------------
+def _sp16(x):
+    from ait_b200 import ops
+    return ops.split_planes(x, f16=True).to(DEV)
+
+
+def _jn16(x):
+    from ait_b200 import ops
+    return ops.join_planes(x, f16=True).cpu()
+
+
+def test_fp16_planes_roundtrip_and_saturation():
+    from ait_b200 import ops
+    x = torch.randn(64, 256, generator=torch.Generator().manual_seed(0)) * 37.0
+    y = ops.join_planes(ops.split_planes(x, f16=True), f16=True)
+    assert float((x - y).abs().max() / x.abs().max()) < 2 ** -20          # 11 + 11 bits
+    big = torch.tensor([[1e6, -3e5, 70000.0, 1.0]])
+    z = ops.join_planes(ops.split_planes(big, f16=True), f16=True)
+    assert torch.isfinite(z).all() and float(z[0, 0]) == 65504.0 and float(z[0, 3]) == 1.0
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (4096 + 5, 2048, 512), (640, 256, 2048), (128, 256, 64)])
+def test_onepass_fp16_gemm_plain_bias_relu(M, N, K):
+    """2-CTA kernel, one pass: the result equals the exact product of the fp16-ROUNDED operands (the hi planes) to fp32
+    accumulation error, and the full-precision product to the 11-bit operand rounding (~tf32 class); the output is written
+    as fp16 planes.  M = 128 (one m-tile) takes the three-pass single-CTA kernel on the same fp16 planes."""
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref_full = F.relu(a.double() @ w.double().t() + bias.double())
+    ref_hi = F.relu(a.half().double() @ w.half().double().t() + bias.double())
+    out = torch.full((M, 2 * N), float("nan"), dtype=BF, device=DEV)
+    ops.gemm(_sp16(a), _sp16(w), out, M=M, N=N, K=K, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=bias.to(DEV),
+             split=True, passes=1, in_f16=True, out_f16=True)
+    got = _jn16(out)
+    if M >= 256:
+        assert _err(got, ref_hi) < 4e-6
+        assert 2e-5 < _err(got, ref_full) < 2e-3      # really one pass: the operand rounding is visible
+    else:
+        assert _err(got, ref_full) < 4e-6             # three passes on fp16 planes: 22-bit operands
+
+
+def test_onepass_fp16_gemm_layernorm_residual():
+    """cluster-LayerNorm kernel, one pass: FFN w_2 shape with an fp16-plane residual and fp16-plane output."""
+    from ait_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(5)
+    M, K = 700, 2048
+    a = torch.relu(torch.randn(M, K, generator=g))
+    w = torch.randn(512, K, generator=g) / K ** 0.5
+    bias, res = torch.randn(512, generator=g), torch.randn(M, 512, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+    x = a.half().double() @ w.half().double().t() + bias.double() + res.double()
+    ref = F.layer_norm(x, (512,), gamma.double(), beta.double(), eps=1e-6)
+    out = torch.full((M, 1024), float("nan"), dtype=BF, device=DEV)
+    ops.gemm(_sp16(a), _sp16(w), out, M=M, N=512, K=K, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN,
+             bias=bias.to(DEV), res=_sp16(res), ldr=512, gamma=gamma.to(DEV), beta=beta.to(DEV), split=True,
+             passes=1, in_f16=True, out_f16=True, res_f16=True)
+    assert _err(_jn16(out), ref) < 1e-5
+    # mixed formats: bf16-plane residual, bf16-plane output, fp16 operands
+    out2 = torch.full((M, 1024), float("nan"), dtype=BF, device=DEV)
+    ops.gemm(_sp16(a), _sp16(w), out2, M=M, N=512, K=K, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN,
+             bias=bias.to(DEV), res=_sp(res), ldr=512, gamma=gamma.to(DEV), beta=beta.to(DEV), split=True,
+             passes=1, in_f16=True)
+    assert _err(_jn(out2), ref) < 3e-5
