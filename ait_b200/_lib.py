@@ -17,8 +17,8 @@ MODES = {"fp32": AITB_F32S, "tf32": AITB_F32, "bf16": AITB_BF16}
 
 PLAN_ENC_ONEPASS = 1
 
-EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK, EPI_RES_ROW_M = (
-    1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+EPI_BIAS, EPI_RELU, EPI_SQUARE, EPI_RES, EPI_POS, EPI_LN, EPI_ACCUM, EPI_RES_RELU, EPI_DUAL, EPI_RELU_MASK, EPI_RES_ROW_M, EPI_HI_ONLY = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048)
 
 
 class View4(C.Structure):

@@ -415,7 +415,10 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
   view_plain(d1, x, 512);
   d1.flags = AITB_EPI_BIAS | AITB_EPI_RELU;
   d1.bias = f.w1.bias;
-  if (onepass) { d1.passes = 1; d1.in_f16 = 1; d1.out_f16 = 1; }
+  if (onepass) {   // the hidden tensor feeds the one-pass w_2 GEMM only: its lo plane is never read
+    d1.passes = 1; d1.in_f16 = 1; d1.out_f16 = 1;
+    d1.flags |= AITB_EPI_HI_ONLY;
+  }
   RUN(gemm_run(&d1, st));
   aitb_gemm_desc d2 = gemm_base(dt, M, 512, 2048, f.w2.w, 512, out, 512, w->round_tf32);
   if (onepass) { d2.passes = 1; d2.in_f16 = 1; d2.out_f16 = 1; d2.res_f16 = 1; }

@@ -647,11 +647,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 //   bias_s  : this warpgroup's bias slice [2][128] floats (double-buffered by accumulator stage)
 //   n0      : first output column of this warp's 128 columns;   row0 : first output row of this warp's 32 rows
 // ---------------------------------------------------------------------------------------------
+// SPLIT_OUT (the one-pass GEMMs of the fp32 configuration's precision plan): the output is two 16-bit planes (bf16 or fp16,
+// p.out_f16) hi | lo, N columns apart; per chunk a hi tile and a lo tile, two staging buffers per warp (chunk c reuses the
+// buffer of chunk c - 2 after cp.async.bulk.wait_group.read 1).  p.flags & AITB_EPI_HI_ONLY: the lo plane is not written
+// (the only consumer reads the hi plane: the FFN hidden tensor between two one-pass GEMMs).
+template <bool SPLIT_OUT>
 __device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const CUtensorMap* tmO, uint32_t stg_s, uint32_t bias_s,
                                                    int bar_id, uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t aph,
                                                    uint32_t t_row, int lane, int wg_tid, int row0, int n0, uint32_t as) {
   const bool has_bias = (p.flags & AITB_EPI_BIAS) != 0;
   const bool relu = (p.flags & AITB_EPI_RELU) != 0;
+  const bool of16 = SPLIT_OUT && p.out_f16 != 0;
+  const bool hi_only = SPLIT_OUT && (p.flags & AITB_EPI_HI_ONLY) != 0;
   const uint32_t bias_buf = bias_s + as * 512u;
   if (lane == 0) bulk_wait_read_all();            // the previous tile's stores no longer read the staging tiles
   if (has_bias) {
@@ -677,6 +684,10 @@ __device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const C
       tc_fence_before();
       mbar_arrive_remote(acc_empty_bar, 0);
     }
+    if (SPLIT_OUT || p.acc_scale != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
+    }
     if (has_bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -685,26 +696,59 @@ __device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const C
         v[4 * j + 2] += __uint_as_float(b.z); v[4 * j + 3] += __uint_as_float(b.w);
       }
     }
-    const uint32_t tile = stg_s + (uint32_t)c * 2048u;
-    const uint32_t rowb = tile + (uint32_t)lane * 64u;
     const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 x;
+    if constexpr (SPLIT_OUT) {
+      if (c >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // chunk c - 2 left its buffer
+      __syncwarp();
+      const uint32_t tile = stg_s + (uint32_t)(c & 1) * 4096u;    // [hi 2 KB | lo 2 KB]
+      const uint32_t rowb = tile + (uint32_t)lane * 64u;
       if (relu) {
-        x.x = pack_bf16x2_relu(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
-        x.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
-      } else {
-        x.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        x.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      sts128(rowb + (((uint32_t)j ^ sw) << 4), x);
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(tmO, tile, n0 + c * 32, row0);
-      bulk_commit_group();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo[8];
+        uint4 hi, lw;
+        hi.x = split_hi2(v[8 * j], v[8 * j + 1], of16, lo[0], lo[1]);
+        hi.y = split_hi2(v[8 * j + 2], v[8 * j + 3], of16, lo[2], lo[3]);
+        hi.z = split_hi2(v[8 * j + 4], v[8 * j + 5], of16, lo[4], lo[5]);
+        hi.w = split_hi2(v[8 * j + 6], v[8 * j + 7], of16, lo[6], lo[7]);
+        sts128(rowb + (((uint32_t)j ^ sw) << 4), hi);
+        if (!hi_only) {
+          lw.x = pack_plane2(lo[0], lo[1], of16); lw.y = pack_plane2(lo[2], lo[3], of16);
+          lw.z = pack_plane2(lo[4], lo[5], of16); lw.w = pack_plane2(lo[6], lo[7], of16);
+          sts128(rowb + 2048u + (((uint32_t)j ^ sw) << 4), lw);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO, tile, n0 + c * 32, row0);
+        if (!hi_only) tma_store_2d(tmO, tile + 2048u, p.o_lo + n0 + c * 32, row0);
+        bulk_commit_group();
+      }
+    } else {
+      const uint32_t tile = stg_s + (uint32_t)c * 2048u;
+      const uint32_t rowb = tile + (uint32_t)lane * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 x;
+        if (relu) {
+          x.x = pack_bf16x2_relu(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
+          x.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
+        } else {
+          x.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          x.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        }
+        sts128(rowb + (((uint32_t)j ^ sw) << 4), x);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO, tile, n0 + c * 32, row0);
+        bulk_commit_group();
+      }
     }
   }
 }
@@ -1055,7 +1099,7 @@ template <typename T, bool SPLIT, bool SIMPLE = false, bool FAST = false, bool O
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const GemmKParams p) {
-  static_assert(!FAST || (!SPLIT && !SIMPLE && sizeof(T) == 2), "FAST epilogue: plain bf16 only");
+  static_assert(!FAST || (!SIMPLE && sizeof(T) == 2 && (!SPLIT || ONEPASS)), "FAST epilogue: plain bf16, or the one-pass split variant");
   static_assert(!ONEPASS || SPLIT, "ONEPASS: the one-pass variant of the split (two-plane) configuration");
   constexpr bool SPLIT_IN = SPLIT && !ONEPASS;   // stages hold both planes, three MMAs per K slice
   constexpr int BLOCK_N = 256;
@@ -1192,7 +1236,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
       if constexpr (FAST) {
         const uint32_t bias_s = smem_u32(smem + k2Stages * k2StageBytes + 8 * 8192 + 128) + (uint32_t)half * 1024u;
-        epilogue_fast_tile(p, &tmO, smem_u32(stg), bias_s, 1 + half, &acc_full[as], &acc_empty[as], aph,
+        epilogue_fast_tile<SPLIT>(p, &tmO, smem_u32(stg), bias_s, 1 + half, &acc_full[as], &acc_empty[as], aph,
                            t_row + (uint32_t)(half * 128), lane, q * 32 + lane, (mp * 2 + (int)rank) * kBlockM + q * 32,
                            nt * BLOCK_N + half * 128, as);
       } else {
@@ -1417,6 +1461,7 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
                "aitb_gemm: pointers must be 16/32-byte aligned");
   AITB_REQUIRE(d->out_scale == 0.f || d->out_scale == 1.f || (d->flags & AITB_EPI_LN) == 0 || split,
                "aitb_gemm: out_scale is not applied by the LayerNorm epilogue of the non-split configurations");
+  AITB_REQUIRE((d->flags & AITB_EPI_HI_ONLY) == 0 || split, "aitb_gemm: HI_ONLY belongs to the split configuration");
   AITB_REQUIRE((d->flags & AITB_EPI_RELU_MASK) == 0 || (!split && (d->flags & (AITB_EPI_RES | AITB_EPI_LN)) == 0),
                "aitb_gemm: RELU_MASK excludes RES / LN and the split configuration");
   if (d->flags & (AITB_EPI_RES | AITB_EPI_RELU_MASK))
@@ -1550,16 +1595,24 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     if (simple) return launch_gemm2<float, false, true>(tmA, tmB, tmA, kp, stream);
     // bf16 outputs, rows = GEMM rows, epilogue at most bias + ReLU: the TMA-store fast epilogue (A/B: AITB_NO_FAST_EPI=1)
     static const bool fast_on = getenv("AITB_NO_FAST_EPI") == nullptr;
-    const bool fast = fast_on && d->dtype == AITB_BF16 && kp.a_m_dim != 2 && kp.rows_in == kp.rows_out &&
-                      (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU)) == 0 && kp.acc_scale == 1.f &&
-                      (((uintptr_t)d->out) & 15) == 0 && ((size_t)d->ldo * 2) % 16 == 0;
-    if (fast) {
+    const bool fast_shape = fast_on && kp.a_m_dim != 2 && kp.rows_in == kp.rows_out &&
+                            (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_HI_ONLY)) == 0 &&
+                            (((uintptr_t)d->out) & 15) == 0 && ((size_t)d->ldo * 2) % 16 == 0;
+    if (fast_shape && d->dtype == AITB_BF16 && kp.acc_scale == 1.f) {
       CUtensorMap tmO;
       const uint64_t odims[2] = {(uint64_t)d->N, (uint64_t)d->M};
       const uint64_t ostr[1] = {(uint64_t)d->ldo * 2};
       const uint32_t obox[2] = {32u, 32u};
       if (encode_map(&tmO, AITB_BF16, d->out, 2, odims, ostr, obox, "O", true)) return 1;
       return launch_gemm2<__nv_bfloat16, false, false, true>(tmA, tmB, tmO, kp, stream);
+    }
+    if (fast_shape && onepass) {   // two 16-bit planes per row: hi at column 0, lo at column ldo
+      CUtensorMap tmO;
+      const uint64_t odims[2] = {(uint64_t)d->ldo + (uint64_t)d->N, (uint64_t)d->M};
+      const uint64_t ostr[1] = {(uint64_t)d->ldo * 4};
+      const uint32_t obox[2] = {32u, 32u};
+      if (encode_map(&tmO, AITB_BF16, d->out, 2, odims, ostr, obox, "O", true)) return 1;
+      return launch_gemm2<__nv_bfloat16, true, false, true, true>(tmA, tmB, tmO, kp, stream);
     }
     return d->dtype == AITB_F32 ? launch_gemm2<float, false, false>(tmA, tmB, tmA, kp, stream)
            : onepass            ? launch_gemm2<__nv_bfloat16, true, false, false, true>(tmA, tmB, tmA, kp, stream)

@@ -42,6 +42,9 @@ PROPOSALS = 300
 PRE_NMS, NMS_THR = 6000, 0.7
 FLOP_PER_PAIR = 1.494e9          # de-duplicated algorithmic FLOPs per pair (SURVEY 8d / BASELINE.md section 3)
 FLOP_PER_UNIT_SHARED = 0.214e9 + 0.646e9
+# fp32 configuration, precision plan: enc_emb 51.4 + encoder QKV 100.7 + encoder FFN 2 x 102.8 + cross-attention K/V
+# 51.4 MFLOP per pair run ONE tensor-core pass, the rest three
+FLOP_PER_PAIR_ONEPASS = 0.4091e9
 METRIC = "proposal-query pairs/sec (ROIAlign+AIT head+NMS)"
 
 
@@ -627,6 +630,9 @@ def run_ours(args):
     pairs = B * P
     step_flops = pairs * FLOP_PER_PAIR + B * FLOP_PER_UNIT_SHARED
     head_tflops = step_flops / (ms_head * 1e-3) / 1e12
+    plan_on = split and bool(getattr(eng, "plan", 0) & 1)
+    # average MMA passes per algorithmic product over the whole head (the plan runs 27 % of the FLOPs in one pass)
+    head_passes = passes if not plan_on else (3.0 * step_flops - 2.0 * pairs * FLOP_PER_PAIR_ONEPASS) / step_flops
     esz = 4 if dtype == torch.float32 else 2
     roi_bytes = B * (1024 * 38 * 63 * esz) + pairs * 49 * 1024 * esz
     traffic, traffic_file = ncu_traffic(mode)
@@ -711,7 +717,11 @@ def run_ours(args):
                          "head_step_tflops": head_tflops,
                          "head_frac_of_burst_algorithmic": head_tflops / tf_burst,
                          "head_frac_of_sustained_algorithmic": head_tflops / tf_sus,
-                         "head_frac_of_sustained_executed": passes * head_tflops / tf_sus,
+                         "head_frac_of_sustained_executed": head_passes * head_tflops / tf_sus,
+                         "head_mma_passes_per_product": head_passes,
+                         "precision_plan": ("encoder-side GEMMs (enc_emb, encoder QKV, encoder FFN w_1 / w_2, cross-attention K/V: "
+                                            "27 % of the FLOPs) one pass on fp16 hi planes, the rest three bf16 passes" if plan_on
+                                            else "none"),
                          "sustained_peak": tf_sus},
             "roofline_roi_align": {"bound": "hbm", "achieved": roi_bytes / (ms_roi * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": roi_bytes / (ms_roi * 1e-3) / 1e9 / hbm, "us": ms_roi * 1e3,

@@ -126,7 +126,9 @@ enum {
                               f = the RELU / SQUARE flags (SKBlock: relu(conv1x1)^2 + relu(conv3x3)^2) */
   AITB_EPI_RELU_MASK = 512, /* backward of ReLU: v = residual[res_row, n] > 0 ? v : 0  (`res` = the saved activation;
                               excludes RES / LN / split) */
-  AITB_EPI_RES_ROW_M = 1024 /* the residual row is derived from the GEMM row m instead of the (remapped) output row */
+  AITB_EPI_RES_ROW_M = 1024, /* the residual row is derived from the GEMM row m instead of the (remapped) output row */
+  AITB_EPI_HI_ONLY = 2048    /* AITB_F32S: only the hi plane of the output is consumed (by a one-pass GEMM); the 2-CTA one-pass
+                                kernel then skips the lo plane (other kernels write both) */
 };
 
 typedef struct {

@@ -282,3 +282,30 @@ def test_onepass_fp16_gemm_layernorm_residual():
              bias=bias.to(DEV), res=_sp(res), ldr=512, gamma=gamma.to(DEV), beta=beta.to(DEV), split=True,
              passes=1, in_f16=True)
     assert _err(_jn(out2), ref) < 3e-5
+
+
+@pytest.mark.parametrize("flags_name", ["none", "bias_relu", "bias_relu_hi_only"])
+def test_onepass_fast_epilogue_matches_general_path(flags_name, monkeypatch):
+    """The TMA-store fast epilogue of the one-pass 2-CTA kernel (hi | lo planes, fp16) against the exact product of the hi
+    planes, ragged M (TMA clips the last rows) and, with HI_ONLY, an untouched lo plane."""
+    from ait_b200 import _lib as L, ops
+    M, N, K = 128 * 7 + 45, 1536, 512
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    flags = 0 if flags_name == "none" else (L.EPI_BIAS | L.EPI_RELU)
+    if flags_name.endswith("hi_only"):
+        flags |= L.EPI_HI_ONLY
+    x = a.half().double() @ w.half().double().t()
+    ref = F.relu(x + bias.double()) if flags else x
+    out = torch.full((M + 3, 2 * N), 7.0, dtype=BF, device=DEV)          # 3 guard rows past M
+    ops.gemm(_sp16(a), _sp16(w), out, M=M, N=N, K=K, block_n=256, flags=flags, bias=bias.to(DEV) if flags else None,
+             split=True, passes=1, in_f16=True, out_f16=True)
+    assert bool((out[M:].float() == 7.0).all()), "rows past M were written"
+    if flags_name.endswith("hi_only"):
+        assert bool((out[:M, N:].float() == 7.0).all()), "HI_ONLY wrote the lo plane"
+        hi = out[:M, :N].contiguous().view(torch.float16).float().cpu()
+        assert _err(hi, ref) < 1e-3                                       # 11-bit plane alone
+    else:
+        assert _err(_jn16(out[:M]), ref) < 4e-6
