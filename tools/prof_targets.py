@@ -55,8 +55,18 @@ w_sk = torch.randn(512, 64, device=dev) * 0.1
 b_sk = torch.zeros(512, device=dev)
 ao = buf(G * 64, 64)
 cb = 1 if split else 1  # column offsets below are in storage elements of the hi plane
+if split:
+    x512_16 = ops.split_planes(torch.randn(M, 512, device=dev), f16=True)
+    wqkv_16 = ops.split_planes(torch.randn(1536, 512, device=dev) / 512 ** 0.5, f16=True)
+    w2_16 = ops.split_planes(torch.randn(512, 2048, device=dev) / 2048 ** 0.5, f16=True)
+    qkv_out = buf(M, 1536)
+# the nms(dets, scores, thr) drop-in on one image's top-6000 boxes (bitmask + on-device scan)
+from ait_b200.roi_layers import nms as nms_dropin  # noqa: E402
+o0 = torch.argsort(scores[0], descending=True)[:6000]
+d0, s0 = boxes[0][o0].contiguous(), scores[0][o0].contiguous()
 torch.cuda.synchronize()
 for _ in range(reps):
+    nms_dropin(d0, s0, 0.7)
     ops.gemm(x512, w1, hid, M=M, N=2048, K=512, block_n=256, flags=L.EPI_BIAS | L.EPI_RELU, bias=b2048, split=split)
     ops.gemm(hid, w2, o512, M=M, N=512, K=2048, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN, bias=b512,
              res=x512, ldr=512, gamma=gamma, beta=b512, split=split)
@@ -73,5 +83,9 @@ for _ in range(reps):
     else:
         ops.roi_align_forward(nhwc, rois.view(-1, 5), 1 / 16.0, 7, 7, 0, token_major=True)
     propose_rois(boxes, scores)
+    if split:   # precision plan: the one-pass variants (fp16 hi planes) of the encoder QKV projection and the FFN w_2 GEMM
+        ops.gemm(x512_16, wqkv_16, qkv_out, M=M, N=1536, K=512, block_n=256, split=True, passes=1, in_f16=True)
+        ops.gemm(hid, w2_16, o512, M=M, N=512, K=2048, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN, bias=b512,
+                 res=x512_16, ldr=512, gamma=gamma, beta=b512, split=True, passes=1, in_f16=True, out_f16=True, res_f16=True)
 torch.cuda.synchronize()
 print("done")
