@@ -651,16 +651,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 // p.out_f16) hi | lo, N columns apart; per chunk a hi tile and a lo tile, two staging buffers per warp (chunk c reuses the
 // buffer of chunk c - 2 after cp.async.bulk.wait_group.read 1).  p.flags & AITB_EPI_HI_ONLY: the lo plane is not written
 // (the only consumer reads the hi plane: the FFN hidden tensor between two one-pass GEMMs).
+// Residual (plain bf16 only: the layer-4 conv3 launches, bias + residual + ReLU): the four 32 x 32 residual tiles of the warp are
+// TMA-LOADED into the same staging tiles at the start of the tile (one mbarrier per warp, `res_bar`), long before the
+// accumulator is ready; a thread then reads its own row (4 ld.shared.v4), adds, and writes the result back IN PLACE.
 template <bool SPLIT_OUT>
 __device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const CUtensorMap* tmO, uint32_t stg_s, uint32_t bias_s,
                                                    int bar_id, uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t aph,
-                                                   uint32_t t_row, int lane, int wg_tid, int row0, int n0, uint32_t as) {
+                                                   uint32_t t_row, int lane, int wg_tid, int row0, int n0, uint32_t as,
+                                                   const CUtensorMap* tmR = nullptr, uint64_t* res_bar = nullptr,
+                                                   uint32_t res_phase = 0) {
   const bool has_bias = (p.flags & AITB_EPI_BIAS) != 0;
   const bool relu = (p.flags & AITB_EPI_RELU) != 0;
+  const bool has_res = !SPLIT_OUT && (p.flags & AITB_EPI_RES) != 0;
+  const bool res_relu = (p.flags & AITB_EPI_RES_RELU) != 0;
   const bool of16 = SPLIT_OUT && p.out_f16 != 0;
   const bool hi_only = SPLIT_OUT && (p.flags & AITB_EPI_HI_ONLY) != 0;
   const uint32_t bias_buf = bias_s + as * 512u;
-  if (lane == 0) bulk_wait_read_all();            // the previous tile's stores no longer read the staging tiles
+  if (lane == 0) {
+    bulk_wait_read_all();                         // the previous tile's stores no longer read the staging tiles
+    if (has_res) {                                // residual tiles -> the staging tiles (rows >= M are zero-filled by TMA)
+      mbar_arrive_expect_tx(res_bar, 4 * 2048);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(stg_s + (uint32_t)c * 2048u)), tmR, res_bar, n0 + c * 32, row0);
+    }
+  }
   if (has_bias) {
     const float b = __ldg(p.bias + n0 + wg_tid);
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_buf + (uint32_t)wg_tid * 4u), "f"(b) : "memory");
@@ -731,10 +746,29 @@ __device__ __forceinline__ void epilogue_fast_tile(const GemmKParams& p, const C
     } else {
       const uint32_t tile = stg_s + (uint32_t)c * 2048u;
       const uint32_t rowb = tile + (uint32_t)lane * 64u;
+      bool relu_c = relu;
+      if (has_res) {
+        if (c == 0) mbar_wait(res_bar, res_phase);
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 r = lds128(rowb + (((uint32_t)j ^ sw) << 4));
+          const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[8 * j + 2 * e] += __uint_as_float(rw[e] << 16);
+            v[8 * j + 2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+          }
+        }
+        relu_c = res_relu;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 x;
-        if (relu) {
+        if (relu_c) {
           x.x = pack_bf16x2_relu(v[8 * j], v[8 * j + 1]); x.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
           x.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]); x.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
         } else {
@@ -1092,13 +1126,13 @@ static constexpr int k2SmemBytes = 6 * (kABytes + k2HalfB) + 1024 + 256 + 8 * 40
 // | 8 warps x 4 staging tiles (64 KB) | barriers | 2 warpgroups x 2 x 512 B bias slices.
 static constexpr int k2FastStages = 5;
 // (no alignment slack: the dynamic shared memory of this kernel is declared __align__(1024); checked at run time)
-static constexpr int k2FastSmemBytes = k2FastStages * (kABytes + k2HalfB) + 8 * 8192 + 128 + 2048;
+static constexpr int k2FastSmemBytes = k2FastStages * (kABytes + k2HalfB) + 8 * 8192 + 256 + 2048;
 static_assert(k2FastSmemBytes <= 232448, "fast 2-CTA kernel exceeds the 227 KB shared-memory limit");
 
 template <typename T, bool SPLIT, bool SIMPLE = false, bool FAST = false, bool ONEPASS = false>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const GemmKParams p) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
   static_assert(!FAST || (!SIMPLE && sizeof(T) == 2 && (!SPLIT || ONEPASS)), "FAST epilogue: plain bf16, or the one-pass split variant");
   static_assert(!ONEPASS || SPLIT, "ONEPASS: the one-pass variant of the split (two-plane) configuration");
   constexpr bool SPLIT_IN = SPLIT && !ONEPASS;   // stages hold both planes, three MMAs per K slice
@@ -1120,6 +1154,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_full = bars + 2 * k2Stages;  // [kAcc]      (local in each CTA)
   uint64_t* acc_empty = acc_full + kAcc;     // [kAcc]      (used in the leader)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+  uint64_t* res_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bars) + 128);   // FAST: [8] one per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1128,7 +1163,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (FAST) tma_prefetch_desc(&tmO);
+    if constexpr (FAST) {
+      tma_prefetch_desc(&tmO);
+      if (p.flags & AITB_EPI_RES) tma_prefetch_desc(&tmR);
+      for (int s = 0; s < 8; ++s) mbar_init(&res_bars[s], 1);
+    }
     for (int s = 0; s < k2Stages; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&empty_bar[s], 1);
@@ -1235,10 +1274,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t aph = (lt / kAcc) & 1;
       const uint32_t t_row = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
       if constexpr (FAST) {
-        const uint32_t bias_s = smem_u32(smem + k2Stages * k2StageBytes + 8 * 8192 + 128) + (uint32_t)half * 1024u;
+        const uint32_t bias_s = smem_u32(smem + k2Stages * k2StageBytes + 8 * 8192 + 256) + (uint32_t)half * 1024u;
         epilogue_fast_tile<SPLIT>(p, &tmO, smem_u32(stg), bias_s, 1 + half, &acc_full[as], &acc_empty[as], aph,
                            t_row + (uint32_t)(half * 128), lane, q * 32 + lane, (mp * 2 + (int)rank) * kBlockM + q * 32,
-                           nt * BLOCK_N + half * 128, as);
+                           nt * BLOCK_N + half * 128, as, &tmR, &res_bars[warp - 4], lt & 1u);
       } else {
         epilogue_tile<T, BLOCK_N, false, SPLIT, 128, 2, SIMPLE>(p, stg, nullptr, nullptr, &acc_full[as], t_row, q, lane,
                                                                 mp * 2 + (int)rank, nt * BLOCK_N, as, aph, rank, half * 128,
@@ -1366,7 +1405,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 template <typename T, bool SPLIT, bool SIMPLE, bool FAST = false, bool ONEPASS = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& kp,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const CUtensorMap* tmR = nullptr) {
   static SmemAttrOnce once;
   auto kern = gemm2_tcgen05_kernel<T, SPLIT, SIMPLE, FAST, ONEPASS>;
   constexpr int k2SmemBytes = FAST ? k2FastSmemBytes : aitb::k2SmemBytes;
@@ -1386,7 +1425,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR ? *tmR : tmA, kp);
   if (e != cudaSuccess) {
     set_error("gemm2_tcgen05_kernel: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -1595,16 +1634,24 @@ int gemm_run(const aitb_gemm_desc* d, cudaStream_t stream) {
     if (simple) return launch_gemm2<float, false, true>(tmA, tmB, tmA, kp, stream);
     // bf16 outputs, rows = GEMM rows, epilogue at most bias + ReLU: the TMA-store fast epilogue (A/B: AITB_NO_FAST_EPI=1)
     static const bool fast_on = getenv("AITB_NO_FAST_EPI") == nullptr;
-    const bool fast_shape = fast_on && kp.a_m_dim != 2 && kp.rows_in == kp.rows_out &&
-                            (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_HI_ONLY)) == 0 &&
-                            (((uintptr_t)d->out) & 15) == 0 && ((size_t)d->ldo * 2) % 16 == 0;
-    if (fast_shape && d->dtype == AITB_BF16 && kp.acc_scale == 1.f) {
-      CUtensorMap tmO;
+    const bool fast_base = fast_on && kp.a_m_dim != 2 && kp.rows_in == kp.rows_out &&
+                           (((uintptr_t)d->out) & 15) == 0 && ((size_t)d->ldo * 2) % 16 == 0;
+    const bool fast_shape = fast_base && (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_HI_ONLY)) == 0;
+    // plain bf16 also takes a (row-for-row) residual with the optional ReLU after it: the layer-4 conv3 launches
+    const bool fast_res = fast_base && d->dtype == AITB_BF16 && (d->flags & AITB_EPI_RES) != 0 &&
+                          (d->flags & ~(AITB_EPI_BIAS | AITB_EPI_RELU | AITB_EPI_RES | AITB_EPI_RES_RELU)) == 0 &&
+                          kp.res_div == 1 && kp.res_rep == 1 && (((uintptr_t)d->res) & 15) == 0 && ((size_t)d->ldr * 2) % 16 == 0;
+    if ((fast_shape || fast_res) && d->dtype == AITB_BF16 && kp.acc_scale == 1.f) {
+      CUtensorMap tmO, tmR;
       const uint64_t odims[2] = {(uint64_t)d->N, (uint64_t)d->M};
       const uint64_t ostr[1] = {(uint64_t)d->ldo * 2};
       const uint32_t obox[2] = {32u, 32u};
       if (encode_map(&tmO, AITB_BF16, d->out, 2, odims, ostr, obox, "O", true)) return 1;
-      return launch_gemm2<__nv_bfloat16, false, false, true>(tmA, tmB, tmO, kp, stream);
+      if (fast_res) {
+        const uint64_t rstr[1] = {(uint64_t)d->ldr * 2};
+        if (encode_map(&tmR, AITB_BF16, d->res, 2, odims, rstr, obox, "R", true)) return 1;
+      }
+      return launch_gemm2<__nv_bfloat16, false, false, true>(tmA, tmB, tmO, kp, stream, fast_res ? &tmR : nullptr);
     }
     if (fast_shape && onepass) {   // two 16-bit planes per row: hi at column 0, lo at column ldo
       CUtensorMap tmO;

@@ -213,3 +213,27 @@ def test_attn_core_tcgen05_variant(mode, split, monkeypatch):
         got = out.float().cpu()
         tol = dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(got.double(), ref, **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M", [1000, 128 * 6, 4096 + 37])
+@pytest.mark.parametrize("res_relu", [True, False])
+def test_gemm_bias_residual_relu_two_cta(dtype, M, res_relu):
+    """layer-4 conv3 shape (N = 2048, K = 512): bias + row-for-row residual (+ ReLU after it).  bf16 takes the TMA-store fast
+    epilogue with the TMA-loaded residual tile (ragged M: TMA zero-fills / clips the rows past M); guard rows stay untouched."""
+    from ait_b200 import _lib as L, ops
+    N, K = 2048, 512
+    g = torch.Generator().manual_seed(M)
+    a = _prep(torch.randn(M, K, generator=g), dtype)
+    w = _prep(torch.randn(N, K, generator=g) / K ** 0.5, dtype)
+    bias = torch.randn(N, generator=g)
+    res = _prep(torch.randn(M, N, generator=g), dtype)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    if res_relu:
+        ref = F.relu(ref)
+    out = torch.full((M + 2, N), 5.0, dtype=dtype, device=DEV)
+    flags = L.EPI_BIAS | L.EPI_RES | (L.EPI_RES_RELU if res_relu else 0)
+    ops.gemm(a.to(DEV, dtype), w.to(DEV, dtype), out, M=M, N=N, K=K, block_n=256, flags=flags, bias=bias.to(DEV),
+             res=res.to(DEV, dtype), ldr=N)
+    assert bool((out[M:].float() == 5.0).all()), "rows past M were written"
+    torch.testing.assert_close(out[:M].float().cpu().double(), ref, **_tol(dtype))

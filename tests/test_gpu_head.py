@@ -276,3 +276,25 @@ def test_modules_on_a_non_current_device():
     keep = nms(boxes[0, :500].to(d1), scores[0, :500].to(d1), 0.5)
     assert keep.device == torch.device(d1) and keep.numel() > 0
     assert torch.cuda.current_device() == 0
+
+
+def test_pipeline_cuda_graph_replay_matches_eager():
+    """DetectionPipeline(graph=True): proposal tail + head captured once per shape and replayed; identical results to the
+    eager launches, also for new inputs of the same shape."""
+    from ait_b200 import synth
+    from ait_b200.pipeline import DetectionPipeline
+    head, _ = golden_head()
+    head = head.to(DEV)
+    B, P = 2, 20
+    pipe_g = DetectionPipeline(head, 6000, P, 0.7, graph=True)
+    pipe_e = DetectionPipeline(head, 6000, P, 0.7, graph=False)
+    for first in (0, 7, 0):
+        non_img = torch.stack([synth.c4_map(first + u) for u in range(B)]).to(DEV)
+        non_qry = torch.stack([synth.query_feat(first + u) for u in range(B)]).to(DEV)
+        data = [synth.rpn_outputs(first + u) for u in range(B)]
+        boxes, scores = torch.stack([d[0] for d in data]).to(DEV), torch.stack([d[1] for d in data]).to(DEV)
+        re, ce, be = pipe_e(non_img, non_qry, boxes, scores)
+        rg, cg, bg = pipe_g(non_img, non_qry, boxes, scores)
+        torch.cuda.synchronize()
+        assert torch.equal(rg, re) and torch.equal(cg, ce) and torch.equal(bg, be)
+    assert len(pipe_g._captured) == 1
