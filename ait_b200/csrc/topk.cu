@@ -147,15 +147,15 @@ topk_rank_kernel(const int32_t* __restrict__ cand_count, const unsigned long lon
 // = one pass of counting sort + tiny insertion ranks instead of the 91 barrier-separated stages of an 8192-key bitonic
 // network (80 us -> see DESIGN).  The result is the same total order (score desc, index asc), independent of any atomics'
 // arrival order.  Degenerate score distributions (all candidates in one bucket) stay exact, just slower (nc^2 / 1024
-// compares per thread).  Images with more than kBucketCap candidates set `fallback[b]` and are left to the kernels above.
+// compares per thread).  Images with more than kBucketCap candidates keep their segments in global memory (`spill`).
 // ---------------------------------------------------------------------------------------------
 static constexpr int kBucketCap = 16384;
 static constexpr int kBuckets = 1024;
 
 __global__ void __launch_bounds__(1024)
 topk_bucket_kernel(const float* __restrict__ scores, int n_total, int n, int64_t* __restrict__ order,
-                   int32_t* __restrict__ fallback) {
-  extern __shared__ __align__(16) unsigned long long seg[];    // [kBucketCap]
+                   unsigned long long* __restrict__ spill) {
+  extern __shared__ __align__(16) unsigned long long seg_s[];  // [kBucketCap]
   __shared__ int hist[4096];
   __shared__ int bcnt[kBuckets], bbase[kBuckets], bfill[kBuckets];
   __shared__ int chunk_sum[32], wsum[32];
@@ -194,11 +194,9 @@ topk_bucket_kernel(const float* __restrict__ scores, int n_total, int n, int64_t
   }
   __syncthreads();
   const int thr = s_thr, nc = s_nc;
-  if (nc > kBucketCap) {                // uniform
-    if (tid == 0) fallback[b] = 1;
-    return;
-  }
-  if (tid == 0) fallback[b] = 0;
+  // the bucket segments live in shared memory; an image with more than kBucketCap candidates (a threshold bin crowded with
+  // equal-ish scores) spills them to the caller's workspace instead -- same algorithm, L2 latency on the rank reads
+  unsigned long long* seg = nc <= kBucketCap ? seg_s : spill + (size_t)b * n_total;
   const uint32_t kmin = (uint32_t)thr << 20;
   const uint32_t range = s_kmax - kmin;               // >= 0: the largest key is a candidate
   int shift = 0;
@@ -278,17 +276,17 @@ int topk_run(const float* scores, int B, int n_total, int n, int64_t* order, voi
   int32_t* fallback = reinterpret_cast<int32_t*>(w);
   w += al256((size_t)B * 4);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(w);
-  // fused bucket kernel first (A/B: AITB_TOPK_NO_BUCKET=1); the three-kernel path below then only works on the images it
-  // flagged (more than kBucketCap candidates) and returns at once for the others
+  // the fused bucket kernel (default); AITB_TOPK_NO_BUCKET=1: the round-1 histogram / compact / bitonic(+rank) kernels (A/B)
   static const bool use_bucket = getenv("AITB_TOPK_NO_BUCKET") == nullptr;
   if (use_bucket) {
     static SmemAttrOnce bonce;
     const int bsmem = kBucketCap * 8;
     if (ensure_dyn_smem((const void*)topk_bucket_kernel, bsmem, bonce, "topk_bucket_kernel")) return 1;
-    topk_bucket_kernel<<<B, 1024, bsmem, stream>>>(scores, n_total, n, order, fallback);
-    if (check_launch("topk_bucket_kernel")) return 1;
+    topk_bucket_kernel<<<B, 1024, bsmem, stream>>>(scores, n_total, n, order, cand);
+    return check_launch("topk_bucket_kernel");
   }
-  topk_hist_kernel<<<B, 1024, 0, stream>>>(scores, n_total, n, thr_bin, cand_count, use_bucket ? fallback : nullptr);
+  (void)fallback;
+  topk_hist_kernel<<<B, 1024, 0, stream>>>(scores, n_total, n, thr_bin, cand_count, nullptr);
   if (check_launch("topk_hist_kernel")) return 1;
   topk_compact_kernel<<<dim3((n_total + 255) / 256, B), 256, 0, stream>>>(scores, n_total, thr_bin, cand_count, cand);
   if (check_launch("topk_compact_kernel")) return 1;

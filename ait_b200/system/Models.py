@@ -122,6 +122,10 @@ class _AITTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.saved is None:      # the activation buffer (GBs) is released after the first backward, like autograd's own buffers
+            raise RuntimeError("ait_b200.Transformer: trying to backward through the AIT training step a second time: its "
+                               "saved activations were freed after the first backward (retain_graph=True is not supported; "
+                               "run the forward again)")
         g_props, g_query, g_params = ctx.engine.ait_backward(grad_out, ctx.saved, ctx.bs, ctx.num_props,
                                                              token_major_grad=ctx.tm_out)
         ctx.saved = None

@@ -73,6 +73,21 @@ def test_topk_with_ties_is_stable():
             assert np.array_equal(order[b], ref)
 
 
+def test_topk_crowded_threshold_bin_spills_and_stays_exact():
+    """all scores inside ONE bin of the 12-bit histogram (so every score is a candidate: 30 000 > the 16 384 the fused kernel keeps
+    in shared memory -> bucket segments spill to the workspace), and a heavily tied distribution (a few distinct values: one bucket
+    holds thousands of keys, ranks by counting)."""
+    from ait_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    s = 0.5 + 0.04 * torch.rand(2, 30000, generator=g)
+    s[1] = (torch.randint(0, 4, (30000,), generator=g).float() + 1.0) / 8.0          # four distinct values
+    for n in (6000, 20000, 30000):
+        order = ops.topk_desc(s.to(DEV), n).cpu().numpy()
+        for b in range(2):
+            ref = np.argsort(-s[b].double().numpy(), kind="stable")[:n]
+            assert np.array_equal(order[b], ref)
+
+
 @pytest.mark.parametrize("scales,pre,post", [((8, 16, 32), 6000, 300), ((4, 8, 16, 32), 12000, 2000)])
 def test_proposal_tail_matches_oracle_bit_exact(scales, pre, post):
     """rows a1+a2: rois [B, post, 5] identical to the reference loop (proposal_layer.py:129-166)."""

@@ -55,6 +55,10 @@ w_sk = torch.randn(512, 64, device=dev) * 0.1
 b_sk = torch.zeros(512, device=dev)
 ao = buf(G * 64, 64)
 cb = 1 if split else 1  # column offsets below are in storage elements of the hi plane
+sk_in = act(torch.randn(G * 64, 1024, device=dev)).view(G, 64, -1)
+sk_w = act(torch.randn(1024, 1280, device=dev) / 1280 ** 0.5)
+sk_out = buf(G * 64, 1024).view(G, 64, -1)
+b1024 = torch.zeros(1024, device=dev)
 if split:
     x512_16 = ops.split_planes(torch.randn(M, 512, device=dev), f16=True)
     wqkv_16 = ops.split_planes(torch.randn(1536, 512, device=dev) / 512 ** 0.5, f16=True)
@@ -83,6 +87,10 @@ for _ in range(reps):
     else:
         ops.roi_align_forward(nhwc, rois.view(-1, 5), 1 / 16.0, 7, 7, 0, token_major=True)
     propose_rois(boxes, scores)
+    # the grouped SKBlock convolutions as one dual-accumulator GEMM (gemm_tcgen05_kernel<.., 128, 0, SPLIT>: 9 shifted 3x3 taps + the
+    # 1x1 centre tap, relu^2 sum epilogue) on the proposal maps [G, 8, 8, 1024]
+    ops.gemm(sk_in, sk_w, sk_out, M=G * 64, N=1024, K=128, block_n=128, view="map", map_args=(1024, 8, 8, 1, G), taps=9,
+             group_c=128, flags=L.EPI_BIAS | L.EPI_RELU | L.EPI_SQUARE | L.EPI_DUAL, bias=b1024, dual=True, bias2=b1024, split=split)
     if split:   # precision plan: the one-pass variants (fp16 hi planes) of the encoder QKV projection and the FFN w_2 GEMM
         ops.gemm(x512_16, wqkv_16, qkv_out, M=M, N=1536, K=512, block_n=256, split=True, passes=1, in_f16=True)
         ops.gemm(hid, w2_16, o512, M=M, N=512, K=2048, block_n=512, flags=L.EPI_BIAS | L.EPI_RES | L.EPI_LN, bias=b512,
