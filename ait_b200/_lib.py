@@ -81,6 +81,7 @@ class HeadWeights(C.Structure):
         ("w_bbox", C.c_void_p), ("b_bbox", C.c_void_p),
         ("w_cls1", C.c_void_p), ("b_cls1", C.c_void_p),
         ("w_cls2", C.c_void_p), ("b_cls2", C.c_void_p),
+        ("p_drop", C.c_float), ("p_attn", C.c_float), ("drop_seed", C.c_ulonglong),
     ]
 
 
@@ -155,6 +156,8 @@ SIGNATURES = {
     "aitb_ait_backward_tm": (_i, [C.POINTER(HeadWeights), _vp, _i, _i, _vp, _sz, C.POINTER(AITGrads), _vp, _vp, _vp, _sz,
                                   _vp]),
     "aitb_ait_saved_offset": (_sz, [_i, _i, _i]),
+    "aitb_dropout_mask": (_i, [C.c_float, C.c_ulonglong, _i, _i, _vp, _vp]),
+    "aitb_attn_dropout_mask": (_i, [C.c_float, C.c_ulonglong, _i, _i, _vp, _vp]),
     "aitb_anchor_target_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "aitb_anchor_target_assign": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aitb_anchor_target_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libaitb200.so")
-SOURCES = ["capi.cu", "gemm.cu", "attn.cu", "nms.cu", "topk.cu", "roi_align.cu", "heads.cu", "bwd.cu", "boxes.cu", "coatt.cu", "attn_tc.cu", "targets.cu", "fc_ln.cu", "heads_train.cu", "train_aux.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "attn.cu", "nms.cu", "topk.cu", "roi_align.cu", "heads.cu", "bwd.cu", "boxes.cu", "coatt.cu", "attn_tc.cu", "targets.cu", "fc_ln.cu", "heads_train.cu", "train_aux.cu", "dropout.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -152,7 +152,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnThreads, 4)
 attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
                  int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, int mask_mode, int n_keys,
-                 T* __restrict__ out, int round_tf, int kv_rows) {
+                 T* __restrict__ out, int round_tf, int kv_rows, DropCfg dc) {
   __shared__ __align__(16) __half Qs[kT * kHS];
   __shared__ __align__(16) __half Ks[kT * kHS];
   __shared__ __align__(16) __half Vs[kT * kHS];
@@ -179,6 +179,7 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
     __syncthreads();
     float p[8][4];
     scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
+    if (dc.thr) drop_frag(dc, grp, h, row0, p);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       float c0 = p[nt][0] + p[nt][2], c1 = p[nt][1] + p[nt][3];
@@ -245,6 +246,7 @@ attn_core_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restric
     __syncthreads();
     float p[8][4];
     scores_softmax(Qs, Ks, row0, mask_mode, n_keys, p);
+    if (dc.thr) drop_frag(dc, grp, h, row0, p);
     float oh[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) oh[nt][0] = oh[nt][1] = oh[nt][2] = oh[nt][3] = 0.f;
@@ -591,8 +593,14 @@ int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v,
 // 64 - kv_rows readable finite rows after the last pair)
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
-                  int round_tf, int kv_rows) {
+                  int round_tf, int kv_rows, const DropCfg* drop) {
   AITB_REQUIRE(G > 0, "aitb_attn_core: G must be positive");
+  DropCfg dc;
+  dc.scale = 1.f; dc.thr = dc.k0 = dc.k1 = 0u;
+  if (drop && drop->thr) {
+    AITB_REQUIRE(dtype == AITB_F32, "aitb_attn_core: attention dropout exists in the training (fp32-storage) path only");
+    dc = *drop;
+  }
   AITB_REQUIRE(q && k && v && w_sk && b_sk && out, "aitb_attn_core: null pointer");
   AITB_REQUIRE(q_rep >= 1, "aitb_attn_core: q_rep must be >= 1");
   AITB_REQUIRE(mask_mode == 0 || mask_mode == 1, "aitb_attn_core: mask_mode must be 0 (key padding) or 1 (causal)");
@@ -611,12 +619,12 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
   if (dtype == AITB_F32) {
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
-                                                            (float*)out, round_tf, kv_rows);
+                                                            (float*)out, round_tf, kv_rows, dc);
   } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || want_two_pass)) {
     // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch)
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
-        mask_mode, n_keys, (__nv_bfloat16*)out, 0, kv_rows);
+        mask_mode, n_keys, (__nv_bfloat16*)out, 0, kv_rows, dc);
   } else if (dtype == AITB_BF16) {   // one-pass kernel, plain bf16 planes, persistent CTAs (128 accumulator registers per thread)
     static SmemAttrOnce once;
     if (ensure_dyn_smem((const void*)attn_core_split_kernel<false>, OnePass<false>::kSmem, once, "attn_core one-pass")) return 1;

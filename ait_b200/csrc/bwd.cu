@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 2)
 attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __restrict__ k, const float* __restrict__ v,
                 int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, const float* __restrict__ dout,
                 int mask_mode, int n_keys, float* __restrict__ dq, int lddq, float* __restrict__ dk,
-                float* __restrict__ dv, int lddkv, float* __restrict__ dz_out, float* __restrict__ s_out) {
+                float* __restrict__ dv, int lddkv, float* __restrict__ dz_out, float* __restrict__ s_out, DropCfg dc) {
   extern __shared__ __align__(16) float bsm[];
   float* sQ = bsm;
   float* sK = sQ + kBT * kBS;
@@ -376,9 +376,10 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
     float p[8][4], o[8][4];
     mm64<false, false>(sQ, sK, row0, p);            // S = Q K^T
     softmax_frag(p, row0, mask_mode, n_keys);
+    if (dc.thr) drop_frag(dc, grp, h, row0, p);     // P' = dropout(P): the forward's draws (attn.cu)
     frag_to_smem(p, sP, row0);
     __syncwarp();
-    mm64<false, true>(sP, sV, row0, o);             // O_h = P V   (only this warp's rows of P are read)
+    mm64<false, true>(sP, sV, row0, o);             // O_h = P' V   (only this warp's rows of P' are read)
     frag_colsum(o, part);
     __syncthreads();
     if (tid < kBT) s_acc += part[tid] + part[kBT + tid] + part[2 * kBT + tid] + part[3 * kBT + tid];
@@ -453,17 +454,20 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
                                                                   tf32r(d4.z * g4.z + s4.z), tf32r(d4.w * g4.w + s4.w));
     }
     __syncthreads();
-    float p[8][4], dp[8][4];
+    float p[8][4], pm[8][4], dp[8][4];
     mm64<false, false>(sQ, sK, row0, p);
     softmax_frag(p, row0, mask_mode, n_keys);
-    frag_to_smem(p, sP, row0);
-    mm64<false, false>(sX, sV, row0, dp);           // dP = dO_h V^T
-    // dS = P * (dP - rowsum(dP * P))
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { pm[nt][0] = p[nt][0]; pm[nt][1] = p[nt][1]; pm[nt][2] = p[nt][2]; pm[nt][3] = p[nt][3]; }
+    if (dc.thr) drop_frag(dc, grp, h, row0, pm);    // P' = P * M (M = mask / (1 - p_drop)); pm == p without dropout
+    frag_to_smem(pm, sP, row0);
+    mm64<false, false>(sX, sV, row0, dp);           // dP' = dO_h V^T;  dP = dP' * M
+    // dS = P * (dP - rowsum(dP * P)) = P' * dP' - P * rowsum(dP' * P')
     float r_lo = 0.f, r_hi = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      r_lo += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
-      r_hi += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+      r_lo += dp[nt][0] * pm[nt][0] + dp[nt][1] * pm[nt][1];
+      r_hi += dp[nt][2] * pm[nt][2] + dp[nt][3] * pm[nt][3];
     }
     r_lo += __shfl_xor_sync(0xffffffffu, r_lo, 1);
     r_lo += __shfl_xor_sync(0xffffffffu, r_lo, 2);
@@ -471,15 +475,15 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
     r_hi += __shfl_xor_sync(0xffffffffu, r_hi, 2);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      dp[nt][0] = p[nt][0] * (dp[nt][0] - r_lo); dp[nt][1] = p[nt][1] * (dp[nt][1] - r_lo);
-      dp[nt][2] = p[nt][2] * (dp[nt][2] - r_hi); dp[nt][3] = p[nt][3] * (dp[nt][3] - r_hi);
+      dp[nt][0] = pm[nt][0] * dp[nt][0] - p[nt][0] * r_lo; dp[nt][1] = pm[nt][1] * dp[nt][1] - p[nt][1] * r_lo;
+      dp[nt][2] = pm[nt][2] * dp[nt][2] - p[nt][2] * r_hi; dp[nt][3] = pm[nt][3] * dp[nt][3] - p[nt][3] * r_hi;
     }
     __syncthreads();                                // every warp is done reading sX (dO_h) as the A operand of dP ...
     // dV_h = P^T dO_h needs sX (dO_h) and sP from all warps; dS goes to a separate tile: reuse sQ? no -- Q is
     // still needed for dK.  Write dS over sDS = sX only after dV is done; so: dV first.
     {
       float dvf[8][4];
-      mm64<true, true>(sP, sX, row0, dvf);          // [j, c] = sum_t P[t, j] dO[t, c]
+      mm64<true, true>(sP, sX, row0, dvf);          // [j, c] = sum_t P'[t, j] dO[t, c]
       store_frag(dvf, dv + (size_t)grp * kBT * lddkv + h * kBT, lddkv, row0, 1.f);
     }
     __syncthreads();
@@ -501,14 +505,17 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
 
 int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
                  const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
-                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream) {
+                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream, const DropCfg* drop) {
+  DropCfg dc;
+  dc.scale = 1.f; dc.thr = dc.k0 = dc.k1 = 0u;
+  if (drop && drop->thr) dc = *drop;
   AITB_REQUIRE(G > 0 && q && k && v && w_sk && b_sk && dout && dq && dk && dv && dz && s_out, "aitb_attn_bwd: bad arguments");
   AITB_REQUIRE(q_rep >= 1 && (mask_mode == 0 || mask_mode == 1) && n_keys >= 1 && n_keys <= kBT, "aitb_attn_bwd: bad mode");
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && lddq % 2 == 0 && lddkv % 2 == 0, "aitb_attn_bwd: bad leading dimensions");
   static SmemAttrOnce once;
   if (ensure_dyn_smem((const void*)attn_bwd_kernel, kAttnBwdSmem, once, "attn_bwd_kernel")) return 1;
   attn_bwd_kernel<<<G, kAttnBwdThreads, kAttnBwdSmem, stream>>>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, mask_mode,
-                                                               n_keys, dq, lddq, dk, dv, lddkv, dz, s_out);
+                                                               n_keys, dq, lddq, dk, dv, lddkv, dz, s_out, dc);
   return check_launch("attn_bwd_kernel");
 }
 

@@ -28,7 +28,7 @@ int roi_align_bwd_run(const float* grad, const float* rois, int B, int C, int H,
                       int pw, int sampling_ratio, float* gfeat, cudaStream_t stream);
 int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
                   const float* b_sk, int G, int mask_mode, int n_keys, int dtype, void* out, cudaStream_t stream,
-                  int round_tf = 0, int kv_rows = 64);
+                  int round_tf = 0, int kv_rows = 64, const DropCfg* drop = nullptr);
 int pool_heads_run(const void* top, int dtype, int G, int P, const float* qfeat, const float* w_bbox,
                    const float* b_bbox, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* feat_out, float* bbox_out, float* cls_out, cudaStream_t stream);
@@ -43,7 +43,12 @@ int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStrea
 int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t stream);
 int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
                  const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
-                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream);
+                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream, const DropCfg* drop = nullptr);
+int drop_res_ln_run(float* z, const float* pos, int grp, int valid, const float* res, int res_div, int res_rep, const float* gamma,
+                    const float* beta, float eps, float p, unsigned long long seed, int site, int rows, int round_tf,
+                    float* rstd_out, cudaStream_t st);
+int drop_bwd_run(const float* dx, float* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
+                 cudaStream_t st);
 
 int rpn_decode_run(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,
                    int B, int A, int H, int W, float feat_stride, float* proposals, float* fg_scores, cudaStream_t st);
@@ -362,6 +367,18 @@ static int side_stream(SideStream** out) {
   return 0;
 }
 
+// training-mode dropout of aitb_ait_forward_train / aitb_ait_backward (aitb_head_weights.p_drop / p_attn / drop_seed); every
+// nn.Dropout of the reference's Transformer is a SITE with its own Philox key; the inference entry points pass nullptr
+struct TrainDrop {
+  float p, p_attn;
+  unsigned long long seed;
+  DropCfg attn(int site) const { return make_drop(p_attn, seed, site); }
+};
+static bool train_drop_of(const aitb_head_weights* w, TrainDrop& td) {
+  td.p = w->p_drop; td.p_attn = w->p_attn; td.seed = w->drop_seed;
+  return td.p > 0.f || td.p_attn > 0.f;
+}
+
 #define RUN(expr)        \
   do {                   \
     if ((expr)) return 1; \
@@ -376,8 +393,20 @@ static int side_stream(SideStream** out) {
 static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* qbuf, int ldq, int q_rep,
                      const void* kbuf, const void* vbuf, int ldkv, int G, int mask_mode, int n_keys, void* ao,
                      const void* res, int res_rep, void* out, cudaStream_t st, float* rstd = nullptr, int out_rows = 64,
-                     int kv_rows = 64, int res_f16 = 0, int out_f16 = 0) {
+                     int kv_rows = 64, int res_f16 = 0, int out_f16 = 0, const TrainDrop* td = nullptr, int site_attn = 0,
+                     int site_fc = 0) {
   const int dt = w->dtype;
+  if (td) {   // training with dropout (fp32 storage, 64-row layout): P <- dropout(P) inside the attention core, then
+              // q = LayerNorm(dropout(fc(q)) + residual) as GEMM + one streaming kernel (dropout.cu)
+    const DropCfg da = td->attn(site_attn);
+    RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st, w->round_tf32,
+                      kv_rows, &da));
+    aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 256, out, 512, 0);
+    view_plain(d, ao, 64);
+    RUN(gemm_run(&d, st));
+    return drop_res_ln_run((float*)out, nullptr, 64, 64, (const float*)res, 64, res_rep, m.ln.gamma, m.ln.beta, 1e-6f, td->p,
+                           td->seed, site_fc, G * 64, w->round_tf32, rstd, st);
+  }
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32, kv_rows));
   // fc (64 -> 512, no bias) + residual + LayerNorm   (SubLayers.py:97-100)
@@ -409,7 +438,8 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
 
 // onepass (precision plan, AITB_F32S): x, the hidden tensor and the output are fp16 planes, both GEMMs run one pass
 static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* x, int M, void* hidden, void* out,
-                     cudaStream_t st, float* rstd = nullptr, bool onepass = false) {
+                     cudaStream_t st, float* rstd = nullptr, bool onepass = false, const TrainDrop* td = nullptr,
+                     int site = 0) {
   const int dt = w->dtype;
   aitb_gemm_desc d1 = gemm_base(dt, M, 2048, 512, f.w1.w, 256, hidden, 2048, w->round_tf32);
   view_plain(d1, x, 512);
@@ -423,6 +453,15 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
   aitb_gemm_desc d2 = gemm_base(dt, M, 512, 2048, f.w2.w, 512, out, 512, w->round_tf32);
   if (onepass) { d2.passes = 1; d2.in_f16 = 1; d2.out_f16 = 1; d2.res_f16 = 1; }
   view_plain(d2, hidden, 2048);
+  if (td) {   // x = LayerNorm(dropout(w_2(.) + b_2) + residual)   (SubLayers.py:181-185)
+    d2.round_tf32 = 0;
+    d2.block_n = 256;             // 512 is the LayerNorm variant
+    d2.flags = AITB_EPI_BIAS;
+    d2.bias = f.w2.bias;
+    RUN(gemm_run(&d2, st));
+    return drop_res_ln_run((float*)out, nullptr, 64, 64, (const float*)x, 64, 1, f.ln.gamma, f.ln.beta, 1e-6f, td->p, td->seed,
+                           site, M, w->round_tf32, rstd, st);
+  }
   d2.flags = AITB_EPI_BIAS | AITB_EPI_RES | AITB_EPI_LN;
   d2.bias = f.w2.bias;
   d2.res = x;
@@ -436,25 +475,34 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
 // Decoder part that does not depend on the proposals (system/Models.py:250-253 repeats the
 // query per proposal): dec_emb + pos + LN, causal self-attention block, cross-attention query projection.
 // Computed once per unit on the side stream while the encoder runs.
-static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaStream_t st) {
+static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaStream_t st, const TrainDrop* td = nullptr) {
   const int dt = w->dtype, cb = colsize(dt), rt = w->round_tf32;
   const int RQ = B * 64;
   aitb_gemm_desc d = gemm_base(dt, RQ, 512, 1024, w->dec_emb.w, 512, hb.T0, 512, rt);
   view_plain(d, hb.qtok, 1024);
-  d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
   d.bias = w->dec_emb.bias;
-  d.pos = w->dec_pos;
-  d.pos_rows = 64;
-  d.gamma = w->dec_ln.gamma;
-  d.beta = w->dec_ln.beta;
-  d.ln_rstd = hb.r_T0;
-  RUN(gemm_run(&d, st));
+  if (td) {   // dec_output = LayerNorm(dropout(emb + pos))   (Models.py:152-153)
+    d.round_tf32 = 0;
+    d.block_n = 256;
+    d.flags = AITB_EPI_BIAS;
+    RUN(gemm_run(&d, st));
+    RUN(drop_res_ln_run((float*)hb.T0, w->dec_pos, 64, 64, nullptr, 64, 1, w->dec_ln.gamma, w->dec_ln.beta, 1e-6f, td->p,
+                        td->seed, AITB_DROP_DEC_EMB, RQ, rt, hb.r_T0, st));
+  } else {
+    d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
+    d.pos = w->dec_pos;
+    d.pos_rows = 64;
+    d.gamma = w->dec_ln.gamma;
+    d.beta = w->dec_ln.beta;
+    d.ln_rstd = hb.r_T0;
+    RUN(gemm_run(&d, st));
+  }
   aitb_gemm_desc dq = gemm_base(dt, RQ, 1536, 512, w->dec_slf.w_qkv, 256, hb.QKVd, 1536, rt);
   view_plain(dq, hb.T0, 512);
   RUN(gemm_run(&dq, st));
   const uint8_t* qkv = (const uint8_t*)hb.QKVd;
   RUN(mha_block(w, w->dec_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, B, 1, 64, hb.AOd, hb.T0, 1,
-                hb.T1, st, hb.r_T1));
+                hb.T1, st, hb.r_T1, 64, 64, 0, 0, td, AITB_DROP_DEC_SLF_ATTN, AITB_DROP_DEC_SLF_FC));
   aitb_gemm_desc dc = gemm_base(dt, RQ, 512, 512, w->dec_enc.w_qkv, 256, hb.Qc, 512, rt);
   view_plain(dc, hb.T1, 512);
   return gemm_run(&dc, st);
@@ -466,7 +514,7 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
 // everywhere and never read as queries again: SURVEY fact 7, bit-identical output), so the encoder FFN and the
 // cross-attention K / V projection run on 49 rows per pair.  The training path keeps the 64-row layout.
 static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void* enc_tap, cudaStream_t st,
-                    cudaEvent_t query_ready, bool compact = true) {
+                    cudaEvent_t query_ready, bool compact = true, const TrainDrop* td = nullptr) {
   const int dt = w->dtype, eb = esize(dt), cb = colsize(dt), rt = w->round_tf32;
   const int bp = B * P, R = bp * 64;
   const int er = compact ? 49 : 64, RE = bp * er;   // encoder rows per pair / in total after the self-attention block
@@ -477,18 +525,28 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
   {
     aitb_gemm_desc d = gemm_base(dt, bp * 49, 512, 1024, w->enc_emb.w, 512, hb.X1, 512, rt);
     view_plain(d, hb.pooled, 1024);
-    d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
     d.bias = w->enc_emb.bias;
-    d.pos = w->enc_pos;
-    d.pos_rows = 64;
     d.rows_in = 49;
     d.rows_out = 64;
-    d.gamma = w->enc_ln.gamma;
-    d.beta = w->enc_ln.beta;
-    d.ln_rstd = hb.r_X1;
-    if (plan) { d.passes = 1; d.in_f16 = 1; d.out_f16 = 1; }
-    RUN(gemm_run(&d, st));
-    RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st, plan ? 1 : 0));
+    if (td) {   // enc_output = LayerNorm(dropout(emb + pos)) (Models.py:98-99); the 15 zero-padded rows of a pair are dropped too
+                // (LayerNorm(dropout(pos_t))): as queries of the self-attention they enter its head gate (mean over all 64 rows)
+      d.round_tf32 = 0;
+      d.block_n = 256;
+      d.flags = AITB_EPI_BIAS;
+      RUN(gemm_run(&d, st));
+      RUN(drop_res_ln_run((float*)hb.X1, w->enc_pos, 64, 49, nullptr, 64, 1, w->enc_ln.gamma, w->enc_ln.beta, 1e-6f, td->p,
+                          td->seed, AITB_DROP_ENC_EMB, R, rt, hb.r_X1, st));
+    } else {
+      d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
+      d.pos = w->enc_pos;
+      d.pos_rows = 64;
+      d.gamma = w->enc_ln.gamma;
+      d.beta = w->enc_ln.beta;
+      d.ln_rstd = hb.r_X1;
+      if (plan) { d.passes = 1; d.in_f16 = 1; d.out_f16 = 1; }
+      RUN(gemm_run(&d, st));
+      RUN(ln_pad_rows(hb.X1, dt, bp, 49, w->enc_pos, w->enc_ln, rt, st, plan ? 1 : 0));
+    }
   }
   // ---- encoder self-attention
   {
@@ -498,9 +556,9 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     RUN(gemm_run(&d, st));
     const uint8_t* qkv = (const uint8_t*)hb.QKV;
     RUN(mha_block(w, w->enc_slf, qkv, 1536, 1, qkv + 512 * cb, qkv + 1024 * cb, 1536, bp, 0, 49, hb.AO, hb.X1, 1,
-                  hb.X2, st, hb.r_X2, er, 64, plan ? 1 : 0, plan ? 1 : 0));
+                  hb.X2, st, hb.r_X2, er, 64, plan ? 1 : 0, plan ? 1 : 0, td, AITB_DROP_ENC_SLF_ATTN, AITB_DROP_ENC_SLF_FC));
   }
-  RUN(ffn_block(w, w->enc_ffn, hb.X2, RE, hb.Hh, hb.ENC, st, hb.r_ENC, plan));
+  RUN(ffn_block(w, w->enc_ffn, hb.X2, RE, hb.Hh, hb.ENC, st, hb.r_ENC, plan, td, AITB_DROP_ENC_FFN));
   if (enc_tap) {   // [bp, 64, 512] tap: the rows that exist (pad rows of the tap are left untouched when compact)
     cudaError_t e = cudaMemcpy2DAsync(enc_tap, (size_t)64 * 512 * eb, hb.ENC, (size_t)er * 512 * eb, (size_t)er * 512 * eb, bp,
                                       cudaMemcpyDeviceToDevice, st);
@@ -523,9 +581,9 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
     }
     const uint8_t* kv = (const uint8_t*)hb.KVc;
     RUN(mha_block(w, w->dec_enc, hb.Qc, 512, P, kv, kv + 512 * cb, 1024, bp, 0, 49, hb.AOc, hb.T1, P, hb.D1, st,
-                  hb.r_D1, 64, er));
+                  hb.r_D1, 64, er, 0, 0, td, AITB_DROP_DEC_ENC_ATTN, AITB_DROP_DEC_ENC_FC));
   }
-  RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh2, hb.DEC, st, hb.r_DEC));
+  RUN(ffn_block(w, w->dec_ffn, hb.D1, R, hb.Hh2, hb.DEC, st, hb.r_DEC, false, td, AITB_DROP_DEC_FFN));
   // ---- dec_trans (1x1 conv 512->1024 + bias); token-major output == NHWC of [bp,1024,8,8]
   {
     aitb_gemm_desc d = gemm_base(dt, R, 1024, 512, w->dec_trans.w, 256, hb.AIT, 1024, rt);
@@ -683,16 +741,25 @@ struct FfnBwd {
   const aitb_ffn* w;
   const aitb_ffn_g* g;
   const float *x, *hid, *y, *rstd;   // saved: input [R,512], hidden [R,2048], output (post-LN) [R,512], 1/sigma
+  const TrainDrop* td;               // dropout between w_2 and the residual add (NULL / p == 0: none)
+  int site;
+  float* gz;                         // [R,512] scratch: the masked gradient of the w_2 output
 };
 
 // backward of y = LN(relu(x W1^T + b1) W2^T + b2 + x); gy -> gx (both [R, 512]); gf / gh are scratch
 static int ffn_backward(const FfnBwd& f, int R, const float* gy, float* gf, float* gh, float* gx, float* w1t, float* w2t,
                         cudaStream_t st) {
   RUN(ln_bwd_run(gy, f.y, f.w->ln.gamma, f.w->ln.beta, f.rstd, R, 64, 64, gf, f.g->ln.gamma, f.g->ln.beta, st));
-  RUN(colsum_run(gf, 512, R, 512, f.g->w2.bias, st));
-  RUN(wgrad_run(gf, 512, f.hid, 2048, R, 512, 2048, f.g->w2.w, 2048, st));
+  // gf = gradient of (dropout(z) + x): the residual path (last line) takes it as is, the w_2 path through the mask
+  const float* gz = gf;
+  if (f.td && f.td->p > 0.f) {
+    RUN(drop_bwd_run(gf, f.gz, f.td->p, f.td->seed, f.site, R, 64, 64, st));
+    gz = f.gz;
+  }
+  RUN(colsum_run(gz, 512, R, 512, f.g->w2.bias, st));
+  RUN(wgrad_run(gz, 512, f.hid, 2048, R, 512, 2048, f.g->w2.w, 2048, st));
   RUN(transpose_w(f.w->w2.w, 512, 2048, w2t, st));                       // [2048, 512]
-  RUN(dgrad(gf, R, 512, 2048, w2t, gh, AITB_EPI_RELU_MASK, f.hid, 2048, st));
+  RUN(dgrad(gz, R, 512, 2048, w2t, gh, AITB_EPI_RELU_MASK, f.hid, 2048, st));
   RUN(colsum_run(gh, 2048, R, 2048, f.g->w1.bias, st));
   RUN(wgrad_run(gh, 2048, f.x, 512, R, 2048, 512, f.g->w1.w, 512, st));
   RUN(transpose_w(f.w->w1.w, 2048, 512, w1t, st));                       // [512, 2048]
@@ -715,7 +782,7 @@ size_t aitb_ait_saved_bytes(int B, int P) {
 size_t aitb_ait_backward_workspace_bytes(int B, int P) {
   const size_t bp = (size_t)B * P, R = bp * 64, RQ = (size_t)B * 64;
   // per-row widths of the gradient buffers taken in aitb_ait_backward (+ transposed weights, attention dz / s)
-  size_t n = R * (1024 + 512 + 512 + 2048 + 512 + 512 + 64 + 512 + 1024 + 512 + 512 + 512 + 64 + 1536 + 512) +
+  size_t n = R * (1024 + 512 + 512 + 2048 + 512 + 512 + 64 + 512 + 1024 + 512 + 512 + 512 + 64 + 1536 + 512 + 512 /* dropout */) +
              bp * 49 * (512 + 1024) + RQ * (512 * 6 + 64 + 1536 + 1024) + 2 * (bp + B) * (512 + 64) +
              (size_t)4 * 1024 * 1024 /* largest W^T pair */;
   return n * 4 + 64 * 1024 /* alignment slack of ~40 buffers */ + 1024;
@@ -739,8 +806,11 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
                       1024, 49, 1, st, w->round_tf32));
   }
   RUN(transpose_run(x_query, AITB_F32, hb.qtok, AITB_F32, B, 1024, 64, 1, st, w->round_tf32));
-  RUN(ait_query_side(w, hb, B, st));
-  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr, false));
+  TrainDrop td;
+  const bool drop = train_drop_of(w, td);
+  AITB_REQUIRE(td.p >= 0.f && td.p < 1.f && td.p_attn >= 0.f && td.p_attn < 1.f, "aitb_ait_forward_train: dropout probabilities must be in [0, 1)");
+  RUN(ait_query_side(w, hb, B, st, drop ? &td : nullptr));
+  RUN(ait_core(w, hb, B, P, nullptr, st, nullptr, false, drop ? &td : nullptr));
   // out_nchw == NULL: the caller consumes the token-major result in place (aitb_ait_saved_offset(B, P, 1)) -- no NCHW copy
   for (int g0 = 0; out_nchw && g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
@@ -784,8 +854,15 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   const float* S_AOc = (const float*)hb.AOc; const float* S_D1 = (const float*)hb.D1; const float* S_H2 = (const float*)hb.Hh2;
   const float* S_DEC = (const float*)hb.DEC;
 
+  TrainDrop td;
+  const bool drop = train_drop_of(w, td);
+  const TrainDrop* tdp = drop ? &td : nullptr;
+  const bool dp = drop && td.p > 0.f;       // the row-wise sites (the attention-probability sites follow p_attn)
+  const DropCfg da_enc = td.attn(AITB_DROP_ENC_SLF_ATTN), da_dec = td.attn(AITB_DROP_DEC_SLF_ATTN),
+                da_x = td.attn(AITB_DROP_DEC_ENC_ATTN);
   float* wta = f((size_t)2048 * 1024);   // transposed-weight scratch (two slots)
   float* wtb = f((size_t)2048 * 1024);
+  float* gZ = dp ? f((size_t)R * 512) : nullptr;   // masked copy of a LayerNorm-input gradient (one site at a time)
   // ---- dec_trans: AIT = DEC Wt^T + b
   float* gAIT_buf = f((size_t)R * 1024);
   const float* gAIT = grad_token_major ? grad_out_nchw : gAIT_buf;   // token-major: already [bp*64, 1024], tf32-rounded
@@ -804,17 +881,22 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   float* gH = f((size_t)R * 2048);
   float* gD1 = f((size_t)R * 512);
   {
-    FfnBwd fb{&w->dec_ffn, &g->dec_ffn, S_D1, S_H2, S_DEC, hb.r_DEC};
+    FfnBwd fb{&w->dec_ffn, &g->dec_ffn, S_D1, S_H2, S_DEC, hb.r_DEC, tdp, AITB_DROP_DEC_FFN, gZ};
     RUN(ffn_backward(fb, R, gDEC, gF, gH, gD1, wta, wtb, st));
   }
   // ---- cross attention: D1 = LN(AOc Wfc^T + T1[unit])
   float* gC1 = f((size_t)R * 512);
   RUN(ln_bwd_run(gD1, S_D1, w->dec_enc.ln.gamma, w->dec_enc.ln.beta, hb.r_D1, R, 64, 64, gC1, g->dec_enc.ln.gamma,
                  g->dec_enc.ln.beta, st));
-  RUN(wgrad_run(gC1, 512, S_AOc, 64, R, 512, 64, g->dec_enc.w_fc, 64, st));
+  const float* gC1m = gC1;                                               // gradient of fc's output: through the dropout mask
+  if (dp) {
+    RUN(drop_bwd_run(gC1, gZ, td.p, td.seed, AITB_DROP_DEC_ENC_FC, R, 64, 64, st));
+    gC1m = gZ;
+  }
+  RUN(wgrad_run(gC1m, 512, S_AOc, 64, R, 512, 64, g->dec_enc.w_fc, 64, st));
   float* gAO = f((size_t)R * 64);
   RUN(transpose_w(w->dec_enc.w_fc, 512, 64, wta, st));                   // [64, 512]
-  RUN(dgrad(gC1, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
+  RUN(dgrad(gC1m, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
   float* gT1res = f((size_t)RQ * 512);
   RUN(bsum_run(gC1, B, P, 64 * 512, gT1res, st));                        // residual T1 is shared by the unit's P pairs
   float* dQpp = f((size_t)R * 512);
@@ -822,7 +904,7 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   float* dz = f((size_t)(bp + B) * 512);
   float* sv = f((size_t)(bp + B) * 64);
   RUN(attn_bwd_run(S_Qc, 512, P, S_KVc, S_KVc + 512, 1024, w->dec_enc.w_sk, w->dec_enc.b_sk, gAO, bp, 0, 49, dQpp, 512,
-                   gKVc, gKVc + 512, 1024, dz, sv, st));
+                   gKVc, gKVc + 512, 1024, dz, sv, st, &da_x));
   RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->dec_enc.w_sk, 64, st));
   RUN(colsum_run(dz, 512, bp, 512, g->dec_enc.b_sk, st));
   float* gQc = f((size_t)RQ * 512);
@@ -840,19 +922,24 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   // ---- encoder FFN
   float* gX2 = f((size_t)R * 512);
   {
-    FfnBwd fb{&w->enc_ffn, &g->enc_ffn, S_X2, S_H1, S_ENC, hb.r_ENC};
+    FfnBwd fb{&w->enc_ffn, &g->enc_ffn, S_X2, S_H1, S_ENC, hb.r_ENC, tdp, AITB_DROP_ENC_FFN, gZ};
     RUN(ffn_backward(fb, R, gENC, gF, gH, gX2, wta, wtb, st));
   }
   // ---- encoder self attention: X2 = LN(AO Wfc^T + X1)
   float* gA1 = f((size_t)R * 512);
   RUN(ln_bwd_run(gX2, S_X2, w->enc_slf.ln.gamma, w->enc_slf.ln.beta, hb.r_X2, R, 64, 64, gA1, g->enc_slf.ln.gamma,
                  g->enc_slf.ln.beta, st));
-  RUN(wgrad_run(gA1, 512, S_AO, 64, R, 512, 64, g->enc_slf.w_fc, 64, st));
+  const float* gA1m = gA1;
+  if (dp) {
+    RUN(drop_bwd_run(gA1, gZ, td.p, td.seed, AITB_DROP_ENC_SLF_FC, R, 64, 64, st));
+    gA1m = gZ;
+  }
+  RUN(wgrad_run(gA1m, 512, S_AO, 64, R, 512, 64, g->enc_slf.w_fc, 64, st));
   RUN(transpose_w(w->enc_slf.w_fc, 512, 64, wta, st));
-  RUN(dgrad(gA1, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
+  RUN(dgrad(gA1m, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
   float* gQKV = f((size_t)R * 1536);
   RUN(attn_bwd_run(S_QKV, 1536, 1, S_QKV + 512, S_QKV + 1024, 1536, w->enc_slf.w_sk, w->enc_slf.b_sk, gAO, bp, 0, 49, gQKV,
-                   1536, gQKV + 512, gQKV + 1024, 1536, dz, sv, st));
+                   1536, gQKV + 512, gQKV + 1024, 1536, dz, sv, st, &da_enc));
   RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->enc_slf.w_sk, 64, st));
   RUN(colsum_run(dz, 512, bp, 512, g->enc_slf.b_sk, st));
   RUN(wgrad_run(gQKV, 1536, S_X1, 512, R, 1536, 512, g->enc_slf.w_qkv, 512, st));
@@ -862,6 +949,7 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   // ---- encoder input: X1 = LN(enc_emb(pooled) + b + pos) on the 49 real rows (pad rows: LN(pos) -> dgamma / dbeta only)
   float* gE0 = f((size_t)R49 * 512);
   RUN(ln_bwd_run(gX1, S_X1, w->enc_ln.gamma, w->enc_ln.beta, hb.r_X1, R, 64, 49, gE0, g->enc_ln.gamma, g->enc_ln.beta, st));
+  if (dp) RUN(drop_bwd_run(gE0, gE0, td.p, td.seed, AITB_DROP_ENC_EMB, R, 64, 49, st));   // in place, compact 49-row layout
   RUN(colsum_run(gE0, 512, R49, 512, g->enc_emb.bias, st));
   RUN(wgrad_run(gE0, 512, S_pooled, 1024, R49, 512, 1024, g->enc_emb.w, 1024, st));
   float* gPooled = f((size_t)R49 * 1024);
@@ -876,15 +964,20 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   float* gS1 = f((size_t)RQ * 512);
   RUN(ln_bwd_run(gT1, S_T1, w->dec_slf.ln.gamma, w->dec_slf.ln.beta, hb.r_T1, RQ, 64, 64, gS1, g->dec_slf.ln.gamma,
                  g->dec_slf.ln.beta, st));
-  RUN(wgrad_run(gS1, 512, S_AOd, 64, RQ, 512, 64, g->dec_slf.w_fc, 64, st));
+  const float* gS1m = gS1;
+  if (dp) {
+    RUN(drop_bwd_run(gS1, gZ, td.p, td.seed, AITB_DROP_DEC_SLF_FC, RQ, 64, 64, st));
+    gS1m = gZ;
+  }
+  RUN(wgrad_run(gS1m, 512, S_AOd, 64, RQ, 512, 64, g->dec_slf.w_fc, 64, st));
   float* gAOd = f((size_t)RQ * 64);
   RUN(transpose_w(w->dec_slf.w_fc, 512, 64, wta, st));
-  RUN(dgrad(gS1, RQ, 512, 64, wta, gAOd, 0, nullptr, 0, st));
+  RUN(dgrad(gS1m, RQ, 512, 64, wta, gAOd, 0, nullptr, 0, st));
   float* gQKVd = f((size_t)RQ * 1536);
   float* dzd = dz + (size_t)bp * 512;
   float* svd = sv + (size_t)bp * 64;
   RUN(attn_bwd_run(S_QKVd, 1536, 1, S_QKVd + 512, S_QKVd + 1024, 1536, w->dec_slf.w_sk, w->dec_slf.b_sk, gAOd, B, 1, 64, gQKVd,
-                   1536, gQKVd + 512, gQKVd + 1024, 1536, dzd, svd, st));
+                   1536, gQKVd + 512, gQKVd + 1024, 1536, dzd, svd, st, &da_dec));
   RUN(wgrad_run(dzd, 512, svd, 64, B, 512, 64, g->dec_slf.w_sk, 64, st));
   RUN(colsum_run(dzd, 512, B, 512, g->dec_slf.b_sk, st));
   RUN(wgrad_run(gQKVd, 1536, S_T0, 512, RQ, 1536, 512, g->dec_slf.w_qkv, 512, st));
@@ -893,6 +986,7 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   RUN(dgrad(gQKVd, RQ, 1536, 512, wta, gT0, AITB_EPI_RES, gS1, 512, st));
   float* gQ0 = f((size_t)RQ * 512);
   RUN(ln_bwd_run(gT0, S_T0, w->dec_ln.gamma, w->dec_ln.beta, hb.r_T0, RQ, 64, 64, gQ0, g->dec_ln.gamma, g->dec_ln.beta, st));
+  if (dp) RUN(drop_bwd_run(gQ0, gQ0, td.p, td.seed, AITB_DROP_DEC_EMB, RQ, 64, 64, st));
   RUN(colsum_run(gQ0, 512, RQ, 512, g->dec_emb.bias, st));
   RUN(wgrad_run(gQ0, 512, S_qtok, 1024, RQ, 512, 1024, g->dec_emb.w, 1024, st));
   float* gQtok = f((size_t)RQ * 1024);

@@ -453,6 +453,60 @@ __device__ __forceinline__ float2 unpack_plane2(uint32_t x, bool f16) {
   return make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Counter-based random numbers (Philox4x32-10) and the dropout element rules shared by the training forward, the
+// backward and the mask-materialisation kernels of the tests.  A value is KEPT iff its 32-bit draw >= thr = p * 2^32
+// and then scaled by 1 / (1 - p) (nn.Dropout).  Nothing is stored: forward and backward regenerate the same draws.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+struct DropCfg {
+  float scale;       // 1 / (1 - p); 0 thr = dropout off
+  uint32_t thr;      // p * 2^32
+  uint32_t k0, k1;   // Philox key: the step's 64-bit seed, the site folded into k0
+};
+__host__ __device__ inline DropCfg make_drop(float p, unsigned long long seed, int site) {
+  DropCfg d;
+  if (!(p > 0.f)) { d.scale = 1.f; d.thr = 0u; d.k0 = d.k1 = 0u; return d; }
+  d.scale = 1.f / (1.f - p);
+  d.thr = (uint32_t)((double)p * 4294967296.0);
+  d.k0 = (uint32_t)seed ^ (0x9E3779B9u * (uint32_t)(site + 1));
+  d.k1 = (uint32_t)(seed >> 32);
+  return d;
+}
+// row-wise sites (LayerNorm inputs): the four draws of columns 4 * cq .. 4 * cq + 3 of row `row`
+__device__ __forceinline__ uint4 drop_row_draw(const DropCfg& d, uint32_t row, uint32_t cq) {
+  return philox4x32_10(make_uint4(row, cq, 0xD509u, 0u), make_uint2(d.k0, d.k1));
+}
+// attention probabilities: the four draws of an mma C fragment -- rows (r_lo, r_lo + 8), columns (2 cp, 2 cp + 1) of head h of
+// pair grp; r_lo has bit 3 clear
+__device__ __forceinline__ uint4 drop_attn_draw(const DropCfg& d, uint32_t grp, uint32_t h, uint32_t r_lo, uint32_t cp) {
+  return philox4x32_10(make_uint4(grp, h, (r_lo << 8) | cp, 0xA77Eu), make_uint2(d.k0, d.k1));
+}
+__device__ __forceinline__ float drop_mul(const DropCfg& d, uint32_t draw) { return draw >= d.thr ? d.scale : 0.f; }
+// training-mode dropout of the attention probabilities (system/Modules.py:24) on an mma C fragment of a warp's 16 rows
+// (p[nt][0..3]: rows row0 + g, + 8; columns nt * 8 + 2 t, + 1): p <- p * mask / (1 - p_drop).  Forward (attn.cu, both passes)
+// and backward (bwd.cu) regenerate the same draws from (pair, head, row, column pair).
+__device__ __forceinline__ void drop_frag(const DropCfg& dc, int grp, int h, int row0, float (&p)[8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const uint4 d = drop_attn_draw(dc, (uint32_t)grp, (uint32_t)h, (uint32_t)(row0 + g), (uint32_t)(nt * 4 + t));
+    p[nt][0] *= drop_mul(dc, d.x); p[nt][1] *= drop_mul(dc, d.y);
+    p[nt][2] *= drop_mul(dc, d.z); p[nt][3] *= drop_mul(dc, d.w);
+  }
+}
+
 // load / store 8 consecutive activation elements (16-byte aligned for bf16, 32 for fp32)
 __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);

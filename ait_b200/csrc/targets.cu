@@ -242,18 +242,6 @@ anchor_subsample_kernel(int8_t* __restrict__ labels, int total, const uint8_t* _
 // uniform 32-bit key; "a uniformly random subset of size k" = the k smallest keys (radix select in shared memory),
 // "rand * n with replacement" = a key per output slot.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
 __device__ __forceinline__ uint32_t cand_key(uint64_t seed, int image, int list, int idx) {
   return philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)image, (uint32_t)list, 0x5eedu),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x;

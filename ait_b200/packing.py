@@ -246,6 +246,31 @@ class HeadEngine:
                                       ".layer_norm.bias")]
         return names
 
+    def set_train_dropout(self, p_drop=0.0, p_attn=0.0, seed=0):
+        """Dropout of the training step (aitb_head_weights.p_drop / p_attn / drop_seed): forward and backward of one step
+        read the same three values and regenerate the same masks; the inference entry points ignore them."""
+        self.w.p_drop, self.w.p_attn, self.w.drop_seed = float(p_drop), float(p_attn), int(seed)
+
+    def dropout_masks(self, bs, P, device):
+        """The multipliers (0 | 1 / (1 - p)) of every dropout site of the current (p_drop, p_attn, seed), materialised for
+        parity tests: {site name: tensor}; row-wise sites [rows, 512], attention sites [G, 8, 64, 64]."""
+        lib = L.load()
+        bp = bs * P
+        rows = {"enc_emb": (1, bp * 64), "dec_emb": (2, bs * 64), "enc_slf_fc": (3, bp * 64), "dec_slf_fc": (4, bs * 64),
+                "dec_enc_fc": (5, bp * 64), "enc_ffn": (6, bp * 64), "dec_ffn": (7, bp * 64)}
+        attn = {"enc_slf_attn": (8, bp), "dec_slf_attn": (9, bs), "dec_enc_attn": (10, bp)}
+        out = {}
+        with torch.cuda.device(device):
+            for name, (site, n) in rows.items():
+                t = torch.empty((n, 512), dtype=torch.float32, device=device)
+                L.check(lib.aitb_dropout_mask(self.w.p_drop, self.w.drop_seed, site, n, L.ptr(t), L.stream_ptr()))
+                out[name] = t
+            for name, (site, g) in attn.items():
+                t = torch.empty((g, 8, 64, 64), dtype=torch.float32, device=device)
+                L.check(lib.aitb_attn_dropout_mask(self.w.p_attn, self.w.drop_seed, site, g, L.ptr(t), L.stream_ptr()))
+                out[name] = t
+        return out
+
     def ait_forward_train(self, x_props, x_query, token_major_out=False):
         """Transformer.forward keeping the activations the backward needs -> (out, saved buffer).
         token_major_out: no NCHW copy -- `out` is the [bp,64,1024] token-major, tf32-rounded result living inside the saved

@@ -60,6 +60,9 @@ class MultiHeadAttention(_Holder):
         self.fc = nn.Linear(d_v, d_model, bias=False)
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
         self.p_dropout = dropout
+        # ScaledDotProductAttention(temperature, attn_dropout=0.1): SubLayers.py:55 never forwards `dropout`, so the
+        # attention-probability dropout is 0.1 in .train() whatever the constructor says (Modules.py:9-14,24)
+        self.p_attn_dropout = 0.1
 
 
 class PositionwiseFeedForward(_Holder):
@@ -106,14 +109,27 @@ class Decoder(_Holder):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
 
 
+def set_dropout(module, p=None, p_attn=None):
+    """Set the training-mode dropout probabilities of every AIT sub-layer below `module` (a Transformer or anything that
+    contains one): p -> the nn.Dropout sites, p_attn -> the attention probabilities (the reference hard-wires 0.1 there).
+    set_dropout(m, 0.0, 0.0) gives the deterministic training graph (BASELINE configs[3] numbers, the gradient goldens)."""
+    for mod in module.modules():
+        if p is not None and hasattr(mod, "p_dropout"):
+            mod.p_dropout = float(p)
+        if p_attn is not None and hasattr(mod, "p_attn_dropout"):
+            mod.p_attn_dropout = float(p_attn)
+    return module
+
+
 class _AITTrainFunction(torch.autograd.Function):
     """Transformer.forward with a hand-written backward (libaitb200: tcgen05 dgrad / wgrad GEMMs, LayerNorm /
     attention / selective-head-gate backward kernels).  The reference relies on torch autograd over
     system/Models.py:231-280; gradients match it to tf32 accuracy (tests/test_gpu_train.py)."""
 
     @staticmethod
-    def forward(ctx, x_props, x_query, module, tm_out, *params):
+    def forward(ctx, x_props, x_query, module, tm_out, drop, *params):
         engine = packing.HeadEngine(transformer=module, dtype="tf32")     # weights change every step: repack
+        engine.set_train_dropout(*drop)             # (p_drop, p_attn, seed): the backward regenerates the same masks
         out, saved = engine.ait_forward_train(x_props, x_query, token_major_out=tm_out)
         ctx.engine, ctx.saved, ctx.tm_out = engine, saved, tm_out
         ctx.bs, ctx.num_props = x_query.shape[0], x_props.shape[0] // x_query.shape[0]
@@ -129,7 +145,7 @@ class _AITTrainFunction(torch.autograd.Function):
         g_props, g_query, g_params = ctx.engine.ait_backward(grad_out, ctx.saved, ctx.bs, ctx.num_props,
                                                              token_major_grad=ctx.tm_out)
         ctx.saved = None
-        return (g_props.to(ctx.in_dtypes[0]), g_query.to(ctx.in_dtypes[1]), None, None) + tuple(g_params)
+        return (g_props.to(ctx.in_dtypes[0]), g_query.to(ctx.in_dtypes[1]), None, None, None) + tuple(g_params)
 
 
 class Transformer(nn.Module):
@@ -140,7 +156,7 @@ class Transformer(nn.Module):
 
     def __init__(self, src_pad_idx=1, trg_pad_idx=1, d_word_vec=512, d_model=512, d_inner=2048, n_layers=6,
                  n_head=8, d_k=64, d_v=64, dropout=0.1, n_position=200, trg_emb_prj_weight_sharing=True,
-                 emb_src_trg_weight_sharing=True, compute_dtype=torch.float32):
+                 emb_src_trg_weight_sharing=True, compute_dtype=torch.float32, attn_dropout=None):
         super().__init__()
         if d_model != d_word_vec:
             raise AssertionError("To facilitate the residual connections, the dimensions of all module "
@@ -167,6 +183,27 @@ class Transformer(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
         self._engine = None
+        self.last_dropout_seed = 0
+        if attn_dropout is not None:       # not a reference argument: the reference hard-wires 0.1 (Modules.py:9)
+            for m in self.modules():
+                if hasattr(m, "p_attn_dropout"):
+                    m.p_attn_dropout = float(attn_dropout)
+
+    def _draw_dropout(self):
+        """(p_drop, p_attn, seed) of one training step.  The engine has ONE probability per kind: every holder must agree."""
+        ps = {float(m.p_dropout) for m in self.modules() if hasattr(m, "p_dropout")}
+        pa = {float(m.p_attn_dropout) for m in self.modules() if hasattr(m, "p_attn_dropout")}
+        if len(ps) != 1 or len(pa) != 1:
+            raise RuntimeError("ait_b200.Transformer: all sub-layers must share one dropout / one attention-dropout "
+                               "probability (got %s / %s)" % (sorted(ps), sorted(pa)))
+        p, p_attn = ps.pop(), pa.pop()
+        if not (0.0 <= p < 1.0 and 0.0 <= p_attn < 1.0):
+            raise RuntimeError("ait_b200.Transformer: dropout probabilities must be in [0, 1)")
+        seed = 0
+        if p > 0.0 or p_attn > 0.0:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        self.last_dropout_seed = seed
+        return (p, p_attn, seed)
 
     def invalidate(self):
         """Call after changing parameters in place (load_state_dict does it automatically)."""
@@ -185,10 +222,13 @@ class Transformer(nn.Module):
         (token_major_out, training step only: the [bs*num_props, 64, 1024] token-major, tf32-rounded result without the NCHW
         copy, for `sk_train.sknet_train(..., channels_last_in=True)`; its gradient comes back in the same layout)
         (Models.py:231-280).  .eval(): inference engine (no autograd graph, dropout = identity, like the reference in
-        .eval()).  .train() with dropout = 0.0: differentiable training step with the library's own backward."""
-        if self.training and any(m.p_dropout > 0 for m in self.modules() if hasattr(m, "p_dropout")):
-            raise RuntimeError("ait_b200.Transformer: training-mode dropout is not implemented in the fused "
-                               "engine; call .eval() (or construct with dropout=0.0, BASELINE config 4)")
+        .eval()).  .train(): differentiable training step with the library's own backward; dropout as in the reference's
+        .train(): p = `dropout` at the seven nn.Dropout sites (Models.py:98,152; SubLayers.py:97,182) and 0.1 on the attention
+        probabilities (Modules.py:24; `attn_dropout=` overrides it, 0.0 for a deterministic graph).  The masks come from
+        a counter-based generator keyed by a per-step seed drawn from torch's CPU generator (torch.manual_seed makes a
+        run reproducible; `last_dropout_seed` records it); the decoder-side sites draw ONE mask per unit, shared by the
+        unit's proposals, because the query side runs once per unit (the reference recomputes it, with fresh masks, per
+        proposal)."""
         if x_props.dim() != 4 or x_query.dim() != 4:
             raise RuntimeError("expected x_props [bp,1024,7,7] and x_query [bs,1024,8,8]")
         bp, c_p, h_p, w_p = x_props.shape
@@ -204,7 +244,7 @@ class Transformer(nn.Module):
             # tf32 tensor-core math
             sd = dict(self.named_parameters())
             params = [sd[n] for n in packing.HeadEngine.ait_param_names()]
-            return _AITTrainFunction.apply(x_props, x_query, self, bool(token_major_out), *params)
+            return _AITTrainFunction.apply(x_props, x_query, self, bool(token_major_out), self._draw_dropout(), *params)
         if token_major_out:
             raise RuntimeError("ait_b200.Transformer: token_major_out is a training-step hand-over (module in .train(), grad enabled)")
         fp = packing.fingerprint(self)          # in-place parameter updates since the last packing?

@@ -281,7 +281,26 @@ typedef struct {
   const float* b_cls1;
   const float* w_cls2; /* [2, 8] */
   const float* b_cls2;
+  /* training-mode dropout, read by aitb_ait_forward_train / aitb_ait_backward only (every inference entry point ignores
+   * them = the reference in .eval()).  p_drop: the nn.Dropout(dropout) sites (Models.py:98,152; SubLayers.py:97,182);
+   * p_attn: the attention-probability dropout (Modules.py:9,24 -- always 0.1 in the reference's .train()); drop_seed: the
+   * step's seed -- forward and backward of one step must see the same three values.  All zero = no dropout. */
+  float p_drop;
+  float p_attn;
+  unsigned long long drop_seed;
 } aitb_head_weights;
+
+/* dropout sites (one Philox key per site; aitb_dropout_mask / aitb_attn_dropout_mask materialise a site's multipliers) */
+#define AITB_DROP_ENC_EMB 1      /* rows [bp*64] (incl. the 15 zero-padded rows of a pair: they feed the self-attention's head gate) */
+#define AITB_DROP_DEC_EMB 2      /* rows [B*64]: ONE mask per unit, shared by the unit's P pairs (the query side runs once) */
+#define AITB_DROP_ENC_SLF_FC 3   /* rows [bp*64] */
+#define AITB_DROP_DEC_SLF_FC 4   /* rows [B*64] */
+#define AITB_DROP_DEC_ENC_FC 5   /* rows [bp*64] */
+#define AITB_DROP_ENC_FFN 6      /* rows [bp*64] */
+#define AITB_DROP_DEC_FFN 7      /* rows [bp*64] */
+#define AITB_DROP_ENC_SLF_ATTN 8 /* [bp, 8, 64, 64] */
+#define AITB_DROP_DEC_SLF_ATTN 9 /* [B, 8, 64, 64] */
+#define AITB_DROP_DEC_ENC_ATTN 10 /* [bp, 8, 64, 64] */
 
 typedef struct {
   /* optional taps of intermediates for parity tests (NULL = skip); all in `dtype` unless noted */
@@ -402,7 +421,7 @@ int aitb_attn_bwd(const float* q, int ldq, int q_rep, const float* k, const floa
 
 /* AIT training step (config 4): Transformer.forward with the activations the backward needs kept in `saved`
  * (caller-owned, aitb_ait_saved_bytes), then the backward producing the gradients of both inputs and of all
- * parameters the forward uses.  dtype must be AITB_F32; dropout is not modelled (p = 0, as config 4 states). */
+ * parameters the forward uses.  dtype must be AITB_F32; dropout follows aitb_head_weights.p_drop / p_attn / drop_seed. */
 typedef struct { float* w; float* bias; } aitb_linear_g;
 typedef struct { float* gamma; float* beta; } aitb_lnorm_g;
 typedef struct { float* w_qkv; float* w_sk; float* b_sk; float* w_fc; aitb_lnorm_g ln; } aitb_mha_g;
@@ -430,6 +449,14 @@ size_t aitb_ait_saved_offset(int B, int P, int which);
 int aitb_ait_backward_tm(const aitb_head_weights* w, const float* grad_out_tm, int B, int P, const void* saved,
                          size_t saved_bytes, const aitb_ait_grads* grads, float* grad_props, float* grad_query,
                          void* workspace, size_t workspace_bytes, aitb_stream_t stream);
+
+/* Dropout masks of one training step, materialised for parity tests: the multipliers (0 or 1 / (1 - p)) the training
+ * forward / backward regenerate on the fly from (seed, site, element index) with Philox4x32-10 -- nothing is stored by the
+ * step itself.  The reference's own masks come from torch's generator state and cannot be reproduced; parity is checked by
+ * injecting THESE masks into the oracle (tests/test_gpu_train.py).
+ *   aitb_dropout_mask: out [rows, 512] fp32 of a row-wise site;  aitb_attn_dropout_mask: out [G, 8, 64, 64] fp32 */
+int aitb_dropout_mask(float p, unsigned long long seed, int site, int rows, float* out, aitb_stream_t stream);
+int aitb_attn_dropout_mask(float p, unsigned long long seed, int site, int G, float* out, aitb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4  training-only samplers and losses (ait_b200/csrc/targets.cu)

@@ -28,11 +28,14 @@ def _cast(sd, dtype):
 # ------------------------------------------------------------------------------------------------
 # AIT  (lib/model/system/Models.py, Layers.py, SubLayers.py, Modules.py)
 # ------------------------------------------------------------------------------------------------
-def _attention(q, k, v, mask):
-    """ScaledDotProductAttention.forward (system/Modules.py:16-29), temperature = sqrt(64) = 8."""
+def _attention(q, k, v, mask, drop=None):
+    """ScaledDotProductAttention.forward (system/Modules.py:16-29), temperature = sqrt(64) = 8.
+    drop: the multipliers (0 | 1 / (1 - p)) nn.Dropout would apply to the probabilities in .train() (:24), injected."""
     attn = torch.matmul(q / 8.0, k.transpose(2, 3))
     attn = attn.masked_fill(mask == 0, -1e9)
     attn = F.softmax(attn, dim=-1)
+    if drop is not None:
+        attn = attn * drop
     return torch.matmul(attn, v)
 
 
@@ -46,29 +49,53 @@ def _sh_block(x, w):
     return x * g
 
 
-def _mha(w, q_in, k_in, v_in, mask):
-    """MultiHeadAttention.forward (system/SubLayers.py:68-102), n_head = 8, d_k = d_v = 64, eval mode."""
+def _mha(w, q_in, k_in, v_in, mask, drop_attn=None, drop_fc=None):
+    """MultiHeadAttention.forward (system/SubLayers.py:68-102), n_head = 8, d_k = d_v = 64; eval mode unless the dropout
+    multipliers of .train() are injected (drop_attn [b,8,lq,lk] at Modules.py:24, drop_fc [b,lq,512] at SubLayers.py:97)."""
     b, lq, lk = q_in.size(0), q_in.size(1), k_in.size(1)
     residual = q_in
     q = F.linear(q_in, w["w_qs.weight"]).view(b, lq, 8, 64).transpose(1, 2)
     k = F.linear(k_in, w["w_ks.weight"]).view(b, lk, 8, 64).transpose(1, 2)
     v = F.linear(v_in, w["w_vs.weight"]).view(b, lk, 8, 64).transpose(1, 2)
-    o = _attention(q, k, v, mask.unsqueeze(1))
+    o = _attention(q, k, v, mask.unsqueeze(1), drop_attn)
     o = _sh_block(o, w).sum(dim=1, keepdim=True)            # selective heads, summed (:89-92)
     o = o.transpose(1, 2).contiguous().view(b, lq, -1)
-    o = F.linear(o, w["fc.weight"]) + residual
+    o = F.linear(o, w["fc.weight"])
+    if drop_fc is not None:
+        o = o * drop_fc
+    o = o + residual
     return F.layer_norm(o, (512,), w["layer_norm.weight"], w["layer_norm.bias"], eps=1e-6)
 
 
-def _ffn(w, x):
-    """PositionwiseFeedForward.forward (system/SubLayers.py:177-187)."""
-    y = F.linear(F.relu(F.linear(x, w["w_1.weight"], w["w_1.bias"])), w["w_2.weight"], w["w_2.bias"]) + x
+def _ffn(w, x, drop=None):
+    """PositionwiseFeedForward.forward (system/SubLayers.py:177-187); drop [b,l,512]: injected multipliers of :182."""
+    y = F.linear(F.relu(F.linear(x, w["w_1.weight"], w["w_1.bias"])), w["w_2.weight"], w["w_2.bias"])
+    if drop is not None:
+        y = y * drop
+    y = y + x
     return F.layer_norm(y, (512,), w["layer_norm.weight"], w["layer_norm.bias"], eps=1e-6)
 
 
-def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False):
-    """Transformer.forward (system/Models.py:231-280).  sd: the 48 transformer keys (no prefix)."""
+def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False, drop=None):
+    """Transformer.forward (system/Models.py:231-280).  sd: the 48 transformer keys (no prefix).
+    drop: .train() with the dropout multipliers INJECTED (the reference draws them from torch's generator; the device
+    path from its own counter-based generator, `HeadEngine.dropout_masks`): dict of enc_emb / enc_slf_fc / dec_enc_fc /
+    enc_ffn / dec_ffn [bp*64, 512], dec_emb / dec_slf_fc [bs*64, 512], enc_slf_attn / dec_enc_attn [bp,8,64,64],
+    dec_slf_attn [bs,8,64,64].  The decoder-side masks are per UNIT and repeated over the unit's proposals (the device path
+    runs the query side once per unit).  None = eval mode."""
     w = _cast(sd, dtype)
+    dm = {} if drop is None else {k: v.to(device=x_props.device, dtype=dtype) for k, v in drop.items()}
+
+    def rows(name, per_unit=False):          # [n*64, 512] -> [bp, 64, 512]
+        if name not in dm:
+            return None
+        m = dm[name].view(-1, 64, 512)
+        return m.repeat_interleave(num_props, dim=0) if per_unit else m
+
+    def heads(name, per_unit=False):         # [n, 8, 64, 64] -> [bp, 8, 64, 64]
+        if name not in dm:
+            return None
+        return dm[name].repeat_interleave(num_props, dim=0) if per_unit else dm[name]
     x_props, x_query = x_props.to(dtype), x_query.to(dtype)
     bp, bs = x_props.size(0), x_query.size(0)
     num_props = bp // bs
@@ -85,17 +112,21 @@ def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False):
     src = torch.cat([src, torch.zeros(bp, n_t - n_s, 512, dtype=dtype, device=dev)], dim=1)   # :268-270
     # Encoder.forward (:83-111)
     e = src + w["encoder.position_enc.pos_table"][:, :n_t]
+    if rows("enc_emb") is not None:                                                # Encoder.dropout (:98)
+        e = e * rows("enc_emb")
     e = F.layer_norm(e, (512,), w["encoder.layer_norm.weight"], w["encoder.layer_norm.bias"], eps=1e-6)
     el = _sub(w, "encoder.layer_stack.0.")
-    e = _mha(_sub(el, "slf_attn."), e, e, e, src_mask)
-    e = _ffn(_sub(el, "pos_ffn."), e)
+    e = _mha(_sub(el, "slf_attn."), e, e, e, src_mask, heads("enc_slf_attn"), rows("enc_slf_fc"))
+    e = _ffn(_sub(el, "pos_ffn."), e, rows("enc_ffn"))
     # Decoder.forward (:143-172)
     d = trg + w["decoder.position_enc.pos_table"][:, :n_t]
+    if rows("dec_emb", True) is not None:                                          # Decoder.dropout (:152)
+        d = d * rows("dec_emb", True)
     d = F.layer_norm(d, (512,), w["decoder.layer_norm.weight"], w["decoder.layer_norm.bias"], eps=1e-6)
     dl = _sub(w, "decoder.layer_stack.0.")
-    d = _mha(_sub(dl, "slf_attn."), d, d, d, trg_mask)
-    d = _mha(_sub(dl, "enc_attn."), d, e, e, src_mask)
-    d = _ffn(_sub(dl, "pos_ffn."), d)
+    d = _mha(_sub(dl, "slf_attn."), d, d, d, trg_mask, heads("dec_slf_attn", True), rows("dec_slf_fc", True))
+    d = _mha(_sub(dl, "enc_attn."), d, e, e, src_mask, heads("dec_enc_attn"), rows("dec_enc_fc"))
+    d = _ffn(_sub(dl, "pos_ffn."), d, rows("dec_ffn"))
     out = d.permute(0, 2, 1).contiguous().view(bp, 512, 8, 8)                      # :276-277
     out = F.conv2d(out, w["dec_trans.0.weight"], w["dec_trans.0.bias"])           # :278
     return (out, e) if return_enc else out

@@ -54,8 +54,8 @@ def test_shims_uninstall_restores_sys_modules():
 @pytest.mark.gpu
 def test_reference_demo_usage_runs_against_the_shims(shims):
     """What adaptive_image_transformer.py:5-51 does, through the reference's import path: same constructor arguments, same
-    keyword call, same output shape.  The demo leaves the module in train mode (dropout 0.1 active, output random); the
-    drop-in's inference engine is the eval-mode graph, and train mode with dropout > 0 raises instead of skipping it."""
+    keyword call, same output shape.  The demo leaves the module in train mode (dropout 0.1 active, output random): the
+    drop-in then runs its training step with dropout, like the reference; .eval() is the deterministic inference engine."""
     from transformer.Models import Transformer
     batch_size, num_props, channels = 4, 128, 1024
     props_feat = torch.rand(batch_size * num_props, channels, 7, 7).cuda()
@@ -64,11 +64,13 @@ def test_reference_demo_usage_runs_against_the_shims(shims):
                       n_position=8 * 8, n_layers=1, n_head=8, dropout=0.1)
     AIT = AIT.cuda()
     assert "Transformer" in repr(AIT) and "layer_stack" in repr(AIT)      # print(AIT) of the demo
-    with pytest.raises(RuntimeError, match="dropout"):
-        AIT(x_props=props_feat, x_query=non_qry)
+    out_train = AIT(x_props=props_feat, x_query=non_qry)                   # the demo's own call: .train(), dropout active
+    assert tuple(out_train.shape) == (batch_size * num_props, channels, 8, 8) and out_train.dtype == torch.float32
+    assert torch.isfinite(out_train).all() and AIT.last_dropout_seed != 0
     out = AIT.eval()(x_props=props_feat, x_query=non_qry)
     assert tuple(out.shape) == (batch_size * num_props, channels, 8, 8) and out.dtype == torch.float32
     assert torch.isfinite(out).all()
+    assert float((out_train.detach() - out).abs().max()) > 1e-2 * float(out.abs().max())
 
 
 @pytest.mark.gpu

@@ -117,9 +117,17 @@ def test_transformer_module_drop_in_matches_reference_golden():
     out = t(x_props=xp.to(DEV), x_query=xq.to(DEV))
     assert out.shape == (6, 1024, 8, 8) and out.dtype == torch.float32
     assert _scaled_err(out.cpu()[:, ::8], g["out_s"]) < REL["fp32"]
+    # .train(): dropout is neither skipped nor refused -- the training step draws a fresh seed per call from torch's generator
     t.train()
-    with pytest.raises(RuntimeError):
-        t(x_props=xp.to(DEV), x_query=xq.to(DEV))          # dropout is not silently skipped
+    torch.manual_seed(5)
+    o1 = t(x_props=xp.to(DEV), x_query=xq.to(DEV))
+    s1 = t.last_dropout_seed
+    o2 = t(x_props=xp.to(DEV), x_query=xq.to(DEV))
+    torch.manual_seed(5)
+    o3 = t(x_props=xp.to(DEV), x_query=xq.to(DEV))
+    assert s1 != 0 and t.last_dropout_seed == s1
+    assert torch.equal(o1, o3) and not torch.equal(o1, o2)
+    assert float((o1 - out).abs().max()) > 1e-2 * float(out.abs().max())     # p = 0.1 masks move the output visibly
 
 
 def test_sknet_and_head_to_tail_modules_match_oracle():

@@ -143,7 +143,7 @@ def test_ait_training_step_matches_oracle_autograd(B, P, smooth):
     of the FFNs (measured 1.8e-2): gate 4e-2 there."""
     from ait_b200.system.Models import Transformer
     torch.manual_seed(0)
-    m = Transformer(n_layers=1, dropout=0.0, n_position=64).train()
+    m = Transformer(n_layers=1, dropout=0.0, n_position=64, attn_dropout=0.0).train()
     if smooth:
         with torch.no_grad():
             m.encoder.layer_stack[0].pos_ffn.w_1.bias += 5.0
@@ -175,6 +175,74 @@ def test_ait_training_step_matches_oracle_autograd(B, P, smooth):
     assert _l2rel(dict(m.named_parameters())[name].grad, 2 * pg_ref[name]) < gate
 
 
+@pytest.mark.parametrize("p,p_attn,B,P", [(0.1, 0.1, 2, 3), (0.0, 0.1, 1, 2), (0.25, 0.0, 2, 2)])
+def test_ait_training_step_with_dropout_matches_oracle_autograd(p, p_attn, B, P):
+    """.train() WITH dropout (the reference's default training mode: dropout = 0.1 at the seven nn.Dropout sites and the
+    hard-wired 0.1 on the attention probabilities): the device regenerates its masks from (seed, site, element) in forward
+    and backward and never stores them; `HeadEngine.dropout_masks` materialises the same multipliers, which are injected
+    into the fp64 oracle (whose ten dropout sites are pinned to the reference's nn.Dropout instances by
+    tests/test_oracle_pins.py::test_oracle_dropout_sites_match_reference_golden).  Output, both input gradients and all
+    46 parameter gradients must then agree to tf32 accuracy (smooth FFN: every ReLU active, see the test above)."""
+    from ait_b200 import packing
+    from ait_b200.system.Models import Transformer
+    from oracle import head_oracle
+    torch.manual_seed(0)
+    m = Transformer(n_layers=1, dropout=p, n_position=64, attn_dropout=p_attn).train()
+    with torch.no_grad():
+        m.encoder.layer_stack[0].pos_ffn.w_1.bias += 5.0
+        m.decoder.layer_stack[0].pos_ffn.w_1.bias += 5.0
+    g = torch.Generator().manual_seed(31 + B)
+    x_props = torch.randn(B * P, 1024, 7, 7, generator=g).relu()
+    x_query = torch.randn(B, 1024, 8, 8, generator=g).relu()
+    gout = torch.randn(B * P, 1024, 8, 8, generator=g)
+    sd = {k: v.detach().double().clone().requires_grad_(v.is_floating_point() and "pos_table" not in k)
+          for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    xp2, xq2 = x_props.to(DEV).requires_grad_(), x_query.to(DEV).requires_grad_()
+    torch.manual_seed(123)
+    out = m(xp2, xq2)
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    seed = m.last_dropout_seed
+    assert seed != 0
+    eng = packing.HeadEngine(transformer=m, dtype="tf32")
+    eng.set_train_dropout(p, p_attn, seed)
+    masks = {k: v.cpu() for k, v in eng.dropout_masks(B, P, torch.device(DEV)).items()}
+    for name, mk in masks.items():          # Bernoulli(1 - q) multipliers 0 | 1 / (1 - q)
+        q = p_attn if name.endswith("_attn") else p
+        if q == 0.0:
+            assert bool((mk == 1.0).all()), name
+            continue
+        keep = mk > 0
+        assert torch.allclose(mk[keep], torch.full_like(mk[keep], 1.0 / (1.0 - q)), rtol=1e-6), name
+        frac = float(keep.float().mean())
+        assert abs(frac - (1.0 - q)) < 4.0 * (q * (1 - q) / mk.numel()) ** 0.5 + 1e-3, (name, frac)
+    if p > 0.0:
+        assert not torch.equal(masks["enc_slf_fc"], masks["enc_ffn"])       # one key per site
+    if p_attn > 0.0:
+        assert not torch.equal(masks["enc_slf_attn"], masks["dec_enc_attn"])
+    xp, xq = x_props.double().requires_grad_(), x_query.double().requires_grad_()
+    ref = head_oracle.ait_forward(sd, xp, xq, dtype=torch.float64, drop=masks)
+    ref.backward(gout.double())
+    with torch.no_grad():
+        plain = head_oracle.ait_forward(sd, xp, xq, dtype=torch.float64)
+    assert _l2rel(out, plain) > 5e-2                                          # the masks move the result far beyond the gate
+    gate = 6e-3
+    assert _l2rel(out, ref.detach()) < 2e-3
+    assert _l2rel(xp2.grad, xp.grad) < gate, "grad x_props"
+    assert _l2rel(xq2.grad, xq.grad) < gate, "grad x_query"
+    errs = {name: _l2rel(prm.grad, sd[name].grad) for name, prm in m.named_parameters()}
+    bad = {k: v for k, v in errs.items() if v > gate}
+    assert len(errs) == 46 and not bad, bad
+    # same seed -> same masks -> same step; a new seed -> a different one
+    m.zero_grad()
+    torch.manual_seed(123)
+    out_b = m(xp2, xq2)
+    assert m.last_dropout_seed == seed and torch.equal(out_b, out)
+    out_c = m(xp2, xq2)
+    assert m.last_dropout_seed != seed and not torch.equal(out_c, out)
+
+
 def test_ait_training_step_matches_reference_golden_gradients():
     """tests/golden/ait_grad.pt: gradients produced by the UNMODIFIED reference Transformer (CPU fp32 autograd,
     dropout 0.0) with the weights of synth.make_head(seed=0) -- see tests/golden/make_golden_grad.py."""
@@ -187,9 +255,8 @@ def test_ait_training_step_matches_reference_golden_gradients():
     gout = torch.randn(2, 1024, 8, 8, generator=g)
     head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
     m = head.transformer
-    for mod in m.modules():
-        if hasattr(mod, "p_dropout"):
-            mod.p_dropout = 0.0
+    from ait_b200.system.Models import set_dropout
+    set_dropout(m, 0.0, 0.0)
     m = m.to(DEV).train()
     xp2, xq2 = xp.to(DEV).requires_grad_(), xq.to(DEV).requires_grad_()
     out = m(xp2, xq2)
@@ -351,9 +418,8 @@ def test_whole_head_training_step_matches_oracle_autograd():
     from oracle import head_oracle, target_oracle
     B, P = 2, 4
     head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
-    for mod in head.modules():
-        if hasattr(mod, "p_dropout"):
-            mod.p_dropout = 0.0
+    from ait_b200.system.Models import set_dropout
+    set_dropout(head, 0.0, 0.0)
     sd = {k: v.clone() for k, v in head.state_dict().items()}
     g = torch.Generator().manual_seed(71)
     maps = torch.stack([synth.c4_map(u) for u in range(B)])
@@ -469,9 +535,8 @@ def test_whole_head_training_step_matches_reference_golden_gradients():
     gold = load_golden("head_grad.pt")
     B, P = gold["B"], gold["P"]
     head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
-    for mod in head.modules():
-        if hasattr(mod, "p_dropout"):
-            mod.p_dropout = 0.0
+    from ait_b200.system.Models import set_dropout
+    set_dropout(head, 0.0, 0.0)
     g = torch.Generator().manual_seed(gold["seed"])
     maps = torch.stack([synth.c4_map(u) for u in range(B)])
     qrys = torch.stack([synth.query_feat(u) for u in range(B)])

@@ -168,6 +168,37 @@ def test_oracle_autograd_matches_reference_golden_gradients():
         assert err < 1e-3, (name, err)
 
 
+def test_oracle_dropout_sites_match_reference_golden():
+    """.train() WITH dropout: the oracle with the seeded masks of oracle/drop_masks.py injected at its ten sites reproduces
+    output and gradients of the unmodified reference Transformer whose ten nn.Dropout instances were fed the same masks
+    (tests/golden/ait_drop.pt, made by tests/golden/make_golden_drop.py)."""
+    from ait_b200 import synth
+    from oracle import drop_masks
+    gold = load_golden("ait_drop.pt")
+    bs, P = gold["bs"], gold["num_props"]
+    g = torch.Generator().manual_seed(gold["seed"])
+    xp = torch.rand(bs * P, 1024, 7, 7, generator=g).requires_grad_()
+    xq = torch.rand(bs, 1024, 8, 8, generator=g).requires_grad_()
+    gout = torch.randn(bs * P, 1024, 8, 8, generator=g)
+    masks = drop_masks.make_masks(gold["mask_seed"], bs, P, gold["p"], gold["p_attn"])
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
+    sd = {k: v.detach().clone().requires_grad_("pos_table" not in k) for k, v in head.transformer.state_dict().items()}
+    out = head_oracle.ait_forward(sd, xp, xq, drop=masks)
+    out.backward(gout)
+    with torch.no_grad():
+        plain = head_oracle.ait_forward(sd, xp, xq)
+    assert float((plain[:, ::8] - gold["out_s"]).abs().max()) > 1e-2 * float(gold["out_s"].abs().max())   # the masks matter
+    assert torch.allclose(out.detach()[:, ::8], gold["out_s"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xp.grad[:, ::4], gold["grad_props_s"], rtol=1e-3, atol=1e-5)
+    assert torch.allclose(xq.grad[:, ::4], gold["grad_query_s"], rtol=1e-3, atol=1e-5)
+    assert len(gold["params"]) == 46
+    for name, ref in gold["params"].items():
+        gr = sd[name].grad.reshape(-1)
+        sample = gr[::ref["stride"]][:ref["sample"].numel()]
+        err = float((sample - ref["sample"]).norm() / ref["sample"].norm())
+        assert err < 1e-3, (name, err)
+
+
 def _proposal_inputs(seed=21, B=2, A=9, H=19, W=31):
     import torch
     g = torch.Generator().manual_seed(seed)

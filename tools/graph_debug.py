@@ -13,9 +13,8 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "global"
 dev = "cuda:0"
 B, P = int(os.environ.get("GB", 2)), int(os.environ.get("GP", 8))
 head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
-for mod in head.modules():
-    if hasattr(mod, "p_dropout"):
-        mod.p_dropout = 0.0
+from ait_b200.system.Models import set_dropout
+set_dropout(head, 0.0, 0.0)
 head = head.to(dev).train()
 maps = torch.stack([synth.c4_map(u) for u in range(B)]).to(dev).requires_grad_()
 qrys = torch.stack([synth.query_feat(u) for u in range(B)]).to(dev).requires_grad_()

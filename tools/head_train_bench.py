@@ -23,9 +23,8 @@ P = int(argv[2]) if len(argv) > 2 else 128
 steps = int(argv[3]) if len(argv) > 3 else 5
 dev = "cuda:0"
 head = synth.make_head(seed=0, calibrated=True, randomize_bn=True)
-for mod in head.modules():
-    if hasattr(mod, "p_dropout"):
-        mod.p_dropout = 0.0
+from ait_b200.system.Models import set_dropout
+set_dropout(head, 0.0, 0.0)
 head = head.to(dev).train()
 maps = torch.stack([synth.c4_map(u) for u in range(B)]).to(dev).requires_grad_()
 qrys = torch.stack([synth.query_feat(u) for u in range(B)]).to(dev).requires_grad_()

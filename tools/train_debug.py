@@ -11,7 +11,7 @@ from oracle import head_oracle  # noqa: E402
 B, P = 2, 3
 DEV = "cuda:0"
 torch.manual_seed(0)
-m = Transformer(n_layers=1, dropout=0.0, n_position=64).train()
+m = Transformer(n_layers=1, dropout=0.0, n_position=64, attn_dropout=0.0).train()
 if len(sys.argv) > 1 and sys.argv[1] == "smooth":     # every ReLU active: gradients are smooth in the weights
     with torch.no_grad():
         m.encoder.layer_stack[0].pos_ffn.w_1.bias += 5.0

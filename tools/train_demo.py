@@ -40,9 +40,8 @@ def make_batch(B, dev, R=300):
 
 def run(B=2, steps=8, lr=1e-2, dev="cuda:0", verbose=True, mom=0.0, calibrated=False):
     head = synth.make_head(seed=0, calibrated=calibrated, randomize_bn=True)   # stock init: the reference's normal_init
-    for mod in head.modules():
-        if hasattr(mod, "p_dropout"):
-            mod.p_dropout = 0.0
+    from ait_b200.system.Models import set_dropout
+    set_dropout(head, 0.0, 0.0)
     head = head.to(dev).train()
     for n, p in head.named_parameters():           # frozen BatchNorm (set_bn_fix), like the reference
         if ".bn" in n or "downsample.1" in n:

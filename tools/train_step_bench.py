@@ -17,7 +17,7 @@ P = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 dev = "cuda:0"
 torch.manual_seed(0)
-m = Transformer(n_layers=1, dropout=0.0, n_position=64).to(dev).train()
+m = Transformer(n_layers=1, dropout=0.0, n_position=64, attn_dropout=0.0).to(dev).train()
 g = torch.Generator(device=dev).manual_seed(1)
 xp = torch.randn(B * P, 1024, 7, 7, device=dev, generator=g).relu().requires_grad_()
 xq = torch.randn(B, 1024, 8, 8, device=dev, generator=g).relu().requires_grad_()
