@@ -143,6 +143,7 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp]),
     "aitb_det_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "aitb_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "aitb_wgrad_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "aitb_wgrad_conv": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "aitb_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "aitb_colsum": (_i, [_vp, _i, _i, _i, _vp, _vp]),

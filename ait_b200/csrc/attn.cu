@@ -598,7 +598,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
   DropCfg dc;
   dc.scale = 1.f; dc.thr = dc.k0 = dc.k1 = 0u;
   if (drop && drop->thr) {
-    AITB_REQUIRE(dtype == AITB_F32, "aitb_attn_core: attention dropout exists in the training (fp32-storage) path only");
+    AITB_REQUIRE(dtype == AITB_F32 || dtype == AITB_BF16, "aitb_attn_core: attention dropout exists in the training paths (fp32 / bf16 storage) only");
     dc = *drop;
   }
   AITB_REQUIRE(q && k && v && w_sk && b_sk && out, "aitb_attn_core: null pointer");
@@ -610,7 +610,7 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
                "aitb_attn_core: compact K/V rows need the key-padding mask with n_keys <= kv_rows");
   static const bool want_tc = getenv("AITB_ATTN_TC") != nullptr;            // A/B switches: read once per process
   static const bool want_two_pass = getenv("AITB_ATTN_TWO_PASS") != nullptr;
-  if ((dtype == AITB_BF16 || dtype == AITB_F32S) && want_tc) {
+  if ((dtype == AITB_BF16 || dtype == AITB_F32S) && want_tc && !dc.thr) {
     // opt-in tcgen05 kernel (attn_tc.cu): Q K^T and P V on the 5th-generation tensor cores, TMEM accumulators, TMA
     // operands -- correct, but measured slower than the kernels below on the benchmark shape (see its header)
     const int rc = attn_tc_run(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, G, mask_mode, n_keys, dtype, out, stream, kv_rows);
@@ -620,8 +620,9 @@ int attn_core_run(const void* q, int ldq, int q_rep, const void* k, const void* 
     attn_core_kernel<float><<<G, kAttnThreads, 0, stream>>>((const float*)q, ldq, q_rep, (const float*)k,
                                                             (const float*)v, ldkv, w_sk, b_sk, mask_mode, n_keys,
                                                             (float*)out, round_tf, kv_rows, dc);
-  } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || want_two_pass)) {
-    // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch)
+  } else if (dtype == AITB_BF16 && (ldq % 8 != 0 || ldkv % 8 != 0 || want_two_pass || dc.thr)) {
+    // 16-byte cp.async needs 8-element pitches: the two-pass kernel takes any multiple of 4 (also the A/B switch, and the
+    // kernel that implements the training-mode dropout of the probabilities)
     attn_core_kernel<__nv_bfloat16><<<G, kAttnThreads, 0, stream>>>(
         (const __nv_bfloat16*)q, ldq, q_rep, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, w_sk, b_sk,
         mask_mode, n_keys, (__nv_bfloat16*)out, 0, kv_rows, dc);

@@ -15,8 +15,10 @@
 //   attn_bwd_kernel        selective-head attention backward (softmax, gate, head sum), one CTA per pair.
 //
 // (dgrad GEMMs dX = dY * W reuse the forward kernel of gemm.cu with a transposed weight copy.)
-// fp32 storage, tf32 tensor-core math, fp32 accumulation.
+// Two storage configurations: fp32 storage with tf32 tensor-core math (T = float), and bf16 storage with bf16 tensor-core
+// math (T = __nv_bfloat16); fp32 accumulation and fp32 parameter gradients in both.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -30,13 +32,24 @@ namespace aitb {
 int encode_map_f32_mn(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, const char* what);
 
+int encode_map_bf16(CUtensorMap* tm, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const char* what);
+
 // ---------------------------------------------------------------------------------------------
 // wgrad
 // ---------------------------------------------------------------------------------------------
 static constexpr int kWgStages = 4;
-static constexpr int kWgRows = 32;                      // contraction rows per pipeline stage (4 MMAs of K = 8)
-static constexpr int kWgABytes = 4 * kWgRows * 128;     // 4 column groups of 32 fp32 (MMA M = 128)
+static constexpr int kWgRows = 32;                      // tf32: contraction rows per pipeline stage (4 MMAs of K = 8)
+static constexpr int kWgABytes = 4 * kWgRows * 128;     // 16 KB: the 128 dY columns (MMA M = 128) of one stage, both configurations
 static constexpr int kWgThreads = 192;
+// per storage type: a stage holds kRows contraction rows as column groups of kGW elements (= 128 bytes, one TMA box each);
+// one MMA consumes kKRows rows (K = 8 tf32 / K = 16 bf16), i.e. kKRows * 128 bytes of every group
+template <bool BF16> struct WgCfg {
+  static constexpr int kRows = BF16 ? 64 : 32;
+  static constexpr int kGW = BF16 ? 64 : 32;
+  static constexpr int kKRows = BF16 ? 16 : 8;
+  static constexpr int kEs = BF16 ? 2 : 4;
+};
 
 struct WgradParams {
   int M;          // rows (contraction length)
@@ -59,22 +72,28 @@ struct WgradParams {
 // along MN (32 fp32), FOUR contraction rows per 512-byte atom, the 32-byte chunks of a row XOR-ed with
 // (row & 3).  Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units: atoms `lbo_bytes` apart along
 // MN and 512 bytes apart along K, which is exactly what a TMA box of {32 fp32, R rows} leaves behind.
+// MN-major bf16 operand: the ordinary 128-byte swizzle (layout type 2; TMA: CU_TENSOR_MAP_SWIZZLE_128B) -- rows of 128
+// contiguous bytes along MN (64 bf16), EIGHT contraction rows per 1024-byte atom, 16-byte chunks XOR-ed with (row & 7).
+template <bool BF16>
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)((BF16 ? 1024 : 512) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
+  d |= (uint64_t)(BF16 ? 2 : 1) << 61;   // SWIZZLE_128B | SWIZZLE_128B_BASE32B
   return d;
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                      const WgradParams p) {
+  using W = WgCfg<BF16>;
+  constexpr int kWgRows = W::kRows, kGW = W::kGW;    // shadow the tf32 constants of the namespace
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int b_bytes = (p.bn / 32) * kWgRows * 128;
+  const int b_bytes = (p.bn / kGW) * kWgRows * 128;
   const int stage_bytes = kWgABytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -118,37 +137,38 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        // one {32 cols, 32 rows} box per 128-byte column group (= one MN-major atom column); rows beyond M
+        // one {128 bytes of columns, kWgRows rows} box per column group (= one MN-major atom column); rows beyond M
         // are zero-filled by TMA
         const int r = row0 + it * kWgRows;
-        for (int g = 0; g < 4; ++g) tma_load_2d(sa + g * (kWgRows * 128), &tmY, &full_bar[s], nt * 128 + g * 32, r);
+        for (int g = 0; g < 128 / kGW; ++g) tma_load_2d(sa + g * (kWgRows * 128), &tmY, &full_bar[s], nt * 128 + g * kGW, r);
         const int xc = kt * p.bn;
         if (p.conv_S == 0) {
-          for (int g = 0; g < p.bn / 32; ++g)
-            tma_load_2d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], nt * p.x_group_stride + xc + g * 32, r);
+          for (int g = 0; g < p.bn / kGW; ++g)
+            tma_load_2d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], nt * p.x_group_stride + xc + g * kGW, r);
         } else {
           const int tap = xc / p.conv_cg, cc = xc - tap * p.conv_cg + nt * p.x_group_stride;
           const int ss = p.conv_S * p.conv_S;
           const int gi = r / ss, y0 = (r - gi * ss) / p.conv_S;
-          for (int g = 0; g < p.bn / 32; ++g)
-            tma_load_4d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], cc + g * 32, tap % 3 - 1, y0 + tap / 3 - 1, gi);
+          for (int g = 0; g < p.bn / kGW; ++g)
+            tma_load_4d(sa + kWgABytes + g * (kWgRows * 128), &tmX, &full_bar[s], cc + g * kGW, tap % 3 - 1, y0 + tap / 3 - 1, gi);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && iters > 0) {
-      // tf32, fp32 accumulate, A and B both MN-major (bits 15 / 16)
-      const uint32_t idesc = make_idesc(2u, 128u, (uint32_t)p.bn) | (1u << 15) | (1u << 16);
+      // tf32 / bf16 operands, fp32 accumulate, A and B both MN-major (bits 15 / 16)
+      const uint32_t idesc = make_idesc(BF16 ? 1u : 2u, 128u, (uint32_t)p.bn) | (1u << 15) | (1u << 16);
       for (int it = 0; it < iters; ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = make_mnmajor_desc(sa, kWgRows * 128);
-        const uint64_t bdesc = make_mnmajor_desc(sa + kWgABytes, kWgRows * 128);
+        const uint64_t adesc = make_mnmajor_desc<BF16>(sa, kWgRows * 128);
+        const uint64_t bdesc = make_mnmajor_desc<BF16>(sa + kWgABytes, kWgRows * 128);
+        constexpr int kStep = W::kKRows * 128 / 16;   // 8 rows (two 512-byte atoms) per K = 8 tf32 MMA; 16 rows (two 1024-byte atoms) per K = 16 bf16 MMA
 #pragma unroll
-        for (int k = 0; k < kWgRows / 8; ++k)  // 8 contraction rows (two 512-byte atoms) per K = 8 MMA
-          umma_ss<4>(tmem_base, adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kWgRows / W::kKRows; ++k)
+          umma_ss<W::kEs>(tmem_base, adesc + (uint64_t)(k * kStep), bdesc + (uint64_t)(k * kStep), idesc, (it | k) != 0 ? 1u : 0u);
         tc_commit(&empty_bar[s]);
       }
       tc_commit(acc_full);
@@ -204,11 +224,6 @@ static constexpr int kBH = 8;
 static constexpr int kAttnBwdThreads = 128;
 static constexpr int kAttnBwdSmem = (6 * kBT * kBS + 4 * kBT /*col partials*/ + 2 * kBH * kBT /*gate, dg -> dz*/ + 2 * kBT) * 4;
 
-__device__ __forceinline__ float tf32r(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -240,26 +255,26 @@ __device__ __forceinline__ void mm64(const float* __restrict__ a, const float* _
   }
 }
 
-// global [64 rows, ld] fp32 (64 columns from `g`) -> shared tile, rounded to tf32
-__device__ __forceinline__ void load_tile_f32(const float* __restrict__ g, int ld, float* __restrict__ s) {
+// global [64 rows, ld] (64 columns from `g`) -> shared fp32 tile, rounded to tf32 (bf16 values are tf32-exact)
+template <typename T>
+__device__ __forceinline__ void load_tile_f32(const T* __restrict__ g, int ld, float* __restrict__ s) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int f = threadIdx.x + kAttnBwdThreads * i;
     const int r = f >> 4, c4 = (f & 15) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * ld + c4));
+    const float4 v = ld4(g + (size_t)r * ld + c4);
     *reinterpret_cast<float4*>(s + r * kBS + c4) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
   }
 }
 
-// this warp's C fragment -> global rows r0.., 64 columns
-__device__ __forceinline__ void store_frag(const float (&c)[8][4], float* __restrict__ gp, int ld, int r0, float scale) {
+// this warp's C fragment -> global rows r0.., 64 columns (rounded to the storage's operand precision)
+template <typename T>
+__device__ __forceinline__ void store_frag(const float (&c)[8][4], T* __restrict__ gp, int ld, int r0, float scale) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<float2*>(gp + (size_t)(r0 + g) * ld + nt * 8 + 2 * t) =
-        make_float2(tf32r(c[nt][0] * scale), tf32r(c[nt][1] * scale));
-    *reinterpret_cast<float2*>(gp + (size_t)(r0 + g + 8) * ld + nt * 8 + 2 * t) =
-        make_float2(tf32r(c[nt][2] * scale), tf32r(c[nt][3] * scale));
+    st2r(gp + (size_t)(r0 + g) * ld + nt * 8 + 2 * t, c[nt][0] * scale, c[nt][1] * scale);
+    st2r(gp + (size_t)(r0 + g + 8) * ld + nt * 8 + 2 * t, c[nt][2] * scale, c[nt][3] * scale);
   }
 }
 
@@ -331,11 +346,12 @@ __device__ __forceinline__ void frag_colsum(const float (&c)[8][4], float* __res
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kAttnBwdThreads, 2)
-attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __restrict__ k, const float* __restrict__ v,
-                int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, const float* __restrict__ dout,
-                int mask_mode, int n_keys, float* __restrict__ dq, int lddq, float* __restrict__ dk,
-                float* __restrict__ dv, int lddkv, float* __restrict__ dz_out, float* __restrict__ s_out, DropCfg dc) {
+attn_bwd_kernel(const T* __restrict__ q, int ldq, int q_rep, const T* __restrict__ k, const T* __restrict__ v,
+                int ldkv, const float* __restrict__ w_sk, const float* __restrict__ b_sk, const T* __restrict__ dout,
+                int mask_mode, int n_keys, T* __restrict__ dq, int lddq, T* __restrict__ dk,
+                T* __restrict__ dv, int lddkv, T* __restrict__ dz_out, T* __restrict__ s_out, DropCfg dc) {
   extern __shared__ __align__(16) float bsm[];
   float* sQ = bsm;
   float* sK = sQ + kBT * kBS;
@@ -352,16 +368,16 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
   const int grp = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
-  const float* qg = q + (size_t)(grp / q_rep) * kBT * ldq;
-  const float* kg = k + (size_t)grp * kBT * ldkv;
-  const float* vg = v + (size_t)grp * kBT * ldkv;
+  const T* qg = q + (size_t)(grp / q_rep) * kBT * ldq;
+  const T* kg = k + (size_t)grp * kBT * ldkv;
+  const T* vg = v + (size_t)grp * kBT * ldkv;
   {  // dOut tile (kept in fp32: it is multiplied elementwise, rounded where it becomes an MMA operand)
-    const float* dg_ = dout + (size_t)grp * kBT * kBT;
+    const T* dg_ = dout + (size_t)grp * kBT * kBT;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int f = tid + kAttnBwdThreads * i;
       const int r = f >> 4, c4 = (f & 15) * 4;
-      *reinterpret_cast<float4*>(sDOut + r * kBS + c4) = __ldg(reinterpret_cast<const float4*>(dg_ + (size_t)r * kBT + c4));
+      *reinterpret_cast<float4*>(sDOut + r * kBS + c4) = ld4(dg_ + (size_t)r * kBT + c4);
     }
   }
   float s_acc = 0.f;  // thread c < 64: sum_h sum_t O_h[t, c]
@@ -425,9 +441,9 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
       gate[h * kBT + c] = e[h];
       const float dzv = e[h] * (dgv[h * kBT + c] - dot);
       dgv[h * kBT + c] = dzv;                                   // dz
-      dz_out[(size_t)grp * kBH * kBT + h * kBT + c] = dzv;
+      st1(dz_out + (size_t)grp * kBH * kBT + h * kBT + c, dzv);
     }
-    s_out[(size_t)grp * kBT + c] = svec[c];
+    st1(s_out + (size_t)grp * kBT + c, svec[c]);
   }
   __syncthreads();
   if (tid < kBT) {   // ds[c'] = sum_o W_sk[o, c'] dz[o]; stored as ds / T (the mean over T rows)
@@ -503,9 +519,10 @@ attn_bwd_kernel(const float* __restrict__ q, int ldq, int q_rep, const float* __
   }
 }
 
-int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
-                 const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
-                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream, const DropCfg* drop) {
+template <typename T>
+static int attn_bwd_run_t(const T* q, int ldq, int q_rep, const T* k, const T* v, int ldkv, const float* w_sk,
+                          const float* b_sk, const T* dout, int G, int mask_mode, int n_keys, T* dq, int lddq, T* dk,
+                          T* dv, int lddkv, T* dz, T* s_out, cudaStream_t stream, const DropCfg* drop) {
   DropCfg dc;
   dc.scale = 1.f; dc.thr = dc.k0 = dc.k1 = 0u;
   if (drop && drop->thr) dc = *drop;
@@ -513,10 +530,23 @@ int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float
   AITB_REQUIRE(q_rep >= 1 && (mask_mode == 0 || mask_mode == 1) && n_keys >= 1 && n_keys <= kBT, "aitb_attn_bwd: bad mode");
   AITB_REQUIRE(ldq % 4 == 0 && ldkv % 4 == 0 && lddq % 2 == 0 && lddkv % 2 == 0, "aitb_attn_bwd: bad leading dimensions");
   static SmemAttrOnce once;
-  if (ensure_dyn_smem((const void*)attn_bwd_kernel, kAttnBwdSmem, once, "attn_bwd_kernel")) return 1;
-  attn_bwd_kernel<<<G, kAttnBwdThreads, kAttnBwdSmem, stream>>>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, mask_mode,
-                                                               n_keys, dq, lddq, dk, dv, lddkv, dz, s_out, dc);
+  if (ensure_dyn_smem((const void*)attn_bwd_kernel<T>, kAttnBwdSmem, once, "attn_bwd_kernel")) return 1;
+  attn_bwd_kernel<T><<<G, kAttnBwdThreads, kAttnBwdSmem, stream>>>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, mask_mode,
+                                                                  n_keys, dq, lddq, dk, dv, lddkv, dz, s_out, dc);
   return check_launch("attn_bwd_kernel");
+}
+int attn_bwd_run(const float* q, int ldq, int q_rep, const float* k, const float* v, int ldkv, const float* w_sk,
+                 const float* b_sk, const float* dout, int G, int mask_mode, int n_keys, float* dq, int lddq, float* dk,
+                 float* dv, int lddkv, float* dz, float* s_out, cudaStream_t stream, const DropCfg* drop) {
+  return attn_bwd_run_t<float>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, G, mask_mode, n_keys, dq, lddq, dk, dv, lddkv, dz,
+                               s_out, stream, drop);
+}
+int attn_bwd_run(const __nv_bfloat16* q, int ldq, int q_rep, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
+                 const float* w_sk, const float* b_sk, const __nv_bfloat16* dout, int G, int mask_mode, int n_keys,
+                 __nv_bfloat16* dq, int lddq, __nv_bfloat16* dk, __nv_bfloat16* dv, int lddkv, __nv_bfloat16* dz,
+                 __nv_bfloat16* s_out, cudaStream_t stream, const DropCfg* drop) {
+  return attn_bwd_run_t<__nv_bfloat16>(q, ldq, q_rep, k, v, ldkv, w_sk, b_sk, dout, G, mask_mode, n_keys, dq, lddq, dk, dv,
+                                       lddkv, dz, s_out, stream, drop);
 }
 
 static int sms_bwd() { return current_sm_count(); }
@@ -532,10 +562,11 @@ static int sms_bwd() { return current_sm_count(); }
 // row (group * valid + t) -- the encoder's 64 -> 49 un-padding (system/Models.py:268-270); the pad rows still
 // feed dgamma / dbeta (their x_hat is LayerNorm(pos_table[t])).
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ gamma,
+ln_bwd_kernel(const T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ rstd, int rows, int grp, int valid,
-              float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float red[2][8][512];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gm[16], bt[16], ig[16], dg_acc[16], db_acc[16];
@@ -552,8 +583,8 @@ ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const fl
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * 512 + j * 128 + lane * 4));
-      const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + (size_t)row * 512 + j * 128 + lane * 4));
+      const float4 g4 = ld4(g + (size_t)row * 512 + j * 128 + lane * 4);
+      const float4 y4 = ld4(y + (size_t)row * 512 + j * 128 + lane * 4);
       gv[4 * j] = g4.x; gv[4 * j + 1] = g4.y; gv[4 * j + 2] = g4.z; gv[4 * j + 3] = g4.w;
       xh[4 * j] = y4.x; xh[4 * j + 1] = y4.y; xh[4 * j + 2] = y4.z; xh[4 * j + 3] = y4.w;
     }
@@ -571,15 +602,15 @@ ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const fl
     const int t = row % grp;
     if (t < valid) {
       const float rs = rstd[row];
-      float* o = dx + ((size_t)(row / grp) * valid + t) * 512;
+      T* o = dx + ((size_t)(row / grp) * valid + t) * 512;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float4 r;
-        r.x = tf32r(rs * (gv[4 * j] - m1 - xh[4 * j] * m2));          // rounded (RN): dx feeds tf32 MMAs next
-        r.y = tf32r(rs * (gv[4 * j + 1] - m1 - xh[4 * j + 1] * m2));
-        r.z = tf32r(rs * (gv[4 * j + 2] - m1 - xh[4 * j + 2] * m2));
-        r.w = tf32r(rs * (gv[4 * j + 3] - m1 - xh[4 * j + 3] * m2));
-        *reinterpret_cast<float4*>(o + j * 128 + lane * 4) = r;
+        r.x = rs * (gv[4 * j] - m1 - xh[4 * j] * m2);          // stored rounded (RN): dx feeds tensor-core MMAs next
+        r.y = rs * (gv[4 * j + 1] - m1 - xh[4 * j + 1] * m2);
+        r.z = rs * (gv[4 * j + 2] - m1 - xh[4 * j + 2] * m2);
+        r.w = rs * (gv[4 * j + 3] - m1 - xh[4 * j + 3] * m2);
+        st4r(o + j * 128 + lane * 4, r);
       }
     }
   }
@@ -599,26 +630,36 @@ ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const fl
   }
 }
 
-int ln_bwd_run(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows,
-               int grp, int valid, float* dx, float* dgamma, float* dbeta, cudaStream_t stream) {
+template <typename T>
+static int ln_bwd_run_t(const T* g, const T* y, const float* gamma, const float* beta, const float* rstd, int rows,
+                        int grp, int valid, T* dx, float* dgamma, float* dbeta, cudaStream_t stream) {
   AITB_REQUIRE(g && y && gamma && beta && rstd && dx && dgamma && dbeta, "aitb_ln_bwd: null pointer");
   AITB_REQUIRE(rows > 0 && grp > 0 && valid > 0 && valid <= grp && rows % grp == 0, "aitb_ln_bwd: bad row grouping");
   int grid = (rows + 7) / 8;
   if (grid > 4 * sms_bwd()) grid = 4 * sms_bwd();
-  ln_bwd_kernel<<<grid, 256, 0, stream>>>(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta);
+  ln_bwd_kernel<T><<<grid, 256, 0, stream>>>(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta);
   return check_launch("ln_bwd_kernel");
+}
+int ln_bwd_run(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows,
+               int grp, int valid, float* dx, float* dgamma, float* dbeta, cudaStream_t stream) {
+  return ln_bwd_run_t<float>(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta, stream);
+}
+int ln_bwd_run(const __nv_bfloat16* g, const __nv_bfloat16* y, const float* gamma, const float* beta, const float* rstd,
+               int rows, int grp, int valid, __nv_bfloat16* dx, float* dgamma, float* dbeta, cudaStream_t stream) {
+  return ln_bwd_run_t<__nv_bfloat16>(g, y, gamma, beta, rstd, rows, grp, valid, dx, dgamma, dbeta, stream);
 }
 
 // out[c] += sum over rows of x[row, c]   (bias gradients), x row-major [rows, ld], c < cols (cols % 4 == 0)
+template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, int rows_per_cta, float* __restrict__ out) {
+colsum_kernel(const T* __restrict__ x, int ld, int rows, int cols, int rows_per_cta, float* __restrict__ out) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = r0; r < r1; ++r) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ld + c));
+    const float4 v = ld4(x + (size_t)r * ld + c);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   atomicAdd(out + c, acc.x);
@@ -627,7 +668,8 @@ colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, int rows_
   atomicAdd(out + c + 3, acc.w);
 }
 
-int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStream_t stream) {
+template <typename T>
+static int colsum_run_t(const T* x, int ld, int rows, int cols, float* out, cudaStream_t stream) {
   AITB_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0, "aitb_colsum: bad arguments");
   const int gx = (cols / 4 + 255) / 256;
   int gy = (4 * sms_bwd() + gx - 1) / gx;
@@ -635,34 +677,49 @@ int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStrea
   if (gy < 1) gy = 1;
   const int rpc = (rows + gy - 1) / gy;
   gy = (rows + rpc - 1) / rpc;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>(x, ld, rows, cols, rpc, out);
+  colsum_kernel<T><<<dim3(gx, gy), 256, 0, stream>>>(x, ld, rows, cols, rpc, out);
   return check_launch("colsum_kernel");
+}
+int colsum_run(const float* x, int ld, int rows, int cols, float* out, cudaStream_t stream) {
+  return colsum_run_t<float>(x, ld, rows, cols, out, stream);
+}
+int colsum_run(const __nv_bfloat16* x, int ld, int rows, int cols, float* out, cudaStream_t stream) {
+  return colsum_run_t<__nv_bfloat16>(x, ld, rows, cols, out, stream);
 }
 
 // out[b, l] = sum_p x[b, p, l]   (gradient of the unit -> proposal broadcast), l < L (L % 4 == 0)
+template <typename T>
 __global__ void __launch_bounds__(256)
-bsum_kernel(const float* __restrict__ x, int P, int L, float* __restrict__ out) {
+bsum_kernel(const T* __restrict__ x, int P, int L, T* __restrict__ out) {
   const int l = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (l >= L) return;
-  const float* xb = x + (size_t)blockIdx.y * P * L + l;
+  const T* xb = x + (size_t)blockIdx.y * P * L + l;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = 0; p < P; ++p) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * L));
+    const float4 v = ld4(xb + (size_t)p * L);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  *reinterpret_cast<float4*>(out + (size_t)blockIdx.y * L + l) = acc;
+  if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(out + (size_t)blockIdx.y * L + l) = acc;   // fp32: unrounded, as before
+  else st4r(out + (size_t)blockIdx.y * L + l, acc);
 }
 
-int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t stream) {
+template <typename T>
+static int bsum_run_t(const T* x, int B, int P, int L, T* out, cudaStream_t stream) {
   AITB_REQUIRE(x && out && B > 0 && P > 0 && L > 0 && L % 4 == 0, "aitb_bsum: bad arguments");
-  bsum_kernel<<<dim3((L / 4 + 255) / 256, B), 256, 0, stream>>>(x, P, L, out);
+  bsum_kernel<T><<<dim3((L / 4 + 255) / 256, B), 256, 0, stream>>>(x, P, L, out);
   return check_launch("bsum_kernel");
+}
+int bsum_run(const float* x, int B, int P, int L, float* out, cudaStream_t stream) { return bsum_run_t<float>(x, B, P, L, out, stream); }
+int bsum_run(const __nv_bfloat16* x, int B, int P, int L, __nv_bfloat16* out, cudaStream_t stream) {
+  return bsum_run_t<__nv_bfloat16>(x, B, P, L, out, stream);
 }
 
 // dw [N, ldw] += dy[M, ldy (cols n_off .. n_off + N)]^T * x[M, ldx (cols 0 .. K)]
 // shared tail of the two entry points: tiling, split over row chunks, launch
-static int wgrad_launch(const float* dy, int ldy, const CUtensorMap& tmX, int M, int N, int K, int bn, float* dw, int ldw,
+template <bool BF16>
+static int wgrad_launch(const void* dy, int ldy, const CUtensorMap& tmX, int M, int N, int K, int bn, float* dw, int ldw,
                         int conv_S, int conv_cg, int x_group_stride, cudaStream_t stream) {
+  constexpr int kWgRows = WgCfg<BF16>::kRows, kGW = WgCfg<BF16>::kGW;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.M = M;
@@ -686,16 +743,17 @@ static int wgrad_launch(const float* dy, int ldy, const CUtensorMap& tmX, int M,
   CUtensorMap tmY;
   {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)ldy * 4};
-    const uint32_t box[2] = {32, (uint32_t)kWgRows};
-    if (encode_map_f32_mn(&tmY, dy, 2, dims, str, box, "wgrad dY")) return 1;
+    const uint64_t str[1] = {(uint64_t)ldy * WgCfg<BF16>::kEs};
+    const uint32_t box[2] = {(uint32_t)kGW, (uint32_t)kWgRows};
+    if (BF16 ? encode_map_bf16(&tmY, dy, dims, str, box, "wgrad dY") : encode_map_f32_mn(&tmY, dy, 2, dims, str, box, "wgrad dY"))
+      return 1;
   }
-  const int smem = kWgStages * (kWgABytes + (bn / 32) * kWgRows * 128) + 1024 + 256;
+  const int smem = kWgStages * (kWgABytes + (bn / kGW) * kWgRows * 128) + 1024 + 256;   // bn * 128 bytes of X per stage either way
   static SmemAttrOnce once;
-  if (ensure_dyn_smem((const void*)wgrad_tcgen05_kernel, kWgStages * (kWgABytes + 8 * kWgRows * 128) + 1024 + 256, once,
+  if (ensure_dyn_smem((const void*)wgrad_tcgen05_kernel<BF16>, kWgStages * (kWgABytes + 256 * 128) + 1024 + 256, once,
                       "wgrad_tcgen05_kernel"))
     return 1;
-  wgrad_tcgen05_kernel<<<tiles * p.splits, kWgThreads, smem, stream>>>(tmY, tmX, p);
+  wgrad_tcgen05_kernel<BF16><<<tiles * p.splits, kWgThreads, smem, stream>>>(tmY, tmX, p);
   return check_launch("wgrad_tcgen05_kernel");
 }
 
@@ -714,7 +772,26 @@ int wgrad_run(const float* dy, int ldy, const float* x, int ldx, int M, int N, i
   const uint64_t str[1] = {(uint64_t)ldx * 4};
   const uint32_t box[2] = {32, (uint32_t)kWgRows};
   if (encode_map_f32_mn(&tmX, x, 2, dims, str, box, "wgrad X")) return 1;
-  return wgrad_launch(dy, ldy, tmX, M, N, K, bn, dw, ldw, 0, 0, 0, stream);
+  return wgrad_launch<false>(dy, ldy, tmX, M, N, K, bn, dw, ldw, 0, 0, 0, stream);
+}
+
+// bf16 storage: dY and X are bf16 row-major activations, dW stays fp32 (accumulated)
+int wgrad_run(const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int M, int N, int K, float* dw, int ldw,
+              cudaStream_t stream) {
+  AITB_REQUIRE(dy && x && dw, "aitb_wgrad: null pointer");
+  AITB_REQUIRE(M > 0 && N > 0 && K > 0, "aitb_wgrad: empty problem");
+  AITB_REQUIRE(N % 128 == 0, "aitb_wgrad: N=%d must be a multiple of 128", N);
+  AITB_REQUIRE(K % 64 == 0, "aitb_wgrad: K=%d must be a multiple of 64", K);
+  AITB_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0 && ldw % 4 == 0, "aitb_wgrad: bf16 leading dimensions must be multiples of 8 (dW: 4)");
+  AITB_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dw & 15) == 0,
+               "aitb_wgrad: pointers must be 16-byte aligned");
+  const int bn = K % 256 == 0 ? 256 : (K % 128 == 0 ? 128 : 64);
+  CUtensorMap tmX;
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+  const uint64_t str[1] = {(uint64_t)ldx * 2};
+  const uint32_t box[2] = {64, (uint32_t)WgCfg<true>::kRows};
+  if (encode_map_bf16(&tmX, x, dims, str, box, "wgrad X")) return 1;
+  return wgrad_launch<true>(dy, ldy, tmX, M, N, K, bn, dw, ldw, 0, 0, 0, stream);
 }
 
 // Weight gradient of a (grouped) 1x1 or 3x3 stride-1 "same" convolution on a channels-last S x S map, no im2col:
@@ -749,7 +826,7 @@ int wgrad_conv_run(const float* dy, int ldy, const float* x, int G, int S, int C
     const uint32_t box[4] = {32, (uint32_t)S, (uint32_t)(S == 8 ? 4 : 4), (uint32_t)(S == 8 ? 1 : 2)};   // 32 rows per stage
     if (encode_map_f32_mn(&tmX, x, 4, dims, str, box, "wgrad_conv X map")) return 1;
   }
-  return wgrad_launch(dy, ldy, tmX, M, N, K, bn, dw, ldw, taps == 9 ? S : 0, cg, groups > 1 ? cg : 0, stream);
+  return wgrad_launch<false>(dy, ldy, tmX, M, N, K, bn, dw, ldw, taps == 9 ? S : 0, cg, groups > 1 ? cg : 0, stream);
 }
 
 }  // namespace aitb

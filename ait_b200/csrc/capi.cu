@@ -49,6 +49,24 @@ int drop_res_ln_run(float* z, const float* pos, int grp, int valid, const float*
                     float* rstd_out, cudaStream_t st);
 int drop_bwd_run(const float* dx, float* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
                  cudaStream_t st);
+// bf16-storage overloads of the training kernels (bwd.cu, dropout.cu)
+typedef __nv_bfloat16 bf16_t;
+int wgrad_run(const bf16_t* dy, int ldy, const bf16_t* x, int ldx, int M, int N, int K, float* dw, int ldw, cudaStream_t stream);
+int ln_bwd_run(const bf16_t* g, const bf16_t* y, const float* gamma, const float* beta, const float* rstd, int rows, int grp,
+               int valid, bf16_t* dx, float* dgamma, float* dbeta, cudaStream_t stream);
+int colsum_run(const bf16_t* x, int ld, int rows, int cols, float* out, cudaStream_t stream);
+int bsum_run(const bf16_t* x, int B, int P, int L, bf16_t* out, cudaStream_t stream);
+int attn_bwd_run(const bf16_t* q, int ldq, int q_rep, const bf16_t* k, const bf16_t* v, int ldkv, const float* w_sk,
+                 const float* b_sk, const bf16_t* dout, int G, int mask_mode, int n_keys, bf16_t* dq, int lddq, bf16_t* dk,
+                 bf16_t* dv, int lddkv, bf16_t* dz, bf16_t* s_out, cudaStream_t stream, const DropCfg* drop = nullptr);
+int drop_res_ln_run(bf16_t* z, const float* pos, int grp, int valid, const bf16_t* res, int res_div, int res_rep,
+                    const float* gamma, const float* beta, float eps, float p, unsigned long long seed, int site, int rows,
+                    int round_tf, float* rstd_out, cudaStream_t st);
+int drop_bwd_run(const bf16_t* dx, bf16_t* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
+                 cudaStream_t st);
+template <typename T> struct DtOf;
+template <> struct DtOf<float> { static constexpr int v = AITB_F32; };
+template <> struct DtOf<bf16_t> { static constexpr int v = AITB_BF16; };
 
 int rpn_decode_run(const float* scores_nchw, const float* deltas_nchw, const float* base_anchors, const float* im_info,
                    int B, int A, int H, int W, float feat_stride, float* proposals, float* fg_scores, cudaStream_t st);
@@ -374,6 +392,9 @@ struct TrainDrop {
   unsigned long long seed;
   DropCfg attn(int site) const { return make_drop(p_attn, seed, site); }
 };
+// y = LayerNorm(dropout(z [+ pos]) + residual) in place, fp32 or bf16 storage
+static int drop_res_ln_dt(int dt, void* z, const float* pos, int valid, const void* res, int res_rep, const aitb_lnorm& ln,
+                          const TrainDrop& td, int site, int rows, int round_tf, float* rstd, cudaStream_t st);
 static bool train_drop_of(const aitb_head_weights* w, TrainDrop& td) {
   td.p = w->p_drop; td.p_attn = w->p_attn; td.seed = w->drop_seed;
   return td.p > 0.f || td.p_attn > 0.f;
@@ -383,6 +404,16 @@ static bool train_drop_of(const aitb_head_weights* w, TrainDrop& td) {
   do {                   \
     if ((expr)) return 1; \
   } while (0)
+
+static int drop_res_ln_dt(int dt, void* z, const float* pos, int valid, const void* res, int res_rep, const aitb_lnorm& ln,
+                          const TrainDrop& td, int site, int rows, int round_tf, float* rstd, cudaStream_t st) {
+  if (dt == AITB_F32)
+    return drop_res_ln_run((float*)z, pos, 64, valid, (const float*)res, 64, res_rep, ln.gamma, ln.beta, 1e-6f, td.p, td.seed, site,
+                           rows, round_tf, rstd, st);
+  AITB_REQUIRE(dt == AITB_BF16, "training dropout: fp32 or bf16 storage only");
+  return drop_res_ln_run((bf16_t*)z, pos, 64, valid, (const bf16_t*)res, 64, res_rep, ln.gamma, ln.beta, 1e-6f, td.p, td.seed, site,
+                         rows, 0, rstd, st);
+}
 
 // ---------------------------------------------------------------------------------------------
 // AIT: Transformer.forward (system/Models.py:231-280) on token-major inputs
@@ -404,8 +435,7 @@ static int mha_block(const aitb_head_weights* w, const aitb_mha& m, const void* 
     aitb_gemm_desc d = gemm_base(dt, G * 64, 512, 64, m.w_fc, 256, out, 512, 0);
     view_plain(d, ao, 64);
     RUN(gemm_run(&d, st));
-    return drop_res_ln_run((float*)out, nullptr, 64, 64, (const float*)res, 64, res_rep, m.ln.gamma, m.ln.beta, 1e-6f, td->p,
-                           td->seed, site_fc, G * 64, w->round_tf32, rstd, st);
+    return drop_res_ln_dt(dt, out, nullptr, 64, res, res_rep, m.ln, *td, site_fc, G * 64, w->round_tf32, rstd, st);
   }
   RUN(attn_core_run(qbuf, ldq, q_rep, kbuf, vbuf, ldkv, m.w_sk, m.b_sk, G, mask_mode, n_keys, dt, ao, st,
                     w->round_tf32, kv_rows));
@@ -459,8 +489,7 @@ static int ffn_block(const aitb_head_weights* w, const aitb_ffn& f, const void* 
     d2.flags = AITB_EPI_BIAS;
     d2.bias = f.w2.bias;
     RUN(gemm_run(&d2, st));
-    return drop_res_ln_run((float*)out, nullptr, 64, 64, (const float*)x, 64, 1, f.ln.gamma, f.ln.beta, 1e-6f, td->p, td->seed,
-                           site, M, w->round_tf32, rstd, st);
+    return drop_res_ln_dt(dt, out, nullptr, 64, x, 1, f.ln, *td, site, M, w->round_tf32, rstd, st);
   }
   d2.flags = AITB_EPI_BIAS | AITB_EPI_RES | AITB_EPI_LN;
   d2.bias = f.w2.bias;
@@ -486,8 +515,7 @@ static int ait_query_side(const aitb_head_weights* w, HeadBufs& hb, int B, cudaS
     d.block_n = 256;
     d.flags = AITB_EPI_BIAS;
     RUN(gemm_run(&d, st));
-    RUN(drop_res_ln_run((float*)hb.T0, w->dec_pos, 64, 64, nullptr, 64, 1, w->dec_ln.gamma, w->dec_ln.beta, 1e-6f, td->p,
-                        td->seed, AITB_DROP_DEC_EMB, RQ, rt, hb.r_T0, st));
+    RUN(drop_res_ln_dt(dt, hb.T0, w->dec_pos, 64, nullptr, 1, w->dec_ln, *td, AITB_DROP_DEC_EMB, RQ, rt, hb.r_T0, st));
   } else {
     d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
     d.pos = w->dec_pos;
@@ -534,8 +562,7 @@ static int ait_core(const aitb_head_weights* w, HeadBufs& hb, int B, int P, void
       d.block_n = 256;
       d.flags = AITB_EPI_BIAS;
       RUN(gemm_run(&d, st));
-      RUN(drop_res_ln_run((float*)hb.X1, w->enc_pos, 64, 49, nullptr, 64, 1, w->enc_ln.gamma, w->enc_ln.beta, 1e-6f, td->p,
-                          td->seed, AITB_DROP_ENC_EMB, R, rt, hb.r_X1, st));
+      RUN(drop_res_ln_dt(dt, hb.X1, w->enc_pos, 49, nullptr, 1, w->enc_ln, *td, AITB_DROP_ENC_EMB, R, rt, hb.r_X1, st));
     } else {
       d.flags = AITB_EPI_BIAS | AITB_EPI_POS | AITB_EPI_LN;
       d.pos = w->enc_pos;
@@ -684,13 +711,15 @@ static int check_weights(const aitb_head_weights* w, bool with_top) {
 
 // ---------------------------------------------------------------------------------------------
 // Training step of the AIT module (config 4): forward keeping activations, then the backward.
-// fp32 storage + tf32 tensor-core math.  The reference gets this from torch autograd over
+// Two configurations: fp32 storage + tf32 tensor-core math (AITB_F32), bf16 storage + bf16 tensor-core math (AITB_BF16);
+// fp32 accumulation, LayerNorm statistics and parameter gradients in both.  The reference gets this from torch autograd over
 // system/Models.py:231-280; the op order below is the exact reverse of ait_query_side / ait_core.
 // ---------------------------------------------------------------------------------------------
-static void carve_train(Bump& b, HeadBufs& hb, int B, int P) {
+static void carve_train(Bump& b, HeadBufs& hb, int B, int P, int es = 4) {
   const size_t bp = (size_t)B * P, R = bp * 64, RQ = (size_t)B * 64;
   memset(&hb, 0, sizeof(hb));
-  auto f = [&](size_t n) { return b.take(n * 4); };
+  auto f = [&](size_t n) { return b.take(n * es); };
+  auto f4 = [&](size_t n) { return (float*)b.take(n * 4); };
   hb.pooled = f(bp * 49 * 1024);
   hb.qtok = f(RQ * 1024);
   hb.X1 = f(R * 512);
@@ -710,21 +739,22 @@ static void carve_train(Bump& b, HeadBufs& hb, int B, int P) {
   hb.Hh2 = f(R * 2048);
   hb.DEC = f(R * 512);
   hb.AIT = f(R * 1024);
-  hb.r_X1 = (float*)f(R);
-  hb.r_X2 = (float*)f(R);
-  hb.r_ENC = (float*)f(R);
-  hb.r_T0 = (float*)f(RQ);
-  hb.r_T1 = (float*)f(RQ);
-  hb.r_D1 = (float*)f(R);
-  hb.r_DEC = (float*)f(R);
+  hb.r_X1 = f4(R);
+  hb.r_X2 = f4(R);
+  hb.r_ENC = f4(R);
+  hb.r_T0 = f4(RQ);
+  hb.r_T1 = f4(RQ);
+  hb.r_D1 = f4(R);
+  hb.r_DEC = f4(R);
 }
 
 // dX[M, Np] = epilogue( dY[M, Kp] * W[Kp, Np] )  with W^T ([Np, Kp], K-major) in `wt`: the forward GEMM kernel
-static int dgrad(const float* dy, int M, int Kp, int Np, const float* wt, float* out, int flags, const float* res,
+template <typename T>
+static int dgrad(const T* dy, int M, int Kp, int Np, const T* wt, T* out, int flags, const T* res,
                  int ldr, cudaStream_t st) {
   const int bn = Np % 256 == 0 ? 256 : (Np % 128 == 0 ? 128 : 64);
-  // gradients are rounded to tf32 (RN) where they are produced: the next MMA would otherwise truncate them
-  aitb_gemm_desc d = gemm_base(AITB_F32, M, Np, Kp, wt, bn, out, Np, 1);
+  // fp32 storage: gradients are rounded to tf32 (RN) where they are produced -- the next MMA would otherwise truncate them
+  aitb_gemm_desc d = gemm_base(DtOf<T>::v, M, Np, Kp, wt, bn, out, Np, sizeof(T) == 4 ? 1 : 0);
   view_plain(d, dy, Kp);
   d.flags = flags;
   d.res = res;
@@ -732,26 +762,30 @@ static int dgrad(const float* dy, int M, int Kp, int Np, const float* wt, float*
   return gemm_run(&d, st);
 }
 
-// W [N, K] -> W^T [K, N]
-static int transpose_w(const void* w, int N, int K, float* out, cudaStream_t st) {
-  return transpose_run(w, AITB_F32, out, AITB_F32, 1, N, K, 1, st);
+// W [N, K] -> W^T [K, N]  (the packed weights have the storage type of the activations)
+template <typename T>
+static int transpose_w(const void* w, int N, int K, T* out, cudaStream_t st) {
+  return transpose_run(w, DtOf<T>::v, out, DtOf<T>::v, 1, N, K, 1, st);
 }
 
+template <typename T>
 struct FfnBwd {
   const aitb_ffn* w;
   const aitb_ffn_g* g;
-  const float *x, *hid, *y, *rstd;   // saved: input [R,512], hidden [R,2048], output (post-LN) [R,512], 1/sigma
+  const T *x, *hid, *y;              // saved: input [R,512], hidden [R,2048], output (post-LN) [R,512]
+  const float* rstd;                 // saved 1/sigma
   const TrainDrop* td;               // dropout between w_2 and the residual add (NULL / p == 0: none)
   int site;
-  float* gz;                         // [R,512] scratch: the masked gradient of the w_2 output
+  T* gz;                             // [R,512] scratch: the masked gradient of the w_2 output
 };
 
 // backward of y = LN(relu(x W1^T + b1) W2^T + b2 + x); gy -> gx (both [R, 512]); gf / gh are scratch
-static int ffn_backward(const FfnBwd& f, int R, const float* gy, float* gf, float* gh, float* gx, float* w1t, float* w2t,
+template <typename T>
+static int ffn_backward(const FfnBwd<T>& f, int R, const T* gy, T* gf, T* gh, T* gx, T* w1t, T* w2t,
                         cudaStream_t st) {
   RUN(ln_bwd_run(gy, f.y, f.w->ln.gamma, f.w->ln.beta, f.rstd, R, 64, 64, gf, f.g->ln.gamma, f.g->ln.beta, st));
   // gf = gradient of (dropout(z) + x): the residual path (last line) takes it as is, the w_2 path through the mask
-  const float* gz = gf;
+  const T* gz = gf;
   if (f.td && f.td->p > 0.f) {
     RUN(drop_bwd_run(gf, f.gz, f.td->p, f.td->seed, f.site, R, 64, 64, st));
     gz = f.gz;
@@ -759,11 +793,11 @@ static int ffn_backward(const FfnBwd& f, int R, const float* gy, float* gf, floa
   RUN(colsum_run(gz, 512, R, 512, f.g->w2.bias, st));
   RUN(wgrad_run(gz, 512, f.hid, 2048, R, 512, 2048, f.g->w2.w, 2048, st));
   RUN(transpose_w(f.w->w2.w, 512, 2048, w2t, st));                       // [2048, 512]
-  RUN(dgrad(gz, R, 512, 2048, w2t, gh, AITB_EPI_RELU_MASK, f.hid, 2048, st));
+  RUN(dgrad<T>(gz, R, 512, 2048, w2t, gh, AITB_EPI_RELU_MASK, f.hid, 2048, st));
   RUN(colsum_run(gh, 2048, R, 2048, f.g->w1.bias, st));
   RUN(wgrad_run(gh, 2048, f.x, 512, R, 2048, 512, f.g->w1.w, 512, st));
   RUN(transpose_w(f.w->w1.w, 2048, 512, w1t, st));                       // [512, 2048]
-  return dgrad(gh, R, 2048, 512, w1t, gx, AITB_EPI_RES, gf, 512, st);
+  return dgrad<T>(gh, R, 2048, 512, w1t, gx, AITB_EPI_RES, gf, 512, st);
 }
 
 }  // namespace aitb
@@ -792,20 +826,23 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
                            float* out_nchw, void* saved, size_t saved_bytes, aitb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RUN(check_weights(w, false));
-  AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_forward_train: the training path runs in the fp32-storage / tf32 configuration");
+  AITB_REQUIRE(w->dtype == AITB_F32 || w->dtype == AITB_BF16,
+               "aitb_ait_forward_train: the training path runs in the fp32-storage / tf32 or the bf16 configuration");
   AITB_REQUIRE(B > 0 && P > 0 && x_props && x_query && saved, "aitb_ait_forward_train: bad arguments");
+  AITB_REQUIRE(w->dtype == AITB_F32 || out_nchw, "aitb_ait_forward_train: the token-major hand-over (out_nchw == NULL) exists in the fp32-storage configuration only");
+  const int dt = w->dtype, es = esize(dt);
   AITB_REQUIRE(((uintptr_t)saved & 1023) == 0 && saved_bytes >= aitb_ait_saved_bytes(B, P),
                "aitb_ait_forward_train: `saved` must be 1024-byte aligned and aitb_ait_saved_bytes large");
   const int bp = B * P;
   Bump b{(uint8_t*)saved, 0};
   HeadBufs hb;
-  carve_train(b, hb, B, P);
+  carve_train(b, hb, B, P, es);
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
-    RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (float*)hb.pooled + (size_t)g0 * 49 * 1024, AITB_F32, gn,
+    RUN(transpose_run(x_props + (size_t)g0 * 1024 * 49, AITB_F32, (uint8_t*)hb.pooled + (size_t)g0 * 49 * 1024 * es, dt, gn,
                       1024, 49, 1, st, w->round_tf32));
   }
-  RUN(transpose_run(x_query, AITB_F32, hb.qtok, AITB_F32, B, 1024, 64, 1, st, w->round_tf32));
+  RUN(transpose_run(x_query, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   TrainDrop td;
   const bool drop = train_drop_of(w, td);
   AITB_REQUIRE(td.p >= 0.f && td.p < 1.f && td.p_attn >= 0.f && td.p_attn < 1.f, "aitb_ait_forward_train: dropout probabilities must be in [0, 1)");
@@ -814,7 +851,7 @@ int aitb_ait_forward_train(const aitb_head_weights* w, const float* x_props, con
   // out_nchw == NULL: the caller consumes the token-major result in place (aitb_ait_saved_offset(B, P, 1)) -- no NCHW copy
   for (int g0 = 0; out_nchw && g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
-    RUN(transpose_run((const float*)hb.AIT + (size_t)g0 * 64 * 1024, AITB_F32, out_nchw + (size_t)g0 * 1024 * 64, AITB_F32,
+    RUN(transpose_run((const uint8_t*)hb.AIT + (size_t)g0 * 64 * 1024 * es, dt, out_nchw + (size_t)g0 * 1024 * 64, AITB_F32,
                       gn, 1024, 64, 0, st));
   }
   return 0;
@@ -829,12 +866,17 @@ size_t aitb_ait_saved_offset(int B, int P, int which) {
   return (size_t)((const uint8_t*)(which == 1 ? hb.AIT : hb.pooled) - base);
 }
 
+}  // extern "C"
+
+template <typename T>
 static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_nchw, int grad_token_major, int B, int P,
                              const void* saved, size_t saved_bytes, const aitb_ait_grads* g, float* grad_props,
                              float* grad_query, void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RUN(check_weights(w, false));
-  AITB_REQUIRE(w->dtype == AITB_F32, "aitb_ait_backward: the training path runs in the fp32-storage / tf32 configuration");
+  constexpr int dt = DtOf<T>::v;
+  AITB_REQUIRE(w->dtype == dt, "aitb_ait_backward: internal dtype dispatch error");
+  AITB_REQUIRE(dt == AITB_F32 || !grad_token_major, "aitb_ait_backward_tm: the token-major hand-over exists in the fp32-storage configuration only");
   AITB_REQUIRE(B > 0 && P > 0 && grad_out_nchw && saved && g && grad_props && grad_query && workspace,
                "aitb_ait_backward: bad arguments");
   AITB_REQUIRE(((uintptr_t)saved & 1023) == 0 && saved_bytes >= aitb_ait_saved_bytes(B, P), "aitb_ait_backward: bad `saved`");
@@ -843,16 +885,16 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   const int bp = B * P, R = bp * 64, RQ = B * 64, R49 = bp * 49;
   Bump sb{(uint8_t*)const_cast<void*>(saved), 0};
   HeadBufs hb;
-  carve_train(sb, hb, B, P);
+  carve_train(sb, hb, B, P, (int)sizeof(T));
   Bump b{(uint8_t*)workspace, 0};
-  auto f = [&](size_t n) { return (float*)b.take(n * 4); };
-  const float* S_pooled = (const float*)hb.pooled; const float* S_qtok = (const float*)hb.qtok;
-  const float* S_X1 = (const float*)hb.X1; const float* S_QKV = (const float*)hb.QKV; const float* S_AO = (const float*)hb.AO;
-  const float* S_X2 = (const float*)hb.X2; const float* S_H1 = (const float*)hb.Hh; const float* S_ENC = (const float*)hb.ENC;
-  const float* S_T0 = (const float*)hb.T0; const float* S_QKVd = (const float*)hb.QKVd; const float* S_AOd = (const float*)hb.AOd;
-  const float* S_T1 = (const float*)hb.T1; const float* S_Qc = (const float*)hb.Qc; const float* S_KVc = (const float*)hb.KVc;
-  const float* S_AOc = (const float*)hb.AOc; const float* S_D1 = (const float*)hb.D1; const float* S_H2 = (const float*)hb.Hh2;
-  const float* S_DEC = (const float*)hb.DEC;
+  auto f = [&](size_t n) { return (T*)b.take(n * sizeof(T)); };
+  const T* S_pooled = (const T*)hb.pooled; const T* S_qtok = (const T*)hb.qtok;
+  const T* S_X1 = (const T*)hb.X1; const T* S_QKV = (const T*)hb.QKV; const T* S_AO = (const T*)hb.AO;
+  const T* S_X2 = (const T*)hb.X2; const T* S_H1 = (const T*)hb.Hh; const T* S_ENC = (const T*)hb.ENC;
+  const T* S_T0 = (const T*)hb.T0; const T* S_QKVd = (const T*)hb.QKVd; const T* S_AOd = (const T*)hb.AOd;
+  const T* S_T1 = (const T*)hb.T1; const T* S_Qc = (const T*)hb.Qc; const T* S_KVc = (const T*)hb.KVc;
+  const T* S_AOc = (const T*)hb.AOc; const T* S_D1 = (const T*)hb.D1; const T* S_H2 = (const T*)hb.Hh2;
+  const T* S_DEC = (const T*)hb.DEC;
 
   TrainDrop td;
   const bool drop = train_drop_of(w, td);
@@ -860,157 +902,163 @@ static int ait_backward_impl(const aitb_head_weights* w, const float* grad_out_n
   const bool dp = drop && td.p > 0.f;       // the row-wise sites (the attention-probability sites follow p_attn)
   const DropCfg da_enc = td.attn(AITB_DROP_ENC_SLF_ATTN), da_dec = td.attn(AITB_DROP_DEC_SLF_ATTN),
                 da_x = td.attn(AITB_DROP_DEC_ENC_ATTN);
-  float* wta = f((size_t)2048 * 1024);   // transposed-weight scratch (two slots)
-  float* wtb = f((size_t)2048 * 1024);
-  float* gZ = dp ? f((size_t)R * 512) : nullptr;   // masked copy of a LayerNorm-input gradient (one site at a time)
+  T* wta = f((size_t)2048 * 1024);   // transposed-weight scratch (two slots)
+  T* wtb = f((size_t)2048 * 1024);
+  T* gZ = dp ? f((size_t)R * 512) : nullptr;   // masked copy of a LayerNorm-input gradient (one site at a time)
   // ---- dec_trans: AIT = DEC Wt^T + b
-  float* gAIT_buf = f((size_t)R * 1024);
-  const float* gAIT = grad_token_major ? grad_out_nchw : gAIT_buf;   // token-major: already [bp*64, 1024], tf32-rounded
+  T* gAIT_buf = f((size_t)R * 1024);
+  const T* gAIT = grad_token_major ? (const T*)(const void*)grad_out_nchw : gAIT_buf;   // token-major (fp32 storage only): already [bp*64, 1024], tf32-rounded
   for (int g0 = 0; !grad_token_major && g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
-    RUN(transpose_run(grad_out_nchw + (size_t)g0 * 1024 * 64, AITB_F32, gAIT_buf + (size_t)g0 * 64 * 1024, AITB_F32, gn, 1024, 64,
+    RUN(transpose_run(grad_out_nchw + (size_t)g0 * 1024 * 64, AITB_F32, gAIT_buf + (size_t)g0 * 64 * 1024, dt, gn, 1024, 64,
                       1, st, 1));
   }
   RUN(colsum_run(gAIT, 1024, R, 1024, g->dec_trans.bias, st));
   RUN(wgrad_run(gAIT, 1024, S_DEC, 512, R, 1024, 512, g->dec_trans.w, 512, st));
-  float* gDEC = f((size_t)R * 512);
+  T* gDEC = f((size_t)R * 512);
   RUN(transpose_w(w->dec_trans.w, 1024, 512, wta, st));                  // [512, 1024]
-  RUN(dgrad(gAIT, R, 1024, 512, wta, gDEC, 0, nullptr, 0, st));
+  RUN(dgrad<T>(gAIT, R, 1024, 512, wta, gDEC, 0, (const T*)nullptr, 0, st));
   // ---- decoder FFN
-  float* gF = f((size_t)R * 512);
-  float* gH = f((size_t)R * 2048);
-  float* gD1 = f((size_t)R * 512);
+  T* gF = f((size_t)R * 512);
+  T* gH = f((size_t)R * 2048);
+  T* gD1 = f((size_t)R * 512);
   {
-    FfnBwd fb{&w->dec_ffn, &g->dec_ffn, S_D1, S_H2, S_DEC, hb.r_DEC, tdp, AITB_DROP_DEC_FFN, gZ};
+    FfnBwd<T> fb{&w->dec_ffn, &g->dec_ffn, S_D1, S_H2, S_DEC, hb.r_DEC, tdp, AITB_DROP_DEC_FFN, gZ};
     RUN(ffn_backward(fb, R, gDEC, gF, gH, gD1, wta, wtb, st));
   }
   // ---- cross attention: D1 = LN(AOc Wfc^T + T1[unit])
-  float* gC1 = f((size_t)R * 512);
+  T* gC1 = f((size_t)R * 512);
   RUN(ln_bwd_run(gD1, S_D1, w->dec_enc.ln.gamma, w->dec_enc.ln.beta, hb.r_D1, R, 64, 64, gC1, g->dec_enc.ln.gamma,
                  g->dec_enc.ln.beta, st));
-  const float* gC1m = gC1;                                               // gradient of fc's output: through the dropout mask
+  const T* gC1m = gC1;                                               // gradient of fc's output: through the dropout mask
   if (dp) {
     RUN(drop_bwd_run(gC1, gZ, td.p, td.seed, AITB_DROP_DEC_ENC_FC, R, 64, 64, st));
     gC1m = gZ;
   }
   RUN(wgrad_run(gC1m, 512, S_AOc, 64, R, 512, 64, g->dec_enc.w_fc, 64, st));
-  float* gAO = f((size_t)R * 64);
+  T* gAO = f((size_t)R * 64);
   RUN(transpose_w(w->dec_enc.w_fc, 512, 64, wta, st));                   // [64, 512]
-  RUN(dgrad(gC1m, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
-  float* gT1res = f((size_t)RQ * 512);
+  RUN(dgrad<T>(gC1m, R, 512, 64, wta, gAO, 0, (const T*)nullptr, 0, st));
+  T* gT1res = f((size_t)RQ * 512);
   RUN(bsum_run(gC1, B, P, 64 * 512, gT1res, st));                        // residual T1 is shared by the unit's P pairs
-  float* dQpp = f((size_t)R * 512);
-  float* gKVc = f((size_t)R * 1024);
-  float* dz = f((size_t)(bp + B) * 512);
-  float* sv = f((size_t)(bp + B) * 64);
+  T* dQpp = f((size_t)R * 512);
+  T* gKVc = f((size_t)R * 1024);
+  T* dz = f((size_t)(bp + B) * 512);
+  T* sv = f((size_t)(bp + B) * 64);
   RUN(attn_bwd_run(S_Qc, 512, P, S_KVc, S_KVc + 512, 1024, w->dec_enc.w_sk, w->dec_enc.b_sk, gAO, bp, 0, 49, dQpp, 512,
                    gKVc, gKVc + 512, 1024, dz, sv, st, &da_x));
   RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->dec_enc.w_sk, 64, st));
   RUN(colsum_run(dz, 512, bp, 512, g->dec_enc.b_sk, st));
-  float* gQc = f((size_t)RQ * 512);
+  T* gQc = f((size_t)RQ * 512);
   RUN(bsum_run(dQpp, B, P, 64 * 512, gQc, st));
-  const float* Wq = (const float*)w->dec_enc.w_qkv;
-  const float* Wkv = Wq + (size_t)512 * 512;
+  const T* Wq = (const T*)w->dec_enc.w_qkv;
+  const T* Wkv = Wq + (size_t)512 * 512;
   RUN(wgrad_run(gKVc, 1024, S_ENC, 512, R, 1024, 512, g->dec_enc.w_qkv + (size_t)512 * 512, 512, st));
-  float* gENC = f((size_t)R * 512);
+  T* gENC = f((size_t)R * 512);
   RUN(transpose_w(Wkv, 1024, 512, wta, st));                             // [512, 1024]
-  RUN(dgrad(gKVc, R, 1024, 512, wta, gENC, 0, nullptr, 0, st));
+  RUN(dgrad<T>(gKVc, R, 1024, 512, wta, gENC, 0, (const T*)nullptr, 0, st));
   RUN(wgrad_run(gQc, 512, S_T1, 512, RQ, 512, 512, g->dec_enc.w_qkv, 512, st));
-  float* gT1 = f((size_t)RQ * 512);
+  T* gT1 = f((size_t)RQ * 512);
   RUN(transpose_w(Wq, 512, 512, wta, st));
-  RUN(dgrad(gQc, RQ, 512, 512, wta, gT1, AITB_EPI_RES, gT1res, 512, st));
+  RUN(dgrad<T>(gQc, RQ, 512, 512, wta, gT1, AITB_EPI_RES, gT1res, 512, st));
   // ---- encoder FFN
-  float* gX2 = f((size_t)R * 512);
+  T* gX2 = f((size_t)R * 512);
   {
-    FfnBwd fb{&w->enc_ffn, &g->enc_ffn, S_X2, S_H1, S_ENC, hb.r_ENC, tdp, AITB_DROP_ENC_FFN, gZ};
+    FfnBwd<T> fb{&w->enc_ffn, &g->enc_ffn, S_X2, S_H1, S_ENC, hb.r_ENC, tdp, AITB_DROP_ENC_FFN, gZ};
     RUN(ffn_backward(fb, R, gENC, gF, gH, gX2, wta, wtb, st));
   }
   // ---- encoder self attention: X2 = LN(AO Wfc^T + X1)
-  float* gA1 = f((size_t)R * 512);
+  T* gA1 = f((size_t)R * 512);
   RUN(ln_bwd_run(gX2, S_X2, w->enc_slf.ln.gamma, w->enc_slf.ln.beta, hb.r_X2, R, 64, 64, gA1, g->enc_slf.ln.gamma,
                  g->enc_slf.ln.beta, st));
-  const float* gA1m = gA1;
+  const T* gA1m = gA1;
   if (dp) {
     RUN(drop_bwd_run(gA1, gZ, td.p, td.seed, AITB_DROP_ENC_SLF_FC, R, 64, 64, st));
     gA1m = gZ;
   }
   RUN(wgrad_run(gA1m, 512, S_AO, 64, R, 512, 64, g->enc_slf.w_fc, 64, st));
   RUN(transpose_w(w->enc_slf.w_fc, 512, 64, wta, st));
-  RUN(dgrad(gA1m, R, 512, 64, wta, gAO, 0, nullptr, 0, st));
-  float* gQKV = f((size_t)R * 1536);
+  RUN(dgrad<T>(gA1m, R, 512, 64, wta, gAO, 0, (const T*)nullptr, 0, st));
+  T* gQKV = f((size_t)R * 1536);
   RUN(attn_bwd_run(S_QKV, 1536, 1, S_QKV + 512, S_QKV + 1024, 1536, w->enc_slf.w_sk, w->enc_slf.b_sk, gAO, bp, 0, 49, gQKV,
                    1536, gQKV + 512, gQKV + 1024, 1536, dz, sv, st, &da_enc));
   RUN(wgrad_run(dz, 512, sv, 64, bp, 512, 64, g->enc_slf.w_sk, 64, st));
   RUN(colsum_run(dz, 512, bp, 512, g->enc_slf.b_sk, st));
   RUN(wgrad_run(gQKV, 1536, S_X1, 512, R, 1536, 512, g->enc_slf.w_qkv, 512, st));
-  float* gX1 = f((size_t)R * 512);
+  T* gX1 = f((size_t)R * 512);
   RUN(transpose_w(w->enc_slf.w_qkv, 1536, 512, wta, st));                // [512, 1536]
-  RUN(dgrad(gQKV, R, 1536, 512, wta, gX1, AITB_EPI_RES, gA1, 512, st));
+  RUN(dgrad<T>(gQKV, R, 1536, 512, wta, gX1, AITB_EPI_RES, gA1, 512, st));
   // ---- encoder input: X1 = LN(enc_emb(pooled) + b + pos) on the 49 real rows (pad rows: LN(pos) -> dgamma / dbeta only)
-  float* gE0 = f((size_t)R49 * 512);
+  T* gE0 = f((size_t)R49 * 512);
   RUN(ln_bwd_run(gX1, S_X1, w->enc_ln.gamma, w->enc_ln.beta, hb.r_X1, R, 64, 49, gE0, g->enc_ln.gamma, g->enc_ln.beta, st));
   if (dp) RUN(drop_bwd_run(gE0, gE0, td.p, td.seed, AITB_DROP_ENC_EMB, R, 64, 49, st));   // in place, compact 49-row layout
   RUN(colsum_run(gE0, 512, R49, 512, g->enc_emb.bias, st));
   RUN(wgrad_run(gE0, 512, S_pooled, 1024, R49, 512, 1024, g->enc_emb.w, 1024, st));
-  float* gPooled = f((size_t)R49 * 1024);
+  T* gPooled = f((size_t)R49 * 1024);
   RUN(transpose_w(w->enc_emb.w, 512, 1024, wta, st));                    // [1024, 512]
-  RUN(dgrad(gE0, R49, 512, 1024, wta, gPooled, 0, nullptr, 0, st));
+  RUN(dgrad<T>(gE0, R49, 512, 1024, wta, gPooled, 0, (const T*)nullptr, 0, st));
   for (int g0 = 0; g0 < bp; g0 += 32768) {
     const int gn = bp - g0 < 32768 ? bp - g0 : 32768;
-    RUN(transpose_run(gPooled + (size_t)g0 * 49 * 1024, AITB_F32, grad_props + (size_t)g0 * 1024 * 49, AITB_F32, gn, 1024, 49,
+    RUN(transpose_run(gPooled + (size_t)g0 * 49 * 1024, dt, grad_props + (size_t)g0 * 1024 * 49, AITB_F32, gn, 1024, 49,
                       0, st));
   }
   // ---- query side: T1 = LN(AOd Wfc^T + T0), T0 = LN(dec_emb(q) + b + pos), Qc = T1 Wq^T
-  float* gS1 = f((size_t)RQ * 512);
+  T* gS1 = f((size_t)RQ * 512);
   RUN(ln_bwd_run(gT1, S_T1, w->dec_slf.ln.gamma, w->dec_slf.ln.beta, hb.r_T1, RQ, 64, 64, gS1, g->dec_slf.ln.gamma,
                  g->dec_slf.ln.beta, st));
-  const float* gS1m = gS1;
+  const T* gS1m = gS1;
   if (dp) {
     RUN(drop_bwd_run(gS1, gZ, td.p, td.seed, AITB_DROP_DEC_SLF_FC, RQ, 64, 64, st));
     gS1m = gZ;
   }
   RUN(wgrad_run(gS1m, 512, S_AOd, 64, RQ, 512, 64, g->dec_slf.w_fc, 64, st));
-  float* gAOd = f((size_t)RQ * 64);
+  T* gAOd = f((size_t)RQ * 64);
   RUN(transpose_w(w->dec_slf.w_fc, 512, 64, wta, st));
-  RUN(dgrad(gS1m, RQ, 512, 64, wta, gAOd, 0, nullptr, 0, st));
-  float* gQKVd = f((size_t)RQ * 1536);
-  float* dzd = dz + (size_t)bp * 512;
-  float* svd = sv + (size_t)bp * 64;
+  RUN(dgrad<T>(gS1m, RQ, 512, 64, wta, gAOd, 0, (const T*)nullptr, 0, st));
+  T* gQKVd = f((size_t)RQ * 1536);
+  T* dzd = dz + (size_t)bp * 512;
+  T* svd = sv + (size_t)bp * 64;
   RUN(attn_bwd_run(S_QKVd, 1536, 1, S_QKVd + 512, S_QKVd + 1024, 1536, w->dec_slf.w_sk, w->dec_slf.b_sk, gAOd, B, 1, 64, gQKVd,
                    1536, gQKVd + 512, gQKVd + 1024, 1536, dzd, svd, st, &da_dec));
   RUN(wgrad_run(dzd, 512, svd, 64, B, 512, 64, g->dec_slf.w_sk, 64, st));
   RUN(colsum_run(dzd, 512, B, 512, g->dec_slf.b_sk, st));
   RUN(wgrad_run(gQKVd, 1536, S_T0, 512, RQ, 1536, 512, g->dec_slf.w_qkv, 512, st));
-  float* gT0 = f((size_t)RQ * 512);
+  T* gT0 = f((size_t)RQ * 512);
   RUN(transpose_w(w->dec_slf.w_qkv, 1536, 512, wta, st));
-  RUN(dgrad(gQKVd, RQ, 1536, 512, wta, gT0, AITB_EPI_RES, gS1, 512, st));
-  float* gQ0 = f((size_t)RQ * 512);
+  RUN(dgrad<T>(gQKVd, RQ, 1536, 512, wta, gT0, AITB_EPI_RES, gS1, 512, st));
+  T* gQ0 = f((size_t)RQ * 512);
   RUN(ln_bwd_run(gT0, S_T0, w->dec_ln.gamma, w->dec_ln.beta, hb.r_T0, RQ, 64, 64, gQ0, g->dec_ln.gamma, g->dec_ln.beta, st));
   if (dp) RUN(drop_bwd_run(gQ0, gQ0, td.p, td.seed, AITB_DROP_DEC_EMB, RQ, 64, 64, st));
   RUN(colsum_run(gQ0, 512, RQ, 512, g->dec_emb.bias, st));
   RUN(wgrad_run(gQ0, 512, S_qtok, 1024, RQ, 512, 1024, g->dec_emb.w, 1024, st));
-  float* gQtok = f((size_t)RQ * 1024);
+  T* gQtok = f((size_t)RQ * 1024);
   RUN(transpose_w(w->dec_emb.w, 512, 1024, wta, st));
-  RUN(dgrad(gQ0, RQ, 512, 1024, wta, gQtok, 0, nullptr, 0, st));
-  RUN(transpose_run(gQtok, AITB_F32, grad_query, AITB_F32, B, 1024, 64, 0, st));
+  RUN(dgrad<T>(gQ0, RQ, 512, 1024, wta, gQtok, 0, (const T*)nullptr, 0, st));
+  RUN(transpose_run(gQtok, dt, grad_query, AITB_F32, B, 1024, 64, 0, st));
   AITB_REQUIRE(b.off <= workspace_bytes, "aitb_ait_backward: internal workspace accounting error (%zu > %zu)", b.off,
                workspace_bytes);
   return 0;
 }
 
+extern "C" {
+
 int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, int B, int P, const void* saved,
                       size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
                       void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
-  return ait_backward_impl(w, grad_out_nchw, 0, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
-                           stream);
+  if (w && w->dtype == AITB_BF16)
+    return ait_backward_impl<bf16_t>(w, grad_out_nchw, 0, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace,
+                                     workspace_bytes, stream);
+  return ait_backward_impl<float>(w, grad_out_nchw, 0, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
+                                  stream);
 }
 
 int aitb_ait_backward_tm(const aitb_head_weights* w, const float* grad_out_tm, int B, int P, const void* saved,
                          size_t saved_bytes, const aitb_ait_grads* g, float* grad_props, float* grad_query,
                          void* workspace, size_t workspace_bytes, aitb_stream_t stream) {
   AITB_REQUIRE(((uintptr_t)grad_out_tm & 15) == 0, "aitb_ait_backward_tm: grad_out must be 16-byte aligned");
-  return ait_backward_impl(w, grad_out_tm, 1, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
-                           stream);
+  AITB_REQUIRE(w && w->dtype == AITB_F32, "aitb_ait_backward_tm: the token-major hand-over exists in the fp32-storage configuration only");
+  return ait_backward_impl<float>(w, grad_out_tm, 1, B, P, saved, saved_bytes, g, grad_props, grad_query, workspace, workspace_bytes,
+                                  stream);
 }
 
 int aitb_ln_bwd(const float* g, const float* y, const float* gamma, const float* beta, const float* rstd, int rows, int grp,
@@ -1312,6 +1360,10 @@ int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order,
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
                aitb_stream_t stream) {
   return wgrad_run(dy, ldy, x, ldx, M, N, K, dw, ldw, (cudaStream_t)stream);
+}
+int aitb_wgrad_bf16(const void* dy, int ldy, const void* x, int ldx, int M, int N, int K, float* dw, int ldw,
+                    aitb_stream_t stream) {
+  return wgrad_run((const bf16_t*)dy, ldy, (const bf16_t*)x, ldx, M, N, K, dw, ldw, (cudaStream_t)stream);
 }
 
 int aitb_wgrad_conv(const float* dy, int ldy, const float* x, int G, int S, int C, int N, int groups, int taps, float* dw,

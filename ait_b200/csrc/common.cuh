@@ -507,6 +507,38 @@ __device__ __forceinline__ void drop_frag(const DropCfg& dc, int grp, int h, int
   }
 }
 
+// ---- training kernels (bwd.cu, dropout.cu): generic 4 / 2 / 1-element access of fp32 or bf16 storage
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// four consecutive activation / gradient elements (16-byte aligned fp32, 8-byte aligned bf16); stores round to the
+// storage's operand precision: tf32 (RN) for fp32 storage -- the next consumer is a tf32 MMA --, bf16 (RN) otherwise
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4r(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
+}
+__device__ __forceinline__ void st4r(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ void st2r(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(tf32r(a), tf32r(b)); }
+__device__ __forceinline__ void st2r(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 // load / store 8 consecutive activation elements (16-byte aligned for bf16, 32 for fp32)
 __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);

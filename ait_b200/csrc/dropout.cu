@@ -10,6 +10,7 @@
 // projection output = dx * mask / (1 - p); the residual path takes dx unmasked).
 // The reference's Philox stream cannot be reproduced (torch's generator state, one draw per element in launch order):
 // parity is checked with OUR masks injected into the oracle (aitb_dropout_mask / aitb_attn_dropout_mask materialise them).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,16 +19,11 @@
 
 namespace aitb {
 
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // z [rows, 512] in place -> y; rows are groups of `grp` (64) tokens, z of rows >= `valid` of a group reads as 0; pos row = row % grp; residual row =
 // ((row / res_div) / res_rep) * res_div + row % res_div  (res_rep = P: the unit's residual broadcast to its P pairs)
+template <typename T>
 __global__ void __launch_bounds__(256)
-drop_res_ln_kernel(float* __restrict__ z, const float* __restrict__ pos, int grp, int valid, const float* __restrict__ res, int res_div,
+drop_res_ln_kernel(T* __restrict__ z, const float* __restrict__ pos, int grp, int valid, const T* __restrict__ res, int res_div,
                    int res_rep, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, DropCfg dc,
                    int rows, int round_tf, float* __restrict__ rstd_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -36,14 +32,14 @@ drop_res_ln_kernel(float* __restrict__ z, const float* __restrict__ pos, int grp
     // y = LayerNorm(dropout(pos_t)) -- NOT dead: they are queries of the encoder self-attention and enter its head gate
     const bool pad = row % grp >= valid;
     float v[16];
-    float* zr = z + (size_t)row * 512;
+    T* zr = z + (size_t)row * 512;
     const float* pr = pos ? pos + (size_t)(row % grp) * 512 : nullptr;
-    const float* rr = res ? res + (size_t)(((row / res_div) / res_rep) * res_div + row % res_div) * 512 : nullptr;
+    const T* rr = res ? res + (size_t)(((row / res_div) / res_rep) * res_div + row % res_div) * 512 : nullptr;
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = j * 128 + lane * 4;
-      float4 x = pad ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(zr + c);
+      float4 x = pad ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(zr + c);
       if (pr) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(pr + c));
         x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
@@ -53,7 +49,7 @@ drop_res_ln_kernel(float* __restrict__ z, const float* __restrict__ pos, int grp
         x.x *= drop_mul(dc, d.x); x.y *= drop_mul(dc, d.y); x.z *= drop_mul(dc, d.z); x.w *= drop_mul(dc, d.w);
       }
       if (rr) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rr + c));
+        const float4 q = ld4(rr + c);
         x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
       }
       v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
@@ -75,16 +71,17 @@ drop_res_ln_kernel(float* __restrict__ z, const float* __restrict__ pos, int grp
       o.y = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
       o.z = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
       o.w = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
-      if (round_tf) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
-      *reinterpret_cast<float4*>(zr + c) = o;
+      if (sizeof(T) == 2 || round_tf) st4r(zr + c, o);
+      else *reinterpret_cast<float4*>(zr + c) = o;
     }
   }
 }
 
 // dz[r', :] = dx[r', :] * mask(row, :) / (1 - p); dx / dz hold `valid` of every `grp` rows (the encoder's 64 -> 49 compaction):
 // r' = (row / grp) * valid + row % grp for row % grp < valid.  dz may alias dx.
+template <typename T>
 __global__ void __launch_bounds__(256)
-drop_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dz, DropCfg dc, int rows, int grp, int valid) {
+drop_bwd_kernel(const T* __restrict__ dx, T* __restrict__ dz, DropCfg dc, int rows, int grp, int valid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const int t = row % grp;
@@ -93,11 +90,10 @@ drop_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dz, DropCfg dc
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = j * 128 + lane * 4;
-      float4 x = *reinterpret_cast<const float4*>(dx + o + c);
+      float4 x = ld4(dx + o + c);
       const uint4 d = drop_row_draw(dc, (uint32_t)row, (uint32_t)(j * 32 + lane));
-      x.x = tf32_rn(x.x * drop_mul(dc, d.x)); x.y = tf32_rn(x.y * drop_mul(dc, d.y));
-      x.z = tf32_rn(x.z * drop_mul(dc, d.z)); x.w = tf32_rn(x.w * drop_mul(dc, d.w));
-      *reinterpret_cast<float4*>(dz + o + c) = x;
+      x.x *= drop_mul(dc, d.x); x.y *= drop_mul(dc, d.y); x.z *= drop_mul(dc, d.z); x.w *= drop_mul(dc, d.w);
+      st4r(dz + o + c, x);
     }
   }
 }
@@ -131,26 +127,47 @@ attn_drop_mask_kernel(DropCfg dc, int G, float* __restrict__ out) {
 
 int check_launch(const char* what);
 
-int drop_res_ln_run(float* z, const float* pos, int grp, int valid, const float* res, int res_div, int res_rep, const float* gamma,
-                    const float* beta, float eps, float p, unsigned long long seed, int site, int rows, int round_tf,
-                    float* rstd_out, cudaStream_t st) {
+template <typename T>
+static int drop_res_ln_run_t(T* z, const float* pos, int grp, int valid, const T* res, int res_div, int res_rep, const float* gamma,
+                             const float* beta, float eps, float p, unsigned long long seed, int site, int rows, int round_tf,
+                             float* rstd_out, cudaStream_t st) {
   AITB_REQUIRE(z && gamma && beta && rows > 0 && grp > 0 && valid > 0 && valid <= grp && res_div > 0 && res_rep > 0 && p >= 0.f &&
                    p < 1.f, "drop_res_ln: bad arguments");
   int grid = (rows + 7) / 8;
   if (grid > 8 * current_sm_count()) grid = 8 * current_sm_count();
-  drop_res_ln_kernel<<<grid, 256, 0, st>>>(z, pos, grp, valid, res, res_div, res_rep, gamma, beta, eps, make_drop(p, seed, site), rows,
-                                           round_tf, rstd_out);
+  drop_res_ln_kernel<T><<<grid, 256, 0, st>>>(z, pos, grp, valid, res, res_div, res_rep, gamma, beta, eps, make_drop(p, seed, site),
+                                              rows, round_tf, rstd_out);
   return check_launch("drop_res_ln_kernel");
 }
+int drop_res_ln_run(float* z, const float* pos, int grp, int valid, const float* res, int res_div, int res_rep, const float* gamma,
+                    const float* beta, float eps, float p, unsigned long long seed, int site, int rows, int round_tf,
+                    float* rstd_out, cudaStream_t st) {
+  return drop_res_ln_run_t<float>(z, pos, grp, valid, res, res_div, res_rep, gamma, beta, eps, p, seed, site, rows, round_tf, rstd_out, st);
+}
+int drop_res_ln_run(__nv_bfloat16* z, const float* pos, int grp, int valid, const __nv_bfloat16* res, int res_div, int res_rep,
+                    const float* gamma, const float* beta, float eps, float p, unsigned long long seed, int site, int rows,
+                    int round_tf, float* rstd_out, cudaStream_t st) {
+  return drop_res_ln_run_t<__nv_bfloat16>(z, pos, grp, valid, res, res_div, res_rep, gamma, beta, eps, p, seed, site, rows, round_tf,
+                                          rstd_out, st);
+}
 
-int drop_bwd_run(const float* dx, float* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
-                 cudaStream_t st) {
+template <typename T>
+static int drop_bwd_run_t(const T* dx, T* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
+                          cudaStream_t st) {
   AITB_REQUIRE(dx && dz && rows > 0 && grp > 0 && valid > 0 && valid <= grp && rows % grp == 0 && p > 0.f && p < 1.f,
                "drop_bwd: bad arguments");
   int grid = (rows + 7) / 8;
   if (grid > 8 * current_sm_count()) grid = 8 * current_sm_count();
-  drop_bwd_kernel<<<grid, 256, 0, st>>>(dx, dz, make_drop(p, seed, site), rows, grp, valid);
+  drop_bwd_kernel<T><<<grid, 256, 0, st>>>(dx, dz, make_drop(p, seed, site), rows, grp, valid);
   return check_launch("drop_bwd_kernel");
+}
+int drop_bwd_run(const float* dx, float* dz, float p, unsigned long long seed, int site, int rows, int grp, int valid,
+                 cudaStream_t st) {
+  return drop_bwd_run_t<float>(dx, dz, p, seed, site, rows, grp, valid, st);
+}
+int drop_bwd_run(const __nv_bfloat16* dx, __nv_bfloat16* dz, float p, unsigned long long seed, int site, int rows, int grp,
+                 int valid, cudaStream_t st) {
+  return drop_bwd_run_t<__nv_bfloat16>(dx, dz, p, seed, site, rows, grp, valid, st);
 }
 
 }  // namespace aitb

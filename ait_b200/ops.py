@@ -264,19 +264,19 @@ def pool_heads(top, P, qfeat=None, w_bbox=None, b_bbox=None, w1=None, b1=None, w
 # training building blocks (fp32 storage, tf32 tensor-core math)
 # ---------------------------------------------------------------------------------------------
 def wgrad(dy, x, dw=None, N=None, K=None):
-    """dw[N, K] += dy[:, :N]^T x[:, :K] for row-major fp32 dy [M, ldy], x [M, ldx] (dw zero-initialised when
-    not given)."""
+    """dw[N, K] += dy[:, :N]^T x[:, :K] for row-major dy [M, ldy], x [M, ldx], both fp32 (tf32 MMAs) or both bf16; dw
+    fp32 (zero-initialised when not given)."""
     lib = L.load()
     _need_cuda(dy, x)
-    if dy.dtype != torch.float32 or x.dtype != torch.float32 or dy.stride(-1) != 1 or x.stride(-1) != 1:
-        raise RuntimeError("ait_b200.wgrad: row-major float32 operands required")
+    if dy.dtype != x.dtype or dy.dtype not in (torch.float32, torch.bfloat16) or dy.stride(-1) != 1 or x.stride(-1) != 1:
+        raise RuntimeError("ait_b200.wgrad: row-major operands of one dtype (float32 or bfloat16) required")
     M = dy.shape[0]
     N = N or dy.shape[1]
     K = K or x.shape[1]
     if dw is None:
         dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
-    L.check(lib.aitb_wgrad(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw), dw.stride(0),
-                           L.stream_ptr()))
+    fn = lib.aitb_wgrad if dy.dtype == torch.float32 else lib.aitb_wgrad_bf16
+    L.check(fn(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw), dw.stride(0), L.stream_ptr()))
     return dw
 
 

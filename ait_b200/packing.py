@@ -272,11 +272,15 @@ class HeadEngine:
         return out
 
     def ait_forward_train(self, x_props, x_query, token_major_out=False):
-        """Transformer.forward keeping the activations the backward needs -> (out, saved buffer).
-        token_major_out: no NCHW copy -- `out` is the [bp,64,1024] token-major, tf32-rounded result living inside the saved
-        buffer (the operand layout of the next stage's GEMMs)."""
-        if self.mode != "tf32":
-            raise RuntimeError("ait_b200: the training path runs in the fp32-storage / tf32 configuration")
+        """Transformer.forward keeping the activations the backward needs -> (out, saved buffer).  Engine dtype "tf32" (fp32
+        storage, tf32 tensor-core math) or "bf16" (bf16 storage and math; fp32 accumulation, statistics, parameter gradients).
+        token_major_out (tf32 only): no NCHW copy -- `out` is the [bp,64,1024] token-major, tf32-rounded result living inside
+        the saved buffer (the operand layout of the next stage's GEMMs)."""
+        if self.mode not in ("tf32", "bf16"):
+            raise RuntimeError("ait_b200: the training path runs in the fp32-storage / tf32 or the bf16 configuration "
+                               "(engine dtype 'tf32' | 'bf16'), not %r" % self.mode)
+        if token_major_out and self.mode != "tf32":
+            raise RuntimeError("ait_b200: the token-major training hand-over exists in the tf32 configuration only")
         lib = L.load()
         ops._need_cuda(x_props, x_query)
         x_props = x_props.contiguous().float()
@@ -301,6 +305,8 @@ class HeadEngine:
     def ait_backward(self, grad_out, saved, bs, P, token_major_grad=False):
         """-> (grad_props [bp,1024,7,7], grad_query [bs,1024,8,8], [gradient per name of ait_param_names()]).
         token_major_grad: grad_out is [bp,64,1024] token-major and already tf32-rounded (see ait_forward_train)."""
+        if token_major_grad and self.mode != "tf32":
+            raise RuntimeError("ait_b200: the token-major training hand-over exists in the tf32 configuration only")
         lib = L.load()
         dev = grad_out.device
         grad_out = grad_out.contiguous().float()

@@ -124,11 +124,13 @@ def set_dropout(module, p=None, p_attn=None):
 class _AITTrainFunction(torch.autograd.Function):
     """Transformer.forward with a hand-written backward (libaitb200: tcgen05 dgrad / wgrad GEMMs, LayerNorm /
     attention / selective-head-gate backward kernels).  The reference relies on torch autograd over
-    system/Models.py:231-280; gradients match it to tf32 accuracy (tests/test_gpu_train.py)."""
+    system/Models.py:231-280; gradients match it to tf32 accuracy, or to bf16 accuracy when the module was built with
+    compute_dtype=torch.bfloat16 (tests/test_gpu_train.py).  Inputs, outputs and all gradients are fp32 tensors either way."""
 
     @staticmethod
     def forward(ctx, x_props, x_query, module, tm_out, drop, *params):
-        engine = packing.HeadEngine(transformer=module, dtype="tf32")     # weights change every step: repack
+        # weights change every step: repack.  compute_dtype bfloat16 -> the bf16 training configuration, else fp32 storage / tf32 math
+        engine = packing.HeadEngine(transformer=module, dtype="bf16" if packing.L.mode_name(module.compute_dtype) == "bf16" else "tf32")
         engine.set_train_dropout(*drop)             # (p_drop, p_attn, seed): the backward regenerates the same masks
         out, saved = engine.ait_forward_train(x_props, x_query, token_major_out=tm_out)
         ctx.engine, ctx.saved, ctx.tm_out = engine, saved, tm_out

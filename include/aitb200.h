@@ -398,6 +398,10 @@ int aitb_det_assemble(const float* pred, const float* cls, const int64_t* order,
  * leading dimensions ldy / ldx; dw must be initialised by the caller, e.g. zeroed).  N % 128 == 0, K % 64 == 0. */
 int aitb_wgrad(const float* dy, int ldy, const float* x, int ldx, int M, int N, int K, float* dw, int ldw,
                aitb_stream_t stream);
+/* same for bf16 row-major activations (the bf16 training configuration): both operands MN-major bf16 tiles in the ordinary
+ * 128-byte swizzle, kind::f16 MMAs of K = 16, dW fp32 accumulated.  ldy / ldx multiples of 8. */
+int aitb_wgrad_bf16(const void* dy, int ldy, const void* x, int ldx, int M, int N, int K, float* dw, int ldw,
+                    aitb_stream_t stream);
 /* Weight gradient of a (grouped) 1x1 / 3x3 stride-1 "same" convolution on a channels-last S x S map (S = 4 | 8) WITHOUT an
  * im2col buffer: x [G,S,S,C] is read through a 4-D TMA view, one shifted box per tap, out-of-map rows zero-filled (= the
  * padding); dW [N, taps*Cg] (tap-major, Cg = C / groups) += dY^T * shifted X.  groups > 1: N / groups must be 128 (one
