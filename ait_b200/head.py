@@ -11,6 +11,7 @@ import torch.nn as nn
 from . import packing
 from .modules import SKNet, make_layer4
 from .roi_layers import ROIAlign
+from ._lib import mode_name as packing_mode
 from .system.Models import Transformer
 
 POOLING_SIZE = 7          # cfg.POOLING_SIZE (lib/model/utils/config.py:294)
@@ -69,7 +70,7 @@ class DetectionHead(nn.Module):
         """The same slice of `_fasterRCNN.forward` (:273-335) as a differentiable training step (BASELINE config 4):
         ROIAlign -> AIT -> SKNet -> `_head_to_tail` (pairs and queries) -> bbox / score heads, every stage with the
         library's own forward-keeping-activations + backward (`_ROIAlign`, `_AITTrainFunction`, sk_train, top_train,
-        targets.score_heads; fp32 storage, tf32 tensor-core math, dropout 0).  Returns (score [B*P,2] logits,
+        targets.score_heads; fp32 storage, tf32 tensor-core math; the Transformer applies its training-mode dropout, see system/Models.py).  Returns (score [B*P,2] logits,
         bbox_pred [B*P,4]) -- what the reference's losses consume (:349-361).  Gradients reach non_img, non_qry and
         every trainable parameter (AIT 46, the four SK convolutions + biases, the ten layer-4 convolutions -- BatchNorm is
         frozen like `set_bn_fix` --, the three Linear layers); `sk.*.fc` / `sk.*.sk` get none, as in the reference,
@@ -83,8 +84,10 @@ class DetectionHead(nn.Module):
         props = self.RCNN_roi_align(non_img, rois.reshape(-1, 5))                 # :279
         # stage-to-stage hand-over in the GEMM operand layout (token-major / channels-last, tf32-rounded): AIT -> SKNet -> layer4
         # without an NCHW round trip, forward or backward
-        props = self.transformer(x_props=props, x_query=non_qry, token_major_out=True)         # :289
-        props, query = sk_train.sknet_train(self.sk, props, non_qry, channels_last_out=True, channels_last_in=True)   # :294
+        # (the bf16 AIT training configuration returns fp32 NCHW: the rest of the head trains in fp32 storage / tf32 math)
+        tm = packing_mode(self.transformer.compute_dtype) != "bf16"
+        props = self.transformer(x_props=props, x_query=non_qry, token_major_out=tm)           # :289
+        props, query = sk_train.sknet_train(self.sk, props, non_qry, channels_last_out=True, channels_last_in=tm)   # :294
         pf = top_train.head_to_tail_train(self.RCNN_top, props, channels_last=True)            # :299
         qf = top_train.head_to_tail_train(self.RCNN_top, query, channels_last=True)            # :300
         return targets.score_heads(pf, qf, P, self.RCNN_bbox_pred, self.RCNN_cls_score)   # :318-335

@@ -113,9 +113,52 @@ def train_step_extra(dev, tf_burst):
                "finite": bool(all(torch.isfinite(p_.grad).all() for p_ in head.parameters() if p_.grad is not None))}
         del head, maps, qrys, losses
         torch.cuda.empty_cache()
+        out["ait_step"] = ait_step_extra(dev, B, P)
         return out
     except Exception as e:  # supplementary: report, never break the headline line
         return {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
+def ait_step_extra(dev, B, P):
+    """The AIT module's own training step (Transformer forward + backward, the part of configs[3] that exists in both
+    storage configurations) in fp32 storage / tf32 math and in bf16, each without and with the reference's training-mode
+    dropout (0.1 at the nn.Dropout sites, 0.1 on the attention probabilities): ms per forward+backward, 2 warm-up + 3 timed."""
+    import torch
+    from ait_b200.system.Models import Transformer
+    res = {"workload": "Transformer.train() forward+backward, %d units x %d proposals; x_props [bp,1024,7,7], x_query [B,1024,8,8]" % (B, P)}
+    g = torch.Generator().manual_seed(5)
+    xp = torch.rand(B * P, 1024, 7, 7, generator=g).to(dev).requires_grad_()
+    xq = torch.rand(B, 1024, 8, 8, generator=g).to(dev).requires_grad_()
+    gout = torch.randn(B * P, 1024, 8, 8, generator=g).to(dev)
+    for name, cd, p in (("tf32", torch.float32, 0.0), ("tf32_dropout", torch.float32, 0.1), ("bf16", torch.bfloat16, 0.0),
+                        ("bf16_dropout", torch.bfloat16, 0.1)):
+        try:
+            torch.manual_seed(0)
+            m = Transformer(n_layers=1, dropout=p, n_position=64, attn_dropout=p, compute_dtype=cd).to(dev).train()
+
+            def step():
+                m.zero_grad(set_to_none=True)
+                xp.grad = None
+                xq.grad = None
+                m(xp, xq).backward(gout)
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st.record()
+            for _ in range(3):
+                step()
+            en.record()
+            torch.cuda.synchronize()
+            ms = st.elapsed_time(en) / 3
+            ok = bool(torch.isfinite(xp.grad).all() and all(torch.isfinite(q.grad).all() for q in m.parameters()))
+            res[name] = {"ms_per_step": ms, "pairs_per_s": B * P / (ms * 1e-3), "finite": ok}
+            del m
+            torch.cuda.empty_cache()
+        except Exception as e:
+            res[name] = {"failed": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return res
 
 
 def peaks():

@@ -638,3 +638,47 @@ def test_whole_head_training_step_matches_reference_golden_gradients():
         errs[name] = check(name, params[name].grad, entry)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
     print("whole-head train vs reference golden: worst rel-L2", [(k, "%.1e" % v) for k, v in worst])
+
+
+def test_whole_head_training_step_with_default_dropout():
+    """`DetectionHead().train()` out of the box (dropout 0.1 like `_fasterRCNN`'s Transformer, attention dropout 0.1): the
+    whole-head training step runs with the masks active -- finite losses and gradients for every trainable parameter, a
+    reproducible step under torch.manual_seed, and losses that differ from the dropout-free step (train mode no
+    longer raises out of the box)."""
+    from ait_b200 import synth
+    from ait_b200.system.Models import set_dropout
+    B, P = 2, 4
+    head = synth.make_head(seed=0, calibrated=True, randomize_bn=True).to(DEV).train()
+    maps = torch.stack([synth.c4_map(u) for u in range(B)]).to(DEV).requires_grad_()
+    qrys = torch.stack([synth.query_feat(u) for u in range(B)]).to(DEV).requires_grad_()
+    rois = torch.stack([synth.random_rois(u, P, batch_index=u) for u in range(B)]).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    label = (torch.rand(B * P, generator=g) < 0.5).long().to(DEV)
+    tgt = (0.3 * torch.randn(B * P, 4, generator=g)).to(DEV)
+    inw = (label > 0).float().view(-1, 1).expand(-1, 4).contiguous()
+
+    def step(seed):
+        head.zero_grad(set_to_none=True)
+        maps.grad = None
+        torch.manual_seed(seed)
+        losses = head.training_losses(maps, qrys, rois, label, tgt, inw, inw)
+        sum(losses).backward()
+        torch.cuda.synchronize()
+        return [float(x.detach()) for x in losses], maps.grad.clone()
+
+    l1, g1 = step(7)
+    assert head.transformer.last_dropout_seed != 0
+    l2, g2 = step(7)
+    l3, _ = step(8)
+    assert all(torch.isfinite(torch.tensor(l1))) and torch.isfinite(g1).all()
+    # no gradient by design: frozen BatchNorm (`set_bn_fix`) and the `sk.*.fc` / `sk.*.sk` layers SKBlock.forward discards
+    frozen = lambda n: ".bn" in n or "downsample.1" in n or (n.startswith("sk.") and (".fc." in n or ".sk." in n))   # noqa: E731
+    missing = [n for n, p_ in head.named_parameters() if p_.requires_grad and p_.grad is None and not frozen(n)]
+    assert not missing, missing
+    assert sum(1 for p_ in head.parameters() if p_.grad is not None) == 70
+    assert l1 == l2                                     # same seed, same masks (losses are reduced deterministically)
+    assert float((g1 - g2).abs().max()) <= 1e-3 * float(g1.abs().max())       # ROIAlign backward: atomics order only
+    assert l1 != l3
+    set_dropout(head, 0.0, 0.0)
+    l0, _ = step(7)
+    assert head.transformer.last_dropout_seed == 0 and l0 != l1
