@@ -863,7 +863,8 @@ size_t aitb_ait_saved_offset(int B, int P, int which) {
   Bump b{base, 0};
   HeadBufs hb;
   carve_train(b, hb, B, P);
-  return (size_t)((const uint8_t*)(which == 1 ? hb.AIT : hb.pooled) - base);
+  const void* p = which == 1 ? hb.AIT : which == 2 ? hb.Hh : which == 3 ? hb.Hh2 : hb.pooled;
+  return (size_t)((const uint8_t*)p - base);
 }
 
 }  // extern "C"

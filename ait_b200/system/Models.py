@@ -109,6 +109,9 @@ class Decoder(_Holder):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
 
 
+_keep_saved_for_tests = [False, None]     # [enabled, the last training forward's saved-activation buffer]
+
+
 def set_dropout(module, p=None, p_attn=None):
     """Set the training-mode dropout probabilities of every AIT sub-layer below `module` (a Transformer or anything that
     contains one): p -> the nn.Dropout sites, p_attn -> the attention probabilities (the reference hard-wires 0.1 there).
@@ -134,6 +137,8 @@ class _AITTrainFunction(torch.autograd.Function):
         engine.set_train_dropout(*drop)             # (p_drop, p_attn, seed): the backward regenerates the same masks
         out, saved = engine.ait_forward_train(x_props, x_query, token_major_out=tm_out)
         ctx.engine, ctx.saved, ctx.tm_out = engine, saved, tm_out
+        if _keep_saved_for_tests[0]:
+            _keep_saved_for_tests[1] = saved       # the parity tests read the device's FFN ReLU decisions out of it
         ctx.bs, ctx.num_props = x_query.shape[0], x_props.shape[0] // x_query.shape[0]
         ctx.in_dtypes = (x_props.dtype, x_query.dtype)
         return out

@@ -23,7 +23,8 @@ from . import ops
 from .packing import round_to_tf32
 
 _F = L.EPI_BIAS | L.EPI_RELU
-_last_saved_for_tests = None
+_last_saved_for_tests = None      # the last call's saved activations
+_saved_log_for_tests = None       # tests set this to a list: every call appends its saved activations (props call, then query call)
 
 
 def _tap_major(w):
@@ -112,6 +113,8 @@ class _HeadToTailFn(torch.autograd.Function):
         ctx.G, ctx.consts, ctx.packed, ctx.saved, ctx.x0, ctx.cl_in = G, consts, packed, saved, x0, cl_in
         global _last_saved_for_tests
         _last_saved_for_tests = saved   # the parity test rebuilds the reference with exactly these ReLU masks
+        if _saved_log_for_tests is not None:
+            _saved_log_for_tests.append(saved)
         ctx.wshapes = [tuple(w.shape) for w in weights]
         return feat
 

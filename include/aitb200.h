@@ -447,7 +447,9 @@ int aitb_ait_backward(const aitb_head_weights* w, const float* grad_out_nchw, in
                       void* workspace, size_t workspace_bytes, aitb_stream_t stream);
 /* Layout hand-over inside a training step (no NCHW round trip between AIT and the next stage): aitb_ait_forward_train
  * accepts out_nchw == NULL and leaves the token-major result [bp*64, 1024] (row = pair*64 + y*8 + x, tf32-rounded) in
- * `saved` at byte offset aitb_ait_saved_offset(B, P, 1) (which = 0: the token-major pooled input [bp*49, 1024]);
+ * `saved` at byte offset aitb_ait_saved_offset(B, P, 1) (which = 0: the token-major pooled input [bp*49, 1024]; 2 / 3: the
+ * post-ReLU hidden tensors [bp*64, 2048] of the encoder / decoder FFN -- tests read the device's ReLU decisions there;
+ * offsets of the fp32-storage configuration);
  * aitb_ait_backward_tm takes the incoming gradient in that same token-major layout, already rounded to tf32. */
 size_t aitb_ait_saved_offset(int B, int P, int which);
 int aitb_ait_backward_tm(const aitb_head_weights* w, const float* grad_out_tm, int B, int P, const void* saved,

@@ -16,6 +16,22 @@ import torch.nn.functional as F
 from . import c_ops
 
 
+# Tests only: callable(tag, pre_activation) -> multiplier mask (or None = plain ReLU).  The training parity tests rebuild the
+# fp64 reference graph with the DEVICE's ReLU decisions (a tf32 forward flips the mask of hidden units whose pre-activation is
+# within rounding error of zero; with the masks injected both sides differentiate the same piecewise-linear function).
+# Tags: "enc_ffn", "dec_ffn", "l4.<call index>.<block>.<1|2|3>" (call index: head_to_tail calls in order, props then query).
+RELU_HOOK = None
+_l4_calls = [0]
+
+
+def _relu(x, tag):
+    if RELU_HOOK is not None:
+        m = RELU_HOOK(tag, x)
+        if m is not None:
+            return x * m.to(device=x.device, dtype=x.dtype)
+    return F.relu(x)
+
+
 def _sub(sd, prefix):
     n = len(prefix)
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
@@ -67,9 +83,9 @@ def _mha(w, q_in, k_in, v_in, mask, drop_attn=None, drop_fc=None):
     return F.layer_norm(o, (512,), w["layer_norm.weight"], w["layer_norm.bias"], eps=1e-6)
 
 
-def _ffn(w, x, drop=None):
+def _ffn(w, x, drop=None, tag="ffn"):
     """PositionwiseFeedForward.forward (system/SubLayers.py:177-187); drop [b,l,512]: injected multipliers of :182."""
-    y = F.linear(F.relu(F.linear(x, w["w_1.weight"], w["w_1.bias"])), w["w_2.weight"], w["w_2.bias"])
+    y = F.linear(_relu(F.linear(x, w["w_1.weight"], w["w_1.bias"]), tag), w["w_2.weight"], w["w_2.bias"])
     if drop is not None:
         y = y * drop
     y = y + x
@@ -117,7 +133,7 @@ def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False, dro
     e = F.layer_norm(e, (512,), w["encoder.layer_norm.weight"], w["encoder.layer_norm.bias"], eps=1e-6)
     el = _sub(w, "encoder.layer_stack.0.")
     e = _mha(_sub(el, "slf_attn."), e, e, e, src_mask, heads("enc_slf_attn"), rows("enc_slf_fc"))
-    e = _ffn(_sub(el, "pos_ffn."), e, rows("enc_ffn"))
+    e = _ffn(_sub(el, "pos_ffn."), e, rows("enc_ffn"), "enc_ffn")
     # Decoder.forward (:143-172)
     d = trg + w["decoder.position_enc.pos_table"][:, :n_t]
     if rows("dec_emb", True) is not None:                                          # Decoder.dropout (:152)
@@ -126,7 +142,7 @@ def ait_forward(sd, x_props, x_query, dtype=torch.float32, return_enc=False, dro
     dl = _sub(w, "decoder.layer_stack.0.")
     d = _mha(_sub(dl, "slf_attn."), d, d, d, trg_mask, heads("dec_slf_attn", True), rows("dec_slf_fc", True))
     d = _mha(_sub(dl, "enc_attn."), d, e, e, src_mask, heads("dec_enc_attn"), rows("dec_enc_fc"))
-    d = _ffn(_sub(dl, "pos_ffn."), d, rows("dec_ffn"))
+    d = _ffn(_sub(dl, "pos_ffn."), d, rows("dec_ffn"), "dec_ffn")
     out = d.permute(0, 2, 1).contiguous().view(bp, 512, 8, 8)                      # :276-277
     out = F.conv2d(out, w["dec_trans.0.weight"], w["dec_trans.0.bias"])           # :278
     return (out, e) if return_enc else out
@@ -154,20 +170,22 @@ def _bn(w, p, x):
                         training=False, eps=1e-5)
 
 
-def _bottleneck(w, x, stride, has_down):
-    out = F.relu(_bn(w, "bn1.", F.conv2d(x, w["conv1.weight"], stride=stride)))
-    out = F.relu(_bn(w, "bn2.", F.conv2d(out, w["conv2.weight"], padding=1)))
+def _bottleneck(w, x, stride, has_down, tag="l4"):
+    out = _relu(_bn(w, "bn1.", F.conv2d(x, w["conv1.weight"], stride=stride)), tag + ".1")
+    out = _relu(_bn(w, "bn2.", F.conv2d(out, w["conv2.weight"], padding=1)), tag + ".2")
     out = _bn(w, "bn3.", F.conv2d(out, w["conv3.weight"]))
     res = _bn(w, "downsample.1.", F.conv2d(x, w["downsample.0.weight"], stride=stride)) if has_down else x
-    return F.relu(out + res)
+    return _relu(out + res, tag + ".3")
 
 
 def head_to_tail(sd, x, dtype=torch.float32):
     """sd: RCNN_top keys ('0.<block>.<...>').  x [G,1024,8,8] -> [G,2048]."""
     w = _cast(sd, dtype)
     x = x.to(dtype)
+    call = _l4_calls[0]
+    _l4_calls[0] += 1
     for i in range(3):
-        x = _bottleneck(_sub(w, "0.%d." % i), x, 2 if i == 0 else 1, i == 0)
+        x = _bottleneck(_sub(w, "0.%d." % i), x, 2 if i == 0 else 1, i == 0, "l4.%d.%d" % (call, i))
     return x.mean(3).mean(2)
 
 
@@ -184,6 +202,7 @@ def head_forward(sd, non_img, non_qry, rois, dtype=torch.float32, roi_align_fn=N
     """non_img [B,1024,H,W], non_qry [B,1024,8,8], rois [B,P,5] -> dict of outputs + intermediates.
     roi_align_fn: optional replacement for the C oracle (bench.py passes the reference's own CPU kernel)."""
     B, P = rois.shape[0], rois.shape[1]
+    _l4_calls[0] = 0
     pooled = (roi_align_fn or roi_align)(non_img, rois.reshape(-1, 5))                 # :279
     ait, enc = ait_forward(_sub(sd, "transformer."), pooled, non_qry, dtype, True)     # :289
     sp, sq = sknet_forward(_sub(sd, "sk."), ait, non_qry, dtype)                       # :294
