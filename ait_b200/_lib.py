@@ -143,6 +143,8 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp]),
     "aitb_det_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "aitb_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "aitb_group_norm_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp, _vp, _vp]),
+    "aitb_group_norm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "aitb_wgrad_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "aitb_wgrad_conv": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "aitb_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

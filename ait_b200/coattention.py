@@ -5,6 +5,7 @@ in_ch 1024, c_hidden 512, with_residual, 'division' normalisation.  Same paramet
 omega.{0,1}, theta.{0,1}); executed by `aitb_coattention_forward` -- tcgen05 GEMMs for the five 1x1 convolutions
 and the three attention products (the contraction over image positions runs on the MN-major kernel, no
 transposed copy of the map), GroupNorm + residual kernels -- in fp32 storage with tf32 tensor-core math.
+`.train()` with gradients enabled runs the differentiable step of ait_b200/coatt_train.py (own backward).
 """
 import ctypes as C
 
@@ -84,8 +85,10 @@ class CoAttention(nn.Module):
 
     def forward(self, x_img, x_qry):
         """x_img [B,1024,H,W], x_qry [B,1024,8,8] -> (non_img [B,1024,H,W], non_qry [B,1024,8,8])."""
-        if self.training:
-            raise RuntimeError("ait_b200.CoAttention: inference only; call .eval()")
+        if self.training and torch.is_grad_enabled() and (
+                x_img.requires_grad or x_qry.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from . import coatt_train          # differentiable training step (forward keeping activations + own backward)
+            return coatt_train.coattention_train(self, x_img, x_qry)
         lib = L.load()
         ops._need_cuda(x_img, x_qry)
         if x_img.dtype != torch.float32 or x_qry.dtype != torch.float32:

@@ -168,7 +168,7 @@ def _esize(dt):
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
          rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False, ln_rstd=None,
-         passes=0, in_f16=False, out_f16=False, res_f16=False):
+         passes=0, in_f16=False, out_f16=False, res_f16=False, out_scale=0.0, ldo=None):
     """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
     map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels).
     split=True: AITB_F32S -- a / w / out / res are two-plane bf16 matrices (see split_planes); K, lda, ldr
@@ -204,7 +204,7 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.block_n = block_n
     d.flags = flags
     d.out = out.data_ptr()
-    d.ldo = out.shape[-1] // (2 if split else 1)
+    d.ldo = ldo or out.shape[-1] // (2 if split else 1)     # ldo: `out` is a column block of a wider row-major buffer
     d.rows_in = rows_in or M
     d.rows_out = rows_out or M
     d.bias = 0 if bias is None else bias.data_ptr()
@@ -220,6 +220,7 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
     d.bias2 = 0 if bias2 is None else bias2.data_ptr()
     d.ln_rstd = 0 if ln_rstd is None else ln_rstd.data_ptr()
     d.passes, d.in_f16, d.out_f16, d.res_f16 = int(passes), int(bool(in_f16)), int(bool(out_f16)), int(bool(res_f16))
+    d.out_scale = float(out_scale)                # the accumulator is multiplied by it before bias / activation (0 = unset = 1)
     L.check(lib.aitb_gemm(C.byref(d), L.stream_ptr()))
     return out
 

@@ -373,6 +373,17 @@ int aitb_coattention_forward(const aitb_coatt_weights* w, const float* x_img, co
                              float* non_img, float* non_qry, void* workspace, size_t workspace_bytes,
                              aitb_stream_t stream);
 
+/* Training path of the co-attention block (ait_b200/coatt_train.py composes forward and backward from aitb_gemm / aitb_wgrad /
+ * aitb_transpose_cs and these two): GroupNorm(groups, 1024) (+ identity) on token-major [B, N, 1024]
+ * fp32, forward keeping the per-(image, group) (sum, sum of squares) in `sums` [B, groups, 2] doubles, and its backward:
+ * dx [B, N, 1024] (rounded to tf32 when round_tf32), dgamma / dbeta [1024] ACCUMULATED; bsums: [B, groups, 2] doubles scratch.
+ * Reference: nn.GroupNorm inside `theta` / `omega` (blocks_coatt_transformer_sk.py:31-42) + torch autograd. */
+int aitb_group_norm_forward(const float* x, const float* identity, const float* gamma, const float* beta, int B, int N,
+                            int groups, float eps, double* sums, float* out, aitb_stream_t stream);
+int aitb_group_norm_backward(const float* dy, const float* x, const double* sums, const float* gamma, int B, int N,
+                             int groups, float eps, int round_tf32, double* bsums, float* dx, float* dgamma, float* dbeta,
+                             aitb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * f2  detection post-processing (test_net_voc.py:380-446)
  *   aitb_box_decode: pred = clip(bbox_transform_inv(box, delta * h_stds + h_means)) [/ im_scale];

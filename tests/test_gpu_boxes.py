@@ -153,6 +153,46 @@ def test_coattention_matches_oracle_and_golden(B, H, W):
     assert torch.equal(a.cpu(), x_img) and torch.equal(b.cpu(), x_qry)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 19, 31), (1, 38, 63)])
+def test_coattention_training_step_matches_oracle_autograd(B, H, W):
+    """row f3, training: `CoAttention.train()` forward + backward on the device (ait_b200/coatt_train.py: tcgen05 dgrad / wgrad
+    GEMMs, GroupNorm backward kernel) against fp64 autograd over the oracle restatement of
+    blocks_coatt_transformer_sk.py:60-122 -- both outputs, both input gradients and all 14 parameter gradients, tf32
+    tensor-core math: 3e-3 relative L2, measured <= 8e-4 (the non-local branch is smooth: no ReLU, no mask flips)."""
+    from test_oracle_pins import _coatt_inputs
+    from ait_b200.coattention import CoAttention
+    x_img, x_qry, sd = _coatt_inputs(29, B=B, H=H, W=W)
+    g = torch.Generator().manual_seed(3)
+    g_img, g_qry = torch.randn(x_img.shape, generator=g), torch.randn(x_qry.shape, generator=g)
+    sd64 = {k: v.double().requires_grad_() for k, v in sd.items()}
+    xi64, xq64 = x_img.double().requires_grad_(), x_qry.double().requires_grad_()
+    ri, rq = head_oracle.coattention_forward(sd64, xi64, xq64, dtype=torch.float64)
+    torch.autograd.backward([ri, rq], [g_img.double(), g_qry.double()])
+    m = CoAttention(in_ch=1024, c_hidden=512, with_residual=True, normlization="division")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    xi, xq = x_img.to(DEV).requires_grad_(), x_qry.to(DEV).requires_grad_()
+    oi, oq = m(xi, xq)
+    torch.autograd.backward([oi, oq], [g_img.to(DEV), g_qry.to(DEV)])
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.detach().double().cpu() - b).norm() / b.norm())
+
+    # outputs: the non-local term on its own scale (the identity dominates the sum)
+    assert rel(oi.detach().cpu().double() - x_img.double(), ri.detach() - x_img.double()) < 2e-3
+    assert rel(oq.detach().cpu().double() - x_qry.double(), rq.detach() - x_qry.double()) < 2e-3
+    errs = {"x_img": rel(xi.grad - g_img.to(DEV), xi64.grad - g_img.double()),      # gradients minus the identity path
+            "x_qry": rel(xq.grad - g_qry.to(DEV), xq64.grad - g_qry.double())}
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        errs[name] = rel(prm.grad, sd64[name].grad)
+    print("co-attention train errs", {k: "%.1e" % v for k, v in errs.items()})
+    assert len(errs) == 16 and max(errs.values()) < 3e-3, errs          # measured <= 8e-4
+    with pytest.raises(RuntimeError, match="second time"):
+        torch.autograd.backward([oi, oq], [g_img.to(DEV), g_qry.to(DEV)])
+
+
 def test_detector_tail_end_to_end():
     """co-attention -> RPN -> proposal layer -> head -> detections as one module: every stage equals the stage-wise
     oracle when that oracle is fed OUR upstream tensors (stage parity is tested above; this checks the plumbing)."""
