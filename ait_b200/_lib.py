@@ -178,6 +178,7 @@ SIGNATURES = {
     "aitb_im2col3x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "aitb_map_subsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "aitb_map_upsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "aitb_map_pad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "aitb_im2col3x3_grouped": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "aitb_sk_combine": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "aitb_sk_combine_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),

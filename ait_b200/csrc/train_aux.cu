@@ -99,6 +99,23 @@ map_resample_kernel(const float* __restrict__ x, int S, int s, int stride, int C
 
 using namespace aitb;
 
+// channels-last map [B, H, W, C] -> zero-bordered copy [B, H + 2, W + 2, C] (one CTA per destination position): the 3x3 weight
+// gradient on an arbitrary H x W map then is nine plain row-contraction GEMMs on row-shifted views of the padded copies
+// (ait_b200/rpn_train.py)
+__global__ void __launch_bounds__(256)
+map_pad_kernel(const float* __restrict__ x, int H, int W, int C, float* __restrict__ out) {
+  const int Wp = W + 2, Hp = H + 2;
+  const int pos = blockIdx.x;                     // (b, y', x') of the padded map
+  const int xp = pos % Wp, yp = (pos / Wp) % Hp, b = pos / (Wp * Hp);
+  float4* o = reinterpret_cast<float4*>(out + (size_t)pos * C);
+  if (xp == 0 || xp == Wp - 1 || yp == 0 || yp == Hp - 1) {
+    for (int c = threadIdx.x; c < C / 4; c += 256) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4* s = reinterpret_cast<const float4*>(x + ((size_t)(b * H + yp - 1) * W + xp - 1) * C);
+  for (int c = threadIdx.x; c < C / 4; c += 256) o[c] = __ldg(s + c);
+}
+
 extern "C" {
 
 int aitb_relu_bwd(const float* dy, const float* y, float* out, size_t n, aitb_stream_t stream) {
@@ -156,6 +173,13 @@ int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, fl
   AITB_REQUIRE(x && out && G > 0 && S > 0 && s > 0 && stride > 0 && (s - 1) * stride < S && C % 4 == 0, "aitb_map_upsample: bad arguments");
   map_resample_kernel<<<G * S * S, 256, 0, (cudaStream_t)stream>>>(x, S, s, stride, C, 0, out);
   return check_launch("map_resample_kernel");
+}
+
+int aitb_map_pad(const float* x, int B, int H, int W, int C, float* out, aitb_stream_t stream) {
+  AITB_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "aitb_map_pad: bad arguments");
+  AITB_REQUIRE((long long)B * (H + 2) * (W + 2) < (1ll << 31), "aitb_map_pad: too many positions");
+  map_pad_kernel<<<B * (H + 2) * (W + 2), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, out);
+  return check_launch("map_pad_kernel");
 }
 
 }  // extern "C"

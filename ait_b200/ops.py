@@ -165,12 +165,20 @@ def _esize(dt):
     return 4 if dt == L.AITB_F32 else 2
 
 
+def tiled_rows(H, W, B):
+    """GEMM rows of the "tiled" map view: boxes of bx x by = 128 positions, ceil(H / by) boxes per image."""
+    by = 128 // (64 if W <= 64 else 128)
+    return B * ((H + by - 1) // by) * 128
+
+
 def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, taps=1, group_c=0, flags=0,
          bias=None, res=None, ldr=0, res_div=1, res_rep=1, pos=None, pos_rows=1, gamma=None, beta=None,
          rows_in=None, rows_out=None, round_tf32=False, eps=1e-6, dual=False, bias2=None, split=False, ln_rstd=None,
          passes=0, in_f16=False, out_f16=False, res_f16=False, out_scale=0.0, ldo=None):
-    """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]) or "map" (A is a channels-last map,
-    map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels).
+    """out = epilogue(A W^T).  `view`: "plain" (A is [M, lda]), "map" (A is a channels-last map,
+    map_args = (C, S, s, stride, G): an s x s grid sampled with `stride` from an S x S map of C channels) or "tiled"
+    (A is a channels-last map [B, H, W, C] of any size with W <= 128, map_args = (C, H, W, B), tiled by boxes of 128
+    positions of one image -- the RPN 3x3 convolution; M must be tiled_rows(H, W, B), the output has B*H*W rows).
     split=True: AITB_F32S -- a / w / out / res are two-plane bf16 matrices (see split_planes); K, lda, ldr
     and the map's C are LOGICAL element counts."""
     lib = L.load()
@@ -188,6 +196,17 @@ def gemm(a, w, out, *, M, N, K, block_n, view="plain", lda=None, map_args=None, 
         d.a.box[:] = [128 // cb, 128, 1, 1]
         d.a_m_dim, d.a_m_step = 1, 128
         d.a_lo_off = lda if split else 0
+    elif view == "tiled":
+        Cc, Hm, Wm, Bm = map_args
+        bx = 64 if Wm <= 64 else 128
+        if Wm > 128 or M != tiled_rows(Hm, Wm, Bm):
+            raise RuntimeError("ait_b200.gemm: tiled map view needs W <= 128 and M = tiled_rows(H, W, B)")
+        d.a.dims[:] = [Cc * (2 if split else 1), Wm, Hm, Bm]
+        d.a.strides[:] = [Cc * eb, Wm * Cc * eb, Hm * Wm * Cc * eb]
+        d.a.box[:] = [128 // cb, bx, 128 // bx, 1]
+        d.a_m_dim, d.a_m_step = 2, 1
+        d.a_lo_off = Cc if split else 0
+        d.map_w, d.map_h = Wm, Hm
     else:
         Cc, S, s, stride, G = map_args
         d.a.dims[:] = [Cc * (2 if split else 1), s, s, G]

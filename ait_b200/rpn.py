@@ -3,7 +3,8 @@ RPN_cls_score | RPN_bbox_pred, the bg/fg softmax and the whole proposal layer, e
 (`aitb_rpn_forward`: one tcgen05 conv GEMM over the C4 map with nine shifted TMA boxes per K chunk, one fused
 1x1 GEMM for both heads, one decode kernel) followed by the on-device top-n + NMS.  Same parameter names as
 the reference (RPN_Conv.*, RPN_cls_score.*, RPN_bbox_pred.*), so detector checkpoints load unchanged.
-The training branch (anchor targets + losses, rpn.py:96-140) is row f4 and not built: .train() raises.
+`.train()` runs the training branch of rpn.py:85-140 on the device: the differentiable head of ait_b200/rpn_train.py (own
+backward), the proposal layer with the TRAIN settings, `AnchorTargetLayer` and the two RPN losses (ait_b200/targets.py).
 """
 import ctypes as C
 
@@ -42,6 +43,8 @@ class _RPN(nn.Module):
         self._packed = None
         self.rpn_loss_cls = 0
         self.rpn_loss_box = 0
+        self._anchor_target = None      # built on first use in .train() (ait_b200.targets.AnchorTargetLayer, not a sub-module:
+        #                                 the reference's RPN_anchor_target has no parameters and no state_dict entries either)
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -112,8 +115,32 @@ class _RPN(nn.Module):
     def forward(self, base_feat, im_info, gt_boxes=None, num_boxes=None):
         """-> (rois [B, post_nms_topN, 5], rpn_loss_cls, rpn_loss_box) like rpn.py:110 (losses are 0 in eval)."""
         if self.training:
-            raise RuntimeError("ait_b200._RPN: inference only (anchor targets / losses are not built); call .eval()")
+            return self._forward_train(base_feat, im_info, gt_boxes, num_boxes)
         c = self.cfg["TEST"]
+        self.rpn_loss_cls = 0                    # rpn.py:92-93: reset on every forward
+        self.rpn_loss_box = 0
         props, fg = self.rpn_outputs(base_feat, im_info)
         rois, _ = propose_rois(props, fg, c["pre_nms_topN"], c["post_nms_topN"], c["nms_thresh"])
+        return rois, self.rpn_loss_cls, self.rpn_loss_box
+
+    def _forward_train(self, base_feat, im_info, gt_boxes, num_boxes):
+        """rpn.py:66-140 in .train(): -> (rois [B, TRAIN post_nms_topN, 5], rpn_loss_cls, rpn_loss_box); the losses carry the
+        graph to base_feat and the six RPN parameters (fp32 storage / tf32 tensor-core math)."""
+        from . import rpn_train, targets
+        from .proposal import rpn_decode
+        if gt_boxes is None:
+            raise AssertionError("ait_b200._RPN: gt_boxes is required in .train() (rpn.py:98)")
+        ops._need_cuda(base_feat, im_info, gt_boxes)
+        score, bbox = rpn_train.rpn_head_train(self, base_feat)                  # rpn_cls_score, rpn_bbox_pred (:70-83)
+        B, A2, H, W = score.shape
+        with torch.no_grad():                                                    # the proposal layer sees `.data` (:89-90)
+            prob = torch.softmax(score.view(B, 2, (A2 // 2) * H, W), dim=1).view(B, A2, H, W)     # :75-77
+            props, fg = rpn_decode(prob, bbox.detach(), self._anchors, im_info, self.feat_stride)
+            c = self.cfg["TRAIN"]
+            rois, _ = propose_rois(props, fg, c["pre_nms_topN"], c["post_nms_topN"], c["nms_thresh"])
+            if self._anchor_target is None:
+                self._anchor_target = targets.AnchorTargetLayer(self.feat_stride, self.anchor_scales, self.anchor_ratios).to(
+                    base_feat.device)
+            rpn_data = self._anchor_target((score.detach(), gt_boxes, im_info, num_boxes))          # :100
+        self.rpn_loss_cls, self.rpn_loss_box = targets.rpn_losses(score, bbox, rpn_data)            # :102-126
         return rois, self.rpn_loss_cls, self.rpn_loss_box

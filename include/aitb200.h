@@ -571,6 +571,10 @@ int aitb_relu_bwd(const float* dy, const float* y, float* out, size_t n, aitb_st
 int aitb_im2col3x3(const float* x, int G, int s, int C, float* out, aitb_stream_t stream);
 int aitb_map_subsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
 int aitb_map_upsample(const float* x, int G, int S, int s, int stride, int C, float* out, aitb_stream_t stream);
+/* channels-last map [B, H, W, C] -> zero-bordered copy [B, H+2, W+2, C] (C % 4 == 0): the 3x3 weight gradient on an arbitrary
+ * H x W map (the RPN head's training step, ait_b200/rpn_train.py; rpn.py:18-110 + torch autograd in the reference) is then nine
+ * aitb_wgrad launches on row-shifted views of the padded gradient / input maps. */
+int aitb_map_pad(const float* x, int B, int H, int W, int C, float* out, aitb_stream_t stream);
 
 /* SKNet training path (lib/model/modules/blocks_coatt_transformer_sk.py:960-998; composed with aitb_gemm / aitb_wgrad by
  * ait_b200/sk_train.py; the reference gets the backward from torch autograd):

@@ -1,5 +1,6 @@
 """GPU parity of the rows either side of the head: the whole proposal layer (f1) and the
 detection post-processing (f2), against the CPU oracle and the reference golden."""
+import numpy as np
 import pytest
 import torch
 
@@ -191,6 +192,95 @@ def test_coattention_training_step_matches_oracle_autograd(B, H, W):
     assert len(errs) == 16 and max(errs.values()) < 3e-3, errs          # measured <= 8e-4
     with pytest.raises(RuntimeError, match="second time"):
         torch.autograd.backward([oi, oq], [g_img.to(DEV), g_qry.to(DEV)])
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 19, 31), (1, 38, 63)])
+def test_rpn_head_training_step_matches_oracle_autograd(B, H, W):
+    """row f3, training: the differentiable RPN head (ait_b200/rpn_train.py: 3x3 conv GEMM over the H x W map, stacked 1x1
+    heads; backward = flipped-tap conv GEMM, nine row-shifted MN-major wgrads on zero-bordered maps, ReLU mask in the dgrad
+    epilogue) against fp64 autograd over rpn.py:66-83 as restated by the oracle.  First with the plain ReLU (a tf32 forward
+    flips the mask of pre-activations within rounding of zero: gate 5e-2), then with the DEVICE's ReLU decisions injected
+    into the fp64 graph: every gradient 2e-3 relative L2 (measured 4e-4)."""
+    import torch.nn.functional as F
+    from test_oracle_pins import _rpn_inputs
+    from ait_b200 import rpn_train
+    from ait_b200.rpn import _RPN
+    base_feat, _, sd = _rpn_inputs(23, B=B, H=H, W=W)
+    g = torch.Generator().manual_seed(9)
+    g_s, g_b = torch.randn(B, 18, H, W, generator=g), torch.randn(B, 36, H, W, generator=g)
+    m = _RPN(1024)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    x = base_feat.to(DEV).requires_grad_()
+    score, bbox = rpn_train.rpn_head_train(m, x)
+    torch.autograd.backward([score, bbox], [g_s.to(DEV), g_b.to(DEV)])
+    torch.cuda.synchronize()
+    mask = (rpn_train._last_conv1_for_tests > 0).double().cpu().view(B, H, W, 512).permute(0, 3, 1, 2)
+
+    def ref(with_mask):
+        w = {k: v.double().requires_grad_() for k, v in sd.items()}
+        x64 = base_feat.double().requires_grad_()
+        pre = F.conv2d(x64, w["RPN_Conv.weight"], w["RPN_Conv.bias"], padding=1)
+        c1 = pre * mask if with_mask else F.relu(pre)
+        s64 = F.conv2d(c1, w["RPN_cls_score.weight"], w["RPN_cls_score.bias"])
+        b64 = F.conv2d(c1, w["RPN_bbox_pred.weight"], w["RPN_bbox_pred.bias"])
+        torch.autograd.backward([s64, b64], [g_s.double(), g_b.double()])
+        return s64.detach(), b64.detach(), x64.grad, {k: v.grad for k, v in w.items()}
+
+    def rel(a, b):
+        return float((a.detach().double().cpu() - b).norm() / b.norm())
+
+    for with_mask, gate in ((False, 5e-2), (True, 2e-3)):       # measured 1.8e-2 / 4.3e-4
+        s64, b64, gx, gw = ref(with_mask)
+        assert rel(score, s64) < 2e-3 and rel(bbox, b64) < 2e-3
+        errs = {"base_feat": rel(x.grad, gx)}
+        for name, prm in m.named_parameters():
+            assert prm.grad is not None, name
+            errs[name] = rel(prm.grad, gw[name])
+        print("rpn head train errs (device masks: %s)" % with_mask, {k: "%.1e" % v for k, v in errs.items()})
+        assert len(errs) == 7 and max(errs.values()) < gate, errs
+
+
+def test_rpn_module_training_forward_and_losses():
+    """`_RPN.train()(base_feat, im_info, gt_boxes, num_boxes)` like rpn.py:66-140: rois from the proposal layer with the TRAIN
+    settings, rpn_loss_cls / rpn_loss_box equal to the oracle's losses on the same scores and anchor targets, and a backward
+    that reaches base_feat and all six parameters."""
+    from test_oracle_pins import _rpn_inputs
+    from ait_b200.rpn import _RPN
+    from oracle import target_oracle
+    B, H, W = 2, 19, 31
+    base_feat, im_info, sd = _rpn_inputs(23, B=B, H=H, W=W)
+    gt = torch.zeros(B, 4, 5)
+    gt[0, 0] = torch.tensor([40.0, 30.0, 200.0, 180.0, 1.0])
+    gt[0, 1] = torch.tensor([250.0, 100.0, 420.0, 260.0, 1.0])
+    gt[1, 0] = torch.tensor([60.0, 50.0, 300.0, 220.0, 1.0])
+    nb = torch.tensor([2, 1])
+    cfg = {"TEST": dict(pre_nms_topN=6000, post_nms_topN=300, nms_thresh=0.7),
+           "TRAIN": dict(pre_nms_topN=3000, post_nms_topN=128, nms_thresh=0.7)}
+    m = _RPN(1024, cfg=cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    x = base_feat.to(DEV).requires_grad_()
+    np.random.seed(4)
+    rois, l_cls, l_box = m(x, im_info.to(DEV), gt.to(DEV), nb.to(DEV))
+    assert rois.shape == (B, 128, 5) and bool(torch.isfinite(rois).all())
+    (l_cls + l_box).backward()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().max()) > 0
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None and bool(torch.isfinite(prm.grad).all()) and float(prm.grad.abs().max()) > 0, name
+    # the same losses from the oracle's formulas on the device's scores and anchor targets
+    from ait_b200 import rpn_train
+    with torch.no_grad():
+        score, bbox = rpn_train.rpn_head_train(m, base_feat.to(DEV))
+        np.random.seed(4)
+        data = m._anchor_target((score, gt.to(DEV), im_info.to(DEV), nb.to(DEV)))
+    r_cls, r_box = target_oracle.rpn_losses(score.cpu().double(), bbox.cpu().double(), *[d.cpu().double() for d in data])
+    assert abs(float(l_cls.detach()) - float(r_cls)) < 1e-4 * max(1.0, abs(float(r_cls)))
+    assert abs(float(l_box.detach()) - float(r_box)) < 1e-4 * max(1.0, abs(float(r_box)))
+    # .eval() is still the inference path
+    rois_e, a, b = m.eval()(base_feat.to(DEV), im_info.to(DEV))
+    assert rois_e.shape == (B, 300, 5) and (a, b) == (0, 0)
 
 
 def test_detector_tail_end_to_end():
