@@ -320,7 +320,13 @@ template <bool SPLIT> struct OnePass {
   static constexpr int kPlanes = SPLIT ? 6 : 3;
   static constexpr int kBufBytes = kPlanes * kPlaneBytes;
   // 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
-  static constexpr int kSmem = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
+  static constexpr int kMisc = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
+  // plain bf16 configuration: a bf16 copy of W_sk [512, 64] stays resident in shared memory for the CTA's lifetime (64 KB,
+  // 16-byte chunks XOR-swizzled by row).  ncu (profiles/r02n_attn_*): the per-pair gate matvec W_sk s read its 128 KB of
+  // fp32 weights row-per-thread from L2 for every pair (22 sectors per request, 43 % L1 hits) and cost 30 % of the kernel in
+  // long-scoreboard stalls.  The split configuration has no room for it (212 KB of operand planes) and keeps the global path.
+  static constexpr int kWskOff = (kMisc + 127) & ~127;
+  static constexpr int kSmem = SPLIT ? kMisc : kWskOff + kH * kD * kD * 2;
 };
 
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {  // byte offset of 16-byte chunk `chunk` of row `row`
@@ -388,6 +394,21 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   };
 
   if ((int)blockIdx.x < G) issue_head(blockIdx.x, hg * 4, 0);
+  if constexpr (!SPLIT) {   // resident bf16 copy of W_sk: row o = 128 bytes, chunk j (8 inputs) at ((j ^ (o & 7)) << 4)
+    uint8_t* wsm = smem_attn + OnePass<SPLIT>::kWskOff;
+    for (int i = tid; i < kH * kD * kD / 8; i += kSplitThreads) {
+      const int o = i >> 3, j = i & 7;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w_sk + (size_t)o * kD + j * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(w_sk + (size_t)o * kD + j * 8 + 4));
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      uint4 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&p0); v.y = *reinterpret_cast<const uint32_t*>(&p1);
+      v.z = *reinterpret_cast<const uint32_t*>(&p2); v.w = *reinterpret_cast<const uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(wsm + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+    }
+    // visible to every thread before the first gate: the pair loop below passes several __syncthreads first
+  }
 #pragma unroll 1
   for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
   float o[4][8][4];
@@ -518,6 +539,28 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   }
   __syncthreads();
   // ---------------- gate = softmax_h(W_sk s + b_sk)
+  if constexpr (!SPLIT) {   // from the resident bf16 copy: conflict-free LDS.128 (a quarter-warp reads 8 rows, 8 distinct chunks)
+    const uint8_t* wsm = smem_attn + OnePass<SPLIT>::kWskOff;
+    float acc0 = 0.f, acc1 = 0.f;
+    const int o0 = tid, o1 = tid + kSplitThreads;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 sa = *reinterpret_cast<const float4*>(svec + j * 8), sb = *reinterpret_cast<const float4*>(svec + j * 8 + 4);
+      const uint4 w0 = *reinterpret_cast<const uint4*>(wsm + o0 * 128 + ((j ^ (o0 & 7)) << 4));
+      const uint4 w1 = *reinterpret_cast<const uint4*>(wsm + o1 * 128 + ((j ^ (o1 & 7)) << 4));
+      auto dot8 = [&](const uint4& w) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.z));
+        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.w));
+        return a.x * sa.x + a.y * sa.y + b.x * sa.z + b.y * sa.w + c.x * sb.x + c.y * sb.y + d.x * sb.z + d.y * sb.w;
+      };
+      acc0 += dot8(w0);
+      acc1 += dot8(w1);
+    }
+    gate[o0] = acc0 * (1.f / kT) + __ldg(b_sk + o0);
+    gate[o1] = acc1 * (1.f / kT) + __ldg(b_sk + o1);
+  } else {
   for (int oi = tid; oi < kH * kD; oi += kSplitThreads) {
     const float* wr = w_sk + (size_t)oi * kD;
     float acc = 0.f;
@@ -527,6 +570,7 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
     }
     gate[oi] = acc * (1.f / kT) + __ldg(b_sk + oi);
+  }
   }
   __syncthreads();
   if (tid < kD) {
