@@ -320,11 +320,14 @@ template <bool SPLIT> struct OnePass {
   static constexpr int kPlanes = SPLIT ? 6 : 3;
   static constexpr int kBufBytes = kPlanes * kPlaneBytes;
   // 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
-  static constexpr int kMisc = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4;
+  static constexpr int kMisc = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4 + 16 /* TMEM base holder */;
   // plain bf16 configuration: a bf16 copy of W_sk [512, 64] stays resident in shared memory for the CTA's lifetime (64 KB,
   // 16-byte chunks XOR-swizzled by row).  ncu (profiles/r02n_attn_*): the per-pair gate matvec W_sk s read its 128 KB of
   // fp32 weights row-per-thread from L2 for every pair (22 sectors per request, 43 % L1 hits) and cost 30 % of the kernel in
-  // long-scoreboard stalls.  The split configuration has no room for it (212 KB of operand planes) and keeps the global path.
+  // long-scoreboard stalls.  The split configuration has no shared memory left for it (212 KB of operand planes): there the
+  // exact fp32 W_sk lives in TENSOR MEMORY -- 256 of the SM's 512 TMEM columns, otherwise idle in this mma.sync kernel --
+  // written once per CTA with tcgen05.st and read back per pair with tcgen05.ld (output o = block * 128 + lane: TMEM lane
+  // o % 128, columns 64 * (o / 128) .. + 63).
   static constexpr int kWskOff = (kMisc + 127) & ~127;
   static constexpr int kSmem = SPLIT ? kMisc : kWskOff + kH * kD * kD * 2;
 };
@@ -364,6 +367,7 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   float* colsum = part + kT * kPartStride;                            // [8 warps][kD]
   float* svec = colsum + 8 * kD;                                      // [kD]
   float* gate = svec + kD;                                            // [kH][kD]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(gate + kH * kD);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int hg = warp >> 2, rb = warp & 3, gt = tid & 127;  // head group, row block, thread index inside the group
@@ -408,6 +412,36 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       *reinterpret_cast<uint4*>(wsm + o * 128 + ((j ^ (o & 7)) << 4)) = v;
     }
     // visible to every thread before the first gate: the pair loop below passes several __syncthreads first
+  }
+  // split configuration: W_sk (fp32, exact) -> tensor memory.  Warp w owns TMEM lanes 32 (w & 3) .. + 31 (the only lanes a
+  // warp may access) and the column blocks 2 (w >> 2), 2 (w >> 2) + 1; thread = one lane = outputs o = block * 128 + lane.
+  uint32_t tmem_w = 0;
+  if constexpr (SPLIT) {
+    if (warp == 0) {
+      tmem_alloc(tmem_holder, 256);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_w = *tmem_holder + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int bi = 0; bi < 2; ++bi) {
+      const int blk = 2 * (warp >> 2) + bi, o = blk * 128 + (warp & 3) * 32 + lane;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_sk + (size_t)o * kD + half * 32 + j * 4));
+          v[4 * j] = __float_as_uint(w4.x); v[4 * j + 1] = __float_as_uint(w4.y);
+          v[4 * j + 2] = __float_as_uint(w4.z); v[4 * j + 3] = __float_as_uint(w4.w);
+        }
+        tmem_st32(tmem_w + blk * 64 + half * 32, v);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();   // ordered before the first tcgen05.ld by the __syncthreads chain of the pair loop
   }
 #pragma unroll 1
   for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
@@ -560,17 +594,27 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
     }
     gate[o0] = acc0 * (1.f / kT) + __ldg(b_sk + o0);
     gate[o1] = acc1 * (1.f / kT) + __ldg(b_sk + o1);
-  } else {
-  for (int oi = tid; oi < kH * kD; oi += kSplitThreads) {
-    const float* wr = w_sk + (size_t)oi * kD;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < kD; c += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
-      acc += w4.x * svec[c] + w4.y * svec[c + 1] + w4.z * svec[c + 2] + w4.w * svec[c + 3];
+  } else {   // from tensor memory: two outputs per thread, 64 fp32 weights each, 32 columns per tcgen05.ld
+    tc_fence_after();
+#pragma unroll 1
+    for (int bi = 0; bi < 2; ++bi) {
+      const int blk = 2 * (warp >> 2) + bi, o = blk * 128 + (warp & 3) * 32 + lane;
+      float acc = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_w + blk * 64 + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(svec + half * 32 + j * 4);   // broadcast
+          acc += __uint_as_float(v[4 * j]) * s4.x + __uint_as_float(v[4 * j + 1]) * s4.y +
+                 __uint_as_float(v[4 * j + 2]) * s4.z + __uint_as_float(v[4 * j + 3]) * s4.w;
+        }
+      }
+      gate[o] = acc * (1.f / kT) + __ldg(b_sk + o);
     }
-    gate[oi] = acc * (1.f / kT) + __ldg(b_sk + oi);
-  }
+    tc_fence_before();
   }
   __syncthreads();
   if (tid < kD) {
@@ -627,6 +671,14 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   }
   // the next pair's gate / exchange writes are ordered after these reads by its own __syncthreads chain
   }  // persistent loop over pairs
+  if constexpr (SPLIT) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      tmem_dealloc(*tmem_holder, 256);
+    }
+  }
 }
 
 int attn_tc_run(const void* q, int ldq, int q_rep, const void* k, const void* v, int ldkv, const float* w_sk,
