@@ -338,19 +338,18 @@ static void carve(Bump& b, HeadBufs& hb, int B, int P, int HW, int dtype, bool w
   hb.DEC = b.take(R * 512 * eb);
   hb.AIT = b.take(R * 1024 * eb);
   if (with_top) {
-    const size_t R16 = bp * 16, RQ16 = (size_t)B * 16;
-    hb.SK = b.take(R * 1024 * eb);
+    // RCNN_top has ONE set of weights for the proposal maps and the query maps (`_head_to_tail` is called on both,
+    // faster_rcnn_coatt_transformer_sk.py:299-300): the B query maps sit right behind the bp proposal maps in the SKNet output
+    // buffer and layer 4 runs once over bp + B maps -- the query side costs one extra 128-row tile instead of eleven tiny
+    // single-tile launches on the side stream (which delayed the persistent main-stream kernels they had to squeeze between)
+    const size_t R16 = (bp + B) * 16;
+    hb.SK = b.take((R + RQ) * 1024 * eb);
+    hb.SKq = (uint8_t*)hb.SK + R * 1024 * eb;
     hb.c1 = b.take(R16 * 512 * eb);
     hb.c2 = b.take(R16 * 512 * eb);
     hb.ds = b.take(R16 * 2048 * eb);
     hb.y0 = b.take(R16 * 2048 * eb);
     hb.y1 = b.take(R16 * 2048 * eb);
-    hb.SKq = b.take(RQ * 1024 * eb);
-    hb.qc1 = b.take(RQ16 * 512 * eb);
-    hb.qc2 = b.take(RQ16 * 512 * eb);
-    hb.qds = b.take(RQ16 * 2048 * eb);
-    hb.qy0 = b.take(RQ16 * 2048 * eb);
-    hb.qy1 = b.take(RQ16 * 2048 * eb);
     hb.feat = (float*)b.take(bp * 2048 * 4);
     hb.qfeat = (float*)b.take((size_t)B * 2048 * 4);
   }
@@ -1416,7 +1415,7 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
     cudaError_t e = cudaMemcpyAsync(taps->pooled, hb.pooled, (size_t)bp * 49 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "pooled tap copy failed: %s", cudaGetErrorString(e));
   }
-  // query branch on the side stream: decoder self-attention block, SKNet(query), RCNN_top(query), pooling
+  // query branch on the side stream: decoder self-attention block, SKNet(query) (RCNN_top(query) rides in the proposal launches)
   SideStream* ss = nullptr;
   RUN(side_stream(&ss));
   float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
@@ -1428,10 +1427,6 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
     RUN(ait_query_side(w, hb, B, ss->stream));
     cudaEventRecord(ss->q1, ss->stream);
     RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, ss->stream));
-    void* yq = nullptr;
-    RUN(layer4(w, hb.SKq, B, hb.qc1, hb.qc2, hb.qds, hb.qy0, hb.qy1, &yq, ss->stream));
-    RUN(pool_heads_run(yq, dt, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, qfeat, nullptr,
-                       nullptr, ss->stream));
     cudaEventRecord(ss->q2, ss->stream);
   }
   // a5-a9: AIT
@@ -1446,14 +1441,16 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
     cudaError_t e = cudaMemcpyAsync(taps->sk_out, hb.SK, (size_t)bp * 64 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "sk tap copy failed: %s", cudaGetErrorString(e));
   }
-  // a11: RCNN_top, proposal branch
-  void* ytop = nullptr;
-  RUN(layer4(w, hb.SK, bp, hb.c1, hb.c2, hb.ds, hb.y0, hb.y1, &ytop, st));
-  // a12: spatial mean + bbox / similarity heads (join the query branch first)
+  // a11: RCNN_top over the bp proposal maps and the B query maps in one set of launches (join the query branch first)
   {
     cudaError_t e = cudaStreamWaitEvent(st, ss->q2, 0);
     AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
   }
+  void* ytop = nullptr;
+  RUN(layer4(w, hb.SK, bp + B, hb.c1, hb.c2, hb.ds, hb.y0, hb.y1, &ytop, st));
+  // a12: spatial mean of the query maps, then spatial mean + bbox / similarity heads of the pairs
+  RUN(pool_heads_run((const uint8_t*)ytop + (size_t)bp * 16 * 2048 * eb, dt, B, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, qfeat, nullptr, nullptr, st));
   RUN(pool_heads_run(ytop, dt, bp, P, qfeat, w->w_bbox, w->b_bbox, w->w_cls1, w->b_cls1, w->w_cls2, w->b_cls2,
                      taps ? taps->feat : nullptr, bbox_pred, cls_prob, st));
   return 0;
