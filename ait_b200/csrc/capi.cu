@@ -1401,6 +1401,26 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
   HeadBufs hb;
   carve(b, hb, B, P, 64 * 64, dt, true, true);
 
+  // query branch on the side stream: decoder self-attention block, SKNet(query) (RCNN_top(query) rides in the proposal launches).
+  // Forked BEFORE the map transpose / ROIAlign: those kernels use no shared memory, so the query side's small GEMM CTAs find room
+  // next to them instead of squeezing between the persistent full-shared-memory GEMMs of the encoder
+  RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
+  SideStream* ss = nullptr;
+  RUN(side_stream(&ss));
+  float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
+  auto fork_query = [&]() -> int {
+    cudaError_t e = cudaEventRecord(ss->fork, st);
+    AITB_REQUIRE(e == cudaSuccess, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+    AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+    RUN(ait_query_side(w, hb, B, ss->stream));
+    cudaEventRecord(ss->q1, ss->stream);
+    RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, ss->stream));
+    cudaEventRecord(ss->q2, ss->stream);
+    return 0;
+  };
+  static const bool fork_late = getenv("AITB_QUERY_FORK_LATE") != nullptr;   // A/B switch: fork after ROIAlign (round-1 order)
+  if (!fork_late) RUN(fork_query());
   // a3: ROIAlign from a channels-last copy of the map, token-major output feeding enc_emb
   // exact copy (fp32 in the F32 and F32S configurations): ROIAlign parity
   RUN(transpose_run(feat_nchw, AITB_F32, hb.featT, dt == AITB_BF16 ? AITB_BF16 : AITB_F32, B, 1024, H * W, 1, st));
@@ -1410,25 +1430,11 @@ int aitb_head_forward(const aitb_head_weights* w, const float* feat_nchw, int H,
                           (uint8_t*)hb.pooled + (size_t)k0 * 49 * 1024 * eb, st, taps && taps->pooled ? 0 : w->round_tf32,
                           (dt == AITB_F32S && (w->plan & AITB_PLAN_ENC_ONEPASS)) ? 1 : 0));
   }
-  RUN(transpose_run(query_nchw, AITB_F32, hb.qtok, dt, B, 1024, 64, 1, st, w->round_tf32));
   if (taps && taps->pooled) {
     cudaError_t e = cudaMemcpyAsync(taps->pooled, hb.pooled, (size_t)bp * 49 * 1024 * eb, cudaMemcpyDeviceToDevice, st);
     AITB_REQUIRE(e == cudaSuccess, "pooled tap copy failed: %s", cudaGetErrorString(e));
   }
-  // query branch on the side stream: decoder self-attention block, SKNet(query) (RCNN_top(query) rides in the proposal launches)
-  SideStream* ss = nullptr;
-  RUN(side_stream(&ss));
-  float* qfeat = (taps && taps->qfeat) ? taps->qfeat : hb.qfeat;
-  {
-    cudaError_t e = cudaEventRecord(ss->fork, st);
-    AITB_REQUIRE(e == cudaSuccess, "cudaEventRecord failed: %s", cudaGetErrorString(e));
-    e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
-    AITB_REQUIRE(e == cudaSuccess, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
-    RUN(ait_query_side(w, hb, B, ss->stream));
-    cudaEventRecord(ss->q1, ss->stream);
-    RUN(sk_block(w, w->sk_query, hb.qtok, B, hb.SKq, ss->stream));
-    cudaEventRecord(ss->q2, ss->stream);
-  }
+  if (fork_late) RUN(fork_query());
   // a5-a9: AIT
   RUN(ait_core(w, hb, B, P, taps ? taps->enc_out : nullptr, st, ss->q1));
   if (taps && taps->ait_out) {
