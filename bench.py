@@ -698,6 +698,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         ref_cls = step()
         dt = time.perf_counter() - t0
+        torch.set_num_threads(1)     # release the host thread pool: its spinning workers slow the launch-bound legs that follow
         cpu_baseline = {"value": 2 * P / dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": kind,
                         "sample": "2 units x %d proposals, one pass after one warm-up (top-%d NMS + head); %s"
                                   % (P, PRE_NMS, what)}
