@@ -182,3 +182,41 @@ def test_training_weight_repacking_host_logic():
     w1t, w3t = sk_train.dgrad_weights(tap_major(w1), tap_major(w3))
     got = F.conv2d(g1, unpack(w1t, 1024, 128, 1), groups=8) + F.conv2d(g3, unpack(w3t, 1024, 128, 3), padding=1, groups=8)
     assert torch.allclose(got, x.grad, rtol=1e-10, atol=1e-10)
+
+
+def test_training_dropout_host_logic():
+    """Host side of the training-mode dropout (no GPU): the reference's semantics -- p = `dropout` at the nn.Dropout sites,
+    0.1 on the attention probabilities whatever the constructor says (Modules.py:9-14) --, `set_dropout`, the per-step seed
+    drawn from torch's CPU generator (reproducible under torch.manual_seed, 0 when dropout is off), and the seeded mask
+    helper of the oracle (Bernoulli(1 - p) multipliers, per-unit decoder-side sites)."""
+    import torch
+    from ait_b200.system.Models import Transformer, set_dropout
+    from oracle import drop_masks
+    t = Transformer(n_layers=1, dropout=0.3, n_position=64)
+    assert {m.p_dropout for m in t.modules() if hasattr(m, "p_dropout")} == {0.3}
+    assert {m.p_attn_dropout for m in t.modules() if hasattr(m, "p_attn_dropout")} == {0.1}
+    torch.manual_seed(11)
+    p, pa, s1 = t._draw_dropout()
+    torch.manual_seed(11)
+    assert t._draw_dropout() == (p, pa, s1) and (p, pa) == (0.3, 0.1) and s1 != 0 and t.last_dropout_seed == s1
+    assert t._draw_dropout()[2] != s1
+    set_dropout(t, 0.0, 0.0)
+    assert t._draw_dropout() == (0.0, 0.0, 0)
+    assert Transformer(n_layers=1, dropout=0.0, n_position=64, attn_dropout=0.0)._draw_dropout() == (0.0, 0.0, 0)
+    t.encoder.layer_stack[0].pos_ffn.p_dropout = 0.5            # the engine has one probability per kind
+    with pytest.raises(RuntimeError):
+        t._draw_dropout()
+    m = drop_masks.make_masks(5, 2, 3, 0.2, 0.1)
+    assert set(m) == set(drop_masks.ROW_SITES) | set(drop_masks.ATTN_SITES)
+    assert m["enc_ffn"].shape == (6 * 64, 512) and m["dec_emb"].shape == (2 * 64, 512)        # per pair / per unit
+    assert m["enc_slf_attn"].shape == (6, 8, 64, 64) and m["dec_slf_attn"].shape == (2, 8, 64, 64)
+    keep = m["enc_ffn"] > 0
+    assert abs(float(keep.float().mean()) - 0.8) < 0.01 and torch.allclose(m["enc_ffn"][keep], torch.tensor(1.25))
+
+
+def test_tiled_map_view_rows():
+    """`ops.tiled_rows`: GEMM rows of the tiled H x W map view of the RPN 3x3 convolution (boxes of 128 positions)."""
+    from ait_b200 import ops
+    assert ops.tiled_rows(38, 63, 8) == 8 * 19 * 128        # 64 x 2 boxes, 19 per image
+    assert ops.tiled_rows(19, 31, 2) == 2 * 10 * 128
+    assert ops.tiled_rows(50, 100, 1) == 50 * 128           # wide maps: 128 x 1 boxes
