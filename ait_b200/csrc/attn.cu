@@ -320,7 +320,8 @@ template <bool SPLIT> struct OnePass {
   static constexpr int kPlanes = SPLIT ? 6 : 3;
   static constexpr int kBufBytes = kPlanes * kPlaneBytes;
   // 2 groups x 2 buffers + exchange tile + per-warp column sums + s + gate
-  static constexpr int kMisc = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4 + 16 /* TMEM base holder */;
+  static constexpr int kMisc = 4 * kBufBytes + (kT * kPartStride + 8 * kD + kD + kH * kD) * 4 + 16 /* TMEM base holder */ +
+                               kH * kD * 4 /* b_sk */;
   // plain bf16 configuration: a bf16 copy of W_sk [512, 64] stays resident in shared memory for the CTA's lifetime (64 KB,
   // 16-byte chunks XOR-swizzled by row).  ncu (profiles/r02n_attn_*): the per-pair gate matvec W_sk s read its 128 KB of
   // fp32 weights row-per-thread from L2 for every pair (22 sectors per request, 43 % L1 hits) and cost 30 % of the kernel in
@@ -368,6 +369,7 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   float* svec = colsum + 8 * kD;                                      // [kD]
   float* gate = svec + kD;                                            // [kH][kD]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(gate + kH * kD);
+  float* s_bsk = reinterpret_cast<float*>(tmem_holder + 4);           // [kH * kD]: the gate bias, read per pair
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int hg = warp >> 2, rb = warp & 3, gt = tid & 127;  // head group, row block, thread index inside the group
@@ -398,6 +400,7 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
   };
 
   if ((int)blockIdx.x < G) issue_head(blockIdx.x, hg * 4, 0);
+  for (int i = tid; i < kH * kD; i += kSplitThreads) s_bsk[i] = __ldg(b_sk + i);   // visible after the pair loop's first barriers
   if constexpr (!SPLIT) {   // resident bf16 copy of W_sk: row o = 128 bytes, chunk j (8 inputs) at ((j ^ (o & 7)) << 4)
     uint8_t* wsm = smem_attn + OnePass<SPLIT>::kWskOff;
     for (int i = tid; i < kH * kD * kD / 8; i += kSplitThreads) {
@@ -592,8 +595,8 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
       acc0 += dot8(w0);
       acc1 += dot8(w1);
     }
-    gate[o0] = acc0 * (1.f / kT) + __ldg(b_sk + o0);
-    gate[o1] = acc1 * (1.f / kT) + __ldg(b_sk + o1);
+    gate[o0] = acc0 * (1.f / kT) + s_bsk[o0];
+    gate[o1] = acc1 * (1.f / kT) + s_bsk[o1];
   } else {   // from tensor memory: two outputs per thread, 64 fp32 weights each, 32 columns per tcgen05.ld
     tc_fence_after();
 #pragma unroll 1
@@ -612,7 +615,7 @@ attn_core_split_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int q_lo, i
                  __uint_as_float(v[4 * j + 2]) * s4.z + __uint_as_float(v[4 * j + 3]) * s4.w;
         }
       }
-      gate[o] = acc * (1.f / kT) + __ldg(b_sk + o);
+      gate[o] = acc * (1.f / kT) + s_bsk[o];
     }
     tc_fence_before();
   }

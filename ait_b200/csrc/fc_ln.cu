@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/aitb200.h"
 #include "common.cuh"
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_ln_kernel(const FcLnParams p
     {
       const int nb = blk + gridDim.x;
       if (nb < n_blk) stage_a(nb, (it + 1) & 1);
+      // (tried in round 2: prefetch.global.L2 of the next block's residual rows by the t == 0 lanes -- measured 3.5 % SLOWER,
+      //  177 vs 171 us: the kernel is bandwidth-, not latency-limited on those loads; dropped)
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
